@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of the /retrieve dense lane (BASELINE.json configs[1]):
+1M x 1024 fp32 corpus, single-query exact cosine scan + top-k=50 (HBM-bound GEMV), on N B200s.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # the reference's CPU path (pgvector restated) timed alone
+
+A "step" is one batch of Q distinct single-query scans (Q = --queries-per-step, default 64) over
+the resident corpus: every query reads every row once (no cross-query reuse: the corpus is far
+larger than L2), keeps its top-(k+14) in the scan kernel, is re-scored in fp64 and ordered.  With
+N > 1 the 1M-row corpus is row-sharded (strong scaling: total work fixed), each rank scans its
+shard, and the per-rank top-k lists are exchanged with ONE NCCL all-gather per step and merged
+by the K4 kernel on every rank.
+
+value    : whole-job queries/sec with the queries already resident in HBM (device-timed).
+e2e      : the same through the facade with HOST buffers (numpy in, numpy out): H2D of the
+           queries and D2H of ids/scores/counts inside the timed region, every step.
+roofline : dominant kernel = exact_scan_kernel; achieved = rows_local*dim*4 bytes per query /
+           its CUDA-event duration measured live on the launching stream.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec (top-k=50, 1024-d) exact fp32 scan"
+UNIT = "queries/s"
+N_ROWS = 1_000_000
+DIM = 1024
+TOPK = 50
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries-per-step", type=int, default=64)
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
+    ap.add_argument("--cpu-sample-queries", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(rows_total: int, sample_rows: int, sample_queries: int, threads: int):
+    """pgvector-restated exact scan (oracle/pgvector_restated.c) on a bounded sample, scaled to the
+    workload's row count (the scan is linear in rows)."""
+    import numpy as np
+    from oracle import cpu_oracle as orc
+    sample_rows = min(sample_rows, rows_total)
+    x = orc.synth_rows(20260209, 0, sample_rows)
+    qs = orc.synth_rows(20260210, 10_000_000, sample_queries)
+    orc.exact_scan(qs[0], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=threads)   # warm
+    t0 = time.perf_counter()
+    for i in range(sample_queries):
+        orc.exact_scan(qs[i], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=threads)
+    dt = time.perf_counter() - t0
+    cores = threads if threads > 0 else orc.num_threads()
+    qps_sample = sample_queries / dt
+    return {"value": qps_sample * sample_rows / rows_total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_queries} queries x {sample_rows} of {rows_total} rows (pgvector 0.8.1 cosine loop "
+                      f"restated in C, fp32 accumulate, {cores} OpenMP threads; rate scaled by rows)",
+            "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation of the path is SQL on Postgres+pgvector,
+    which cannot run in this image (no postgres/pgvector/sqlalchemy); the arm times the C
+    restatement of pgvector's exact scan on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import cpu_oracle as orc
+    import numpy as np
+    rows = min(args.cpu_sample_rows, args.rows)
+    q_per_step = max(1, min(args.queries_per_step, 8))
+    x = orc.synth_rows(20260209, 0, rows)
+    qs = orc.synth_rows(20260210, 0, (args.steps + args.warmup) * q_per_step)
+    qi = 0
+    for _ in range(args.warmup):
+        for _ in range(q_per_step):
+            orc.exact_scan(qs[qi], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=0); qi += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(q_per_step):
+            orc.exact_scan(qs[qi], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=0); qi += 1
+    dt = time.perf_counter() - t0
+    value = args.steps * q_per_step / dt * rows / args.rows
+    cores = orc.num_threads()
+    sample = (f"{q_per_step} queries/step x {rows} of {args.rows} rows, rate scaled by rows; pgvector 0.8.1 "
+              f"exact-scan loop restated in C (oracle/pgvector_restated.c), {cores} OpenMP threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"exact-scan dense lane, {args.rows} x {DIM} fp32, top-k={TOPK}, single-query scans",
+                       "rows": args.rows, "dim": DIM, "k": TOPK},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cadence_rag_b200 import _ffi
+    from cadence_rag_b200.dist import ShardedSearcher, shard_range
+    from cadence_rag_b200.store import DenseStore, SYNTH_QUERY_SEED, synth_rows_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    _ffi.require_device()
+
+    Q = args.queries_per_step
+    first, count = shard_range(args.rows, rank, world)
+    store = DenseStore("chunks", max(count, 1), dim=DIM, device=local_rank, fp32=True, bf16=False)
+    store.append_synthetic(count, first_row=first)
+    store.finalize()
+    searcher = ShardedSearcher(store)
+    total_steps = args.warmup + args.steps
+    # distinct queries for every step, resident in HBM before the timed region
+    q_dev = synth_rows_device(SYNTH_QUERY_SEED, 0, total_steps * Q, DIM, device=local_rank).view(total_steps, Q, DIM)
+    q_host = q_dev.cpu().numpy()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for s in range(args.warmup):
+        searcher.search(q_dev[s], TOPK)
+    barrier()
+
+    # ---- timed: device-resident queries
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _ffi.lib().cdr_prof_enable(1)
+    launches0 = _ffi.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    last = None
+    for s in range(args.warmup, total_steps):
+        last = searcher.search(q_dev[s], TOPK)
+    ev1.record()
+    barrier()
+    launches = _ffi.kernel_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    import ctypes
+    k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
+    _ffi.check(_ffi.lib().cdr_prof_read(0, ctypes.byref(k_ms), ctypes.byref(k_n)))
+    _ffi.lib().cdr_prof_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, float(launches), k_ms.value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches_total, k_ms_max = float(tmax[0]), int(tsum[1]), float(tmax[2])
+    else:
+        launches_total, k_ms_max = int(launches), k_ms.value
+    value = args.steps * Q / (ms / 1e3)
+
+    # single-query latency (device-timed, one query per call)
+    lat = []
+    for i in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); searcher.search(q_dev[args.warmup + i % args.steps][i % Q: i % Q + 1], TOPK); b.record()
+        torch.cuda.synchronize()
+        lat.append(a.elapsed_time(b))
+    lat.sort()
+
+    # ---- timed: end to end with host buffers
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step(s):
+            if world == 1:
+                return store.search_exact(q_host[s], TOPK)           # cdr_search_exact_f32_host
+            qd = torch.from_numpy(q_host[s]).cuda(non_blocking=False)
+            ids, sc, n = searcher.search(qd, TOPK)
+            return ids.cpu().numpy(), sc.cpu().numpy(), n.cpu().numpy()
+        for s in range(min(args.warmup, 3)):
+            e2e_step(s)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.warmup, total_steps):
+            out = e2e_step(s)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": args.steps * Q / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4,
+               "d2h_bytes_per_step": Q * TOPK * 16 + Q * 4}
+        # the host-buffer path returns the same bits as the device path
+        assert np.array_equal(out[0], last[0].cpu().numpy()), "e2e ids differ from device-path ids"
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        launches_k1 = int(k_n.value)
+        bytes_per_launch = float(count) * DIM * 4 * Q          # one launch scans the shard for Q queries
+        achieved = bytes_per_launch / (k_ms_max / max(launches_k1, 1) / 1e3) / 1e9 if k_ms_max > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_row", 0) * count * Q if tj.get("dram_bytes_per_row") else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: {args.rows} x {DIM} fp32 corpus, single-query exact cosine "
+                                   f"scan + top-k={TOPK}; step = {Q} distinct queries, one scan of the resident "
+                                   f"corpus per query",
+                       "rows": args.rows, "dim": DIM, "k": TOPK, "queries_per_step": Q,
+                       "sharding": f"rows/{world}" if world > 1 else "none",
+                       "l2": "inputs larger than L2 (shard bytes >> 126 MB), distinct queries every step",
+                       "single_query_latency_ms_p50": lat[len(lat) // 2], "single_query_latency_ms_min": lat[0]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "kernel": "exact_scan_kernel<8,2,2>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "avg_launch_ms": k_ms_max / max(launches_k1, 1), "launches_timed": launches_k1},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.rows, args.cpu_sample_rows, args.cpu_sample_queries, 0)
+            one = cpu_baseline(args.rows, min(args.cpu_sample_rows, 50_000), 4, 1)
+            line["cpu_baseline"]["single_thread_value"] = one["value"]
+        print(json.dumps(line), flush=True)
+    store.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,199 @@
+// abi.cu -- extern "C" surface glue: thread-local error text, launch counter, profiling
+// events, and the exact-lane entry points (device- and host-buffer flavours).
+#include "common.cuh"
+
+#include <cstring>
+#include <string>
+
+std::atomic<int64_t> g_cdr_launches{0};
+
+static thread_local char t_err[512] = "";
+
+void cdr_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *cdr_last_error(void) { return t_err; }
+extern "C" int32_t cdr_abi_version(void) { return CDR_ABI_VERSION; }
+extern "C" int64_t cdr_kernel_launch_count(void) { return g_cdr_launches.load(); }
+
+extern "C" int32_t cdr_device_count(int32_t *out_count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (out_count) *out_count = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess || n <= 0) {
+        cdr_set_error("no CUDA device visible (%s); this engine has no CPU fallback",
+                      e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+        return CDR_ERR_NO_DEVICE;
+    }
+    return CDR_OK;
+}
+
+// ---------------------------------------------------------------------------- profiling
+// When enabled, every launch of a dominant kernel (kind 0 = K1 exact scan, 1 = K2 batched
+// bf16 GEMM) is bracketed by CUDA events recorded on the launching stream; cdr_prof_read
+// synchronises those events and returns the summed device time.  Off by default (no events).
+namespace {
+struct ProfState {
+    std::mutex mu;
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs[2];
+    cudaEvent_t pending[2] = {nullptr, nullptr};
+};
+ProfState g_prof;
+}  // namespace
+
+void cdr_prof_mark_begin(int kind, cudaStream_t st)
+{
+    if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof.pending[kind] = e;
+}
+
+void cdr_prof_mark_end(int kind, cudaStream_t st)
+{
+    if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (!g_prof.pending[kind]) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof.pairs[kind].push_back({g_prof.pending[kind], e});
+    g_prof.pending[kind] = nullptr;
+}
+
+extern "C" int32_t cdr_prof_enable(int32_t on)
+{
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (int k = 0; k < 2; ++k) {
+        for (auto &pr : g_prof.pairs[k]) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        g_prof.pairs[k].clear();
+        if (g_prof.pending[k]) cudaEventDestroy(g_prof.pending[k]);
+        g_prof.pending[k] = nullptr;
+    }
+    g_prof.on = on != 0;
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_prof_read(int32_t kind, double *out_total_ms, int64_t *out_launches)
+{
+    CDR_REQUIRE(kind == 0 || kind == 1, CDR_ERR_INVALID, "cdr_prof_read: kind must be 0 or 1");
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    double tot = 0.0;
+    for (auto &pr : g_prof.pairs[kind]) {
+        CDR_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        CDR_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+    }
+    if (out_total_ms) *out_total_ms = tot;
+    if (out_launches) *out_launches = (int64_t)g_prof.pairs[kind].size();
+    return CDR_OK;
+}
+
+// ---------------------------------------------------------------------------- exact lane
+int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
+                          const uint32_t *allow, int k, double *out_score, int64_t *out_id,
+                          int32_t *out_n, cudaStream_t st);
+
+static int check_search_args(const char *fn, cdr_store *s, const void *q, int nq, int k,
+                             const void *o1, const void *o2, const void *o3)
+{
+    CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "%s: store is NULL", fn);
+    CDR_REQUIRE(s->finalized, CDR_ERR_STATE, "%s: store not finalized", fn);
+    CDR_REQUIRE(nq >= 0 && (nq == 0 || q != nullptr), CDR_ERR_INVALID, "%s: bad query batch", fn);
+    CDR_REQUIRE(k >= 1 && k <= CDR_MAX_K, CDR_ERR_UNSUPPORTED, "%s: k=%d outside [1,%d]", fn, k, CDR_MAX_K);
+    CDR_REQUIRE(o1 && o2 && o3, CDR_ERR_INVALID, "%s: output buffers required", fn);
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_search_exact_f32(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                                        const uint32_t *allow_dev, double *out_score_dev,
+                                        int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
+{
+    int rc = check_search_args("cdr_search_exact_f32", s, q_dev, nq, k, out_score_dev, out_id_dev, out_n_dev);
+    if (rc != CDR_OK) return rc;
+    CDR_REQUIRE(s->emb_f32 != nullptr, CDR_ERR_STATE,
+                "cdr_search_exact_f32: store has no fp32 rows (created without CDR_STORE_FP32)");
+    if (nq == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(s->mu);
+    ScanWorkspace &ws = s->ws[st];
+    // rows with embedding IS NULL are excluded even when the caller passes no filter
+    const uint32_t *allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
+    // grid.y is limited to 65535 queries per launch
+    for (int q0 = 0; q0 < nq; q0 += 32768) {
+        const int m = (nq - q0) < 32768 ? (nq - q0) : 32768;
+        rc = cdr_exact_scan_launch(s, ws, q_dev + (size_t)q0 * s->dim, m, allow, k,
+                                   out_score_dev + (size_t)q0 * k, out_id_dev + (size_t)q0 * k,
+                                   out_n_dev + q0, st);
+        if (rc != CDR_OK) return rc;
+    }
+    return CDR_OK;
+}
+
+// Shared host-buffer wrapper: H2D queries, run `fn`, D2H results, synchronise.
+typedef int32_t (*search_fn)(cdr_store *, const float *, int32_t, int32_t, const uint32_t *, double *,
+                             int64_t *, int32_t *, void *);
+
+static int32_t search_host(const char *name, search_fn fn, cdr_store *s, const float *q_host,
+                           int32_t nq, int32_t k, const uint32_t *allow_dev, double *out_score_host,
+                           int64_t *out_id_host, int32_t *out_n_host, void *stream)
+{
+    int rc = check_search_args(name, s, q_host, nq, k, out_score_host, out_id_host, out_n_host);
+    if (rc != CDR_OK) return rc;
+    if (nq == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    float *qd = nullptr;
+    unsigned char *od = nullptr;
+    const size_t qb = (size_t)nq * s->dim * 4;
+    const size_t sb = (size_t)nq * k * 8, ib = (size_t)nq * k * 8, nb = (size_t)nq * 4;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        ScanWorkspace &ws = s->ws[st];
+        if (cdr_ws_reserve((void **)&ws.q_stage, &ws.q_stage_bytes, qb) != CDR_OK) return CDR_ERR_OOM;
+        if (cdr_ws_reserve(&ws.out_stage, &ws.out_stage_bytes, sb + ib + nb + 512) != CDR_OK) return CDR_ERR_OOM;
+        qd = ws.q_stage;
+        od = (unsigned char *)ws.out_stage;
+    }
+    double *sd = (double *)od;
+    int64_t *idd = (int64_t *)(od + sb);
+    int32_t *nd = (int32_t *)(od + sb + ib);
+    CDR_CUDA(cudaMemcpyAsync(qd, q_host, qb, cudaMemcpyHostToDevice, st));
+    rc = fn(s, qd, nq, k, allow_dev, sd, idd, nd, stream);
+    if (rc != CDR_OK) return rc;
+    CDR_CUDA(cudaMemcpyAsync(out_score_host, sd, sb, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaMemcpyAsync(out_id_host, idd, ib, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaMemcpyAsync(out_n_host, nd, nb, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaStreamSynchronize(st));
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_search_exact_f32_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                             const uint32_t *allow_dev, double *out_score_host,
+                                             int64_t *out_id_host, int32_t *out_n_host, void *stream)
+{
+    return search_host("cdr_search_exact_f32_host", cdr_search_exact_f32, s, q_host, nq, k, allow_dev,
+                       out_score_host, out_id_host, out_n_host, stream);
+}
+
+extern "C" int32_t cdr_search_batch_bf16_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                              const uint32_t *allow_dev, double *out_score_host,
+                                              int64_t *out_id_host, int32_t *out_n_host, void *stream)
+{
+    return search_host("cdr_search_batch_bf16_host", cdr_search_batch_bf16, s, q_host, nq, k, allow_dev,
+                       out_score_host, out_id_host, out_n_host, stream);
+}

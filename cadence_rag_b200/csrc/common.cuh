@@ -1,0 +1,279 @@
+// common.cuh -- shared host/device helpers for libcadence_dense (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/cadence_dense.h"
+
+// ------------------------------------------------------------------------------------ errors
+void cdr_set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_cdr_launches;
+
+#define CDR_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            cdr_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                          __LINE__);                                                          \
+            return _e == cudaErrorMemoryAllocation ? CDR_ERR_OOM : CDR_ERR_CUDA;              \
+        }                                                                                     \
+    } while (0)
+
+#define CDR_LAUNCH_CHECK()                                                                    \
+    do {                                                                                      \
+        g_cdr_launches.fetch_add(1, std::memory_order_relaxed);                               \
+        CDR_CUDA(cudaGetLastError());                                                         \
+    } while (0)
+
+#define CDR_REQUIRE(cond, code, ...)                                                          \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            cdr_set_error(__VA_ARGS__);                                                       \
+            return (code);                                                                    \
+        }                                                                                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ store
+struct ScanWorkspace {
+    uint64_t *cta_keys = nullptr;   // [nq_cap, grid, KC] packed candidate keys from K1
+    size_t cta_keys_bytes = 0;
+    float *q_stage = nullptr;       // [nq_cap, dim] fp32 staging for the *_host entry points
+    size_t q_stage_bytes = 0;
+    void *out_stage = nullptr;      // result staging for the *_host entry points
+    size_t out_stage_bytes = 0;
+    void *gemm_ws = nullptr;        // K2 candidate lists, thresholds, bf16 queries
+    size_t gemm_ws_bytes = 0;
+};
+
+struct cdr_store {
+    int device = 0;
+    int dim = 0;
+    int sm_count = 0;
+    uint32_t flags = 0;
+    int64_t capacity = 0;
+    int64_t n_rows = 0;
+    int64_t n_valid = 0;
+    bool finalized = false;
+    bool any_invalid = false;
+
+    float *emb_f32 = nullptr;            // [capacity, dim]
+    __nv_bfloat16 *emb_bf16 = nullptr;   // [capacity, dim], rows L2-normalised before rounding
+    float *inv_norm = nullptr;           // [capacity + pad] 1/||x|| in fp32 (inf for zero rows)
+    int64_t *ids = nullptr;              // [capacity]
+    int32_t *call_slot = nullptr;        // [capacity]
+    int64_t *started_at = nullptr;       // [capacity] microseconds
+    uint64_t *tag_bits = nullptr;        // [capacity]
+    uint32_t *valid = nullptr;           // bitmap [ceil(capacity/32)] embedding IS NOT NULL
+    unsigned long long *d_scratch = nullptr;  // small device scratch (counters / flags)
+
+    std::mutex mu;
+    std::map<cudaStream_t, ScanWorkspace> ws;
+};
+
+int cdr_ws_reserve(void **ptr, size_t *have, size_t need);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// profiling hooks (abi.cu)
+void cdr_prof_mark_begin(int kind, cudaStream_t st);
+void cdr_prof_mark_end(int kind, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------ device
+#ifdef __CUDACC__
+
+#define CDR_EMPTY_KEY 0ull
+
+// Monotone map float -> uint32 (larger float => larger code).  NaN => 1 (below every real
+// cosine, above the empty key's 0), so NaN rows sort last but stay eligible (SQL semantics).
+__device__ __forceinline__ uint32_t cdr_order_f32(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 1u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// key = (order(score) << 32) | (0xFFFFFFFF - row): bigger key = better (score desc, row asc).
+__device__ __forceinline__ uint64_t cdr_pack_key(float score, uint32_t row)
+{
+    return ((uint64_t)cdr_order_f32(score) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+}
+__device__ __forceinline__ uint32_t cdr_key_row(uint64_t key)
+{
+    return 0xFFFFFFFFu - (uint32_t)key;
+}
+
+// (score desc, NaN last, id asc) "a sorts before b"
+__device__ __forceinline__ bool cdr_result_before(double sa, int64_t ia, double sb, int64_t ib)
+{
+    bool na = sa != sa, nb = sb != sb;
+    if (na != nb) return nb;
+    if (!na && sa != sb) return sa > sb;
+    return ia < ib;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier / bulk-copy PTX wrappers
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// 1-D bulk async copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ float warp_sum_f32(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- warp-level bitonic primitives on NPL x 32 uint64 keys, element e = i*32 + lane.
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_exchange(uint64_t (&k)[NPL], int lane, int size,
+                                                      int stride)
+{
+    if (stride >= 32) {
+        const int rs = stride >> 5;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            if ((i & rs) == 0) {
+                const int e = i * 32 + lane;
+                const bool desc = (e & size) == 0;
+                uint64_t a = k[i], b = k[i | rs];
+                const bool swap = desc ? (a < b) : (a > b);
+                if (swap) { k[i] = b; k[i | rs] = a; }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int e = i * 32 + lane;
+            const bool desc = (e & size) == 0;
+            const bool lower = (lane & stride) == 0;
+            uint64_t mine = k[i];
+            uint64_t other = __shfl_xor_sync(0xffffffffu, mine, stride);
+            // the lower element of a descending pair keeps the max
+            const bool keep_max = (desc == lower);
+            k[i] = keep_max ? (mine > other ? mine : other) : (mine < other ? mine : other);
+        }
+    }
+}
+
+// Full sort, descending by key.
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t (&k)[NPL], int lane)
+{
+    constexpr int M = NPL * 32;
+    // fully unrolled so every register index is a compile-time constant (no local memory)
+#pragma unroll
+    for (int size = 2; size <= M; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1)
+            warp_bitonic_exchange<NPL>(k, lane, size == M ? (M << 1) : size, stride);
+    }
+}
+
+// k holds a bitonic sequence; sort it descending.
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_merge_desc(uint64_t (&k)[NPL], int lane)
+{
+    constexpr int M = NPL * 32;
+#pragma unroll
+    for (int stride = M >> 1; stride > 0; stride >>= 1)
+        warp_bitonic_exchange<NPL>(k, lane, M << 1, stride);
+}
+
+// mine: sorted desc (regs); other: sorted desc list of NPL*32 keys in memory.
+// Result: top NPL*32 of the union, sorted desc.
+template <int NPL>
+__device__ __forceinline__ void warp_merge_topk(uint64_t (&mine)[NPL], const uint64_t *other,
+                                                int lane)
+{
+    constexpr int M = NPL * 32;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const int e = i * 32 + lane;
+        uint64_t o = other[M - 1 - e];
+        mine[i] = mine[i] > o ? mine[i] : o;
+    }
+    warp_bitonic_merge_desc<NPL>(mine, lane);
+}
+
+#endif  // __CUDACC__

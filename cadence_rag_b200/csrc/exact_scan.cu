@@ -1,0 +1,523 @@
+// exact_scan.cu -- K1 (HBM-bound fp32 cosine scan with fused running top-k) and the
+// K3/K4 finalize kernel (k-way merge of the per-CTA lists + fp64 re-score + final order).
+//
+// Replaces the reference's mode="exact" dense SQL (app/retrieve.py:339-351, 374-386):
+//   ORDER BY embedding <=> :q LIMIT :k  over  WHERE <filters> AND embedding IS NOT NULL.
+//
+// K1 data flow (one persistent CTA per SM, 9 warps):
+//   warp 8 lane 0 : producer.  For every row tile owned by this CTA it arms the stage's "full"
+//                   mbarrier with the byte count and issues two 1-D bulk async copies
+//                   (cp.async.bulk, SASS UBLKCP): TR rows (TR*dim*4 bytes, 64 KB at dim 1024)
+//                   and the TR inverse norms.  Stages form a ring; a stage is re-armed when the
+//                   8 consumer warps have arrived on its "empty" mbarrier.
+//   warps 0..7    : consumers.  The query lives in registers (J float4 per lane).  Each warp
+//                   owns RPW rows of the tile, reads them from shared memory as conflict-free
+//                   128-bit loads, accumulates the dot product in fp32, butterfly-reduces it,
+//                   scales by 1/||x|| * 1/||q|| and pushes (score,row) keys that beat the warp's
+//                   current KC-th best into a per-warp list in shared memory.
+//   epilogue      : each warp sorts its list (register bitonic network), the 8 lists are
+//                   merged pairwise through shared memory, and the CTA writes its KC best keys.
+// The corpus is read exactly once per query; nothing but KC keys per CTA goes back to HBM.
+//
+// Algorithmic bytes per query: n_rows * dim * 4.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
+constexpr int kMaxStages = 6;
+
+struct ScanParams {
+    const float *rows;        // [n_rows, dim]
+    const float *inv_norm;    // [>= round_up(n_rows, TR)]
+    const uint32_t *allow;    // nullable bitmap
+    const float *queries;     // [nq, dim]
+    uint64_t *cta_keys;       // [nq, gridDim.x, KC]
+    int64_t n_rows;
+    int64_t n_tiles;
+    int n_stages;
+};
+
+// Dynamic shared memory carve-up (computed identically on host and device).
+template <int J, int RPW, int NPL>
+struct ScanSmem {
+    static constexpr int DIM = J * 128;
+    static constexpr int TR = RPW * kConsumerWarps;
+    static constexpr int KC = NPL * 32;
+    static constexpr size_t kTileBytes = (size_t)TR * DIM * 4;
+    static constexpr size_t kMetaBytes = (size_t)TR * 4;   // inverse norms (multiple of 16)
+    static constexpr size_t kListBytes = (size_t)kConsumerWarps * KC * 8;
+    static constexpr size_t kBarBytes = 2 * kMaxStages * 8;
+    static constexpr size_t bytes(int stages)
+    {
+        return (size_t)stages * (kTileBytes + kMetaBytes) + kListBytes + kBarBytes + 128;
+    }
+    static int max_stages(size_t smem_limit)
+    {
+        int s = kMaxStages;
+        while (s > 1 && bytes(s) > smem_limit) --s;
+        return s;
+    }
+};
+
+// Per-warp running top-KC in shared memory: unsorted list + (min key, position) in registers.
+template <int NPL>
+struct WarpTopK {
+    uint64_t *list;   // [KC]
+    uint64_t tau;     // current admission threshold (0 while the list is not full)
+    int count;
+    int min_pos;
+
+    __device__ __forceinline__ void init(uint64_t *l, int lane)
+    {
+        list = l;
+        tau = 0;
+        count = 0;
+        min_pos = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) list[i * 32 + lane] = CDR_EMPTY_KEY;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void refresh_min(int lane)
+    {
+        uint64_t m = ~0ull;
+        int pos = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            uint64_t v = list[i * 32 + lane];
+            if (v < m) { m = v; pos = i * 32 + lane; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint64_t om = __shfl_xor_sync(0xffffffffu, m, o);
+            int op = __shfl_xor_sync(0xffffffffu, pos, o);
+            if (om < m) { m = om; pos = op; }   // keys are unique, so no tie handling needed
+        }
+        tau = m;
+        min_pos = pos;
+    }
+    // warp-uniform call
+    __device__ __forceinline__ void push(uint64_t key, int lane)
+    {
+        constexpr int KC = NPL * 32;
+        if (count < KC) {
+            if (lane == 0) list[count] = key;
+            ++count;
+            __syncwarp();
+            if (count == KC) refresh_min(lane);
+        } else {
+            if (lane == 0) list[min_pos] = key;
+            __syncwarp();
+            refresh_min(lane);
+        }
+    }
+};
+
+template <int J, int RPW, int NPL>
+__global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanParams p)
+{
+    using L = ScanSmem<J, RPW, NPL>;
+    constexpr int DIM = L::DIM, TR = L::TR, KC = L::KC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int S = p.n_stages;
+    unsigned char *tiles = smem_raw;
+    unsigned char *metas = tiles + (size_t)S * L::kTileBytes;
+    uint64_t *lists = reinterpret_cast<uint64_t *>(metas + (size_t)S * L::kMetaBytes);
+    uint64_t *full_bar = lists + kConsumerWarps * KC;
+    uint64_t *empty_bar = full_bar + kMaxStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.y;
+    const int64_t G = gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // number of tiles this CTA owns: t = blockIdx.x + i*G
+    const int64_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + G - 1) / G : 0;
+
+    if (warp == kConsumerWarps) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                const int s = (int)(i % S);
+                const uint32_t ph = (uint32_t)((i / S) & 1);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                const int64_t tile = blockIdx.x + i * G;
+                const int64_t row0 = tile * TR;
+                int64_t nr = p.n_rows - row0;
+                if (nr > TR) nr = TR;
+                const uint32_t row_bytes = (uint32_t)(nr * DIM * 4);
+                mbar_arrive_expect_tx(&full_bar[s], row_bytes + (uint32_t)L::kMetaBytes);
+                bulk_g2s(tiles + (size_t)s * L::kTileBytes, p.rows + row0 * DIM, row_bytes,
+                         &full_bar[s]);
+                bulk_g2s(metas + (size_t)s * L::kMetaBytes, p.inv_norm + row0,
+                         (uint32_t)L::kMetaBytes, &full_bar[s]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        float4 q[J];
+        float qn = 0.f;
+        const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)qi * DIM);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            q[j] = __ldg(&qv[j * 32 + lane]);
+            qn = fmaf(q[j].x, q[j].x, qn);
+            qn = fmaf(q[j].y, q[j].y, qn);
+            qn = fmaf(q[j].z, q[j].z, qn);
+            qn = fmaf(q[j].w, q[j].w, qn);
+        }
+        qn = warp_sum_f32(qn);
+        const float inv_qn = __fdiv_rn(1.0f, __fsqrt_rn(qn));   // inf for a zero query -> NaN scores
+
+        WarpTopK<NPL> top;
+        top.init(lists + warp * KC, lane);
+
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            const int s = (int)(i % S);
+            const uint32_t ph = (uint32_t)((i / S) & 1);
+            const int64_t tile = blockIdx.x + i * G;
+            const int64_t row0 = tile * TR + warp * RPW;
+            // filter bits for this warp's rows (issued before the wait so the latency overlaps)
+            uint32_t allow_bits = 0xFFFFFFFFu;
+            if (p.allow != nullptr) {
+                // RPW <= 2 consecutive rows never straddle a 32-bit word (row0 is even when RPW==2)
+                const uint32_t w = (row0 < p.n_rows) ? __ldg(&p.allow[row0 >> 5]) : 0u;
+                allow_bits = w >> (row0 & 31);
+            }
+            mbar_wait(&full_bar[s], ph);
+
+            const float4 *tv = reinterpret_cast<const float4 *>(tiles + (size_t)s * L::kTileBytes) +
+                               (size_t)(warp * RPW) * (DIM / 4);
+            const float *mv = reinterpret_cast<const float *>(metas + (size_t)s * L::kMetaBytes) +
+                              warp * RPW;
+            float acc[RPW][2];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) acc[r][0] = acc[r][1] = 0.f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const float4 v = tv[r * (DIM / 4) + j * 32 + lane];
+                    float a = acc[r][j & 1];
+                    a = fmaf(v.x, q[j].x, a);
+                    a = fmaf(v.y, q[j].y, a);
+                    a = fmaf(v.z, q[j].z, a);
+                    a = fmaf(v.w, q[j].w, a);
+                    acc[r][j & 1] = a;
+                }
+            }
+            float inv_n[RPW];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) inv_n[r] = mv[r];
+            // all reads of this stage are done (values are in registers): release it early
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                const float dot = warp_sum_f32(acc[r][0] + acc[r][1]);
+                const int64_t row = row0 + r;
+                const bool ok = (row < p.n_rows) && ((allow_bits >> r) & 1u);
+                if (ok) {
+                    const float score = dot * inv_n[r] * inv_qn;
+                    const uint64_t key = cdr_pack_key(score, (uint32_t)row);
+                    if (key > top.tau) top.push(key, lane);
+                }
+            }
+        }
+
+        // ---- per-warp sort, then 3-level pairwise merge through shared memory
+        uint64_t k[NPL];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) k[i] = top.list[i * 32 + lane];
+        warp_bitonic_sort_desc<NPL>(k, lane);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
+#pragma unroll
+        for (int step = 1; step < kConsumerWarps; step <<= 1) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+            if ((warp & (2 * step - 1)) == 0) {
+                warp_merge_topk<NPL>(k, lists + (warp + step) * KC, lane);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+            if ((warp & (2 * step - 1)) == 0) {
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
+            }
+        }
+        if (warp == 0) {
+            uint64_t *out = p.cta_keys + ((size_t)qi * G + blockIdx.x) * KC;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Finalize: one CTA (8 warps) per query.
+//   1. k-way merge: warp w folds lists w, w+8, ... (each sorted desc, KC keys) into its registers
+//      with the bitonic top-k merge, then the 8 partial results are merged pairwise.
+//   2. fp64 re-score of the KC survivors on the resident fp32 rows (pgvector's formula with
+//      fp64 accumulators): sim = ab / sqrt(aa*bb), clamp, distance = 1 - sim, score = 1 - distance.
+//   3. final order (score desc, NaN last, id asc) by rank counting; first k written out.
+struct FinalizeParams {
+    const uint64_t *lists;    // [nq, n_lists, KC]
+    int n_lists;
+    const float *rows;        // fp32 rows (may be null when bf16_rows is used)
+    const __nv_bfloat16 *bf16_rows;
+    const float *queries;     // [nq, dim]
+    const int64_t *ids;
+    int dim;
+    int k;
+    double *out_score;        // [nq, k]
+    int64_t *out_id;          // [nq, k]
+    int32_t *out_n;           // [nq]
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams p)
+{
+    constexpr int KC = NPL * 32;
+    __shared__ uint64_t s_lists[8 * KC];
+    __shared__ double s_score[KC];
+    __shared__ int64_t s_id[KC];
+    __shared__ int s_valid[KC];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x;
+    const uint64_t *base = p.lists + (size_t)qi * p.n_lists * KC;
+
+    uint64_t k[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) k[i] = CDR_EMPTY_KEY;
+    for (int l = warp; l < p.n_lists; l += 8) warp_merge_topk<NPL>(k, base + (size_t)l * KC, lane);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+#pragma unroll
+    for (int step = 1; step < 8; step <<= 1) {
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0) warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0) {
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+        }
+    }
+    __syncthreads();
+
+    // ---- fp64 re-score: warp w takes candidates w, w+8, ...
+    const float *qrow = p.queries + (size_t)qi * p.dim;
+    const int nvec = p.dim >> 2;   // float4 per row
+    double aa = 0.0;
+    for (int v = lane; v < nvec; v += 32) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(qrow) + v);
+        aa = __fma_rn((double)a.x, (double)a.x, aa);
+        aa = __fma_rn((double)a.y, (double)a.y, aa);
+        aa = __fma_rn((double)a.z, (double)a.z, aa);
+        aa = __fma_rn((double)a.w, (double)a.w, aa);
+    }
+    aa = warp_sum_f64(aa);
+    for (int c = warp; c < KC; c += 8) {
+        const uint64_t key = s_lists[c];
+        if (key == CDR_EMPTY_KEY) {
+            if (lane == 0) { s_valid[c] = 0; s_score[c] = 0.0; s_id[c] = -1; }
+            continue;
+        }
+        const uint32_t row = cdr_key_row(key);
+        double ab = 0.0, bb = 0.0;
+        if (p.rows != nullptr) {
+            const float4 *xr = reinterpret_cast<const float4 *>(p.rows + (size_t)row * p.dim);
+            for (int v = lane; v < nvec; v += 32) {
+                const float4 b = __ldg(xr + v);
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(qrow) + v);
+                ab = __fma_rn((double)a.x, (double)b.x, ab);
+                ab = __fma_rn((double)a.y, (double)b.y, ab);
+                ab = __fma_rn((double)a.z, (double)b.z, ab);
+                ab = __fma_rn((double)a.w, (double)b.w, ab);
+                bb = __fma_rn((double)b.x, (double)b.x, bb);
+                bb = __fma_rn((double)b.y, (double)b.y, bb);
+                bb = __fma_rn((double)b.z, (double)b.z, bb);
+                bb = __fma_rn((double)b.w, (double)b.w, bb);
+            }
+        } else {
+            const uint2 *xr = reinterpret_cast<const uint2 *>(p.bf16_rows + (size_t)row * p.dim);
+            for (int v = lane; v < nvec; v += 32) {
+                const uint2 raw = __ldg(xr + v);
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(qrow) + v);
+                const float b0 = __uint_as_float(raw.x << 16), b1 = __uint_as_float(raw.x & 0xFFFF0000u);
+                const float b2 = __uint_as_float(raw.y << 16), b3 = __uint_as_float(raw.y & 0xFFFF0000u);
+                ab = __fma_rn((double)a.x, (double)b0, ab);
+                ab = __fma_rn((double)a.y, (double)b1, ab);
+                ab = __fma_rn((double)a.z, (double)b2, ab);
+                ab = __fma_rn((double)a.w, (double)b3, ab);
+                bb = __fma_rn((double)b0, (double)b0, bb);
+                bb = __fma_rn((double)b1, (double)b1, bb);
+                bb = __fma_rn((double)b2, (double)b2, bb);
+                bb = __fma_rn((double)b3, (double)b3, bb);
+            }
+        }
+        ab = warp_sum_f64(ab);
+        bb = warp_sum_f64(bb);
+        if (lane == 0) {
+            double sim = __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb)));
+            if (sim > 1.0) sim = 1.0;
+            else if (sim < -1.0) sim = -1.0;
+            const double dist = __dsub_rn(1.0, sim);       // pgvector cosine_distance (float8)
+            s_score[c] = __dsub_rn(1.0, dist);             // SQL: 1 - (embedding <=> q)
+            s_id[c] = p.ids[row];
+            s_valid[c] = 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- final order by rank counting
+    int n_valid = 0;
+    for (int c = 0; c < KC; ++c) n_valid += s_valid[c];
+    for (int c = threadIdx.x; c < KC; c += blockDim.x) {
+        if (!s_valid[c]) continue;
+        const double sc = s_score[c];
+        const int64_t id = s_id[c];
+        int rank = 0;
+        for (int o = 0; o < KC; ++o) {
+            if (o != c && s_valid[o] && cdr_result_before(s_score[o], s_id[o], sc, id)) ++rank;
+        }
+        if (rank < p.k) {
+            p.out_score[(size_t)qi * p.k + rank] = sc;
+            p.out_id[(size_t)qi * p.k + rank] = id;
+        }
+    }
+    const int n_out = n_valid < p.k ? n_valid : p.k;
+    for (int c = n_out + threadIdx.x; c < p.k; c += blockDim.x) {
+        p.out_score[(size_t)qi * p.k + c] = __longlong_as_double(0x7FF8000000000000ll);
+        p.out_id[(size_t)qi * p.k + c] = -1;
+    }
+    if (threadIdx.x == 0) p.out_n[qi] = n_out;
+}
+
+template <int J, int RPW, int NPL>
+int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
+                  const uint32_t *allow, int k, double *out_score, int64_t *out_id, int32_t *out_n,
+                  cudaStream_t st)
+{
+    using L = ScanSmem<J, RPW, NPL>;
+    constexpr int KC = L::KC;
+    // per-device launch configuration (the smem opt-in attribute is per device)
+    static int stages_by_dev[64] = {0};
+    static size_t smem_by_dev[64] = {0};
+    int &stages = stages_by_dev[s->device & 63];
+    size_t &smem = smem_by_dev[s->device & 63];
+    if (stages == 0) {
+        int dev_smem = 0;
+        CDR_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+        int st_n = L::max_stages((size_t)dev_smem);
+        smem = L::bytes(st_n);
+        CDR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<J, RPW, NPL>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stages = st_n;
+    }
+    const int64_t n_tiles = (s->n_rows + L::TR - 1) / L::TR;
+    int grid = (int)(n_tiles < s->sm_count ? n_tiles : s->sm_count);
+    if (grid < 1) grid = 1;
+
+    const size_t need = (size_t)nq * grid * KC * sizeof(uint64_t);
+    if (cdr_ws_reserve((void **)&ws.cta_keys, &ws.cta_keys_bytes, need) != CDR_OK) return CDR_ERR_OOM;
+
+    ScanParams sp;
+    sp.rows = s->emb_f32;
+    sp.inv_norm = s->inv_norm;
+    sp.allow = allow;
+    sp.queries = q_dev;
+    sp.cta_keys = ws.cta_keys;
+    sp.n_rows = s->n_rows;
+    sp.n_tiles = n_tiles;
+    sp.n_stages = stages;
+
+    cdr_prof_mark_begin(0, st);
+    exact_scan_kernel<J, RPW, NPL><<<dim3(grid, nq), kScanThreads, smem, st>>>(sp);
+    CDR_LAUNCH_CHECK();
+    cdr_prof_mark_end(0, st);
+
+    FinalizeParams fp;
+    fp.lists = ws.cta_keys;
+    fp.n_lists = grid;
+    fp.rows = s->emb_f32;
+    fp.bf16_rows = nullptr;
+    fp.queries = q_dev;
+    fp.ids = s->ids;
+    fp.dim = s->dim;
+    fp.k = k;
+    fp.out_score = out_score;
+    fp.out_id = out_id;
+    fp.out_n = out_n;
+    scan_finalize_kernel<NPL><<<nq, 256, 0, st>>>(fp);
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+}
+
+template <int NPL>
+int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
+                    const uint32_t *allow, int k, double *out_score, int64_t *out_id,
+                    int32_t *out_n, cudaStream_t st)
+{
+    switch (s->dim) {
+    case 256:  return launch_scan_t<2, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 512:  return launch_scan_t<4, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 768:  return launch_scan_t<6, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 1024: return launch_scan_t<8, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 1536: return launch_scan_t<12, 1, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 2048: return launch_scan_t<16, 1, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    default:
+        cdr_set_error("exact scan: dim %d not built (supported: 256,512,768,1024,1536,2048)", s->dim);
+        return CDR_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+// Chooses the candidate-list width: KC = 64 serves k <= 56, KC = 256 serves k <= 248
+// (KC - k >= 8 spare slots absorb fp32-vs-fp64 rank swaps at the boundary).
+int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
+                          const uint32_t *allow, int k, double *out_score, int64_t *out_id,
+                          int32_t *out_n, cudaStream_t st)
+{
+    if (k <= 56) return launch_scan_dim<2>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+}
+
+// Used by the batched bf16 lane: re-score + order caller-provided candidate lists.
+int cdr_finalize_lists_launch(cdr_store *s, const uint64_t *lists, int n_lists, int kc,
+                              const float *q_dev, int nq, int k, bool use_bf16_rows,
+                              double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st)
+{
+    FinalizeParams fp;
+    fp.lists = lists;
+    fp.n_lists = n_lists;
+    fp.rows = use_bf16_rows ? nullptr : s->emb_f32;
+    fp.bf16_rows = s->emb_bf16;
+    fp.queries = q_dev;
+    fp.ids = s->ids;
+    fp.dim = s->dim;
+    fp.k = k;
+    fp.out_score = out_score;
+    fp.out_id = out_id;
+    fp.out_n = out_n;
+    if (kc == 64) scan_finalize_kernel<2><<<nq, 256, 0, st>>>(fp);
+    else if (kc == 256) scan_finalize_kernel<8><<<nq, 256, 0, st>>>(fp);
+    else {
+        cdr_set_error("finalize: candidate width %d not built", kc);
+        return CDR_ERR_UNSUPPORTED;
+    }
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+}

@@ -1,0 +1,124 @@
+// filter.cu -- K6: per-row predicate -> 1 bit/row allow-bitmap + exact candidate count.
+//
+// Replaces the WHERE clause the reference builds in app/retrieve.py:93-120
+// (_build_filter_clause) plus `AND embedding IS NOT NULL` (app/retrieve.py:318,347), evaluated
+// per row inside Postgres, and the exact COUNT(*) of app/retrieve.py:303-323
+// (_estimate_dense_candidates).  HBM-bound column scan: 20 B/row read (call_slot i32,
+// started_at i64, tag_bits u64) + 1 bit/row written; coalesced, one ballot per 32 rows.
+#include "common.cuh"
+
+namespace {
+
+struct FilterParams {
+    const int32_t *call_slot;
+    const int64_t *started_at;
+    const uint64_t *tag_bits;
+    const uint32_t *valid;
+    const uint32_t *call_bitmap;   // device copy, nullable
+    int64_t n_call_slots;
+    int64_t n_rows;
+    int has_from, has_to, has_tags;
+    int64_t date_from, date_to;
+    uint64_t tag_any;
+    uint32_t *out_allow;
+    unsigned long long *out_count;
+};
+
+__global__ void __launch_bounds__(256) filter_bitmap_kernel(const FilterParams p)
+{
+    const int64_t words = (p.n_rows + 31) >> 5;
+    unsigned long long local = 0;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < words; w += nwarps) {
+        const int64_t row = (w << 5) + lane;
+        bool ok = false;
+        if (row < p.n_rows) {
+            ok = (p.valid[w] >> lane) & 1u;
+            if (ok && p.call_bitmap) {
+                const int32_t slot = p.call_slot[row];
+                ok = slot >= 0 && slot < p.n_call_slots && ((p.call_bitmap[slot >> 5] >> (slot & 31)) & 1u);
+            }
+            if (ok && (p.has_from | p.has_to)) {
+                const int64_t t = p.started_at[row];
+                if (p.has_from && t < p.date_from) ok = false;
+                if (p.has_to && t > p.date_to) ok = false;
+            }
+            if (ok && p.has_tags) ok = (p.tag_bits[row] & p.tag_any) != 0ull;
+        }
+        const unsigned bits = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) {
+            p.out_allow[w] = bits;
+            local += __popc(bits);
+        }
+    }
+    // one atomic per block
+    __shared__ unsigned long long s_cnt[8];
+    if (lane == 0) s_cnt[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_cnt[i];
+        if (t) atomicAdd(p.out_count, t);
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t cdr_filter_build(cdr_store *s, const uint32_t *call_slot_bitmap_host,
+                                    int64_t n_call_slots, int32_t has_date_from, int64_t date_from_us,
+                                    int32_t has_date_to, int64_t date_to_us, int32_t has_tag_filter,
+                                    uint64_t tag_any, uint32_t *out_allow_dev, int64_t *out_count_host,
+                                    void *stream)
+{
+    CDR_REQUIRE(s != nullptr && out_allow_dev != nullptr, CDR_ERR_INVALID, "cdr_filter_build: NULL argument");
+    CDR_REQUIRE(s->finalized, CDR_ERR_STATE, "cdr_filter_build: store not finalized");
+    CDR_REQUIRE(call_slot_bitmap_host == nullptr || n_call_slots >= 0, CDR_ERR_INVALID,
+                "cdr_filter_build: n_call_slots < 0");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *bm_dev = nullptr;
+    if (call_slot_bitmap_host) {
+        const size_t words = (size_t)((n_call_slots + 31) / 32) + 1;
+        CDR_CUDA(cudaMallocAsync(&bm_dev, words * 4, st));
+        CDR_CUDA(cudaMemsetAsync(bm_dev, 0, words * 4, st));
+        if (n_call_slots > 0)
+            CDR_CUDA(cudaMemcpyAsync(bm_dev, call_slot_bitmap_host, (size_t)((n_call_slots + 31) / 32) * 4,
+                                     cudaMemcpyHostToDevice, st));
+    }
+    unsigned long long *cnt = nullptr;
+    CDR_CUDA(cudaMallocAsync(&cnt, sizeof(unsigned long long), st));
+    CDR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+
+    FilterParams p;
+    p.call_slot = s->call_slot;
+    p.started_at = s->started_at;
+    p.tag_bits = s->tag_bits;
+    p.valid = s->valid;
+    p.call_bitmap = bm_dev;
+    p.n_call_slots = n_call_slots;
+    p.n_rows = s->n_rows;
+    p.has_from = has_date_from != 0;
+    p.has_to = has_date_to != 0;
+    p.has_tags = has_tag_filter != 0;
+    p.date_from = date_from_us;
+    p.date_to = date_to_us;
+    p.tag_any = tag_any;
+    p.out_allow = out_allow_dev;
+    p.out_count = cnt;
+    const int64_t words = (s->n_rows + 31) / 32;
+    int64_t blocks = (words + 7) / 8;
+    const int64_t cap = (int64_t)s->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    filter_bitmap_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+    CDR_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    CDR_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaFreeAsync(cnt, st));
+    if (bm_dev) CDR_CUDA(cudaFreeAsync(bm_dev, st));
+    CDR_CUDA(cudaStreamSynchronize(st));
+    if (out_count_host) *out_count_host = (int64_t)h;
+    return CDR_OK;
+}

@@ -1,0 +1,110 @@
+"""tech_tokens lexical lane (host side) -- the second lane of the hybrid /retrieve.
+
+  extract_tech_tokens(text)       app/ingest.py:141-160 (patterns app/ingest.py:24-73)
+  TechTokenIndex.query(...)       the SQL of _fetch_chunks_tech, app/retrieve.py:195-208:
+        WHERE <filters> AND tech_tokens && :tokens
+        ORDER BY call_started_at DESC, chunk_id ASC LIMIT :limit
+
+The reference evaluates ``tech_tokens && :tokens`` with a GIN index inside Postgres
+(alembic/versions/0001_initial_schema.py:96); here it is a dictionary-encoded inverted index
+(token -> sorted row list) on the host.  The lane produces ranks only (no score), so nothing in
+it is floating point.  A device-resident version is SURVEY.md 8(f) row f-1.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+# (regex, flags) -- order matters: findall results are emitted pattern by pattern (ingest.py:143-145)
+_PATTERN_SPECS = (
+    (r"https?://\S+", re.IGNORECASE),
+    (r"\b(?:\d{1,3}\.){3}\d{1,3}\b", 0),              # IPv4
+    (r"\b[A-Z]{2,10}-\d+\b", 0),                       # ticket ids
+    (r"\bE[A-Z0-9_]{2,}\b", 0),                        # errno-style names
+    (r"\bHTTP\s?\d{3}\b", re.IGNORECASE),
+    (r"\bORA-\d{4,}\b", re.IGNORECASE),
+    (r"\bv?\d+\.\d+(?:\.\d+)?\b", 0),                  # versions
+    (r"\b[a-f0-9]{7,40}\b", re.IGNORECASE),            # commit hashes
+    (r"(?:/[\w.\-]+)+", 0),                            # file paths
+)
+# canonical token <- trigger regex (all case-insensitive); order = emission order (ingest.py:146-148)
+_DOMAIN_SPECS = (
+    ("BOM", r"\bbill of materials\b"), ("BOM", r"\bbom\b"), ("build", r"\bbuild(?:s|ing)?\b"),
+    ("SSD", r"\bssd\b"), ("object store", r"\bobject\s+(?:store|storage)\b"), ("object", r"\bobject\b"),
+    ("tiering", r"\btiering\b"), ("Lenovo", r"\blenovo\b"), ("Dell", r"\bdell\b"),
+    ("Supermicro", r"\bsuper[\s-]?micro\b|\bsmc\b"), ("AWS", r"\baws\b|\bamazon web services\b"),
+    ("Amazon", r"\bamazon\b"), ("Azure", r"\bazure\b"), ("Microsoft", r"\bmicrosoft\b"),
+    ("GCP", r"\bgcp\b|\bgoogle cloud(?: platform)?\b"), ("Google", r"\bgoogle\b"),
+    ("OCI", r"\boci\b|\boracle cloud(?: infrastructure)?\b"), ("Oracle", r"\boracle\b"),
+    ("competitive", r"\bcompet(?:e|es|ing|ition|itive|itor|itors)\b"), ("incumbent", r"\bincumbent\b"),
+    ("bake-off", r"\bbake[\s-]?off\b"), ("head-to-head", r"\bhead[\s-]?to[\s-]?head\b"),
+    ("vs", r"\bvs\.?(?=\s|$)|\bversus\b"),
+)
+_PATTERNS = tuple(re.compile(p, f) for p, f in _PATTERN_SPECS)
+_DOMAIN = tuple((re.compile(p, re.IGNORECASE), canon) for canon, p in _DOMAIN_SPECS)
+
+
+def extract_tech_tokens(text: str) -> List[str]:
+    """Tokens of the exact-match lane: regex hits, then domain canonicals; stripped, empty dropped,
+    first occurrence kept under case-insensitive comparison, original casing preserved."""
+    found: List[str] = []
+    for rx in _PATTERNS:
+        found += rx.findall(text)
+    found += [canon for rx, canon in _DOMAIN if rx.search(text)]
+    out: Dict[str, str] = {}
+    for tok in found:
+        tok = tok.strip()
+        if tok:
+            out.setdefault(tok.lower(), tok)
+    return list(out.values())
+
+
+class TechTokenIndex:
+    """token -> ascending row list.  Element equality is case-sensitive, as text[] `&&` is."""
+
+    def __init__(self):
+        self._lists: Dict[str, List[int]] = {}
+        self._arrays: Dict[str, np.ndarray] = {}
+
+    def add_row(self, row: int, tokens: Iterable[str]) -> None:
+        for tok in set(tokens):
+            self._lists.setdefault(tok, []).append(row)
+        self._arrays.clear()
+
+    def add_postings(self, token: str, rows: np.ndarray) -> None:
+        """Bulk load (synthetic corpora): rows must be ascending."""
+        self._arrays[token] = np.ascontiguousarray(rows, dtype=np.int64)
+        self._lists.pop(token, None)
+
+    def postings(self, token: str) -> np.ndarray:
+        arr = self._arrays.get(token)
+        if arr is None:
+            arr = np.asarray(sorted(self._lists.get(token, ())), dtype=np.int64)
+            self._arrays[token] = arr
+        return arr
+
+    def query(self, tokens: Sequence[str], cols: Dict[str, np.ndarray], limit: int, *,
+              call_slots: Optional[Sequence[int]] = None, date_from=None, date_to=None,
+              tag_mask: Optional[int] = None) -> np.ndarray:
+        """Rows matching any token and the filter, ordered (call_started_at DESC, id ASC), first
+        ``limit``.  ``cols`` are the store's host columns (ids, call_slot, started_at, tag_bits)."""
+        from .store import to_micros
+        lists = [self.postings(t) for t in tokens]
+        lists = [l for l in lists if l.size]
+        if not lists or limit <= 0:
+            return np.empty(0, dtype=np.int64)
+        rows = np.unique(np.concatenate(lists))
+        keep = np.ones(rows.size, dtype=bool)
+        if call_slots is not None:
+            keep &= np.isin(cols["call_slot"][rows], np.asarray(list(call_slots), dtype=np.int32))
+        if date_from is not None:
+            keep &= cols["started_at"][rows] >= to_micros(date_from)
+        if date_to is not None:
+            keep &= cols["started_at"][rows] <= to_micros(date_to)
+        if tag_mask is not None:
+            keep &= (cols["tag_bits"][rows] & np.uint64(tag_mask)) != 0
+        rows = rows[keep]
+        order = np.lexsort((cols["ids"][rows], -cols["started_at"][rows]))
+        return rows[order][:limit]

@@ -1,0 +1,438 @@
+"""Dense-lane retrieval facade -- the reference's app/retrieve.py call surface over the GPU store.
+
+Same function names, argument order and return shapes as the reference for the functions on the
+hot path; ``conn`` is a :class:`DenseConnection` instead of a SQLAlchemy
+connection and ``query_embedding`` may be the reference's ``"[...]"`` literal, a float sequence
+or a tensor:
+
+  _resolve_call_ids            app/retrieve.py:46-90
+  _estimate_dense_candidates   app/retrieve.py:303-323   exact COUNT(*) -> K6 popcount
+  _dense_has_scoping           app/retrieve.py:267-274
+  _choose_dense_mode           app/retrieve.py:277-287
+  _fetch_chunks_dense          app/retrieve.py:326-354   SQL ORDER BY <=> LIMIT -> K1 / K2
+  _fetch_artifacts_dense       app/retrieve.py:357-389
+  _fetch_chunks_tech / _fetch_artifacts_tech   app/retrieve.py:183-242 (host inverted index)
+  _rrf_merge                   app/retrieve.py:245-260   -> K5 (bit-exact)
+  _vector_literal              app/retrieve.py:263-264
+  _build_debug_lane            app/retrieve.py:35-43
+  retrieve_ids                 the ids_only branch of retrieve_evidence, app/retrieve.py:392-573
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from datetime import datetime
+from typing import Any, Dict, Iterable, List, Mapping, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import DenseEngineError
+from .config import settings
+from .embeddings import EmbeddingClientError, embed_texts, embeddings_enabled
+from .lexical import TechTokenIndex, extract_tech_tokens
+from .store import DenseStore
+
+DEFAULT_RRF_K = 60
+DEFAULT_CHUNK_BM25_TOPK = 50
+DEFAULT_ARTIFACT_CHUNK_BM25_TOPK = 10
+DEFAULT_DENSE_CHUNK_TOPK = 50
+DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK = 10
+DEFAULT_TECH_TOPK = 50
+
+
+@dataclass
+class RetrieveFilters:
+    """Duck-type of the reference's pydantic model (app/schemas.py:77-83)."""
+    date_from: Optional[datetime] = None
+    date_to: Optional[datetime] = None
+    call_ids: Optional[List[Any]] = None
+    external_id: Optional[str] = None
+    external_source: Optional[str] = None
+    call_tags: Optional[List[str]] = None
+
+
+class DenseConnection:
+    """Stands where ``with engine.connect() as conn`` stands in the reference
+    (app/retrieve.py:445): request-scoped access to the resident stores.  Filter bitmaps built
+    for a request are cached on the connection, so the COUNT(*) estimate and the search share one
+    K6 launch."""
+
+    def __init__(self, engine: "DenseEngine"):
+        self.engine = engine
+        self._bitmaps: Dict[Tuple, Tuple[Any, int]] = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self._bitmaps.clear()
+        return False
+
+    def store(self, table_name: str) -> DenseStore:
+        try:
+            return self.engine.stores[table_name]
+        except KeyError:
+            raise DenseEngineError(f"no resident store for table {table_name!r}") from None
+
+
+class DenseEngine:
+    """Holds the resident stores ("chunks", "artifact_chunks"), their tech-token indexes and the
+    external_id -> call_id map used by filters."""
+
+    def __init__(self):
+        self.stores: Dict[str, DenseStore] = {}
+        self.tech_indexes: Dict[str, TechTokenIndex] = {}
+        self.external_ids: Dict[Tuple[str, Optional[str]], Set[Any]] = {}
+
+    def register(self, store: DenseStore, tech_index: Optional[TechTokenIndex] = None) -> None:
+        self.stores[store.table_name] = store
+        if tech_index is not None:
+            self.tech_indexes[store.table_name] = tech_index
+
+    def register_call(self, call_id, external_id: Optional[str] = None, external_source: Optional[str] = None) -> None:
+        if external_id is not None:
+            self.external_ids.setdefault((external_id, external_source), set()).add(call_id)
+
+    def connect(self) -> DenseConnection:
+        return DenseConnection(self)
+
+
+# --------------------------------------------------------------------------- small pure helpers
+def _build_debug_lane(rows: Sequence[Mapping[str, Any]], id_field: str) -> List[Dict[str, Any]]:
+    return [{id_field: row[id_field], "rank": rank, "score": row.get("score")}
+            for rank, row in enumerate(rows, start=1)]
+
+
+def _vector_literal(values: Sequence[float]) -> str:
+    return "[" + ",".join(format(float(v), ".10g") for v in values) + "]"
+
+
+def _query_vector(query_embedding) -> np.ndarray:
+    """Reference literal / float sequence / tensor -> float32 vector.  The text form is parsed the
+    way pgvector's vector_in does (strtof per element => exact float32 rounding)."""
+    if isinstance(query_embedding, str):
+        body = query_embedding.strip()
+        if not (body.startswith("[") and body.endswith("]")):
+            raise DenseEngineError("malformed vector literal")
+        return np.array([np.float32(tok) for tok in body[1:-1].split(",")], dtype=np.float32)
+    if hasattr(query_embedding, "detach"):
+        return query_embedding.detach().to("cpu").numpy().astype(np.float32).reshape(-1)
+    return np.asarray(query_embedding, dtype=np.float32).reshape(-1)
+
+
+def _resolve_call_ids(conn: DenseConnection, filters: Optional[RetrieveFilters]) -> Optional[List[Any]]:
+    if not filters:
+        return None
+    call_ids: Optional[Set[Any]] = set(filters.call_ids) if filters.call_ids else None
+    if filters.external_id:
+        resolved: Set[Any] = set()
+        for (ext_id, ext_src), ids in conn.engine.external_ids.items():
+            if ext_id != filters.external_id:
+                continue
+            # reference: no source given => any source; else IS NOT DISTINCT FROM :external_source
+            if filters.external_source is None or ext_src == filters.external_source:
+                resolved |= ids
+        if call_ids:
+            call_ids &= resolved
+        else:
+            call_ids = resolved
+    if call_ids is None:
+        return None
+    return sorted(call_ids, key=str)
+
+
+def _dense_has_scoping(filters: Optional[RetrieveFilters], call_ids: Optional[Sequence[Any]]) -> bool:
+    if call_ids is not None:
+        return True
+    if not filters:
+        return False
+    return bool(filters.date_from or filters.date_to or filters.call_tags)
+
+
+def _choose_dense_mode(estimated_rows: int, filters: Optional[RetrieveFilters],
+                       call_ids: Optional[Sequence[Any]]) -> str:
+    if estimated_rows <= 0:
+        return "exact"
+    if _dense_has_scoping(filters, call_ids):
+        if estimated_rows <= max(settings.embeddings_exact_scan_threshold, 0):
+            return "exact"
+    return "ann"
+
+
+# --------------------------------------------------------------------------- filters -> bitmap
+def _filter_spec(store: DenseStore, filters: Optional[RetrieveFilters],
+                 call_ids: Optional[Sequence[Any]]) -> Dict[str, Any]:
+    """_build_filter_clause (app/retrieve.py:93-120) as store codes: call slots, dates, tag mask."""
+    date_from = (filters.date_from or None) if filters else None
+    date_to = (filters.date_to or None) if filters else None
+    tags = list(filters.call_tags) if (filters and filters.call_tags) else None
+    slots = None
+    if call_ids is not None:
+        slots = []
+        for c in call_ids:
+            s = store.slot_of_call(c)
+            if s is None and store.synthetic is not None and isinstance(c, (int, np.integer)):
+                s = int(c)          # synthetic stores: call id == slot number
+            if s is not None:
+                slots.append(s)
+    return dict(call_slots=slots, date_from=date_from, date_to=date_to,
+                tag_mask=None if tags is None else store.bits_of_tags(tags))
+
+
+def _filter_bitmap(conn: DenseConnection, table_name: str, filters: Optional[RetrieveFilters],
+                   call_ids: Optional[Sequence[Any]]):
+    """(allow tensor or None, candidate count) for WHERE <filters> AND embedding IS NOT NULL."""
+    store = conn.store(table_name)
+    spec = _filter_spec(store, filters, call_ids)
+    key = (table_name, None if spec["call_slots"] is None else tuple(spec["call_slots"]),
+           spec["date_from"], spec["date_to"], spec["tag_mask"])
+    hit = conn._bitmaps.get(key)
+    if hit is not None:
+        return hit
+    if all(v is None for v in spec.values()):
+        result = (None, int(store.info()["n_valid"]))
+    else:
+        result = store.filter_bitmap(**spec)
+    conn._bitmaps[key] = result
+    return result
+
+
+def _estimate_dense_candidates(conn: DenseConnection, table_name: str,
+                               filters: Optional[RetrieveFilters],
+                               call_ids: Optional[Sequence[Any]]) -> int:
+    return int(_filter_bitmap(conn, table_name, filters, call_ids)[1])
+
+
+# --------------------------------------------------------------------------- dense lanes
+def _rows_from_hits(store: DenseStore, ids: np.ndarray, scores: np.ndarray) -> List[Dict[str, Any]]:
+    out: List[Dict[str, Any]] = []
+    if len(ids) == 0:
+        return out
+    cols = store.host_columns()
+    pos = np.searchsorted(cols["ids"], ids)
+    for i, sc, p in zip(ids.tolist(), scores.tolist(), pos.tolist()):
+        slot = int(cols["call_slot"][p])
+        call_id = store.call_ids_by_slot[slot] if slot < len(store.call_ids_by_slot) else slot
+        row = {store.key_field: i, "call_id": call_id}
+        row.update(store.payload.get(i, {}))
+        row["score"] = sc
+        out.append(row)
+    return out
+
+
+def _fetch_dense(conn: DenseConnection, table_name: str, query_embedding, filters, call_ids,
+                 mode: str, limit: int) -> List[Dict[str, Any]]:
+    store = conn.store(table_name)
+    if limit <= 0:
+        return []
+    q = _query_vector(query_embedding)
+    want = max(1, int(settings.embeddings_dim))
+    if q.shape[0] != want or q.shape[0] != store.dim:
+        raise DenseEngineError(f"expected {want} dimensions, not {q.shape[0]}")
+    allow, count = _filter_bitmap(conn, table_name, filters, call_ids)
+    if count <= 0:
+        return []
+    # mode "ann" permits the approximate lane (reference: HNSW ef_search, app/retrieve.py:291-298);
+    # a single query is answered exactly by the HBM-bound scan whenever fp32 rows are resident.
+    use_batch = (mode == "ann" and store.has_bf16 and
+                 (not store.has_fp32 or settings.cadence_gpu_ann_min_batch <= 1))
+    if use_batch:
+        ids, scores, n = store.search_batch(q, limit, allow)
+    else:
+        ids, scores, n = store.search_exact(q, limit, allow)
+    m = int(n[0])
+    return _rows_from_hits(store, ids[0, :m], scores[0, :m])
+
+
+def _fetch_chunks_dense(conn: DenseConnection, query_embedding, filters: Optional[RetrieveFilters],
+                        call_ids: Optional[Sequence[Any]], mode: str, limit: int) -> List[Dict[str, Any]]:
+    return _fetch_dense(conn, "chunks", query_embedding, filters, call_ids, mode, limit)
+
+
+def _fetch_artifacts_dense(conn: DenseConnection, query_embedding, filters: Optional[RetrieveFilters],
+                           call_ids: Optional[Sequence[Any]], mode: str, limit: int) -> List[Dict[str, Any]]:
+    return _fetch_dense(conn, "artifact_chunks", query_embedding, filters, call_ids, mode, limit)
+
+
+def fetch_dense_batch(conn: DenseConnection, table_name: str, queries, filters, call_ids, mode: str,
+                      limit: int):
+    """Batched form (nq queries at once; not in the reference, which embeds one query per
+    request): returns (ids[nq,limit], scores[nq,limit], n[nq]).  mode "ann" with at least
+    ``cadence_gpu_ann_min_batch`` queries runs on the tcgen05 lane."""
+    store = conn.store(table_name)
+    allow, count = _filter_bitmap(conn, table_name, filters, call_ids)
+    nq = int(queries.shape[0])
+    if mode == "ann" and store.has_bf16 and (nq >= settings.cadence_gpu_ann_min_batch or not store.has_fp32):
+        return store.search_batch(queries, limit, allow)
+    return store.search_exact(queries, limit, allow)
+
+
+# --------------------------------------------------------------------------- tech_tokens lane
+def _fetch_tech(conn: DenseConnection, table_name: str, tokens: Sequence[str], filters, call_ids,
+                limit: int) -> List[Dict[str, Any]]:
+    if not tokens:
+        return []
+    index = conn.engine.tech_indexes.get(table_name)
+    if index is None:
+        return []
+    store = conn.store(table_name)
+    # the tech lane's WHERE has no `embedding IS NOT NULL` term (app/retrieve.py:195-208), so the
+    # predicate is evaluated on the host columns of the posting rows, not through the K6 bitmap
+    spec = _filter_spec(store, filters, call_ids)
+    rows = index.query(tokens, store.host_columns(), limit, **spec)
+    cols = store.host_columns()
+    out = []
+    for p in rows.tolist():
+        i = int(cols["ids"][p])
+        slot = int(cols["call_slot"][p])
+        call_id = store.call_ids_by_slot[slot] if slot < len(store.call_ids_by_slot) else slot
+        row = {store.key_field: i, "call_id": call_id}
+        row.update(store.payload.get(i, {}))
+        out.append(row)
+    return out
+
+
+def _fetch_chunks_tech(conn, tokens, filters, call_ids, limit):
+    return _fetch_tech(conn, "chunks", tokens, filters, call_ids, limit)
+
+
+def _fetch_artifacts_tech(conn, tokens, filters, call_ids, limit):
+    return _fetch_tech(conn, "artifact_chunks", tokens, filters, call_ids, limit)
+
+
+# --------------------------------------------------------------------------- RRF (K5)
+def _rrf_merge(lanes: Mapping[str, Sequence[Mapping[str, Any]]], key_field: str,
+               k: int = DEFAULT_RRF_K) -> List[Tuple[Dict[str, Any], Set[str], float]]:
+    """Bit-exact GPU restatement of app/retrieve.py:245-260.  Keys must be integer ids
+    (chunk_id / artifact_chunk_id are BIGSERIAL)."""
+    names = list(lanes.keys())
+    if not names:
+        return []
+    items: Dict[int, Mapping[str, Any]] = {}
+    flat: List[int] = []
+    offsets = [0]
+    for name in names:
+        for row in lanes[name]:
+            key = int(row[key_field])
+            items.setdefault(key, row)
+            flat.append(key)
+        offsets.append(len(flat))
+    if not flat:
+        return []
+    if len(flat) > _ffi.CDR_RRF_MAX_ITEMS:
+        raise DenseEngineError(f"rrf: {len(flat)} lane items exceed {_ffi.CDR_RRF_MAX_ITEMS}")
+    ids, scores, masks, n = rrf_merge_batch(np.asarray(flat, dtype=np.int64),
+                                            np.asarray(offsets, dtype=np.int32), 1, len(names), k,
+                                            max_out=len(flat))
+    out = []
+    for i in range(int(n[0])):
+        key = int(ids[0, i])
+        hit = {names[l] for l in range(len(names)) if (int(masks[0, i]) >> l) & 1}
+        out.append((items[key], hit, float(scores[0, i])))
+    return out
+
+
+def rrf_merge_batch(lane_ids: np.ndarray, lane_offsets: np.ndarray, nq: int, n_lanes: int, k: int,
+                    max_out: int):
+    """Host-buffer K5 call for nq queries: see cdr_rrf_merge_host in include/cadence_dense.h."""
+    import torch
+    _ffi.require_device()
+    lane_ids = np.ascontiguousarray(lane_ids, dtype=np.int64)
+    lane_offsets = np.ascontiguousarray(lane_offsets, dtype=np.int32)
+    assert lane_offsets.shape[0] == nq * n_lanes + 1
+    out_ids = np.empty((nq, max_out), dtype=np.int64)
+    out_sc = np.empty((nq, max_out), dtype=np.float64)
+    out_mask = np.empty((nq, max_out), dtype=np.uint32)
+    out_n = np.empty((nq,), dtype=np.int32)
+    with torch.cuda.device(settings.cadence_gpu_device):
+        _ffi.check(_ffi.lib().cdr_rrf_merge_host(_ffi.ptr(lane_ids), _ffi.ptr(lane_offsets), nq, n_lanes, k,
+                                                 max_out, _ffi.ptr(out_ids), _ffi.ptr(out_sc),
+                                                 _ffi.ptr(out_mask), _ffi.ptr(out_n), _ffi.stream_ptr()),
+                   "cdr_rrf_merge_host")
+    return out_ids, out_sc, out_mask, out_n
+
+
+# --------------------------------------------------------------------------- ids_only retrieve
+def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilters] = None,
+                 bm25_chunks: Sequence[Mapping[str, Any]] = (),
+                 bm25_artifacts: Sequence[Mapping[str, Any]] = (), debug: bool = False) -> Dict[str, Any]:
+    """The ``return_style == "ids_only"`` flow of retrieve_evidence (app/retrieve.py:392-573) over
+    the GPU engine.  The BM25 lane is out of scope (pg_search); its ranked rows are accepted as an
+    opaque input lane, exactly where the reference feeds them into _rrf_merge."""
+    query = query.strip()
+    if not query:
+        return {"retrieved_ids": []}
+    tech_tokens = extract_tech_tokens(query)
+    dense_enabled = embeddings_enabled()
+    dense_error: Optional[str] = None
+    dense_model_id: Optional[str] = None
+    query_embedding: Optional[str] = None
+    if dense_enabled:
+        try:
+            embedded = embed_texts([query])
+            dense_model_id = embedded.model
+            query_embedding = _vector_literal(embedded.vectors[0])
+        except EmbeddingClientError as exc:
+            dense_enabled = False
+            dense_error = str(exc)
+
+    tech_chunks: List[Dict[str, Any]] = []
+    tech_artifacts: List[Dict[str, Any]] = []
+    dense_chunks: List[Dict[str, Any]] = []
+    dense_artifacts: List[Dict[str, Any]] = []
+    modes: Dict[str, Optional[str]] = {"chunks": None, "artifact_chunks": None}
+    candidates = {"chunks": 0, "artifact_chunks": 0}
+    with engine.connect() as conn:
+        call_ids = _resolve_call_ids(conn, filters)
+        if "chunks" in engine.stores:
+            tech_chunks = _fetch_chunks_tech(conn, tech_tokens, filters, call_ids, DEFAULT_TECH_TOPK)
+        if "artifact_chunks" in engine.stores:
+            tech_artifacts = _fetch_artifacts_tech(conn, tech_tokens, filters, call_ids, DEFAULT_TECH_TOPK)
+        if dense_enabled and query_embedding is not None:
+            try:
+                for table, fetch, topk, sink in (
+                        ("chunks", _fetch_chunks_dense, DEFAULT_DENSE_CHUNK_TOPK, dense_chunks),
+                        ("artifact_chunks", _fetch_artifacts_dense, DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK, dense_artifacts)):
+                    if table not in engine.stores:
+                        continue
+                    candidates[table] = _estimate_dense_candidates(conn, table, filters, call_ids)
+                    modes[table] = _choose_dense_mode(candidates[table], filters, call_ids)
+                    sink.extend(fetch(conn, query_embedding, filters, call_ids, modes[table], topk))
+            except DenseEngineError as exc:   # fail open to lexical-only, like EmbeddingClientError
+                dense_enabled = False
+                dense_error = str(exc)
+                dense_chunks.clear()
+                dense_artifacts.clear()
+
+    chunk_lanes: Dict[str, Sequence[Mapping[str, Any]]] = {"bm25": list(bm25_chunks), "tech_tokens": tech_chunks}
+    artifact_lanes: Dict[str, Sequence[Mapping[str, Any]]] = {"bm25": list(bm25_artifacts), "tech_tokens": tech_artifacts}
+    if dense_enabled:
+        chunk_lanes["dense"] = dense_chunks
+        artifact_lanes["dense"] = dense_artifacts
+    chunk_ranked = _rrf_merge(chunk_lanes, "chunk_id")
+    artifact_ranked = _rrf_merge(artifact_lanes, "artifact_chunk_id")
+
+    combined: List[Tuple[str, int, float]] = []
+    for row, _lanes, score in artifact_ranked:
+        combined.append(("artifact_chunk", row["artifact_chunk_id"], score))
+    for row, _lanes, score in chunk_ranked:
+        combined.append(("chunk", row["chunk_id"], score))
+    kind_order = {"artifact_chunk": 0, "chunk": 1}
+    combined.sort(key=lambda item: (-item[2], kind_order[item[0]], item[1]))
+    response: Dict[str, Any] = {"retrieved_ids": [f"{kind}:{item_id}" for kind, item_id, _ in combined]}
+    if debug:
+        chunk_dbg = {"bm25": _build_debug_lane(list(bm25_chunks), "chunk_id"),
+                     "tech_tokens": _build_debug_lane(tech_chunks, "chunk_id")}
+        art_dbg = {"bm25": _build_debug_lane(list(bm25_artifacts), "artifact_chunk_id"),
+                   "tech_tokens": _build_debug_lane(tech_artifacts, "artifact_chunk_id")}
+        if dense_enabled:
+            chunk_dbg["dense"] = _build_debug_lane(dense_chunks, "chunk_id")
+            art_dbg["dense"] = _build_debug_lane(dense_artifacts, "artifact_chunk_id")
+        response["debug"] = {
+            "lanes": {"chunks": chunk_dbg, "artifacts": art_dbg},
+            "dense": {"enabled": dense_enabled, "model_id": dense_model_id, "error": dense_error,
+                      "modes": dict(modes), "candidate_rows": dict(candidates)},
+            "fused": {"chunks": [(r["chunk_id"], sorted(l), s) for r, l, s in chunk_ranked],
+                      "artifacts": [(r["artifact_chunk_id"], sorted(l), s) for r, l, s in artifact_ranked]},
+        }
+    return response

@@ -1,0 +1,314 @@
+"""Resident corpus store -- host-side owner of one ``cdr_store`` (one per reference table).
+
+Replaces what the reference keeps in Postgres for the dense lane: the ``embedding vector(1024)``
+column and the filter columns of ``chunks`` / ``artifact_chunks``
+(alembic/versions/0001_initial_schema.py:78-87, 0006_add_artifact_chunks.py:22-33), plus the
+dictionaries that turn call UUIDs and tag strings into the codes the device columns hold.
+"""
+from __future__ import annotations
+
+import ctypes
+from datetime import datetime, timezone
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import DenseEngineError
+
+_EPOCH = datetime(1970, 1, 1, tzinfo=timezone.utc)
+
+SYNTH_CORPUS_SEED = 20260209     # BASELINE.md "Data"
+SYNTH_QUERY_SEED = 20260210
+SYNTH_ROWS_PER_CALL = 200
+SYNTH_T0_US = 1_700_000_000_000_000
+SYNTH_CALL_PERIOD_US = 3_600_000_000
+
+
+def to_micros(value) -> int:
+    """datetime (naive => UTC, like a timestamptz session in UTC) or int microseconds -> int."""
+    if isinstance(value, datetime):
+        if value.tzinfo is None:
+            value = value.replace(tzinfo=timezone.utc)
+        delta = value - _EPOCH
+        return (delta.days * 86400 + delta.seconds) * 1_000_000 + delta.microseconds
+    return int(value)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def synth_rows_device(seed: int, first_row: int, n: int, dim: int, device: Optional[int] = None):
+    """[n, dim] fp32 CUDA tensor of synthetic rows (global rows first_row..) -- used for queries."""
+    torch = _torch()
+    _ffi.require_device()
+    from .config import settings
+    dev = settings.cadence_gpu_device if device is None else device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, dim), dtype=torch.float32, device=f"cuda:{dev}")
+        _ffi.check(_ffi.lib().cdr_synth_rows(_ffi.ptr(out), ctypes.c_uint64(seed), first_row, n, dim,
+                                             _ffi.stream_ptr()), "cdr_synth_rows")
+    return out
+
+
+class DenseStore:
+    """One table's resident embeddings + filter columns on one GPU."""
+
+    def __init__(self, table_name: str, capacity_rows: int, dim: Optional[int] = None,
+                 device: Optional[int] = None, fp32: bool = True, bf16: bool = True,
+                 key_field: Optional[str] = None):
+        from .config import settings
+        _ffi.require_device()
+        self.table_name = table_name
+        self.key_field = key_field or ("artifact_chunk_id" if table_name == "artifact_chunks" else "chunk_id")
+        self.dim = int(dim or max(1, int(settings.embeddings_dim)))
+        self.device = settings.cadence_gpu_device if device is None else int(device)
+        self.flags = (_ffi.CDR_STORE_FP32 if fp32 else 0) | (_ffi.CDR_STORE_BF16 if bf16 else 0)
+        self.capacity = int(capacity_rows)
+        self._h = ctypes.c_void_p()
+        _ffi.check(_ffi.lib().cdr_store_create(ctypes.byref(self._h), self.device, self.capacity,
+                                               self.dim, self.flags), "cdr_store_create")
+        self.finalized = False
+        # dictionaries (host): call UUID -> slot, tag -> bit
+        self.call_slots: Dict[Any, int] = {}
+        self.call_ids_by_slot: List[Any] = []
+        self.tag_bits: Dict[str, int] = {}
+        # optional payload columns returned with each hit (speaker, text, ... as in the SQL SELECT)
+        self.payload: Dict[int, Dict[str, Any]] = {}
+        self.synthetic = None   # (seed, first_row) when filled by the on-device generator
+        self._host_cols: Optional[Dict[str, np.ndarray]] = None
+
+    # ------------------------------------------------------------------ lifecycle
+    @property
+    def handle(self) -> ctypes.c_void_p:
+        if not self._h:
+            raise DenseEngineError("store destroyed", _ffi.CDR_ERR_STATE)
+        return self._h
+
+    def close(self) -> None:
+        if self._h:
+            _ffi.lib().cdr_store_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        torch = _torch()
+        return _ffi.stream_ptr(torch.cuda.current_stream(self.device))
+
+    # ------------------------------------------------------------------ dictionaries
+    def slot_of_call(self, call_id, create: bool = False) -> Optional[int]:
+        slot = self.call_slots.get(call_id)
+        if slot is None and create:
+            slot = len(self.call_ids_by_slot)
+            self.call_slots[call_id] = slot
+            self.call_ids_by_slot.append(call_id)
+        return slot
+
+    def bits_of_tags(self, tags: Optional[Iterable[str]], create: bool = False) -> int:
+        mask = 0
+        for tag in tags or ():
+            bit = self.tag_bits.get(tag)
+            if bit is None and create:
+                if len(self.tag_bits) >= 64:
+                    raise DenseEngineError("tag dictionary is limited to 64 distinct tags", _ffi.CDR_ERR_UNSUPPORTED)
+                bit = len(self.tag_bits)
+                self.tag_bits[tag] = bit
+            if bit is not None:
+                mask |= 1 << bit
+        return mask
+
+    # ------------------------------------------------------------------ ingest
+    def append(self, embeddings, ids: Sequence[int], call_ids: Optional[Sequence[Any]] = None,
+               call_started_at: Optional[Sequence[Any]] = None,
+               call_tags: Optional[Sequence[Optional[Iterable[str]]]] = None,
+               valid: Optional[Sequence[bool]] = None,
+               payload: Optional[Sequence[Dict[str, Any]]] = None) -> None:
+        """Append rows (the counterpart of embedding_pipeline._update_embeddings,
+        app/embedding_pipeline.py:149-168).  ``embeddings``: [n, dim] float32 (numpy, torch CPU or
+        torch CUDA); rows with ``valid[i] == False`` model ``embedding IS NULL``."""
+        torch = _torch()
+        n = len(ids)
+        if n == 0:
+            return
+        is_dev = hasattr(embeddings, "is_cuda") and embeddings.is_cuda
+        if is_dev:
+            emb = embeddings.to(dtype=torch.float32).contiguous()
+        else:
+            emb = np.ascontiguousarray(np.asarray(embeddings, dtype=np.float32))
+        if tuple(emb.shape) != (n, self.dim):
+            raise DenseEngineError(f"embeddings shape {tuple(emb.shape)} != ({n}, {self.dim})")
+        ids_np = np.ascontiguousarray(np.asarray(ids, dtype=np.int64))
+        slots = np.zeros(n, dtype=np.int32)
+        if call_ids is not None:
+            slots = np.fromiter((self.slot_of_call(c, create=True) for c in call_ids), dtype=np.int32, count=n)
+        started = np.zeros(n, dtype=np.int64)
+        if call_started_at is not None:
+            started = np.fromiter((to_micros(t) for t in call_started_at), dtype=np.int64, count=n)
+        tags = np.zeros(n, dtype=np.uint64)
+        if call_tags is not None:
+            tags = np.fromiter((self.bits_of_tags(t, create=True) for t in call_tags), dtype=np.uint64, count=n)
+        valid_np = None
+        if valid is not None:
+            valid_np = np.ascontiguousarray(np.asarray(valid, dtype=np.uint8))
+
+        def dev(a):
+            return torch.from_numpy(a).to(f"cuda:{self.device}") if is_dev else a
+
+        cols = [dev(ids_np), dev(slots), dev(started), dev(tags.view(np.int64)), None if valid_np is None else dev(valid_np)]
+        with torch.cuda.device(self.device):
+            _ffi.check(_ffi.lib().cdr_store_append(
+                self.handle, _ffi.ptr(emb), _ffi.ptr(cols[0]), _ffi.ptr(cols[1]), _ffi.ptr(cols[2]),
+                _ffi.ptr(cols[3]), _ffi.ptr(cols[4]), n, 1 if is_dev else 0, self._stream()), "cdr_store_append")
+            if is_dev:
+                torch.cuda.current_stream(self.device).synchronize()
+        if payload is not None:
+            for i, row in zip(ids_np.tolist(), payload):
+                self.payload[i] = row
+
+    def append_synthetic(self, n: int, *, seed: int = SYNTH_CORPUS_SEED, first_row: int = 0,
+                         id_base: int = 1, rows_per_call: int = SYNTH_ROWS_PER_CALL,
+                         t0_us: int = SYNTH_T0_US, call_period_us: int = SYNTH_CALL_PERIOD_US) -> None:
+        """Fill with rows first_row..first_row+n-1 of the synthetic corpus, generated on device
+        (spec: oracle/synth_ref.c; BASELINE.md "Data")."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            _ffi.check(_ffi.lib().cdr_store_append_synthetic(
+                self.handle, ctypes.c_uint64(seed), first_row, n, id_base, rows_per_call, t0_us,
+                call_period_us, self._stream()), "cdr_store_append_synthetic")
+        self.synthetic = dict(seed=seed, first_row=first_row, id_base=id_base, rows_per_call=rows_per_call,
+                              t0_us=t0_us, call_period_us=call_period_us)
+        # synthetic call ids are the slot numbers themselves; 16 synthetic tags "tag0".."tag15"
+        if not self.tag_bits:
+            self.tag_bits = {f"tag{i}": i for i in range(16)}
+
+    def finalize(self) -> None:
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            _ffi.check(_ffi.lib().cdr_store_finalize(self.handle, self._stream()), "cdr_store_finalize")
+        self.finalized = True
+
+    # ------------------------------------------------------------------ introspection
+    def info(self) -> Dict[str, int]:
+        rows, dim, flags, nv, dev = (ctypes.c_int64(), ctypes.c_int32(), ctypes.c_uint32(),
+                                     ctypes.c_int64(), ctypes.c_int32())
+        _ffi.check(_ffi.lib().cdr_store_info(self.handle, ctypes.byref(rows), ctypes.byref(dim),
+                                             ctypes.byref(flags), ctypes.byref(nv), ctypes.byref(dev)))
+        return dict(rows=rows.value, dim=dim.value, flags=flags.value, n_valid=nv.value, device=dev.value)
+
+    @property
+    def rows(self) -> int:
+        return self.info()["rows"]
+
+    @property
+    def has_fp32(self) -> bool:
+        return bool(self.flags & _ffi.CDR_STORE_FP32)
+
+    @property
+    def has_bf16(self) -> bool:
+        return bool(self.flags & _ffi.CDR_STORE_BF16)
+
+    def read_rows(self, first_row: int, n: int, what: Sequence[str] = ("f32",)) -> Dict[str, np.ndarray]:
+        """Copy resident columns back to the host (tests / snapshots)."""
+        out: Dict[str, np.ndarray] = {}
+        spec = {"f32": ((n, self.dim), np.float32), "bf16": ((n, self.dim), np.uint16), "ids": ((n,), np.int64),
+                "call_slot": ((n,), np.int32), "started_at": ((n,), np.int64), "tag_bits": ((n,), np.uint64),
+                "inv_norm": ((n,), np.float32)}
+        order = ["f32", "bf16", "ids", "call_slot", "started_at", "tag_bits", "inv_norm"]
+        ptrs = []
+        for name in order:
+            if name in what:
+                shape, dt = spec[name]
+                out[name] = np.empty(shape, dtype=dt)
+                ptrs.append(_ffi.ptr(out[name]))
+            else:
+                ptrs.append(None)
+        _ffi.check(_ffi.lib().cdr_store_read_rows(self.handle, first_row, n, *ptrs), "cdr_store_read_rows")
+        return out
+
+    def host_columns(self) -> Dict[str, np.ndarray]:
+        """ids / call_slot / started_at / tag_bits of all rows on the host (cached; lexical lane)."""
+        if self._host_cols is None:
+            self._host_cols = self.read_rows(0, self.rows, ("ids", "call_slot", "started_at", "tag_bits"))
+        return self._host_cols
+
+    # ------------------------------------------------------------------ filters (K6)
+    def filter_bitmap(self, *, call_slots: Optional[Sequence[int]] = None, date_from=None, date_to=None,
+                      tag_mask: Optional[int] = None):
+        """Build the allow-bitmap for a WHERE clause and count its rows.
+
+        call_slots: None = unscoped; [] = ``call_ids == []`` (matches nothing).
+        tag_mask: None = no tag filter; 0 = a tag filter whose tags are all unknown (matches nothing).
+        Returns (allow: torch.int32 CUDA tensor [ceil(rows/32)], count: int)."""
+        torch = _torch()
+        rows = self.rows
+        words = (rows + 31) // 32
+        n_slots = 0
+        bm = None
+        if call_slots is not None:
+            n_slots = max(len(self.call_ids_by_slot), (max(call_slots) + 1) if len(call_slots) else 0, 1)
+            if self.synthetic is not None:
+                n_slots = max(n_slots, (self.synthetic["first_row"] + rows) // self.synthetic["rows_per_call"] + 1)
+            bm = np.zeros((n_slots + 31) // 32, dtype=np.uint32)
+            for s in call_slots:
+                if 0 <= s < n_slots:
+                    bm[s >> 5] |= np.uint32(1 << (s & 31))
+        count = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            allow = torch.empty(max(words, 1), dtype=torch.int32, device=f"cuda:{self.device}")
+            _ffi.check(_ffi.lib().cdr_filter_build(
+                self.handle, _ffi.ptr(bm), n_slots,
+                0 if date_from is None else 1, 0 if date_from is None else to_micros(date_from),
+                0 if date_to is None else 1, 0 if date_to is None else to_micros(date_to),
+                0 if tag_mask is None else 1, ctypes.c_uint64(tag_mask or 0),
+                _ffi.ptr(allow), ctypes.byref(count), self._stream()), "cdr_filter_build")
+        return allow, int(count.value)
+
+    # ------------------------------------------------------------------ search
+    def _search(self, fn_name: str, queries, k: int, allow) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        torch = _torch()
+        on_dev = hasattr(queries, "is_cuda") and queries.is_cuda
+        if on_dev:
+            q = queries.to(dtype=torch.float32).contiguous()
+            if q.dim() == 1:
+                q = q.unsqueeze(0)
+        else:
+            q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+            if q.ndim == 1:
+                q = q[None, :]
+        nq = int(q.shape[0])
+        if int(q.shape[1]) != self.dim:
+            raise DenseEngineError(f"query dim {int(q.shape[1])} != store dim {self.dim}")
+        with torch.cuda.device(self.device):
+            if on_dev:
+                dev = f"cuda:{self.device}"
+                sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
+                ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+                fn = getattr(_ffi.lib(), fn_name)
+                _ffi.check(fn(self.handle, _ffi.ptr(q), nq, k, _ffi.ptr(allow), _ffi.ptr(sc), _ffi.ptr(ids),
+                              _ffi.ptr(cnt), self._stream()), fn_name)
+                return ids, sc, cnt
+            sc = np.empty((nq, k), dtype=np.float64)
+            ids = np.empty((nq, k), dtype=np.int64)
+            cnt = np.empty((nq,), dtype=np.int32)
+            fn = getattr(_ffi.lib(), fn_name + "_host")
+            _ffi.check(fn(self.handle, _ffi.ptr(q), nq, k, _ffi.ptr(allow), _ffi.ptr(sc), _ffi.ptr(ids),
+                          _ffi.ptr(cnt), self._stream()), fn_name + "_host")
+            return ids, sc, cnt
+
+    def search_exact(self, queries, k: int, allow=None):
+        """mode="exact": fp32 cosine scan (K1) + fp64 re-score.  Host queries -> host results
+        (numpy, through the *_host C entry point: H2D + kernels + D2H + sync); CUDA tensors ->
+        CUDA tensors (asynchronous on the current stream).  Returns (ids[nq,k], scores[nq,k], n[nq])."""
+        return self._search("cdr_search_exact_f32", queries, k, allow)
+
+    def search_batch(self, queries, k: int, allow=None):
+        """mode="ann" served by the batched bf16 tensor-core lane (K2) + exact re-score."""
+        return self._search("cdr_search_batch_bf16", queries, k, allow)

@@ -1,0 +1,194 @@
+/*
+ * cadence_dense.h -- C ABI of the B200-native dense-retrieval engine (libcadence_dense.so).
+ *
+ * This is the drop-in boundary for cadence-rag's /retrieve dense lane.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference repo).  The
+ * reference reaches its dense lane through SQL sent to Postgres+pgvector; the binding a
+ * maintainer adds is the ctypes stub shown in INTEGRATION.md (cadence_rag_b200/_ffi.py is
+ * that stub, shipped).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns int32 status: CDR_OK (0) or a negative CDR_ERR_* code; a
+ *     human-readable message for the calling thread is available from cdr_last_error().
+ *   - "dev" pointers are CUDA device pointers on the store's device; "host" pointers are
+ *     ordinary (ideally pinned) host memory.  The caller owns every query/output buffer.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous on that stream unless the name ends in `_host` (those synchronise).
+ *   - rows are addressed by their position in the store ("row"); ids are the reference's
+ *     BIGSERIAL chunk_id / artifact_chunk_id values (alembic/versions/0001_initial_schema.py:78,
+ *     0006_add_artifact_chunks.py:22) and MUST be appended in strictly increasing order
+ *     (the order `SELECT ... ORDER BY chunk_id` yields), so that "ties broken by chunk_id"
+ *     equals "ties broken by row".
+ *   - ordering of every dense result: score descending, NaN scores last (a zero-norm vector
+ *     gives a NaN cosine distance in pgvector, which PostgreSQL sorts last), ties by id
+ *     ascending.  Fewer survivors than k => short list (SQL LIMIT semantics).
+ */
+#ifndef CADENCE_DENSE_H
+#define CADENCE_DENSE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDR_ABI_VERSION 1
+
+/* status codes */
+#define CDR_OK                 0
+#define CDR_ERR_INVALID       -1   /* bad argument */
+#define CDR_ERR_CUDA          -2   /* CUDA runtime/driver error (see cdr_last_error) */
+#define CDR_ERR_OOM           -3   /* device allocation failed / capacity exceeded */
+#define CDR_ERR_UNSORTED_IDS  -4   /* ids not strictly increasing */
+#define CDR_ERR_STATE         -5   /* store not in the right state for the call */
+#define CDR_ERR_UNSUPPORTED   -6   /* dim / k / precision combination not built */
+#define CDR_ERR_NO_DEVICE     -7   /* no CUDA device: there is NO CPU fallback */
+
+/* store flags: which copies of the embeddings stay resident */
+#define CDR_STORE_FP32  1u   /* fp32 rows (exact lane, fp64 re-score) */
+#define CDR_STORE_BF16  2u   /* bf16 rows, L2-normalised (batched tensor-core lane) */
+
+#define CDR_MAX_K 248        /* largest LIMIT served by the fused top-k paths */
+
+typedef struct cdr_store cdr_store;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int32_t     cdr_abi_version(void);
+const char *cdr_last_error(void);                 /* thread-local, never NULL */
+int32_t     cdr_device_count(int32_t *out_count); /* CDR_ERR_NO_DEVICE when none */
+
+/* ---- resident corpus store: one per reference table ("chunks", "artifact_chunks") ----------
+ * Replaces the `embedding vector(1024)` column + its filter columns
+ * (alembic/versions/0001_initial_schema.py:78-87, 0006_add_artifact_chunks.py:22-33) as read by
+ * app/retrieve.py:339-351 / 374-386. */
+int32_t cdr_store_create(cdr_store **out, int32_t device, int64_t capacity_rows, int32_t dim,
+                         uint32_t flags);
+int32_t cdr_store_destroy(cdr_store *s);
+
+/* Append n rows.  Replaces app/embedding_pipeline.py:149-168 (_update_embeddings: one
+ * `UPDATE ... SET embedding = CAST(:e AS vector(D))` per row).  rows_f32 is [n, dim] row-major.
+ * valid_u8 (nullable) marks rows whose embedding IS NOT NULL (1) / IS NULL (0; row content
+ * ignored).  call_slot is the dictionary code of call_id; started_at_us is call_started_at in
+ * microseconds since the Unix epoch; tag_bits is the per-call tag dictionary mask.
+ * is_device != 0 => all pointers are device pointers. */
+int32_t cdr_store_append(cdr_store *s, const float *rows_f32, const int64_t *ids,
+                         const int32_t *call_slot, const int64_t *started_at_us,
+                         const uint64_t *tag_bits, const uint8_t *valid_u8, int64_t n,
+                         int32_t is_device, void *stream);
+
+/* Append n synthetic rows generated on the device (global rows first_row..first_row+n-1 of the
+ * counter-based corpus specified in oracle/synth_ref.c).  id = id_base + global
+ * row, call_slot = global_row / rows_per_call, started_at = t0_us + call_slot * call_period_us,
+ * tag_bits = two Philox-chosen tags of 16 per call. */
+int32_t cdr_store_append_synthetic(cdr_store *s, uint64_t seed, int64_t first_row, int64_t n,
+                                   int64_t id_base, int32_t rows_per_call, int64_t t0_us,
+                                   int64_t call_period_us, void *stream);
+
+/* Seal the store: checks id monotonicity, builds the valid bitmap / search workspaces. */
+int32_t cdr_store_finalize(cdr_store *s, void *stream);
+
+/* rows, dim, flags, n_valid (rows with embedding IS NOT NULL), device */
+int32_t cdr_store_info(const cdr_store *s, int64_t *rows, int32_t *dim, uint32_t *flags,
+                       int64_t *n_valid, int32_t *device);
+
+/* Copy resident data back to the host (tests, snapshots).  Any out pointer may be NULL. */
+int32_t cdr_store_read_rows(cdr_store *s, int64_t first_row, int64_t n, float *out_f32_host,
+                            uint16_t *out_bf16_host, int64_t *out_ids_host,
+                            int32_t *out_call_slot_host, int64_t *out_started_at_host,
+                            uint64_t *out_tag_bits_host, float *out_inv_norm_host);
+
+/* ---- synthetic queries / rows into caller memory ---------------------------------------- */
+int32_t cdr_synth_rows(float *out_dev, uint64_t seed, int64_t first_row, int64_t n, int32_t dim,
+                       void *stream);
+
+/* ---- K6 filter bitmap --------------------------------------------------------------------
+ * Replaces app/retrieve.py:93-120 (_build_filter_clause) evaluated per row inside Postgres, and
+ * app/retrieve.py:303-323 (_estimate_dense_candidates: exact COUNT(*) ... AND embedding IS NOT
+ * NULL) via out_count.  Predicate per row:
+ *   valid AND (call_slot_bitmap == NULL OR bit(call_slot))            -- call_id = ANY(:call_ids)
+ *         AND (!has_date_from OR started_at >= date_from_us)          -- call_started_at >= :date_from
+ *         AND (!has_date_to   OR started_at <= date_to_us)            -- call_started_at <= :date_to
+ *         AND (!has_tag_filter OR (tag_bits & tag_any) != 0)          -- c.tags && :call_tags
+ * call_slot_bitmap_host: nullable host bitmap over call slots (n_call_slots bits, uint32 words);
+ * a non-NULL all-zero bitmap is `call_ids == []` (matches nothing).
+ * out_allow_dev: uint32[ceil(rows/32)] device bitmap, bit r => row r passes.
+ * out_count_host: number of passing rows (the call synchronises the stream to return it). */
+int32_t cdr_filter_build(cdr_store *s, const uint32_t *call_slot_bitmap_host,
+                         int64_t n_call_slots, int32_t has_date_from, int64_t date_from_us,
+                         int32_t has_date_to, int64_t date_to_us, int32_t has_tag_filter,
+                         uint64_t tag_any, uint32_t *out_allow_dev, int64_t *out_count_host,
+                         void *stream);
+
+/* ---- K1 + K3/K4: exact fp32 cosine scan with fused top-k, fp64 re-score -------------------
+ * Replaces the SQL at app/retrieve.py:339-351 (_fetch_chunks_dense) / 374-386
+ * (_fetch_artifacts_dense) in mode "exact":
+ *   SELECT id, 1 - (embedding <=> :q) AS score ... WHERE <filters> AND embedding IS NOT NULL
+ *   ORDER BY embedding <=> :q LIMIT :k
+ * q_dev: [nq, dim] fp32.  allow_dev: bitmap from cdr_filter_build or NULL (all valid rows).
+ * out_score_dev f64[nq,k] (= 1 - cosine distance), out_id_dev i64[nq,k], out_n_dev i32[nq].
+ * Unused tail slots are filled with score NaN / id -1. */
+int32_t cdr_search_exact_f32(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                             const uint32_t *allow_dev, double *out_score_dev,
+                             int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
+
+/* Same call with HOST buffers: copies the queries host->device, searches, copies the results
+ * device->host and synchronises.  This is the call the reference-facing plugin makes per
+ * request (the counterpart of conn.execute(...).mappings() at app/retrieve.py:340-353). */
+int32_t cdr_search_exact_f32_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                  const uint32_t *allow_dev, double *out_score_host,
+                                  int64_t *out_id_host, int32_t *out_n_host, void *stream);
+
+/* ---- K2 + K3: batched bf16 tensor-core scan (tcgen05) with fused threshold top-k epilogue --
+ * Serves mode "ann" of app/retrieve.py:290-298 (_configure_dense_session: HNSW ef_search) by
+ * brute force on the tensor cores: the score matrix never reaches HBM; survivors are re-scored
+ * exactly (fp64 accumulate on the fp32 rows when resident, else on the bf16 rows) and ordered
+ * like the exact lane.  q_dev: [nq, dim] fp32 (converted to bf16 internally). */
+int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                              const uint32_t *allow_dev, double *out_score_dev,
+                              int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
+int32_t cdr_search_batch_bf16_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                   const uint32_t *allow_dev, double *out_score_host,
+                                   int64_t *out_id_host, int32_t *out_n_host, void *stream);
+
+/* ---- K4: k-way merge of per-shard top-k lists ---------------------------------------------
+ * Row-sharded corpora (one store per GPU): after the NCCL all-gather of every rank's
+ * [nq,k] (score,id,n) lists this merges R lists per query into the global top-k with the
+ * same ordering rule.  scores f64[R,nq,k], ids i64[R,nq,k], n i32[R,nq]. */
+int32_t cdr_topk_merge(const double *scores_dev, const int64_t *ids_dev, const int32_t *n_dev,
+                       int32_t R, int32_t nq, int32_t k, double *out_score_dev,
+                       int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
+
+/* ---- K5: reciprocal-rank fusion -------------------------------------------------------------
+ * Replaces app/retrieve.py:245-260 (_rrf_merge), bit-exact: for lanes in order (bm25,
+ * tech_tokens, dense; app/retrieve.py:537-547) and ranks from 1,
+ *   score[id] = score.get(id, 0.0) + 1.0 / (rrf_k + rank)           (IEEE fp64, no contraction)
+ * then a stable descending sort, so ties keep first-seen order.
+ * lane_ids_dev: all lanes of all queries concatenated; lane_offsets_dev: i32[nq*L + 1], lane l of
+ * query q is lane_ids[off[q*L+l] .. off[q*L+l+1]).  At most CDR_RRF_MAX_ITEMS ids per query.
+ * Outputs are [nq, max_out]: fused ids, fp64 scores, lane-hit bit masks (bit l = lane l),
+ * and out_n[nq] = number of distinct ids. */
+#define CDR_RRF_MAX_ITEMS 1024
+int32_t cdr_rrf_merge(const int64_t *lane_ids_dev, const int32_t *lane_offsets_dev, int32_t nq,
+                      int32_t L, int32_t rrf_k, int32_t max_out, int64_t *out_ids_dev,
+                      double *out_scores_dev, uint32_t *out_lane_mask_dev, int32_t *out_n_dev,
+                      void *stream);
+int32_t cdr_rrf_merge_host(const int64_t *lane_ids_host, const int32_t *lane_offsets_host,
+                           int32_t nq, int32_t L, int32_t rrf_k, int32_t max_out,
+                           int64_t *out_ids_host, double *out_scores_host,
+                           uint32_t *out_lane_mask_host, int32_t *out_n_host, void *stream);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+/* Number of this library's kernels launched by the calling process so far (bench.py's
+ * gpu_launches claim). */
+int64_t cdr_kernel_launch_count(void);
+/* Average device time (ms) of the dominant scan kernel measured with CUDA events on `stream`
+ * between cdr_prof_begin / cdr_prof_end (bench.py's roofline.achieved).  kind: 0 = K1 exact
+ * scan, 1 = K2 batched bf16. */
+int32_t cdr_prof_enable(int32_t on);
+int32_t cdr_prof_read(int32_t kind, double *out_total_ms, int64_t *out_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CADENCE_DENSE_H */

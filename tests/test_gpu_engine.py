@@ -1,0 +1,540 @@
+"""GPU tier (-m gpu): parity of the CUDA path against the CPU oracle, through the C ABI.
+
+Bars (BASELINE.md "Parity bars"): fp32 exact lane -- top-k id list identical to the fp64 oracle
+(ties by id), scores within 1e-12 relative of the fp64 oracle and within 1e-5 relative of the
+pgvector-restated fp32 oracle, whose id list must also agree except at positions whose fp64 gap
+to a neighbour is < 2e-6 relative (compared as sets); filter bitmaps / counts / RRF / merges are
+bit-exact.
+"""
+import json
+import os
+from datetime import datetime, timedelta, timezone
+from uuid import UUID
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from cadence_rag_b200 import _ffi, embeddings, retrieve  # noqa: E402
+from cadence_rag_b200._ffi import DenseEngineError  # noqa: E402
+from cadence_rag_b200.config import settings  # noqa: E402
+from cadence_rag_b200.lexical import TechTokenIndex  # noqa: E402
+from cadence_rag_b200.retrieve import DenseEngine, RetrieveFilters  # noqa: E402
+from cadence_rag_b200.store import (DenseStore, SYNTH_CALL_PERIOD_US, SYNTH_CORPUS_SEED,  # noqa: E402
+                                    SYNTH_QUERY_SEED, SYNTH_ROWS_PER_CALL, SYNTH_T0_US, synth_rows_device)
+from oracle import cpu_oracle as orc  # noqa: E402
+from oracle import ports  # noqa: E402
+
+REL_F64 = 1e-12     # GPU fp64 re-score vs oracle fp64 (summation order only)
+REL_PGV = 1e-5      # north_star: scores within 1e-5 relative of pgvector exact
+AMBIG = 2e-6        # near-tie policy
+
+
+def make_synth_store(n, dim=1024, fp32=True, bf16=True, first_row=0, name="chunks"):
+    s = DenseStore(name, n, dim=dim, device=0, fp32=fp32, bf16=bf16)
+    s.append_synthetic(n, first_row=first_row)
+    s.finalize()
+    return s
+
+
+def assert_matches_oracles(ids, scores, cnt, q, x, k, allow=None, row_ids=None):
+    """ids/scores/cnt: one query's GPU result."""
+    want_ids, want_sc = orc.exact_scan(q, x, k, ids=row_ids, allow=allow, variant=orc.VARIANT_F64)
+    m = len(want_ids)
+    assert int(cnt) == m
+    assert ids[:m].tolist() == want_ids.tolist()
+    fin = ~np.isnan(want_sc)
+    assert np.array_equal(np.isnan(scores[:m]), ~fin)
+    assert np.allclose(scores[:m][fin], want_sc[fin], rtol=REL_F64, atol=1e-15)
+    assert np.all(ids[m:] == -1)
+    # pgvector-restated fp32 order: equal outside ambiguous near-ties, scores within 1e-5 relative
+    p_ids, p_sc = orc.exact_scan(q, x, k, ids=row_ids, allow=allow, variant=orc.VARIANT_PGV32)
+    assert len(p_ids) == m
+    assert np.allclose(scores[:m][fin], p_sc[fin], rtol=REL_PGV, atol=1e-9)
+    if p_ids.tolist() != want_ids.tolist():
+        sc = want_sc
+        gaps = np.abs(np.diff(sc)) / np.maximum(np.abs(sc[:-1]), 1e-30)
+        amb = np.zeros(m, dtype=bool)
+        amb[:-1] |= gaps < AMBIG
+        amb[1:] |= gaps < AMBIG
+        amb[-1] = True   # the boundary position may swap with rank k+1
+        assert [i for i, a in zip(want_ids.tolist(), amb) if not a] == \
+               [i for i, a in zip(p_ids.tolist(), amb) if not a]
+
+
+# =================================================================== generator + store columns
+def test_generator_bit_exact_vs_oracle():
+    for seed, first, n, dim in [(SYNTH_CORPUS_SEED, 0, 257, 1024), (SYNTH_QUERY_SEED, 2**33 + 11, 64, 1024),
+                                (5, 99, 40, 256), (5, 0, 9, 2048), (9, 3, 5, 8)]:
+        got = synth_rows_device(seed, first, n, dim, device=0).cpu().numpy()
+        want = orc.synth_rows(seed, first, n, dim)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (seed, first, n, dim)
+
+
+def test_store_columns_match_spec():
+    n, first = 1000, 150
+    s = make_synth_store(n, first_row=first)
+    got = s.read_rows(0, n, ("f32", "bf16", "ids", "call_slot", "started_at", "tag_bits", "inv_norm"))
+    want = orc.synth_rows(SYNTH_CORPUS_SEED, first, n)
+    assert np.array_equal(got["f32"].view(np.uint32), want.view(np.uint32))
+    grow = np.arange(first, first + n)
+    assert np.array_equal(got["ids"], grow + 1)
+    assert np.array_equal(got["call_slot"], grow // SYNTH_ROWS_PER_CALL)
+    assert np.array_equal(got["started_at"], SYNTH_T0_US + (grow // SYNTH_ROWS_PER_CALL) * SYNTH_CALL_PERIOD_US)
+    assert got["tag_bits"].tolist() == [orc.synth_tag_bits(SYNTH_CORPUS_SEED, int(g) // SYNTH_ROWS_PER_CALL) for g in grow]
+    norms = np.linalg.norm(want.astype(np.float64), axis=1)
+    assert np.allclose(got["inv_norm"], 1.0 / norms, rtol=1e-6)
+    # bf16 copy = RN-even of the L2-normalised row
+    scaled = (want * got["inv_norm"][:, None]).astype(np.float32)
+    assert np.array_equal(got["bf16"], orc.f32_to_bf16_bits(scaled))
+    info = s.info()
+    assert info["rows"] == n and info["n_valid"] == n and info["dim"] == 1024
+    s.close()
+
+
+def test_append_host_rows_and_unsorted_ids_rejected():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((50, 1024)).astype(np.float32)
+    s = DenseStore("chunks", 100, dim=1024, device=0)
+    s.append(x[:30], ids=np.arange(10, 40))
+    s.append(torch.from_numpy(x[30:]).cuda(), ids=np.arange(40, 60))
+    s.finalize()
+    back = s.read_rows(0, 50, ("f32", "ids"))
+    assert np.array_equal(back["f32"], x) and np.array_equal(back["ids"], np.arange(10, 60))
+    s.close()
+    bad = DenseStore("chunks", 10, dim=1024, device=0)
+    bad.append(x[:4], ids=[5, 6, 6, 7])
+    with pytest.raises(DenseEngineError) as exc:
+        bad.finalize()
+    assert exc.value.code == _ffi.CDR_ERR_UNSORTED_IDS
+    bad.close()
+    with pytest.raises(DenseEngineError):
+        DenseStore("chunks", 10, dim=1000, device=0)      # dim not a multiple of 128
+    full = DenseStore("chunks", 4, dim=1024, device=0)
+    with pytest.raises(DenseEngineError) as exc:
+        full.append(x[:5], ids=np.arange(5))
+    assert exc.value.code == _ffi.CDR_ERR_OOM
+    full.close()
+
+
+# =================================================================== K6 filter bitmap
+def test_filter_bitmap_matches_port():
+    n = 10_007
+    s = make_synth_store(n)
+    cols = s.read_rows(0, n, ("call_slot", "started_at", "tag_bits"))
+    t = lambda slot: SYNTH_T0_US + slot * SYNTH_CALL_PERIOD_US  # noqa: E731
+    cases = [
+        dict(call_slots=[0, 3, 17, 49]),
+        dict(call_slots=[]),
+        dict(call_slots=[10_000]),                      # unknown call
+        dict(date_from=t(5)), dict(date_to=t(7)), dict(date_from=t(5), date_to=t(7)),
+        dict(date_from=t(8), date_to=t(7)),             # empty range
+        dict(tag_mask=0b101), dict(tag_mask=0),
+        dict(call_slots=list(range(0, 50, 2)), date_from=t(4), date_to=t(40), tag_mask=0xF0F0),
+    ]
+    for spec in cases:
+        allow, count = s.filter_bitmap(**spec)
+        keep = ports.filter_rows(cols["call_slot"], cols["started_at"], cols["tag_bits"], None,
+                                 call_slots=spec.get("call_slots"), date_from_us=spec.get("date_from"),
+                                 date_to_us=spec.get("date_to"), tag_mask=spec.get("tag_mask"))
+        assert count == int(keep.sum()), spec
+        got = allow.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got[: (n + 31) // 32], orc.rows_to_bitmap(keep)), spec
+    s.close()
+
+
+# =================================================================== K1 exact scan parity
+@pytest.fixture(scope="module")
+def corpus_100k():
+    n = 100_000
+    s = make_synth_store(n)
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n)
+    yield s, x
+    s.close()
+
+
+@pytest.mark.parametrize("k", [1, 10, 50, 56, 57, 200, 248])
+def test_exact_scan_matches_oracle_100k(corpus_100k, k):
+    s, x = corpus_100k
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 0, 6)
+    ids, sc, cnt = s.search_exact(qs, k)            # host buffers -> *_host entry point
+    for i in range(qs.shape[0]):
+        assert_matches_oracles(ids[i], sc[i], cnt[i], qs[i], x, k)
+    # device-buffer entry point returns the same bits
+    d_ids, d_sc, d_cnt = s.search_exact(torch.from_numpy(qs).cuda(), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_ids.cpu().numpy(), ids) and np.array_equal(d_cnt.cpu().numpy(), cnt)
+    assert np.array_equal(d_sc.cpu().numpy().view(np.uint64), sc.view(np.uint64))
+
+
+def test_exact_scan_with_filters_100k(corpus_100k):
+    s, x = corpus_100k
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 100, 3)
+    cols = s.read_rows(0, x.shape[0], ("call_slot", "started_at", "tag_bits"))
+    for spec in [dict(call_slots=list(range(10))),                       # 2 000 rows: the C1/C4 filter
+                 dict(call_slots=[7]), dict(tag_mask=0b1), dict(call_slots=[3], tag_mask=0xFFFF),
+                 dict(date_from=SYNTH_T0_US + 490 * SYNTH_CALL_PERIOD_US)]:
+        allow, count = s.filter_bitmap(**spec)
+        keep = ports.filter_rows(cols["call_slot"], cols["started_at"], cols["tag_bits"], None,
+                                 call_slots=spec.get("call_slots"), date_from_us=spec.get("date_from"),
+                                 tag_mask=spec.get("tag_mask"))
+        assert count == keep.sum()
+        ids, sc, cnt = s.search_exact(qs, 50, allow)
+        for i in range(qs.shape[0]):
+            assert_matches_oracles(ids[i], sc[i], cnt[i], qs[i], x, 50, allow=orc.rows_to_bitmap(keep))
+    # call_ids == [] -> nothing
+    allow, count = s.filter_bitmap(call_slots=[])
+    ids, sc, cnt = s.search_exact(qs, 50, allow)
+    assert count == 0 and cnt.tolist() == [0, 0, 0] and np.all(ids == -1) and np.all(np.isnan(sc))
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 2000, 2367, 4097])
+def test_exact_scan_ragged_sizes(n):
+    s = make_synth_store(n)
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n)
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 7, 2)
+    for k in (10, 50):
+        ids, sc, cnt = s.search_exact(qs, k)
+        for i in range(2):
+            assert_matches_oracles(ids[i], sc[i], cnt[i], qs[i], x, k)
+    s.close()
+
+
+@pytest.mark.parametrize("dim", [256, 512, 768, 1536, 2048])
+def test_exact_scan_other_dims(dim, monkeypatch):
+    n = 3000
+    s = make_synth_store(n, dim=dim, bf16=False)
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n, dim)
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 0, 2, dim)
+    ids, sc, cnt = s.search_exact(qs, 50)
+    for i in range(2):
+        assert_matches_oracles(ids[i], sc[i], cnt[i], qs[i], x, 50)
+    s.close()
+
+
+def test_exact_scan_edge_semantics():
+    """duplicates (tie -> id order), zero vector (NaN last), NULL embedding (excluded),
+    non-normalised rows, custom ids, LIMIT > survivors."""
+    rng = np.random.default_rng(42)
+    n = 600
+    x = rng.standard_normal((n, 1024)).astype(np.float32) * rng.uniform(0.1, 30, size=(n, 1)).astype(np.float32)
+    q = rng.standard_normal(1024).astype(np.float32)
+    x[10] = q * 2.0                      # best match, cosine 1
+    x[200] = x[10]; x[400] = x[10] * 0.5  # exact / scaled duplicates -> ties broken by id
+    x[50] = 0.0; x[51] = 0.0             # zero vectors -> NaN -> last
+    for j in range(100, 140):            # 40 identical rows: more equal scores than spare candidate slots
+        x[j] = x[100]
+    valid = np.ones(n, dtype=bool); valid[[10, 77]] = False    # embedding IS NULL
+    row_ids = np.arange(n, dtype=np.int64) * 7 + 1000
+    s = DenseStore("chunks", n, dim=1024, device=0)
+    s.append(x, ids=row_ids, valid=valid)
+    s.finalize()
+    assert s.info()["n_valid"] == n - 2
+    allow = orc.rows_to_bitmap(valid)
+    for k in (5, 50, 248):
+        ids, sc, cnt = s.search_exact(q, k)
+        assert_matches_oracles(ids[0], sc[0], cnt[0], q, x, k, allow=allow, row_ids=row_ids)
+    ids, sc, cnt = s.search_exact(q, 3)
+    assert ids[0].tolist() == [row_ids[200], row_ids[400], ids[0][2]] and sc[0][0] == pytest.approx(1.0, abs=1e-12)
+    # zero query -> every score NaN -> id order
+    ids, sc, cnt = s.search_exact(np.zeros(1024, dtype=np.float32), 4)
+    assert ids[0].tolist() == [row_ids[r] for r in (0, 1, 2, 3)] and np.all(np.isnan(sc[0]))
+    s.close()
+    # LIMIT larger than the table, NaN rows still returned last
+    t = DenseStore("chunks", 8, dim=1024, device=0)
+    t.append(x[48:53], ids=[1, 2, 3, 4, 5])
+    t.finalize()
+    ids, sc, cnt = t.search_exact(q, 50)
+    assert_matches_oracles(ids[0], sc[0], cnt[0], q, x[48:53], 50, row_ids=np.arange(1, 6))
+    assert cnt[0] == 5 and np.isnan(sc[0][3]) and np.isnan(sc[0][4]) and ids[0][3:5].tolist() == [3, 4]
+    t.close()
+
+
+def test_exact_scan_adversarial_order():
+    """rows sorted by ascending similarity: every row beats the running threshold."""
+    rng = np.random.default_rng(1)
+    n = 5000
+    q = rng.standard_normal(1024).astype(np.float32)
+    noise = rng.standard_normal((n, 1024)).astype(np.float32)
+    w = np.linspace(-1, 1, n, dtype=np.float32)[:, None]
+    x = (w * q[None, :] + 0.5 * noise).astype(np.float32)
+    s = DenseStore("chunks", n, dim=1024, device=0)
+    s.append(x, ids=np.arange(1, n + 1))
+    s.finalize()
+    ids, sc, cnt = s.search_exact(q, 50)
+    assert_matches_oracles(ids[0], sc[0], cnt[0], q, x, 50)
+    s.close()
+
+
+# =================================================================== K4 merge + logical sharding
+def test_topk_merge_and_sharded_equals_unsharded(corpus_100k):
+    s, x = corpus_100k
+    n, k, R = x.shape[0], 50, 4
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 300, 5)
+    full_ids, full_sc, full_n = s.search_exact(qs, k)
+    per = n // R
+    sc_all = np.empty((R, qs.shape[0], k)); id_all = np.empty((R, qs.shape[0], k), dtype=np.int64)
+    n_all = np.empty((R, qs.shape[0]), dtype=np.int32)
+    for r in range(R):
+        shard = make_synth_store(per, first_row=r * per)
+        id_all[r], sc_all[r], n_all[r] = shard.search_exact(qs, k)
+        shard.close()
+    from cadence_rag_b200.dist import merge_shard_results
+    m_ids, m_sc, m_n = merge_shard_results(torch.from_numpy(sc_all).cuda(), torch.from_numpy(id_all).cuda(),
+                                           torch.from_numpy(n_all).cuda(), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(m_ids.cpu().numpy(), full_ids)
+    assert np.array_equal(m_sc.cpu().numpy().view(np.uint64), full_sc.view(np.uint64))
+    want = ports.merge_topk(sc_all, id_all, n_all, k)
+    for qi, (wi, ws) in enumerate(want):
+        assert m_ids[qi].cpu().tolist() == wi
+    # short / empty / NaN lists
+    sc = np.array([[[0.5, np.nan, 0.0]], [[0.5, 0.25, 0.0]], [[0.0, 0.0, 0.0]]]); ids = np.array([[[9, 4, 0]], [[3, 8, 0]], [[0, 0, 0]]])
+    cnt = np.array([[2], [2], [0]], dtype=np.int32)
+    m_ids, m_sc, m_n = merge_shard_results(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda(),
+                                           torch.from_numpy(cnt).cuda(), 3)
+    assert m_ids.cpu().tolist() == [[3, 9, 8]] and m_n.cpu().tolist() == [3]
+    m_ids, m_sc, m_n = merge_shard_results(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda(),
+                                           torch.from_numpy(cnt).cuda(), 3 + 0)
+    sc5 = np.concatenate([sc, np.zeros_like(sc[:1])]); ids5 = np.concatenate([ids, np.zeros_like(ids[:1])])
+    cnt5 = np.concatenate([cnt, np.zeros_like(cnt[:1])])
+    m_ids, m_sc, m_n = merge_shard_results(torch.from_numpy(sc5).cuda(), torch.from_numpy(ids5).cuda(),
+                                           torch.from_numpy(cnt5).cuda(), 3)
+    assert m_ids.cpu().tolist() == [[3, 9, 8]]
+
+
+# =================================================================== K5 RRF
+def test_rrf_kernel_bit_exact_vs_reference_golden(golden_dir):
+    with open(os.path.join(golden_dir, "reference_pure.json")) as f:
+        cases = json.load(f)["rrf"]
+    # one batched launch over every golden case that shares (L, k); plus the facade per case
+    for case in cases:
+        lanes = {name: [{"chunk_id": i} for i in ids] for name, ids in case["lanes"]}
+        fused = retrieve._rrf_merge(lanes, "chunk_id", case["k"]) if lanes else []
+        got = [[row["chunk_id"], sorted(hit), float(score).hex()] for row, hit, score in fused]
+        assert got == case["fused"], case["lanes"]
+    by_shape = {}
+    for case in cases:
+        if case["lanes"]:
+            by_shape.setdefault((len(case["lanes"]), case["k"]), []).append(case)
+    for (L, k), group in by_shape.items():
+        flat, off = [], [0]
+        for case in group:
+            for _name, ids in case["lanes"]:
+                flat += ids
+                off.append(len(flat))
+        max_out = max(1, max(len(c["fused"]) for c in group))
+        ids, sc, mask, n = retrieve.rrf_merge_batch(np.array(flat + [0], dtype=np.int64), np.array(off, dtype=np.int32),
+                                                    len(group), L, k, max_out)
+        for qi, case in enumerate(group):
+            names = [nm for nm, _ in case["lanes"]]
+            got = [[int(ids[qi, j]), sorted(names[l] for l in range(L) if (int(mask[qi, j]) >> l) & 1),
+                    float(sc[qi, j]).hex()] for j in range(int(n[qi]))]
+            assert got == case["fused"]
+
+
+def test_rrf_row_identity_and_limits():
+    a, b = {"chunk_id": 1, "text": "first"}, {"chunk_id": 1, "text": "second"}
+    fused = retrieve._rrf_merge({"bm25": [a], "dense": [b]}, "chunk_id")
+    assert fused[0][0] is a and fused[0][1] == {"bm25", "dense"}
+    assert retrieve._rrf_merge({}, "chunk_id") == [] and retrieve._rrf_merge({"bm25": []}, "chunk_id") == []
+    big = {"dense": [{"chunk_id": i} for i in range(1025)]}
+    with pytest.raises(DenseEngineError):
+        retrieve._rrf_merge(big, "chunk_id")
+    lanes = {"a": [{"chunk_id": i} for i in range(1, 513)], "b": [{"chunk_id": i} for i in range(512, 0, -1)]}
+    got = retrieve._rrf_merge(lanes, "chunk_id")
+    want = ports.rrf_merge(lanes, "chunk_id")
+    assert [(r["chunk_id"], h, s) for r, h, s in got] == [(r["chunk_id"], h, s) for r, h, s in want]
+
+
+# =================================================================== facade + hybrid (C4)
+def _uuid(i):
+    return UUID(int=i + 1)
+
+
+@pytest.fixture(scope="module")
+def hybrid_engine():
+    """20 000 chunks over 100 calls with UUID call ids, dates, tags, tech tokens + 2 000 artifact
+    chunks; embeddings are the synthetic rows appended through the host path."""
+    n, na = 20_000, 2_000
+    rng = np.random.default_rng(17)
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n)
+    xa = orc.synth_rows(SYNTH_CORPUS_SEED + 5, 0, na)
+    t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+    eng = DenseEngine()
+    meta = {}
+    for name, emb, rows, key in (("chunks", x, n, "chunk_id"), ("artifact_chunks", xa, na, "artifact_chunk_id")):
+        call_of_row = np.arange(rows) // (rows // 100)
+        tags_of_call = [[f"t{c % 5}", f"u{c % 3}"] for c in range(100)]
+        vocab = [f"TOK-{i}" for i in range(200)]
+        zipf = np.minimum(rng.zipf(1.3, size=(rows, 3)) - 1, 199)
+        ntok = rng.integers(0, 4, size=rows)
+        row_tokens = [[vocab[z] for z in zipf[r, : ntok[r]]] for r in range(rows)]
+        ids = np.arange(1, rows + 1, dtype=np.int64) * 2
+        valid = np.ones(rows, dtype=bool); valid[rng.choice(rows, 25, replace=False)] = False
+        store = DenseStore(name, rows, dim=1024, device=0)
+        store.append(emb, ids=ids, call_ids=[_uuid(int(c)) for c in call_of_row],
+                     call_started_at=[t0 + timedelta(hours=int(c)) for c in call_of_row],
+                     call_tags=[tags_of_call[int(c)] for c in call_of_row], valid=valid,
+                     payload=[{"text": f"{name} row {r}"} for r in range(rows)])
+        store.finalize()
+        index = TechTokenIndex()
+        for r, toks in enumerate(row_tokens):
+            index.add_row(r, toks)
+        eng.register(store, index)
+        meta[name] = dict(x=emb, ids=ids, valid=valid, call_of_row=call_of_row, row_tokens=row_tokens,
+                          started=np.array([int((t0 + timedelta(hours=int(c)) - datetime(1970, 1, 1, tzinfo=timezone.utc)).total_seconds()) * 10**6 for c in call_of_row]),
+                          tags_of_call=tags_of_call, key=key)
+    for c in range(100):
+        eng.register_call(_uuid(c), external_id=f"ext-{c // 2}", external_source="crm" if c % 2 else None)
+    yield eng, meta
+    for st in eng.stores.values():
+        st.close()
+
+
+def _oracle_keep(meta, store, filters, call_ids):
+    m = meta
+    slots = None if call_ids is None else [store.call_slots[c] for c in call_ids if c in store.call_slots]
+    tag_mask = None
+    if filters and filters.call_tags:
+        tag_mask = store.bits_of_tags(filters.call_tags)
+    cols = store.host_columns()
+    from cadence_rag_b200.store import to_micros
+    return ports.filter_rows(cols["call_slot"], cols["started_at"], cols["tag_bits"], None, call_slots=slots,
+                             date_from_us=to_micros(filters.date_from) if filters and filters.date_from else None,
+                             date_to_us=to_micros(filters.date_to) if filters and filters.date_to else None,
+                             tag_mask=tag_mask)
+
+
+def test_facade_dense_lane_and_planner(hybrid_engine, monkeypatch):
+    eng, meta = hybrid_engine
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    q = orc.synth_rows(SYNTH_QUERY_SEED, 1, 1)[0]
+    literal = retrieve._vector_literal(q.tolist())
+    t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+    cases = [None, RetrieveFilters(call_ids=[_uuid(3), _uuid(4), _uuid(99)]),
+             RetrieveFilters(date_from=t0 + timedelta(hours=10), date_to=t0 + timedelta(hours=19)),
+             RetrieveFilters(call_tags=["t1", "nope"]), RetrieveFilters(call_tags=["nope"]),
+             RetrieveFilters(external_id="ext-7"), RetrieveFilters(external_id="ext-7", external_source="crm"),
+             RetrieveFilters(external_id="ext-7", call_ids=[_uuid(14)]), RetrieveFilters(external_id="missing")]
+    for filters in cases:
+        with eng.connect() as conn:
+            call_ids = retrieve._resolve_call_ids(conn, filters)
+            for table, fetch, limit in (("chunks", retrieve._fetch_chunks_dense, 50),
+                                        ("artifact_chunks", retrieve._fetch_artifacts_dense, 10)):
+                m = meta[table]; store = eng.stores[table]
+                keep = _oracle_keep(m, store, filters, call_ids) & m["valid"]
+                est = retrieve._estimate_dense_candidates(conn, table, filters, call_ids)
+                assert est == int(keep.sum())
+                mode = retrieve._choose_dense_mode(est, filters, call_ids)
+                assert mode == ports.choose_dense_mode(est, filters, call_ids, settings.embeddings_exact_scan_threshold)
+                rows = fetch(conn, literal, filters, call_ids, mode, limit)
+                want_ids, want_sc = orc.exact_scan(q, m["x"], limit, ids=m["ids"], allow=orc.rows_to_bitmap(keep))
+                assert [r[m["key"]] for r in rows] == want_ids.tolist()
+                assert np.allclose([r["score"] for r in rows], want_sc, rtol=REL_F64)
+                for r in rows[:3]:
+                    row_index = r[m["key"]] // 2 - 1
+                    assert r["call_id"] == _uuid(int(m["call_of_row"][row_index])) and r["text"] == f"{table} row {row_index}"
+    # external_id resolution semantics (app/retrieve.py:46-90)
+    with eng.connect() as conn:
+        assert retrieve._resolve_call_ids(conn, None) is None
+        assert retrieve._resolve_call_ids(conn, RetrieveFilters()) is None
+        assert retrieve._resolve_call_ids(conn, RetrieveFilters(external_id="ext-7")) == sorted([_uuid(14), _uuid(15)], key=str)
+        assert retrieve._resolve_call_ids(conn, RetrieveFilters(external_id="ext-7", external_source="crm")) == [_uuid(15)]
+        assert retrieve._resolve_call_ids(conn, RetrieveFilters(external_id="missing")) == []
+        with pytest.raises(DenseEngineError):
+            retrieve._fetch_chunks_dense(conn, [0.0] * 8, None, None, "exact", 5)
+
+
+def test_hybrid_retrieve_ids_bit_exact(hybrid_engine, monkeypatch):
+    """C4: dense + tech_tokens (+ external bm25 list) -> RRF -> ids_only order, against the
+    restated pipeline (oracle dense ids, port tech lane, port RRF, port ordering)."""
+    eng, meta = hybrid_engine
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    emb = embeddings.SyntheticEmbedder(seed=SYNTH_QUERY_SEED, dim=1024)
+    embeddings.set_embedder(emb)
+    try:
+        t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+        for query, filters in [("why did TOK-1 fail with TOK-3 on 10.0.0.1", None),
+                               ("TOK-0 status", RetrieveFilters(call_ids=[_uuid(c) for c in range(10)])),
+                               ("no tokens here", RetrieveFilters(date_from=t0 + timedelta(hours=50))),
+                               ("TOK-2 and TOK-5", RetrieveFilters(call_tags=["t2"]))]:
+            from cadence_rag_b200.lexical import extract_tech_tokens
+            bm25 = [{"chunk_id": 2 * i} for i in (5, 900, 77, 12000)]
+            out = retrieve.retrieve_ids(eng, query, filters, bm25_chunks=bm25, debug=True)
+            q = np.array(emb([query]).vectors[0], dtype=np.float32)
+            want_q = orc.synth_rows(SYNTH_QUERY_SEED, emb._row_of(query), 1)[0]
+            assert np.array_equal(q, want_q)
+            tokens = extract_tech_tokens(query)
+            with eng.connect() as conn:
+                call_ids = retrieve._resolve_call_ids(conn, filters)
+            ranked = {}
+            for table, limit in (("chunks", 50), ("artifact_chunks", 10)):
+                m = meta[table]; store = eng.stores[table]
+                keep = _oracle_keep(m, store, filters, call_ids)
+                d_ids, _ = orc.exact_scan(q, m["x"], limit, ids=m["ids"], allow=orc.rows_to_bitmap(keep & m["valid"]))
+                tech = ports.tech_lane(m["row_tokens"], m["ids"], store.host_columns()["started_at"], keep, tokens, 50)
+                lanes = {"bm25": bm25 if table == "chunks" else [], "tech_tokens": [{m["key"]: i} for i in tech],
+                         "dense": [{m["key"]: int(i)} for i in d_ids]}
+                ranked[table] = ports.rrf_merge(lanes, m["key"])
+                fused_dbg = out["debug"]["fused"]["chunks" if table == "chunks" else "artifacts"]
+                assert [(r[m["key"]], sorted(h), s) for r, h, s in ranked[table]] == [tuple(t) for t in fused_dbg]
+            assert out["retrieved_ids"] == ports.ids_only_order(ranked["artifact_chunks"], ranked["chunks"])
+            assert out["debug"]["dense"]["enabled"] is True
+    finally:
+        embeddings.set_embedder(None)
+    # embeddings disabled -> lexical only (reference: test_ingest_retrieve.py:313-344 behaviour)
+    monkeypatch.setattr(settings, "embeddings_base_url", "")
+    out = retrieve.retrieve_ids(eng, "TOK-1", None, debug=True)
+    assert out["debug"]["dense"]["enabled"] is False and "dense" not in out["debug"]["lanes"]["chunks"]
+    assert retrieve.retrieve_ids(eng, "   ")["retrieved_ids"] == []
+
+
+# =================================================================== full size (BASELINE C2): 1M x 1024
+@pytest.fixture(scope="module")
+def corpus_1m():
+    s = make_synth_store(1_000_000, bf16=False)
+    yield s
+    s.close()
+
+
+def test_full_size_1m_properties_and_oracle(corpus_1m):
+    s = corpus_1m
+    k = 50
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 0, 16)
+    ids, sc, cnt = s.search_exact(qs, k)
+    assert np.all(cnt == k)
+    # size-independent properties: sorted, bounded, unique ids, idempotent, batch == single
+    assert np.all(np.diff(sc, axis=1) <= 0) and np.all(np.abs(sc) <= 1.0)
+    assert all(len(set(r.tolist())) == k for r in ids)
+    ids2, sc2, _ = s.search_exact(qs, k)
+    assert np.array_equal(ids, ids2) and np.array_equal(sc.view(np.uint64), sc2.view(np.uint64))
+    one_ids, one_sc, _ = s.search_exact(qs[3], k)
+    assert np.array_equal(one_ids[0], ids[3]) and np.array_equal(one_sc[0].view(np.uint64), sc[3].view(np.uint64))
+    # top-10 is a prefix of top-50
+    ids10, _, _ = s.search_exact(qs, 10)
+    assert np.array_equal(ids10, ids[:, :10])
+    # reported scores are the fp64 cosine of the reported rows
+    for qi in (0, 15):
+        rows = s.read_rows(int(ids[qi, 0]) - 1, 1, ("f32",))["f32"][0].astype(np.float64)
+        q64 = qs[qi].astype(np.float64)
+        cos = rows @ q64 / np.sqrt((rows @ rows) * (q64 @ q64))
+        assert abs(cos - sc[qi, 0]) < 1e-12
+    # oracle at full size (C oracle, all host cores) for 4 queries
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, 1_000_000)
+    for qi in range(4):
+        assert_matches_oracles(ids[qi], sc[qi], cnt[qi], qs[qi], x, k)
+    # logical 2-way sharding of the same corpus merges to the same answer (multi-GPU data path)
+    from cadence_rag_b200.dist import merge_shard_results
+    parts = []
+    for r in range(2):
+        sh = make_synth_store(500_000, bf16=False, first_row=r * 500_000)
+        parts.append(sh.search_exact(torch.from_numpy(qs).cuda(), k))
+        torch.cuda.synchronize()
+        sh.close()
+    m_ids, m_sc, m_n = merge_shard_results(torch.stack([p[1] for p in parts]), torch.stack([p[0] for p in parts]),
+                                           torch.stack([p[2] for p in parts]), k)
+    assert np.array_equal(m_ids.cpu().numpy(), ids) and np.array_equal(m_sc.cpu().numpy().view(np.uint64), sc.view(np.uint64))

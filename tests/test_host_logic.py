@@ -1,0 +1,262 @@
+"""CPU tier: host-side mirror of the reference interface (no GPU compute).
+
+Reads like the reference's own unit tests (tests/unit/test_retrieve_planner.py,
+tests/unit/test_embeddings_client.py, tests/unit/test_ingest_utils.py) pointed at this package,
+plus the C-ABI load/export check.
+"""
+import ctypes
+import json
+import os
+import re
+import subprocess
+from datetime import datetime, timezone
+from uuid import uuid4
+
+import numpy as np
+import pytest
+
+import cadence_rag_b200 as pkg
+from cadence_rag_b200 import _ffi, embeddings, lexical, retrieve
+from cadence_rag_b200.config import settings
+from cadence_rag_b200.retrieve import RetrieveFilters, _choose_dense_mode
+from oracle import ports
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pure(golden_dir):
+    with open(os.path.join(golden_dir, "reference_pure.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built_library():
+    if not os.path.exists(_ffi.library_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+# ---------------------------------------------------------------- planner (reference tests mirrored)
+def test_choose_dense_mode_exact_for_small_scoped_sets(monkeypatch):
+    monkeypatch.setattr(settings, "embeddings_exact_scan_threshold", 2000)
+    filters = RetrieveFilters(call_ids=[uuid4()])
+    assert _choose_dense_mode(estimated_rows=200, filters=filters, call_ids=filters.call_ids) == "exact"
+
+
+def test_choose_dense_mode_ann_for_large_scoped_sets(monkeypatch):
+    monkeypatch.setattr(settings, "embeddings_exact_scan_threshold", 2000)
+    filters = RetrieveFilters(date_from=datetime.now(timezone.utc), date_to=datetime.now(timezone.utc))
+    assert _choose_dense_mode(estimated_rows=5000, filters=filters, call_ids=None) == "ann"
+
+
+def test_choose_dense_mode_ann_for_unscoped_queries(monkeypatch):
+    monkeypatch.setattr(settings, "embeddings_exact_scan_threshold", 5000)
+    assert _choose_dense_mode(estimated_rows=100, filters=None, call_ids=None) == "ann"
+
+
+def test_choose_dense_mode_exact_when_no_candidates(monkeypatch):
+    monkeypatch.setattr(settings, "embeddings_exact_scan_threshold", 10)
+    assert _choose_dense_mode(estimated_rows=0, filters=None, call_ids=None) == "exact"
+
+
+def test_planner_matches_reference_golden_table(pure, monkeypatch):
+    now = datetime(2026, 2, 9, tzinfo=timezone.utc)
+    for case in pure["planner"]:
+        monkeypatch.setattr(settings, "embeddings_exact_scan_threshold", case["threshold"])
+        kind = case["kind"]
+        filters, call_ids = None, None
+        if kind == "nofilter_callids":
+            call_ids = ["c1"]
+        elif kind == "empty_callids":
+            call_ids = []
+        elif kind == "date_from":
+            filters = RetrieveFilters(date_from=now)
+        elif kind == "date_to":
+            filters = RetrieveFilters(date_to=now)
+        elif kind == "tags":
+            filters = RetrieveFilters(call_tags=["x"])
+        elif kind == "empty_tags":
+            filters = RetrieveFilters(call_tags=[])
+        elif kind == "filters_only_external":
+            filters = RetrieveFilters(external_id="abc")
+        assert retrieve._choose_dense_mode(case["rows"], filters, call_ids) == case["mode"], case
+        assert retrieve._dense_has_scoping(filters, call_ids) == case["scoped"], case
+
+
+# ---------------------------------------------------------------- small pure helpers vs goldens
+def test_vector_literal_and_parse(pure):
+    for case in pure["vector_literal"]:
+        vals = [float.fromhex(h) for h in case["values_hex"]]
+        assert retrieve._vector_literal(vals) == case["literal"]
+        parsed = retrieve._query_vector(case["literal"])
+        assert np.array_equal(parsed.view(np.uint32), np.array(vals, dtype=np.float32).view(np.uint32))
+    with pytest.raises(pkg.DenseEngineError):
+        retrieve._query_vector("1,2,3")
+
+
+def test_build_debug_lane(pure):
+    for case in pure["debug_lane"]:
+        assert retrieve._build_debug_lane(case["rows"], case["id_field"]) == case["lane"]
+
+
+def test_extract_tech_tokens_matches_reference_golden(pure):
+    for case in pure["tech_tokens"]:
+        assert lexical.extract_tech_tokens(case["text"]) == case["tokens"], case["text"]
+
+
+def test_extract_tech_tokens_reference_unit_cases():
+    # tests/unit/test_ingest_utils.py:12-28 style known answers
+    toks = lexical.extract_tech_tokens("Which ticket tracked the ECONNRESET issue for ABC-123 on v1.2.3?")
+    assert toks == ["ABC-123", "ECONNRESET", "v1.2.3"]
+
+
+def test_tech_index_matches_port():
+    rng = np.random.default_rng(3)
+    n = 400
+    vocab = [f"T{i}" for i in range(30)] + ["t1", "ABC-1"]
+    row_tokens = [list(rng.choice(vocab, size=int(rng.integers(0, 4)), replace=False)) for _ in range(n)]
+    ids = np.arange(1, n + 1, dtype=np.int64) * 3
+    started = (rng.integers(0, 20, size=n) * 1000).astype(np.int64)
+    slots = rng.integers(0, 10, size=n).astype(np.int32)
+    tags = (np.uint64(1) << rng.integers(0, 8, size=n).astype(np.uint64))
+    cols = {"ids": ids, "started_at": started, "call_slot": slots, "tag_bits": tags}
+    idx = lexical.TechTokenIndex()
+    for r, toks in enumerate(row_tokens):
+        idx.add_row(r, toks)
+    for tokens, spec in [(["T1", "T2"], {}), (["t1"], {}), (["T3"], {"call_slots": [1, 2, 3]}),
+                         (["T4", "T5", "nope"], {"date_from": 5000, "date_to": 15000}),
+                         (["T6"], {"tag_mask": 0b1010}), (["T7"], {"call_slots": []}), ([], {})]:
+        keep = ports.filter_rows(slots, started, tags, None, call_slots=spec.get("call_slots"),
+                                 date_from_us=spec.get("date_from"), date_to_us=spec.get("date_to"),
+                                 tag_mask=spec.get("tag_mask"))
+        want = ports.tech_lane(row_tokens, ids, started, keep, tokens, 50)
+        got = ids[idx.query(tokens, cols, 50, **spec)].tolist() if tokens else []
+        assert got == want
+
+
+# ---------------------------------------------------------------- embedding client (reference tests mirrored)
+class _FakeResponse:
+    def __init__(self, status_code, body, text=""):
+        self.status_code, self._body, self.text = status_code, body, text
+
+    def json(self):
+        return self._body
+
+
+class _FakeClient:
+    calls = []
+    response = None
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def post(self, url, json=None):
+        _FakeClient.calls.append((url, json))
+        r = _FakeClient.response
+        return r(json) if callable(r) else r
+
+
+@pytest.fixture
+def fake_http(monkeypatch):
+    monkeypatch.setattr(settings, "embeddings_base_url", "http://embed.local/")
+    monkeypatch.setattr(settings, "embeddings_dim", 4)
+    monkeypatch.setattr(embeddings.httpx, "Client", _FakeClient)
+    embeddings.set_embedder(None)
+    _FakeClient.calls = []
+    return _FakeClient
+
+
+def test_embed_texts_posts_to_embed_and_validates(fake_http):
+    fake_http.response = _FakeResponse(200, {"embeddings": [[1, 2, 3, 4], [5, 6, 7, 8]], "model": "m"})
+    res = embeddings.embed_texts([" a ", "b", "  "])
+    assert fake_http.calls[0][0] == "http://embed.local/embed"
+    assert fake_http.calls[0][1]["texts"] == ["a", "b"]
+    assert res.vectors == [[1.0, 2.0, 3.0, 4.0], [5.0, 6.0, 7.0, 8.0]] and res.model == "m"
+
+
+def test_embed_texts_rejects_wrong_dim_and_errors(fake_http):
+    fake_http.response = _FakeResponse(200, {"embeddings": [[1, 2, 3]]})
+    with pytest.raises(embeddings.EmbeddingClientError, match="has dim 3; expected 4"):
+        embeddings.embed_texts(["a"])
+    fake_http.response = _FakeResponse(500, {}, text="boom")
+    with pytest.raises(embeddings.EmbeddingClientError, match="returned 500: boom"):
+        embeddings.embed_texts(["a"])
+    fake_http.response = _FakeResponse(200, {"embeddings": [[1, 2, 3, 4], [1, 2, 3, 4]]})
+    with pytest.raises(embeddings.EmbeddingClientError, match="count mismatch"):
+        embeddings.embed_texts(["a"])
+    fake_http.response = _FakeResponse(200, {"nope": 1})
+    with pytest.raises(embeddings.EmbeddingClientError, match="missing 'embeddings'"):
+        embeddings.embed_texts(["a"])
+    with pytest.raises(embeddings.EmbeddingClientError, match="at least one non-empty"):
+        embeddings.embed_texts(["  "])
+
+
+def test_embed_texts_batched_splits(fake_http):
+    fake_http.response = lambda payload: _FakeResponse(
+        200, {"embeddings": [[0, 0, 0, float(len(t))] for t in payload["texts"]]})
+    res = embeddings.embed_texts_batched(["a", "bb", "ccc", "dddd", "eeeee"], batch_size=2)
+    assert [len(c[1]["texts"]) for c in fake_http.calls] == [2, 2, 1]
+    assert [v[3] for v in res.vectors] == [1.0, 2.0, 3.0, 4.0, 5.0]
+    with pytest.raises(embeddings.EmbeddingClientError):
+        embeddings.embed_texts_batched(["a"], batch_size=-1)
+
+
+def test_embeddings_disabled_without_base_url(monkeypatch):
+    monkeypatch.setattr(settings, "embeddings_base_url", "  ")
+    embeddings.set_embedder(None)
+    assert embeddings.embeddings_enabled() is False
+    with pytest.raises(embeddings.EmbeddingClientError, match="EMBEDDINGS_BASE_URL is not configured"):
+        embeddings.embed_texts(["a"])
+
+
+# ---------------------------------------------------------------- C ABI: loads, exports everything declared
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cadence_dense.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cdr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    L = ctypes.CDLL(_ffi.library_path())
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/cadence_dense.h but not exported"
+    # and the ctypes stub binds exactly the declared set
+    assert sorted(_ffi.SIGNATURES) == declared
+    assert _ffi.abi_version() == 1
+
+
+def test_library_is_sm100a_with_bulk_copy_and_no_legacy_mma():
+    out = subprocess.run(["cuobjdump", "-lelf", _ffi.library_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: covered by the gpu tier")
+    with pytest.raises(pkg.DenseEngineError) as exc:
+        _ffi.require_device()
+    assert exc.value.code == _ffi.CDR_ERR_NO_DEVICE
+    from cadence_rag_b200.store import DenseStore
+    with pytest.raises(pkg.DenseEngineError):
+        DenseStore("chunks", 16)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _d, files in os.walk(os.path.join(ROOT, "cadence_rag_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+                assert "liboracle" not in src, fn
