@@ -272,8 +272,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
 //      fp64 accumulators): sim = ab / sqrt(aa*bb), clamp, distance = 1 - sim, score = 1 - distance.
 //   3. final order (score desc, NaN last, id asc) by rank counting; first k written out.
 struct FinalizeParams {
-    const uint64_t *lists;    // [nq, n_lists, KC]
+    const uint64_t *lists;    // sorted mode: [nq, n_lists, KC]; unsorted mode: [nq, cap]
     int n_lists;
+    const uint32_t *counts;   // unsorted mode: valid keys per query (clamped to cap); else nullptr
+    int cap;
     const float *rows;        // fp32 rows (may be null when bf16_rows is used)
     const __nv_bfloat16 *bf16_rows;
     const float *queries;     // [nq, dim]
@@ -301,7 +303,29 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams
     uint64_t k[NPL];
 #pragma unroll
     for (int i = 0; i < NPL; ++i) k[i] = CDR_EMPTY_KEY;
-    for (int l = warp; l < p.n_lists; l += 8) warp_merge_topk<NPL>(k, base + (size_t)l * KC, lane);
+    if (p.counts == nullptr) {
+        for (int l = warp; l < p.n_lists; l += 8) warp_merge_topk<NPL>(k, base + (size_t)l * KC, lane);
+    } else {
+        // one unsorted list per query (K2 candidates): sort KC-sized chunks, fold them in
+        const uint64_t *list = p.lists + (size_t)qi * p.cap;
+        uint32_t n = p.counts[qi];
+        if (n > (uint32_t)p.cap) n = p.cap;
+        const int chunks = (int)((n + KC - 1) / KC);
+        for (int ch = warp; ch < chunks; ch += 8) {
+            uint64_t c[NPL];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                const uint32_t e = (uint32_t)ch * KC + i * 32 + lane;
+                c[i] = e < n ? list[e] : CDR_EMPTY_KEY;
+            }
+            warp_bitonic_sort_desc<NPL>(c, lane);
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = c[i];
+            __syncwarp();
+            warp_merge_topk<NPL>(k, s_lists + warp * KC, lane);
+            __syncwarp();
+        }
+    }
 #pragma unroll
     for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
 #pragma unroll
@@ -451,6 +475,8 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     FinalizeParams fp;
     fp.lists = ws.cta_keys;
     fp.n_lists = grid;
+    fp.counts = nullptr;
+    fp.cap = 0;
     fp.rows = s->emb_f32;
     fp.bf16_rows = nullptr;
     fp.queries = q_dev;
@@ -495,14 +521,17 @@ int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
     return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
 }
 
-// Used by the batched bf16 lane: re-score + order caller-provided candidate lists.
-int cdr_finalize_lists_launch(cdr_store *s, const uint64_t *lists, int n_lists, int kc,
-                              const float *q_dev, int nq, int k, bool use_bf16_rows,
-                              double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st)
+// Used by the batched bf16 lane (gemm_topk.cu): select the top-kc of one unsorted candidate
+// list per query, re-score them exactly and order them.
+int cdr_finalize_unsorted_launch(cdr_store *s, const uint64_t *lists, const uint32_t *counts, int cap,
+                                 int kc, const float *q_dev, int nq, int k, bool use_bf16_rows,
+                                 double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st)
 {
     FinalizeParams fp;
     fp.lists = lists;
-    fp.n_lists = n_lists;
+    fp.n_lists = 1;
+    fp.counts = counts;
+    fp.cap = cap;
     fp.rows = use_bf16_rows ? nullptr : s->emb_f32;
     fp.bf16_rows = s->emb_bf16;
     fp.queries = q_dev;
@@ -513,6 +542,7 @@ int cdr_finalize_lists_launch(cdr_store *s, const uint64_t *lists, int n_lists, 
     fp.out_id = out_id;
     fp.out_n = out_n;
     if (kc == 64) scan_finalize_kernel<2><<<nq, 256, 0, st>>>(fp);
+    else if (kc == 128) scan_finalize_kernel<4><<<nq, 256, 0, st>>>(fp);
     else if (kc == 256) scan_finalize_kernel<8><<<nq, 256, 0, st>>>(fp);
     else {
         cdr_set_error("finalize: candidate width %d not built", kc);

@@ -1,10 +1,550 @@
-// gemm_topk.cu -- K2 placeholder (replaced by the tcgen05 kernel in the next commit).
+// gemm_topk.cu -- K2: batched bf16 tensor-core scan (tcgen05 / TMEM / TMA) with a fused
+// threshold-append top-k epilogue.  The score matrix S = Q . X^T never reaches HBM.
+//
+// Serves mode "ann" of the reference (app/retrieve.py:290-298 enables pgvector's HNSW with
+// ef_search; here brute force on the 5th-gen tensor cores replaces the graph walk) for batches
+// of queries.  Survivors are re-scored exactly and ordered like the exact lane (exact_scan.cu).
+//
+// Shapes: Q bf16 [nq_pad, D] (rows L2-normalised, zero padded to a multiple of 128),
+//         X bf16 [N, D] (rows L2-normalised at ingest), both K-major.
+// CTA tile: 128 queries (UMMA M) x 256 corpus rows (UMMA N), K step 64 (= one 128-byte swizzle
+// atom per operand row), kStages-deep TMA->smem ring, fp32 accumulators in TMEM, two
+// accumulator buffers (2 x 256 columns = all 512) so the epilogue of tile t overlaps the MMAs of
+// tile t+1.
+//
+// Warp roles (256 threads, one CTA per SM, persistent over work items):
+//   warp 0   TMA producer   : cp.async.bulk.tensor.2d (128B swizzle) A and B boxes per K block
+//   warp 1   MMA issuer     : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                             (128x256x16), tcgen05.commit releases smem stages / publishes TMEM
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue      : tcgen05.ld 32x32b (thread = one query row), running max of each
+//                             32-column chunk against the query's threshold tau; the rare chunks
+//                             that beat it append (score,row) keys to the query's candidate list
+//                             in global memory (one atomicAdd per chunk).
+//
+// Exactness argument: every row whose bf16 score >= tau[q] is appended (complete above the
+// threshold), and tau[q] is always the KC-th best score of a subset of the rows seen so far, so
+// the final list contains the bf16 top-KC of the whole corpus.  The corpus is processed in
+// geometrically growing segments (16, 256, 4096, ... tiles in a multiplicative permutation of
+// the tile order); between segments a select kernel compacts each list to its top-KC and raises
+// tau.  No row is ever multiplied twice.  List overflow (adversarial data) is flagged and the
+// affected queries are re-run on the exact lane by the host wrapper.
 #include "common.cuh"
+
+#include <cuda.h>
+
+int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
+                          const uint32_t *allow, int k, double *out_score, int64_t *out_id,
+                          int32_t *out_n, cudaStream_t st);
+int cdr_finalize_unsorted_launch(cdr_store *s, const uint64_t *lists, const uint32_t *counts, int cap,
+                                 int kc, const float *q_dev, int nq, int k, bool use_bf16_rows,
+                                 double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st);
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 256;
+constexpr int kBlockK = 64;                 // bf16 elements = 128 bytes = one swizzle atom row
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kGemmThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers (tcgen05 / TMA); forms follow the PTX ISA for sm_100a
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M128 N256 K16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(const void *tile)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(tile) & 0x3FFFFu) >> 4);      // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                                  // leading byte offset (unused)
+    d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset
+    d |= (uint64_t)1 << 46;                                  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    return d;
+}
+constexpr uint32_t kInstrDesc = (1u << 4)                    // D format: fp32
+                                | (1u << 7)                  // A format: bf16
+                                | (1u << 10)                 // B format: bf16
+                                | ((uint32_t)(kBlockN >> 3) << 17)
+                                | ((uint32_t)(kBlockM >> 4) << 24);   // A, B K-major (bits 15,16 = 0)
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct GemmParams {
+    const float *tau;          // [nq_pad] admission threshold per query (-inf => take everything)
+    uint64_t *lists;           // [nq, cap] candidate keys
+    uint32_t *counts;          // [nq]
+    const uint32_t *allow;     // nullable row bitmap
+    int64_t n_rows;
+    int nq;                    // real queries
+    int m_tiles;               // nq_pad / 128
+    int cap;
+    int64_t n_tiles_total;     // ceil(n_rows / 256)
+    int64_t perm_mul;          // tile permutation multiplier (coprime with n_tiles_total)
+    int64_t tile_begin, tile_end;   // permuted tile index range of this segment
+    int k_blocks;              // D / 64
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                 const GemmParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    // 128B swizzle needs 1024-byte aligned tiles
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *tiles = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
+    uint64_t *full_bar = bars;                    // [kStages]
+    uint64_t *empty_bar = bars + kStages;         // [kStages]
+    uint64_t *tmem_full = bars + 2 * kStages;     // [2]
+    uint64_t *tmem_empty = bars + 2 * kStages + 2;  // [2]
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_q);
+        prefetch_tmap(&map_x);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 4);     // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    const int64_t seg_tiles = p.tile_end - p.tile_begin;
+    const int64_t n_items = seg_tiles * p.m_tiles;      // item w -> (tile_begin + w / m_tiles, w % m_tiles)
+    const int64_t G = gridDim.x;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t w = blockIdx.x; w < n_items; w += G) {
+                const int64_t tj = p.tile_begin + w / p.m_tiles;
+                const int mt = (int)(w % p.m_tiles);
+                const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
+                for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    unsigned char *a = tiles + (size_t)s * kStageBytes;
+                    tma_load_2d(a, &map_q, kb * kBlockK, mt * kBlockM, &full_bar[s]);
+                    tma_load_2d(a + kABytes, &map_x, kb * kBlockK, (int)(nt * kBlockN), &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        uint32_t it = 0, tile_no = 0;
+        for (int64_t w = blockIdx.x; w < n_items; w += G, ++tile_no) {
+            const uint32_t buf = tile_no & 1u;
+            const uint32_t use = tile_no >> 1;                    // how many times this buffer was used before
+            mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * kBlockN;
+            for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const unsigned char *a = tiles + (size_t)s * kStageBytes;
+                    const uint64_t adesc = make_smem_desc(a);
+                    const uint64_t bdesc = make_smem_desc(a + kABytes);
+#pragma unroll
+                    for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                        umma_bf16(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), kInstrDesc,
+                                  (kb | k4) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);                   // smem stage free when these MMAs retire
+                    if (kb == p.k_blocks - 1) umma_commit(&tmem_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue
+        const int ew = warp & 3;                                  // TMEM lane quarter of this warp
+        uint32_t tile_no = 0;
+        for (int64_t w = blockIdx.x; w < n_items; w += G, ++tile_no) {
+            const int64_t tj = p.tile_begin + w / p.m_tiles;
+            const int mt = (int)(w % p.m_tiles);
+            const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
+            const int64_t row0 = nt * kBlockN;
+            const int q = mt * kBlockM + ew * 32 + lane;
+            const bool q_ok = q < p.nq;
+            const float tau = q_ok ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
+            int64_t lim = p.n_rows - row0;                        // valid columns in this tile
+            if (lim > kBlockN) lim = kBlockN;
+            const uint32_t buf = tile_no & 1u;
+            const uint32_t use = tile_no >> 1;
+            mbar_wait(&tmem_full[buf], use & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * kBlockN;
+#pragma unroll 1
+            for (int c = 0; c < kBlockN / 32; ++c) {
+                __syncwarp();
+                float v[32];
+                tmem_ld32(taddr + c * 32, v);
+                if (c * 32 >= lim) continue;                      // warp-uniform (tail tile)
+                float m = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                const int rem = (int)(lim - c * 32);
+                if (m >= tau || rem < 32) {
+                    // slow path: exact per-element test, filter bit, append
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (v[j] >= tau) mask |= 1u << j;
+                    if (rem < 32) mask &= (1u << rem) - 1u;
+                    if (mask != 0 && p.allow != nullptr) {
+                        // 32 consecutive rows starting at a multiple of 32: exactly one bitmap word
+                        mask &= __ldg(&p.allow[(row0 + c * 32) >> 5]);
+                    }
+                    if (mask != 0) {
+                        const uint32_t cnt = __popc(mask);
+                        uint32_t base = atomicAdd(&p.counts[q], cnt);
+                        uint64_t *dst = p.lists + (size_t)q * p.cap;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if ((mask >> j) & 1u) {
+                                if (base < (uint32_t)p.cap) dst[base] = cdr_pack_key(v[j], (uint32_t)(row0 + c * 32 + j));
+                                ++base;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- query preparation: q_bf16[q,:] = RN(q / ||q||), zero rows for padding; tau = -inf
+__global__ void prep_queries_kernel(const float *q, __nv_bfloat16 *out, float *tau, uint32_t *counts,
+                                    uint32_t *overflow, int nq, int nq_pad, int dim)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nq_pad) return;
+    __nv_bfloat16 *o = out + (size_t)row * dim;
+    if (row >= nq) {
+        for (int i = lane; i < dim; i += 32) o[i] = __float2bfloat16_rn(0.f);
+        if (lane == 0) tau[row] = __int_as_float(0x7f800000);
+        return;
+    }
+    const float *r = q + (size_t)row * dim;
+    float n2 = 0.f;
+    for (int i = lane; i < dim; i += 32) n2 = fmaf(r[i], r[i], n2);
+    n2 = warp_sum_f32(n2);
+    const float inv = n2 > 0.f ? __fdiv_rn(1.0f, __fsqrt_rn(n2)) : 0.f;
+    for (int i = lane; i < dim; i += 32) o[i] = __float2bfloat16_rn(r[i] * inv);
+    if (lane == 0) {
+        tau[row] = __int_as_float(0xff800000);   // -inf
+        counts[row] = 0;
+        overflow[row] = 0;
+    }
+}
+
+__device__ __forceinline__ float key_score(uint64_t key)
+{
+    const uint32_t o = (uint32_t)(key >> 32);
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+
+// ---- between segments: compact list[q] to its top-KC (sorted desc), raise tau[q]
+template <int NPL>
+__global__ void __launch_bounds__(256) select_compact_kernel(uint64_t *lists, uint32_t *counts, float *tau,
+                                                             uint32_t *overflow, int cap)
+{
+    constexpr int KC = NPL * 32;
+    __shared__ uint64_t s_lists[8 * KC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x;
+    uint64_t *list = lists + (size_t)q * cap;
+    uint32_t n = counts[q];
+    if (n > (uint32_t)cap) {
+        if (threadIdx.x == 0) overflow[q] = 1;
+        n = cap;
+    }
+    uint64_t k[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) k[i] = CDR_EMPTY_KEY;
+    const int chunks = (int)((n + KC - 1) / KC);
+    for (int ch = warp; ch < chunks; ch += 8) {
+        uint64_t c[NPL];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const uint32_t e = (uint32_t)ch * KC + i * 32 + lane;
+            c[i] = e < n ? list[e] : CDR_EMPTY_KEY;
+        }
+        warp_bitonic_sort_desc<NPL>(c, lane);
+        // merge: k = top KC of (k U c); c reversed is read through shared memory
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = c[i];
+        __syncwarp();
+        warp_merge_topk<NPL>(k, s_lists + warp * KC, lane);
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+#pragma unroll
+    for (int step = 1; step < 8; step <<= 1) {
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0) warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0) {
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+        }
+    }
+    __syncthreads();   // every read of list[] happened before the merges above
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) list[i * 32 + lane] = k[i];
+        const uint64_t last = __shfl_sync(0xffffffffu, k[NPL - 1], 31);   // element KC-1
+        if (lane == 0) {
+            counts[q] = n < (uint32_t)KC ? n : (uint32_t)KC;
+            if (last != CDR_EMPTY_KEY) tau[q] = key_score(last);
+        }
+    }
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(encode_tiled_fn *out)
+{
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CDR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        CDR_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, CDR_ERR_CUDA,
+                    "cuTensorMapEncodeTiled not available from the driver");
+        fn = (encode_tiled_fn)p;
+    }
+    *out = fn;
+    return CDR_OK;
+}
+
+int make_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_rows)
+{
+    encode_tiled_fn enc;
+    int rc = get_encode_fn(&enc);
+    if (rc != CDR_OK) return rc;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dim * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CDR_REQUIRE(r == CUDA_SUCCESS, CDR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld dim=%d", (int)r,
+                (long long)rows, dim);
+    return CDR_OK;
+}
+
+int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+}  // namespace
 
 extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
                                          const uint32_t *allow_dev, double *out_score_dev,
                                          int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
 {
-    cdr_set_error("cdr_search_batch_bf16: not built yet");
-    return CDR_ERR_UNSUPPORTED;
+    CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "cdr_search_batch_bf16: store is NULL");
+    CDR_REQUIRE(s->finalized, CDR_ERR_STATE, "cdr_search_batch_bf16: store not finalized");
+    CDR_REQUIRE(s->emb_bf16 != nullptr, CDR_ERR_STATE,
+                "cdr_search_batch_bf16: store has no bf16 rows (created without CDR_STORE_BF16)");
+    CDR_REQUIRE(nq >= 0 && (nq == 0 || q_dev), CDR_ERR_INVALID, "cdr_search_batch_bf16: bad query batch");
+    CDR_REQUIRE(k >= 1 && k <= 192, CDR_ERR_UNSUPPORTED, "cdr_search_batch_bf16: k=%d outside [1,192]", k);
+    CDR_REQUIRE(out_score_dev && out_id_dev && out_n_dev, CDR_ERR_INVALID, "cdr_search_batch_bf16: outputs required");
+    CDR_REQUIRE(s->dim % kBlockK == 0, CDR_ERR_UNSUPPORTED, "cdr_search_batch_bf16: dim %% 64 != 0");
+    if (nq == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::unique_lock<std::mutex> lk(s->mu);
+    ScanWorkspace &ws = s->ws[st];
+
+    const int kc = k <= 64 ? 128 : 256;          // candidates kept per query (>= k + 64)
+    const int cap = 32 * kc;
+    const int nq_pad = (nq + kBlockM - 1) / kBlockM * kBlockM;
+    const int dim = s->dim;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_q = up((size_t)nq_pad * dim * 2), b_tau = up((size_t)nq_pad * 4), b_cnt = up((size_t)nq_pad * 4);
+    const size_t b_ovf = up((size_t)nq_pad * 4), b_lists = up((size_t)nq * cap * 8);
+    if (cdr_ws_reserve(&ws.gemm_ws, &ws.gemm_ws_bytes, b_q + b_tau + b_cnt + b_ovf + b_lists) != CDR_OK) return CDR_ERR_OOM;
+    unsigned char *c = (unsigned char *)ws.gemm_ws;
+    __nv_bfloat16 *q_bf16 = (__nv_bfloat16 *)c; c += b_q;
+    float *tau = (float *)c; c += b_tau;
+    uint32_t *counts = (uint32_t *)c; c += b_cnt;
+    uint32_t *overflow = (uint32_t *)c; c += b_ovf;
+    uint64_t *lists = (uint64_t *)c;
+
+    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q_dev, q_bf16, tau, counts, overflow, nq, nq_pad, dim);
+    CDR_LAUNCH_CHECK();
+
+    CUtensorMap map_q, map_x;
+    int rc = make_map(&map_q, q_bf16, nq_pad, dim, kBlockM);
+    if (rc != CDR_OK) return rc;
+    rc = make_map(&map_x, s->emb_bf16, s->n_rows, dim, kBlockN);
+    if (rc != CDR_OK) return rc;
+
+    static bool attr_done[64] = {false};
+    if (!attr_done[s->device & 63]) {
+        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        attr_done[s->device & 63] = true;
+    }
+
+    GemmParams p;
+    p.tau = tau;
+    p.lists = lists;
+    p.counts = counts;
+    p.allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
+    p.n_rows = s->n_rows;
+    p.nq = nq;
+    p.m_tiles = nq_pad / kBlockM;
+    p.cap = cap;
+    p.n_tiles_total = (s->n_rows + kBlockN - 1) / kBlockN;
+    p.k_blocks = dim / kBlockK;
+    // multiplicative permutation of the tile order so every segment samples the whole corpus
+    int64_t mul = 1;
+    if (p.n_tiles_total > 2) {
+        mul = (int64_t)((double)p.n_tiles_total * 0.6180339887498949) | 1;
+        while (gcd64(mul, p.n_tiles_total) != 1) mul += 2;
+    }
+    p.perm_mul = mul;
+
+    int64_t begin = 0, seg = 16;
+    while (begin < p.n_tiles_total) {
+        int64_t end = begin + seg;
+        // do not leave a tiny trailing segment
+        if (end > p.n_tiles_total || p.n_tiles_total - end < seg) end = p.n_tiles_total;
+        p.tile_begin = begin;
+        p.tile_end = end;
+        const int64_t items = (end - begin) * p.m_tiles;
+        const int grid = (int)(items < s->sm_count ? items : s->sm_count);
+        cdr_prof_mark_begin(1, st);
+        gemm_topk_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(map_q, map_x, p);
+        CDR_LAUNCH_CHECK();
+        cdr_prof_mark_end(1, st);
+        if (end < p.n_tiles_total) {
+            if (kc == 128) select_compact_kernel<4><<<nq, 256, 0, st>>>(lists, counts, tau, overflow, cap);
+            else select_compact_kernel<8><<<nq, 256, 0, st>>>(lists, counts, tau, overflow, cap);
+            CDR_LAUNCH_CHECK();
+        }
+        begin = end;
+        seg *= 16;
+    }
+
+    rc = cdr_finalize_unsorted_launch(s, lists, counts, cap, kc, q_dev, nq, k, s->emb_f32 == nullptr, out_score_dev,
+                                      out_id_dev, out_n_dev, st);
+    if (rc != CDR_OK) return rc;
+
+    // ---- overflow / short-result check (one small D2H + sync), exact-lane fallback per query
+    std::vector<uint32_t> h_ovf(nq), h_cnt(nq);
+    std::vector<int32_t> h_n(nq);
+    CDR_CUDA(cudaMemcpyAsync(h_ovf.data(), overflow, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaMemcpyAsync(h_cnt.data(), counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaMemcpyAsync(h_n.data(), out_n_dev, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaStreamSynchronize(st));
+    const uint32_t *allow = p.allow;
+    for (int q = 0; q < nq; ++q) {
+        const bool over = h_ovf[q] != 0 || h_cnt[q] > (uint32_t)cap;
+        const bool shrt = h_n[q] < k && h_n[q] < s->n_valid;   // NaN rows / restrictive filters
+        if (!over && !shrt) continue;
+        CDR_REQUIRE(s->emb_f32 != nullptr, CDR_ERR_UNSUPPORTED,
+                    "cdr_search_batch_bf16: query %d needs the exact lane (candidate overflow or short result) "
+                    "but the store keeps no fp32 rows", q);
+        rc = cdr_exact_scan_launch(s, ws, q_dev + (size_t)q * dim, 1, allow, k,
+                                   out_score_dev + (size_t)q * k, out_id_dev + (size_t)q * k, out_n_dev + q, st);
+        if (rc != CDR_OK) return rc;
+    }
+    return CDR_OK;
 }

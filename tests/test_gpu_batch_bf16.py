@@ -1,0 +1,121 @@
+"""GPU tier: the batched bf16 tensor-core lane (K2, tcgen05) against the oracle.
+
+Bar: recall@k >= 0.999 against the fp32 truth.  Because every survivor is re-scored
+exactly (fp64 accumulate on the resident fp32 rows), the lane is expected to return the exact
+lane's ids for all but boundary-noise cases; both are asserted.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from cadence_rag_b200 import _ffi  # noqa: E402
+from cadence_rag_b200.store import DenseStore, SYNTH_CORPUS_SEED, SYNTH_QUERY_SEED  # noqa: E402
+from oracle import cpu_oracle as orc  # noqa: E402
+
+
+def _store(n, fp32=True, first_row=0):
+    s = DenseStore("chunks", n, dim=1024, device=0, fp32=fp32, bf16=True)
+    s.append_synthetic(n, first_row=first_row)
+    s.finalize()
+    return s
+
+
+def _recall(got_ids, got_n, want_lists):
+    hit = tot = 0
+    for i, want in enumerate(want_lists):
+        hit += len(set(want.tolist()) & set(got_ids[i, :int(got_n[i])].tolist()))
+        tot += len(want)
+    return hit / max(tot, 1)
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    n = 100_000
+    s = _store(n)
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n)
+    yield s, x
+    s.close()
+
+
+@pytest.mark.parametrize("nq,k", [(200, 50), (128, 10), (1, 50), (130, 100), (64, 192)])
+def test_batch_lane_recall_and_exactness(corpus, nq, k):
+    s, x = corpus
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 1000, nq)
+    ids, sc, cnt = s.search_batch(qs, k)
+    assert np.all(cnt == k)
+    e_ids, e_sc, e_cnt = s.search_exact(qs, k)
+    check = min(nq, 24)
+    want = [orc.exact_scan(qs[i], x, k, variant=orc.VARIANT_F64)[0] for i in range(check)]
+    assert _recall(ids, cnt, want) >= 0.999
+    # vs the exact lane over all queries
+    same = sum(int(np.array_equal(ids[i], e_ids[i])) for i in range(nq))
+    assert same >= int(np.floor(0.99 * nq)), f"{same}/{nq} queries identical to the exact lane"
+    assert _recall(ids, cnt, [e_ids[i] for i in range(nq)]) >= 0.999
+    for i in range(nq):
+        if np.array_equal(ids[i], e_ids[i]):
+            assert np.array_equal(sc[i].view(np.uint64), e_sc[i].view(np.uint64))
+    assert np.all(np.diff(sc, axis=1) <= 0)
+    # device-buffer entry point gives the same bits
+    d_ids, d_sc, d_cnt = s.search_batch(torch.from_numpy(qs).cuda(), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_ids.cpu().numpy(), ids)
+
+
+def test_batch_lane_with_filter(corpus):
+    s, x = corpus
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 5000, 40)
+    for spec in (dict(tag_mask=0b11), dict(call_slots=list(range(0, 500, 3))), dict(call_slots=[1, 2])):
+        allow, count = s.filter_bitmap(**spec)
+        ids, sc, cnt = s.search_batch(qs, 50, allow)
+        e_ids, e_sc, e_cnt = s.search_exact(qs, 50, allow)
+        assert np.array_equal(cnt, e_cnt)
+        assert _recall(ids, cnt, [e_ids[i, :int(e_cnt[i])] for i in range(40)]) >= 0.999
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 4096, 5000, 70_000])
+def test_batch_lane_ragged_sizes(n):
+    s = _store(n)
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 0, 9)
+    ids, sc, cnt = s.search_batch(qs, 50)
+    e_ids, e_sc, e_cnt = s.search_exact(qs, 50)
+    assert np.array_equal(cnt, e_cnt) and np.all(cnt == min(n, 50))
+    assert _recall(ids, cnt, [e_ids[i, :int(e_cnt[i])] for i in range(9)]) >= 0.999
+    s.close()
+
+
+def test_batch_lane_bf16_only_store():
+    """C5 residency: bf16 rows only.  Truth = fp32 query x bf16-valued rows, fp64 accumulate."""
+    n = 50_000
+    s = _store(n, fp32=False)
+    xb = s.read_rows(0, n, ("bf16",))["bf16"]
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 77, 32)
+    ids, sc, cnt = s.search_batch(qs, 50)
+    want = [orc.exact_scan_bf16rows(qs[i], xb, 50) for i in range(32)]
+    assert _recall(ids, cnt, [w[0] for w in want]) >= 0.999
+    for i in range(32):
+        if ids[i].tolist() == want[i][0].tolist():
+            assert np.allclose(sc[i], want[i][1], rtol=1e-12)
+    with pytest.raises(_ffi.DenseEngineError):
+        s.search_exact(qs, 50)          # no fp32 rows resident -> loud error, no silent path
+    s.close()
+
+
+def test_batch_lane_overflow_falls_back_to_exact_lane():
+    """Adversarial corpus: thousands of identical rows overflow the candidate lists; the wrapper
+    re-runs those queries on the exact lane, so results stay exact (ties by id)."""
+    rng = np.random.default_rng(3)
+    n = 30_000
+    x = rng.standard_normal((n, 1024)).astype(np.float32)
+    x[5000:25000] = x[5000]
+    q = (x[5000] + 0.1 * rng.standard_normal(1024)).astype(np.float32)
+    s = DenseStore("chunks", n, dim=1024, device=0)
+    s.append(x, ids=np.arange(1, n + 1))
+    s.finalize()
+    qs = np.stack([q, rng.standard_normal(1024).astype(np.float32)])
+    ids, sc, cnt = s.search_batch(qs, 50)
+    for i in range(2):
+        w_ids, w_sc = orc.exact_scan(qs[i], x, 50, variant=orc.VARIANT_F64)
+        assert ids[i].tolist() == w_ids.tolist()
+    s.close()
