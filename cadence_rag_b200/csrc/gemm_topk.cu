@@ -32,6 +32,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                           const uint32_t *allow, int k, double *out_score, int64_t *out_id,
@@ -62,6 +63,28 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// same, multicast: the box lands at the same smem offset in every CTA of `mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx for the bytes it got
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar,
+                                               uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -81,6 +104,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M128 N256 K16
@@ -145,6 +175,11 @@ struct GemmParams {
     int k_blocks;              // D / 64
 };
 
+// kCluster == 2: the two CTAs of a cluster work on the same corpus tile with different query
+// tiles; each loads half of the B (corpus) box and multicasts it to both, halving the L2->SM
+// traffic of the large operand.  A stage may be refilled only when BOTH CTAs' MMAs have drained
+// it, so the MMA warps commit to the empty barrier of both CTAs.
+template <int kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const GemmParams p)
@@ -169,7 +204,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], kCluster);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
@@ -180,20 +215,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (warp == 2) tmem_alloc(tmem_base_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();     // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
+    const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
+    const int mt_per = p.m_tiles / kCluster;             // query tiles per CTA of the cluster
     const int64_t seg_tiles = p.tile_end - p.tile_begin;
-    const int64_t n_items = seg_tiles * p.m_tiles;      // item w -> (tile_begin + w / m_tiles, w % m_tiles)
-    const int64_t G = gridDim.x;
+    const int64_t n_items = seg_tiles * mt_per;          // item w -> (tile_begin + w / mt_per, (w % mt_per)*kCluster + crank)
+    const int64_t G = gridDim.x / kCluster;
+    const int64_t w0 = blockIdx.x / kCluster;
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t w = blockIdx.x; w < n_items; w += G) {
-                const int64_t tj = p.tile_begin + w / p.m_tiles;
-                const int mt = (int)(w % p.m_tiles);
+            for (int64_t w = w0; w < n_items; w += G) {
+                const int64_t tj = p.tile_begin + w / mt_per;
+                const int mt = (int)(w % mt_per) * kCluster + (int)crank;
                 const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
                 for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
                     const int s = it % kStages;
@@ -202,14 +241,21 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                     unsigned char *a = tiles + (size_t)s * kStageBytes;
                     tma_load_2d(a, &map_q, kb * kBlockK, mt * kBlockM, &full_bar[s]);
-                    tma_load_2d(a + kABytes, &map_x, kb * kBlockK, (int)(nt * kBlockN), &full_bar[s]);
+                    if (kCluster == 1) {
+                        tma_load_2d(a + kABytes, &map_x, kb * kBlockK, (int)(nt * kBlockN), &full_bar[s]);
+                    } else {
+                        // this CTA's half of the corpus box (128 rows), delivered to both CTAs
+                        const int half = kBlockN / kCluster;
+                        tma_load_2d_mc(a + kABytes + (size_t)crank * (kBBytes / kCluster), &map_x, kb * kBlockK,
+                                       (int)(nt * kBlockN) + (int)crank * half, &full_bar[s], (uint16_t)0x3);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         uint32_t it = 0, tile_no = 0;
-        for (int64_t w = blockIdx.x; w < n_items; w += G, ++tile_no) {
+        for (int64_t w = w0; w < n_items; w += G, ++tile_no) {
             const uint32_t buf = tile_no & 1u;
             const uint32_t use = tile_no >> 1;                    // how many times this buffer was used before
             mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
@@ -230,7 +276,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         umma_bf16(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), kInstrDesc,
                                   (kb | k4) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);                   // smem stage free when these MMAs retire
+                    // smem stage free when these MMAs retire (in every CTA that TMA-writes it)
+                    if (kCluster == 1) umma_commit(&empty_bar[s]);
+                    else umma_commit_mc(&empty_bar[s], (uint16_t)0x3);
                     if (kb == p.k_blocks - 1) umma_commit(&tmem_full[buf]);
                 }
                 __syncwarp();
@@ -240,9 +288,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ---------------------------------------------------------------- epilogue
         const int ew = warp & 3;                                  // TMEM lane quarter of this warp
         uint32_t tile_no = 0;
-        for (int64_t w = blockIdx.x; w < n_items; w += G, ++tile_no) {
-            const int64_t tj = p.tile_begin + w / p.m_tiles;
-            const int mt = (int)(w % p.m_tiles);
+        for (int64_t w = w0; w < n_items; w += G, ++tile_no) {
+            const int64_t tj = p.tile_begin + w / mt_per;
+            const int mt = (int)(w % mt_per) * kCluster + (int)crank;
             const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
             const int64_t row0 = nt * kBlockN;
             const int q = mt * kBlockM + ew * 32 + lane;
@@ -298,6 +346,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();     // no CTA exits while its peer may still multicast into it
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -432,6 +481,13 @@ int make_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_
 
 int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
+// 2 = multicast the corpus tile across a 2-CTA cluster (default), 1 = independent CTAs.
+// CADENCE_K2_CLUSTER=1 in the environment selects the latter (A/B measurements).
+int g_k2_cluster = [] {
+    const char *e = getenv("CADENCE_K2_CLUSTER");
+    return (e && e[0] == '1') ? 1 : 2;
+}();
+
 }  // namespace
 
 extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
@@ -473,12 +529,16 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     CUtensorMap map_q, map_x;
     int rc = make_map(&map_q, q_bf16, nq_pad, dim, kBlockM);
     if (rc != CDR_OK) return rc;
-    rc = make_map(&map_x, s->emb_bf16, s->n_rows, dim, kBlockN);
+    // B-tile multicast across a 2-CTA cluster needs an even number of query tiles
+    const int m_tiles = nq_pad / kBlockM;
+    const int cluster = (m_tiles % 2 == 0 && g_k2_cluster == 2) ? 2 : 1;
+    rc = make_map(&map_x, s->emb_bf16, s->n_rows, dim, kBlockN / cluster);
     if (rc != CDR_OK) return rc;
 
     static bool attr_done[64] = {false};
     if (!attr_done[s->device & 63]) {
-        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr_done[s->device & 63] = true;
     }
 
@@ -489,7 +549,7 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     p.allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
     p.n_rows = s->n_rows;
     p.nq = nq;
-    p.m_tiles = nq_pad / kBlockM;
+    p.m_tiles = m_tiles;
     p.cap = cap;
     p.n_tiles_total = (s->n_rows + kBlockN - 1) / kBlockN;
     p.k_blocks = dim / kBlockK;
@@ -501,17 +561,37 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     }
     p.perm_mul = mul;
 
-    int64_t begin = 0, seg = 16;
+    // Segment sizes: 16 tiles, then at most kSegGrowth x (tiles already seen).  With tau = the
+    // KC-th best of the rows seen so far, a segment of g x seen rows appends ~ g*KC keys per query
+    // (cap = 32*KC leaves a 2.6x margin over the expectation at g = 12).
+    constexpr int64_t kSegGrowth = 12;
+    int64_t begin = 0;
     while (begin < p.n_tiles_total) {
-        int64_t end = begin + seg;
-        // do not leave a tiny trailing segment
-        if (end > p.n_tiles_total || p.n_tiles_total - end < seg) end = p.n_tiles_total;
+        int64_t end = begin == 0 ? 16 : begin + kSegGrowth * begin;
+        if (end > p.n_tiles_total) end = p.n_tiles_total;
         p.tile_begin = begin;
         p.tile_end = end;
-        const int64_t items = (end - begin) * p.m_tiles;
-        const int grid = (int)(items < s->sm_count ? items : s->sm_count);
+        const int64_t items = (end - begin) * (p.m_tiles / cluster);
+        int64_t max_clusters = s->sm_count / cluster;
+        const int grid = (int)(items < max_clusters ? items : max_clusters) * cluster;
         cdr_prof_mark_begin(1, st);
-        gemm_topk_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(map_q, map_x, p);
+        if (cluster == 1) {
+            gemm_topk_kernel<1><<<grid, kGemmThreads, kGemmSmem, st>>>(map_q, map_x, p);
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(kGemmThreads);
+            cfg.dynamicSmemBytes = kGemmSmem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2>, map_q, map_x, p));
+        }
         CDR_LAUNCH_CHECK();
         cdr_prof_mark_end(1, st);
         if (end < p.n_tiles_total) {
@@ -520,7 +600,6 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
             CDR_LAUNCH_CHECK();
         }
         begin = end;
-        seg *= 16;
     }
 
     rc = cdr_finalize_unsorted_launch(s, lists, counts, cap, kc, q_dev, nq, k, s->emb_f32 == nullptr, out_score_dev,
