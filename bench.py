@@ -111,6 +111,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(args, world):
+    return {"workload": f"BASELINE configs[1]: {args.rows} x {DIM} fp32 corpus, single-query exact cosine scan + "
+                        f"top-k={TOPK}; step = {args.queries_per_step} distinct queries, one scan of the corpus per query",
+            "rows": args.rows, "dim": DIM, "k": TOPK, "queries_per_step": args.queries_per_step}
+
+
 # ----------------------------------------------------------------------------- CPU baseline
 def cpu_baseline(rows_total: int, sample_rows: int, sample_queries: int, threads: int):
     """pgvector-restated exact scan (oracle/pgvector_restated.c) on a bounded sample, scaled to the
@@ -163,8 +169,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"exact-scan dense lane, {args.rows} x {DIM} fp32, top-k={TOPK}, single-query scans",
-                       "rows": args.rows, "dim": DIM, "k": TOPK},
+            "config": workload_config(args, 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -209,8 +214,11 @@ def run_batch_bf16(args):
     e_ids, _, _ = store.search_exact(q_dev[total - 1][:64], TOPK)
     got = out[0][:64].cpu().numpy(); want = e_ids.cpu().numpy()
     recall = float(np.mean([len(set(got[i]) & set(want[i])) / TOPK for i in range(64)]))
-    # e2e with host buffers
-    q_host = q_dev.cpu().numpy()
+    # e2e with host buffers (pinned)
+    q_pinned = torch.empty(q_dev.shape, dtype=torch.float32, pin_memory=True)
+    q_pinned.copy_(q_dev); torch.cuda.synchronize()
+    q_host = q_pinned.numpy()
+    store.search_batch(q_host[0], TOPK)
     t0 = time.perf_counter()
     for s in range(args.warmup, total):
         store.search_batch(q_host[s], TOPK)
@@ -273,7 +281,9 @@ def main():
     total_steps = args.warmup + args.steps
     # distinct queries for every step, resident in HBM before the timed region
     q_dev = synth_rows_device(SYNTH_QUERY_SEED, 0, total_steps * Q, DIM, device=local_rank).view(total_steps, Q, DIM)
-    q_host = q_dev.cpu().numpy()
+    q_pinned = torch.empty(q_dev.shape, dtype=torch.float32, pin_memory=True)   # e2e inputs: pinned host memory
+    q_pinned.copy_(q_dev)
+    q_host = q_pinned.numpy()
     torch.cuda.synchronize()
 
     def barrier():
@@ -369,13 +379,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: {args.rows} x {DIM} fp32 corpus, single-query exact cosine "
-                                   f"scan + top-k={TOPK}; step = {Q} distinct queries, one scan of the resident "
-                                   f"corpus per query",
-                       "rows": args.rows, "dim": DIM, "k": TOPK, "queries_per_step": Q,
-                       "sharding": f"rows/{world}" if world > 1 else "none",
-                       "l2": "inputs larger than L2 (shard bytes >> 126 MB), distinct queries every step",
-                       "single_query_latency_ms_p50": lat[len(lat) // 2], "single_query_latency_ms_min": lat[0]},
+            "config": dict(workload_config(args, world), sharding=f"rows/{world}" if world > 1 else "none",
+                           l2="inputs larger than L2 (shard bytes >> 126 MB), distinct queries every step",
+                           single_query_latency_ms_p50=lat[len(lat) // 2], single_query_latency_ms_min=lat[0]),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,

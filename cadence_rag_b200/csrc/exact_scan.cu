@@ -287,31 +287,74 @@ struct FinalizeParams {
     int32_t *out_n;           // [nq]
 };
 
-template <int NPL>
-__global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams p)
+// fp64 cosine of query (a-values in smem as float) x one resident row; all lanes return the result.
+__device__ __forceinline__ void rescore_accumulate(const float4 a, const float4 b, double &ab, double &bb)
+{
+    ab = __fma_rn((double)a.x, (double)b.x, ab);
+    ab = __fma_rn((double)a.y, (double)b.y, ab);
+    ab = __fma_rn((double)a.z, (double)b.z, ab);
+    ab = __fma_rn((double)a.w, (double)b.w, ab);
+    bb = __fma_rn((double)b.x, (double)b.x, bb);
+    bb = __fma_rn((double)b.y, (double)b.y, bb);
+    bb = __fma_rn((double)b.z, (double)b.z, bb);
+    bb = __fma_rn((double)b.w, (double)b.w, bb);
+}
+__device__ __forceinline__ float4 load_row_vec(const float *rows, const __nv_bfloat16 *bf16_rows, size_t row,
+                                               int dim, int v)
+{
+    if (rows != nullptr) return __ldg(reinterpret_cast<const float4 *>(rows + row * dim) + v);
+    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(bf16_rows + row * dim) + v);
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
+                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+}
+
+template <int NPL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const FinalizeParams p)
 {
     constexpr int KC = NPL * 32;
-    __shared__ uint64_t s_lists[8 * KC];
+    __shared__ uint64_t s_lists[WARPS * KC];
     __shared__ double s_score[KC];
     __shared__ int64_t s_id[KC];
     __shared__ int s_valid[KC];
+    __shared__ int s_nvalid;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x;
     const uint64_t *base = p.lists + (size_t)qi * p.n_lists * KC;
+    if (threadIdx.x == 0) s_nvalid = 0;
 
     uint64_t k[NPL];
 #pragma unroll
     for (int i = 0; i < NPL; ++i) k[i] = CDR_EMPTY_KEY;
     if (p.counts == nullptr) {
-        for (int l = warp; l < p.n_lists; l += 8) warp_merge_topk<NPL>(k, base + (size_t)l * KC, lane);
+        // sorted lists: software-pipelined so the next list's keys are in flight during a merge
+        uint64_t nxt[NPL];
+        int l = warp;
+        if (l < p.n_lists) {
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) nxt[i] = base[(size_t)l * KC + (KC - 1 - (i * 32 + lane))];
+        }
+        while (l < p.n_lists) {
+            uint64_t cur[NPL];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) cur[i] = nxt[i];
+            const int ln = l + WARPS;
+            if (ln < p.n_lists) {
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) nxt[i] = base[(size_t)ln * KC + (KC - 1 - (i * 32 + lane))];
+            }
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) k[i] = k[i] > cur[i] ? k[i] : cur[i];   // cur is already reversed
+            warp_bitonic_merge_desc<NPL>(k, lane);
+            l = ln;
+        }
     } else {
         // one unsorted list per query (K2 candidates): sort KC-sized chunks, fold them in
         const uint64_t *list = p.lists + (size_t)qi * p.cap;
         uint32_t n = p.counts[qi];
         if (n > (uint32_t)p.cap) n = p.cap;
         const int chunks = (int)((n + KC - 1) / KC);
-        for (int ch = warp; ch < chunks; ch += 8) {
+        for (int ch = warp; ch < chunks; ch += WARPS) {
             uint64_t c[NPL];
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
@@ -329,18 +372,17 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams
 #pragma unroll
     for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
 #pragma unroll
-    for (int step = 1; step < 8; step <<= 1) {
-        __syncthreads();
-        if ((warp & (2 * step - 1)) == 0) warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
+    for (int step = 1; step < WARPS; step <<= 1) {
         __syncthreads();
         if ((warp & (2 * step - 1)) == 0) {
+            warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+            for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];   // own slot: nobody reads it at this level
         }
     }
     __syncthreads();
 
-    // ---- fp64 re-score: warp w takes candidates w, w+8, ...
+    // ---- fp64 re-score: warp w takes candidates w, w+WARPS, ...; two rows in flight per warp
     const float *qrow = p.queries + (size_t)qi * p.dim;
     const int nvec = p.dim >> 2;   // float4 per row
     double aa = 0.0;
@@ -352,62 +394,50 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams
         aa = __fma_rn((double)a.w, (double)a.w, aa);
     }
     aa = warp_sum_f64(aa);
-    for (int c = warp; c < KC; c += 8) {
-        const uint64_t key = s_lists[c];
-        if (key == CDR_EMPTY_KEY) {
-            if (lane == 0) { s_valid[c] = 0; s_score[c] = 0.0; s_id[c] = -1; }
-            continue;
-        }
-        const uint32_t row = cdr_key_row(key);
-        double ab = 0.0, bb = 0.0;
-        if (p.rows != nullptr) {
-            const float4 *xr = reinterpret_cast<const float4 *>(p.rows + (size_t)row * p.dim);
+    int my_valid = 0;
+    for (int c0 = warp; c0 < KC; c0 += 2 * WARPS) {
+        const int c1 = c0 + WARPS;
+        const uint64_t key0 = s_lists[c0];
+        const uint64_t key1 = c1 < KC ? s_lists[c1] : CDR_EMPTY_KEY;
+        const bool ok0 = key0 != CDR_EMPTY_KEY, ok1 = key1 != CDR_EMPTY_KEY;
+        const size_t row0 = ok0 ? cdr_key_row(key0) : 0, row1 = ok1 ? cdr_key_row(key1) : 0;
+        double ab0 = 0.0, bb0 = 0.0, ab1 = 0.0, bb1 = 0.0;
+        if (ok0 | ok1) {
             for (int v = lane; v < nvec; v += 32) {
-                const float4 b = __ldg(xr + v);
+                const float4 b0 = load_row_vec(p.rows, p.bf16_rows, row0, p.dim, v);
+                const float4 b1 = load_row_vec(p.rows, p.bf16_rows, row1, p.dim, v);
                 const float4 a = __ldg(reinterpret_cast<const float4 *>(qrow) + v);
-                ab = __fma_rn((double)a.x, (double)b.x, ab);
-                ab = __fma_rn((double)a.y, (double)b.y, ab);
-                ab = __fma_rn((double)a.z, (double)b.z, ab);
-                ab = __fma_rn((double)a.w, (double)b.w, ab);
-                bb = __fma_rn((double)b.x, (double)b.x, bb);
-                bb = __fma_rn((double)b.y, (double)b.y, bb);
-                bb = __fma_rn((double)b.z, (double)b.z, bb);
-                bb = __fma_rn((double)b.w, (double)b.w, bb);
-            }
-        } else {
-            const uint2 *xr = reinterpret_cast<const uint2 *>(p.bf16_rows + (size_t)row * p.dim);
-            for (int v = lane; v < nvec; v += 32) {
-                const uint2 raw = __ldg(xr + v);
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(qrow) + v);
-                const float b0 = __uint_as_float(raw.x << 16), b1 = __uint_as_float(raw.x & 0xFFFF0000u);
-                const float b2 = __uint_as_float(raw.y << 16), b3 = __uint_as_float(raw.y & 0xFFFF0000u);
-                ab = __fma_rn((double)a.x, (double)b0, ab);
-                ab = __fma_rn((double)a.y, (double)b1, ab);
-                ab = __fma_rn((double)a.z, (double)b2, ab);
-                ab = __fma_rn((double)a.w, (double)b3, ab);
-                bb = __fma_rn((double)b0, (double)b0, bb);
-                bb = __fma_rn((double)b1, (double)b1, bb);
-                bb = __fma_rn((double)b2, (double)b2, bb);
-                bb = __fma_rn((double)b3, (double)b3, bb);
+                rescore_accumulate(a, b0, ab0, bb0);
+                rescore_accumulate(a, b1, ab1, bb1);
             }
         }
-        ab = warp_sum_f64(ab);
-        bb = warp_sum_f64(bb);
-        if (lane == 0) {
-            double sim = __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb)));
-            if (sim > 1.0) sim = 1.0;
-            else if (sim < -1.0) sim = -1.0;
-            const double dist = __dsub_rn(1.0, sim);       // pgvector cosine_distance (float8)
-            s_score[c] = __dsub_rn(1.0, dist);             // SQL: 1 - (embedding <=> q)
-            s_id[c] = p.ids[row];
-            s_valid[c] = 1;
+        ab0 = warp_sum_f64(ab0); bb0 = warp_sum_f64(bb0);
+        ab1 = warp_sum_f64(ab1); bb1 = warp_sum_f64(bb1);
+        if (lane < 2) {
+            const int c = lane == 0 ? c0 : c1;
+            const bool ok = lane == 0 ? ok0 : ok1;
+            if (c < KC) {
+                if (ok) {
+                    const double ab = lane == 0 ? ab0 : ab1, bb = lane == 0 ? bb0 : bb1;
+                    double sim = __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb)));
+                    if (sim > 1.0) sim = 1.0;
+                    else if (sim < -1.0) sim = -1.0;
+                    const double dist = __dsub_rn(1.0, sim);       // pgvector cosine_distance (float8)
+                    s_score[c] = __dsub_rn(1.0, dist);             // SQL: 1 - (embedding <=> q)
+                    s_id[c] = p.ids[lane == 0 ? row0 : row1];
+                    s_valid[c] = 1;
+                    my_valid += 1;
+                } else {
+                    s_valid[c] = 0; s_score[c] = 0.0; s_id[c] = -1;
+                }
+            }
         }
     }
+    if (my_valid) atomicAdd(&s_nvalid, my_valid);
     __syncthreads();
 
     // ---- final order by rank counting
-    int n_valid = 0;
-    for (int c = 0; c < KC; ++c) n_valid += s_valid[c];
+    const int n_valid = s_nvalid;
     for (int c = threadIdx.x; c < KC; c += blockDim.x) {
         if (!s_valid[c]) continue;
         const double sc = s_score[c];
@@ -427,6 +457,20 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams
         p.out_id[(size_t)qi * p.k + c] = -1;
     }
     if (threadIdx.x == 0) p.out_n[qi] = n_out;
+}
+
+// one launch helper for every candidate width
+static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_t st)
+{
+    if (kc == 64) scan_finalize_kernel<2, 32><<<nq, 1024, 0, st>>>(fp);
+    else if (kc == 128) scan_finalize_kernel<4, 32><<<nq, 1024, 0, st>>>(fp);
+    else if (kc == 256) scan_finalize_kernel<8, 16><<<nq, 512, 0, st>>>(fp);
+    else {
+        cdr_set_error("finalize: candidate width %d not built", kc);
+        return CDR_ERR_UNSUPPORTED;
+    }
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
 }
 
 template <int J, int RPW, int NPL>
@@ -486,9 +530,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     fp.out_score = out_score;
     fp.out_id = out_id;
     fp.out_n = out_n;
-    scan_finalize_kernel<NPL><<<nq, 256, 0, st>>>(fp);
-    CDR_LAUNCH_CHECK();
-    return CDR_OK;
+    return launch_finalize(fp, KC, nq, st);
 }
 
 template <int NPL>
@@ -541,13 +583,5 @@ int cdr_finalize_unsorted_launch(cdr_store *s, const uint64_t *lists, const uint
     fp.out_score = out_score;
     fp.out_id = out_id;
     fp.out_n = out_n;
-    if (kc == 64) scan_finalize_kernel<2><<<nq, 256, 0, st>>>(fp);
-    else if (kc == 128) scan_finalize_kernel<4><<<nq, 256, 0, st>>>(fp);
-    else if (kc == 256) scan_finalize_kernel<8><<<nq, 256, 0, st>>>(fp);
-    else {
-        cdr_set_error("finalize: candidate width %d not built", kc);
-        return CDR_ERR_UNSUPPORTED;
-    }
-    CDR_LAUNCH_CHECK();
-    return CDR_OK;
+    return launch_finalize(fp, kc, nq, st);
 }

@@ -53,7 +53,12 @@ constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 256;
 constexpr int kTmemCols = 512;
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// epilogue append staging: each of the 128 epilogue threads owns kBufN (key, query) slots in
+// shared memory, laid out [slot][thread]; they are flushed to the global candidate lists in
+// batches (kBufN independent atomics in flight) instead of one blocking atomic per hit
+constexpr int kBufN = 16;
+constexpr size_t kBufBytes = (size_t)kBufN * 128 * (8 + 2);
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBufBytes;
 
 // ---- PTX wrappers (tcgen05 / TMA); forms follow the PTX ISA for sm_100a
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
@@ -194,6 +199,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t *tmem_full = bars + 2 * kStages;     // [2]
     uint64_t *tmem_empty = bars + 2 * kStages + 2;  // [2]
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    uint64_t *buf_key = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [kBufN][128]
+    uint16_t *buf_q = reinterpret_cast<uint16_t *>(buf_key + kBufN * 128);                            // [kBufN][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -287,13 +294,27 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue
         const int ew = warp & 3;                                  // TMEM lane quarter of this warp
+        const int et = ew * 32 + lane;                            // epilogue thread 0..127
+        int nbuf = 0;
+        // flush this thread's staged appends: all atomics first (independent, pipelined), then the stores
+        auto flush = [&]() {
+            uint32_t base[kBufN];
+#pragma unroll
+            for (int i = 0; i < kBufN; ++i)
+                if (i < nbuf) base[i] = atomicAdd(&p.counts[buf_q[i * 128 + et]], 1u);
+#pragma unroll
+            for (int i = 0; i < kBufN; ++i)
+                if (i < nbuf && base[i] < (uint32_t)p.cap)
+                    p.lists[(size_t)buf_q[i * 128 + et] * p.cap + base[i]] = buf_key[i * 128 + et];
+            nbuf = 0;
+        };
         uint32_t tile_no = 0;
         for (int64_t w = w0; w < n_items; w += G, ++tile_no) {
             const int64_t tj = p.tile_begin + w / mt_per;
             const int mt = (int)(w % mt_per) * kCluster + (int)crank;
             const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
             const int64_t row0 = nt * kBlockN;
-            const int q = mt * kBlockM + ew * 32 + lane;
+            const int q = mt * kBlockM + et;
             const bool q_ok = q < p.nq;
             const float tau = q_ok ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
             int64_t lim = p.n_rows - row0;                        // valid columns in this tile
@@ -313,8 +334,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                 for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
                 const int rem = (int)(lim - c * 32);
-                if (m >= tau || rem < 32) {
-                    // slow path: exact per-element test, filter bit, append
+                if (m >= tau) {
+                    // slow path (rare): exact per-element test, filter bit, staged append
                     uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -325,14 +346,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         mask &= __ldg(&p.allow[(row0 + c * 32) >> 5]);
                     }
                     if (mask != 0) {
-                        const uint32_t cnt = __popc(mask);
-                        uint32_t base = atomicAdd(&p.counts[q], cnt);
-                        uint64_t *dst = p.lists + (size_t)q * p.cap;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if ((mask >> j) & 1u) {
-                                if (base < (uint32_t)p.cap) dst[base] = cdr_pack_key(v[j], (uint32_t)(row0 + c * 32 + j));
-                                ++base;
+                                if (nbuf == kBufN) flush();
+                                buf_key[nbuf * 128 + et] = cdr_pack_key(v[j], (uint32_t)(row0 + c * 32 + j));
+                                buf_q[nbuf * 128 + et] = (uint16_t)q;
+                                ++nbuf;
                             }
                         }
                     }
@@ -342,6 +362,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
+        if (nbuf > 0) flush();
     }
 
     tc_fence_before();
@@ -503,6 +524,18 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     CDR_REQUIRE(out_score_dev && out_id_dev && out_n_dev, CDR_ERR_INVALID, "cdr_search_batch_bf16: outputs required");
     CDR_REQUIRE(s->dim % kBlockK == 0, CDR_ERR_UNSUPPORTED, "cdr_search_batch_bf16: dim %% 64 != 0");
     if (nq == 0) return CDR_OK;
+    // the epilogue stages 16-bit query indices: larger batches run as chunks of 16384 queries
+    constexpr int kMaxBatch = 16384;
+    if (nq > kMaxBatch) {
+        for (int q0 = 0; q0 < nq; q0 += kMaxBatch) {
+            const int m = nq - q0 < kMaxBatch ? nq - q0 : kMaxBatch;
+            int rc = cdr_search_batch_bf16(s, q_dev + (size_t)q0 * s->dim, m, k, allow_dev,
+                                           out_score_dev + (size_t)q0 * k, out_id_dev + (size_t)q0 * k,
+                                           out_n_dev + q0, stream);
+            if (rc != CDR_OK) return rc;
+        }
+        return CDR_OK;
+    }
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     std::unique_lock<std::mutex> lk(s->mu);
