@@ -178,7 +178,24 @@ struct GemmParams {
     int64_t perm_mul;          // tile permutation multiplier (coprime with n_tiles_total)
     int64_t tile_begin, tile_end;   // permuted tile index range of this segment
     int k_blocks;              // D / 64
+    int debug_no_append;       // measurement aid (CADENCE_K2_DRYRUN=1): treat tau as +inf => pure GEMM + max
 };
+
+// Flush one epilogue thread's staged appends to the global candidate lists: all atomics first
+// (independent, so their round trips overlap), then the stores.  Deliberately NOT inlined: the
+// epilogue's hot loop must stay small enough for the instruction cache.
+__device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int cap, const uint64_t *buf_key,
+                                          const uint16_t *buf_q, int et, int nbuf)
+{
+    uint32_t base[kBufN];
+#pragma unroll
+    for (int i = 0; i < kBufN; ++i)
+        if (i < nbuf) base[i] = atomicAdd(&counts[buf_q[i * 128 + et]], 1u);
+#pragma unroll
+    for (int i = 0; i < kBufN; ++i)
+        if (i < nbuf && base[i] < (uint32_t)cap)
+            lists[(size_t)buf_q[i * 128 + et] * cap + base[i]] = buf_key[i * 128 + et];
+}
 
 // kCluster == 2: the two CTAs of a cluster work on the same corpus tile with different query
 // tiles; each loads half of the B (corpus) box and multicasts it to both, halving the L2->SM
@@ -296,18 +313,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int ew = warp & 3;                                  // TMEM lane quarter of this warp
         const int et = ew * 32 + lane;                            // epilogue thread 0..127
         int nbuf = 0;
-        // flush this thread's staged appends: all atomics first (independent, pipelined), then the stores
-        auto flush = [&]() {
-            uint32_t base[kBufN];
-#pragma unroll
-            for (int i = 0; i < kBufN; ++i)
-                if (i < nbuf) base[i] = atomicAdd(&p.counts[buf_q[i * 128 + et]], 1u);
-#pragma unroll
-            for (int i = 0; i < kBufN; ++i)
-                if (i < nbuf && base[i] < (uint32_t)p.cap)
-                    p.lists[(size_t)buf_q[i * 128 + et] * p.cap + base[i]] = buf_key[i * 128 + et];
-            nbuf = 0;
-        };
         uint32_t tile_no = 0;
         for (int64_t w = w0; w < n_items; w += G, ++tile_no) {
             const int64_t tj = p.tile_begin + w / mt_per;
@@ -316,7 +321,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int64_t row0 = nt * kBlockN;
             const int q = mt * kBlockM + et;
             const bool q_ok = q < p.nq;
-            const float tau = q_ok ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
+            const float tau = (q_ok && !p.debug_no_append) ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
             int64_t lim = p.n_rows - row0;                        // valid columns in this tile
             if (lim > kBlockN) lim = kBlockN;
             const uint32_t buf = tile_no & 1u;
@@ -345,14 +350,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         // 32 consecutive rows starting at a multiple of 32: exactly one bitmap word
                         mask &= __ldg(&p.allow[(row0 + c * 32) >> 5]);
                     }
-                    if (mask != 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if ((mask >> j) & 1u) {
-                                if (nbuf == kBufN) flush();
-                                buf_key[nbuf * 128 + et] = cdr_pack_key(v[j], (uint32_t)(row0 + c * 32 + j));
-                                buf_q[nbuf * 128 + et] = (uint16_t)q;
-                                ++nbuf;
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t mh = (mask >> (16 * h)) & 0xFFFFu;
+                        if (mh != 0) {
+                            if (nbuf + __popc(mh) > kBufN) {       // make room for up to 16 hits
+                                flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
+                                nbuf = 0;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if ((mh >> j) & 1u) {
+                                    buf_key[nbuf * 128 + et] =
+                                        cdr_pack_key(v[16 * h + j], (uint32_t)(row0 + c * 32 + 16 * h + j));
+                                    buf_q[nbuf * 128 + et] = (uint16_t)q;
+                                    ++nbuf;
+                                }
                             }
                         }
                     }
@@ -362,7 +375,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
-        if (nbuf > 0) flush();
+        if (nbuf > 0) flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
     }
 
     tc_fence_before();
@@ -586,6 +599,8 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     p.cap = cap;
     p.n_tiles_total = (s->n_rows + kBlockN - 1) / kBlockN;
     p.k_blocks = dim / kBlockK;
+    static const bool dryrun = [] { const char *e = getenv("CADENCE_K2_DRYRUN"); return e && e[0] == '1'; }();
+    p.debug_no_append = dryrun ? 1 : 0;
     // multiplicative permutation of the tile order so every segment samples the whole corpus
     int64_t mul = 1;
     if (p.n_tiles_total > 2) {
