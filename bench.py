@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bf16-only", action="store_true", help="batch_bf16: keep only bf16 rows resident (C5 residency)")
     ap.add_argument("--workload", default="exact_f32", choices=["exact_f32", "batch_bf16"],
                     help="exact_f32 = BASELINE configs[1] (default, the contract line); "
                          "batch_bf16 = configs[2]: 10M x 1024 bf16, 1024 queries on the tcgen05 lane")
@@ -178,72 +179,123 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- B200 arm
 def run_batch_bf16(args):
-    """Secondary line (BASELINE configs[2]): rows x 1024 bf16 corpus, 1024 queries per step on the
-    tcgen05 lane (K2) + exact re-score.  roofline: tensor-bound, 2*nq*rows*dim FLOP per step."""
+    """Secondary line (BASELINE configs[2] on 1 GPU, configs[4] row-sharded on N GPUs): rows x 1024
+    bf16 corpus, 1024 queries per step on the tcgen05 lane (K2) + exact re-score; with N > 1 the
+    corpus is row-sharded and the per-rank top-k lists are all-gathered and merged (K4).
+    roofline: tensor-bound, 2*nq*rows_local*dim FLOP per step per GPU."""
     import ctypes
     import numpy as np
     import torch
+    import torch.distributed as dist
     from cadence_rag_b200 import _ffi
+    from cadence_rag_b200.dist import ShardedSearcher, shard_range
     from cadence_rag_b200.store import DenseStore, SYNTH_QUERY_SEED, synth_rows_device
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     rows = args.rows if args.rows != N_ROWS else 10_000_000
     nq = 1024
-    torch.cuda.set_device(0)
-    store = DenseStore("chunks", rows, dim=DIM, device=0, fp32=True, bf16=True)
-    store.append_synthetic(rows)
+    first, count = shard_range(rows, rank, world)
+    store = DenseStore("chunks", count, dim=DIM, device=local_rank, fp32=not args.bf16_only, bf16=True)
+    store.append_synthetic(count, first_row=first)
     store.finalize()
+    searcher = ShardedSearcher(store)
     total = args.warmup + args.steps
-    q_dev = synth_rows_device(SYNTH_QUERY_SEED, 0, total * nq, DIM, device=0).view(total, nq, DIM)
+    q_dev = synth_rows_device(SYNTH_QUERY_SEED, 0, total * nq, DIM, device=local_rank).view(total, nq, DIM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for s in range(args.warmup):
-        store.search_batch(q_dev[s], TOPK)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0); sampler.start()
+        searcher.search(q_dev[s], TOPK, mode="ann")
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     _ffi.lib().cdr_prof_enable(1)
     launches0 = _ffi.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     ev0.record()
     for s in range(args.warmup, total):
-        out = store.search_batch(q_dev[s], TOPK)
-    ev1.record(); torch.cuda.synchronize()
+        out = searcher.search(q_dev[s], TOPK, mode="ann")
+    ev1.record()
+    barrier()
     ms = ev0.elapsed_time(ev1)
     k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
     _ffi.check(_ffi.lib().cdr_prof_read(1, ctypes.byref(k_ms), ctypes.byref(k_n)))
     _ffi.lib().cdr_prof_enable(0)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
     launches = _ffi.kernel_launch_count() - launches0
-    # recall@50 of the last batch against the exact fp32 lane (same store), 64 queries
-    e_ids, _, _ = store.search_exact(q_dev[total - 1][:64], TOPK)
-    got = out[0][:64].cpu().numpy(); want = e_ids.cpu().numpy()
-    recall = float(np.mean([len(set(got[i]) & set(want[i])) / TOPK for i in range(64)]))
-    # e2e with host buffers (pinned)
+    t = torch.tensor([ms, float(launches), k_ms.value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches, gemm_ms = float(tmax[0]), int(tsum[1]), float(tmax[2])
+    else:
+        gemm_ms = k_ms.value
+    # recall@50 of the last batch against the exact fp32 lane (same sharded corpus), 64 queries
+    recall = None
+    if store.has_fp32:
+        e_ids, _, _ = searcher.search(q_dev[total - 1][:64].contiguous(), TOPK, mode="exact")
+        got = out[0][:64].cpu().numpy(); want = e_ids.cpu().numpy()
+        recall = float(np.mean([len(set(got[i]) & set(want[i])) / TOPK for i in range(64)]))
+    # e2e with host buffers (pinned): H2D of the queries + D2H of the merged result every step
     q_pinned = torch.empty(q_dev.shape, dtype=torch.float32, pin_memory=True)
     q_pinned.copy_(q_dev); torch.cuda.synchronize()
     q_host = q_pinned.numpy()
-    store.search_batch(q_host[0], TOPK)
+
+    def e2e_step(s):
+        if world == 1:
+            return store.search_batch(q_host[s], TOPK)
+        qd = torch.from_numpy(q_host[s]).cuda()
+        ids, sc, n = searcher.search(qd, TOPK, mode="ann")
+        return ids.cpu().numpy(), sc.cpu().numpy(), n.cpu().numpy()
+    e2e_step(0)
+    barrier()
     t0 = time.perf_counter()
     for s in range(args.warmup, total):
-        store.search_batch(q_host[s], TOPK)
+        e2e_step(s)
+    barrier()
     dt = time.perf_counter() - t0
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    flops_step = 2.0 * nq * rows * DIM
-    achieved = flops_step * args.steps / (k_ms.value / 1e3) / 1e12 if k_ms.value > 0 else None
-    line = {"metric": "queries/sec (top-k=50, 1024-d) batched bf16 tcgen05 lane", "value": args.steps * nq / (ms / 1e3),
-            "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: {rows} x {DIM} bf16 corpus, batch {nq} queries, tcgen05 GEMM "
-                                   f"with fused threshold top-k epilogue + exact re-score, top-k={TOPK}",
-                       "rows": rows, "dim": DIM, "k": TOPK, "queries_per_step": nq,
-                       "l2": "inputs larger than L2", "recall_at_50_vs_exact_fp32_lane": recall},
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": args.steps * nq / dt, "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 4,
-                    "d2h_bytes_per_step": nq * TOPK * 16 + nq * 4},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if achieved else None, "traffic": None, "kernel": "gemm_topk_kernel",
-                         "peak_source": "measured bf16_tflops_sustained (kernel timed inside a long step)",
-                         "peak_burst": peaks.get("bf16_tflops"), "gemm_ms_per_step": k_ms.value / args.steps,
-                         "launches_timed": int(k_n.value)}}
-    print(json.dumps(line), flush=True)
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peaks = json.load(open(pk)) if os.path.exists(pk) else {}
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        flops_step_gpu = 2.0 * nq * count * DIM
+        achieved = flops_step_gpu * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        line = {"metric": "queries/sec (top-k=50, 1024-d) batched bf16 tcgen05 lane",
+                "value": args.steps * nq / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[{2 if world == 1 else 4}]: {rows} x {DIM} bf16 corpus"
+                                       f"{' row-sharded over %d GPUs' % world if world > 1 else ''}, batch {nq} queries, "
+                                       f"tcgen05 GEMM with fused threshold top-k epilogue + exact re-score, top-k={TOPK}",
+                           "rows": rows, "rows_per_gpu": count, "dim": DIM, "k": TOPK, "queries_per_step": nq,
+                           "resident": "bf16 only" if args.bf16_only else "fp32 + bf16",
+                           "l2": "inputs larger than L2", "recall_at_50_vs_exact_fp32_lane": recall},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": args.steps * nq / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": nq * DIM * 4,
+                        "d2h_bytes_per_step": nq * TOPK * 16 + nq * 4},
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak if achieved else None, "traffic": None,
+                             "kernel": "gemm_topk_kernel", "per": "GPU (max over ranks)",
+                             "peak_source": "measured bf16_tflops_sustained (kernel timed inside a long step)",
+                             "peak_burst": peaks.get("bf16_tflops"), "gemm_ms_per_step": gemm_ms / args.steps,
+                             "launches_timed": int(k_n.value)}}
+        print(json.dumps(line), flush=True)
     store.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

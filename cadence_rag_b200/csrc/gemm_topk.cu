@@ -335,9 +335,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
                 if (c * 32 >= lim) continue;                      // warp-uniform (tail tile)
-                float m = v[0];
+                // max of the chunk as a 4-wide tree (short dependency chain: this warp is alone on its SMSP)
+                float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
 #pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                for (int j = 8; j < 32; j += 4) {
+                    m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+                }
+                const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                 const int rem = (int)(lim - c * 32);
                 if (m >= tau) {
                     // slow path (rare): exact per-element test, filter bit, staged append
@@ -374,6 +378,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            // Flush half-full staging buffers NOW, after the accumulator buffer went back to the MMA
+            // warp: the atomics' round trip then overlaps the next tile's MMAs instead of holding TMEM.
+            if (nbuf >= kBufN / 2) {
+                flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
+                nbuf = 0;
+            }
         }
         if (nbuf > 0) flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
     }
@@ -611,8 +621,9 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
 
     // Segment sizes: 16 tiles, then at most kSegGrowth x (tiles already seen).  With tau = the
     // KC-th best of the rows seen so far, a segment of g x seen rows appends ~ g*KC keys per query
-    // (cap = 32*KC leaves a 2.6x margin over the expectation at g = 12).
-    constexpr int64_t kSegGrowth = 12;
+    // (cap = 32*KC leaves an 8x margin over the expectation at g = 4).  Smaller g = fewer appends
+    // (total ~ KC * g * log_{1+g}(N/4096) per query) but more launches; g = 4 gives 7 segments at 10M rows.
+    constexpr int64_t kSegGrowth = 4;
     int64_t begin = 0;
     while (begin < p.n_tiles_total) {
         int64_t end = begin == 0 ? 16 : begin + kSegGrowth * begin;

@@ -436,3 +436,122 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
                       "artifacts": [(r["artifact_chunk_id"], sorted(l), s) for r, l, s in artifact_ranked]},
         }
     return response
+
+
+# --------------------------------------------------------------------------- evidence pack (f-3)
+DEFAULT_MAX_ARTIFACTS = 2
+DEFAULT_MAX_QUOTES_PER_CALL = 2
+DEFAULT_SNIPPET_CHARS = 800
+
+
+@dataclass
+class Budget:
+    """app/schemas.py:71-73."""
+    max_evidence_items: int = 8
+    max_total_chars: int = 6000
+
+
+def _clip(text: str, max_chars: int) -> str:
+    """app/retrieve.py:27-32: hard cut with a trailing ellipsis inside the budget."""
+    if max_chars <= 0:
+        return ""
+    return text if len(text) <= max_chars else text[: max_chars - 1].rstrip() + "…"
+
+
+def retrieve_evidence(engine: DenseEngine, query: str, filters: Optional[RetrieveFilters] = None,
+                      budget: Optional[Budget] = None, intent: str = "auto",
+                      return_style: str = "evidence_pack_json", debug: bool = False,
+                      bm25_chunks: Sequence[Mapping[str, Any]] = (),
+                      bm25_artifacts: Sequence[Mapping[str, Any]] = ()) -> Dict[str, Any]:
+    """The reference's /retrieve response contract (app/retrieve.py:392-688) over the GPU engine:
+    lanes -> RRF -> either ``ids_only`` or the budgeted evidence pack (<= 2 artifacts, <= 2 quotes
+    per call, snippet <= 800 chars, total chars <= budget) with the same ``notes.retrieval`` block.
+    Payload columns (`content`, `artifact_id`, `kind`, `text`, `speaker`, `start_ts_ms`,
+    `end_ts_ms`) come from the rows registered with the stores."""
+    from uuid import uuid4
+    query_id = str(uuid4())
+    budget = budget or Budget()
+    if not query.strip():
+        if return_style == "ids_only":
+            return {"query_id": query_id, "retrieved_ids": []}
+        return {"query_id": query_id, "intent": intent, "budget": dict(vars(budget)), "artifacts": [],
+                "quotes": [], "notes": {"error": "empty query"}}
+    inner = retrieve_ids(engine, query, filters, bm25_chunks=bm25_chunks, bm25_artifacts=bm25_artifacts, debug=True)
+    dbg = inner["debug"]
+    if return_style == "ids_only":
+        out = {"query_id": query_id, "retrieved_ids": inner["retrieved_ids"]}
+        if debug:
+            out["debug"] = dbg
+        return out
+
+    rows_by_id = {"chunks": {}, "artifacts": {}}
+    for kind, table, key in (("chunks", "chunks", "chunk_id"), ("artifacts", "artifact_chunks", "artifact_chunk_id")):
+        store = engine.stores.get(table)
+        for ident, lanes, score in dbg["fused"][kind]:
+            row = {key: ident}
+            if store is not None:
+                row.update(store.payload.get(ident, {}))
+                cols = store.host_columns()
+                pos = int(np.searchsorted(cols["ids"], ident))
+                if pos < len(cols["ids"]) and cols["ids"][pos] == ident:
+                    slot = int(cols["call_slot"][pos])
+                    row["call_id"] = store.call_ids_by_slot[slot] if slot < len(store.call_ids_by_slot) else slot
+            rows_by_id[kind][ident] = (row, lanes)
+
+    remaining = budget.max_total_chars
+    used = 0
+    artifacts_out: List[Dict[str, Any]] = []
+    for ident, lanes, _s in dbg["fused"]["artifacts"]:
+        if used >= budget.max_evidence_items or len(artifacts_out) >= min(DEFAULT_MAX_ARTIFACTS, budget.max_evidence_items):
+            break
+        if remaining <= 0:
+            break
+        row, _ = rows_by_id["artifacts"][ident]
+        snippet = _clip(str(row.get("content", "")), min(DEFAULT_SNIPPET_CHARS, remaining))
+        remaining -= len(snippet)
+        artifacts_out.append({"evidence_id": f"A-{ident}", "call_id": str(row.get("call_id")),
+                              "artifact_id": row.get("artifact_id"), "artifact_chunk_id": ident,
+                              "kind": row.get("kind"), "snippet": snippet, "why_relevant": " + ".join(sorted(lanes))})
+        used += 1
+    quotes_out: List[Dict[str, Any]] = []
+    per_call: Dict[str, int] = {}
+    for ident, lanes, _s in dbg["fused"]["chunks"]:
+        if used >= budget.max_evidence_items or remaining <= 0:
+            break
+        row, _ = rows_by_id["chunks"][ident]
+        call_id = str(row.get("call_id"))
+        if per_call.get(call_id, 0) >= DEFAULT_MAX_QUOTES_PER_CALL:
+            continue
+        snippet = _clip(str(row.get("text", "")), min(DEFAULT_SNIPPET_CHARS, remaining))
+        remaining -= len(snippet)
+        quotes_out.append({"evidence_id": f"Q-{ident}", "call_id": call_id, "chunk_id": ident,
+                           "speaker": row.get("speaker"), "start_ts_ms": row.get("start_ts_ms"),
+                           "end_ts_ms": row.get("end_ts_ms"), "snippet": snippet,
+                           "why_relevant": " + ".join(sorted(lanes))})
+        per_call[call_id] = per_call.get(call_id, 0) + 1
+        used += 1
+
+    dense = dbg["dense"]
+    modes = dense["modes"]
+    planner = ("lexical_only" if not dense["enabled"] else
+               ("ann" if "ann" in (modes.get("chunks"), modes.get("artifact_chunks")) else "exact"))
+    response = {
+        "query_id": query_id, "intent": intent, "budget": dict(vars(budget)),
+        "artifacts": artifacts_out, "quotes": quotes_out,
+        "notes": {"retrieval": {
+            "planner": planner,
+            "dense_topk": max(DEFAULT_DENSE_CHUNK_TOPK, DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK) if dense["enabled"] else 0,
+            "lex_topk": DEFAULT_CHUNK_BM25_TOPK, "artifact_chunk_lex_topk": DEFAULT_ARTIFACT_CHUNK_BM25_TOPK,
+            "reranked_from": None, "bm25_chunk_topk": DEFAULT_CHUNK_BM25_TOPK,
+            "bm25_artifact_chunk_topk": DEFAULT_ARTIFACT_CHUNK_BM25_TOPK, "tech_token_topk": DEFAULT_TECH_TOPK,
+            "tech_tokens": extract_tech_tokens(query.strip()),
+            "lanes": {"bm25": True, "tech_tokens": True, "dense": dense["enabled"]},
+            "dense_model_id": dense["model_id"], "dense_error": dense["error"],
+            "dense_modes": {"chunks": modes.get("chunks"), "artifact_chunks": modes.get("artifact_chunks")},
+            "dense_candidate_rows": dict(dense["candidate_rows"]),
+            "hnsw_ef_search": settings.embeddings_hnsw_ef_search if dense["enabled"] else None,
+        }},
+    }
+    if debug:
+        response["debug"] = dbg
+    return response
