@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bf16-only", action="store_true", help="batch_bf16: keep only bf16 rows resident (C5 residency)")
-    ap.add_argument("--workload", default="exact_f32", choices=["exact_f32", "batch_bf16"],
+    ap.add_argument("--workload", default="exact_f32", choices=["exact_f32", "batch_bf16", "hybrid"],
                     help="exact_f32 = BASELINE configs[1] (default, the contract line); "
                          "batch_bf16 = configs[2]: 10M x 1024 bf16, 1024 queries on the tcgen05 lane")
     return ap.parse_args()
@@ -125,6 +125,8 @@ def cpu_baseline(rows_total: int, sample_rows: int, sample_queries: int, threads
     import numpy as np
     from oracle import cpu_oracle as orc
     sample_rows = min(sample_rows, rows_total)
+    if threads <= 0:
+        threads = os.cpu_count() or 1      # explicit: launchers may export OMP_NUM_THREADS=1
     x = orc.synth_rows(20260209, 0, sample_rows)
     qs = orc.synth_rows(20260210, 10_000_000, sample_queries)
     orc.exact_scan(qs[0], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=threads)   # warm
@@ -132,7 +134,7 @@ def cpu_baseline(rows_total: int, sample_rows: int, sample_queries: int, threads
     for i in range(sample_queries):
         orc.exact_scan(qs[i], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=threads)
     dt = time.perf_counter() - t0
-    cores = threads if threads > 0 else orc.num_threads()
+    cores = threads
     qps_sample = sample_queries / dt
     return {"value": qps_sample * sample_rows / rows_total, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{sample_queries} queries x {sample_rows} of {rows_total} rows (pgvector 0.8.1 cosine loop "
@@ -150,20 +152,20 @@ def run_reference(args):
     from oracle import cpu_oracle as orc
     import numpy as np
     rows = min(args.cpu_sample_rows, args.rows)
+    cores = os.cpu_count() or 1            # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     q_per_step = max(1, min(args.queries_per_step, 8))
     x = orc.synth_rows(20260209, 0, rows)
     qs = orc.synth_rows(20260210, 0, (args.steps + args.warmup) * q_per_step)
     qi = 0
     for _ in range(args.warmup):
         for _ in range(q_per_step):
-            orc.exact_scan(qs[qi], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=0); qi += 1
+            orc.exact_scan(qs[qi], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=cores); qi += 1
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for _ in range(q_per_step):
-            orc.exact_scan(qs[qi], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=0); qi += 1
+            orc.exact_scan(qs[qi], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=cores); qi += 1
     dt = time.perf_counter() - t0
     value = args.steps * q_per_step / dt * rows / args.rows
-    cores = orc.num_threads()
     sample = (f"{q_per_step} queries/step x {rows} of {args.rows} rows, rate scaled by rows; pgvector 0.8.1 "
               f"exact-scan loop restated in C (oracle/pgvector_restated.c), {cores} OpenMP threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -229,6 +231,11 @@ def run_batch_bf16(args):
     ms = ev0.elapsed_time(ev1)
     k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
     _ffi.check(_ffi.lib().cdr_prof_read(1, ctypes.byref(k_ms), ctypes.byref(k_n)))
+    per_launch = np.zeros(int(k_n.value), dtype=np.float64)
+    got_n = ctypes.c_int64(0)
+    _ffi.check(_ffi.lib().cdr_prof_read_launches(1, _ffi.ptr(per_launch), per_launch.size, ctypes.byref(got_n)))
+    segs = max(1, int(k_n.value) // max(args.steps, 1))
+    last_step_launch_ms = [round(float(v), 4) for v in per_launch[-segs:]]
     _ffi.lib().cdr_prof_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     launches = _ffi.kernel_launch_count() - launches0
@@ -290,12 +297,115 @@ def run_batch_bf16(args):
                              "kernel": "gemm_topk_kernel", "per": "GPU (max over ranks)",
                              "peak_source": "measured bf16_tflops_sustained (kernel timed inside a long step)",
                              "peak_burst": peaks.get("bf16_tflops"), "gemm_ms_per_step": gemm_ms / args.steps,
-                             "launches_timed": int(k_n.value)}}
+                             "launches_timed": int(k_n.value), "segment_launch_ms_last_step": last_step_launch_ms}}
         print(json.dumps(line), flush=True)
     store.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return 0
+
+
+def run_hybrid(args):
+    """Secondary line (BASELINE configs[3] + configs[0]): hybrid /retrieve over 1M chunks through the
+    facade -- synthetic embedder, K6 filter bitmap + count, planner, K1 exact scan, host tech_tokens
+    lane, K5 RRF -- for (a) a 10-call filter (2 000 candidate rows => mode "exact", the C1 shape) and
+    (b) no filter.  Fused ranks are checked bit-exact against the restated pipeline on 8 queries."""
+    import numpy as np
+    import torch
+    from cadence_rag_b200 import _ffi, embeddings, retrieve
+    from cadence_rag_b200.config import settings
+    from cadence_rag_b200.lexical import TechTokenIndex
+    from cadence_rag_b200.retrieve import DenseEngine, RetrieveFilters
+    from cadence_rag_b200.store import DenseStore, SYNTH_CORPUS_SEED, SYNTH_QUERY_SEED
+    from oracle import cpu_oracle as orc
+    from oracle import ports
+    rows = args.rows
+    torch.cuda.set_device(0)
+    store = DenseStore("chunks", rows, dim=DIM, device=0, fp32=True, bf16=False)
+    store.append_synthetic(rows)
+    store.finalize()
+    rng = np.random.default_rng(SYNTH_CORPUS_SEED)
+    vocab = 10_000
+    ntok = rng.integers(0, 4, size=rows)
+    tok = np.minimum(rng.zipf(1.1, size=(rows, 3)) - 1, vocab - 1)
+    index = TechTokenIndex()
+    flat_rows = np.repeat(np.arange(rows), 3)[(np.arange(3)[None, :] < ntok[:, None]).reshape(-1)]
+    flat_tok = tok.reshape(-1)[(np.arange(3)[None, :] < ntok[:, None]).reshape(-1)]
+    order = np.lexsort((flat_rows, flat_tok))
+    flat_rows, flat_tok = flat_rows[order], flat_tok[order]
+    starts = np.searchsorted(flat_tok, np.arange(vocab + 1))
+    for t in range(vocab):
+        if starts[t + 1] > starts[t]:
+            index.add_postings(f"TK-{t}", np.unique(flat_rows[starts[t]:starts[t + 1]]))
+    eng = DenseEngine()
+    eng.register(store, index)
+    emb = embeddings.SyntheticEmbedder(seed=SYNTH_QUERY_SEED, dim=DIM)
+    embeddings.set_embedder(emb)
+    settings.embeddings_dim = DIM
+    filt = RetrieveFilters(call_ids=list(range(10)))          # synthetic call id == call slot; 200 rows/call
+    out = {}
+    # parity of the fused ranks on a few queries (restated pipeline: oracle dense + port tech + port RRF)
+    x_small = orc.synth_rows(SYNTH_CORPUS_SEED, 0, 2000)
+    cols = store.host_columns()
+    for qi in range(8):
+        text = f"status of TK-{qi} and TK-{qi * 7 + 1} on v1.{qi}"
+        got = retrieve.retrieve_ids(eng, text, filt, debug=True)
+        q = np.array(emb([text]).vectors[0], dtype=np.float32)
+        d_ids, _ = orc.exact_scan(q, x_small, TOPK)           # the 10 calls are rows 0..1999
+        toks = retrieve.extract_tech_tokens(text)
+        keep = cols["call_slot"] < 10
+        hit_rows = np.unique(np.concatenate([index.postings(t) for t in toks] + [np.empty(0, dtype=np.int64)]))
+        hit_rows = hit_rows[keep[hit_rows]]
+        o = np.lexsort((cols["ids"][hit_rows], -cols["started_at"][hit_rows]))
+        tech_ids = cols["ids"][hit_rows[o]][:50].tolist()
+        want = ports.rrf_merge({"bm25": [], "tech_tokens": [{"chunk_id": i} for i in tech_ids],
+                                "dense": [{"chunk_id": int(i)} for i in d_ids]}, "chunk_id")
+        assert [(r["chunk_id"], sorted(h), s_) for r, h, s_ in want] == [tuple(t) for t in got["debug"]["fused"]["chunks"]], qi
+        assert got["debug"]["dense"]["modes"]["chunks"] == "exact" and got["debug"]["dense"]["candidate_rows"]["chunks"] == 2000
+    for name, f in (("filtered_10_calls_2000_rows", filt), ("unfiltered", None)):
+        n = args.steps * 8
+        for i in range(8):
+            retrieve.retrieve_ids(eng, f"warm TK-{i} TK-{i + 3}", f)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n):
+            retrieve.retrieve_ids(eng, f"status of TK-{i % 500} and TK-{(i * 13) % 900}", f)
+        dt = time.perf_counter() - t0
+        out[name] = {"queries_per_s": n / dt, "ms_per_query": dt / n * 1e3, "queries": n}
+    # C1: 2 000-row store, GPU exact-scan latency vs the CPU restatement (1 thread and all cores)
+    small = DenseStore("chunks", 2000, dim=DIM, device=0, fp32=True, bf16=False)
+    small.append_synthetic(2000); small.finalize()
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 0, 64)
+    qd = torch.from_numpy(qs).cuda()
+    for i in range(5):
+        small.search_exact(qd[i:i + 1], TOPK)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(64):
+        small.search_exact(qd[i:i + 1], TOPK)
+    ev1.record(); torch.cuda.synchronize()
+    gpu_ms = ev0.elapsed_time(ev1) / 64
+    t0 = time.perf_counter()
+    for i in range(64):
+        small.search_exact(qs[i], TOPK)
+    host_ms = (time.perf_counter() - t0) / 64 * 1e3
+    cpu = {}
+    for th in (1, 0):
+        t0 = time.perf_counter()
+        for i in range(64):
+            orc.exact_scan(qs[i], x_small, TOPK, variant=orc.VARIANT_PGV32, nthreads=th)
+        cpu["1_thread" if th == 1 else f"{orc.num_threads()}_threads"] = (time.perf_counter() - t0) / 64 * 1e3
+    line = {"metric": "hybrid /retrieve queries/sec (dense top-50 + tech_tokens lane + RRF k=60)",
+            "value": out["unfiltered"]["queries_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": 8, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: hybrid /retrieve, {rows} chunks, through retrieve_ids "
+                                   "(host facade, one query at a time)", "rows": rows, "k": TOPK},
+            "hybrid": out, "fused_ranks_bit_exact_queries": 8,
+            "c1_exact_scan_2000_rows": {"gpu_device_ms": gpu_ms, "gpu_host_buffers_ms": host_ms, "cpu_ms": cpu}}
+    print(json.dumps(line), flush=True)
+    embeddings.set_embedder(None)
+    store.close(); small.close()
     return 0
 
 
@@ -305,6 +415,8 @@ def main():
         return run_reference(args)
     if args.workload == "batch_bf16":
         return run_batch_bf16(args)
+    if args.workload == "hybrid":
+        return run_hybrid(args)
 
     import numpy as np
     import torch

@@ -85,6 +85,7 @@ SIGNATURES = {
     "cdr_kernel_launch_count": (_i64, []),
     "cdr_prof_enable": (_i32, [_i32]),
     "cdr_prof_read": (_i32, [_i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
+    "cdr_prof_read_launches": (_i32, [_i32, _vp, _i64, ctypes.POINTER(_i64)]),
 }
 
 

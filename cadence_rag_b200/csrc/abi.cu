@@ -102,6 +102,22 @@ extern "C" int32_t cdr_prof_read(int32_t kind, double *out_total_ms, int64_t *ou
     return CDR_OK;
 }
 
+extern "C" int32_t cdr_prof_read_launches(int32_t kind, double *out_ms, int64_t max_n, int64_t *out_n)
+{
+    CDR_REQUIRE((kind == 0 || kind == 1) && out_ms && max_n >= 0, CDR_ERR_INVALID, "cdr_prof_read_launches: bad arguments");
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    int64_t n = 0;
+    for (auto &pr : g_prof.pairs[kind]) {
+        if (n >= max_n) break;
+        CDR_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        CDR_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        out_ms[n++] = ms;
+    }
+    if (out_n) *out_n = n;
+    return CDR_OK;
+}
+
 // ---------------------------------------------------------------------------- exact lane
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                           const uint32_t *allow, int k, double *out_score, int64_t *out_id,

@@ -187,6 +187,8 @@ int64_t cdr_kernel_launch_count(void);
  * scan, 1 = K2 batched bf16. */
 int32_t cdr_prof_enable(int32_t on);
 int32_t cdr_prof_read(int32_t kind, double *out_total_ms, int64_t *out_launches);
+/* Per-launch device times (ms) of the recorded launches, oldest first; writes min(n, max_n). */
+int32_t cdr_prof_read_launches(int32_t kind, double *out_ms, int64_t max_n, int64_t *out_n);
 
 #ifdef __cplusplus
 }

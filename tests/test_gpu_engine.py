@@ -538,3 +538,39 @@ def test_full_size_1m_properties_and_oracle(corpus_1m):
     m_ids, m_sc, m_n = merge_shard_results(torch.stack([p[1] for p in parts]), torch.stack([p[0] for p in parts]),
                                            torch.stack([p[2] for p in parts]), k)
     assert np.array_equal(m_ids.cpu().numpy(), ids) and np.array_equal(m_sc.cpu().numpy().view(np.uint64), sc.view(np.uint64))
+
+
+def test_retrieve_evidence_pack_contract(hybrid_engine, monkeypatch):
+    """f-3: the /retrieve response contract (app/retrieve.py:575-678) over the GPU engine."""
+    eng, meta = hybrid_engine
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    # give artifact rows the payload columns the evidence pack reads
+    art = eng.stores["artifact_chunks"]
+    for i in list(art.payload)[:2000]:
+        art.payload[i].update(content="artifact text " * 100, artifact_id=i // 10, kind="summary")
+    embeddings.set_embedder(embeddings.SyntheticEmbedder(seed=SYNTH_QUERY_SEED, dim=1024))
+    try:
+        out = retrieve.retrieve_evidence(eng, "why did TOK-1 fail", None, retrieve.Budget(8, 2000), debug=True)
+        assert set(out) >= {"query_id", "intent", "budget", "artifacts", "quotes", "notes", "debug"}
+        assert len(out["artifacts"]) <= 2 and len(out["artifacts"]) + len(out["quotes"]) <= 8
+        assert sum(len(a["snippet"]) for a in out["artifacts"]) + sum(len(q["snippet"]) for q in out["quotes"]) <= 2000
+        assert all(len(a["snippet"]) <= 800 and a["evidence_id"].startswith("A-") for a in out["artifacts"])
+        per_call = {}
+        for qt in out["quotes"]:
+            per_call[qt["call_id"]] = per_call.get(qt["call_id"], 0) + 1
+            assert qt["evidence_id"] == f"Q-{qt['chunk_id']}" and qt["why_relevant"]
+        assert max(per_call.values(), default=0) <= 2
+        r = out["notes"]["retrieval"]
+        assert r["planner"] == "ann" and r["dense_topk"] == 50 and r["lanes"]["dense"] is True
+        assert r["tech_tokens"] == ["TOK-1"] and r["hnsw_ef_search"] == settings.embeddings_hnsw_ef_search
+        # order of evidence follows the fused ranking
+        fused_chunks = [t[0] for t in out["debug"]["fused"]["chunks"]]
+        pos = [fused_chunks.index(qt["chunk_id"]) for qt in out["quotes"]]
+        assert pos == sorted(pos)
+        ids_only = retrieve.retrieve_evidence(eng, "why did TOK-1 fail", None, return_style="ids_only")
+        assert ids_only["retrieved_ids"] == retrieve.retrieve_ids(eng, "why did TOK-1 fail")["retrieved_ids"]
+        empty = retrieve.retrieve_evidence(eng, "  ")
+        assert empty["notes"] == {"error": "empty query"} and empty["quotes"] == []
+        assert retrieve._clip("abcdef", 4) == "abc…" and retrieve._clip("abc", 0) == "" and retrieve._clip("abc", 5) == "abc"
+    finally:
+        embeddings.set_embedder(None)
