@@ -321,7 +321,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int64_t row0 = nt * kBlockN;
             const int q = mt * kBlockM + et;
             const bool q_ok = q < p.nq;
-            const float tau = (q_ok && !p.debug_no_append) ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
+            const float tau = (q_ok && p.debug_no_append != 1) ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
             int64_t lim = p.n_rows - row0;                        // valid columns in this tile
             if (lim > kBlockN) lim = kBlockN;
             const uint32_t buf = tile_no & 1u;
@@ -354,10 +354,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         // 32 consecutive rows starting at a multiple of 32: exactly one bitmap word
                         mask &= __ldg(&p.allow[(row0 + c * 32) >> 5]);
                     }
+                    if (p.debug_no_append == 2) mask = 0;          // timing aid: mask built, nothing staged
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t mh = (mask >> (16 * h)) & 0xFFFFu;
                         if (mh != 0) {
+                            if (p.debug_no_append == 3) nbuf = 0;  // timing aid: stage, never flush
                             if (nbuf + __popc(mh) > kBufN) {       // make room for up to 16 hits
                                 flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
                                 nbuf = 0;
@@ -380,7 +382,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             // Flush half-full staging buffers NOW, after the accumulator buffer went back to the MMA
             // warp: the atomics' round trip then overlaps the next tile's MMAs instead of holding TMEM.
-            if (nbuf >= kBufN / 2) {
+            if (nbuf >= kBufN / 2 && p.debug_no_append != 3) {
                 flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
                 nbuf = 0;
             }
@@ -609,8 +611,8 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     p.cap = cap;
     p.n_tiles_total = (s->n_rows + kBlockN - 1) / kBlockN;
     p.k_blocks = dim / kBlockK;
-    static const bool dryrun = [] { const char *e = getenv("CADENCE_K2_DRYRUN"); return e && e[0] == '1'; }();
-    p.debug_no_append = dryrun ? 1 : 0;
+    static const int dryrun = [] { const char *e = getenv("CADENCE_K2_DRYRUN"); return e ? atoi(e) : 0; }();
+    p.debug_no_append = dryrun;
     // multiplicative permutation of the tile order so every segment samples the whole corpus
     int64_t mul = 1;
     if (p.n_tiles_total > 2) {

@@ -165,6 +165,15 @@ __global__ void valid_bits_kernel(const uint8_t *valid_u8, uint32_t *bitmap, int
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_valid, (unsigned long long)__popc(b));
 }
 
+__global__ void expand_valid_kernel(const uint32_t *bitmap, int64_t row0, int64_t n, uint8_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t r = row0 + i;
+        out[i] = (bitmap[r >> 5] >> (r & 31)) & 1u;
+    }
+}
+
 // flag[0] |= 1 when ids are not strictly increasing
 __global__ void check_ids_kernel(const int64_t *ids, int64_t n, unsigned long long *flag)
 {
@@ -467,5 +476,23 @@ extern "C" int32_t cdr_store_read_rows(cdr_store *s, int64_t first_row, int64_t 
     if (out_started_at_host) CDR_CUDA(cudaMemcpy(out_started_at_host, s->started_at + first_row, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (out_tag_bits_host) CDR_CUDA(cudaMemcpy(out_tag_bits_host, s->tag_bits + first_row, (size_t)n * 8, cudaMemcpyDeviceToHost));
     if (out_inv_norm_host) CDR_CUDA(cudaMemcpy(out_inv_norm_host, s->inv_norm + first_row, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_store_read_valid(cdr_store *s, int64_t first_row, int64_t n, uint8_t *out_valid_u8_host)
+{
+    CDR_REQUIRE(s != nullptr && out_valid_u8_host != nullptr, CDR_ERR_INVALID, "cdr_store_read_valid: NULL argument");
+    CDR_REQUIRE(first_row >= 0 && n >= 0 && first_row + n <= s->n_rows, CDR_ERR_INVALID,
+                "cdr_store_read_valid: range [%lld,+%lld) outside [0,%lld)", (long long)first_row, (long long)n,
+                (long long)s->n_rows);
+    if (n == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    uint8_t *tmp = nullptr;
+    CDR_CUDA(cudaMalloc(&tmp, (size_t)n));
+    expand_valid_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->valid, first_row, n, tmp);
+    CDR_LAUNCH_CHECK();
+    cudaError_t e = cudaMemcpy(out_valid_u8_host, tmp, (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    CDR_CUDA(e);
     return CDR_OK;
 }

@@ -172,6 +172,106 @@ class DenseStore:
             for i, row in zip(ids_np.tolist(), payload):
                 self.payload[i] = row
 
+    def append_literals(self, literals: Sequence[Optional[str]], ids: Sequence[int], **columns) -> None:
+        """Append rows given as pgvector text literals -- the wire format the reference writes with
+        ``UPDATE ... SET embedding = CAST(:embedding AS vector(D))`` (app/embedding_pipeline.py:149-168,
+        literal built by _vector_literal, :63-64).  ``None`` models ``embedding IS NULL``.  Each element
+        is parsed with float32 rounding, as pgvector's vector_in (strtof) does."""
+        n = len(ids)
+        emb = np.zeros((n, self.dim), dtype=np.float32)
+        valid = np.ones(n, dtype=bool)
+        for i, lit in enumerate(literals):
+            if lit is None:
+                valid[i] = False
+                continue
+            body = lit.strip()
+            if not (body.startswith("[") and body.endswith("]")):
+                raise DenseEngineError(f"row {i}: malformed vector literal")
+            vals = np.array(body[1:-1].split(","), dtype=np.float32)
+            if vals.shape[0] != self.dim:
+                raise DenseEngineError(f"row {i}: expected {self.dim} dimensions, not {vals.shape[0]}")
+            emb[i] = vals
+        if "valid" in columns:
+            valid &= np.asarray(columns.pop("valid"), dtype=bool)
+        self.append(emb, ids, valid=valid, **columns)
+
+    def append_embed_response(self, body: Dict[str, Any], ids: Sequence[int], **columns) -> None:
+        """Append the ``{"embeddings": [[...], ...]}`` payload of the gateway's POST /embed
+        (app/embeddings.py:71-82), validated like the reference client does."""
+        vecs = body.get("embeddings")
+        if not isinstance(vecs, list) or len(vecs) != len(ids):
+            raise DenseEngineError("embedding response count mismatch")
+        for i, v in enumerate(vecs):
+            if len(v) != self.dim:
+                raise DenseEngineError(f"embedding {i} has dim {len(v)}; expected {self.dim}")
+        self.append(np.asarray(vecs, dtype=np.float32), ids, **columns)
+
+    # ------------------------------------------------------------------ snapshot / restore
+    def save(self, path: str, chunk_rows: int = 1 << 16) -> None:
+        """Snapshot the resident store to a directory: raw fp32 rows (or bf16 bits for bf16-only
+        stores) plus the filter columns, validity, dictionaries and payload.  The reference keeps this
+        state durable in Postgres; here it is what a restart reloads instead of re-reading the DB."""
+        import json, os, pickle
+        os.makedirs(path, exist_ok=True)
+        rows = self.rows
+        what = "f32" if self.has_fp32 else "bf16"
+        dt = np.float32 if self.has_fp32 else np.uint16
+        mm = np.lib.format.open_memmap(os.path.join(path, f"emb_{what}.npy"), mode="w+", dtype=dt, shape=(rows, self.dim))
+        valid = np.empty(rows, dtype=np.uint8)
+        for r0 in range(0, rows, chunk_rows):
+            m = min(chunk_rows, rows - r0)
+            mm[r0:r0 + m] = self.read_rows(r0, m, (what,))[what]
+            _ffi.check(_ffi.lib().cdr_store_read_valid(self.handle, r0, m, _ffi.ptr(valid[r0:r0 + m])), "cdr_store_read_valid")
+        mm.flush(); del mm
+        cols = self.read_rows(0, rows, ("ids", "call_slot", "started_at", "tag_bits"))
+        np.savez(os.path.join(path, "columns.npz"), valid=valid, **cols)
+        meta = dict(table_name=self.table_name, key_field=self.key_field, dim=self.dim, rows=rows, fp32=self.has_fp32,
+                    bf16=self.has_bf16, tag_bits=self.tag_bits, synthetic=self.synthetic)
+        with open(os.path.join(path, "meta.json"), "w") as f:
+            json.dump(meta, f)
+        with open(os.path.join(path, "host_state.pkl"), "wb") as f:
+            pickle.dump(dict(call_ids_by_slot=self.call_ids_by_slot, payload=self.payload), f)
+
+    @classmethod
+    def load(cls, path: str, device: Optional[int] = None, capacity_rows: Optional[int] = None,
+             chunk_rows: int = 1 << 16) -> "DenseStore":
+        """Rebuild a finalized store from :meth:`save`'s directory.  bf16-only snapshots restore the
+        bf16 values exactly (they are widened to fp32, whose re-normalisation and RN-even rounding
+        reproduce the same bits for already-rounded unit rows only approximately, so fp32 snapshots
+        are the lossless form)."""
+        import json, os, pickle
+        torch = _torch()
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        rows = meta["rows"]
+        store = cls(meta["table_name"], capacity_rows or max(rows, 1), dim=meta["dim"], device=device,
+                    fp32=meta["fp32"], bf16=meta["bf16"], key_field=meta["key_field"])
+        cols = np.load(os.path.join(path, "columns.npz"))
+        what = "f32" if meta["fp32"] else "bf16"
+        mm = np.load(os.path.join(path, f"emb_{what}.npy"), mmap_mode="r")
+        with open(os.path.join(path, "host_state.pkl"), "rb") as f:
+            host = pickle.load(f)
+        store.call_ids_by_slot = host["call_ids_by_slot"]
+        store.call_slots = {c: i for i, c in enumerate(store.call_ids_by_slot)}
+        store.payload = host["payload"]
+        store.tag_bits = {k: int(v) for k, v in meta["tag_bits"].items()}
+        store.synthetic = meta["synthetic"]
+        with torch.cuda.device(store.device):
+            for r0 in range(0, rows, chunk_rows):
+                m = min(chunk_rows, rows - r0)
+                block = np.ascontiguousarray(mm[r0:r0 + m])
+                if what == "bf16":
+                    block = (block.astype(np.uint32) << 16).view(np.float32)
+                sl = slice(r0, r0 + m)
+                _ffi.check(_ffi.lib().cdr_store_append(
+                    store.handle, _ffi.ptr(block), _ffi.ptr(np.ascontiguousarray(cols["ids"][sl])),
+                    _ffi.ptr(np.ascontiguousarray(cols["call_slot"][sl])),
+                    _ffi.ptr(np.ascontiguousarray(cols["started_at"][sl])),
+                    _ffi.ptr(np.ascontiguousarray(cols["tag_bits"][sl])),
+                    _ffi.ptr(np.ascontiguousarray(cols["valid"][sl])), m, 0, store._stream()), "cdr_store_append")
+        store.finalize()
+        return store
+
     def append_synthetic(self, n: int, *, seed: int = SYNTH_CORPUS_SEED, first_row: int = 0,
                          id_base: int = 1, rows_per_call: int = SYNTH_ROWS_PER_CALL,
                          t0_us: int = SYNTH_T0_US, call_period_us: int = SYNTH_CALL_PERIOD_US) -> None:

@@ -98,6 +98,9 @@ int32_t cdr_store_read_rows(cdr_store *s, int64_t first_row, int64_t n, float *o
                             int32_t *out_call_slot_host, int64_t *out_started_at_host,
                             uint64_t *out_tag_bits_host, float *out_inv_norm_host);
 
+/* Validity flags (embedding IS NOT NULL) of rows [first_row, first_row+n) as bytes (snapshots). */
+int32_t cdr_store_read_valid(cdr_store *s, int64_t first_row, int64_t n, uint8_t *out_valid_u8_host);
+
 /* ---- synthetic queries / rows into caller memory ---------------------------------------- */
 int32_t cdr_synth_rows(float *out_dev, uint64_t seed, int64_t first_row, int64_t n, int32_t dim,
                        void *stream);

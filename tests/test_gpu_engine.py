@@ -574,3 +574,39 @@ def test_retrieve_evidence_pack_contract(hybrid_engine, monkeypatch):
         assert retrieve._clip("abcdef", 4) == "abc…" and retrieve._clip("abc", 0) == "" and retrieve._clip("abc", 5) == "abc"
     finally:
         embeddings.set_embedder(None)
+
+
+def test_wire_formats_and_snapshot_roundtrip(tmp_path, monkeypatch):
+    """f-2: pgvector text literals / POST /embed payloads in, snapshot -> restore."""
+    n = 3000
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n)
+    lits = [retrieve._vector_literal(row.tolist()) for row in x[:200]]
+    lits[7] = None                                                       # embedding IS NULL
+    s = DenseStore("chunks", n, dim=1024, device=0)
+    t0 = datetime(2026, 3, 1, tzinfo=timezone.utc)
+    s.append_literals(lits, ids=np.arange(1, 201), call_ids=[_uuid(i // 50) for i in range(200)],
+                      call_started_at=[t0 + timedelta(days=i // 50) for i in range(200)],
+                      call_tags=[["a"] if i % 2 else ["b", "c"] for i in range(200)],
+                      payload=[{"text": f"row {i}"} for i in range(200)])
+    s.append_embed_response({"embeddings": x[200:].tolist(), "model": "m"}, ids=np.arange(201, n + 1),
+                            call_ids=[_uuid(9)] * (n - 200))
+    s.finalize()
+    back = s.read_rows(0, n, ("f32",))["f32"]
+    keep = np.ones(n, dtype=bool); keep[7] = False
+    assert np.array_equal(back[keep].view(np.uint32), x[keep].view(np.uint32))   # .10g literal round-trips float32
+    assert s.info()["n_valid"] == n - 1
+    with pytest.raises(DenseEngineError):
+        s2 = DenseStore("chunks", 4, dim=1024, device=0); s2.append_literals(["[1,2,3]"], ids=[1])
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 0, 3)
+    allow, cnt = s.filter_bitmap(tag_mask=s.bits_of_tags(["b"]))
+    before = s.search_exact(qs, 20), s.search_exact(qs, 20, allow), s.search_batch(qs, 20)
+    s.save(str(tmp_path / "snap"))
+    r = DenseStore.load(str(tmp_path / "snap"), device=0)
+    assert r.info() == s.info() and r.tag_bits == s.tag_bits and r.payload[5] == {"text": "row 4"}
+    allow_r, cnt_r = r.filter_bitmap(tag_mask=r.bits_of_tags(["b"]))
+    assert cnt_r == cnt
+    after = r.search_exact(qs, 20), r.search_exact(qs, 20, allow_r), r.search_batch(qs, 20)
+    for b, a in zip(before, after):
+        assert np.array_equal(b[0], a[0]) and np.array_equal(b[1].view(np.uint64), a[1].view(np.uint64))
+    assert r.slot_of_call(_uuid(9)) == s.slot_of_call(_uuid(9))
+    s.close(); r.close()
