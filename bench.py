@@ -297,7 +297,9 @@ def run_batch_bf16(args):
                              "kernel": "gemm_topk_kernel", "per": "GPU (max over ranks)",
                              "peak_source": "measured bf16_tflops_sustained (kernel timed inside a long step)",
                              "peak_burst": peaks.get("bf16_tflops"), "gemm_ms_per_step": gemm_ms / args.steps,
-                             "launches_timed": int(k_n.value), "segment_launch_ms_last_step": last_step_launch_ms}}
+                             "launches_timed": int(k_n.value), "segment_launch_ms_last_step": last_step_launch_ms,
+                             "gemm_ms_by_step": [round(float(per_launch[i * segs:(i + 1) * segs].sum()), 3)
+                                                 for i in range(args.steps)]}}
         print(json.dumps(line), flush=True)
     store.close()
     if world > 1:

@@ -555,3 +555,34 @@ def retrieve_evidence(engine: DenseEngine, query: str, filters: Optional[Retriev
     if debug:
         response["debug"] = dbg
     return response
+
+
+# --------------------------------------------------------------------------- hierarchical scoping (f-4)
+def fetch_chunks_dense_hierarchical(conn: DenseConnection, query_embedding, filters: Optional[RetrieveFilters],
+                                    call_ids: Optional[Sequence[Any]], artifact_limit: int = DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK,
+                                    chunk_limit: int = DEFAULT_DENSE_CHUNK_TOPK, max_calls: int = 8) -> Dict[str, Any]:
+    """The two-stage dense retrieval the reference specifies but only half implements
+    (APP_SPEC.md:621-638; today both corpora are searched globally, app/retrieve.py:472-487):
+      1. dense search over ``artifact_chunks`` (summaries / decisions / action items),
+      2. the calls of the best artifact hits become a shortlist (first-seen order, <= max_calls),
+      3. ``chunks`` is searched *scoped to those calls* -- the K6 bitmap restricts the K1 scan, and the
+         planner sees a scoped query, so small shortlists run in mode "exact".
+    Returns the artifact rows, the shortlist, the scoped chunk rows and the planner decisions."""
+    art_count = _estimate_dense_candidates(conn, "artifact_chunks", filters, call_ids)
+    art_mode = _choose_dense_mode(art_count, filters, call_ids)
+    artifacts = _fetch_artifacts_dense(conn, query_embedding, filters, call_ids, art_mode, artifact_limit)
+    shortlist: List[Any] = []
+    for row in artifacts:
+        if row["call_id"] not in shortlist:
+            shortlist.append(row["call_id"])
+        if len(shortlist) >= max_calls:
+            break
+    if call_ids is not None:
+        allowed = set(call_ids)
+        shortlist = [c for c in shortlist if c in allowed]
+    chunk_count = _estimate_dense_candidates(conn, "chunks", filters, shortlist)
+    chunk_mode = _choose_dense_mode(chunk_count, filters, shortlist)
+    chunks = _fetch_chunks_dense(conn, query_embedding, filters, shortlist, chunk_mode, chunk_limit)
+    return {"artifacts": artifacts, "call_shortlist": shortlist, "chunks": chunks,
+            "modes": {"artifact_chunks": art_mode, "chunks": chunk_mode},
+            "candidate_rows": {"artifact_chunks": art_count, "chunks": chunk_count}}

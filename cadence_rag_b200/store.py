@@ -221,7 +221,8 @@ class DenseStore:
         for r0 in range(0, rows, chunk_rows):
             m = min(chunk_rows, rows - r0)
             mm[r0:r0 + m] = self.read_rows(r0, m, (what,))[what]
-            _ffi.check(_ffi.lib().cdr_store_read_valid(self.handle, r0, m, _ffi.ptr(valid[r0:r0 + m])), "cdr_store_read_valid")
+            vslice = valid[r0:r0 + m]
+            _ffi.check(_ffi.lib().cdr_store_read_valid(self.handle, r0, m, _ffi.ptr(vslice)), "cdr_store_read_valid")
         mm.flush(); del mm
         cols = self.read_rows(0, rows, ("ids", "call_slot", "started_at", "tag_bits"))
         np.savez(os.path.join(path, "columns.npz"), valid=valid, **cols)
@@ -263,12 +264,15 @@ class DenseStore:
                 if what == "bf16":
                     block = (block.astype(np.uint32) << 16).view(np.float32)
                 sl = slice(r0, r0 + m)
+                # keep the contiguous copies alive across the C call (ptr() only returns an address)
+                c_ids = np.ascontiguousarray(cols["ids"][sl])
+                c_slot = np.ascontiguousarray(cols["call_slot"][sl])
+                c_time = np.ascontiguousarray(cols["started_at"][sl])
+                c_tags = np.ascontiguousarray(cols["tag_bits"][sl])
+                c_valid = np.ascontiguousarray(cols["valid"][sl])
                 _ffi.check(_ffi.lib().cdr_store_append(
-                    store.handle, _ffi.ptr(block), _ffi.ptr(np.ascontiguousarray(cols["ids"][sl])),
-                    _ffi.ptr(np.ascontiguousarray(cols["call_slot"][sl])),
-                    _ffi.ptr(np.ascontiguousarray(cols["started_at"][sl])),
-                    _ffi.ptr(np.ascontiguousarray(cols["tag_bits"][sl])),
-                    _ffi.ptr(np.ascontiguousarray(cols["valid"][sl])), m, 0, store._stream()), "cdr_store_append")
+                    store.handle, _ffi.ptr(block), _ffi.ptr(c_ids), _ffi.ptr(c_slot), _ffi.ptr(c_time),
+                    _ffi.ptr(c_tags), _ffi.ptr(c_valid), m, 0, store._stream()), "cdr_store_append")
         store.finalize()
         return store
 

@@ -610,3 +610,27 @@ def test_wire_formats_and_snapshot_roundtrip(tmp_path, monkeypatch):
         assert np.array_equal(b[0], a[0]) and np.array_equal(b[1].view(np.uint64), a[1].view(np.uint64))
     assert r.slot_of_call(_uuid(9)) == s.slot_of_call(_uuid(9))
     s.close(); r.close()
+
+
+def test_hierarchical_scoping(hybrid_engine, monkeypatch):
+    """f-4: artifact hits -> call shortlist -> chunk search scoped to the shortlist."""
+    eng, meta = hybrid_engine
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    q = orc.synth_rows(SYNTH_QUERY_SEED, 3, 1)[0]
+    with eng.connect() as conn:
+        out = retrieve.fetch_chunks_dense_hierarchical(conn, q, None, None, max_calls=5)
+    ma, mc = meta["artifact_chunks"], meta["chunks"]
+    a_ids, _ = orc.exact_scan(q, ma["x"], 10, ids=ma["ids"], allow=orc.rows_to_bitmap(ma["valid"]))
+    assert [r["artifact_chunk_id"] for r in out["artifacts"]] == a_ids.tolist()
+    want_calls = []
+    for i in a_ids.tolist():
+        c = _uuid(int(ma["call_of_row"][i // 2 - 1]))
+        if c not in want_calls:
+            want_calls.append(c)
+    want_calls = want_calls[:5]
+    assert out["call_shortlist"] == want_calls
+    keep = np.isin(mc["call_of_row"], [c.int - 1 for c in want_calls]) & mc["valid"]
+    c_ids, c_sc = orc.exact_scan(q, mc["x"], 50, ids=mc["ids"], allow=orc.rows_to_bitmap(keep))
+    assert [r["chunk_id"] for r in out["chunks"]] == c_ids.tolist()
+    assert out["candidate_rows"]["chunks"] == int(keep.sum()) and out["modes"]["chunks"] == "exact"
+    assert all(r["call_id"] in want_calls for r in out["chunks"])
