@@ -83,6 +83,10 @@ SIGNATURES = {
     "cdr_topk_merge": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cdr_rrf_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_rrf_merge_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cdr_tech_index_create": (_i32, [ctypes.POINTER(_vp), _vp, _vp, _i32, _vp, _vp]),
+    "cdr_tech_index_destroy": (_i32, [_vp]),
+    "cdr_tech_lane_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _i64, _i32, _i64, _i32, _u64, _i32,
+                                  _vp, _vp, _vp]),
     "cdr_kernel_launch_count": (_i64, []),
     "cdr_prof_enable": (_i32, [_i32]),
     "cdr_prof_read": (_i32, [_i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),

@@ -276,4 +276,58 @@ __device__ __forceinline__ void warp_merge_topk(uint64_t (&mine)[NPL], const uin
     warp_bitonic_merge_desc<NPL>(mine, lane);
 }
 
+// Per-warp running top-KC in shared memory: unsorted list + (min key, position) in registers.
+template <int NPL>
+struct WarpTopK {
+    uint64_t *list;   // [KC]
+    uint64_t tau;     // current admission threshold (0 while the list is not full)
+    int count;
+    int min_pos;
+
+    __device__ __forceinline__ void init(uint64_t *l, int lane)
+    {
+        list = l;
+        tau = 0;
+        count = 0;
+        min_pos = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) list[i * 32 + lane] = CDR_EMPTY_KEY;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void refresh_min(int lane)
+    {
+        uint64_t m = ~0ull;
+        int pos = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            uint64_t v = list[i * 32 + lane];
+            if (v < m) { m = v; pos = i * 32 + lane; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            uint64_t om = __shfl_xor_sync(0xffffffffu, m, o);
+            int op = __shfl_xor_sync(0xffffffffu, pos, o);
+            if (om < m) { m = om; pos = op; }   // keys are unique, so no tie handling needed
+        }
+        tau = m;
+        min_pos = pos;
+    }
+    // warp-uniform call
+    __device__ __forceinline__ void push(uint64_t key, int lane)
+    {
+        constexpr int KC = NPL * 32;
+        if (count < KC) {
+            if (lane == 0) list[count] = key;
+            ++count;
+            __syncwarp();
+            if (count == KC) refresh_min(lane);
+        } else {
+            if (lane == 0) list[min_pos] = key;
+            __syncwarp();
+            refresh_min(lane);
+        }
+    }
+};
+
+
 #endif  // __CUDACC__

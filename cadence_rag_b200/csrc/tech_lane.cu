@@ -1,0 +1,249 @@
+// tech_lane.cu -- device-resident tech_tokens lexical lane.
+//
+// Replaces the SQL of _fetch_chunks_tech / _fetch_artifacts_tech (app/retrieve.py:183-242):
+//     WHERE <filters> AND tech_tokens && :tokens
+//     ORDER BY call_started_at DESC, <id> ASC LIMIT :limit
+// which Postgres answers from a GIN index on the text[] column (alembic 0001:96).  Here the index
+// is a dictionary-encoded CSR posting structure in HBM (token id -> ascending row list) plus one
+// precomputed u32 per row: its rank in the global order (call_started_at DESC, id ASC).  The lane
+// has no score, so "top-limit" = the `limit` smallest ranks among matching rows: the same packed
+// u64 key / warp top-k machinery as the dense lane applies, with key =
+// ((0xFFFFFFFF - rank) << 32) | (0xFFFFFFFF - row).
+//
+// One CTA (8 warps) per query.  Warp w scans, for every query token, the part of the posting list
+// that falls in its row range [w*N/8, (w+1)*N/8) (two binary searches), so all occurrences of a row
+// (it may match several tokens) meet in one warp and are de-duplicated on insert.  The filter
+// predicate (call_id = ANY, date range, tags overlap -- app/retrieve.py:93-120, WITHOUT the dense
+// lane's `embedding IS NOT NULL`) is evaluated on the posting rows only.
+#include "common.cuh"
+
+struct cdr_tech_index {
+    cdr_store *store = nullptr;
+    int32_t n_tokens = 0;
+    int64_t n_postings = 0;
+    int64_t *offsets = nullptr;    // [n_tokens + 1]
+    uint32_t *rows = nullptr;      // [n_postings]
+    uint32_t *rank = nullptr;      // [store rows]
+};
+
+namespace {
+
+constexpr int kTechWarps = 8;
+constexpr int kTechMaxTokens = 32;
+
+struct TechParams {
+    const int64_t *offsets;
+    const uint32_t *post_rows;
+    const uint32_t *rank;
+    const int64_t *ids;
+    const int32_t *call_slot;
+    const int64_t *started_at;
+    const uint64_t *tag_bits;
+    const uint32_t *call_bitmap;   // nullable
+    int64_t n_call_slots;
+    int64_t n_rows;
+    int n_index_tokens;
+    int has_from, has_to, has_tags;
+    int64_t date_from, date_to;
+    uint64_t tag_any;
+    const int32_t *q_tokens;       // [nq, max_tokens]
+    const int32_t *q_ntok;         // [nq]
+    int max_tokens;
+    int limit;
+    int64_t *out_ids;              // [nq, limit]
+    int32_t *out_n;                // [nq]
+};
+
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *a, int64_t lo, int64_t hi, uint32_t v)
+{
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechParams p)
+{
+    constexpr int KC = NPL * 32;
+    __shared__ uint64_t s_lists[kTechWarps * KC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x;
+    const int ntok = min(p.q_ntok[q], p.max_tokens);
+    const int32_t *toks = p.q_tokens + (size_t)q * p.max_tokens;
+
+    WarpTopK<NPL> top;
+    top.init(s_lists + warp * KC, lane);
+    const uint32_t r_lo = (uint32_t)((p.n_rows * warp) / kTechWarps);
+    const uint32_t r_hi = (uint32_t)((p.n_rows * (warp + 1)) / kTechWarps);
+
+    for (int t = 0; t < ntok; ++t) {
+        const int32_t tok = toks[t];
+        if (tok < 0 || tok >= p.n_index_tokens) continue;            // unknown token: no postings
+        const int64_t b0 = p.offsets[tok], b1 = p.offsets[tok + 1];
+        const int64_t lo = lower_bound_u32(p.post_rows, b0, b1, r_lo);
+        const int64_t hi = lower_bound_u32(p.post_rows, lo, b1, r_hi);
+        for (int64_t base = lo; base < hi; base += 32) {
+            const int64_t i = base + lane;
+            uint64_t key = CDR_EMPTY_KEY;
+            if (i < hi) {
+                const uint32_t row = p.post_rows[i];
+                bool ok = true;
+                if (p.call_bitmap) {
+                    const int32_t slot = p.call_slot[row];
+                    ok = slot >= 0 && slot < p.n_call_slots && ((p.call_bitmap[slot >> 5] >> (slot & 31)) & 1u);
+                }
+                if (ok && (p.has_from | p.has_to)) {
+                    const int64_t ts = p.started_at[row];
+                    if (p.has_from && ts < p.date_from) ok = false;
+                    if (p.has_to && ts > p.date_to) ok = false;
+                }
+                if (ok && p.has_tags) ok = (p.tag_bits[row] & p.tag_any) != 0ull;
+                if (ok) key = ((uint64_t)(0xFFFFFFFFu - p.rank[row]) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+            }
+            // insert the lanes' candidates one by one (warp-uniform), skipping rows already listed
+            unsigned pending = __ballot_sync(0xffffffffu, key > top.tau);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint64_t k = __shfl_sync(0xffffffffu, key, src);
+                if (k <= top.tau) continue;
+                bool dup = false;
+#pragma unroll
+                for (int e = 0; e < NPL; ++e) dup |= top.list[e * 32 + lane] == k;
+                if (__any_sync(0xffffffffu, dup)) continue;
+                top.push(k, lane);
+            }
+        }
+    }
+
+    // per-warp sort, then pairwise merge tree (as in the dense lane)
+    uint64_t k[NPL];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) k[i] = top.list[i * 32 + lane];
+    warp_bitonic_sort_desc<NPL>(k, lane);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
+#pragma unroll
+    for (int step = 1; step < kTechWarps; step <<= 1) {
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0) {
+            warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
+        }
+    }
+    __syncthreads();
+    int n = 0;
+    for (int e = threadIdx.x; e < KC; e += blockDim.x) {
+        const uint64_t key = s_lists[e];
+        if (e < p.limit) p.out_ids[(size_t)q * p.limit + e] = key != CDR_EMPTY_KEY ? p.ids[cdr_key_row(key)] : -1;
+    }
+    if (threadIdx.x == 0) {
+        for (int e = 0; e < KC && e < p.limit; ++e) n += s_lists[e] != CDR_EMPTY_KEY;
+        p.out_n[q] = n;
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t cdr_tech_index_create(cdr_tech_index **out, cdr_store *s, const int64_t *post_offsets_host,
+                                         int32_t n_tokens, const uint32_t *post_rows_host,
+                                         const uint32_t *rank_host)
+{
+    CDR_REQUIRE(out && s && post_offsets_host && rank_host && n_tokens >= 0, CDR_ERR_INVALID,
+                "cdr_tech_index_create: NULL argument");
+    CDR_REQUIRE(s->finalized, CDR_ERR_STATE, "cdr_tech_index_create: store not finalized");
+    *out = nullptr;
+    const int64_t total = post_offsets_host[n_tokens];
+    CDR_REQUIRE(total >= 0 && (total == 0 || post_rows_host), CDR_ERR_INVALID, "cdr_tech_index_create: bad postings");
+    DeviceGuard g(s->device);
+    cdr_tech_index *ix = new cdr_tech_index();
+    ix->store = s;
+    ix->n_tokens = n_tokens;
+    ix->n_postings = total;
+    cudaError_t e = cudaMalloc(&ix->offsets, (size_t)(n_tokens + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->rows, (size_t)(total > 0 ? total : 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->rank, (size_t)(s->n_rows > 0 ? s->n_rows : 1) * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(ix->offsets, post_offsets_host, (size_t)(n_tokens + 1) * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && total > 0) e = cudaMemcpy(ix->rows, post_rows_host, (size_t)total * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && s->n_rows > 0) e = cudaMemcpy(ix->rank, rank_host, (size_t)s->n_rows * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cdr_set_error("cdr_tech_index_create: %s", cudaGetErrorString(e));
+        cudaFree(ix->offsets); cudaFree(ix->rows); cudaFree(ix->rank);
+        delete ix;
+        return e == cudaErrorMemoryAllocation ? CDR_ERR_OOM : CDR_ERR_CUDA;
+    }
+    *out = ix;
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_tech_index_destroy(cdr_tech_index *ix)
+{
+    if (!ix) return CDR_OK;
+    DeviceGuard g(ix->store->device);
+    cudaDeviceSynchronize();
+    cudaFree(ix->offsets);
+    cudaFree(ix->rows);
+    cudaFree(ix->rank);
+    delete ix;
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_tech_lane_host(cdr_tech_index *ix, const int32_t *token_ids_host, const int32_t *n_tokens_host,
+                                      int32_t nq, int32_t max_tokens, const uint32_t *call_slot_bitmap_host,
+                                      int64_t n_call_slots, int32_t has_date_from, int64_t date_from_us,
+                                      int32_t has_date_to, int64_t date_to_us, int32_t has_tag_filter,
+                                      uint64_t tag_any, int32_t limit, int64_t *out_ids_host, int32_t *out_n_host,
+                                      void *stream)
+{
+    CDR_REQUIRE(ix && token_ids_host && n_tokens_host && out_ids_host && out_n_host, CDR_ERR_INVALID,
+                "cdr_tech_lane_host: NULL argument");
+    CDR_REQUIRE(nq >= 0 && max_tokens >= 1 && max_tokens <= kTechMaxTokens, CDR_ERR_INVALID,
+                "cdr_tech_lane_host: need 1 <= max_tokens <= %d", kTechMaxTokens);
+    CDR_REQUIRE(limit >= 1 && limit <= CDR_MAX_K, CDR_ERR_UNSUPPORTED, "cdr_tech_lane_host: limit=%d outside [1,%d]",
+                limit, CDR_MAX_K);
+    if (nq == 0) return CDR_OK;
+    cdr_store *s = ix->store;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_tok = up((size_t)nq * max_tokens * 4), b_nt = up((size_t)nq * 4);
+    const size_t b_bm = call_slot_bitmap_host ? up((size_t)((n_call_slots + 31) / 32 + 1) * 4) : 0;
+    const size_t b_oid = up((size_t)nq * limit * 8), b_on = up((size_t)nq * 4);
+    unsigned char *buf = nullptr;
+    CDR_CUDA(cudaMallocAsync(&buf, b_tok + b_nt + b_bm + b_oid + b_on, st));
+    unsigned char *c = buf;
+    int32_t *d_tok = (int32_t *)c; c += b_tok;
+    int32_t *d_nt = (int32_t *)c; c += b_nt;
+    uint32_t *d_bm = call_slot_bitmap_host ? (uint32_t *)c : nullptr; c += b_bm;
+    int64_t *d_oid = (int64_t *)c; c += b_oid;
+    int32_t *d_on = (int32_t *)c;
+    CDR_CUDA(cudaMemcpyAsync(d_tok, token_ids_host, (size_t)nq * max_tokens * 4, cudaMemcpyHostToDevice, st));
+    CDR_CUDA(cudaMemcpyAsync(d_nt, n_tokens_host, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+    if (d_bm) {
+        CDR_CUDA(cudaMemsetAsync(d_bm, 0, b_bm, st));
+        if (n_call_slots > 0)
+            CDR_CUDA(cudaMemcpyAsync(d_bm, call_slot_bitmap_host, (size_t)((n_call_slots + 31) / 32) * 4,
+                                     cudaMemcpyHostToDevice, st));
+    }
+    TechParams p;
+    p.offsets = ix->offsets; p.post_rows = ix->rows; p.rank = ix->rank;
+    p.ids = s->ids; p.call_slot = s->call_slot; p.started_at = s->started_at; p.tag_bits = s->tag_bits;
+    p.call_bitmap = d_bm; p.n_call_slots = n_call_slots; p.n_rows = s->n_rows; p.n_index_tokens = ix->n_tokens;
+    p.has_from = has_date_from != 0; p.has_to = has_date_to != 0; p.has_tags = has_tag_filter != 0;
+    p.date_from = date_from_us; p.date_to = date_to_us; p.tag_any = tag_any;
+    p.q_tokens = d_tok; p.q_ntok = d_nt; p.max_tokens = max_tokens; p.limit = limit;
+    p.out_ids = d_oid; p.out_n = d_on;
+    if (limit <= 64) tech_lane_kernel<2><<<nq, kTechWarps * 32, 0, st>>>(p);
+    else tech_lane_kernel<8><<<nq, kTechWarps * 32, 0, st>>>(p);
+    CDR_LAUNCH_CHECK();
+    CDR_CUDA(cudaMemcpyAsync(out_ids_host, d_oid, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaMemcpyAsync(out_n_host, d_on, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CDR_CUDA(cudaFreeAsync(buf, st));
+    CDR_CUDA(cudaStreamSynchronize(st));
+    return CDR_OK;
+}

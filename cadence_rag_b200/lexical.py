@@ -108,3 +108,86 @@ class TechTokenIndex:
         rows = rows[keep]
         order = np.lexsort((cols["ids"][rows], -cols["started_at"][rows]))
         return rows[order][:limit]
+
+
+class DeviceTechIndex:
+    """The same index resident in HBM: CSR postings over dictionary-encoded
+    tokens + one precomputed rank per row; queries run in the ``tech_lane_kernel`` (csrc/tech_lane.cu)
+    through ``cdr_tech_lane_host``.  Built once from a host :class:`TechTokenIndex` and the store's
+    columns; a token unknown to the dictionary simply has no postings."""
+
+    MAX_TOKENS = 32
+
+    def __init__(self, host_index: TechTokenIndex, store):
+        import ctypes
+        from . import _ffi
+        self._ffi = _ffi
+        self.store = store
+        tokens = sorted(set(host_index._lists) | set(host_index._arrays))
+        self.token_ids: Dict[str, int] = {t: i for i, t in enumerate(tokens)}
+        lists = [host_index.postings(t) for t in tokens]
+        offsets = np.zeros(len(tokens) + 1, dtype=np.int64)
+        if lists:
+            offsets[1:] = np.cumsum([l.size for l in lists])
+        rows = (np.concatenate(lists) if lists else np.empty(0, dtype=np.int64)).astype(np.uint32)
+        cols = store.host_columns()
+        order = np.lexsort((cols["ids"], -cols["started_at"]))          # (call_started_at DESC, id ASC)
+        rank = np.empty(order.size, dtype=np.uint32)
+        rank[order] = np.arange(order.size, dtype=np.uint32)
+        self._h = ctypes.c_void_p()
+        _ffi.check(_ffi.lib().cdr_tech_index_create(ctypes.byref(self._h), store.handle, _ffi.ptr(offsets),
+                                                    len(tokens), _ffi.ptr(rows), _ffi.ptr(rank)),
+                   "cdr_tech_index_create")
+
+    def close(self) -> None:
+        if self._h:
+            self._ffi.lib().cdr_tech_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query_batch(self, token_lists: Sequence[Sequence[str]], limit: int, *,
+                    call_slots: Optional[Sequence[int]] = None, date_from=None, date_to=None,
+                    tag_mask: Optional[int] = None):
+        """ids[nq, limit] (unused slots -1) and n[nq] for nq token lists under one filter."""
+        import ctypes
+        import torch
+        from .store import to_micros
+        _ffi = self._ffi
+        nq = len(token_lists)
+        tok = np.full((nq, self.MAX_TOKENS), -1, dtype=np.int32)
+        ntok = np.zeros(nq, dtype=np.int32)
+        for i, toks in enumerate(token_lists):
+            ids = [self.token_ids.get(t, -1) for t in toks]
+            ids = [t for t in ids if t >= 0][: self.MAX_TOKENS]
+            tok[i, :len(ids)] = ids
+            ntok[i] = len(ids)
+        bm, n_slots = None, 0
+        if call_slots is not None:
+            n_slots = max(len(self.store.call_ids_by_slot), (max(call_slots) + 1) if len(call_slots) else 0, 1)
+            if self.store.synthetic is not None:
+                n_slots = max(n_slots, (self.store.synthetic["first_row"] + self.store.rows) // self.store.synthetic["rows_per_call"] + 1)
+            bm = np.zeros((n_slots + 31) // 32, dtype=np.uint32)
+            for s_ in call_slots:
+                if 0 <= s_ < n_slots:
+                    bm[s_ >> 5] |= np.uint32(1 << (s_ & 31))
+        out_ids = np.empty((nq, limit), dtype=np.int64)
+        out_n = np.empty(nq, dtype=np.int32)
+        with torch.cuda.device(self.store.device):
+            _ffi.check(_ffi.lib().cdr_tech_lane_host(
+                self._h, _ffi.ptr(tok), _ffi.ptr(ntok), nq, self.MAX_TOKENS, _ffi.ptr(bm), n_slots,
+                0 if date_from is None else 1, 0 if date_from is None else to_micros(date_from),
+                0 if date_to is None else 1, 0 if date_to is None else to_micros(date_to),
+                0 if tag_mask is None else 1, ctypes.c_uint64(tag_mask or 0), limit,
+                _ffi.ptr(out_ids), _ffi.ptr(out_n), self.store._stream()), "cdr_tech_lane_host")
+        return out_ids, out_n
+
+    def query_ids(self, tokens: Sequence[str], limit: int, **spec) -> List[int]:
+        if not tokens or limit <= 0:
+            return []
+        ids, n = self.query_batch([list(tokens)], limit, **spec)
+        return ids[0, :int(n[0])].tolist()

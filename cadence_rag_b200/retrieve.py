@@ -29,7 +29,7 @@ from . import _ffi
 from ._ffi import DenseEngineError
 from .config import settings
 from .embeddings import EmbeddingClientError, embed_texts, embeddings_enabled
-from .lexical import TechTokenIndex, extract_tech_tokens
+from .lexical import DeviceTechIndex, TechTokenIndex, extract_tech_tokens
 from .store import DenseStore
 
 DEFAULT_RRF_K = 60
@@ -82,12 +82,18 @@ class DenseEngine:
     def __init__(self):
         self.stores: Dict[str, DenseStore] = {}
         self.tech_indexes: Dict[str, TechTokenIndex] = {}
+        self.device_tech_indexes: Dict[str, DeviceTechIndex] = {}
         self.external_ids: Dict[Tuple[str, Optional[str]], Set[Any]] = {}
 
-    def register(self, store: DenseStore, tech_index: Optional[TechTokenIndex] = None) -> None:
+    def register(self, store: DenseStore, tech_index: Optional[TechTokenIndex] = None,
+                 device_tech_lane: bool = True) -> None:
+        """``tech_index``: host inverted index of the table's tech_tokens.  With ``device_tech_lane``
+        (default) it is also uploaded as a :class:`DeviceTechIndex` and the lane runs on the GPU."""
         self.stores[store.table_name] = store
         if tech_index is not None:
             self.tech_indexes[store.table_name] = tech_index
+            if device_tech_lane:
+                self.device_tech_indexes[store.table_name] = DeviceTechIndex(tech_index, store)
 
     def register_call(self, call_id, external_id: Optional[str] = None, external_source: Optional[str] = None) -> None:
         if external_id is not None:
@@ -279,7 +285,13 @@ def _fetch_tech(conn: DenseConnection, table_name: str, tokens: Sequence[str], f
     # the tech lane's WHERE has no `embedding IS NOT NULL` term (app/retrieve.py:195-208), so the
     # predicate is evaluated on the host columns of the posting rows, not through the K6 bitmap
     spec = _filter_spec(store, filters, call_ids)
-    rows = index.query(tokens, store.host_columns(), limit, **spec)
+    dev_index = conn.engine.device_tech_indexes.get(table_name)
+    cols = store.host_columns()
+    if dev_index is not None:                      # GPU lane (f-1); ids come back already ordered
+        hit_ids = np.asarray(dev_index.query_ids(tokens, limit, **spec), dtype=np.int64)
+        rows = np.searchsorted(cols["ids"], hit_ids)
+    else:
+        rows = index.query(tokens, cols, limit, **spec)
     cols = store.host_columns()
     out = []
     for p in rows.tolist():

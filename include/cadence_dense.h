@@ -181,6 +181,26 @@ int32_t cdr_rrf_merge_host(const int64_t *lane_ids_host, const int32_t *lane_off
                            int64_t *out_ids_host, double *out_scores_host,
                            uint32_t *out_lane_mask_host, int32_t *out_n_host, void *stream);
 
+/* ---- tech_tokens lexical lane, device resident -------------------------
+ * Replaces the SQL of _fetch_chunks_tech / _fetch_artifacts_tech (app/retrieve.py:183-242):
+ *   WHERE <filters> AND tech_tokens && :tokens ORDER BY call_started_at DESC, id ASC LIMIT :limit
+ * The index is CSR postings over dictionary-encoded tokens (token t -> ascending rows
+ * post_rows[post_offsets[t] .. post_offsets[t+1])) plus rank[row] = position of the row in the
+ * order (call_started_at DESC, id ASC).  Queries carry token ids (-1 = unknown token).  The filter
+ * arguments are those of cdr_filter_build, without the `embedding IS NOT NULL` term (the tech
+ * lane's WHERE has none).  Host buffers; synchronises.  out_ids [nq, limit] (unused slots -1). */
+typedef struct cdr_tech_index cdr_tech_index;
+int32_t cdr_tech_index_create(cdr_tech_index **out, cdr_store *s, const int64_t *post_offsets_host,
+                              int32_t n_tokens, const uint32_t *post_rows_host,
+                              const uint32_t *rank_host);
+int32_t cdr_tech_index_destroy(cdr_tech_index *ix);
+int32_t cdr_tech_lane_host(cdr_tech_index *ix, const int32_t *token_ids_host,
+                           const int32_t *n_tokens_host, int32_t nq, int32_t max_tokens,
+                           const uint32_t *call_slot_bitmap_host, int64_t n_call_slots,
+                           int32_t has_date_from, int64_t date_from_us, int32_t has_date_to,
+                           int64_t date_to_us, int32_t has_tag_filter, uint64_t tag_any,
+                           int32_t limit, int64_t *out_ids_host, int32_t *out_n_host, void *stream);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* Number of this library's kernels launched by the calling process so far (bench.py's
  * gpu_launches claim). */

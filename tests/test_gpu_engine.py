@@ -634,3 +634,33 @@ def test_hierarchical_scoping(hybrid_engine, monkeypatch):
     assert [r["chunk_id"] for r in out["chunks"]] == c_ids.tolist()
     assert out["candidate_rows"]["chunks"] == int(keep.sum()) and out["modes"]["chunks"] == "exact"
     assert all(r["call_id"] in want_calls for r in out["chunks"])
+
+
+def test_device_tech_lane_matches_port(hybrid_engine):
+    """f-1: the GPU tech_tokens lane == the restated SQL (port) == the host index, incl. filters,
+    duplicates across tokens, unknown tokens, limits, and batches."""
+    eng, meta = hybrid_engine
+    t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+    for table in ("chunks", "artifact_chunks"):
+        m, store = meta[table], eng.stores[table]
+        dev, host = eng.device_tech_indexes[table], eng.tech_indexes[table]
+        cols = store.host_columns()
+        cases = [(["TOK-0"], {}), (["TOK-0", "TOK-1", "TOK-2", "nope"], {}), (["nope"], {}),
+                 (["TOK-3", "TOK-3"], {"call_slots": list(range(0, 100, 7))}),
+                 (["TOK-1", "TOK-9"], {"date_from": t0 + timedelta(hours=20), "date_to": t0 + timedelta(hours=60)}),
+                 (["TOK-0", "TOK-4"], {"tag_mask": store.bits_of_tags(["t2"])}), (["TOK-2"], {"call_slots": []}),
+                 ([f"TOK-{i}" for i in range(40)], {})]
+        for tokens, spec in cases:
+            for limit in (50, 7, 200):
+                from cadence_rag_b200.store import to_micros
+                keep = ports.filter_rows(cols["call_slot"], cols["started_at"], cols["tag_bits"], None,
+                                         call_slots=spec.get("call_slots"),
+                                         date_from_us=to_micros(spec["date_from"]) if "date_from" in spec else None,
+                                         date_to_us=to_micros(spec["date_to"]) if "date_to" in spec else None,
+                                         tag_mask=spec.get("tag_mask"))
+                want = ports.tech_lane(m["row_tokens"], m["ids"], cols["started_at"], keep, tokens[:32], limit)
+                assert dev.query_ids(tokens, limit, **spec) == want, (table, tokens, spec, limit)
+                assert cols["ids"][host.query(tokens[:32], cols, limit, **spec)].tolist() == want
+        ids, n = dev.query_batch([["TOK-0"], [], ["TOK-5", "TOK-6"]], 50)
+        assert n[1] == 0 and ids[0, :n[0]].tolist() == dev.query_ids(["TOK-0"], 50)
+        assert ids[2, :n[2]].tolist() == dev.query_ids(["TOK-5", "TOK-6"], 50) and np.all(ids[1] == -1)
