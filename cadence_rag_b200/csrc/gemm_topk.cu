@@ -111,6 +111,53 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- cta_group::2 ("2-SM MMA") forms: one MMA spans the CTA pair (M = 256), each CTA holds its
+// own 128 A rows and HALF of the B tile; the leader CTA (rank 0) issues, both CTAs' tensor cores work.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into OWN shared memory whose completion bytes are credited to the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on the barrier at the same offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask)
 {
@@ -146,6 +193,8 @@ constexpr uint32_t kInstrDesc = (1u << 4)                    // D format: fp32
                                 | (1u << 10)                 // B format: bf16
                                 | ((uint32_t)(kBlockN >> 3) << 17)
                                 | ((uint32_t)(kBlockM >> 4) << 24);   // A, B K-major (bits 15,16 = 0)
+constexpr uint32_t kInstrDesc2Sm = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17)
+                                   | ((uint32_t)((2 * kBlockM) >> 4) << 24);   // M = 256 across the CTA pair
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 {
@@ -201,7 +250,12 @@ __device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int
 // tiles; each loads half of the B (corpus) box and multicasts it to both, halving the L2->SM
 // traffic of the large operand.  A stage may be refilled only when BOTH CTAs' MMAs have drained
 // it, so the MMA warps commit to the empty barrier of both CTAs.
-template <int kCluster>
+// k2Sm (requires kCluster == 2): cta_group::2 MMAs.  Each CTA stages its own A tile and only its half
+// of the B tile (32 KB per stage instead of 48 KB => 6 stages instead of 4, and a third less shared
+// memory read per MMA), TMA completions of both CTAs are credited to the leader's "full" barrier,
+// the leader's MMA warp issues for the pair and commits to both CTAs' barriers, and both CTAs'
+// epilogue warps hand their TMEM buffers back to the leader.
+template <int kCluster, bool k2Sm>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const GemmParams p)
@@ -209,13 +263,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     extern __shared__ unsigned char smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    static_assert(!k2Sm || kCluster == 2, "2-SM MMA needs a CTA pair");
+    constexpr int kStg = k2Sm ? 6 : kStages;                              // ring depth
+    constexpr int kBLocal = k2Sm ? kBBytes / 2 : kBBytes;                  // B bytes staged per CTA per stage
+    constexpr int kStgBytes = kABytes + kBLocal;
+    static_assert(kStg * kStgBytes == kStages * kStageBytes, "both modes use the same tile memory");
     unsigned char *tiles = smem;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
-    uint64_t *full_bar = bars;                    // [kStages]
-    uint64_t *empty_bar = bars + kStages;         // [kStages]
-    uint64_t *tmem_full = bars + 2 * kStages;     // [2]
-    uint64_t *tmem_empty = bars + 2 * kStages + 2;  // [2]
-    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    uint64_t *full_bar = bars;                    // [kStg]
+    uint64_t *empty_bar = bars + kStg;            // [kStg]
+    uint64_t *tmem_full = bars + 2 * kStg;        // [2]
+    uint64_t *tmem_empty = bars + 2 * kStg + 2;   // [2]
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStg + 4);
     uint64_t *buf_key = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [kBufN][128]
     uint16_t *buf_q = reinterpret_cast<uint16_t *>(buf_key + kBufN * 128);                            // [kBufN][128]
 
@@ -226,17 +285,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         prefetch_tmap(&map_x);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kCluster);
+        for (int s = 0; s < kStg; ++s) {
+            mbar_init(&full_bar[s], k2Sm ? 2 : 1);               // 2-SM: leader's expect_tx arrive + peer's arrive
+            mbar_init(&empty_bar[s], k2Sm ? 1 : kCluster);       // 2-SM: one multicast commit from the leader
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 4);     // one arrival per epilogue warp
+            mbar_init(&tmem_empty[b], k2Sm ? 8 : 4);             // one arrival per epilogue warp (of both CTAs)
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_base_slot, kTmemCols);
+    if (warp == 2) {
+        if (k2Sm) tmem_alloc_2sm(tmem_base_slot, kTmemCols);
+        else tmem_alloc(tmem_base_slot, kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
     if (kCluster > 1) cluster_sync_all();     // peer barriers are initialised before any remote arrive
@@ -259,11 +321,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const int mt = (int)(w % mt_per) * kCluster + (int)crank;
                 const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
                 for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t ph = (it / kStages) & 1u;
+                    const int s = it % kStg;
+                    const uint32_t ph = (it / kStg) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
+                    unsigned char *a = tiles + (size_t)s * kStgBytes;
+                    if (k2Sm) {
+                        const uint32_t leader_bar = mapa_u32(smem_u32(&full_bar[s]), 0u);
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * kStgBytes);   // both CTAs' bytes
+                        else mbar_arrive_cluster(leader_bar);
+                        tma_load_2d_2sm(a, &map_q, kb * kBlockK, mt * kBlockM, leader_bar);
+                        tma_load_2d_2sm(a + kABytes, &map_x, kb * kBlockK,
+                                        (int)(nt * kBlockN) + (int)crank * (kBlockN / 2), leader_bar);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                    unsigned char *a = tiles + (size_t)s * kStageBytes;
                     tma_load_2d(a, &map_q, kb * kBlockK, mt * kBlockM, &full_bar[s]);
                     if (kCluster == 1) {
                         tma_load_2d(a + kABytes, &map_x, kb * kBlockK, (int)(nt * kBlockN), &full_bar[s]);
@@ -276,8 +347,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
+    } else if (warp == 1 && !(k2Sm && crank != 0)) {
+        // ---------------------------------------------------------------- MMA issuer (2-SM: leader CTA only)
         uint32_t it = 0, tile_no = 0;
         for (int64_t w = w0; w < n_items; w += G, ++tile_no) {
             const uint32_t buf = tile_no & 1u;
@@ -286,24 +357,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + buf * kBlockN;
             for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1u;
+                const int s = it % kStg;
+                const uint32_t ph = (it / kStg) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const unsigned char *a = tiles + (size_t)s * kStageBytes;
+                    const unsigned char *a = tiles + (size_t)s * kStgBytes;
                     const uint64_t adesc = make_smem_desc(a);
                     const uint64_t bdesc = make_smem_desc(a + kABytes);
 #pragma unroll
                     for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
                         // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        umma_bf16(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), kInstrDesc,
-                                  (kb | k4) != 0 ? 1u : 0u);
+                        if (k2Sm)
+                            umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), kInstrDesc2Sm,
+                                          (kb | k4) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16(tmem_d, adesc + (uint64_t)(k4 * 2), bdesc + (uint64_t)(k4 * 2), kInstrDesc,
+                                      (kb | k4) != 0 ? 1u : 0u);
                     }
                     // smem stage free when these MMAs retire (in every CTA that TMA-writes it)
-                    if (kCluster == 1) umma_commit(&empty_bar[s]);
+                    if (k2Sm) umma_commit_2sm_mc(&empty_bar[s], (uint16_t)0x3);
+                    else if (kCluster == 1) umma_commit(&empty_bar[s]);
                     else umma_commit_mc(&empty_bar[s], (uint16_t)0x3);
-                    if (kb == p.k_blocks - 1) umma_commit(&tmem_full[buf]);
+                    if (kb == p.k_blocks - 1) {
+                        if (k2Sm) umma_commit_2sm_mc(&tmem_full[buf], (uint16_t)0x3);
+                        else umma_commit(&tmem_full[buf]);
+                    }
                 }
                 __syncwarp();
             }
@@ -379,7 +458,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            if (lane == 0) {
+                if (k2Sm && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0u));   // leader's barrier
+                else mbar_arrive(&tmem_empty[buf]);
+            }
             // Flush half-full staging buffers NOW, after the accumulator buffer went back to the MMA
             // warp: the atomics' round trip then overlaps the next tile's MMAs instead of holding TMEM.
             if (nbuf >= kBufN / 2 && p.debug_no_append != 3) {
@@ -395,7 +477,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (kCluster > 1) cluster_sync_all();     // no CTA exits while its peer may still multicast into it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (k2Sm) tmem_dealloc_2sm(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -527,11 +610,12 @@ int make_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_
 
 int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
-// 2 = multicast the corpus tile across a 2-CTA cluster (default), 1 = independent CTAs.
-// CADENCE_K2_CLUSTER=1 in the environment selects the latter (A/B measurements).
+// CADENCE_K2_CLUSTER selects the GEMM variant (A/B measurements): 1 = independent CTAs,
+// 2 = multicast the corpus tile across a 2-CTA cluster (default), 3 = cta_group::2 MMAs (2-SM).
 int g_k2_cluster = [] {
     const char *e = getenv("CADENCE_K2_CLUSTER");
-    return (e && e[0] == '1') ? 1 : 2;
+    const int v = e ? atoi(e) : 2;
+    return (v >= 1 && v <= 3) ? v : 2;
 }();
 
 }  // namespace
@@ -589,14 +673,16 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     if (rc != CDR_OK) return rc;
     // B-tile multicast across a 2-CTA cluster needs an even number of query tiles
     const int m_tiles = nq_pad / kBlockM;
-    const int cluster = (m_tiles % 2 == 0 && g_k2_cluster == 2) ? 2 : 1;
+    const int cluster = (m_tiles % 2 == 0 && g_k2_cluster >= 2) ? 2 : 1;
+    const bool two_sm = cluster == 2 && g_k2_cluster == 3;
     rc = make_map(&map_x, s->emb_bf16, s->n_rows, dim, kBlockN / cluster);
     if (rc != CDR_OK) return rc;
 
     static bool attr_done[64] = {false};
     if (!attr_done[s->device & 63]) {
-        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr_done[s->device & 63] = true;
     }
 
@@ -637,7 +723,7 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
         const int grid = (int)(items < max_clusters ? items : max_clusters) * cluster;
         cdr_prof_mark_begin(1, st);
         if (cluster == 1) {
-            gemm_topk_kernel<1><<<grid, kGemmThreads, kGemmSmem, st>>>(map_q, map_x, p);
+            gemm_topk_kernel<1, false><<<grid, kGemmThreads, kGemmSmem, st>>>(map_q, map_x, p);
         } else {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
@@ -651,7 +737,8 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2>, map_q, map_x, p));
+            if (two_sm) CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2, true>, map_q, map_x, p));
+            else CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2, false>, map_q, map_x, p));
         }
         CDR_LAUNCH_CHECK();
         cdr_prof_mark_end(1, st);
