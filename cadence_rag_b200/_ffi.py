@@ -87,11 +87,20 @@ SIGNATURES = {
     "cdr_tech_index_destroy": (_i32, [_vp]),
     "cdr_tech_lane_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _i64, _i32, _i64, _i32, _u64, _i32,
                                   _vp, _vp, _vp]),
+    "cdr_hybrid_retrieve_host": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cdr_kernel_launch_count": (_i64, []),
     "cdr_prof_enable": (_i32, [_i32]),
     "cdr_prof_read": (_i32, [_i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
     "cdr_prof_read_launches": (_i32, [_i32, _vp, _i64, ctypes.POINTER(_i64)]),
 }
+
+
+class FilterSpec(ctypes.Structure):
+    """struct cdr_filter_spec (include/cadence_dense.h)."""
+    _fields_ = [("call_slot_bitmap_host", _vp), ("n_call_slots", _i64), ("has_date_from", _i32),
+                ("has_date_to", _i32), ("date_from_us", _i64), ("date_to_us", _i64), ("has_tag_filter", _i32),
+                ("reserved", _i32), ("tag_any", _u64)]
 
 
 def lib() -> ctypes.CDLL:

@@ -52,6 +52,10 @@ struct ScanWorkspace {
     size_t out_stage_bytes = 0;
     void *gemm_ws = nullptr;        // K2 candidate lists, thresholds, bf16 queries
     size_t gemm_ws_bytes = 0;
+    void *hyb_dev = nullptr;        // fused /retrieve call: device copy of the packed request + results
+    size_t hyb_dev_bytes = 0;
+    void *hyb_host = nullptr;       // ... and its pinned host mirror (one H2D + one D2H per request)
+    size_t hyb_host_bytes = 0;
 };
 
 struct cdr_store {

@@ -66,6 +66,37 @@ __global__ void __launch_bounds__(256) filter_bitmap_kernel(const FilterParams p
 
 }  // namespace
 
+// Enqueue K6 on `st`.  bm_dev: device copy of the call-slot bitmap (nullable); cnt_dev must be zero.
+int cdr_filter_launch(cdr_store *s, const uint32_t *bm_dev, int64_t n_call_slots, int has_from, int64_t date_from_us,
+                      int has_to, int64_t date_to_us, int has_tags, uint64_t tag_any, uint32_t *out_allow_dev,
+                      unsigned long long *cnt_dev, cudaStream_t st)
+{
+    FilterParams p;
+    p.call_slot = s->call_slot;
+    p.started_at = s->started_at;
+    p.tag_bits = s->tag_bits;
+    p.valid = s->valid;
+    p.call_bitmap = bm_dev;
+    p.n_call_slots = n_call_slots;
+    p.n_rows = s->n_rows;
+    p.has_from = has_from != 0;
+    p.has_to = has_to != 0;
+    p.has_tags = has_tags != 0;
+    p.date_from = date_from_us;
+    p.date_to = date_to_us;
+    p.tag_any = tag_any;
+    p.out_allow = out_allow_dev;
+    p.out_count = cnt_dev;
+    const int64_t words = (s->n_rows + 31) / 32;
+    int64_t blocks = (words + 7) / 8;
+    const int64_t cap = (int64_t)s->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    filter_bitmap_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+}
+
 extern "C" int32_t cdr_filter_build(cdr_store *s, const uint32_t *call_slot_bitmap_host,
                                     int64_t n_call_slots, int32_t has_date_from, int64_t date_from_us,
                                     int32_t has_date_to, int64_t date_to_us, int32_t has_tag_filter,
@@ -90,30 +121,9 @@ extern "C" int32_t cdr_filter_build(cdr_store *s, const uint32_t *call_slot_bitm
     unsigned long long *cnt = nullptr;
     CDR_CUDA(cudaMallocAsync(&cnt, sizeof(unsigned long long), st));
     CDR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
-
-    FilterParams p;
-    p.call_slot = s->call_slot;
-    p.started_at = s->started_at;
-    p.tag_bits = s->tag_bits;
-    p.valid = s->valid;
-    p.call_bitmap = bm_dev;
-    p.n_call_slots = n_call_slots;
-    p.n_rows = s->n_rows;
-    p.has_from = has_date_from != 0;
-    p.has_to = has_date_to != 0;
-    p.has_tags = has_tag_filter != 0;
-    p.date_from = date_from_us;
-    p.date_to = date_to_us;
-    p.tag_any = tag_any;
-    p.out_allow = out_allow_dev;
-    p.out_count = cnt;
-    const int64_t words = (s->n_rows + 31) / 32;
-    int64_t blocks = (words + 7) / 8;
-    const int64_t cap = (int64_t)s->sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    filter_bitmap_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
-    CDR_LAUNCH_CHECK();
+    int rc = cdr_filter_launch(s, bm_dev, n_call_slots, has_date_from, date_from_us, has_date_to, date_to_us,
+                               has_tag_filter, tag_any, out_allow_dev, cnt, st);
+    if (rc != CDR_OK) return rc;
     unsigned long long h = 0;
     CDR_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaFreeAsync(cnt, st));

@@ -207,6 +207,8 @@ void free_ws(ScanWorkspace &w)
     cudaFree(w.q_stage);
     cudaFree(w.out_stage);
     cudaFree(w.gemm_ws);
+    cudaFree(w.hyb_dev);
+    if (w.hyb_host) cudaFreeHost(w.hyb_host);
     w = ScanWorkspace();
 }
 

@@ -193,6 +193,29 @@ extern "C" int32_t cdr_tech_index_destroy(cdr_tech_index *ix)
     return CDR_OK;
 }
 
+// Enqueue the lane kernel on `st`; every pointer is a device pointer (d_bm nullable).
+int cdr_tech_lane_launch(cdr_tech_index *ix, const int32_t *d_tok, const int32_t *d_nt, int nq, int max_tokens,
+                         const uint32_t *d_bm, int64_t n_call_slots, int has_date_from, int64_t date_from_us,
+                         int has_date_to, int64_t date_to_us, int has_tag_filter, uint64_t tag_any, int limit,
+                         int64_t *d_oid, int32_t *d_on, cudaStream_t st)
+{
+    cdr_store *s = ix->store;
+    TechParams p;
+    p.offsets = ix->offsets; p.post_rows = ix->rows; p.rank = ix->rank;
+    p.ids = s->ids; p.call_slot = s->call_slot; p.started_at = s->started_at; p.tag_bits = s->tag_bits;
+    p.call_bitmap = d_bm; p.n_call_slots = n_call_slots; p.n_rows = s->n_rows; p.n_index_tokens = ix->n_tokens;
+    p.has_from = has_date_from != 0; p.has_to = has_date_to != 0; p.has_tags = has_tag_filter != 0;
+    p.date_from = date_from_us; p.date_to = date_to_us; p.tag_any = tag_any;
+    p.q_tokens = d_tok; p.q_ntok = d_nt; p.max_tokens = max_tokens; p.limit = limit;
+    p.out_ids = d_oid; p.out_n = d_on;
+    if (limit <= 64) tech_lane_kernel<2><<<nq, kTechWarps * 32, 0, st>>>(p);
+    else tech_lane_kernel<8><<<nq, kTechWarps * 32, 0, st>>>(p);
+    CDR_LAUNCH_CHECK();
+    return CDR_OK;
+}
+
+cdr_store *cdr_tech_index_store(cdr_tech_index *ix) { return ix->store; }
+
 extern "C" int32_t cdr_tech_lane_host(cdr_tech_index *ix, const int32_t *token_ids_host, const int32_t *n_tokens_host,
                                       int32_t nq, int32_t max_tokens, const uint32_t *call_slot_bitmap_host,
                                       int64_t n_call_slots, int32_t has_date_from, int64_t date_from_us,
@@ -230,17 +253,9 @@ extern "C" int32_t cdr_tech_lane_host(cdr_tech_index *ix, const int32_t *token_i
             CDR_CUDA(cudaMemcpyAsync(d_bm, call_slot_bitmap_host, (size_t)((n_call_slots + 31) / 32) * 4,
                                      cudaMemcpyHostToDevice, st));
     }
-    TechParams p;
-    p.offsets = ix->offsets; p.post_rows = ix->rows; p.rank = ix->rank;
-    p.ids = s->ids; p.call_slot = s->call_slot; p.started_at = s->started_at; p.tag_bits = s->tag_bits;
-    p.call_bitmap = d_bm; p.n_call_slots = n_call_slots; p.n_rows = s->n_rows; p.n_index_tokens = ix->n_tokens;
-    p.has_from = has_date_from != 0; p.has_to = has_date_to != 0; p.has_tags = has_tag_filter != 0;
-    p.date_from = date_from_us; p.date_to = date_to_us; p.tag_any = tag_any;
-    p.q_tokens = d_tok; p.q_ntok = d_nt; p.max_tokens = max_tokens; p.limit = limit;
-    p.out_ids = d_oid; p.out_n = d_on;
-    if (limit <= 64) tech_lane_kernel<2><<<nq, kTechWarps * 32, 0, st>>>(p);
-    else tech_lane_kernel<8><<<nq, kTechWarps * 32, 0, st>>>(p);
-    CDR_LAUNCH_CHECK();
+    int rc = cdr_tech_lane_launch(ix, d_tok, d_nt, nq, max_tokens, d_bm, n_call_slots, has_date_from, date_from_us,
+                                  has_date_to, date_to_us, has_tag_filter, tag_any, limit, d_oid, d_on, st);
+    if (rc != CDR_OK) { cudaFreeAsync(buf, st); return rc; }
     CDR_CUDA(cudaMemcpyAsync(out_ids_host, d_oid, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaMemcpyAsync(out_n_host, d_on, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaFreeAsync(buf, st));

@@ -150,6 +150,19 @@ class DeviceTechIndex:
         except Exception:
             pass
 
+    def encode_tokens(self, token_lists: Sequence[Sequence[str]]):
+        """Token strings -> (ids int32 [nq, MAX_TOKENS] padded with -1, counts int32 [nq]); tokens the
+        dictionary does not know have no postings and are dropped."""
+        nq = len(token_lists)
+        tok = np.full((nq, self.MAX_TOKENS), -1, dtype=np.int32)
+        ntok = np.zeros(nq, dtype=np.int32)
+        for i, toks in enumerate(token_lists):
+            ids = [self.token_ids.get(t, -1) for t in toks]
+            ids = [t for t in ids if t >= 0][: self.MAX_TOKENS]
+            tok[i, :len(ids)] = ids
+            ntok[i] = len(ids)
+        return tok, ntok
+
     def query_batch(self, token_lists: Sequence[Sequence[str]], limit: int, *,
                     call_slots: Optional[Sequence[int]] = None, date_from=None, date_to=None,
                     tag_mask: Optional[int] = None):
@@ -159,22 +172,8 @@ class DeviceTechIndex:
         from .store import to_micros
         _ffi = self._ffi
         nq = len(token_lists)
-        tok = np.full((nq, self.MAX_TOKENS), -1, dtype=np.int32)
-        ntok = np.zeros(nq, dtype=np.int32)
-        for i, toks in enumerate(token_lists):
-            ids = [self.token_ids.get(t, -1) for t in toks]
-            ids = [t for t in ids if t >= 0][: self.MAX_TOKENS]
-            tok[i, :len(ids)] = ids
-            ntok[i] = len(ids)
-        bm, n_slots = None, 0
-        if call_slots is not None:
-            n_slots = max(len(self.store.call_ids_by_slot), (max(call_slots) + 1) if len(call_slots) else 0, 1)
-            if self.store.synthetic is not None:
-                n_slots = max(n_slots, (self.store.synthetic["first_row"] + self.store.rows) // self.store.synthetic["rows_per_call"] + 1)
-            bm = np.zeros((n_slots + 31) // 32, dtype=np.uint32)
-            for s_ in call_slots:
-                if 0 <= s_ < n_slots:
-                    bm[s_ >> 5] |= np.uint32(1 << (s_ & 31))
+        tok, ntok = self.encode_tokens(token_lists)
+        bm, n_slots = self.store.slot_bitmap(call_slots)
         out_ids = np.empty((nq, limit), dtype=np.int64)
         out_n = np.empty(nq, dtype=np.int32)
         with torch.cuda.device(self.store.device):

@@ -364,6 +364,88 @@ def rrf_merge_batch(lane_ids: np.ndarray, lane_offsets: np.ndarray, nq: int, n_l
     return out_ids, out_sc, out_mask, out_n
 
 
+# --------------------------------------------------------------------------- fused per-table request
+_LANE_NAMES = ("bm25", "tech_tokens", "dense")
+
+
+def _embedding_f32(values: Sequence[float]) -> np.ndarray:
+    """What `CAST(:q AS vector(1024))` yields for `_vector_literal(values)`, without the text round
+    trip when it is provably the identity: a float32-representable value printed with 10 significant
+    digits (`.10g`, 9 suffice for float32) parses back to itself.  Anything else (fp64 decimals from a
+    JSON body, NaN) takes the literal path."""
+    a64 = np.asarray(values, dtype=np.float64).reshape(-1)
+    a32 = a64.astype(np.float32)
+    if np.array_equal(a32.astype(np.float64), a64):
+        return a32
+    return _query_vector(_vector_literal(values))
+
+
+def _rows_from_ids(store: DenseStore, ids: np.ndarray) -> List[Dict[str, Any]]:
+    cols = store.host_columns()
+    out: List[Dict[str, Any]] = []
+    for i, p in zip(ids.tolist(), np.searchsorted(cols["ids"], ids).tolist()):
+        slot = int(cols["call_slot"][p])
+        call_id = store.call_ids_by_slot[slot] if slot < len(store.call_ids_by_slot) else slot
+        row = {store.key_field: i, "call_id": call_id}
+        row.update(store.payload.get(i, {}))
+        out.append(row)
+    return out
+
+
+def _fused_path_ok(engine: DenseEngine, table: str, dense: bool) -> bool:
+    """The fused C call serves a table when its dense lane is the exact fp32 scan and its tech lane
+    (if any) is device resident; other configurations take the step-by-step path."""
+    store = engine.stores[table]
+    if table in engine.tech_indexes and table not in engine.device_tech_indexes:
+        return False
+    if dense and not store.has_fp32:
+        return False
+    if dense and store.has_bf16 and settings.cadence_gpu_ann_min_batch <= 1:
+        return False        # single queries are routed to the batched bf16 lane by configuration
+    return True
+
+
+def _hybrid_table(conn: DenseConnection, table: str, q32: Optional[np.ndarray], tech_tokens: Sequence[str],
+                  filters: Optional[RetrieveFilters], call_ids: Optional[Sequence[Any]],
+                  bm25_rows: Sequence[Mapping[str, Any]], dense_limit: int,
+                  tech_limit: int = DEFAULT_TECH_TOPK, rrf_k: int = DEFAULT_RRF_K) -> Dict[str, Any]:
+    """All lanes of one table + their fusion through ONE `cdr_hybrid_retrieve_host` call.  Returns
+    {"tech": rows, "dense": rows, "count": COUNT(*), "ranked": [(row, lane-name set, score)]} with the
+    same rows / order the step-by-step functions produce."""
+    store = conn.store(table)
+    key = store.key_field
+    if q32 is not None:
+        want = max(1, int(settings.embeddings_dim))
+        if q32.shape[0] != want or q32.shape[0] != store.dim:
+            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[0]}")
+    spec = _filter_spec(store, filters, call_ids)
+    dev_index = conn.engine.device_tech_indexes.get(table) if tech_tokens else None
+    tok = nt = None
+    if dev_index is not None:
+        tok, nt = dev_index.encode_tokens([list(tech_tokens)])
+    bm25_ids = np.fromiter((int(r[key]) for r in bm25_rows), dtype=np.int64, count=len(bm25_rows))
+    res = store.hybrid_retrieve(None if q32 is None else q32[None, :], dense_limit, tech_index=dev_index,
+                                token_ids=tok, n_tokens=nt, tech_limit=tech_limit, bm25_ids=bm25_ids,
+                                bm25_offsets=np.array([0, bm25_ids.size], dtype=np.int32), rrf_k=rrf_k,
+                                filter_spec=spec)
+    tech_rows = _rows_from_ids(store, res["tech_ids"][0, :int(res["tech_n"][0])])
+    dense_rows: List[Dict[str, Any]] = []
+    if q32 is not None:
+        m = int(res["dense_n"][0])
+        dense_rows = _rows_from_hits(store, res["dense_ids"][0, :m], res["dense_scores"][0, :m])
+    items: Dict[int, Mapping[str, Any]] = {}
+    for lane in (bm25_rows, tech_rows, dense_rows):
+        for row in lane:
+            items.setdefault(int(row[key]), row)
+    ranked = []
+    n_lanes = 3 if q32 is not None else 2
+    for i in range(int(res["fused_n"][0])):
+        mask = int(res["fused_mask"][0, i])
+        hit = {_LANE_NAMES[l] for l in range(n_lanes) if (mask >> l) & 1}
+        ranked.append((items[int(res["fused_ids"][0, i])], hit, float(res["fused_scores"][0, i])))
+    return {"tech": tech_rows, "dense": dense_rows, "count": res["count"] if q32 is not None else 0, "ranked": ranked}
+
+
 # --------------------------------------------------------------------------- ids_only retrieve
 def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilters] = None,
                  bm25_chunks: Sequence[Mapping[str, Any]] = (),
@@ -378,12 +460,12 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
     dense_enabled = embeddings_enabled()
     dense_error: Optional[str] = None
     dense_model_id: Optional[str] = None
-    query_embedding: Optional[str] = None
+    query_embedding = None       # float32 vector == CAST(_vector_literal(v) AS vector(D)) (see _embedding_f32)
     if dense_enabled:
         try:
             embedded = embed_texts([query])
             dense_model_id = embedded.model
-            query_embedding = _vector_literal(embedded.vectors[0])
+            query_embedding = _embedding_f32(embedded.vectors[0])
         except EmbeddingClientError as exc:
             dense_enabled = False
             dense_error = str(exc)
@@ -394,6 +476,42 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
     dense_artifacts: List[Dict[str, Any]] = []
     modes: Dict[str, Optional[str]] = {"chunks": None, "artifact_chunks": None}
     candidates = {"chunks": 0, "artifact_chunks": 0}
+    tables = [t for t in ("chunks", "artifact_chunks") if t in engine.stores]
+    fused = bool(tables) and all(_fused_path_ok(engine, t, dense_enabled) for t in tables)
+    if fused:
+        # one C call per table: filter + lanes + RRF on the device, one sync (csrc/hybrid.cu)
+        limits = {"chunks": DEFAULT_DENSE_CHUNK_TOPK, "artifact_chunks": DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK}
+        bm25 = {"chunks": list(bm25_chunks), "artifact_chunks": list(bm25_artifacts)}
+        with engine.connect() as conn:
+            call_ids = _resolve_call_ids(conn, filters)
+            per_table: Dict[str, Dict[str, Any]] = {}
+            try:
+                for t in tables:
+                    per_table[t] = _hybrid_table(conn, t, query_embedding if dense_enabled else None, tech_tokens,
+                                                 filters, call_ids, bm25[t], limits[t])
+            except DenseEngineError as exc:       # fail open to lexical-only, like EmbeddingClientError
+                if not dense_enabled:
+                    raise
+                dense_enabled = False
+                dense_error = str(exc)
+                for t in tables:
+                    per_table[t] = _hybrid_table(conn, t, None, tech_tokens, filters, call_ids, bm25[t], limits[t])
+        empty = {"tech": [], "dense": [], "count": 0, "ranked": []}
+        ch, ar = per_table.get("chunks", empty), per_table.get("artifact_chunks", empty)
+        tech_chunks, tech_artifacts = ch["tech"], ar["tech"]
+        dense_chunks, dense_artifacts = ch["dense"], ar["dense"]
+        if dense_enabled:
+            for t in tables:
+                candidates[t] = per_table[t]["count"]
+                modes[t] = _choose_dense_mode(candidates[t], filters, call_ids)
+        chunk_ranked, artifact_ranked = ch["ranked"], ar["ranked"]
+        if "chunks" not in per_table:
+            chunk_ranked = _rrf_merge({"bm25": list(bm25_chunks), "tech_tokens": []}, "chunk_id")
+        if "artifact_chunks" not in per_table:
+            artifact_ranked = _rrf_merge({"bm25": list(bm25_artifacts), "tech_tokens": []}, "artifact_chunk_id")
+        return _ids_response(chunk_ranked, artifact_ranked, bm25_chunks, bm25_artifacts, tech_chunks, tech_artifacts,
+                             dense_chunks, dense_artifacts, dense_enabled, dense_model_id, dense_error, modes,
+                             candidates, debug)
     with engine.connect() as conn:
         call_ids = _resolve_call_ids(conn, filters)
         if "chunks" in engine.stores:
@@ -423,7 +541,15 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
         artifact_lanes["dense"] = dense_artifacts
     chunk_ranked = _rrf_merge(chunk_lanes, "chunk_id")
     artifact_ranked = _rrf_merge(artifact_lanes, "artifact_chunk_id")
+    return _ids_response(chunk_ranked, artifact_ranked, bm25_chunks, bm25_artifacts, tech_chunks, tech_artifacts,
+                         dense_chunks, dense_artifacts, dense_enabled, dense_model_id, dense_error, modes,
+                         candidates, debug)
 
+
+def _ids_response(chunk_ranked, artifact_ranked, bm25_chunks, bm25_artifacts, tech_chunks, tech_artifacts,
+                  dense_chunks, dense_artifacts, dense_enabled, dense_model_id, dense_error, modes, candidates,
+                  debug: bool) -> Dict[str, Any]:
+    """ids_only combine (app/retrieve.py:552-573) + the debug payload."""
     combined: List[Tuple[str, int, float]] = []
     for row, _lanes, score in artifact_ranked:
         combined.append(("artifact_chunk", row["artifact_chunk_id"], score))

@@ -79,6 +79,7 @@ class DenseStore:
         self.payload: Dict[int, Dict[str, Any]] = {}
         self.synthetic = None   # (seed, first_row) when filled by the on-device generator
         self._host_cols: Optional[Dict[str, np.ndarray]] = None
+        self._rows: Optional[int] = None
 
     # ------------------------------------------------------------------ lifecycle
     @property
@@ -308,6 +309,10 @@ class DenseStore:
 
     @property
     def rows(self) -> int:
+        if self.finalized:                      # the store is immutable after finalize
+            if self._rows is None:
+                self._rows = self.info()["rows"]
+            return self._rows
         return self.info()["rows"]
 
     @property
@@ -343,6 +348,36 @@ class DenseStore:
         return self._host_cols
 
     # ------------------------------------------------------------------ filters (K6)
+    def slot_bitmap(self, call_slots: Optional[Sequence[int]]):
+        """Host bitmap over call slots for ``call_id = ANY(:call_ids)``: (uint32 words or None, n_slots).
+        None = unscoped; an all-zero bitmap = ``call_ids == []``."""
+        if call_slots is None:
+            return None, 0
+        n_slots = max(len(self.call_ids_by_slot), (max(call_slots) + 1) if len(call_slots) else 0, 1)
+        if self.synthetic is not None:
+            n_slots = max(n_slots, (self.synthetic["first_row"] + self.rows) // self.synthetic["rows_per_call"] + 1)
+        bm = np.zeros((n_slots + 31) // 32, dtype=np.uint32)
+        for s in call_slots:
+            if 0 <= s < n_slots:
+                bm[s >> 5] |= np.uint32(1 << (s & 31))
+        return bm, n_slots
+
+    def filter_spec_struct(self, *, call_slots=None, date_from=None, date_to=None, tag_mask=None):
+        """(cdr_filter_spec, keep-alive) for the fused C call; None when the filter is empty."""
+        if call_slots is None and date_from is None and date_to is None and tag_mask is None:
+            return None, None
+        bm, n_slots = self.slot_bitmap(call_slots)
+        spec = _ffi.FilterSpec()
+        spec.call_slot_bitmap_host = _ffi.ptr(bm)
+        spec.n_call_slots = n_slots
+        spec.has_date_from = 0 if date_from is None else 1
+        spec.date_from_us = 0 if date_from is None else to_micros(date_from)
+        spec.has_date_to = 0 if date_to is None else 1
+        spec.date_to_us = 0 if date_to is None else to_micros(date_to)
+        spec.has_tag_filter = 0 if tag_mask is None else 1
+        spec.tag_any = int(tag_mask or 0)
+        return spec, bm
+
     def filter_bitmap(self, *, call_slots: Optional[Sequence[int]] = None, date_from=None, date_to=None,
                       tag_mask: Optional[int] = None):
         """Build the allow-bitmap for a WHERE clause and count its rows.
@@ -353,16 +388,7 @@ class DenseStore:
         torch = _torch()
         rows = self.rows
         words = (rows + 31) // 32
-        n_slots = 0
-        bm = None
-        if call_slots is not None:
-            n_slots = max(len(self.call_ids_by_slot), (max(call_slots) + 1) if len(call_slots) else 0, 1)
-            if self.synthetic is not None:
-                n_slots = max(n_slots, (self.synthetic["first_row"] + rows) // self.synthetic["rows_per_call"] + 1)
-            bm = np.zeros((n_slots + 31) // 32, dtype=np.uint32)
-            for s in call_slots:
-                if 0 <= s < n_slots:
-                    bm[s >> 5] |= np.uint32(1 << (s & 31))
+        bm, n_slots = self.slot_bitmap(call_slots)
         count = ctypes.c_int64(0)
         with torch.cuda.device(self.device):
             allow = torch.empty(max(words, 1), dtype=torch.int32, device=f"cuda:{self.device}")
@@ -416,3 +442,58 @@ class DenseStore:
     def search_batch(self, queries, k: int, allow=None):
         """mode="ann" served by the batched bf16 tensor-core lane (K2) + exact re-score."""
         return self._search("cdr_search_batch_bf16", queries, k, allow)
+
+    # ------------------------------------------------------------------ fused hybrid /retrieve
+    def hybrid_retrieve(self, queries, dense_k: int, *, tech_index=None, token_ids=None, n_tokens=None,
+                        tech_limit: int = 50, bm25_ids=None, bm25_offsets=None, rrf_k: int = 60,
+                        filter_spec: Optional[Dict[str, Any]] = None, max_out: Optional[int] = None):
+        """One ``cdr_hybrid_retrieve_host`` call (include/cadence_dense.h): filter -> dense exact lane ->
+        tech_tokens lane -> RRF for nq queries sharing one filter; one H2D, one D2H, one sync.
+
+        queries: [nq, dim] float32 numpy or None (dense lane disabled).  token_ids [nq, T] int32 /
+        n_tokens [nq] int32 with ``tech_index`` a DeviceTechIndex.  bm25_ids / bm25_offsets: the opaque
+        BM25 lane (ranked ids back to back, offsets [nq+1]).  Returns a dict of numpy arrays."""
+        torch = _torch()
+        dense = queries is not None
+        if dense:
+            q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+            if q.ndim == 1:
+                q = q[None, :]
+            if q.shape[1] != self.dim:
+                raise DenseEngineError(f"query dim {q.shape[1]} != store dim {self.dim}")
+            nq = int(q.shape[0])
+        else:
+            q = None
+            nq = int(len(n_tokens)) if n_tokens is not None else (len(bm25_offsets) - 1 if bm25_offsets is not None else 0)
+        tok = nt = None
+        max_tokens = 1
+        if tech_index is not None and token_ids is not None:
+            tok = np.ascontiguousarray(token_ids, dtype=np.int32)
+            nt = np.ascontiguousarray(n_tokens, dtype=np.int32)
+            max_tokens = int(tok.shape[1])
+        b_ids = b_off = None
+        bm25_max = 0
+        if bm25_offsets is not None:
+            b_off = np.ascontiguousarray(bm25_offsets, dtype=np.int32)
+            b_ids = np.ascontiguousarray(bm25_ids if bm25_ids is not None else np.empty(0), dtype=np.int64)
+            bm25_max = int(np.diff(b_off).max()) if nq else 0
+        kd = int(dense_k) if dense else 0
+        if max_out is None:
+            max_out = max(1, bm25_max + int(tech_limit) + kd)
+        spec, keep = self.filter_spec_struct(**(filter_spec or {}))
+        out = {"dense_ids": np.empty((nq, max(kd, 1)), dtype=np.int64), "dense_scores": np.empty((nq, max(kd, 1)), dtype=np.float64),
+               "dense_n": np.zeros(nq, dtype=np.int32), "tech_ids": np.empty((nq, tech_limit), dtype=np.int64),
+               "tech_n": np.zeros(nq, dtype=np.int32), "fused_ids": np.empty((nq, max_out), dtype=np.int64),
+               "fused_scores": np.empty((nq, max_out), dtype=np.float64), "fused_mask": np.empty((nq, max_out), dtype=np.uint32),
+               "fused_n": np.zeros(nq, dtype=np.int32)}
+        count = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            _ffi.check(_ffi.lib().cdr_hybrid_retrieve_host(
+                self.handle, None if tech_index is None else tech_index._h, None if spec is None else ctypes.addressof(spec),
+                _ffi.ptr(q), nq, kd, _ffi.ptr(tok), _ffi.ptr(nt), max_tokens, int(tech_limit), _ffi.ptr(b_ids), _ffi.ptr(b_off),
+                int(rrf_k), int(max_out), ctypes.addressof(count), _ffi.ptr(out["dense_ids"]), _ffi.ptr(out["dense_scores"]),
+                _ffi.ptr(out["dense_n"]), _ffi.ptr(out["tech_ids"]), _ffi.ptr(out["tech_n"]), _ffi.ptr(out["fused_ids"]),
+                _ffi.ptr(out["fused_scores"]), _ffi.ptr(out["fused_mask"]), _ffi.ptr(out["fused_n"]), self._stream()),
+                "cdr_hybrid_retrieve_host")
+        out["count"] = int(count.value)
+        return out

@@ -201,6 +201,44 @@ int32_t cdr_tech_lane_host(cdr_tech_index *ix, const int32_t *token_ids_host,
                            int64_t date_to_us, int32_t has_tag_filter, uint64_t tag_any,
                            int32_t limit, int64_t *out_ids_host, int32_t *out_n_host, void *stream);
 
+/* ---- fused hybrid /retrieve for one table ---------------------------------------------------
+ * One call = what retrieve_evidence runs per request and table between `with engine.connect()` and
+ * the RRF (app/retrieve.py:445-550):
+ *   _fetch_chunks_tech (:183-209)  ->  _estimate_dense_candidates (:303-323)  ->
+ *   _fetch_chunks_dense mode "exact" (:326-354)  ->  _rrf_merge({bm25, tech_tokens, dense}) (:245-260)
+ * for nq queries that share one filter, with ONE host->device copy of the packed request, ONE
+ * device->host copy of the packed response and ONE stream synchronisation.  The BM25 lane
+ * (pg_search; out of scope) is an input: bm25_ids_host holds each query's ranked ids back to back,
+ * bm25_offsets_host[nq+1] delimits them (both NULL = empty lane).
+ *   filter        NULL or all-empty = unscoped.  Applied to both lanes; only the dense lane also
+ *                 requires `embedding IS NOT NULL` (as in the reference SQL).
+ *   q_host        [nq, dim] fp32, or NULL = dense lane disabled (EmbeddingClientError path,
+ *                 app/retrieve.py:426-432): the fusion then has the two lexical lanes only.
+ *   tech_index    NULL = empty tech_tokens lane; token ids as for cdr_tech_lane_host.
+ * Lane order in the fusion and in the lane-hit masks: bit 0 bm25, bit 1 tech_tokens, bit 2 dense.
+ * Outputs (host): out_count = COUNT(*) of the dense lane's WHERE clause (n_valid when unscoped);
+ * dense ids/scores [nq, dense_k] + n; tech ids [nq, tech_limit] + n; fused ids/scores/masks
+ * [nq, max_out] + n.  Unused slots: id -1. */
+typedef struct cdr_filter_spec {
+    const uint32_t *call_slot_bitmap_host;   /* NULL = no call filter; all-zero = call_ids == [] */
+    int64_t n_call_slots;
+    int32_t has_date_from;
+    int32_t has_date_to;
+    int64_t date_from_us;
+    int64_t date_to_us;
+    int32_t has_tag_filter;
+    int32_t reserved;
+    uint64_t tag_any;
+} cdr_filter_spec;
+
+int32_t cdr_hybrid_retrieve_host(
+    cdr_store *s, cdr_tech_index *tech_index, const cdr_filter_spec *filter, const float *q_host, int32_t nq,
+    int32_t dense_k, const int32_t *token_ids_host, const int32_t *n_tokens_host, int32_t max_tokens,
+    int32_t tech_limit, const int64_t *bm25_ids_host, const int32_t *bm25_offsets_host, int32_t rrf_k,
+    int32_t max_out, int64_t *out_count_host, int64_t *out_dense_ids_host, double *out_dense_scores_host,
+    int32_t *out_dense_n_host, int64_t *out_tech_ids_host, int32_t *out_tech_n_host, int64_t *out_fused_ids_host,
+    double *out_fused_scores_host, uint32_t *out_fused_mask_host, int32_t *out_fused_n_host, void *stream);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* Number of this library's kernels launched by the calling process so far (bench.py's
  * gpu_launches claim). */

@@ -493,6 +493,74 @@ def test_hybrid_retrieve_ids_bit_exact(hybrid_engine, monkeypatch):
     assert retrieve.retrieve_ids(eng, "   ")["retrieved_ids"] == []
 
 
+def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
+    """cdr_hybrid_retrieve_host (one C call per table: K6 + K1 + tech lane + K5, one sync) returns exactly
+    what the step-by-step facade functions return: lanes, COUNT(*), planner modes, fused ranks, ids."""
+    eng, meta = hybrid_engine
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    emb = embeddings.SyntheticEmbedder(seed=SYNTH_QUERY_SEED, dim=1024)
+    embeddings.set_embedder(emb)
+    t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+    bm25 = [{"chunk_id": 2 * i} for i in (5, 900, 77, 12000)]
+    bm25a = [{"artifact_chunk_id": 2 * i} for i in (3, 1500)]
+    cases = [("why did TOK-1 fail with TOK-3 on 10.0.0.1", None, bm25, bm25a),
+             ("TOK-0 status", RetrieveFilters(call_ids=[_uuid(c) for c in range(10)]), [], []),
+             ("no tokens here", RetrieveFilters(date_from=t0 + timedelta(hours=50)), bm25, []),
+             ("TOK-2 and TOK-5", RetrieveFilters(call_tags=["t2"]), [], bm25a),
+             ("TOK-7 TOK-9 TOK-11", RetrieveFilters(external_id="ext-7"), bm25, bm25a),
+             ("TOK-4", RetrieveFilters(external_id="missing"), bm25, []),          # call_ids == [] -> no rows
+             ("TOK-4 UNKNOWN-99999", RetrieveFilters(call_tags=["nope"]), [], []),
+             ("TOK-1", RetrieveFilters(date_from=t0 + timedelta(hours=5), date_to=t0 + timedelta(hours=6), call_tags=["t0", "u1"]), bm25, bm25a)]
+    try:
+        for query, filters, b_c, b_a in cases:
+            launches0 = _ffi.kernel_launch_count()
+            fused = retrieve.retrieve_ids(eng, query, filters, bm25_chunks=b_c, bm25_artifacts=b_a, debug=True)
+            assert _ffi.kernel_launch_count() > launches0
+            with monkeypatch.context() as mp:
+                mp.setattr(retrieve, "_fused_path_ok", lambda *a, **k: False)
+                step = retrieve.retrieve_ids(eng, query, filters, bm25_chunks=b_c, bm25_artifacts=b_a, debug=True)
+            assert fused == step, (query, filters)
+        # dense lane disabled -> the fused call fuses the two lexical lanes only
+        monkeypatch.setattr(settings, "embeddings_base_url", "")
+        fused = retrieve.retrieve_ids(eng, "TOK-1 TOK-3", cases[1][1], bm25_chunks=bm25, debug=True)
+        with monkeypatch.context() as mp:
+            mp.setattr(retrieve, "_fused_path_ok", lambda *a, **k: False)
+            step = retrieve.retrieve_ids(eng, "TOK-1 TOK-3", cases[1][1], bm25_chunks=bm25, debug=True)
+        assert fused == step and fused["debug"]["dense"]["enabled"] is False
+    finally:
+        embeddings.set_embedder(None)
+
+    # batched form: nq queries in one call == nq single calls
+    store = eng.stores["chunks"]; dev_index = eng.device_tech_indexes["chunks"]
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 100, 5)
+    token_lists = [["TOK-1"], ["TOK-2", "TOK-3"], [], ["TOK-0", "NOPE"], ["TOK-199"]]
+    tok, nt = dev_index.encode_tokens(token_lists)
+    b_ids = np.array([10, 24000, 154, 8, 8, 10], dtype=np.int64)
+    b_off = np.array([0, 3, 3, 4, 6, 6], dtype=np.int32)
+    spec = dict(call_slots=list(range(0, 60)), date_from=None, date_to=None, tag_mask=None)
+    both = store.hybrid_retrieve(qs, 50, tech_index=dev_index, token_ids=tok, n_tokens=nt, tech_limit=50,
+                                 bm25_ids=b_ids, bm25_offsets=b_off, filter_spec=spec)
+    for i in range(5):
+        one = store.hybrid_retrieve(qs[i], 50, tech_index=dev_index, token_ids=tok[i:i + 1], n_tokens=nt[i:i + 1],
+                                    tech_limit=50, bm25_ids=b_ids[b_off[i]:b_off[i + 1]],
+                                    bm25_offsets=np.array([0, b_off[i + 1] - b_off[i]], dtype=np.int32), filter_spec=spec)
+        assert one["count"] == both["count"]
+        for name in ("dense_ids", "dense_scores", "tech_ids", "fused_ids", "fused_scores", "fused_mask"):
+            n = {"dense": "dense_n", "tech_": "tech_n", "fused": "fused_n"}[name[:5]]
+            m = int(one[n][0])
+            assert int(both[n][i]) == m
+            assert np.array_equal(one[name][0, :m], both[name][i, :m]), (i, name)
+        # and the fused ranks equal the reference restatement fed with the same lanes
+        lanes = {"bm25": [{"chunk_id": int(v)} for v in b_ids[b_off[i]:b_off[i + 1]]],
+                 "tech_tokens": [{"chunk_id": int(v)} for v in one["tech_ids"][0, :int(one["tech_n"][0])]],
+                 "dense": [{"chunk_id": int(v)} for v in one["dense_ids"][0, :int(one["dense_n"][0])]]}
+        want = ports.rrf_merge(lanes, "chunk_id")
+        m = int(one["fused_n"][0])
+        assert [(r["chunk_id"], s_) for r, _h, s_ in want] == list(zip(one["fused_ids"][0, :m].tolist(), one["fused_scores"][0, :m].tolist()))
+    with pytest.raises(DenseEngineError):
+        store.hybrid_retrieve(qs[:, :8], 50)
+
+
 # =================================================================== full size (BASELINE C2): 1M x 1024
 @pytest.fixture(scope="module")
 def corpus_1m():
