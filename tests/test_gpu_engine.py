@@ -520,15 +520,16 @@ def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
                 mp.setattr(retrieve, "_fused_path_ok", lambda *a, **k: False)
                 step = retrieve.retrieve_ids(eng, query, filters, bm25_chunks=b_c, bm25_artifacts=b_a, debug=True)
             assert fused == step, (query, filters)
-        # dense lane disabled -> the fused call fuses the two lexical lanes only
-        monkeypatch.setattr(settings, "embeddings_base_url", "")
-        fused = retrieve.retrieve_ids(eng, "TOK-1 TOK-3", cases[1][1], bm25_chunks=bm25, debug=True)
-        with monkeypatch.context() as mp:
-            mp.setattr(retrieve, "_fused_path_ok", lambda *a, **k: False)
-            step = retrieve.retrieve_ids(eng, "TOK-1 TOK-3", cases[1][1], bm25_chunks=bm25, debug=True)
-        assert fused == step and fused["debug"]["dense"]["enabled"] is False
     finally:
         embeddings.set_embedder(None)
+    # dense lane disabled -> the fused call fuses the two lexical lanes only
+    monkeypatch.setattr(settings, "embeddings_base_url", "")
+    fused = retrieve.retrieve_ids(eng, "TOK-1 TOK-3", cases[1][1], bm25_chunks=bm25, debug=True)
+    with monkeypatch.context() as mp:
+        mp.setattr(retrieve, "_fused_path_ok", lambda *a, **k: False)
+        step = retrieve.retrieve_ids(eng, "TOK-1 TOK-3", cases[1][1], bm25_chunks=bm25, debug=True)
+    assert fused == step
+    assert fused["debug"]["dense"]["enabled"] is False and len(fused["retrieved_ids"]) > 4
 
     # batched form: nq queries in one call == nq single calls
     store = eng.stores["chunks"]; dev_index = eng.device_tech_indexes["chunks"]
