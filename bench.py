@@ -310,7 +310,8 @@ def run_batch_bf16(args):
                                        f"tcgen05 GEMM with fused threshold top-k epilogue + exact re-score, top-k={TOPK}",
                            "rows": rows, "rows_per_gpu": count, "dim": DIM, "k": TOPK, "queries_per_step": nq,
                            "resident": "bf16 only" if args.bf16_only else "fp32 + bf16",
-                           "l2": "inputs larger than L2", "recall_at_50_vs_exact_fp32_lane": recall},
+                           "l2": "inputs larger than L2", "recall_at_50_vs_exact_fp32_lane": recall,
+                           "exchange": searcher.transport},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": None if tt is None else {"value": args.steps * nq / float(tt[0]), "unit": UNIT,
                                                 "h2d_bytes_per_step": nq * DIM * 4,
@@ -326,6 +327,9 @@ def run_batch_bf16(args):
                              "gemm_ms_by_step": [round(float(per_launch[i * segs:(i + 1) * segs].sum()), 3)
                                                  for i in range(args.steps)]}}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    searcher.close()
     store.close()
     if world > 1:
         dist.barrier()
@@ -599,6 +603,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, world), sharding=f"rows/{world}" if world > 1 else "none",
+                           exchange=searcher.transport,
                            l2="inputs larger than L2 (shard bytes >> 126 MB), distinct queries every step",
                            single_query_latency_ms_p50=lat[len(lat) // 2], single_query_latency_ms_min=lat[0]),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
@@ -613,6 +618,9 @@ def main():
             one = cpu_baseline(args.rows, min(args.cpu_sample_rows, 50_000), 4, 1, target_seconds=4.0)
             line["cpu_baseline"]["single_thread_value"] = one["value"]
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+    searcher.close()
     store.close()
     if world > 1:
         dist.barrier()

@@ -27,6 +27,8 @@ CDR_STORE_FP32 = 1
 CDR_STORE_BF16 = 2
 CDR_MAX_K = 248
 CDR_RRF_MAX_ITEMS = 1024
+CDR_PEER_MAX_RANKS = 16
+CDR_PEER_HANDLE_BYTES = 64
 
 _CODE_NAMES = {
     CDR_ERR_INVALID: "CDR_ERR_INVALID", CDR_ERR_CUDA: "CDR_ERR_CUDA", CDR_ERR_OOM: "CDR_ERR_OOM",
@@ -81,6 +83,10 @@ SIGNATURES = {
     "cdr_search_batch_bf16": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_search_batch_bf16_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_topk_merge": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cdr_peer_group_create": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _vp]),
+    "cdr_peer_group_connect": (_i32, [_vp, _vp]),
+    "cdr_peer_group_destroy": (_i32, [_vp]),
+    "cdr_peer_exchange_merge": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cdr_rrf_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_rrf_merge_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_tech_index_create": (_i32, [ctypes.POINTER(_vp), _vp, _vp, _i32, _vp, _vp]),

@@ -9,7 +9,7 @@ OBJ="$HERE/../../build/obj"
 mkdir -p "$OBJ"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++"
 pids=""
-for f in abi store filter exact_scan rrf topk_merge gemm_topk tech_lane hybrid; do
+for f in abi store filter exact_scan rrf topk_merge gemm_topk tech_lane hybrid peer; do
     extra=""
     # K5 must not contract fp64 add/div chains (bit-exact RRF)
     [ "$f" = "rrf" ] && extra="-fmad=false"
@@ -21,5 +21,5 @@ for f in abi store filter exact_scan rrf topk_merge gemm_topk tech_lane hybrid; 
 done
 for p in $pids; do wait $p; done
 $NVCC -shared -o "$OUT" "$OBJ"/abi.o "$OBJ"/store.o "$OBJ"/filter.o "$OBJ"/exact_scan.o "$OBJ"/rrf.o \
-    "$OBJ"/topk_merge.o "$OBJ"/gemm_topk.o "$OBJ"/tech_lane.o "$OBJ"/hybrid.o -ccbin /usr/bin/g++
+    "$OBJ"/topk_merge.o "$OBJ"/gemm_topk.o "$OBJ"/tech_lane.o "$OBJ"/hybrid.o "$OBJ"/peer.o -ccbin /usr/bin/g++
 echo "built $OUT"

@@ -46,6 +46,8 @@ extern std::atomic<int64_t> g_cdr_launches;
 struct ScanWorkspace {
     uint64_t *cta_keys = nullptr;   // [nq_cap, grid, KC] packed candidate keys from K1
     size_t cta_keys_bytes = 0;
+    unsigned int *tile_ctr = nullptr;   // [nq_cap] K1 work-stealing counters (zero between launches)
+    size_t tile_ctr_bytes = 0;
     float *q_stage = nullptr;       // [nq_cap, dim] fp32 staging for the *_host entry points
     size_t q_stage_bytes = 0;
     void *out_stage = nullptr;      // result staging for the *_host entry points

@@ -22,6 +22,8 @@
 // Algorithmic bytes per query: n_rows * dim * 4.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kConsumerWarps = 8;
@@ -37,6 +39,7 @@ struct ScanParams {
     int64_t n_rows;
     int64_t n_tiles;
     int n_stages;
+    unsigned int *tile_ctr;   // [nq] zero on entry (reset by the finalize kernel); nullptr = static tile assignment
 };
 
 // Dynamic shared memory carve-up (computed identically on host and device).
@@ -48,7 +51,7 @@ struct ScanSmem {
     static constexpr size_t kTileBytes = (size_t)TR * DIM * 4;
     static constexpr size_t kMetaBytes = (size_t)TR * 4;   // inverse norms (multiple of 16)
     static constexpr size_t kListBytes = (size_t)kConsumerWarps * KC * 8;
-    static constexpr size_t kBarBytes = 2 * kMaxStages * 8;
+    static constexpr size_t kBarBytes = 3 * kMaxStages * 8;   // full + empty barriers + the tile index of each stage
     static constexpr size_t bytes(int stages)
     {
         return (size_t)stages * (kTileBytes + kMetaBytes) + kListBytes + kBarBytes + 128;
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     uint64_t *lists = reinterpret_cast<uint64_t *>(metas + (size_t)S * L::kMetaBytes);
     uint64_t *full_bar = lists + kConsumerWarps * KC;
     uint64_t *empty_bar = full_bar + kMaxStages;
+    long long *stage_tile = reinterpret_cast<long long *>(empty_bar + kMaxStages);   // tile held by a stage, -1 = end
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.y;
@@ -88,17 +92,31 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     }
     __syncthreads();
 
-    // number of tiles this CTA owns: t = blockIdx.x + i*G
-    const int64_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + G - 1) / G : 0;
+    // Tile assignment.  The first S tiles of a CTA are static (blockIdx.x + i*G: no latency at start-up);
+    // after that the producer draws tiles from a per-query counter (work stealing), so SMs that sit
+    // closer to the memory partitions simply scan more tiles and all CTAs finish together -- with a
+    // static split the slowest SM sets the latency of a single-query scan.  tile_ctr == nullptr keeps
+    // the static split (t = blockIdx.x + i*G).  A stage whose tile index is -1 ends the stream.
+    const bool dynamic = p.tile_ctr != nullptr;
 
     if (warp == kConsumerWarps) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
-            for (int64_t i = 0; i < my_tiles; ++i) {
+            int64_t next_dyn = -1;
+            for (int64_t i = 0;; ++i) {
                 const int s = (int)(i % S);
                 const uint32_t ph = (uint32_t)((i / S) & 1);
+                int64_t tile = blockIdx.x + i * G;
+                if (dynamic && i >= S) tile = next_dyn;
+                // draw the next tile now: the atomic's round trip overlaps the wait for a free stage
+                if (dynamic && i + 1 >= S) next_dyn = (int64_t)S * G + atomicAdd(&p.tile_ctr[qi], 1u);
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                const int64_t tile = blockIdx.x + i * G;
+                if (tile >= p.n_tiles) {
+                    stage_tile[s] = -1;
+                    mbar_arrive(&full_bar[s]);
+                    break;
+                }
+                stage_tile[s] = tile;
                 const int64_t row0 = tile * TR;
                 int64_t nr = p.n_rows - row0;
                 if (nr > TR) nr = TR;
@@ -129,19 +147,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
         WarpTopK<NPL> top;
         top.init(lists + warp * KC, lane);
 
-        for (int64_t i = 0; i < my_tiles; ++i) {
+        for (int64_t i = 0;; ++i) {
             const int s = (int)(i % S);
             const uint32_t ph = (uint32_t)((i / S) & 1);
-            const int64_t tile = blockIdx.x + i * G;
+            mbar_wait(&full_bar[s], ph);
+            const int64_t tile = stage_tile[s];
+            if (tile < 0) break;
             const int64_t row0 = tile * TR + warp * RPW;
-            // filter bits for this warp's rows (issued before the wait so the latency overlaps)
+            // filter bits for this warp's rows (consumed after the dot products, so the load overlaps them)
             uint32_t allow_bits = 0xFFFFFFFFu;
             if (p.allow != nullptr) {
                 // RPW <= 2 consecutive rows never straddle a 32-bit word (row0 is even when RPW==2)
                 const uint32_t w = (row0 < p.n_rows) ? __ldg(&p.allow[row0 >> 5]) : 0u;
                 allow_bits = w >> (row0 & 31);
             }
-            mbar_wait(&full_bar[s], ph);
 
             const float4 *tv = reinterpret_cast<const float4 *>(tiles + (size_t)s * L::kTileBytes) +
                                (size_t)(warp * RPW) * (DIM / 4);
@@ -232,6 +251,7 @@ struct FinalizeParams {
     double *out_score;        // [nq, k]
     int64_t *out_id;          // [nq, k]
     int32_t *out_n;           // [nq]
+    unsigned int *reset_ctr;  // nullable: K1's work-stealing counter of this query, zeroed for the next launch
 };
 
 // fp64 cosine of query (a-values in smem as float) x one resident row; all lanes return the result.
@@ -403,7 +423,10 @@ __global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const Finaliz
         p.out_score[(size_t)qi * p.k + c] = __longlong_as_double(0x7FF8000000000000ll);
         p.out_id[(size_t)qi * p.k + c] = -1;
     }
-    if (threadIdx.x == 0) p.out_n[qi] = n_out;
+    if (threadIdx.x == 0) {
+        p.out_n[qi] = n_out;
+        if (p.reset_ctr) p.reset_ctr[qi] = 0u;
+    }
 }
 
 // one launch helper for every candidate width
@@ -447,6 +470,12 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
 
     const size_t need = (size_t)nq * grid * KC * sizeof(uint64_t);
     if (cdr_ws_reserve((void **)&ws.cta_keys, &ws.cta_keys_bytes, need) != CDR_OK) return CDR_ERR_OOM;
+    // work-stealing counters: zeroed when (re)allocated, re-zeroed by every finalize launch
+    static const bool k1_static = [] { const char *e = getenv("CADENCE_K1_SCHED"); return e && e[0] == 's'; }();
+    if (!k1_static && ws.tile_ctr_bytes < (size_t)nq * 4) {
+        if (cdr_ws_reserve((void **)&ws.tile_ctr, &ws.tile_ctr_bytes, (size_t)nq * 4) != CDR_OK) return CDR_ERR_OOM;
+        CDR_CUDA(cudaMemsetAsync(ws.tile_ctr, 0, ws.tile_ctr_bytes, st));
+    }
 
     ScanParams sp;
     sp.rows = s->emb_f32;
@@ -457,6 +486,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     sp.n_rows = s->n_rows;
     sp.n_tiles = n_tiles;
     sp.n_stages = stages;
+    sp.tile_ctr = k1_static ? nullptr : ws.tile_ctr;
 
     cdr_prof_mark_begin(0, st);
     exact_scan_kernel<J, RPW, NPL><<<dim3(grid, nq), kScanThreads, smem, st>>>(sp);
@@ -477,6 +507,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     fp.out_score = out_score;
     fp.out_id = out_id;
     fp.out_n = out_n;
+    fp.reset_ctr = sp.tile_ctr;
     return launch_finalize(fp, KC, nq, st);
 }
 
@@ -530,5 +561,6 @@ int cdr_finalize_unsorted_launch(cdr_store *s, const uint64_t *lists, const uint
     fp.out_score = out_score;
     fp.out_id = out_id;
     fp.out_n = out_n;
+    fp.reset_ctr = nullptr;
     return launch_finalize(fp, kc, nq, st);
 }

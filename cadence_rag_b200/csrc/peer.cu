@@ -1,0 +1,253 @@
+// peer.cu -- K4p: the multi-GPU exchange step fused with the k-way merge, over NVLink peer memory.
+//
+// Row-sharded corpus, one process per GPU.  The baseline exchange is an NCCL
+// all-gather of every rank's [nq,k] (score,id,n) lists followed by the K4 merge kernel
+// (topk_merge.cu) -- two launches plus the pack/unpack copies around the collective.  Here each
+// rank owns one receive buffer that every peer maps with CUDA IPC, and ONE kernel per rank does
+//   push   : CTA q stores this rank's list for query q into slot[parity][me][q] of EVERY rank's
+//            buffer (posted NVLink writes), then publishes flag[me][q] = epoch with a
+//            system-scope release store;
+//   wait   : R threads spin (acquire loads on LOCAL memory) until flag[r][q] >= epoch for every r;
+//   merge  : the R lists of query q are ranked by counting with the global ordering rule
+//            (score desc, NaN last, id asc) and the first k written out.
+// All ranks end with the identical result, as with the all-gather.  No CTA waits before it has
+// pushed, so the protocol cannot deadlock however the grids are scheduled.
+//
+// Slots are double-buffered by epoch parity: rank A can only finish epoch e+1 after every peer has
+// STARTED epoch e+1, i.e. after that peer's epoch-e kernel (which read parity e&1) completed, so A's
+// epoch e+2 writes never land on data a peer still reads.  All calls of a group must be issued in the
+// same order on every rank and on one stream per rank.
+#include "common.cuh"
+
+#include <cstring>
+
+struct cdr_peer_group {
+    int device = 0, rank = 0, world = 1;
+    int max_nq = 0, max_k = 0;
+    size_t entry_bytes = 0;       // one list: scores f64[max_k], ids i64[max_k], n i32 (+pad)
+    size_t flags_off = 0;         // byte offset of flags u32[world][max_nq]
+    size_t bytes = 0;
+    unsigned char *local = nullptr;
+    unsigned char *peer[CDR_PEER_MAX_RANKS] = {nullptr};   // mapped base of every rank's buffer (own included)
+    bool connected = false;
+    uint32_t epoch = 0;
+};
+
+namespace {
+
+struct PeerParams {
+    unsigned char *base[CDR_PEER_MAX_RANKS];
+    int rank, world;
+    int max_nq, max_k;
+    size_t entry_bytes, flags_off;
+    uint32_t epoch;
+    const double *scores;   // this rank's lists [nq, k]
+    const int64_t *ids;
+    const int32_t *n;
+    int nq, k;
+    double *out_score;
+    int64_t *out_id;
+    int32_t *out_n;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const void *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_publish_merge_kernel(const PeerParams p)
+{
+    extern __shared__ unsigned char raw[];
+    double *s_sc = reinterpret_cast<double *>(raw);
+    int64_t *s_id = reinterpret_cast<int64_t *>(s_sc + (size_t)p.world * p.k);
+    __shared__ int s_cnt;
+    __shared__ int s_n[CDR_PEER_MAX_RANKS];
+    const int q = blockIdx.x;
+    const uint32_t par = p.epoch & 1u;
+    const size_t slot_me = (((size_t)par * p.world + p.rank) * p.max_nq + q) * p.entry_bytes;
+
+    // ---- push: my list for query q into every rank's buffer
+    const int my_n = p.n[q];
+    for (int r = 0; r < p.world; ++r) {
+        unsigned char *dst = p.base[r] + slot_me;
+        unsigned long long *d_sc = reinterpret_cast<unsigned long long *>(dst);
+        unsigned long long *d_id = d_sc + p.max_k;
+        for (int i = threadIdx.x; i < my_n; i += blockDim.x) {
+            d_sc[i] = (unsigned long long)__double_as_longlong(p.scores[(size_t)q * p.k + i]);
+            d_id[i] = (unsigned long long)p.ids[(size_t)q * p.k + i];
+        }
+        if (threadIdx.x == 0) *reinterpret_cast<int32_t *>(d_id + p.max_k) = my_n;
+    }
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (threadIdx.x < p.world) {
+        const int r = threadIdx.x;
+        // the CTA's stores above are ordered before this release (bar.sync + cumulativity)
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<uint32_t *>(p.base[r] + p.flags_off) + (size_t)p.rank * p.max_nq + q, p.epoch);
+        // ---- wait: rank r's list for query q has landed in MY buffer
+        const uint32_t *flag = reinterpret_cast<const uint32_t *>(p.base[p.rank] + p.flags_off) + (size_t)r * p.max_nq + q;
+        long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(flag) - p.epoch) < 0) {
+            if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer never launched -> fail, do not hang
+        }
+        const unsigned char *src = p.base[p.rank] + (((size_t)par * p.world + r) * p.max_nq + q) * p.entry_bytes;
+        s_n[r] = *reinterpret_cast<const volatile int32_t *>(src + (size_t)p.max_k * 16);
+    }
+    __syncthreads();
+
+    // ---- merge (rank counting, as topk_merge_kernel)
+    const int tot = p.world * p.k;
+    int local = 0;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int r = e / p.k, i = e - r * p.k;
+        const bool ok = i < s_n[r];
+        const unsigned char *src = p.base[p.rank] + (((size_t)par * p.world + r) * p.max_nq + q) * p.entry_bytes;
+        s_sc[e] = ok ? __longlong_as_double((long long)ld_relaxed_sys_u64(src + (size_t)i * 8)) : 0.0;
+        s_id[e] = ok ? (int64_t)ld_relaxed_sys_u64(src + (size_t)(p.max_k + i) * 8) : -1;
+        local += ok;
+    }
+    if (local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int64_t id = s_id[e];
+        if (id < 0) continue;
+        const double sc = s_sc[e];
+        int rank = 0;
+        for (int o = 0; o < tot; ++o) {
+            const int64_t oid = s_id[o];
+            if (oid >= 0 && o != e && cdr_result_before(s_sc[o], oid, sc, id)) ++rank;
+        }
+        if (rank < p.k) {
+            p.out_score[(size_t)q * p.k + rank] = sc;
+            p.out_id[(size_t)q * p.k + rank] = id;
+        }
+    }
+    const int n_out = s_cnt < p.k ? s_cnt : p.k;
+    for (int i = n_out + threadIdx.x; i < p.k; i += blockDim.x) {
+        p.out_score[(size_t)q * p.k + i] = __longlong_as_double(0x7FF8000000000000ll);
+        p.out_id[(size_t)q * p.k + i] = -1;
+    }
+    if (threadIdx.x == 0) p.out_n[q] = n_out;
+}
+
+}  // namespace
+
+extern "C" int32_t cdr_peer_group_create(cdr_peer_group **out, int32_t device, int32_t rank, int32_t world,
+                                         int32_t max_nq, int32_t max_k, void *out_handle)
+{
+    CDR_REQUIRE(out && out_handle, CDR_ERR_INVALID, "cdr_peer_group_create: NULL argument");
+    CDR_REQUIRE(world >= 1 && world <= CDR_PEER_MAX_RANKS && rank >= 0 && rank < world, CDR_ERR_INVALID,
+                "cdr_peer_group_create: need 1 <= world <= %d and 0 <= rank < world", CDR_PEER_MAX_RANKS);
+    CDR_REQUIRE(max_nq >= 1 && max_k >= 1 && max_k <= CDR_MAX_K && (int64_t)world * max_k <= 4096, CDR_ERR_INVALID,
+                "cdr_peer_group_create: need max_nq >= 1, 1 <= max_k <= %d, world*max_k <= 4096", CDR_MAX_K);
+    static_assert(sizeof(cudaIpcMemHandle_t) == CDR_PEER_HANDLE_BYTES, "IPC handle size");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cdr_set_error("cdr_peer_group_create: CUDA device %d not available; this engine has no CPU fallback", device);
+        return CDR_ERR_NO_DEVICE;
+    }
+    DeviceGuard g(device);
+    cdr_peer_group *pg = new cdr_peer_group();
+    pg->device = device; pg->rank = rank; pg->world = world; pg->max_nq = max_nq; pg->max_k = max_k;
+    pg->entry_bytes = (size_t)max_k * 16 + 16;
+    pg->flags_off = ((size_t)2 * world * max_nq * pg->entry_bytes + 255) & ~(size_t)255;
+    pg->bytes = pg->flags_off + (size_t)world * max_nq * 4;
+    cudaError_t e = cudaMalloc(&pg->local, pg->bytes);
+    if (e == cudaSuccess) e = cudaMemset(pg->local, 0, pg->bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, pg->local);
+    if (e != cudaSuccess) {
+        cdr_set_error("cdr_peer_group_create: %s", cudaGetErrorString(e));
+        cudaFree(pg->local);
+        delete pg;
+        return e == cudaErrorMemoryAllocation ? CDR_ERR_OOM : CDR_ERR_CUDA;
+    }
+    memcpy(out_handle, &h, sizeof(h));
+    pg->peer[rank] = pg->local;
+    *out = pg;
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_peer_group_connect(cdr_peer_group *pg, const void *all_handles)
+{
+    CDR_REQUIRE(pg && all_handles, CDR_ERR_INVALID, "cdr_peer_group_connect: NULL argument");
+    CDR_REQUIRE(!pg->connected, CDR_ERR_STATE, "cdr_peer_group_connect: already connected");
+    DeviceGuard g(pg->device);
+    for (int r = 0; r < pg->world; ++r) {
+        if (r == pg->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char *)all_handles + (size_t)r * CDR_PEER_HANDLE_BYTES, sizeof(h));
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cdr_set_error("cdr_peer_group_connect: cannot map rank %d's buffer (%s); peer memory needs all ranks on "
+                          "one node with P2P access", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            for (int o = 0; o < r; ++o)
+                if (o != pg->rank && pg->peer[o]) { cudaIpcCloseMemHandle(pg->peer[o]); pg->peer[o] = nullptr; }
+            return CDR_ERR_UNSUPPORTED;
+        }
+        pg->peer[r] = (unsigned char *)ptr;
+    }
+    pg->connected = true;
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_peer_group_destroy(cdr_peer_group *pg)
+{
+    if (!pg) return CDR_OK;
+    DeviceGuard g(pg->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < pg->world; ++r)
+        if (r != pg->rank && pg->peer[r]) cudaIpcCloseMemHandle(pg->peer[r]);
+    cudaFree(pg->local);
+    delete pg;
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_peer_exchange_merge(cdr_peer_group *pg, const double *scores_dev, const int64_t *ids_dev,
+                                           const int32_t *n_dev, int32_t nq, int32_t k, double *out_score_dev,
+                                           int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
+{
+    CDR_REQUIRE(pg && scores_dev && ids_dev && n_dev && out_score_dev && out_id_dev && out_n_dev, CDR_ERR_INVALID,
+                "cdr_peer_exchange_merge: NULL argument");
+    CDR_REQUIRE(pg->connected || pg->world == 1, CDR_ERR_STATE, "cdr_peer_exchange_merge: group not connected");
+    CDR_REQUIRE(nq >= 0 && k >= 1 && k <= pg->max_k, CDR_ERR_INVALID, "cdr_peer_exchange_merge: k=%d outside [1,%d]", k,
+                pg->max_k);
+    DeviceGuard g(pg->device);
+    const size_t smem = (size_t)pg->world * k * 16;
+    static bool attr_set[64] = {false};
+    if (!attr_set[pg->device & 63] && smem > 48 * 1024) {
+        CDR_CUDA(cudaFuncSetAttribute(peer_publish_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+        attr_set[pg->device & 63] = true;
+    }
+    for (int q0 = 0; q0 < nq; q0 += pg->max_nq) {
+        const int m = nq - q0 < pg->max_nq ? nq - q0 : pg->max_nq;
+        PeerParams p;
+        for (int r = 0; r < CDR_PEER_MAX_RANKS; ++r) p.base[r] = pg->peer[r];
+        p.rank = pg->rank; p.world = pg->world; p.max_nq = pg->max_nq; p.max_k = pg->max_k;
+        p.entry_bytes = pg->entry_bytes; p.flags_off = pg->flags_off;
+        p.epoch = ++pg->epoch;
+        p.scores = scores_dev + (size_t)q0 * k; p.ids = ids_dev + (size_t)q0 * k; p.n = n_dev + q0;
+        p.nq = m; p.k = k;
+        p.out_score = out_score_dev + (size_t)q0 * k; p.out_id = out_id_dev + (size_t)q0 * k; p.out_n = out_n_dev + q0;
+        peer_publish_merge_kernel<<<m, 256, smem, (cudaStream_t)stream>>>(p);
+        CDR_LAUNCH_CHECK();
+    }
+    return CDR_OK;
+}

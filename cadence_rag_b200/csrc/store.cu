@@ -204,6 +204,7 @@ int alloc_store(cdr_store *s)
 void free_ws(ScanWorkspace &w)
 {
     cudaFree(w.cta_keys);
+    cudaFree(w.tile_ctr);
     cudaFree(w.q_stage);
     cudaFree(w.out_stage);
     cudaFree(w.gemm_ws);

@@ -72,15 +72,88 @@ def merge_shard_results(scores, ids, n, k: int, stream=None):
     return out_id, out_sc, out_n
 
 
-class ShardedSearcher:
-    """One rank's view of a row-sharded table."""
+class PeerExchange:
+    """NVLink peer-memory transport of the exchange step (csrc/peer.cu, K4p): every rank's receive
+    buffer is mapped into its peers with CUDA IPC and ONE kernel per rank pushes the local lists to
+    all peers, waits for theirs and merges -- no NCCL call and no pack/unpack copies per batch.
+    Construction is collective (the IPC handles travel through ``all_gather_object``)."""
 
-    def __init__(self, store, group=None):
+    def __init__(self, device: int, group=None, max_nq: int = 1024, max_k: int = 64):
+        import torch
+        import torch.distributed as dist
+        self.device = device
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.max_k = max_k
+        self._h = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(_ffi.CDR_PEER_HANDLE_BYTES)
+        with torch.cuda.device(device):
+            _ffi.check(_ffi.lib().cdr_peer_group_create(ctypes.byref(self._h), device, self.rank, self.world,
+                                                        max_nq, max_k, handle), "cdr_peer_group_create")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        status = _ffi.lib().cdr_peer_group_connect(self._h, b"".join(handles))
+        # every rank must take the same transport: agree on the outcome
+        ok = torch.tensor([1 if status == _ffi.CDR_OK else 0], dtype=torch.int32, device=f"cuda:{device}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            msg = _ffi.last_error() if status != _ffi.CDR_OK else "a peer rank could not map the buffers"
+            self.close()
+            raise _ffi.DenseEngineError(f"peer-memory exchange unavailable: {msg}", _ffi.CDR_ERR_UNSUPPORTED)
+
+    def close(self) -> None:
+        if self._h:
+            _ffi.lib().cdr_peer_group_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def exchange_merge(self, ids, scores, n, k: int, stream=None):
+        """Local (ids[nq,k], scores[nq,k], n[nq]) CUDA tensors -> the global top-k on every rank."""
+        import torch
+        nq = int(ids.shape[0])
+        dev = ids.device
+        out_sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        out_id = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        out_n = torch.empty((nq,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _ffi.check(_ffi.lib().cdr_peer_exchange_merge(self._h, _ffi.ptr(scores), _ffi.ptr(ids), _ffi.ptr(n), nq, k,
+                                                          _ffi.ptr(out_sc), _ffi.ptr(out_id), _ffi.ptr(out_n),
+                                                          _ffi.stream_ptr(stream)), "cdr_peer_exchange_merge")
+        return out_id, out_sc, out_n
+
+
+class ShardedSearcher:
+    """One rank's view of a row-sharded table.
+
+    transport: "peer" = fused push + merge kernel over NVLink peer memory (K4p), "nccl" = one
+    all-gather + the K4 merge kernel, "auto" (default; env CADENCE_EXCHANGE overrides) = peer when the
+    ranks can map each other's memory (one node, CUDA tensors), else nccl.  Both give identical bits."""
+
+    def __init__(self, store, group=None, transport: str = "auto", max_nq: int = 1024, max_k: int = 64):
+        import os
         import torch.distributed as dist
         self.store = store
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        transport = os.environ.get("CADENCE_EXCHANGE", transport)
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError(f"transport {transport!r}: expected auto, peer or nccl")
+        self.peer: Optional[PeerExchange] = None
+        self.transport = "none" if self.world == 1 else "nccl"
+        if self.world > 1 and transport in ("auto", "peer") and dist.get_backend(group) == "nccl":
+            try:
+                self.peer = PeerExchange(store.device, group, max_nq=max_nq, max_k=max_k)
+                self.transport = "peer"
+            except _ffi.DenseEngineError:
+                if transport == "peer":
+                    raise
+        elif transport == "peer" and self.world > 1:
+            raise _ffi.DenseEngineError("peer transport needs CUDA ranks (nccl backend)", _ffi.CDR_ERR_UNSUPPORTED)
+
+    def close(self) -> None:
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     def search(self, queries_dev, k: int, allow=None, mode: str = "exact"):
         """queries_dev: [nq, dim] CUDA tensor replicated on every rank.  Returns the global
@@ -89,5 +162,7 @@ class ShardedSearcher:
         ids, scores, n = fn(queries_dev, k, allow)
         if self.world == 1:
             return ids, scores, n
+        if self.peer is not None and k <= self.peer.max_k:
+            return self.peer.exchange_merge(ids, scores, n, k)
         g_sc, g_id, g_n = gather_shard_results(ids, scores, n, self.group)
         return merge_shard_results(g_sc, g_id, g_n, k)

@@ -162,6 +162,29 @@ int32_t cdr_topk_merge(const double *scores_dev, const int64_t *ids_dev, const i
                        int32_t R, int32_t nq, int32_t k, double *out_score_dev,
                        int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
 
+/* ---- K4p: the same exchange + merge over NVLink peer memory, one kernel per rank --------------
+ * Alternative transport for the step above when all ranks are processes on one node: every rank
+ * owns a receive buffer that its peers map with CUDA IPC; cdr_peer_exchange_merge launches ONE
+ * kernel that pushes this rank's [nq,k] lists into every rank's buffer (posted NVLink stores +
+ * a system-scope release flag per query), waits for the peers' lists on local memory, and merges
+ * them with the K4 ordering rule.  No NCCL call, no pack/unpack copies; identical result on every
+ * rank.  Protocol (csrc/peer.cu): every rank issues the same sequence of calls on one stream.
+ *   create  : allocates the buffer for batches of <= max_nq queries, lists of <= max_k; writes the
+ *             64-byte IPC handle to out_handle.  Exchange the handles of all ranks (rank-major,
+ *             e.g. torch.distributed.all_gather_object) and pass them to connect.
+ *   connect : maps the peers' buffers.  CDR_ERR_UNSUPPORTED when a peer cannot be mapped (ranks on
+ *             different nodes / no P2P): the caller then stays on the NCCL transport. */
+#define CDR_PEER_MAX_RANKS 16
+#define CDR_PEER_HANDLE_BYTES 64
+typedef struct cdr_peer_group cdr_peer_group;
+int32_t cdr_peer_group_create(cdr_peer_group **out, int32_t device, int32_t rank, int32_t world,
+                              int32_t max_nq, int32_t max_k, void *out_handle);
+int32_t cdr_peer_group_connect(cdr_peer_group *g, const void *all_handles);
+int32_t cdr_peer_group_destroy(cdr_peer_group *g);
+int32_t cdr_peer_exchange_merge(cdr_peer_group *g, const double *scores_dev, const int64_t *ids_dev,
+                                const int32_t *n_dev, int32_t nq, int32_t k, double *out_score_dev,
+                                int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
+
 /* ---- K5: reciprocal-rank fusion -------------------------------------------------------------
  * Replaces app/retrieve.py:245-260 (_rrf_merge), bit-exact: for lanes in order (bm25,
  * tech_tokens, dense; app/retrieve.py:537-547) and ranks from 1,

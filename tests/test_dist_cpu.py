@@ -38,6 +38,16 @@ def _worker(rank, world, port, n_total, k, out_dir):
     assert g_sc.shape == (world, 3, k) and g_id.dtype == torch.int64 and g_n.dtype == torch.int32
     assert np.array_equal(g_id[rank].numpy(), ids) and np.array_equal(g_n[rank].numpy(), n)
     assert np.array_equal(g_sc[rank].numpy().view(np.uint64), sc.view(np.uint64))   # bit views survive packing
+    # transport selection: gloo ranks cannot map peer memory -> the all-gather transport, loudly for "peer"
+    class _Store:
+        device = 0
+    searcher = cdist.ShardedSearcher(_Store(), transport="auto")
+    assert searcher.transport == "nccl" and searcher.peer is None and searcher.world == world
+    try:
+        cdist.ShardedSearcher(_Store(), transport="peer")
+        raise AssertionError("peer transport must refuse non-CUDA ranks")
+    except cdist._ffi.DenseEngineError:
+        pass
     merged = ports.merge_topk(g_sc.numpy(), g_id.numpy(), g_n.numpy(), k)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array([m[0] for m in merged]))
     dist.barrier()

@@ -33,13 +33,37 @@ def _worker(rank, world, port, n_total, k, out_dir):
     store = DenseStore("chunks", cnt, dim=1024, device=rank)
     store.append_synthetic(cnt, first_row=first)
     store.finalize()
-    searcher = ShardedSearcher(store)
+    searcher = ShardedSearcher(store, transport="nccl")
     qs = synth_rows_device(SYNTH_QUERY_SEED, 0, 130, 1024, device=rank)
     res = {}
     for mode in ("exact", "ann"):
         ids, sc, n = searcher.search(qs, k, mode=mode)
         torch.cuda.synchronize()
         res[mode] = (ids.cpu().numpy(), sc.cpu().numpy(), n.cpu().numpy())
+    # K4p: the same exchange over NVLink peer memory (one push+merge kernel per rank) -- identical bits,
+    # across many epochs (slot parity reuse), batches larger than the slot count (chunking), nq=1, small k
+    peer = ShardedSearcher(store, transport="peer", max_nq=64, max_k=64)
+    assert peer.transport == "peer"
+    for rep in range(6):
+        for nq_i, kk in ((130, k), (1, k), (64, 10), (65, k)):
+            a = searcher.search(qs[:nq_i], kk, mode="exact")
+            b = peer.search(qs[:nq_i], kk, mode="exact")
+            torch.cuda.synchronize()
+            for x, y in zip(a, b):
+                assert torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x,
+                                   y.view(torch.int64) if y.dtype == torch.float64 else y), (rep, nq_i, kk)
+    pb = peer.search(qs, k, mode="ann")
+    torch.cuda.synchronize()
+    assert np.array_equal(pb[0].cpu().numpy(), res["ann"][0])
+    # a filter that empties one rank's shard: short / empty local lists still merge
+    allow, cnt_allowed = store.filter_bitmap(call_slots=[0, 1])          # rows 0..399 live on rank 0 only
+    fa = searcher.search(qs[:5], k, allow=allow, mode="exact")
+    fb = peer.search(qs[:5], k, allow=allow, mode="exact")
+    torch.cuda.synchronize()
+    assert torch.equal(fa[0], fb[0]) and torch.equal(fa[2], fb[2]) and int(fa[2][0]) == k
+    assert (cnt_allowed == 400) == (rank == 0)
+    dist.barrier()
+    peer.close()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), e_ids=res["exact"][0], e_sc=res["exact"][1],
              a_ids=res["ann"][0], a_sc=res["ann"][1])
     if rank == 0:
