@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hnsw-rows", type=int, default=10_000, help="batch_bf16: rows of the CPU HNSW baseline's sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bf16-only", action="store_true", help="batch_bf16: keep only bf16 rows resident (C5 residency)")
     ap.add_argument("--workload", default="exact_f32", choices=["exact_f32", "batch_bf16", "hybrid"],
@@ -151,6 +152,42 @@ def cpu_baseline(rows_total: int, sample_rows: int, sample_queries: int, threads
             "sample": f"{done} queries x {sample_rows} of {rows_total} rows (pgvector 0.8.1 cosine loop "
                       f"restated in C, fp32 accumulate, {cores} OpenMP threads; rate scaled by rows)",
             "seconds": dt}
+
+
+def cpu_baseline_hnsw(rows_sample: int, threads: int, target_seconds: float = 8.0):
+    """The reference's mode "ann" restated on the CPU (oracle/hnsw_baseline.cc: pgvector's HNSW parameters
+    m=16, ef_construction=64, ef_search=80, cosine via normalised inner product) over a bounded sample
+    of the synthetic corpus: build excluded, queries on all host cores (one query per thread, like
+    concurrent backends) and on one thread, recall@50 against the exact oracle.  Graph-walk cost grows
+    ~log(rows), so the rate is reported for the sample size as is, NOT scaled; "restated, not Postgres"."""
+    import numpy as np
+    from oracle import cpu_oracle as orc
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    x = orc.synth_rows(20260209, 0, rows_sample)
+    qs = orc.synth_rows(20260210, 20_000_000, 1024)
+    t0 = time.perf_counter()
+    index = orc.HnswBaseline(x)
+    build_s = time.perf_counter() - t0
+    index.search(qs[:64], TOPK, 80, nthreads=threads)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        rows, _sims, _n = index.search(qs, TOPK, 80, nthreads=threads)
+        done += qs.shape[0]
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds:
+            break
+    t1 = time.perf_counter()
+    index.search(qs[:128], TOPK, 80, nthreads=1)
+    one = 128 / (time.perf_counter() - t1)
+    recall = float(np.mean([len(set(rows[i].tolist()) & set((orc.exact_scan(qs[i], x, TOPK)[0] - 1).tolist())) / TOPK
+                            for i in range(64)]))
+    index.close()
+    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": one,
+            "recall_at_50_vs_exact": recall, "rows": rows_sample, "m": 16, "ef_construction": 64, "ef_search": 80,
+            "build_seconds": build_s,
+            "sample": f"{done} queries over a {rows_sample}-row sample of the synthetic corpus (HNSW restated, not Postgres; "
+                      "rate not scaled to the full corpus)"}
 
 
 def run_reference(args):
@@ -326,6 +363,10 @@ def run_batch_bf16(args):
                              "launches_timed": int(k_n.value), "segment_launch_ms_last_step": last_step_launch_ms,
                              "gemm_ms_by_step": [round(float(per_launch[i * segs:(i + 1) * segs].sum()), 3)
                                                  for i in range(args.steps)]}}
+        if world == 1 and not args.no_cpu_baseline:
+            # the reference's two CPU paths for this config, timed on this box's host cores in the same run
+            line["cpu_baseline"] = cpu_baseline(rows, args.cpu_sample_rows, args.cpu_sample_queries, 0)
+            line["cpu_baseline_hnsw"] = cpu_baseline_hnsw(args.hnsw_rows, 0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -174,23 +174,46 @@ static int32_t search_host(const char *name, search_fn fn, cdr_store *s, const f
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     float *qd = nullptr;
-    unsigned char *od = nullptr;
+    unsigned char *od = nullptr, *hp = nullptr;
     const size_t qb = (size_t)nq * s->dim * 4;
     const size_t sb = (size_t)nq * k * 8, ib = (size_t)nq * k * 8, nb = (size_t)nq * 4;
+    const size_t qb_al = (qb + 255) & ~(size_t)255;
     {
         std::lock_guard<std::mutex> lk(s->mu);
         ScanWorkspace &ws = s->ws[st];
         if (cdr_ws_reserve((void **)&ws.q_stage, &ws.q_stage_bytes, qb) != CDR_OK) return CDR_ERR_OOM;
         if (cdr_ws_reserve(&ws.out_stage, &ws.out_stage_bytes, sb + ib + nb + 512) != CDR_OK) return CDR_ERR_OOM;
+        // pinned mirror of the request / response: one H2D and one D2H DMA per call instead of
+        // driver-staged copies from / to pageable caller memory
+        const size_t need = qb_al + sb + ib + nb;
+        if (ws.hyb_host_bytes < need) {
+            if (ws.hyb_host) { cudaStreamSynchronize(st); cudaFreeHost(ws.hyb_host); ws.hyb_host = nullptr; ws.hyb_host_bytes = 0; }
+            const size_t sz = need < 65536 ? 65536 : need * 2;
+            CDR_CUDA(cudaHostAlloc(&ws.hyb_host, sz, cudaHostAllocDefault));
+            ws.hyb_host_bytes = sz;
+        }
         qd = ws.q_stage;
         od = (unsigned char *)ws.out_stage;
+        hp = (unsigned char *)ws.hyb_host;
     }
     double *sd = (double *)od;
     int64_t *idd = (int64_t *)(od + sb);
     int32_t *nd = (int32_t *)(od + sb + ib);
-    CDR_CUDA(cudaMemcpyAsync(qd, q_host, qb, cudaMemcpyHostToDevice, st));
+    // small requests (the per-request case: one query, 4 KB) go through the pinned mirror; large batches are
+    // copied straight from / to the caller's buffers (a pinned caller buffer then DMAs without a host memcpy)
+    const bool staged = qb <= ((size_t)256 << 10);
+    if (staged) memcpy(hp, q_host, qb);
+    CDR_CUDA(cudaMemcpyAsync(qd, staged ? (const void *)hp : (const void *)q_host, qb, cudaMemcpyHostToDevice, st));
     rc = fn(s, qd, nq, k, allow_dev, sd, idd, nd, stream);
     if (rc != CDR_OK) return rc;
+    if (staged) {
+        CDR_CUDA(cudaMemcpyAsync(hp + qb_al, od, sb + ib + nb, cudaMemcpyDeviceToHost, st));
+        CDR_CUDA(cudaStreamSynchronize(st));
+        memcpy(out_score_host, hp + qb_al, sb);
+        memcpy(out_id_host, hp + qb_al + sb, ib);
+        memcpy(out_n_host, hp + qb_al + sb + ib, nb);
+        return CDR_OK;
+    }
     CDR_CUDA(cudaMemcpyAsync(out_score_host, sd, sb, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaMemcpyAsync(out_id_host, idd, ib, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaMemcpyAsync(out_n_host, nd, nb, cudaMemcpyDeviceToHost, st));

@@ -415,23 +415,26 @@ class DenseStore:
         nq = int(q.shape[0])
         if int(q.shape[1]) != self.dim:
             raise DenseEngineError(f"query dim {int(q.shape[1])} != store dim {self.dim}")
-        with torch.cuda.device(self.device):
-            if on_dev:
-                dev = f"cuda:{self.device}"
-                sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
-                ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-                cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
-                fn = getattr(_ffi.lib(), fn_name)
-                _ffi.check(fn(self.handle, _ffi.ptr(q), nq, k, _ffi.ptr(allow), _ffi.ptr(sc), _ffi.ptr(ids),
-                              _ffi.ptr(cnt), self._stream()), fn_name)
-                return ids, sc, cnt
-            sc = np.empty((nq, k), dtype=np.float64)
-            ids = np.empty((nq, k), dtype=np.int64)
-            cnt = np.empty((nq,), dtype=np.int32)
-            fn = getattr(_ffi.lib(), fn_name + "_host")
+        # no torch.cuda.device() context here: every tensor names its device, the stream is the store
+        # device's current stream, and the C entry points switch devices themselves (DeviceGuard)
+        if on_dev:
+            dev = q.device
+            if dev.index != self.device:
+                raise DenseEngineError(f"queries live on {dev}, the store on cuda:{self.device}")
+            sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+            fn = getattr(_ffi.lib(), fn_name)
             _ffi.check(fn(self.handle, _ffi.ptr(q), nq, k, _ffi.ptr(allow), _ffi.ptr(sc), _ffi.ptr(ids),
-                          _ffi.ptr(cnt), self._stream()), fn_name + "_host")
+                          _ffi.ptr(cnt), self._stream()), fn_name)
             return ids, sc, cnt
+        sc = np.empty((nq, k), dtype=np.float64)
+        ids = np.empty((nq, k), dtype=np.int64)
+        cnt = np.empty((nq,), dtype=np.int32)
+        fn = getattr(_ffi.lib(), fn_name + "_host")
+        _ffi.check(fn(self.handle, _ffi.ptr(q), nq, k, _ffi.ptr(allow), _ffi.ptr(sc), _ffi.ptr(ids),
+                      _ffi.ptr(cnt), self._stream()), fn_name + "_host")
+        return ids, sc, cnt
 
     def search_exact(self, queries, k: int, allow=None):
         """mode="exact": fp32 cosine scan (K1) + fp64 re-score.  Host queries -> host results
@@ -487,13 +490,12 @@ class DenseStore:
                "fused_scores": np.empty((nq, max_out), dtype=np.float64), "fused_mask": np.empty((nq, max_out), dtype=np.uint32),
                "fused_n": np.zeros(nq, dtype=np.int32)}
         count = ctypes.c_int64(0)
-        with torch.cuda.device(self.device):
-            _ffi.check(_ffi.lib().cdr_hybrid_retrieve_host(
-                self.handle, None if tech_index is None else tech_index._h, None if spec is None else ctypes.addressof(spec),
-                _ffi.ptr(q), nq, kd, _ffi.ptr(tok), _ffi.ptr(nt), max_tokens, int(tech_limit), _ffi.ptr(b_ids), _ffi.ptr(b_off),
-                int(rrf_k), int(max_out), ctypes.addressof(count), _ffi.ptr(out["dense_ids"]), _ffi.ptr(out["dense_scores"]),
-                _ffi.ptr(out["dense_n"]), _ffi.ptr(out["tech_ids"]), _ffi.ptr(out["tech_n"]), _ffi.ptr(out["fused_ids"]),
-                _ffi.ptr(out["fused_scores"]), _ffi.ptr(out["fused_mask"]), _ffi.ptr(out["fused_n"]), self._stream()),
-                "cdr_hybrid_retrieve_host")
+        _ffi.check(_ffi.lib().cdr_hybrid_retrieve_host(
+            self.handle, None if tech_index is None else tech_index._h, None if spec is None else ctypes.addressof(spec),
+            _ffi.ptr(q), nq, kd, _ffi.ptr(tok), _ffi.ptr(nt), max_tokens, int(tech_limit), _ffi.ptr(b_ids), _ffi.ptr(b_off),
+            int(rrf_k), int(max_out), ctypes.addressof(count), _ffi.ptr(out["dense_ids"]), _ffi.ptr(out["dense_scores"]),
+            _ffi.ptr(out["dense_n"]), _ffi.ptr(out["tech_ids"]), _ffi.ptr(out["tech_n"]), _ffi.ptr(out["fused_ids"]),
+            _ffi.ptr(out["fused_scores"]), _ffi.ptr(out["fused_mask"]), _ffi.ptr(out["fused_n"]), self._stream()),
+            "cdr_hybrid_retrieve_host")
         out["count"] = int(count.value)
         return out

@@ -222,3 +222,61 @@ def rows_to_bitmap(allow_rows: np.ndarray) -> np.ndarray:
         a = np.concatenate([a, np.zeros(pad, dtype=bool)])
     bits = np.packbits(a.reshape(-1, 32), axis=1, bitorder="little")
     return bits.view(np.uint32).reshape(-1).copy()
+
+
+# ----------------------------------------------------------------------------- HNSW CPU baseline
+class HnswBaseline:
+    """pgvector's mode="ann" restated on the CPU (oracle/hnsw_baseline.cc: HNSW m=16,
+    ef_construction=64, vector_cosine_ops) -- a BASELINE to time next to the GPU brute-force lane,
+    "restated, not Postgres".  Rows are L2-normalised once at build time; the build is serial,
+    queries run on `nthreads` OpenMP threads (one per query, like concurrent backends)."""
+
+    _hlib = None
+
+    @classmethod
+    def _lib(cls):
+        if cls._hlib is None:
+            path = os.path.join(_HERE, "_build", "libhnsw_baseline.so")
+            if not os.path.exists(path):
+                subprocess.run(["make", "-s", "-C", _HERE, "_build/libhnsw_baseline.so"], check=True)
+            L = ctypes.CDLL(path)
+            vp = ctypes.c_void_p
+            L.orc_hnsw_build.argtypes = [vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64]
+            L.orc_hnsw_build.restype = vp
+            L.orc_hnsw_search.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
+            L.orc_hnsw_search.restype = ctypes.c_int
+            L.orc_hnsw_search_batch.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int]
+            L.orc_hnsw_search_batch.restype = None
+            L.orc_hnsw_free.argtypes = [vp]
+            L.orc_hnsw_free.restype = None
+            cls._hlib = L
+        return cls._hlib
+
+    def __init__(self, x: np.ndarray, m: int = 16, ef_construction: int = 64, seed: int = 1):
+        x = np.asarray(x, dtype=np.float32)
+        norms = np.sqrt((x.astype(np.float64) ** 2).sum(axis=1, keepdims=True))
+        self.x = np.ascontiguousarray((x / np.maximum(norms, 1e-30)).astype(np.float32))   # kept alive: the index points into it
+        self.n, self.dim = self.x.shape
+        self._h = self._lib().orc_hnsw_build(_p(self.x), self.n, self.dim, m, ef_construction, seed)
+
+    def search(self, qs: np.ndarray, k: int, ef_search: int = 80, nthreads: int = 0):
+        """rows[nq, k] (0-based, -1 = unused), sims[nq, k], n[nq]."""
+        qs = np.asarray(qs, dtype=np.float32)
+        if qs.ndim == 1:
+            qs = qs[None, :]
+        qn = np.ascontiguousarray((qs / np.maximum(np.linalg.norm(qs.astype(np.float64), axis=1, keepdims=True), 1e-30)).astype(np.float32))
+        nq = qn.shape[0]
+        rows = np.empty((nq, k), dtype=np.int64); sims = np.empty((nq, k), dtype=np.float32); n = np.empty(nq, dtype=np.int32)
+        self._lib().orc_hnsw_search_batch(self._h, _p(qn), nq, k, ef_search, _p(rows), _p(sims), _p(n), nthreads)
+        return rows, sims, n
+
+    def close(self):
+        if self._h:
+            self._lib().orc_hnsw_free(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

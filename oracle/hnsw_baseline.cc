@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <omp.h>
 #include <queue>
 #include <random>
 #include <vector>
@@ -27,8 +28,12 @@ struct Hnsw {
     std::vector<int> level;            // per node
     std::vector<std::vector<std::vector<int>>> links;   // [node][layer] -> neighbours
     int entry = -1, max_level = -1;
-    std::vector<uint32_t> visited;
-    uint32_t epoch = 0;
+    // visited marks live in a per-thread scratch so queries can run concurrently (the build is serial)
+    struct Scratch {
+        std::vector<uint32_t> visited;
+        uint32_t epoch = 0;
+    };
+    Scratch build_scratch;
 
     float dist(const float *a, const float *b) const {
         float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -41,8 +46,11 @@ struct Hnsw {
     typedef std::pair<float, int> Cand;
 
     // Alg. 2: best-first search on one layer with beam `ef`; returns up to ef closest (max-heap order)
-    std::vector<Cand> search_layer(const float *q, std::vector<Cand> entry_pts, int ef, int layer) {
-        if (++epoch == 0) { std::fill(visited.begin(), visited.end(), 0); epoch = 1; }
+    std::vector<Cand> search_layer(Scratch &sc, const float *q, std::vector<Cand> entry_pts, int ef, int layer) {
+        std::vector<uint32_t> &visited = sc.visited;
+        if (visited.size() != (size_t)n) { visited.assign(n, 0); sc.epoch = 0; }
+        if (++sc.epoch == 0) { std::fill(visited.begin(), visited.end(), 0); sc.epoch = 1; }
+        const uint32_t epoch = sc.epoch;
         std::priority_queue<Cand, std::vector<Cand>, std::greater<Cand>> cand;   // closest first
         std::priority_queue<Cand> best;                                           // farthest on top
         for (auto &e : entry_pts) { visited[e.second] = epoch; cand.push(e); best.push(e); }
@@ -80,7 +88,8 @@ struct Hnsw {
 
     void build(const float *rows, int64_t n_, int dim_, int m_, int efc_, uint64_t seed) {
         x = rows; n = n_; dim = dim_; m = m_; efc = efc_;
-        level.resize(n); links.resize(n); visited.assign(n, 0);
+        level.resize(n); links.resize(n);
+        Scratch &sc = build_scratch;
         std::mt19937_64 rng(seed);
         std::uniform_real_distribution<double> uni(0.0, 1.0);
         const double ml = 1.0 / std::log((double)m);
@@ -91,13 +100,17 @@ struct Hnsw {
             const float *q = x + i * dim;
             if (entry < 0) { entry = (int)i; max_level = lv; continue; }
             std::vector<Cand> ep = {{dist(q, x + (int64_t)entry * dim), entry}};
-            for (int l = max_level; l > lv; --l) ep = {search_layer(q, ep, 1, l)[0]};
+            for (int l = max_level; l > lv; --l) ep = {search_layer(sc, q, ep, 1, l)[0]};
             for (int l = std::min(lv, max_level); l >= 0; --l) {
-                std::vector<Cand> w = search_layer(q, ep, efc, l);
+                std::vector<Cand> w = search_layer(sc, q, ep, efc, l);
                 const int mmax = l == 0 ? 2 * m : m;
                 std::vector<int> nb = select_neighbours(w, m);
                 links[i][l] = nb;
-                for (int o : nb) {
+                // back-links: the neighbours' lists are distinct, so their re-pruning runs in parallel
+                // (the result does not depend on the thread count)
+#pragma omp parallel for schedule(dynamic, 1)
+                for (int t0 = 0; t0 < (int)nb.size(); ++t0) {
+                    const int o = nb[t0];
                     auto &ol = links[o][l];
                     ol.push_back((int)i);
                     if ((int)ol.size() > mmax) {
@@ -113,11 +126,11 @@ struct Hnsw {
         }
     }
 
-    int search(const float *q, int k, int ef, int64_t *out_rows, float *out_sim) {
+    int search(Scratch &sc, const float *q, int k, int ef, int64_t *out_rows, float *out_sim) {
         if (entry < 0) return 0;
         std::vector<Cand> ep = {{dist(q, x + (int64_t)entry * dim), entry}};
-        for (int l = max_level; l > 0; --l) ep = {search_layer(q, ep, 1, l)[0]};
-        std::vector<Cand> w = search_layer(q, ep, std::max(ef, k), 0);
+        for (int l = max_level; l > 0; --l) ep = {search_layer(sc, q, ep, 1, l)[0]};
+        std::vector<Cand> w = search_layer(sc, q, ep, std::max(ef, k), 0);
         int m_out = std::min<int>(k, (int)w.size());
         for (int i = 0; i < m_out; ++i) { out_rows[i] = w[i].second; out_sim[i] = -w[i].first; }
         return m_out;
@@ -136,7 +149,26 @@ void *orc_hnsw_build(const float *rows_normalised, int64_t n, int dim, int m, in
 // q must be L2-normalised by the caller; returns #results; rows are 0-based row indices
 int orc_hnsw_search(void *h, const float *q, int k, int ef_search, int64_t *out_rows, float *out_sim)
 {
-    return static_cast<Hnsw *>(h)->search(q, k, ef_search, out_rows, out_sim);
+    Hnsw *g = static_cast<Hnsw *>(h);
+    return g->search(g->build_scratch, q, k, ef_search, out_rows, out_sim);
+}
+// nq independent queries ([nq, dim], L2-normalised) on `nthreads` OpenMP threads (<= 0: all cores), one
+// scratch per thread -- the analogue of nq concurrent Postgres backends walking the same index.
+// out_rows / out_sim are [nq, k] (unused slots -1 / 0); out_n [nq].
+void orc_hnsw_search_batch(void *h, const float *qs, int nq, int k, int ef_search, int64_t *out_rows, float *out_sim,
+                           int *out_n, int nthreads)
+{
+    Hnsw *g = static_cast<Hnsw *>(h);
+    if (nthreads <= 0) nthreads = omp_get_num_procs();
+#pragma omp parallel num_threads(nthreads)
+    {
+        Hnsw::Scratch sc;
+#pragma omp for schedule(dynamic, 4)
+        for (int i = 0; i < nq; ++i) {
+            for (int j = 0; j < k; ++j) { out_rows[(int64_t)i * k + j] = -1; out_sim[(int64_t)i * k + j] = 0.f; }
+            out_n[i] = g->search(sc, qs + (int64_t)i * g->dim, k, ef_search, out_rows + (int64_t)i * k, out_sim + (int64_t)i * k);
+        }
+    }
 }
 void orc_hnsw_free(void *h) { delete static_cast<Hnsw *>(h); }
 }

@@ -205,3 +205,26 @@ def test_ports_match_live_reference():
         assert [(r["chunk_id"], h, s) for r, h, s in got] == [(r["chunk_id"], h, s) for r, h, s in want]
     vals = rng.standard_normal(100).tolist()
     assert ports.vector_literal(vals) == ref.vector_literal(vals)
+
+
+def test_hnsw_baseline_restatement_sane():
+    """The CPU HNSW baseline (bench.py's cpu_baseline_hnsw; pgvector's m=16 / ef_construction=64 / ef_search=80)
+    finds the exact neighbours on data with low intrinsic dimension and is independent of the thread count."""
+    rng = np.random.default_rng(3)
+    n, k = 1500, 20
+    z = rng.standard_normal((n, 12)).astype(np.float32)
+    proj = rng.standard_normal((12, 256)).astype(np.float32)
+    x = z @ proj
+    qs = rng.standard_normal((16, 12)).astype(np.float32) @ proj
+    index = orc.HnswBaseline(x)
+    rows, sims, cnt = index.search(qs, k, 80)
+    rows1, _, _ = index.search(qs, k, 80, nthreads=1)
+    assert np.array_equal(rows, rows1) and (cnt == k).all()
+    hit = 0
+    for i in range(qs.shape[0]):
+        want, want_sc = orc.exact_scan(qs[i], x, k)
+        hit += len(set(rows[i].tolist()) & set((want - 1).tolist()))
+        assert np.all(np.diff(sims[i]) <= 1e-6)                      # closest first
+        assert abs(float(sims[i][0]) - float(want_sc[0])) < 1e-4     # cosine of the best hit
+    assert hit / (k * qs.shape[0]) >= 0.97
+    index.close()
