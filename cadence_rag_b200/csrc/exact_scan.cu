@@ -22,6 +22,7 @@
 // Algorithmic bytes per query: n_rows * dim * 4.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
 #include <cstdlib>
 
 namespace {
@@ -450,11 +451,203 @@ __global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const Finaliz
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Latency variant of the finalize step for small batches (one request = one query): a cluster of
+// 8 CTAs per query.  A single CTA is issue-bound (~60 k warp-instructions on one SM, 25 us); here
+//   1. every CTA merges its share of the per-CTA lists (lists r, r+8, ...) to a top-KC in shared memory,
+//   2. CTA 0 reads the 8 partial lists through distributed shared memory and merges them,
+//   3. every CTA re-scores KC/8 of the survivors in fp64 (one row per warp) and stores score / id into
+//      CTA 0's shared memory,
+//   4. CTA 0 orders the KC results by rank counting and writes the first k.
+// Same arithmetic and ordering as scan_finalize_kernel => identical bits.
+constexpr int kFinCluster = 8;
+
+template <int NPL>
+__global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256)
+    scan_finalize_cluster_kernel(const FinalizeParams p)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int KC = NPL * 32, WARPS = 8;
+    __shared__ uint64_t s_lists[WARPS * KC];   // phase 1: this CTA's partial lists; [0, KC) = its top-KC
+    __shared__ uint64_t s_tree[WARPS * KC];    // phase 2 (CTA 0): the 8 CTAs' lists; [0, KC) = the survivors
+    __shared__ double s_score[KC];             // phase 3 results, written into CTA 0 by all CTAs
+    __shared__ int64_t s_id[KC];
+    __shared__ int s_valid[KC];
+    __shared__ int s_nvalid;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned crank = cluster.block_rank();
+    const int qi = blockIdx.x / kFinCluster;
+    const uint64_t *base = p.lists + (size_t)qi * p.n_lists * KC;
+    if (threadIdx.x == 0) s_nvalid = 0;
+
+    // ---- 1. this CTA's lists: l = crank + 8 * (warp + 8 * j), software-pipelined like the 1-CTA kernel
+    uint64_t k[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) k[i] = CDR_EMPTY_KEY;
+    {
+        constexpr int STRIDE = kFinCluster * WARPS;
+        uint64_t nxt[NPL];
+        int l = (int)crank + kFinCluster * warp;
+        if (l < p.n_lists) {
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) nxt[i] = base[(size_t)l * KC + (KC - 1 - (i * 32 + lane))];
+        }
+        while (l < p.n_lists) {
+            uint64_t cur[NPL];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) cur[i] = nxt[i];
+            const int ln = l + STRIDE;
+            if (ln < p.n_lists) {
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) nxt[i] = base[(size_t)ln * KC + (KC - 1 - (i * 32 + lane))];
+            }
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) k[i] = k[i] > cur[i] ? k[i] : cur[i];
+            warp_bitonic_merge_desc<NPL>(k, lane);
+            l = ln;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+#pragma unroll
+    for (int step = 1; step < WARPS; step <<= 1) {
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0) {
+            warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+        }
+    }
+    cluster.sync();
+
+    // ---- 2. CTA 0: warp w fetches CTA w's top-KC over DSMEM, then the same pairwise tree
+    if (crank == 0) {
+        const uint64_t *remote = cluster.map_shared_rank(s_lists, warp);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) k[i] = remote[i * 32 + lane];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) s_tree[warp * KC + i * 32 + lane] = k[i];
+#pragma unroll
+        for (int step = 1; step < WARPS; step <<= 1) {
+            __syncthreads();
+            if ((warp & (2 * step - 1)) == 0) {
+                warp_merge_topk<NPL>(k, s_tree + (warp + step) * KC, lane);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s_tree[warp * KC + i * 32 + lane] = k[i];
+            }
+        }
+    }
+    cluster.sync();
+
+    // ---- 3. fp64 re-score, one survivor per warp at a time: c = crank*8 + warp + 64*j
+    const uint64_t *survivors = cluster.map_shared_rank(s_tree, 0);
+    double *r_score = cluster.map_shared_rank(s_score, 0);
+    int64_t *r_id = cluster.map_shared_rank(s_id, 0);
+    int *r_valid = cluster.map_shared_rank(s_valid, 0);
+    const float *qrow = p.queries + (size_t)qi * p.dim;
+    const int nvec = p.dim >> 2;
+    constexpr int kRB = 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    double aa = 0.0;
+    for (int v0 = lane; v0 < nvec; v0 += 32 * 2 * kRB) {
+        float4 a[2 * kRB];
+#pragma unroll
+        for (int u = 0; u < 2 * kRB; ++u) {
+            const int v = v0 + 32 * u;
+            a[u] = v < nvec ? __ldg(reinterpret_cast<const float4 *>(qrow) + v) : zero4;
+        }
+#pragma unroll
+        for (int u = 0; u < 2 * kRB; ++u) {
+            aa = __fma_rn((double)a[u].x, (double)a[u].x, aa);
+            aa = __fma_rn((double)a[u].y, (double)a[u].y, aa);
+            aa = __fma_rn((double)a[u].z, (double)a[u].z, aa);
+            aa = __fma_rn((double)a[u].w, (double)a[u].w, aa);
+        }
+    }
+    aa = warp_sum_f64(aa);
+    for (int c = (int)crank * WARPS + warp; c < KC; c += kFinCluster * WARPS) {
+        const uint64_t key = survivors[c];
+        const bool ok = key != CDR_EMPTY_KEY;
+        const size_t row = ok ? cdr_key_row(key) : 0;
+        double ab = 0.0, bb = 0.0;
+        if (ok) {
+            for (int v0 = lane; v0 < nvec; v0 += 32 * kRB) {
+                float4 a[kRB], b[kRB];
+#pragma unroll
+                for (int u = 0; u < kRB; ++u) {
+                    const int v = v0 + 32 * u;
+                    const bool in = v < nvec;
+                    b[u] = in ? load_row_vec(p.rows, p.bf16_rows, row, p.dim, v) : zero4;
+                    a[u] = in ? __ldg(reinterpret_cast<const float4 *>(qrow) + v) : zero4;
+                }
+#pragma unroll
+                for (int u = 0; u < kRB; ++u) rescore_accumulate(a[u], b[u], ab, bb);
+            }
+        }
+        ab = warp_sum_f64(ab);
+        bb = warp_sum_f64(bb);
+        if (lane == 0) {
+            if (ok) {
+                double sim = __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb)));
+                if (sim > 1.0) sim = 1.0;
+                else if (sim < -1.0) sim = -1.0;
+                const double dist = __dsub_rn(1.0, sim);
+                r_score[c] = __dsub_rn(1.0, dist);
+                r_id[c] = p.ids[row];
+                r_valid[c] = 1;
+            } else {
+                r_score[c] = 0.0; r_id[c] = -1; r_valid[c] = 0;
+            }
+        }
+    }
+    cluster.sync();
+    if (crank != 0) return;
+
+    // ---- 4. CTA 0: final order by rank counting
+    int mine = 0;
+    for (int c = threadIdx.x; c < KC; c += blockDim.x) mine += s_valid[c];
+    if (mine) atomicAdd(&s_nvalid, mine);
+    __syncthreads();
+    const int n_valid = s_nvalid;
+    for (int c = threadIdx.x; c < KC; c += blockDim.x) {
+        if (!s_valid[c]) continue;
+        const double sc = s_score[c];
+        const int64_t id = s_id[c];
+        int rank = 0;
+        for (int o = 0; o < KC; ++o) {
+            if (o != c && s_valid[o] && cdr_result_before(s_score[o], s_id[o], sc, id)) ++rank;
+        }
+        if (rank < p.k) {
+            p.out_score[(size_t)qi * p.k + rank] = sc;
+            p.out_id[(size_t)qi * p.k + rank] = id;
+        }
+    }
+    const int n_out = n_valid < p.k ? n_valid : p.k;
+    for (int c = n_out + threadIdx.x; c < p.k; c += blockDim.x) {
+        p.out_score[(size_t)qi * p.k + c] = __longlong_as_double(0x7FF8000000000000ll);
+        p.out_id[(size_t)qi * p.k + c] = -1;
+    }
+    if (threadIdx.x == 0) {
+        p.out_n[qi] = n_out;
+        if (p.reset_ctr) p.reset_ctr[qi] = 0u;
+    }
+}
+
 // one launch helper for every candidate width
 static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_t st)
 {
     // load batch kRB: 2 fits the 64-register budget of the 1024-thread variants (4 spills; measured
     // 25.5 us vs 31.6 us per launch, profiles/r01/README.md)
+    // small batches of sorted per-CTA lists (the exact lane serving single requests): 8-CTA cluster per query
+    static const bool no_cluster = [] { const char *e = getenv("CADENCE_FIN_CLUSTER"); return e && e[0] == '0'; }();
+    if (fp.counts == nullptr && nq <= 16 && !no_cluster && (kc == 64 || kc == 256)) {
+        if (kc == 64) scan_finalize_cluster_kernel<2><<<nq * kFinCluster, 256, 0, st>>>(fp);
+        else scan_finalize_cluster_kernel<8><<<nq * kFinCluster, 256, 0, st>>>(fp);
+        CDR_LAUNCH_CHECK();
+        return CDR_OK;
+    }
     if (kc == 64) scan_finalize_kernel<2, 32, 2><<<nq, 1024, 0, st>>>(fp);
     else if (kc == 128) scan_finalize_kernel<4, 32, 2><<<nq, 1024, 0, st>>>(fp);
     else if (kc == 256) scan_finalize_kernel<8, 16, 4><<<nq, 512, 0, st>>>(fp);

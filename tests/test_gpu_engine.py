@@ -191,6 +191,26 @@ def test_exact_scan_with_filters_100k(corpus_100k):
     assert count == 0 and cnt.tolist() == [0, 0, 0] and np.all(ids == -1) and np.all(np.isnan(sc))
 
 
+@pytest.mark.parametrize("k", [50, 200])
+def test_exact_scan_finalize_variants_agree(corpus_100k, k):
+    """Batches of <= 16 queries finish in the 8-CTA-cluster finalize kernel, larger ones in the one-CTA-per-query
+    kernel: same bits either way (ids, fp64 scores, counts), with and without a filter, and vs the oracle."""
+    s, x = corpus_100k
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 300, 40)
+    allow, _ = s.filter_bitmap(call_slots=list(range(0, 500, 3)))
+    for al in (None, allow):
+        big = s.search_exact(qs, k, al)                      # 40 queries: one CTA per query
+        for q0 in (0, 16, 32):                               # <= 16 queries: cluster kernel
+            small = s.search_exact(qs[q0:q0 + 16], k, al)
+            m = small[0].shape[0]
+            assert np.array_equal(small[0], big[0][q0:q0 + m]) and np.array_equal(small[2], big[2][q0:q0 + m])
+            assert np.array_equal(small[1].view(np.uint64), big[1][q0:q0 + m].view(np.uint64))
+        one = s.search_exact(qs[39], k, al)
+        assert np.array_equal(one[0][0], big[0][39]) and np.array_equal(one[1][0].view(np.uint64), big[1][39].view(np.uint64))
+    assert_matches_oracles(big[0][5], big[1][5], big[2][5], qs[5], x, k,
+                           allow=orc.rows_to_bitmap(np.isin(np.arange(x.shape[0]) // 200, np.arange(0, 500, 3))))
+
+
 @pytest.mark.parametrize("n", [1, 15, 16, 17, 2000, 2367, 4097])
 def test_exact_scan_ragged_sizes(n):
     s = make_synth_store(n)
