@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-queries", type=int, default=1024, help="batch_bf16: queries per batch (configs[2]: 1024)")
     ap.add_argument("--hnsw-rows", type=int, default=10_000, help="batch_bf16: rows of the CPU HNSW baseline's sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bf16-only", action="store_true", help="batch_bf16: keep only bf16 rows resident (C5 residency)")
@@ -248,7 +249,7 @@ def run_batch_bf16(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     rows = args.rows if args.rows != N_ROWS else 10_000_000
-    nq = 1024
+    nq = args.batch_queries
     first, count = shard_range(rows, rank, world)
     store = DenseStore("chunks", count, dim=DIM, device=local_rank, fp32=not args.bf16_only, bf16=True)
     store.append_synthetic(count, first_row=first)
@@ -298,9 +299,10 @@ def run_batch_bf16(args):
     # recall@50 of the last batch against the exact fp32 lane (same sharded corpus), 64 queries
     recall = None
     if store.has_fp32:
-        e_ids, _, _ = searcher.search(q_dev[total - 1][:64].contiguous(), TOPK, mode="exact")
-        got = out[0][:64].cpu().numpy(); want = e_ids.cpu().numpy()
-        recall = float(np.mean([len(set(got[i]) & set(want[i])) / TOPK for i in range(64)]))
+        nr = min(64, nq)
+        e_ids, _, _ = searcher.search(q_dev[total - 1][:nr].contiguous(), TOPK, mode="exact")
+        got = out[0][:nr].cpu().numpy(); want = e_ids.cpu().numpy()
+        recall = float(np.mean([len(set(got[i]) & set(want[i])) / TOPK for i in range(nr)]))
     # e2e with host buffers (pinned): H2D of the queries + D2H of the merged result every step
     q_pinned = torch.empty(q_dev.shape, dtype=torch.float32, pin_memory=True)
     q_pinned.copy_(q_dev); torch.cuda.synchronize()
@@ -356,6 +358,7 @@ def run_batch_bf16(args):
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak if achieved else None, "traffic": traffic,
                              "algorithmic_flops_per_step": flops_step_gpu,
+                             "corpus_stream_gbs": (float(count) * DIM * 2 * args.steps / (gemm_ms / 1e3) / 1e9) if gemm_ms > 0 else None,
                              "algorithmic_dram_bytes_per_step": float(count) * DIM * 2,
                              "kernel": "gemm_topk_kernel", "per": "GPU (max over ranks)",
                              "peak_source": "measured bf16_tflops_sustained (kernel timed inside a long step)",

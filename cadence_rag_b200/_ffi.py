@@ -69,6 +69,7 @@ SIGNATURES = {
     "cdr_store_create": (_i32, [ctypes.POINTER(_vp), _i32, _i64, _i32, _u32]),
     "cdr_store_destroy": (_i32, [_vp]),
     "cdr_store_append": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "cdr_store_update_embeddings": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "cdr_store_append_synthetic": (_i32, [_vp, _u64, _i64, _i64, _i64, _i32, _i64, _i64, _vp]),
     "cdr_store_finalize": (_i32, [_vp, _vp]),
     "cdr_store_info": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i32), ctypes.POINTER(_u32),

@@ -70,6 +70,7 @@ struct cdr_store {
     int64_t n_valid = 0;
     bool finalized = false;
     bool any_invalid = false;
+    int64_t last_id = INT64_MIN;   // id of the last row (host copy; maintained once the store is sealed)
 
     float *emb_f32 = nullptr;            // [capacity, dim]
     __nv_bfloat16 *emb_bf16 = nullptr;   // [capacity, dim], rows L2-normalised before rounding

@@ -12,6 +12,9 @@
 //   valid     1 bit/row                         (embedding IS NOT NULL, app/retrieve.py:318,347)
 #include "common.cuh"
 
+#include <climits>
+#include <cstring>
+
 namespace {
 
 constexpr int kPadRows = 64;   // inv_norm is over-allocated so tail tiles can copy a full tile
@@ -181,6 +184,66 @@ __global__ void check_ids_kernel(const int64_t *ids, int64_t n, unsigned long lo
     if (i + 1 < n && ids[i] >= ids[i + 1]) atomicOr(flag, 1ull);
 }
 
+// ids[i] -> row position (binary search over the strictly increasing id column), -1 when absent
+__global__ void lookup_ids_kernel(const int64_t *store_ids, int64_t n_rows, const int64_t *ids, int64_t n,
+                                  int64_t *out_rows, unsigned long long *missing)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t want = ids[i];
+    int64_t lo = 0, hi = n_rows;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (store_ids[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    const bool found = lo < n_rows && store_ids[lo] == want;
+    out_rows[i] = found ? lo : -1;
+    if (!found) atomicAdd(missing, 1ull);
+}
+
+// UPDATE ... SET embedding = :e WHERE id = :id for n rows (one warp per row): the fp32 row, its inverse
+// norm, its normalised bf16 copy and the `embedding IS NOT NULL` bit.
+__global__ void update_rows_kernel(const float *src, const int64_t *rows, int64_t n, int dim, float *emb_f32,
+                                   __nv_bfloat16 *emb_bf16, float *inv_norm, uint32_t *valid,
+                                   unsigned long long *newly_valid)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int64_t row = rows[i];
+    const float4 *r = reinterpret_cast<const float4 *>(src + i * dim);
+    const int nblk = dim >> 2;
+    float nrm2 = 0.f;
+    for (int b = lane; b < nblk; b += 32) {
+        const float4 v = r[b];
+        nrm2 = fmaf(v.x, v.x, nrm2);
+        nrm2 = fmaf(v.y, v.y, nrm2);
+        nrm2 = fmaf(v.z, v.z, nrm2);
+        nrm2 = fmaf(v.w, v.w, nrm2);
+    }
+    nrm2 = warp_sum_f32(nrm2);
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(nrm2));
+    for (int b = lane; b < nblk; b += 32) {
+        const float4 v = r[b];
+        if (emb_f32) reinterpret_cast<float4 *>(emb_f32 + row * dim)[b] = v;
+        if (emb_bf16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * inv, v.y * inv);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z * inv, v.w * inv);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            reinterpret_cast<uint2 *>(emb_bf16 + row * dim)[b] = pk;
+        }
+    }
+    if (lane == 0) {
+        inv_norm[row] = inv;
+        const uint32_t bit = 1u << (row & 31);
+        const uint32_t old = atomicOr(&valid[row >> 5], bit);
+        if (!(old & bit)) atomicAdd(newly_valid, 1ull);
+    }
+}
+
 int alloc_store(cdr_store *s)
 {
     const int64_t cap = s->capacity;
@@ -296,7 +359,6 @@ extern "C" int32_t cdr_store_append(cdr_store *s, const float *rows_f32, const i
                                     int32_t is_device, void *stream)
 {
     CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "cdr_store_append: store is NULL");
-    CDR_REQUIRE(!s->finalized, CDR_ERR_STATE, "cdr_store_append: store already finalized");
     CDR_REQUIRE(n >= 0 && rows_f32 && ids, CDR_ERR_INVALID, "cdr_store_append: rows/ids required");
     if (n == 0) return CDR_OK;
     CDR_REQUIRE(s->n_rows + n <= s->capacity, CDR_ERR_OOM,
@@ -305,6 +367,27 @@ extern "C" int32_t cdr_store_append(cdr_store *s, const float *rows_f32, const i
     DeviceGuard g(s->device);
     std::lock_guard<std::mutex> lk(s->mu);
     cudaStream_t st = (cudaStream_t)stream;
+    // A sealed store keeps serving while it grows (new chunks of an ingested call): the id order is then
+    // verified BEFORE anything is written, so a rejected batch leaves the store untouched.
+    const bool sealed = s->finalized;
+    int64_t batch_last_id = 0;
+    if (sealed) {
+        std::vector<int64_t> h_ids((size_t)n);
+        if (is_device) {
+            CDR_CUDA(cudaMemcpyAsync(h_ids.data(), ids, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            CDR_CUDA(cudaStreamSynchronize(st));
+        } else {
+            memcpy(h_ids.data(), ids, (size_t)n * 8);
+        }
+        int64_t prev = s->n_rows > 0 ? s->last_id : INT64_MIN;
+        for (int64_t i = 0; i < n; ++i) {
+            CDR_REQUIRE(h_ids[(size_t)i] > prev || (i == 0 && s->n_rows == 0), CDR_ERR_UNSORTED_IDS,
+                        "cdr_store_append: id %lld at position %lld is not above the previous id %lld "
+                        "(rows must arrive in id order)", (long long)h_ids[(size_t)i], (long long)i, (long long)prev);
+            prev = h_ids[(size_t)i];
+        }
+        batch_last_id = prev;
+    }
     const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const int64_t r0 = s->n_rows;
     const size_t d = (size_t)s->dim;
@@ -353,6 +436,78 @@ extern "C" int32_t cdr_store_append(cdr_store *s, const float *rows_f32, const i
     CDR_CUDA(cudaStreamSynchronize(st));
     if (valid_dev) cudaFree(valid_dev);
     s->n_rows += n;
+    if (sealed) {
+        unsigned long long h[2] = {0, 0};
+        CDR_CUDA(cudaMemcpy(h, s->d_scratch, sizeof(h), cudaMemcpyDeviceToHost));
+        s->n_valid = (int64_t)h[1];
+        s->any_invalid = s->n_valid != s->n_rows;
+        s->last_id = batch_last_id;
+    }
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_store_update_embeddings(cdr_store *s, const int64_t *ids_host, const float *rows_f32_host,
+                                               int64_t n, void *stream)
+{
+    CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "cdr_store_update_embeddings: store is NULL");
+    CDR_REQUIRE(s->finalized, CDR_ERR_STATE, "cdr_store_update_embeddings: store not finalized (ids are located by "
+                "binary search over the sealed id column)");
+    CDR_REQUIRE(n >= 0 && (n == 0 || (ids_host && rows_f32_host)), CDR_ERR_INVALID,
+                "cdr_store_update_embeddings: ids/rows required");
+    if (n == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    std::lock_guard<std::mutex> lk(s->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = (size_t)s->dim;
+    int64_t *d_ids = nullptr, *d_rows = nullptr;
+    float *d_src = nullptr;
+    unsigned long long *d_cnt = nullptr;    // [0] missing ids, [1] rows that turned NOT NULL
+    CDR_CUDA(cudaMalloc(&d_ids, (size_t)n * 8));
+    CDR_CUDA(cudaMalloc(&d_rows, (size_t)n * 8));
+    CDR_CUDA(cudaMalloc(&d_cnt, 16));
+    auto release = [&]() { cudaFree(d_ids); cudaFree(d_rows); cudaFree(d_cnt); cudaFree(d_src); };
+    cudaError_t e = cudaMalloc(&d_src, (size_t)n * d * 4);
+    if (e != cudaSuccess) {
+        release();
+        cdr_set_error("cdr_store_update_embeddings: staging %lld rows: %s", (long long)n, cudaGetErrorString(e));
+        return CDR_ERR_OOM;
+    }
+    unsigned long long h[2] = {0, 0};
+    e = cudaMemsetAsync(d_cnt, 0, 16, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        lookup_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->ids, s->n_rows, d_ids, n, d_rows, d_cnt);
+        g_cdr_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && h[0] != 0) {
+        release();
+        cdr_set_error("cdr_store_update_embeddings: %llu of %lld ids are not in the store; nothing was updated", h[0],
+                      (long long)n);
+        return CDR_ERR_INVALID;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, rows_f32_host, (size_t)n * d * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const int wpb = 8;
+        update_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_src, d_rows, n, s->dim, s->emb_f32,
+                                                                                  s->emb_bf16, s->inv_norm, s->valid,
+                                                                                  d_cnt + 1);
+        g_cdr_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    release();
+    if (e != cudaSuccess) {
+        cdr_set_error("cdr_store_update_embeddings: %s", cudaGetErrorString(e));
+        return CDR_ERR_CUDA;
+    }
+    s->n_valid += (int64_t)h[1];
+    s->any_invalid = s->n_valid != s->n_rows;
+    // keep the running count of NOT NULL rows (used when the sealed store grows) in step
+    CDR_CUDA(cudaMemcpy(s->d_scratch + 1, &s->n_valid, 8, cudaMemcpyHostToDevice));
     return CDR_OK;
 }
 
@@ -437,6 +592,7 @@ extern "C" int32_t cdr_store_finalize(cdr_store *s, void *stream)
                 "(load rows ORDER BY chunk_id)");
     s->n_valid = (int64_t)h[1];
     s->any_invalid = s->n_valid != s->n_rows;
+    if (s->n_rows > 0) CDR_CUDA(cudaMemcpy(&s->last_id, s->ids + (s->n_rows - 1), 8, cudaMemcpyDeviceToHost));
     s->finalized = true;
     return CDR_OK;
 }

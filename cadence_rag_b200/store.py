@@ -172,6 +172,57 @@ class DenseStore:
         if payload is not None:
             for i, row in zip(ids_np.tolist(), payload):
                 self.payload[i] = row
+        self._host_cols = None      # a sealed store may grow: drop the cached host columns / row count
+        self._rows = None
+
+    def update_embeddings(self, ids: Sequence[int], vectors) -> None:
+        """``UPDATE <table> SET embedding = CAST(:embedding AS vector(D)) WHERE <id> = :row_id`` for rows that
+        already exist (app/embedding_pipeline.py:149-168, _update_embeddings) -- the backfill of rows ingested
+        with ``embedding IS NULL``.  ``vectors``: [n, dim] floats, or the reference's ``"[...]"`` literals
+        (parsed with float32 rounding like pgvector's vector_in).  All-or-nothing: an unknown id raises and
+        nothing is updated."""
+        n = len(ids)
+        if n == 0:
+            return
+        if len(vectors) != n:
+            raise DenseEngineError(f"row/vector mismatch for {self.table_name}: {n} rows vs {len(vectors)} vectors")
+        if isinstance(vectors[0], str):
+            emb = np.zeros((n, self.dim), dtype=np.float32)
+            for i, lit in enumerate(vectors):
+                body = lit.strip()
+                if not (body.startswith("[") and body.endswith("]")):
+                    raise DenseEngineError(f"row {i}: malformed vector literal")
+                vals = np.array(body[1:-1].split(","), dtype=np.float32)
+                if vals.shape[0] != self.dim:
+                    raise DenseEngineError(f"row {i}: expected {self.dim} dimensions, not {vals.shape[0]}")
+                emb[i] = vals
+        else:
+            emb = np.ascontiguousarray(np.asarray(vectors, dtype=np.float32))
+        if tuple(emb.shape) != (n, self.dim):
+            raise DenseEngineError(f"embeddings shape {tuple(emb.shape)} != ({n}, {self.dim})")
+        ids_np = np.ascontiguousarray(np.asarray(ids, dtype=np.int64))
+        if np.unique(ids_np).size != n:
+            raise DenseEngineError("update_embeddings: ids must be distinct")
+        _ffi.check(_ffi.lib().cdr_store_update_embeddings(self.handle, _ffi.ptr(ids_np), _ffi.ptr(emb), n,
+                                                          self._stream()), "cdr_store_update_embeddings")
+
+    def pending_ids(self, limit: Optional[int] = None, call_id: Any = None) -> np.ndarray:
+        """Ids of rows whose embedding IS NULL, ascending -- the row set of _fetch_pending_rows
+        (app/embedding_pipeline.py:121-146; the text-not-empty test is the caller's, texts live in the
+        payload), optionally restricted to one call."""
+        rows = self.rows
+        valid = np.empty(rows, dtype=np.uint8)
+        if rows:
+            _ffi.check(_ffi.lib().cdr_store_read_valid(self.handle, 0, rows, _ffi.ptr(valid)), "cdr_store_read_valid")
+        cols = self.host_columns()
+        keep = valid == 0
+        if call_id is not None:
+            slot = self.slot_of_call(call_id)
+            if slot is None and self.synthetic is not None and isinstance(call_id, (int, np.integer)):
+                slot = int(call_id)
+            keep &= cols["call_slot"] == (-1 if slot is None else slot)
+        out = cols["ids"][keep]
+        return out if limit is None else out[:limit]
 
     def append_literals(self, literals: Sequence[Optional[str]], ids: Sequence[int], **columns) -> None:
         """Append rows given as pgvector text literals -- the wire format the reference writes with

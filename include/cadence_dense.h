@@ -77,6 +77,20 @@ int32_t cdr_store_append(cdr_store *s, const float *rows_f32, const int64_t *ids
                          const uint64_t *tag_bits, const uint8_t *valid_u8, int64_t n,
                          int32_t is_device, void *stream);
 
+/* A sealed (finalized) store stays live:
+ *  - cdr_store_append keeps working after cdr_store_finalize for rows whose ids continue the increasing
+ *    sequence (new chunks of a newly ingested call); the order is verified before anything is written,
+ *    so a rejected batch (CDR_ERR_UNSORTED_IDS) leaves the store untouched.
+ *  - cdr_store_update_embeddings replaces app/embedding_pipeline.py:149-168 (_update_embeddings) for rows
+ *    that already exist -- the backfill of rows ingested with `embedding IS NULL`:
+ *        UPDATE <table> SET embedding = CAST(:embedding AS vector(D)) WHERE <id> = :row_id
+ *    ids_host[n] are located by binary search on the device; rows_f32_host is [n, dim].  Each row's fp32
+ *    copy, inverse norm, normalised bf16 copy and NOT NULL bit are rewritten.  All-or-nothing: if any id
+ *    is unknown the call fails with CDR_ERR_INVALID and nothing is updated.  Ids must be distinct.
+ * Both synchronise `stream`; searches issued afterwards on that stream see the new rows. */
+int32_t cdr_store_update_embeddings(cdr_store *s, const int64_t *ids_host, const float *rows_f32_host,
+                                    int64_t n, void *stream);
+
 /* Append n synthetic rows generated on the device (global rows first_row..first_row+n-1 of the
  * counter-based corpus specified in oracle/synth_ref.c).  id = id_base + global
  * row, call_slot = global_row / rows_per_call, started_at = t0_us + call_slot * call_period_us,

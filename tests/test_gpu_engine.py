@@ -582,6 +582,74 @@ def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
         store.hybrid_retrieve(qs[:, :8], 50)
 
 
+def test_live_store_backfill_and_growth(monkeypatch):
+    """rows ingested with `embedding IS NULL` are invisible to the dense lane until the backfill
+    (`UPDATE ... SET embedding`, app/embedding_pipeline.py:149-168) fills them in place; a sealed store keeps
+    growing in id order.  After both, every lane answers exactly like a store built in one go."""
+    from cadence_rag_b200 import embedding_pipeline
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    n, n2, k = 3000, 500, 50
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n + n2)
+    ids = np.arange(1, n + n2 + 1, dtype=np.int64) * 3
+    call_ids = [f"call-{r // 100}" for r in range(n + n2)]
+    rng = np.random.default_rng(5)
+    null_rows = np.sort(rng.choice(n, 400, replace=False))
+    valid = np.ones(n, dtype=bool); valid[null_rows] = False
+    texts = [{"text": f"chunk text {r}"} for r in range(n + n2)]
+    texts[int(null_rows[0])] = {"text": "   "}                    # blank text: never pending (length(trim(text)) > 0)
+    live = DenseStore("chunks", n + n2, dim=1024, device=0)
+    live.append(x[:n], ids=ids[:n], call_ids=call_ids[:n], valid=valid, payload=texts[:n])
+    live.finalize()
+    assert live.info()["n_valid"] == n - 400
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 50, 4)
+    got = live.search_exact(qs, k)
+    for i in range(4):
+        assert_matches_oracles(got[0][i], got[1][i], got[2][i], qs[i], x[:n], k, allow=orc.rows_to_bitmap(valid), row_ids=ids[:n])
+    # pending set == rows WHERE embedding IS NULL (optionally of one call), ascending
+    assert live.pending_ids().tolist() == ids[null_rows].tolist()
+    assert live.pending_ids(5).tolist() == ids[null_rows[:5]].tolist()
+    assert live.pending_ids(call_id="call-3").tolist() == [int(ids[r]) for r in null_rows if r // 100 == 3]
+    # all-or-nothing update; distinct ids; literal form
+    with pytest.raises(DenseEngineError):
+        live.update_embeddings([int(ids[null_rows[1]]), 7], x[[null_rows[1], 0]])       # id 7 does not exist
+    assert live.info()["n_valid"] == n - 400
+    with pytest.raises(DenseEngineError):
+        live.update_embeddings([3, 3], x[[0, 0]])
+    live.update_embeddings([int(ids[null_rows[1]])], [retrieve._vector_literal(x[null_rows[1]].tolist())])
+    assert live.info()["n_valid"] == n - 399
+    # the reference's backfill loop over the store, embedder = the true row vectors
+    row_of_text = {texts[r]["text"]: r for r in range(n + n2)}
+    embeddings.set_embedder(lambda batch: embeddings.EmbeddingResult(vectors=[x[row_of_text[t]].tolist() for t in batch], model="rows"))
+    try:
+        summary = embedding_pipeline.run_embedding_backfill([live], batch_size=64)
+    finally:
+        embeddings.set_embedder(None)
+    assert summary.rows_updated == 398 and summary.per_table == {"chunks": 398} and summary.model_used == "rows"
+    assert summary.calls_touched == len({r // 100 for r in null_rows[2:]})
+    assert live.pending_ids().tolist() == [int(ids[null_rows[0]])] and live.info()["n_valid"] == n - 1
+    # growth of the sealed store: in id order only, rejected batches change nothing
+    with pytest.raises(DenseEngineError) as err:
+        live.append(x[n:n + 2], ids=[int(ids[n - 1]), int(ids[n])], call_ids=call_ids[n:n + 2])
+    assert err.value.code == _ffi.CDR_ERR_UNSORTED_IDS and live.rows == n
+    live.append(x[n:], ids=ids[n:], call_ids=call_ids[n:], payload=texts[n:])
+    assert live.rows == n + n2 and live.info()["n_valid"] == n + n2 - 1
+    # == a store built in one go (bitwise), on both lanes
+    valid_all = np.ones(n + n2, dtype=bool); valid_all[null_rows[0]] = False
+    whole = DenseStore("chunks", n + n2, dim=1024, device=0)
+    whole.append(x, ids=ids, call_ids=call_ids, valid=valid_all)
+    whole.finalize()
+    a, b = live.search_exact(qs, k), whole.search_exact(qs, k)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64)) and np.array_equal(a[2], b[2])
+    for i in range(4):
+        assert_matches_oracles(a[0][i], a[1][i], a[2][i], qs[i], x, k, allow=orc.rows_to_bitmap(valid_all), row_ids=ids)
+    a, b = live.search_batch(qs, k), whole.search_batch(qs, k)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
+    assert np.array_equal(live.read_rows(0, n + n2, ("bf16",))["bf16"][valid_all], whole.read_rows(0, n + n2, ("bf16",))["bf16"][valid_all])
+    allow, cnt = live.filter_bitmap(call_slots=[live.slot_of_call("call-3"), live.slot_of_call("call-31")])
+    assert cnt == 200 - int(valid_all[300:400].size - valid_all[300:400].sum())
+    live.close(); whole.close()
+
+
 # =================================================================== full size (BASELINE C2): 1M x 1024
 @pytest.fixture(scope="module")
 def corpus_1m():
