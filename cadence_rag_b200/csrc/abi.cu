@@ -34,6 +34,51 @@ extern "C" int32_t cdr_device_count(int32_t *out_count)
     return CDR_OK;
 }
 
+// ---------------------------------------------------------------------------- per-thread pinned staging
+namespace {
+struct PinnedStage {
+    void *p = nullptr;
+    size_t n = 0;
+};
+thread_local PinnedStage t_stage;   // deliberately not freed at thread exit (the CUDA context may be gone by then)
+}  // namespace
+
+void *cdr_thread_pinned(size_t need)
+{
+    if (t_stage.n >= need && t_stage.p) return t_stage.p;
+    if (t_stage.p) cudaFreeHost(t_stage.p);      // the thread's previous call has synchronised: not in use
+    t_stage.p = nullptr;
+    t_stage.n = 0;
+    const size_t sz = need < 65536 ? 65536 : need * 2;
+    cudaError_t e = cudaHostAlloc(&t_stage.p, sz, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cdr_set_error("cudaHostAlloc(%zu) for request staging failed: %s", sz, cudaGetErrorString(e));
+        t_stage.p = nullptr;
+        return nullptr;
+    }
+    t_stage.n = sz;
+    return t_stage.p;
+}
+
+void *cdr_thread_device(int device, size_t need)
+{
+    thread_local std::map<int, PinnedStage> t_dev;      // same bookkeeping, device memory
+    PinnedStage &b = t_dev[device];
+    if (b.n >= need && b.p) return b.p;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.n = 0;
+    const size_t sz = need < 65536 ? 65536 : need + need / 2;
+    cudaError_t e = cudaMalloc(&b.p, sz);
+    if (e != cudaSuccess) {
+        cdr_set_error("cudaMalloc(%zu) for request staging failed: %s", sz, cudaGetErrorString(e));
+        b.p = nullptr;
+        return nullptr;
+    }
+    b.n = sz;
+    return b.p;
+}
+
 // ---------------------------------------------------------------------------- profiling
 // When enabled, every launch of a dominant kernel (kind 0 = K1 exact scan, 1 = K2 batched
 // bf16 GEMM) is bracketed by CUDA events recorded on the launching stream; cdr_prof_read
@@ -173,35 +218,27 @@ static int32_t search_host(const char *name, search_fn fn, cdr_store *s, const f
     if (nq == 0) return CDR_OK;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    float *qd = nullptr;
-    unsigned char *od = nullptr, *hp = nullptr;
+    unsigned char *hp = nullptr;
     const size_t qb = (size_t)nq * s->dim * 4;
     const size_t sb = (size_t)nq * k * 8, ib = (size_t)nq * k * 8, nb = (size_t)nq * 4;
     const size_t qb_al = (qb + 255) & ~(size_t)255;
-    {
-        std::lock_guard<std::mutex> lk(s->mu);
-        ScanWorkspace &ws = s->ws[st];
-        if (cdr_ws_reserve((void **)&ws.q_stage, &ws.q_stage_bytes, qb) != CDR_OK) return CDR_ERR_OOM;
-        if (cdr_ws_reserve(&ws.out_stage, &ws.out_stage_bytes, sb + ib + nb + 512) != CDR_OK) return CDR_ERR_OOM;
-        // pinned mirror of the request / response: one H2D and one D2H DMA per call instead of
-        // driver-staged copies from / to pageable caller memory
-        const size_t need = qb_al + sb + ib + nb;
-        if (ws.hyb_host_bytes < need) {
-            if (ws.hyb_host) { cudaStreamSynchronize(st); cudaFreeHost(ws.hyb_host); ws.hyb_host = nullptr; ws.hyb_host_bytes = 0; }
-            const size_t sz = need < 65536 ? 65536 : need * 2;
-            CDR_CUDA(cudaHostAlloc(&ws.hyb_host, sz, cudaHostAllocDefault));
-            ws.hyb_host_bytes = sz;
-        }
-        qd = ws.q_stage;
-        od = (unsigned char *)ws.out_stage;
-        hp = (unsigned char *)ws.hyb_host;
+    // this thread's device staging: [queries | scores | ids | counts]
+    unsigned char *dstage = (unsigned char *)cdr_thread_device(s->device, qb_al + sb + ib + nb + 256);
+    if (!dstage) return CDR_ERR_OOM;
+    float *qd = (float *)dstage;
+    unsigned char *od = dstage + qb_al;
+    // small requests (the per-request case: one query, 4 KB) go through this thread's pinned mirror: one
+    // H2D and one D2H DMA per call instead of driver-staged copies from / to pageable caller memory; large
+    // batches are copied straight from / to the caller's buffers (a pinned caller buffer then DMAs without
+    // a host memcpy)
+    const bool staged = qb <= ((size_t)256 << 10);
+    if (staged) {
+        hp = (unsigned char *)cdr_thread_pinned(qb_al + sb + ib + nb);
+        if (!hp) return CDR_ERR_OOM;
     }
     double *sd = (double *)od;
     int64_t *idd = (int64_t *)(od + sb);
     int32_t *nd = (int32_t *)(od + sb + ib);
-    // small requests (the per-request case: one query, 4 KB) go through the pinned mirror; large batches are
-    // copied straight from / to the caller's buffers (a pinned caller buffer then DMAs without a host memcpy)
-    const bool staged = qb <= ((size_t)256 << 10);
     if (staged) memcpy(hp, q_host, qb);
     CDR_CUDA(cudaMemcpyAsync(qd, staged ? (const void *)hp : (const void *)q_host, qb, cudaMemcpyHostToDevice, st));
     rc = fn(s, qd, nq, k, allow_dev, sd, idd, nd, stream);

@@ -48,17 +48,17 @@ struct ScanWorkspace {
     size_t cta_keys_bytes = 0;
     unsigned int *tile_ctr = nullptr;   // [nq_cap] K1 work-stealing counters (zero between launches)
     size_t tile_ctr_bytes = 0;
-    float *q_stage = nullptr;       // [nq_cap, dim] fp32 staging for the *_host entry points
-    size_t q_stage_bytes = 0;
-    void *out_stage = nullptr;      // result staging for the *_host entry points
-    size_t out_stage_bytes = 0;
     void *gemm_ws = nullptr;        // K2 candidate lists, thresholds, bf16 queries
     size_t gemm_ws_bytes = 0;
-    void *hyb_dev = nullptr;        // fused /retrieve call: device copy of the packed request + results
-    size_t hyb_dev_bytes = 0;
-    void *hyb_host = nullptr;       // ... and its pinned host mirror (one H2D + one D2H per request)
-    size_t hyb_host_bytes = 0;
 };
+
+// Request / response staging of the calling THREAD for the *_host entry points: a pinned host mirror and a
+// device buffer per (thread, device), so concurrent requests never share staging even when they share a
+// stream (the kernels' own workspaces above are per stream and protected by stream order + the store lock).
+// Both return nullptr (error text set) when the allocation fails; grown on demand -- the thread's previous
+// call has synchronised by then -- and kept for the thread's life.
+void *cdr_thread_pinned(size_t need);
+void *cdr_thread_device(int device, size_t need);
 
 struct cdr_store {
     int device = 0;

@@ -163,17 +163,13 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
     const size_t x_loff = up16(x_lids + ((size_t)bm25_total + (size_t)nq * (tech_limit + dense_k) + 1) * 8);
     const size_t x_end = up16(x_loff + ((size_t)nq * L + 1) * 4);
 
-    std::lock_guard<std::mutex> lk(s->mu);
+    // request / response mirrors in this thread's pinned + device staging.  The store lock is held while the
+    // work is ENQUEUED only (the kernels' workspaces are per stream).
+    unsigned char *h = (unsigned char *)cdr_thread_pinned(o_end);
+    unsigned char *d = (unsigned char *)cdr_thread_device(s->device, x_end);
+    if (!h || !d) return CDR_ERR_OOM;
+    std::unique_lock<std::mutex> lk(s->mu);
     ScanWorkspace &ws = s->ws[st];
-    if (cdr_ws_reserve(&ws.hyb_dev, &ws.hyb_dev_bytes, x_end) != CDR_OK) return CDR_ERR_OOM;
-    if (ws.hyb_host_bytes < o_end) {
-        if (ws.hyb_host) { cudaStreamSynchronize(st); cudaFreeHost(ws.hyb_host); ws.hyb_host = nullptr; ws.hyb_host_bytes = 0; }
-        const size_t sz = o_end < 65536 ? 65536 : o_end * 2;
-        CDR_CUDA(cudaHostAlloc(&ws.hyb_host, sz, cudaHostAllocDefault));
-        ws.hyb_host_bytes = sz;
-    }
-    unsigned char *h = (unsigned char *)ws.hyb_host;
-    unsigned char *d = (unsigned char *)ws.hyb_dev;
 
     if (dense) memcpy(h + in_q, q_host, (size_t)nq * dim * 4);
     if (tech) {
@@ -246,12 +242,14 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
     if (rc != CDR_OK) return rc;
 
     CDR_CUDA(cudaMemcpyAsync(h + o_cnt, d + o_cnt, o_end - o_cnt, cudaMemcpyDeviceToHost, st));
+    const int64_t n_valid_now = s->n_valid;
+    lk.unlock();
     CDR_CUDA(cudaStreamSynchronize(st));
 
     if (out_count_host) {
         unsigned long long c;
         memcpy(&c, h + o_cnt, 8);
-        *out_count_host = has_filter ? (int64_t)c : s->n_valid;
+        *out_count_host = has_filter ? (int64_t)c : n_valid_now;
     }
     if (dense) {
         memcpy(out_dense_ids_host, h + o_did, (size_t)nq * dense_k * 8);

@@ -268,11 +268,7 @@ void free_ws(ScanWorkspace &w)
 {
     cudaFree(w.cta_keys);
     cudaFree(w.tile_ctr);
-    cudaFree(w.q_stage);
-    cudaFree(w.out_stage);
     cudaFree(w.gemm_ws);
-    cudaFree(w.hyb_dev);
-    if (w.hyb_host) cudaFreeHost(w.hyb_host);
     w = ScanWorkspace();
 }
 

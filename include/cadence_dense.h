@@ -20,6 +20,11 @@
  *     0006_add_artifact_chunks.py:22) and MUST be appended in strictly increasing order
  *     (the order `SELECT ... ORDER BY chunk_id` yields), so that "ties broken by chunk_id"
  *     equals "ties broken by row".
+ *   - threading: entry points are re-entrant.  A store's kernel workspaces are per stream; calls that share a
+ *     stream are serialised by stream order (the store lock is held while work is enqueued), calls on different
+ *     streams overlap on the device.  The *_host entry points stage requests and responses in per-thread pinned
+ *     and device buffers, so concurrent requests never share staging.  Mutating calls (append, update, finalize)
+ *     take the same lock; searches issued after they return see the new rows.
  *   - ordering of every dense result: score descending, NaN scores last (a zero-norm vector
  *     gives a NaN cosine distance in pgvector, which PostgreSQL sorts last), ties by id
  *     ascending.  Fewer survivors than k => short list (SQL LIMIT semantics).

@@ -582,6 +582,50 @@ def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
         store.hybrid_retrieve(qs[:, :8], 50)
 
 
+def test_concurrent_requests_from_threads(hybrid_engine):
+    """The reference serves /retrieve from <= 40 threadpool threads (app/main.py:184-186).  Requests issued
+    concurrently from threads -- sharing the default stream or on a stream of their own, through the host
+    entry points, the device entry point and the fused hybrid call -- return what they return serially."""
+    import threading
+    eng, meta = hybrid_engine
+    store = eng.stores["chunks"]; dev_index = eng.device_tech_indexes["chunks"]
+    nthreads, per = 8, 12
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 900, nthreads * per)
+    tok, nt = dev_index.encode_tokens([[f"TOK-{i % 7}", f"TOK-{i % 11}"] for i in range(nthreads * per)])
+    spec = dict(call_slots=list(range(5, 70)), date_from=None, date_to=None, tag_mask=None)
+    allow, _ = store.filter_bitmap(**spec)
+    want_exact = store.search_exact(qs, 50, allow)
+    want_h = store.hybrid_retrieve(qs, 50, tech_index=dev_index, token_ids=tok, n_tokens=nt, filter_spec=spec)
+    errors = []
+
+    def worker(t):
+        try:
+            own_stream = torch.cuda.Stream() if t % 2 else None
+            ctx = torch.cuda.stream(own_stream) if own_stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+            with ctx:
+                for j in range(per):
+                    i = t * per + j
+                    a = store.search_exact(qs[i], 50, allow)                                   # host entry point
+                    assert np.array_equal(a[0][0], want_exact[0][i]) and np.array_equal(a[1][0].view(np.uint64), want_exact[1][i].view(np.uint64))
+                    b = store.search_exact(torch.from_numpy(qs[i:i + 1]).cuda(), 50, allow)      # device entry point
+                    torch.cuda.current_stream().synchronize()
+                    assert np.array_equal(b[0].cpu().numpy()[0], want_exact[0][i])
+                    h = store.hybrid_retrieve(qs[i], 50, tech_index=dev_index, token_ids=tok[i:i + 1], n_tokens=nt[i:i + 1], filter_spec=spec)
+                    m = int(h["fused_n"][0])
+                    assert m == int(want_h["fused_n"][i]) and h["count"] == want_h["count"]
+                    assert np.array_equal(h["fused_ids"][0, :m], want_h["fused_ids"][i, :m])
+                    assert np.array_equal(h["fused_scores"][0, :m].view(np.uint64), want_h["fused_scores"][i, :m].view(np.uint64))
+        except Exception as exc:   # noqa: BLE001 - reported below
+            errors.append((t, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+
 def test_live_store_backfill_and_growth(monkeypatch):
     """rows ingested with `embedding IS NULL` are invisible to the dense lane until the backfill
     (`UPDATE ... SET embedding`, app/embedding_pipeline.py:149-168) fills them in place; a sealed store keeps
