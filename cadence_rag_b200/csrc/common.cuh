@@ -46,6 +46,8 @@ extern std::atomic<int64_t> g_cdr_launches;
 struct ScanWorkspace {
     uint64_t *cta_keys = nullptr;   // [nq_cap, grid, KC] packed candidate keys from K1
     size_t cta_keys_bytes = 0;
+    uint32_t *row_list = nullptr;       // K1 selective filters: compact list of allowed rows (+ count behind it)
+    size_t row_list_bytes = 0;
     unsigned int *tile_ctr = nullptr;   // [nq_cap] K1 work-stealing counters (zero between launches)
     size_t tile_ctr_bytes = 0;
     void *gemm_ws = nullptr;        // K2 candidate lists, thresholds, bf16 queries

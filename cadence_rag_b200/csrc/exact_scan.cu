@@ -41,6 +41,15 @@ struct ScanParams {
     int64_t n_tiles;
     int n_stages;
     unsigned int *tile_ctr;   // [nq] zero on entry (reset by the finalize kernel); nullptr = static tile assignment
+    // selective filters (see launch_scan_t): the allowed rows as a compact list + their count on the device.
+    //   row_list != nullptr : GATHER launch -- scans list entries [0, *list_count); does nothing when the
+    //                         count exceeds list_cap (the list is then truncated and the full scan serves)
+    //   row_list == nullptr && list_count != nullptr : FULL launch that does nothing when the gather launch serves
+    const uint32_t *row_list;
+    const unsigned int *list_count;
+    uint32_t list_cap;
+    int lists_per_query;      // per-query stride of cta_keys in lists (gather CTAs + full CTAs)
+    int list_offset;          // first list of this launch inside a query's block
 };
 
 // Dynamic shared memory carve-up (computed identically on host and device).
@@ -83,6 +92,22 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.y;
     const int64_t G = gridDim.x;
+    const bool gather = p.row_list != nullptr;
+    int64_t n_tiles = p.n_tiles;
+    uint32_t n_listed = 0;
+    if (p.list_count != nullptr) {
+        n_listed = *p.list_count;                     // written by compact_allow_kernel earlier on the stream
+        const bool list_serves = n_listed <= p.list_cap;
+        if (gather != list_serves) {                  // the other launch of the pair does the work: empty lists
+            if (warp == 0) {
+                uint64_t *out = p.cta_keys + ((size_t)qi * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = CDR_EMPTY_KEY;
+            }
+            return;
+        }
+        if (gather) n_tiles = ((int64_t)n_listed + TR - 1) / TR;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -112,12 +137,27 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                 // draw the next tile now: the atomic's round trip overlaps the wait for a free stage
                 if (dynamic && i + 1 >= S) next_dyn = (int64_t)S * G + atomicAdd(&p.tile_ctr[qi], 1u);
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                if (tile >= p.n_tiles) {
+                if (tile >= n_tiles) {
                     stage_tile[s] = -1;
                     mbar_arrive(&full_bar[s]);
                     break;
                 }
                 stage_tile[s] = tile;
+                if (gather) {
+                    // one 1-D bulk copy per listed row (DIM*4 bytes each) into the same tile layout
+                    const int64_t e0 = tile * TR;
+                    int nr = (int)((int64_t)n_listed - e0 < TR ? (int64_t)n_listed - e0 : TR);
+                    uint32_t rws[TR];
+#pragma unroll
+                    for (int r = 0; r < TR; ++r) rws[r] = r < nr ? __ldg(&p.row_list[e0 + r]) : 0u;
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nr * DIM * 4));
+#pragma unroll
+                    for (int r = 0; r < TR; ++r)
+                        if (r < nr)
+                            bulk_g2s(tiles + (size_t)s * L::kTileBytes + (size_t)r * DIM * 4,
+                                     p.rows + (size_t)rws[r] * DIM, (uint32_t)(DIM * 4), &full_bar[s]);
+                    continue;
+                }
                 const int64_t row0 = tile * TR;
                 int64_t nr = p.n_rows - row0;
                 if (nr > TR) nr = TR;
@@ -154,10 +194,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
             mbar_wait(&full_bar[s], ph);
             const int64_t tile = stage_tile[s];
             if (tile < 0) break;
-            const int64_t row0 = tile * TR + warp * RPW;
+            const int64_t row0 = tile * TR + warp * RPW;   // gather: first LIST ENTRY of this warp
             // filter bits for this warp's rows (consumed after the dot products, so the load overlaps them)
             uint32_t allow_bits = 0xFFFFFFFFu;
-            if (p.allow != nullptr) {
+            uint32_t g_row[RPW];                            // gather: the rows behind the list entries
+            float g_inv[RPW];
+            if (gather) {
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const bool in = row0 + r < (int64_t)n_listed;
+                    g_row[r] = in ? __ldg(&p.row_list[row0 + r]) : 0u;
+                    g_inv[r] = __ldg(&p.inv_norm[g_row[r]]);
+                    if (!in) allow_bits &= ~(1u << r);
+                }
+            } else if (p.allow != nullptr) {
                 // RPW <= 2 consecutive rows never straddle a 32-bit word (row0 is even when RPW==2)
                 const uint32_t w = (row0 < p.n_rows) ? __ldg(&p.allow[row0 >> 5]) : 0u;
                 allow_bits = w >> (row0 & 31);
@@ -185,7 +235,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
             }
             float inv_n[RPW];
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) inv_n[r] = mv[r];
+            for (int r = 0; r < RPW; ++r) inv_n[r] = gather ? g_inv[r] : mv[r];
             // all reads of this stage are done (values are in registers): release it early
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -193,7 +243,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
                 const float dot = warp_sum_f32(acc[r][0] + acc[r][1]);
-                const int64_t row = row0 + r;
+                const int64_t row = gather ? (int64_t)g_row[r] : row0 + r;
                 const bool ok = (row < p.n_rows) && ((allow_bits >> r) & 1u);
                 if (ok) {
                     const float score = dot * inv_n[r] * inv_qn;
@@ -224,9 +274,44 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
             }
         }
         if (warp == 0) {
-            uint64_t *out = p.cta_keys + ((size_t)qi * G + blockIdx.x) * KC;
+            uint64_t *out = p.cta_keys + ((size_t)qi * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
 #pragma unroll
             for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
+        }
+    }
+}
+
+// Allowed rows of a filter bitmap as a compact list (any order: candidate keys carry the row, so the
+// result does not depend on it) + their exact count.  One warp per 32 words; one atomic per warp-iteration.
+__global__ void __launch_bounds__(256) compact_allow_kernel(const uint32_t *allow, int64_t n_rows, uint32_t *list,
+                                                            uint32_t cap, unsigned int *count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t words = (n_rows + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w0 = warp0 * 32; w0 < words; w0 += nwarps * 32) {
+        const int64_t w = w0 + lane;
+        uint32_t bits = w < words ? allow[w] : 0u;
+        if (w == words - 1 && (n_rows & 31)) bits &= (1u << (n_rows & 31)) - 1u;   // caller bitmaps may carry tail bits
+        const int c = __popc(bits);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(count, (unsigned int)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned int pos = base + (unsigned int)(incl - c);
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pos < cap) list[pos] = (uint32_t)((w << 5) + b);
+            ++pos;
         }
     }
 }
@@ -684,7 +769,33 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     int grid = (int)(n_tiles < s->sm_count ? n_tiles : s->sm_count);
     if (grid < 1) grid = 1;
 
-    const size_t need = (size_t)nq * grid * KC * sizeof(uint64_t);
+    // Selective filters.  The reference's planner sends small scoped candidate sets (<= 2 000 rows by default,
+    // app/retrieve.py:277-287) to the exact lane; scanning the whole table for them wastes the bus.  For a
+    // caller-supplied bitmap the allowed rows are compacted into a list (one pass over n_rows/8 bytes) and a
+    // GATHER launch scans only those rows when there are at most n_rows/16 of them; otherwise it exits at once
+    // and the full scan below serves.  The decision is taken on the device (no host round trip); the skipped
+    // launch writes empty candidate lists.  Same per-row arithmetic => identical results either way.
+    static const bool k1_nogather = [] { const char *e = getenv("CADENCE_K1_GATHER"); return e && e[0] == '0'; }();
+    int g_gather = 0;
+    uint32_t list_cap = 0;
+    if (allow != nullptr && allow != s->valid && !k1_nogather && s->n_rows >= 4 * L::TR) {
+        int64_t cap = s->n_rows / 16;
+        if (cap < L::TR) cap = L::TR;
+        list_cap = (uint32_t)cap;
+        const int64_t gt = (cap + L::TR - 1) / L::TR;
+        g_gather = (int)(gt < s->sm_count ? gt : s->sm_count);
+        if (cdr_ws_reserve((void **)&ws.row_list, &ws.row_list_bytes, (size_t)cap * 4 + 16) != CDR_OK) return CDR_ERR_OOM;
+        unsigned int *cnt = reinterpret_cast<unsigned int *>(ws.row_list) + cap;      // the count lives behind the list
+        CDR_CUDA(cudaMemsetAsync(cnt, 0, 4, st));
+        const int64_t words = (s->n_rows + 31) / 32;
+        int64_t blocks = (words + 255) / 256;
+        if (blocks > (int64_t)s->sm_count * 4) blocks = (int64_t)s->sm_count * 4;
+        compact_allow_kernel<<<(unsigned)blocks, 256, 0, st>>>(allow, s->n_rows, ws.row_list, list_cap, cnt);
+        CDR_LAUNCH_CHECK();
+    }
+    const int g_total = g_gather + grid;
+
+    const size_t need = (size_t)nq * g_total * KC * sizeof(uint64_t);
     if (cdr_ws_reserve((void **)&ws.cta_keys, &ws.cta_keys_bytes, need) != CDR_OK) return CDR_ERR_OOM;
     // work-stealing counters: zeroed when (re)allocated, re-zeroed by every finalize launch
     static const bool k1_static = [] { const char *e = getenv("CADENCE_K1_SCHED"); return e && e[0] == 's'; }();
@@ -703,15 +814,30 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     sp.n_tiles = n_tiles;
     sp.n_stages = stages;
     sp.tile_ctr = k1_static ? nullptr : ws.tile_ctr;
+    sp.row_list = nullptr;
+    sp.list_count = nullptr;
+    sp.list_cap = list_cap;
+    sp.lists_per_query = g_total;
+    sp.list_offset = 0;
 
     cdr_prof_mark_begin(0, st);
+    if (g_gather > 0) {
+        ScanParams gp = sp;
+        gp.row_list = ws.row_list;
+        gp.list_count = reinterpret_cast<unsigned int *>(ws.row_list) + list_cap;
+        gp.allow = nullptr;
+        exact_scan_kernel<J, RPW, NPL><<<dim3(g_gather, nq), kScanThreads, smem, st>>>(gp);
+        CDR_LAUNCH_CHECK();
+        sp.list_count = gp.list_count;
+        sp.list_offset = g_gather;
+    }
     exact_scan_kernel<J, RPW, NPL><<<dim3(grid, nq), kScanThreads, smem, st>>>(sp);
     CDR_LAUNCH_CHECK();
     cdr_prof_mark_end(0, st);
 
     FinalizeParams fp;
     fp.lists = ws.cta_keys;
-    fp.n_lists = grid;
+    fp.n_lists = g_total;
     fp.counts = nullptr;
     fp.cap = 0;
     fp.rows = s->emb_f32;

@@ -268,6 +268,7 @@ void free_ws(ScanWorkspace &w)
 {
     cudaFree(w.cta_keys);
     cudaFree(w.tile_ctr);
+    cudaFree(w.row_list);
     cudaFree(w.gemm_ws);
     w = ScanWorkspace();
 }
