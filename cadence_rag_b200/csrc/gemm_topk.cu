@@ -733,7 +733,11 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     // KC-th best of the rows seen so far, a segment of g x seen rows appends ~ g*KC keys per query
     // (cap = 32*KC leaves an 8x margin over the expectation at g = 4).  Smaller g = fewer appends
     // (total ~ KC * g * log_{1+g}(N/4096) per query) but more launches; g = 4 gives 7 segments at 10M rows.
-    constexpr int64_t kSegGrowth = 4;
+    static const int64_t kSegGrowth = [] {           // CADENCE_K2_GROWTH: A/B aid (2..12), default 4
+        const char *e = getenv("CADENCE_K2_GROWTH");
+        const int v = e ? atoi(e) : 4;
+        return (int64_t)((v >= 1 && v <= 12) ? v : 4);
+    }();
     int64_t begin = 0;
     while (begin < p.n_tiles_total) {
         int64_t end = begin == 0 ? 16 : begin + kSegGrowth * begin;

@@ -9,6 +9,7 @@ or a tensor:
   _estimate_dense_candidates   app/retrieve.py:303-323   exact COUNT(*) -> K6 popcount
   _dense_has_scoping           app/retrieve.py:267-274
   _choose_dense_mode           app/retrieve.py:277-287
+  _configure_dense_session     app/retrieve.py:290-300
   _fetch_chunks_dense          app/retrieve.py:326-354   SQL ORDER BY <=> LIMIT -> K1 / K2
   _fetch_artifacts_dense       app/retrieve.py:357-389
   _fetch_chunks_tech / _fetch_artifacts_tech   app/retrieve.py:183-242 (host inverted index)
@@ -60,6 +61,7 @@ class DenseConnection:
     def __init__(self, engine: "DenseEngine"):
         self.engine = engine
         self._bitmaps: Dict[Tuple, Tuple[Any, int]] = {}
+        self.session: Dict[str, Any] = {}       # what _configure_dense_session last set (SET LOCAL ... in the reference)
 
     def __enter__(self):
         return self
@@ -165,6 +167,20 @@ def _choose_dense_mode(estimated_rows: int, filters: Optional[RetrieveFilters],
     return "ann"
 
 
+def _configure_dense_session(conn: "DenseConnection", mode: str) -> None:
+    """app/retrieve.py:290-300.  The reference steers the Postgres planner per statement: mode "exact" turns
+    index scans off (forced sequential scan), mode "ann" turns them on and sets hnsw.iterative_scan /
+    hnsw.ef_search.  Here the mode selects the lane -- "exact": the fp32 HBM-bound scan; "ann": the batched
+    bf16 tensor-core lane is PERMITTED (a single query is still answered exactly whenever fp32 rows are
+    resident) -- and the same settings are recorded on the connection for the debug / notes payload."""
+    if mode == "ann":
+        conn.session = {"mode": "ann", "enable_indexscan": "on", "enable_bitmapscan": "on",
+                        "hnsw.iterative_scan": "relaxed_order",
+                        "hnsw.ef_search": max(1, int(settings.embeddings_hnsw_ef_search))}
+        return
+    conn.session = {"mode": "exact", "enable_indexscan": "off", "enable_bitmapscan": "off"}
+
+
 # --------------------------------------------------------------------------- filters -> bitmap
 def _filter_spec(store: DenseStore, filters: Optional[RetrieveFilters],
                  call_ids: Optional[Sequence[Any]]) -> Dict[str, Any]:
@@ -228,6 +244,7 @@ def _rows_from_hits(store: DenseStore, ids: np.ndarray, scores: np.ndarray) -> L
 
 def _fetch_dense(conn: DenseConnection, table_name: str, query_embedding, filters, call_ids,
                  mode: str, limit: int) -> List[Dict[str, Any]]:
+    _configure_dense_session(conn, mode)
     store = conn.store(table_name)
     if limit <= 0:
         return []

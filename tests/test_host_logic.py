@@ -60,6 +60,22 @@ def test_choose_dense_mode_exact_when_no_candidates(monkeypatch):
     assert _choose_dense_mode(estimated_rows=0, filters=None, call_ids=None) == "exact"
 
 
+def test_configure_dense_session_records_reference_settings(monkeypatch):
+    """app/retrieve.py:290-300: "ann" -> index scans on, relaxed_order, ef_search = max(1, int(setting));
+    anything else -> index scans off."""
+    from cadence_rag_b200.retrieve import DenseConnection, DenseEngine, _configure_dense_session
+    conn = DenseConnection(DenseEngine())
+    monkeypatch.setattr(settings, "embeddings_hnsw_ef_search", 80)
+    _configure_dense_session(conn, "ann")
+    assert conn.session == {"mode": "ann", "enable_indexscan": "on", "enable_bitmapscan": "on",
+                            "hnsw.iterative_scan": "relaxed_order", "hnsw.ef_search": 80}
+    monkeypatch.setattr(settings, "embeddings_hnsw_ef_search", 0)
+    _configure_dense_session(conn, "ann")
+    assert conn.session["hnsw.ef_search"] == 1
+    _configure_dense_session(conn, "exact")
+    assert conn.session == {"mode": "exact", "enable_indexscan": "off", "enable_bitmapscan": "off"}
+
+
 def test_planner_matches_reference_golden_table(pure, monkeypatch):
     now = datetime(2026, 2, 9, tzinfo=timezone.utc)
     for case in pure["planner"]:
