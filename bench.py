@@ -594,6 +594,27 @@ def main():
         launches_total, k_ms_max = int(launches), k_ms.value
     value = args.steps * Q / (ms / 1e3)
 
+    # informational: the same steps with shared reads (3 queries score every streamed tile; identical results)
+    shared = None
+    if Q >= 2:
+        for s_ in range(min(args.warmup, 3)):
+            searcher.search(q_dev[s_], TOPK, shared=True)
+        barrier()
+        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sa.record()
+        for s_ in range(args.warmup, total_steps):
+            got = searcher.search(q_dev[s_], TOPK, shared=True)
+        sb.record()
+        barrier()
+        sms = torch.tensor([sa.elapsed_time(sb)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        assert torch.equal(got[0], last[0]) and torch.equal(got[1].view(torch.int64), last[1].view(torch.int64)), \
+            "shared-read scan differs from one-scan-per-query"
+        shared = {"queries_per_pass": 3, "value": args.steps * Q / (float(sms[0]) / 1e3), "unit": UNIT,
+                  "ms_per_step": float(sms[0]) / args.steps,
+                  "note": "cdr_search_exact_f32_shared: not the contract line (configs[1] is one scan per query)"}
+
     # single-query latency (device-timed, one query per call)
     lat = []
     for i in range(20):
@@ -657,6 +678,7 @@ def main():
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": k_ms_max / max(launches_k1, 1), "launches_timed": launches_k1},
         }
+        line["exact_batch_shared_reads"] = shared
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.rows, args.cpu_sample_rows, args.cpu_sample_queries, 0)
             one = cpu_baseline(args.rows, min(args.cpu_sample_rows, 50_000), 4, 1, target_seconds=4.0)

@@ -164,10 +164,6 @@ extern "C" int32_t cdr_prof_read_launches(int32_t kind, double *out_ms, int64_t 
 }
 
 // ---------------------------------------------------------------------------- exact lane
-int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
-                          const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                          int32_t *out_n, cudaStream_t st);
-
 static int check_search_args(const char *fn, cdr_store *s, const void *q, int nq, int k,
                              const void *o1, const void *o2, const void *o3)
 {
@@ -179,14 +175,13 @@ static int check_search_args(const char *fn, cdr_store *s, const void *q, int nq
     return CDR_OK;
 }
 
-extern "C" int32_t cdr_search_exact_f32(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
-                                        const uint32_t *allow_dev, double *out_score_dev,
-                                        int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
+static int32_t search_exact_dev(const char *fn, bool share_reads, cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                                const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev,
+                                int32_t *out_n_dev, void *stream)
 {
-    int rc = check_search_args("cdr_search_exact_f32", s, q_dev, nq, k, out_score_dev, out_id_dev, out_n_dev);
+    int rc = check_search_args(fn, s, q_dev, nq, k, out_score_dev, out_id_dev, out_n_dev);
     if (rc != CDR_OK) return rc;
-    CDR_REQUIRE(s->emb_f32 != nullptr, CDR_ERR_STATE,
-                "cdr_search_exact_f32: store has no fp32 rows (created without CDR_STORE_FP32)");
+    CDR_REQUIRE(s->emb_f32 != nullptr, CDR_ERR_STATE, "%s: store has no fp32 rows (created without CDR_STORE_FP32)", fn);
     if (nq == 0) return CDR_OK;
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -194,15 +189,31 @@ extern "C" int32_t cdr_search_exact_f32(cdr_store *s, const float *q_dev, int32_
     ScanWorkspace &ws = s->ws[st];
     // rows with embedding IS NULL are excluded even when the caller passes no filter
     const uint32_t *allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
-    // grid.y is limited to 65535 queries per launch
+    // grid.y is limited to 65535 query groups per launch
     for (int q0 = 0; q0 < nq; q0 += 32768) {
         const int m = (nq - q0) < 32768 ? (nq - q0) : 32768;
         rc = cdr_exact_scan_launch(s, ws, q_dev + (size_t)q0 * s->dim, m, allow, k,
                                    out_score_dev + (size_t)q0 * k, out_id_dev + (size_t)q0 * k,
-                                   out_n_dev + q0, st);
+                                   out_n_dev + q0, st, share_reads);
         if (rc != CDR_OK) return rc;
     }
     return CDR_OK;
+}
+
+extern "C" int32_t cdr_search_exact_f32(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                                        const uint32_t *allow_dev, double *out_score_dev,
+                                        int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
+{
+    return search_exact_dev("cdr_search_exact_f32", false, s, q_dev, nq, k, allow_dev, out_score_dev, out_id_dev,
+                            out_n_dev, stream);
+}
+
+extern "C" int32_t cdr_search_exact_f32_shared(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                                               const uint32_t *allow_dev, double *out_score_dev,
+                                               int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
+{
+    return search_exact_dev("cdr_search_exact_f32_shared", true, s, q_dev, nq, k, allow_dev, out_score_dev,
+                            out_id_dev, out_n_dev, stream);
 }
 
 // Shared host-buffer wrapper: H2D queries, run `fn`, D2H results, synchronise.
@@ -263,6 +274,14 @@ extern "C" int32_t cdr_search_exact_f32_host(cdr_store *s, const float *q_host, 
                                              int64_t *out_id_host, int32_t *out_n_host, void *stream)
 {
     return search_host("cdr_search_exact_f32_host", cdr_search_exact_f32, s, q_host, nq, k, allow_dev,
+                       out_score_host, out_id_host, out_n_host, stream);
+}
+
+extern "C" int32_t cdr_search_exact_f32_shared_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                                    const uint32_t *allow_dev, double *out_score_host,
+                                                    int64_t *out_id_host, int32_t *out_n_host, void *stream)
+{
+    return search_host("cdr_search_exact_f32_shared_host", cdr_search_exact_f32_shared, s, q_host, nq, k, allow_dev,
                        out_score_host, out_id_host, out_n_host, stream);
 }
 

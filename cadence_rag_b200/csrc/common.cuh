@@ -102,6 +102,11 @@ struct DeviceGuard {
     }
 };
 
+// K1 + finalize on `st` (exact_scan.cu).  share_reads: score every streamed tile against 3 queries per CTA
+// (batches of concurrent exact requests); false = one scan of the corpus per query.  Same bits either way.
+int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
+                          double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st, bool share_reads);
+
 // profiling hooks (abi.cu)
 void cdr_prof_mark_begin(int kind, cudaStream_t st);
 void cdr_prof_mark_end(int kind, cudaStream_t st);

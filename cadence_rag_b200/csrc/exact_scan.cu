@@ -36,7 +36,8 @@ struct ScanParams {
     const float *inv_norm;    // [>= round_up(n_rows, TR)]
     const uint32_t *allow;    // nullable bitmap
     const float *queries;     // [nq, dim]
-    uint64_t *cta_keys;       // [nq, gridDim.x, KC]
+    int nq;                   // queries of this launch; gridDim.y = ceil(nq / QPC) query groups
+    uint64_t *cta_keys;       // [nq, lists_per_query, KC]
     int64_t n_rows;
     int64_t n_tiles;
     int n_stages;
@@ -53,14 +54,22 @@ struct ScanParams {
 };
 
 // Dynamic shared memory carve-up (computed identically on host and device).
-template <int J, int RPW, int NPL>
+// QPC = queries per CTA: 1 = one scan of the corpus per query (the single-query GEMV of BASELINE configs[1]);
+// kSharedQPC = "shared reads": a CTA scores every tile it streams against 3 queries held in registers, so a
+// batch of concurrent exact requests costs a third of the HBM traffic.  Per-query arithmetic is identical (same
+// lanes, same accumulation order), so both give the same bits.  Why 3: with 9 warps one SM sub-partition hosts
+// 3 warps, i.e. <= 170 registers per thread; 4 queries (128 registers of query data) spill, and because the CTA
+// takes ~all of the unified L1/shared memory for its tile ring the spills go to L2 (measured: 1.26x instead of
+// 4x).  3 queries compile to 168 registers with no spills.
+constexpr int kSharedQPC = 3;
+template <int J, int RPW, int NPL, int QPC>
 struct ScanSmem {
     static constexpr int DIM = J * 128;
     static constexpr int TR = RPW * kConsumerWarps;
     static constexpr int KC = NPL * 32;
     static constexpr size_t kTileBytes = (size_t)TR * DIM * 4;
     static constexpr size_t kMetaBytes = (size_t)TR * 4;   // inverse norms (multiple of 16)
-    static constexpr size_t kListBytes = (size_t)kConsumerWarps * KC * 8;
+    static constexpr size_t kListBytes = (size_t)kConsumerWarps * QPC * KC * 8;
     static constexpr size_t kBarBytes = 3 * kMaxStages * 8;   // full + empty barriers + the tile index of each stage
     static constexpr size_t bytes(int stages)
     {
@@ -74,10 +83,10 @@ struct ScanSmem {
     }
 };
 
-template <int J, int RPW, int NPL>
+template <int J, int RPW, int NPL, int QPC>
 __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanParams p)
 {
-    using L = ScanSmem<J, RPW, NPL>;
+    using L = ScanSmem<J, RPW, NPL, QPC>;
     constexpr int DIM = L::DIM, TR = L::TR, KC = L::KC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
@@ -85,12 +94,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     unsigned char *tiles = smem_raw;
     unsigned char *metas = tiles + (size_t)S * L::kTileBytes;
     uint64_t *lists = reinterpret_cast<uint64_t *>(metas + (size_t)S * L::kMetaBytes);
-    uint64_t *full_bar = lists + kConsumerWarps * KC;
+    uint64_t *full_bar = lists + kConsumerWarps * QPC * KC;
     uint64_t *empty_bar = full_bar + kMaxStages;
     long long *stage_tile = reinterpret_cast<long long *>(empty_bar + kMaxStages);   // tile held by a stage, -1 = end
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = blockIdx.y;
+    const int q0 = blockIdx.y * QPC;                                  // first query of this CTA's group
+    const int nqv = p.nq - q0 < QPC ? p.nq - q0 : QPC;                // valid queries in the group
     const int64_t G = gridDim.x;
     const bool gather = p.row_list != nullptr;
     int64_t n_tiles = p.n_tiles;
@@ -100,9 +110,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
         const bool list_serves = n_listed <= p.list_cap;
         if (gather != list_serves) {                  // the other launch of the pair does the work: empty lists
             if (warp == 0) {
-                uint64_t *out = p.cta_keys + ((size_t)qi * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
+                for (int u = 0; u < nqv; ++u) {
+                    uint64_t *out = p.cta_keys + ((size_t)(q0 + u) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = CDR_EMPTY_KEY;
+                    for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = CDR_EMPTY_KEY;
+                }
             }
             return;
         }
@@ -135,7 +147,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                 int64_t tile = blockIdx.x + i * G;
                 if (dynamic && i >= S) tile = next_dyn;
                 // draw the next tile now: the atomic's round trip overlaps the wait for a free stage
-                if (dynamic && i + 1 >= S) next_dyn = (int64_t)S * G + atomicAdd(&p.tile_ctr[qi], 1u);
+                if (dynamic && i + 1 >= S) next_dyn = (int64_t)S * G + atomicAdd(&p.tile_ctr[blockIdx.y], 1u);
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 if (tile >= n_tiles) {
                     stage_tile[s] = -1;
@@ -171,22 +183,26 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
         }
     } else {
         // ------------------------------------------------------------------ consumers
-        float4 q[J];
-        float qn = 0.f;
-        const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)qi * DIM);
+        float4 q[QPC][J];
+        float inv_qn[QPC];
+        WarpTopK<NPL> top[QPC];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            q[j] = __ldg(&qv[j * 32 + lane]);
-            qn = fmaf(q[j].x, q[j].x, qn);
-            qn = fmaf(q[j].y, q[j].y, qn);
-            qn = fmaf(q[j].z, q[j].z, qn);
-            qn = fmaf(q[j].w, q[j].w, qn);
+        for (int u = 0; u < QPC; ++u) {
+            float qn = 0.f;
+            // a missing query of the last group re-reads the group's first query; its results are never written
+            const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(q0 + (u < nqv ? u : 0)) * DIM);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                q[u][j] = __ldg(&qv[j * 32 + lane]);
+                qn = fmaf(q[u][j].x, q[u][j].x, qn);
+                qn = fmaf(q[u][j].y, q[u][j].y, qn);
+                qn = fmaf(q[u][j].z, q[u][j].z, qn);
+                qn = fmaf(q[u][j].w, q[u][j].w, qn);
+            }
+            qn = warp_sum_f32(qn);
+            inv_qn[u] = __fdiv_rn(1.0f, __fsqrt_rn(qn));   // inf for a zero query -> NaN scores
+            top[u].init(lists + (warp * QPC + u) * KC, lane);
         }
-        qn = warp_sum_f32(qn);
-        const float inv_qn = __fdiv_rn(1.0f, __fsqrt_rn(qn));   // inf for a zero query -> NaN scores
-
-        WarpTopK<NPL> top;
-        top.init(lists + warp * KC, lane);
 
         for (int64_t i = 0;; ++i) {
             const int s = (int)(i % S);
@@ -217,20 +233,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                                (size_t)(warp * RPW) * (DIM / 4);
             const float *mv = reinterpret_cast<const float *>(metas + (size_t)s * L::kMetaBytes) +
                               warp * RPW;
-            float acc[RPW][2];
+            float acc[QPC][RPW][2];
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) acc[r][0] = acc[r][1] = 0.f;
+            for (int u = 0; u < QPC; ++u)
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) acc[u][r][0] = acc[u][r][1] = 0.f;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
-                    const float4 v = tv[r * (DIM / 4) + j * 32 + lane];
-                    float a = acc[r][j & 1];
-                    a = fmaf(v.x, q[j].x, a);
-                    a = fmaf(v.y, q[j].y, a);
-                    a = fmaf(v.z, q[j].z, a);
-                    a = fmaf(v.w, q[j].w, a);
-                    acc[r][j & 1] = a;
+                    const float4 v = tv[r * (DIM / 4) + j * 32 + lane];     // one LDS.128 feeds QPC queries
+#pragma unroll
+                    for (int u = 0; u < QPC; ++u) {
+                        float a = acc[u][r][j & 1];
+                        a = fmaf(v.x, q[u][j].x, a);
+                        a = fmaf(v.y, q[u][j].y, a);
+                        a = fmaf(v.z, q[u][j].z, a);
+                        a = fmaf(v.w, q[u][j].w, a);
+                        acc[u][r][j & 1] = a;
+                    }
                 }
             }
             float inv_n[RPW];
@@ -242,41 +263,48 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
 
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
-                const float dot = warp_sum_f32(acc[r][0] + acc[r][1]);
                 const int64_t row = gather ? (int64_t)g_row[r] : row0 + r;
                 const bool ok = (row < p.n_rows) && ((allow_bits >> r) & 1u);
-                if (ok) {
-                    const float score = dot * inv_n[r] * inv_qn;
-                    const uint64_t key = cdr_pack_key(score, (uint32_t)row);
-                    if (key > top.tau) top.push(key, lane);
+#pragma unroll
+                for (int u = 0; u < QPC; ++u) {
+                    const float dot = warp_sum_f32(acc[u][r][0] + acc[u][r][1]);
+                    if (ok) {
+                        const float score = dot * inv_n[r] * inv_qn[u];
+                        const uint64_t key = cdr_pack_key(score, (uint32_t)row);
+                        if (key > top[u].tau) top[u].push(key, lane);
+                    }
                 }
             }
         }
 
-        // ---- per-warp sort, then 3-level pairwise merge through shared memory
-        uint64_t k[NPL];
-        __syncwarp();
+        // ---- per query: per-warp sort, then 3-level pairwise merge through shared memory
+#pragma unroll 1
+        for (int u = 0; u < QPC; ++u) {
+            uint64_t *mine = lists + (warp * QPC + u) * KC;
+            uint64_t k[NPL];
+            __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) k[i] = top.list[i * 32 + lane];
-        warp_bitonic_sort_desc<NPL>(k, lane);
+            for (int i = 0; i < NPL; ++i) k[i] = mine[i * 32 + lane];
+            warp_bitonic_sort_desc<NPL>(k, lane);
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
+            for (int i = 0; i < NPL; ++i) mine[i * 32 + lane] = k[i];
 #pragma unroll
-        for (int step = 1; step < kConsumerWarps; step <<= 1) {
-            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
-            if ((warp & (2 * step - 1)) == 0) {
-                warp_merge_topk<NPL>(k, lists + (warp + step) * KC, lane);
+            for (int step = 1; step < kConsumerWarps; step <<= 1) {
+                asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+                if ((warp & (2 * step - 1)) == 0) {
+                    warp_merge_topk<NPL>(k, lists + ((warp + step) * QPC + u) * KC, lane);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+                if ((warp & (2 * step - 1)) == 0) {
+#pragma unroll
+                    for (int i = 0; i < NPL; ++i) mine[i * 32 + lane] = k[i];
+                }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
-            if ((warp & (2 * step - 1)) == 0) {
+            if (warp == 0 && u < nqv) {
+                uint64_t *out = p.cta_keys + ((size_t)(q0 + u) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
+                for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
             }
-        }
-        if (warp == 0) {
-            uint64_t *out = p.cta_keys + ((size_t)qi * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
         }
     }
 }
@@ -337,7 +365,8 @@ struct FinalizeParams {
     double *out_score;        // [nq, k]
     int64_t *out_id;          // [nq, k]
     int32_t *out_n;           // [nq]
-    unsigned int *reset_ctr;  // nullable: K1's work-stealing counter of this query, zeroed for the next launch
+    unsigned int *reset_ctr;  // nullable: K1's work-stealing counter of this query's group, zeroed for the next launch
+    int reset_div;            // queries per K1 group (counter index = query / reset_div)
 };
 
 // fp64 cosine of query (a-values in smem as float) x one resident row; all lanes return the result.
@@ -532,7 +561,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const Finaliz
     }
     if (threadIdx.x == 0) {
         p.out_n[qi] = n_out;
-        if (p.reset_ctr) p.reset_ctr[qi] = 0u;
+        if (p.reset_ctr) p.reset_ctr[qi / p.reset_div] = 0u;
     }
 }
 
@@ -716,7 +745,7 @@ __global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256)
     }
     if (threadIdx.x == 0) {
         p.out_n[qi] = n_out;
-        if (p.reset_ctr) p.reset_ctr[qi] = 0u;
+        if (p.reset_ctr) p.reset_ctr[qi / p.reset_div] = 0u;
     }
 }
 
@@ -744,12 +773,12 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
     return CDR_OK;
 }
 
-template <int J, int RPW, int NPL>
+template <int J, int RPW, int NPL, int QPC>
 int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                   const uint32_t *allow, int k, double *out_score, int64_t *out_id, int32_t *out_n,
                   cudaStream_t st)
 {
-    using L = ScanSmem<J, RPW, NPL>;
+    using L = ScanSmem<J, RPW, NPL, QPC>;
     constexpr int KC = L::KC;
     // per-device launch configuration (the smem opt-in attribute is per device)
     static int stages_by_dev[64] = {0};
@@ -761,7 +790,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
         CDR_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
         int st_n = L::max_stages((size_t)dev_smem);
         smem = L::bytes(st_n);
-        CDR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<J, RPW, NPL>,
+        CDR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<J, RPW, NPL, QPC>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         stages = st_n;
     }
@@ -809,6 +838,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     sp.inv_norm = s->inv_norm;
     sp.allow = allow;
     sp.queries = q_dev;
+    sp.nq = nq;
     sp.cta_keys = ws.cta_keys;
     sp.n_rows = s->n_rows;
     sp.n_tiles = n_tiles;
@@ -820,18 +850,19 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     sp.lists_per_query = g_total;
     sp.list_offset = 0;
 
+    const int n_groups = (nq + QPC - 1) / QPC;
     cdr_prof_mark_begin(0, st);
     if (g_gather > 0) {
         ScanParams gp = sp;
         gp.row_list = ws.row_list;
         gp.list_count = reinterpret_cast<unsigned int *>(ws.row_list) + list_cap;
         gp.allow = nullptr;
-        exact_scan_kernel<J, RPW, NPL><<<dim3(g_gather, nq), kScanThreads, smem, st>>>(gp);
+        exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(g_gather, n_groups), kScanThreads, smem, st>>>(gp);
         CDR_LAUNCH_CHECK();
         sp.list_count = gp.list_count;
         sp.list_offset = g_gather;
     }
-    exact_scan_kernel<J, RPW, NPL><<<dim3(grid, nq), kScanThreads, smem, st>>>(sp);
+    exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(grid, n_groups), kScanThreads, smem, st>>>(sp);
     CDR_LAUNCH_CHECK();
     cdr_prof_mark_end(0, st);
 
@@ -850,25 +881,31 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     fp.out_id = out_id;
     fp.out_n = out_n;
     fp.reset_ctr = sp.tile_ctr;
+    fp.reset_div = QPC;
     return launch_finalize(fp, KC, nq, st);
 }
 
 template <int NPL>
 int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                     const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                    int32_t *out_n, cudaStream_t st)
+                    int32_t *out_n, cudaStream_t st, bool share)
 {
+#define CDR_SCAN_CASE(J_, RPW_)                                                                              \
+    if (share) return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
+    return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st)
     switch (s->dim) {
-    case 256:  return launch_scan_t<2, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
-    case 512:  return launch_scan_t<4, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
-    case 768:  return launch_scan_t<6, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
-    case 1024: return launch_scan_t<8, 2, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
-    case 1536: return launch_scan_t<12, 1, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
-    case 2048: return launch_scan_t<16, 1, NPL>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 256:  CDR_SCAN_CASE(2, 2);
+    case 512:  CDR_SCAN_CASE(4, 2);
+    case 768:  CDR_SCAN_CASE(6, 2);
+    case 1024: CDR_SCAN_CASE(8, 2);
+    // kSharedQPC queries x J float4 would not fit the register budget: one scan per query
+    case 1536: return launch_scan_t<12, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 2048: return launch_scan_t<16, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
     default:
         cdr_set_error("exact scan: dim %d not built (supported: 256,512,768,1024,1536,2048)", s->dim);
         return CDR_ERR_UNSUPPORTED;
     }
+#undef CDR_SCAN_CASE
 }
 
 }  // namespace
@@ -877,10 +914,11 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
 // (KC - k >= 8 spare slots absorb fp32-vs-fp64 rank swaps at the boundary).
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                           const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                          int32_t *out_n, cudaStream_t st)
+                          int32_t *out_n, cudaStream_t st, bool share_reads)
 {
-    if (k <= 56) return launch_scan_dim<2>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
-    return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    const bool share = share_reads && nq >= 2;
+    if (k <= 56) return launch_scan_dim<2>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share);
+    return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share);
 }
 
 // Used by the batched bf16 lane (gemm_topk.cu): select the top-kc of one unsorted candidate
@@ -904,5 +942,6 @@ int cdr_finalize_unsorted_launch(cdr_store *s, const uint64_t *lists, const uint
     fp.out_id = out_id;
     fp.out_n = out_n;
     fp.reset_ctr = nullptr;
+    fp.reset_div = 1;
     return launch_finalize(fp, kc, nq, st);
 }

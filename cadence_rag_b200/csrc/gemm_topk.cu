@@ -34,9 +34,6 @@
 #include <cuda.h>
 #include <cstdlib>
 
-int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
-                          const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                          int32_t *out_n, cudaStream_t st);
 int cdr_finalize_unsorted_launch(cdr_store *s, const uint64_t *lists, const uint32_t *counts, int cap,
                                  int kc, const float *q_dev, int nq, int k, bool use_bf16_rows,
                                  double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st);
@@ -798,7 +795,7 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
                     "cdr_search_batch_bf16: query %d needs the exact lane (candidate overflow or short result) "
                     "but the store keeps no fp32 rows", q);
         rc = cdr_exact_scan_launch(s, ws, q_dev + (size_t)q * dim, 1, allow, k,
-                                   out_score_dev + (size_t)q * k, out_id_dev + (size_t)q * k, out_n_dev + q, st);
+                                   out_score_dev + (size_t)q * k, out_id_dev + (size_t)q * k, out_n_dev + q, st, false);
         if (rc != CDR_OK) return rc;
     }
     return CDR_OK;

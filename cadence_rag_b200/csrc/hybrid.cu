@@ -14,8 +14,6 @@
 #include <cstring>
 
 struct cdr_tech_index;
-int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
-                          double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st);
 int cdr_filter_launch(cdr_store *s, const uint32_t *bm_dev, int64_t n_call_slots, int has_from, int64_t date_from_us,
                       int has_to, int64_t date_to_us, int has_tags, uint64_t tag_any, uint32_t *out_allow_dev,
                       unsigned long long *cnt_dev, cudaStream_t st);
@@ -217,7 +215,7 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
     }
     if (dense) {
         rc = cdr_exact_scan_launch(s, ws, (const float *)(d + in_q), nq, allow, dense_k, (double *)(d + o_dsc),
-                                   (int64_t *)(d + o_did), (int32_t *)(d + o_dn), st);
+                                   (int64_t *)(d + o_did), (int32_t *)(d + o_dn), st, /*share_reads=*/true);
         if (rc != CDR_OK) return rc;
     }
 

@@ -155,11 +155,13 @@ class ShardedSearcher:
             self.peer.close()
             self.peer = None
 
-    def search(self, queries_dev, k: int, allow=None, mode: str = "exact"):
+    def search(self, queries_dev, k: int, allow=None, mode: str = "exact", shared: bool = False):
         """queries_dev: [nq, dim] CUDA tensor replicated on every rank.  Returns the global
-        (ids, scores, n) on every rank."""
-        fn = self.store.search_exact if mode == "exact" else self.store.search_batch
-        ids, scores, n = fn(queries_dev, k, allow)
+        (ids, scores, n) on every rank.  shared: see DenseStore.search_exact."""
+        if mode == "exact":
+            ids, scores, n = self.store.search_exact(queries_dev, k, allow, shared=shared)
+        else:
+            ids, scores, n = self.store.search_batch(queries_dev, k, allow)
         if self.world == 1:
             return ids, scores, n
         if self.peer is not None and k <= self.peer.max_k:

@@ -287,7 +287,7 @@ def fetch_dense_batch(conn: DenseConnection, table_name: str, queries, filters, 
     nq = int(queries.shape[0])
     if mode == "ann" and store.has_bf16 and (nq >= settings.cadence_gpu_ann_min_batch or not store.has_fp32):
         return store.search_batch(queries, limit, allow)
-    return store.search_exact(queries, limit, allow)
+    return store.search_exact(queries, limit, allow, shared=True)
 
 
 # --------------------------------------------------------------------------- tech_tokens lane

@@ -487,11 +487,13 @@ class DenseStore:
                       _ffi.ptr(cnt), self._stream()), fn_name + "_host")
         return ids, sc, cnt
 
-    def search_exact(self, queries, k: int, allow=None):
+    def search_exact(self, queries, k: int, allow=None, shared: bool = False):
         """mode="exact": fp32 cosine scan (K1) + fp64 re-score.  Host queries -> host results
         (numpy, through the *_host C entry point: H2D + kernels + D2H + sync); CUDA tensors ->
-        CUDA tensors (asynchronous on the current stream).  Returns (ids[nq,k], scores[nq,k], n[nq])."""
-        return self._search("cdr_search_exact_f32", queries, k, allow)
+        CUDA tensors (asynchronous on the current stream).  Returns (ids[nq,k], scores[nq,k], n[nq]).
+        shared=True: a batch of concurrent requests shares every tile read among 3 queries
+        (``cdr_search_exact_f32_shared``: nq/3 scans of the corpus, same bits); False = one scan per query."""
+        return self._search("cdr_search_exact_f32_shared" if shared else "cdr_search_exact_f32", queries, k, allow)
 
     def search_batch(self, queries, k: int, allow=None):
         """mode="ann" served by the batched bf16 tensor-core lane (K2) + exact re-score."""

@@ -161,6 +161,17 @@ int32_t cdr_search_exact_f32_host(cdr_store *s, const float *q_host, int32_t nq,
                                   const uint32_t *allow_dev, double *out_score_host,
                                   int64_t *out_id_host, int32_t *out_n_host, void *stream);
 
+/* The same lane for a BATCH of concurrent exact requests: every tile a CTA streams from HBM is scored
+ * against 3 queries held in registers ("shared reads"), so nq queries cost nq/3 scans of the corpus.
+ * cdr_search_exact_f32 above keeps one scan per query (the single-query GEMV of the reference's
+ * one-query-per-request flow); per-query arithmetic is the same, and so is every bit of the result. */
+int32_t cdr_search_exact_f32_shared(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                                    const uint32_t *allow_dev, double *out_score_dev,
+                                    int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
+int32_t cdr_search_exact_f32_shared_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                         const uint32_t *allow_dev, double *out_score_host,
+                                         int64_t *out_id_host, int32_t *out_n_host, void *stream);
+
 /* ---- K2 + K3: batched bf16 tensor-core scan (tcgen05) with fused threshold top-k epilogue --
  * Serves mode "ann" of app/retrieve.py:290-298 (_configure_dense_session: HNSW ef_search) by
  * brute force on the tensor cores: the score matrix never reaches HBM; survivors are re-scored

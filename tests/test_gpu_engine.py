@@ -215,6 +215,31 @@ def test_exact_scan_finalize_variants_agree(corpus_100k, k):
                            allow=orc.rows_to_bitmap(np.isin(np.arange(x.shape[0]) // 200, np.arange(0, 500, 3))))
 
 
+@pytest.mark.parametrize("k", [50, 200])
+def test_exact_scan_shared_reads_same_bits(corpus_100k, k):
+    """cdr_search_exact_f32_shared (3 queries score every streamed tile) == one scan per query, bit for bit:
+    ragged group tails (nq = 2, 5, 33), host and device entry points, filters on both sides of the gather
+    boundary, and the oracle."""
+    s, x = corpus_100k
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 700, 33)
+    wide, _ = s.filter_bitmap(call_slots=list(range(0, 500, 3)))
+    narrow, _ = s.filter_bitmap(call_slots=[3, 44, 45])
+    for al in (None, wide, narrow):
+        for nq in (2, 5, 33):
+            a = s.search_exact(qs[:nq], k, al)
+            b = s.search_exact(qs[:nq], k, al, shared=True)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+            assert np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
+        d = s.search_exact(torch.from_numpy(qs).cuda(), k, al, shared=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(d[0].cpu().numpy(), a[0]) and np.array_equal(d[1].cpu().numpy().view(np.uint64), a[1].view(np.uint64))
+    b = s.search_exact(qs[:5], k, None, shared=True)
+    for i in range(5):
+        assert_matches_oracles(b[0][i], b[1][i], b[2][i], qs[i], x, k)
+    one = s.search_exact(qs[4], k, None, shared=True)          # a single query takes the unshared kernel
+    assert np.array_equal(one[0][0], b[0][4])
+
+
 def test_exact_scan_selective_filter_gather_path(corpus_100k):
     """Filters that keep <= rows/16 rows are served by the gather launch (compact row list, only those rows are
     read); larger ones by the full scan -- the decision is taken on the device.  Both sides of the boundary,
