@@ -801,14 +801,21 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     // Selective filters.  The reference's planner sends small scoped candidate sets (<= 2 000 rows by default,
     // app/retrieve.py:277-287) to the exact lane; scanning the whole table for them wastes the bus.  For a
     // caller-supplied bitmap the allowed rows are compacted into a list (one pass over n_rows/8 bytes) and a
-    // GATHER launch scans only those rows when there are at most n_rows/16 of them; otherwise it exits at once
+    // GATHER launch scans only those rows when there are at most n_rows/2 of them (4 KB row gathers stream at
+    // ~4.6 TB/s: 1/64 of the rows 0.048 ms, 1/4 0.254 ms, 1/2 0.470 ms vs 0.61 ms for the full scan of 1 M rows,
+    // profiles/r01/k1_gather_sweep.json); otherwise it exits at once
     // and the full scan below serves.  The decision is taken on the device (no host round trip); the skipped
     // launch writes empty candidate lists.  Same per-row arithmetic => identical results either way.
     static const bool k1_nogather = [] { const char *e = getenv("CADENCE_K1_GATHER"); return e && e[0] == '0'; }();
     int g_gather = 0;
     uint32_t list_cap = 0;
     if (allow != nullptr && allow != s->valid && !k1_nogather && s->n_rows >= 4 * L::TR) {
-        int64_t cap = s->n_rows / 16;
+        static const int64_t gather_div = [] {       // CADENCE_K1_GATHER_DIV: A/B aid, list capacity = rows / div
+            const char *e = getenv("CADENCE_K1_GATHER_DIV");
+            const int v = e ? atoi(e) : 2;
+            return (int64_t)(v >= 1 ? v : 2);
+        }();
+        int64_t cap = s->n_rows / gather_div;
         if (cap < L::TR) cap = L::TR;
         list_cap = (uint32_t)cap;
         const int64_t gt = (cap + L::TR - 1) / L::TR;

@@ -241,15 +241,15 @@ def test_exact_scan_shared_reads_same_bits(corpus_100k, k):
 
 
 def test_exact_scan_selective_filter_gather_path(corpus_100k):
-    """Filters that keep <= rows/16 rows are served by the gather launch (compact row list, only those rows are
+    """Filters that keep <= rows/2 rows are served by the gather launch (compact row list, only those rows are
     read); larger ones by the full scan -- the decision is taken on the device.  Both sides of the boundary,
     ragged list tails, the empty filter and a batch must match the oracle exactly."""
     s, x = corpus_100k
     n = x.shape[0]
-    cap = n // 16
+    cap = n // 2
     rng = np.random.default_rng(11)
     qs = orc.synth_rows(SYNTH_QUERY_SEED, 500, 3)
-    for count in (0, 1, 15, 16, 17, 49, 50, 51, 2000, cap - 1, cap, cap + 1, cap + 4000):
+    for count in (0, 1, 15, 16, 17, 49, 50, 51, 2000, n // 16, cap - 1, cap, cap + 1, cap + 4000):
         keep = np.zeros(n, dtype=bool)
         keep[rng.choice(n, count, replace=False)] = True
         allow = torch.from_numpy(orc.rows_to_bitmap(keep).view(np.int32)).cuda()
