@@ -137,7 +137,45 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     // the static split (t = blockIdx.x + i*G).  A stage whose tile index is -1 ends the stream.
     const bool dynamic = p.tile_ctr != nullptr;
 
-    if (warp == kConsumerWarps) {
+    if (warp == kConsumerWarps && gather) {
+        // ------------------------------------------------------------------ producer, gather launch
+        // The whole warp runs the loop: lane 0 draws tiles and arms the barrier, lanes 0..TR-1 each fetch one
+        // list entry and issue that row's bulk copy, so the TR copies of a tile are issued in parallel.
+        static_assert(TR <= 32, "one lane per row of a tile");
+        int64_t next_dyn = -1;
+        for (int64_t i = 0;; ++i) {
+            const int s = (int)(i % S);
+            const uint32_t ph = (uint32_t)((i / S) & 1);
+            int64_t tile = blockIdx.x + i * G;
+            if (dynamic && i >= S) tile = next_dyn;
+            if (dynamic && i + 1 >= S) {
+                unsigned int t = 0;
+                if (lane == 0) t = atomicAdd(&p.tile_ctr[blockIdx.y], 1u);
+                next_dyn = (int64_t)S * G + __shfl_sync(0xffffffffu, t, 0);
+            }
+            // the list entry of this lane's row can be fetched while the stage is still busy
+            const int64_t e0 = tile * TR;
+            const int nr = tile < n_tiles ? (int)((int64_t)n_listed - e0 < TR ? (int64_t)n_listed - e0 : TR) : 0;
+            const uint32_t my_row = lane < nr ? __ldg(&p.row_list[e0 + lane]) : 0u;
+            if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1u);
+            __syncwarp();
+            if (tile >= n_tiles) {
+                if (lane == 0) {
+                    stage_tile[s] = -1;
+                    mbar_arrive(&full_bar[s]);
+                }
+                break;
+            }
+            if (lane == 0) {
+                stage_tile[s] = tile;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nr * DIM * 4));
+            }
+            __syncwarp();
+            if (lane < nr)
+                bulk_g2s(tiles + (size_t)s * L::kTileBytes + (size_t)lane * DIM * 4, p.rows + (size_t)my_row * DIM,
+                         (uint32_t)(DIM * 4), &full_bar[s]);
+        }
+    } else if (warp == kConsumerWarps) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             int64_t next_dyn = -1;
@@ -155,21 +193,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                     break;
                 }
                 stage_tile[s] = tile;
-                if (gather) {
-                    // one 1-D bulk copy per listed row (DIM*4 bytes each) into the same tile layout
-                    const int64_t e0 = tile * TR;
-                    int nr = (int)((int64_t)n_listed - e0 < TR ? (int64_t)n_listed - e0 : TR);
-                    uint32_t rws[TR];
-#pragma unroll
-                    for (int r = 0; r < TR; ++r) rws[r] = r < nr ? __ldg(&p.row_list[e0 + r]) : 0u;
-                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nr * DIM * 4));
-#pragma unroll
-                    for (int r = 0; r < TR; ++r)
-                        if (r < nr)
-                            bulk_g2s(tiles + (size_t)s * L::kTileBytes + (size_t)r * DIM * 4,
-                                     p.rows + (size_t)rws[r] * DIM, (uint32_t)(DIM * 4), &full_bar[s]);
-                    continue;
-                }
                 const int64_t row0 = tile * TR;
                 int64_t nr = p.n_rows - row0;
                 if (nr > TR) nr = TR;
@@ -219,6 +242,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const bool in = row0 + r < (int64_t)n_listed;
+                    // (the 8 consumer warps overlap these two dependent L2 round trips; carrying them through the
+                    // stage from the producer warp made the producer latency-bound: 0.48 vs 0.41 ms at rows/2)
                     g_row[r] = in ? __ldg(&p.row_list[row0 + r]) : 0u;
                     g_inv[r] = __ldg(&p.inv_norm[g_row[r]]);
                     if (!in) allow_bits &= ~(1u << r);
@@ -802,7 +827,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     // app/retrieve.py:277-287) to the exact lane; scanning the whole table for them wastes the bus.  For a
     // caller-supplied bitmap the allowed rows are compacted into a list (one pass over n_rows/8 bytes) and a
     // GATHER launch scans only those rows when there are at most n_rows/2 of them (4 KB row gathers stream at
-    // ~4.6 TB/s: 1/64 of the rows 0.048 ms, 1/4 0.254 ms, 1/2 0.470 ms vs 0.61 ms for the full scan of 1 M rows,
+    // ~5.4 TB/s: 1/64 of the rows 0.046 ms, 1/4 0.221 ms, 1/2 0.405 ms vs 0.61 ms for the full scan of 1 M rows,
     // profiles/r01/k1_gather_sweep.json); otherwise it exits at once
     // and the full scan below serves.  The decision is taken on the device (no host round trip); the skipped
     // launch writes empty candidate lists.  Same per-row arithmetic => identical results either way.
