@@ -468,6 +468,30 @@ def run_hybrid(args):
                                   filter_spec=spec)
         dt = time.perf_counter() - t0
         out[name]["batched_64_queries_per_s"] = reps * B / dt
+    # concurrent clients: the reference serves /retrieve from a threadpool (app/main.py:184-186); 8 client threads,
+    # each on its own CUDA stream, one request at a time per thread, through retrieve_ids
+    import threading
+    for name, f in (("filtered_10_calls_2000_rows", filt), ("unfiltered", None)):
+        n_threads, per_thread = 8, max(8, args.steps)
+        errs = []
+
+        def client(t):
+            try:
+                with torch.cuda.stream(torch.cuda.Stream()):
+                    for i in range(per_thread):
+                        retrieve.retrieve_ids(eng, f"status of TK-{(t * 97 + i) % 500} and TK-{(i * 13 + t) % 900}", f)
+            except Exception as exc:   # noqa: BLE001
+                errs.append(repr(exc))
+        threads = [threading.Thread(target=client, args=(t,)) for t in range(n_threads)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        dt = time.perf_counter() - t0
+        assert not errs, errs
+        out[name]["concurrent_8_clients_queries_per_s"] = n_threads * per_thread / dt
     if os.environ.get("CADENCE_BENCH_HOST_PROFILE"):
         import cProfile, pstats
         pr = cProfile.Profile(); pr.enable()

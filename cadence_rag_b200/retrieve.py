@@ -286,8 +286,23 @@ def fetch_dense_batch(conn: DenseConnection, table_name: str, queries, filters, 
     allow, count = _filter_bitmap(conn, table_name, filters, call_ids)
     nq = int(queries.shape[0])
     if mode == "ann" and store.has_bf16 and (nq >= settings.cadence_gpu_ann_min_batch or not store.has_fp32):
-        return store.search_batch(queries, limit, allow)
+        if not store.has_fp32 or _batch_lane_is_faster(store, nq, count):
+            return store.search_batch(queries, limit, allow)
     return store.search_exact(queries, limit, allow, shared=True)
+
+
+def _batch_lane_is_faster(store: DenseStore, nq: int, candidate_rows: int) -> bool:
+    """Lane choice inside mode "ann" for a batch.  The bf16 tensor-core lane multiplies EVERY row (the filter is
+    applied in its epilogue): time ~ max(flops / 1.2 PFLOP/s, bf16 corpus bytes / 6.7 TB/s).  The exact lane with
+    shared reads streams only the candidate rows when the filter keeps <= rows/2 (gather launch, ~5.4 TB/s),
+    once per 3 queries.  Measured rates from profiles/r01/README.md; the exact lane wins for selective filters."""
+    rows, dim = store.rows, store.dim
+    nq_pad = -(-nq // 128) * 128
+    t_batch = max(2.0 * nq_pad * rows * dim / 1.2e15, rows * dim * 2 / 6.7e12) + 2e-4
+    scanned = candidate_rows if candidate_rows * 2 <= rows else rows
+    rate = 5.4e12 if scanned < rows else 5.8e12
+    t_exact = -(-nq // 3) * (scanned * dim * 4 / rate + 2e-5) + 5e-5
+    return t_batch < t_exact
 
 
 # --------------------------------------------------------------------------- tech_tokens lane

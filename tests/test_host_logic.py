@@ -326,3 +326,17 @@ def test_run_embedding_backfill_argument_checks(monkeypatch):
     with pytest.raises(RuntimeError, match="EMBEDDINGS_BATCH_SIZE must be > 0"):
         embedding_pipeline.run_embedding_backfill([], batch_size=0)
     assert embedding_pipeline.run_embedding_backfill([], batch_size=4).rows_updated == 0
+
+
+def test_batch_lane_choice_inside_mode_ann():
+    """A batch in mode "ann" runs on the tensor-core lane unless the filter is selective enough for the exact
+    lane's gather launch to beat a full multiplication (cadence_rag_b200.retrieve._batch_lane_is_faster)."""
+    from cadence_rag_b200.retrieve import _batch_lane_is_faster
+
+    class _S:
+        rows, dim = 10_000_000, 1024
+    assert _batch_lane_is_faster(_S, 1024, 10_000_000)            # unfiltered: 17 ms vs 342 full scans
+    assert _batch_lane_is_faster(_S, 1024, 500_000)               # 5 % of the rows: still the batch lane
+    assert not _batch_lane_is_faster(_S, 1024, 2_000)             # the planner's 2 000-row scoped sets
+    assert not _batch_lane_is_faster(_S, 16, 100_000)             # small batch, 1 % of the rows
+    assert _batch_lane_is_faster(_S, 128, 10_000_000)             # HBM-bound small batch, unfiltered
