@@ -482,16 +482,23 @@ def run_hybrid(args):
                         retrieve.retrieve_ids(eng, f"status of TK-{(t * 97 + i) % 500} and TK-{(i * 13 + t) % 900}", f)
             except Exception as exc:   # noqa: BLE001
                 errs.append(repr(exc))
-        threads = [threading.Thread(target=client, args=(t,)) for t in range(n_threads)]
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-        dt = time.perf_counter() - t0
-        assert not errs, errs
-        out[name]["concurrent_8_clients_queries_per_s"] = n_threads * per_thread / dt
+        for label, interval in (("concurrent_8_clients_queries_per_s", None), ("concurrent_8_clients_switchinterval_50us_queries_per_s", 5e-5)):
+            # CPython hands the GIL over every 5 ms by default: a client that returns from the (GIL-free) C call
+            # waits that long behind a peer running Python; sys.setswitchinterval(50 us) removes the convoy
+            old_interval = sys.getswitchinterval()
+            if interval is not None:
+                sys.setswitchinterval(interval)
+            threads = [threading.Thread(target=client, args=(t,)) for t in range(n_threads)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            dt = time.perf_counter() - t0
+            sys.setswitchinterval(old_interval)
+            assert not errs, errs
+            out[name][label] = n_threads * per_thread / dt
     if os.environ.get("CADENCE_BENCH_HOST_PROFILE"):
         import cProfile, pstats
         pr = cProfile.Profile(); pr.enable()
