@@ -62,6 +62,10 @@ def parse_args():
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """nvidia-smi sampled every 50 ms in a side process.  Started BEFORE the warm-up (the tool needs ~0.2 s to
+    deliver its first sample); mark_begin()/mark_end() bracket the timed region and stop() reports the samples
+    that arrived inside it.  A timed region shorter than the sampling period (8 GPUs, short steps) has none:
+    the caller then keeps the same workload running untimed (`extend`) until a few samples exist."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -70,12 +74,15 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.begin = 0
+        self.end = None
+        self.extended = False
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -84,6 +91,25 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark_begin(self):
+        self.begin = len(self.lines)
+
+    def mark_end(self):
+        self.end = len(self.lines)
+
+    def samples_in_region(self) -> int:
+        return (len(self.lines) if self.end is None else self.end) - self.begin
+
+    def extend(self, step_fn, min_samples: int = 3, max_seconds: float = 1.5):
+        """Keep the workload running (untimed) until the region holds min_samples samples."""
+        if not self.proc or self.samples_in_region() >= min_samples:
+            return
+        self.extended = True
+        t0 = time.perf_counter()
+        while len(self.lines) - self.begin < min_samples and time.perf_counter() - t0 < max_seconds:
+            step_fn()
+        self.end = len(self.lines)
 
     def stop(self):
         if not self.proc:
@@ -96,7 +122,8 @@ class ClockSampler:
         sm, mx, power = [], [], []
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        region = self.lines[self.begin:self.end] if self.end is not None else self.lines[self.begin:]
+        for ln in region:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -110,8 +137,11 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power),
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if self.extended:
+            out["note"] = "timed region shorter than the sampling period: sampled over the same steps run on, untimed"
+        return out
 
 
 def workload_config(args, world):
@@ -263,21 +293,23 @@ def run_batch_bf16(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for s in range(args.warmup):
-        searcher.search(q_dev[s], TOPK, mode="ann")
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for s in range(args.warmup):
+        searcher.search(q_dev[s], TOPK, mode="ann")
+    barrier()
     _ffi.lib().cdr_prof_enable(1)
     launches0 = _ffi.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record()
     for s in range(args.warmup, total):
         out = searcher.search(q_dev[s], TOPK, mode="ann")
     ev1.record()
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
     _ffi.check(_ffi.lib().cdr_prof_read(1, ctypes.byref(k_ms), ctypes.byref(k_n)))
@@ -287,8 +319,21 @@ def run_batch_bf16(args):
     segs = max(1, int(k_n.value) // max(args.steps, 1))
     last_step_launch_ms = [round(float(v), 4) for v in per_launch[-segs:]]
     _ffi.lib().cdr_prof_enable(0)
-    clocks = sampler.stop() if rank == 0 else None
     launches = _ffi.kernel_launch_count() - launches0
+    # too few clock samples (short region): every rank keeps stepping, untimed, while rank 0 samples
+    # (a step COUNT agreed by all ranks: every rank must issue the same sequence of exchanges)
+    n_ext = min(20000, int(0.6 / max(ms / 1e3 / max(args.steps, 1), 1e-5)) + 1) if (rank == 0 and sampler.samples_in_region() < 3 and sampler.proc) else 0
+    need_more = torch.tensor([n_ext], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(need_more, 0)
+    if int(need_more.item()):
+        for _ in range(int(need_more.item())):
+            searcher.search(q_dev[total - 1], TOPK, mode="ann")
+        barrier()
+        if rank == 0:
+            sampler.extended = True
+            sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms, float(launches), k_ms.value], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -589,31 +634,46 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts first: nvidia-smi needs ~0.2 s to deliver its first sample)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for s in range(args.warmup):
         searcher.search(q_dev[s], TOPK)
     barrier()
 
     # ---- timed: device-resident queries
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     _ffi.lib().cdr_prof_enable(1)
     launches0 = _ffi.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record()
     last = None
     for s in range(args.warmup, total_steps):
         last = searcher.search(q_dev[s], TOPK)
     ev1.record()
     barrier()
+    sampler.mark_end()
     launches = _ffi.kernel_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     import ctypes
     k_ms, k_n = ctypes.c_double(0), ctypes.c_int64(0)
     _ffi.check(_ffi.lib().cdr_prof_read(0, ctypes.byref(k_ms), ctypes.byref(k_n)))
     _ffi.lib().cdr_prof_enable(0)
+    # too few clock samples (short region, e.g. 8 GPUs): every rank keeps stepping, untimed, while rank 0 samples
+    # (a step COUNT agreed by all ranks: every rank must issue the same sequence of exchanges)
+    n_ext = min(20000, int(0.6 / max(ms / 1e3 / max(args.steps, 1), 1e-5)) + 1) if (rank == 0 and sampler.samples_in_region() < 3 and sampler.proc) else 0
+    need_more = torch.tensor([n_ext], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(need_more, 0)
+    if int(need_more.item()):
+        for _ in range(int(need_more.item())):
+            searcher.search(q_dev[total_steps - 1], TOPK)
+        barrier()
+        if rank == 0:
+            sampler.extended = True
+            sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms, float(launches), k_ms.value], dtype=torch.float64, device="cuda")
