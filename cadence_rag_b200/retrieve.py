@@ -600,6 +600,11 @@ def _ids_response(chunk_ranked, artifact_ranked, bm25_chunks, bm25_artifacts, te
             art_dbg["dense"] = _build_debug_lane(dense_artifacts, "artifact_chunk_id")
         response["debug"] = {
             "lanes": {"chunks": chunk_dbg, "artifacts": art_dbg},
+            "limits": {"bm25_chunk_topk": DEFAULT_CHUNK_BM25_TOPK,
+                       "bm25_artifact_chunk_topk": DEFAULT_ARTIFACT_CHUNK_BM25_TOPK,
+                       "tech_token_topk": DEFAULT_TECH_TOPK,
+                       "dense_chunk_topk": DEFAULT_DENSE_CHUNK_TOPK if dense_enabled else 0,
+                       "dense_artifact_chunk_topk": DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK if dense_enabled else 0},
             "dense": {"enabled": dense_enabled, "model_id": dense_model_id, "error": dense_error,
                       "modes": dict(modes), "candidate_rows": dict(candidates)},
             "fused": {"chunks": [(r["chunk_id"], sorted(l), s) for r, l, s in chunk_ranked],

@@ -340,3 +340,88 @@ def test_batch_lane_choice_inside_mode_ann():
     assert not _batch_lane_is_faster(_S, 1024, 2_000)             # the planner's 2 000-row scoped sets
     assert not _batch_lane_is_faster(_S, 16, 100_000)             # small batch, 1 % of the rows
     assert _batch_lane_is_faster(_S, 128, 10_000_000)             # HBM-bound small batch, unfiltered
+
+
+# ---------------------------------------------------------------- /retrieve response contract vs the reference's own code
+def test_retrieve_evidence_matches_reference_golden(monkeypatch, golden_dir):
+    """tests/golden/reference_evidence.json holds the REFERENCE's retrieve_evidence (app/retrieve.py:392-688, run
+    live by tests/golden/make_golden_evidence.py) on canned lane rows.  The same lanes replayed through
+    cadence_rag_b200.retrieve.retrieve_evidence must give the same response: fused order, ids_only combine,
+    budgeted evidence pack (clipping, <= 2 artifacts, <= 2 quotes per call), planner label, notes, debug."""
+    import contextlib
+    from cadence_rag_b200 import retrieve as R
+    from cadence_rag_b200.embeddings import EmbeddingClientError, EmbeddingResult
+    from oracle import ports
+    with open(os.path.join(golden_dir, "reference_evidence.json")) as f:
+        gold = json.load(f)
+    monkeypatch.setattr(settings, "embeddings_exact_scan_threshold", gold["settings"]["embeddings_exact_scan_threshold"])
+    monkeypatch.setattr(settings, "embeddings_hnsw_ef_search", gold["settings"]["embeddings_hnsw_ef_search"])
+    tables = {"chunks": {r["chunk_id"]: r for r in gold["corpus"]["chunks"]},
+              "artifact_chunks": {r["artifact_chunk_id"]: r for r in gold["corpus"]["artifacts"]}}
+
+    class _Store:
+        def __init__(self, name, key):
+            rows = tables[name]
+            self.table_name, self.key_field = name, key
+            ids = np.array(sorted(rows), dtype=np.int64)
+            calls = sorted({rows[i]["call_id"] for i in rows})
+            self.call_ids_by_slot = calls
+            self._cols = {"ids": ids, "call_slot": np.array([calls.index(rows[int(i)]["call_id"]) for i in ids], dtype=np.int32)}
+            self.payload = {i: {k: v for k, v in rows[i].items() if k not in (key, "call_id")} for i in rows}
+
+        def host_columns(self):
+            return self._cols
+
+    class _Engine:
+        stores = {"chunks": _Store("chunks", "chunk_id"), "artifact_chunks": _Store("artifact_chunks", "artifact_chunk_id")}
+
+        @contextlib.contextmanager
+        def connect(self):
+            yield object()
+
+    def rows_of(case, lane, table, key):
+        out = []
+        for ident, score in case["lanes"][lane]:
+            row = dict(tables[table][ident])
+            if score is not None:
+                row["score"] = score
+            out.append(row)
+        return out
+
+    monkeypatch.setattr(R, "_fused_path_ok", lambda *a, **k: False)
+    monkeypatch.setattr(R, "_rrf_merge", lambda lanes, key, k=60: ports.rrf_merge(lanes, key, k))   # K5 needs a GPU; the port is pinned to the reference
+    n_pack = n_ids = 0
+    for item in gold["cases"]:
+        case, want = item["case"], item["response"]
+        monkeypatch.setattr(R, "embeddings_enabled", lambda c=case: c["dense_enabled"])
+
+        def _embed(texts, c=case):
+            if c["embed_error"]:
+                raise EmbeddingClientError(c["embed_error"])
+            return EmbeddingResult(vectors=[[0.5] * 4], model="golden-embedder")
+        monkeypatch.setattr(R, "embed_texts", _embed)
+        monkeypatch.setattr(R, "_resolve_call_ids", lambda conn, filters, c=case: ["c1"] if c["scoped"] else None)
+        monkeypatch.setattr(R, "_fetch_chunks_tech", lambda *a, c=case: rows_of(c, "tech_chunks", "chunks", "chunk_id"))
+        monkeypatch.setattr(R, "_fetch_artifacts_tech", lambda *a, c=case: rows_of(c, "tech_artifacts", "artifact_chunks", "artifact_chunk_id"))
+        monkeypatch.setattr(R, "_fetch_chunks_dense", lambda *a, c=case: rows_of(c, "dense_chunks", "chunks", "chunk_id"))
+        monkeypatch.setattr(R, "_fetch_artifacts_dense", lambda *a, c=case: rows_of(c, "dense_artifacts", "artifact_chunks", "artifact_chunk_id"))
+        monkeypatch.setattr(R, "_estimate_dense_candidates", lambda conn, table, filters, cids, c=case: c["candidates"][table])
+        got = R.retrieve_evidence(_Engine(), case["query"], None, R.Budget(*case["budget"]), intent=case["intent"],
+                                  return_style=case["return_style"], debug=case["debug"],
+                                  bm25_chunks=rows_of(case, "bm25_chunks", "chunks", "chunk_id"),
+                                  bm25_artifacts=rows_of(case, "bm25_artifacts", "artifact_chunks", "artifact_chunk_id"))
+        got = json.loads(json.dumps(got, default=str))
+        assert set(want) - {"debug"} <= set(got), (case["query"], set(want) - set(got))
+        for key in want:
+            if key == "query_id":
+                continue
+            if key == "debug":
+                for part in ("lanes", "limits", "dense"):
+                    assert got["debug"][part] == want["debug"][part], (case["return_style"], part)
+                continue
+            assert got[key] == want[key], (case["return_style"], case["budget"], key)
+        if case["return_style"] == "ids_only":
+            n_ids += 1
+        else:
+            n_pack += 1
+    assert n_pack >= 20 and n_ids >= 5
