@@ -184,7 +184,10 @@ def _configure_dense_session(conn: "DenseConnection", mode: str) -> None:
 # --------------------------------------------------------------------------- filters -> bitmap
 def _filter_spec(store: DenseStore, filters: Optional[RetrieveFilters],
                  call_ids: Optional[Sequence[Any]]) -> Dict[str, Any]:
-    """_build_filter_clause (app/retrieve.py:93-120) as store codes: call slots, dates, tag mask."""
+    """_build_filter_clause (app/retrieve.py:93-120) as store codes: call slots, dates, tag mask.  Like the
+    reference, no filters object means no predicate at all (call_ids are only ever resolved FROM filters)."""
+    if not filters:
+        return dict(call_slots=None, date_from=None, date_to=None, tag_mask=None)
     date_from = (filters.date_from or None) if filters else None
     date_to = (filters.date_to or None) if filters else None
     tags = list(filters.call_tags) if (filters and filters.call_tags) else None
@@ -743,6 +746,7 @@ def fetch_chunks_dense_hierarchical(conn: DenseConnection, query_embedding, filt
       3. ``chunks`` is searched *scoped to those calls* -- the K6 bitmap restricts the K1 scan, and the
          planner sees a scoped query, so small shortlists run in mode "exact".
     Returns the artifact rows, the shortlist, the scoped chunk rows and the planner decisions."""
+    filters = filters or RetrieveFilters()        # the shortlist below scopes the chunk search even without user filters
     art_count = _estimate_dense_candidates(conn, "artifact_chunks", filters, call_ids)
     art_mode = _choose_dense_mode(art_count, filters, call_ids)
     artifacts = _fetch_artifacts_dense(conn, query_embedding, filters, call_ids, art_mode, artifact_limit)

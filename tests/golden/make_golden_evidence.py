@@ -144,6 +144,56 @@ def run_reference(ref, case):
             setattr(R, name, value)
 
 
+def resolve_cases(ref):
+    """_resolve_call_ids (app/retrieve.py:46-90) against a stand-in `calls` table: the fake connection answers
+    the function's two SELECTs from the bound parameters (external_source IS NOT DISTINCT FROM :external_source)."""
+    from uuid import UUID
+    calls = [(UUID(int=i + 1), f"ext-{i // 3}", [None, "crm", "zoom"][i % 3]) for i in range(18)]
+    calls.append((UUID(int=100), "ext-2", "crm"))        # same (external_id, source) on two calls
+
+    class _Result:
+        def __init__(self, rows):
+            self._rows = rows
+
+        def fetchall(self):
+            return self._rows
+
+    class _Conn:
+        def execute(self, _sql, params):
+            rows = [(c,) for c, ext, src in calls
+                    if ext == params["external_id"] and ("external_source" not in params or src == params["external_source"])]
+            return _Result(rows)
+
+    F = ref.schemas.RetrieveFilters
+    specs = [None, {}, {"call_ids": []}, {"call_ids": [str(calls[4][0]), str(calls[0][0])]}, {"external_id": "ext-2"},
+             {"external_id": "ext-2", "external_source": "crm"}, {"external_id": "ext-2", "external_source": "teams"},
+             {"external_id": "missing"}, {"external_id": "ext-1", "call_ids": [str(calls[3][0]), str(calls[9][0])]},
+             {"external_id": "ext-1", "call_ids": [str(calls[9][0])]}, {"external_id": "", "call_ids": [str(calls[2][0])]},
+             {"external_source": "crm"}, {"call_tags": ["a"]}]
+    out = []
+    for spec in specs:
+        filters = None if spec is None else F(**spec)
+        got = ref.retrieve._resolve_call_ids(_Conn(), filters)
+        out.append({"filters": spec, "call_ids": None if got is None else [str(c) for c in got]})
+    return {"calls": [[str(c), ext, src] for c, ext, src in calls], "cases": out}
+
+
+def filter_clause_cases(ref):
+    """_build_filter_clause (app/retrieve.py:93-120): which predicates a filter produces."""
+    from datetime import datetime, timezone
+    F = ref.schemas.RetrieveFilters
+    t = datetime(2026, 2, 9, tzinfo=timezone.utc)
+    out = []
+    for spec, call_ids in [(None, None), ({}, None), ({"date_from": t}, None), ({"date_to": t}, ["x"]), ({"call_tags": ["a", "b"]}, None),
+                           ({"date_from": t, "date_to": t, "call_tags": ["z"]}, []), ({}, ["x", "y"]), ({"call_tags": []}, None),
+                           (None, ["x"])]:
+        filters = None if spec is None else F(**spec)
+        where, params, join = ref.build_filter_clause(filters, "chunks", call_ids)
+        out.append({"filters": None if spec is None else {k: (v.isoformat() if hasattr(v, "isoformat") else v) for k, v in spec.items()},
+                    "call_ids": call_ids, "where": where, "param_keys": sorted(params), "join_calls": join})
+    return out
+
+
 def main():
     ref = ref_stub.load()
     rng = random.Random(20260210)
@@ -156,6 +206,7 @@ def main():
         json.dump({"settings": {"embeddings_exact_scan_threshold": ref.settings.embeddings_exact_scan_threshold,
                                 "embeddings_hnsw_ef_search": ref.settings.embeddings_hnsw_ef_search},
                    "corpus": {"chunks": list(chunks.values()), "artifacts": list(artifacts.values())},
+                   "resolve_call_ids": resolve_cases(ref), "filter_clause": filter_clause_cases(ref),
                    "cases": out}, f, default=str, separators=(",", ":"))
     print(f"wrote {path}: {len(out)} cases, {os.path.getsize(path)} bytes")
 

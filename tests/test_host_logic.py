@@ -425,3 +425,50 @@ def test_retrieve_evidence_matches_reference_golden(monkeypatch, golden_dir):
         else:
             n_pack += 1
     assert n_pack >= 20 and n_ids >= 5
+
+
+def test_resolve_call_ids_and_filter_clause_match_reference_golden(golden_dir):
+    """_resolve_call_ids (app/retrieve.py:46-90) and _build_filter_clause (:93-120), run live by
+    tests/golden/make_golden_evidence.py against a stand-in `calls` table, vs our external-id map / _filter_spec."""
+    from uuid import UUID
+    from cadence_rag_b200.retrieve import DenseEngine, _filter_spec, _resolve_call_ids
+    with open(os.path.join(golden_dir, "reference_evidence.json")) as f:
+        gold = json.load(f)
+    eng = DenseEngine()
+    for call_id, ext, src in gold["resolve_call_ids"]["calls"]:
+        eng.register_call(UUID(call_id), external_id=ext, external_source=src)
+    for case in gold["resolve_call_ids"]["cases"]:
+        spec = case["filters"]
+        filters = None
+        if spec is not None:
+            spec = dict(spec)
+            if "call_ids" in spec:
+                spec["call_ids"] = [UUID(c) for c in spec["call_ids"]]
+            filters = RetrieveFilters(**spec)
+        with eng.connect() as conn:
+            got = _resolve_call_ids(conn, filters)
+        assert (None if got is None else [str(c) for c in got]) == case["call_ids"], case
+
+    class _Store:
+        synthetic = None
+        call_ids_by_slot = ["x", "y"]
+
+        def slot_of_call(self, c, create=False):
+            return {"x": 0, "y": 1}.get(c)
+
+        def bits_of_tags(self, tags, create=False):
+            return sum(1 << {"a": 0, "b": 1}.get(t, 63) for t in tags if t in ("a", "b"))
+
+    for case in gold["filter_clause"]:
+        spec = case["filters"]
+        filters = None
+        if spec is not None:
+            spec = {k: (datetime.fromisoformat(v) if k.startswith("date_") else v) for k, v in spec.items()}
+            filters = RetrieveFilters(**spec)
+        ours = _filter_spec(_Store(), filters, case["call_ids"])
+        keys = set(case["param_keys"])
+        assert (ours["date_from"] is not None) == ("date_from" in keys), case
+        assert (ours["date_to"] is not None) == ("date_to" in keys), case
+        assert (ours["call_slots"] is not None) == ("call_ids" in keys), case
+        assert (ours["tag_mask"] is not None) == ("call_tags" in keys) == case["join_calls"], case
+        assert (case["where"] == "TRUE") == all(v is None for v in ours.values())
