@@ -440,45 +440,134 @@ def _fused_path_ok(engine: DenseEngine, table: str, dense: bool) -> bool:
     return True
 
 
+def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndarray],
+                        token_lists: Sequence[Sequence[str]], filters: Optional[RetrieveFilters],
+                        call_ids: Optional[Sequence[Any]], bm25_rows: Sequence[Sequence[Mapping[str, Any]]],
+                        dense_limit: int, tech_limit: int = DEFAULT_TECH_TOPK,
+                        rrf_k: int = DEFAULT_RRF_K) -> List[Dict[str, Any]]:
+    """All lanes of one table + their fusion for nq requests that share a filter, through ONE
+    `cdr_hybrid_retrieve_host` call.  q32: [nq, dim] float32 or None (dense lane disabled); token_lists and
+    bm25_rows: one entry per request.  Returns, per request, {"tech": rows, "dense": rows, "count": COUNT(*),
+    "ranked": [(row, lane-name set, score)]} with the rows / order the step-by-step functions produce."""
+    store = conn.store(table)
+    key = store.key_field
+    nq = len(token_lists)
+    if q32 is not None:
+        want = max(1, int(settings.embeddings_dim))
+        if q32.shape[1] != want or q32.shape[1] != store.dim:
+            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[1]}")
+    spec = _filter_spec(store, filters, call_ids)
+    dev_index = conn.engine.device_tech_indexes.get(table) if any(token_lists) else None
+    tok = nt = None
+    if dev_index is not None:
+        tok, nt = dev_index.encode_tokens([list(t) for t in token_lists])
+    counts = [len(rows) for rows in bm25_rows]
+    bm25_ids = np.fromiter((int(r[key]) for rows in bm25_rows for r in rows), dtype=np.int64, count=sum(counts))
+    bm25_off = np.zeros(nq + 1, dtype=np.int32)
+    np.cumsum(counts, out=bm25_off[1:])
+    res = store.hybrid_retrieve(q32, dense_limit, tech_index=dev_index, token_ids=tok, n_tokens=nt,
+                                tech_limit=tech_limit, bm25_ids=bm25_ids, bm25_offsets=bm25_off, rrf_k=rrf_k,
+                                filter_spec=spec)
+    n_lanes = 3 if q32 is not None else 2
+    out = []
+    for qi in range(nq):
+        tech_rows = _rows_from_ids(store, res["tech_ids"][qi, :int(res["tech_n"][qi])])
+        dense_rows: List[Dict[str, Any]] = []
+        if q32 is not None:
+            m = int(res["dense_n"][qi])
+            dense_rows = _rows_from_hits(store, res["dense_ids"][qi, :m], res["dense_scores"][qi, :m])
+        items: Dict[int, Mapping[str, Any]] = {}
+        for lane in (bm25_rows[qi], tech_rows, dense_rows):
+            for row in lane:
+                items.setdefault(int(row[key]), row)
+        ranked = []
+        for i in range(int(res["fused_n"][qi])):
+            mask = int(res["fused_mask"][qi, i])
+            hit = {_LANE_NAMES[l] for l in range(n_lanes) if (mask >> l) & 1}
+            ranked.append((items[int(res["fused_ids"][qi, i])], hit, float(res["fused_scores"][qi, i])))
+        out.append({"tech": tech_rows, "dense": dense_rows, "count": res["count"] if q32 is not None else 0,
+                    "ranked": ranked})
+    return out
+
+
 def _hybrid_table(conn: DenseConnection, table: str, q32: Optional[np.ndarray], tech_tokens: Sequence[str],
                   filters: Optional[RetrieveFilters], call_ids: Optional[Sequence[Any]],
                   bm25_rows: Sequence[Mapping[str, Any]], dense_limit: int,
                   tech_limit: int = DEFAULT_TECH_TOPK, rrf_k: int = DEFAULT_RRF_K) -> Dict[str, Any]:
-    """All lanes of one table + their fusion through ONE `cdr_hybrid_retrieve_host` call.  Returns
-    {"tech": rows, "dense": rows, "count": COUNT(*), "ranked": [(row, lane-name set, score)]} with the
-    same rows / order the step-by-step functions produce."""
-    store = conn.store(table)
-    key = store.key_field
-    if q32 is not None:
-        want = max(1, int(settings.embeddings_dim))
-        if q32.shape[0] != want or q32.shape[0] != store.dim:
-            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[0]}")
-    spec = _filter_spec(store, filters, call_ids)
-    dev_index = conn.engine.device_tech_indexes.get(table) if tech_tokens else None
-    tok = nt = None
-    if dev_index is not None:
-        tok, nt = dev_index.encode_tokens([list(tech_tokens)])
-    bm25_ids = np.fromiter((int(r[key]) for r in bm25_rows), dtype=np.int64, count=len(bm25_rows))
-    res = store.hybrid_retrieve(None if q32 is None else q32[None, :], dense_limit, tech_index=dev_index,
-                                token_ids=tok, n_tokens=nt, tech_limit=tech_limit, bm25_ids=bm25_ids,
-                                bm25_offsets=np.array([0, bm25_ids.size], dtype=np.int32), rrf_k=rrf_k,
-                                filter_spec=spec)
-    tech_rows = _rows_from_ids(store, res["tech_ids"][0, :int(res["tech_n"][0])])
-    dense_rows: List[Dict[str, Any]] = []
-    if q32 is not None:
-        m = int(res["dense_n"][0])
-        dense_rows = _rows_from_hits(store, res["dense_ids"][0, :m], res["dense_scores"][0, :m])
-    items: Dict[int, Mapping[str, Any]] = {}
-    for lane in (bm25_rows, tech_rows, dense_rows):
-        for row in lane:
-            items.setdefault(int(row[key]), row)
-    ranked = []
-    n_lanes = 3 if q32 is not None else 2
-    for i in range(int(res["fused_n"][0])):
-        mask = int(res["fused_mask"][0, i])
-        hit = {_LANE_NAMES[l] for l in range(n_lanes) if (mask >> l) & 1}
-        ranked.append((items[int(res["fused_ids"][0, i])], hit, float(res["fused_scores"][0, i])))
-    return {"tech": tech_rows, "dense": dense_rows, "count": res["count"] if q32 is not None else 0, "ranked": ranked}
+    """One request (see _hybrid_table_batch)."""
+    return _hybrid_table_batch(conn, table, None if q32 is None else q32[None, :], [list(tech_tokens)], filters,
+                               call_ids, [list(bm25_rows)], dense_limit, tech_limit, rrf_k)[0]
+
+
+def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters: Optional[RetrieveFilters] = None,
+                       bm25_chunks: Optional[Sequence[Sequence[Mapping[str, Any]]]] = None,
+                       bm25_artifacts: Optional[Sequence[Sequence[Mapping[str, Any]]]] = None,
+                       debug: bool = False) -> List[Dict[str, Any]]:
+    """`retrieve_ids` for a batch of concurrent requests that share one filter (not in the reference, which
+    serves one query per request): one embedding call, then ONE fused C call per table for the whole batch
+    (shared corpus reads on the dense lane) instead of one per request.  Returns one response per query, each
+    equal to what `retrieve_ids` returns for it.  Falls back to per-request calls when a table cannot take the
+    fused path."""
+    n = len(queries)
+    bm25_chunks = [list(r) for r in bm25_chunks] if bm25_chunks is not None else [[] for _ in range(n)]
+    bm25_artifacts = [list(r) for r in bm25_artifacts] if bm25_artifacts is not None else [[] for _ in range(n)]
+    if len(bm25_chunks) != n or len(bm25_artifacts) != n:
+        raise ValueError("one BM25 lane per query is required")
+    cleaned = [q.strip() for q in queries]
+    live = [i for i, q in enumerate(cleaned) if q]
+    tables = [t for t in ("chunks", "artifact_chunks") if t in engine.stores]
+    dense_enabled = embeddings_enabled()
+    if not live or not tables or not all(_fused_path_ok(engine, t, dense_enabled) for t in tables):
+        return [retrieve_ids(engine, q, filters, bm25_chunks=bm25_chunks[i], bm25_artifacts=bm25_artifacts[i], debug=debug)
+                for i, q in enumerate(queries)]
+    dense_error: Optional[str] = None
+    dense_model_id: Optional[str] = None
+    q32 = None
+    if dense_enabled:
+        try:
+            embedded = embed_texts([cleaned[i] for i in live])
+            dense_model_id = embedded.model
+            q32 = np.stack([_embedding_f32(v) for v in embedded.vectors])
+        except EmbeddingClientError as exc:
+            dense_enabled = False
+            dense_error = str(exc)
+    token_lists = [extract_tech_tokens(cleaned[i]) for i in live]
+    limits = {"chunks": DEFAULT_DENSE_CHUNK_TOPK, "artifact_chunks": DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK}
+    bm25 = {"chunks": [bm25_chunks[i] for i in live], "artifact_chunks": [bm25_artifacts[i] for i in live]}
+    with engine.connect() as conn:
+        call_ids = _resolve_call_ids(conn, filters)
+        per_table: Dict[str, List[Dict[str, Any]]] = {}
+        try:
+            for t in tables:
+                per_table[t] = _hybrid_table_batch(conn, t, q32 if dense_enabled else None, token_lists, filters,
+                                                   call_ids, bm25[t], limits[t])
+        except DenseEngineError as exc:       # fail open to lexical-only, like EmbeddingClientError
+            if not dense_enabled:
+                raise
+            dense_enabled = False
+            dense_error = str(exc)
+            for t in tables:
+                per_table[t] = _hybrid_table_batch(conn, t, None, token_lists, filters, call_ids, bm25[t], limits[t])
+    empty = {"tech": [], "dense": [], "count": 0, "ranked": []}
+    responses: List[Dict[str, Any]] = [{"retrieved_ids": []} for _ in range(n)]
+    for j, i in enumerate(live):
+        ch = per_table["chunks"][j] if "chunks" in per_table else empty
+        ar = per_table["artifact_chunks"][j] if "artifact_chunks" in per_table else empty
+        modes: Dict[str, Optional[str]] = {"chunks": None, "artifact_chunks": None}
+        candidates = {"chunks": 0, "artifact_chunks": 0}
+        if dense_enabled:
+            for t in tables:
+                candidates[t] = per_table[t][j]["count"]
+                modes[t] = _choose_dense_mode(candidates[t], filters, call_ids)
+        chunk_ranked, artifact_ranked = ch["ranked"], ar["ranked"]
+        if "chunks" not in per_table:
+            chunk_ranked = _rrf_merge({"bm25": bm25_chunks[i], "tech_tokens": []}, "chunk_id")
+        if "artifact_chunks" not in per_table:
+            artifact_ranked = _rrf_merge({"bm25": bm25_artifacts[i], "tech_tokens": []}, "artifact_chunk_id")
+        responses[i] = _ids_response(chunk_ranked, artifact_ranked, bm25_chunks[i], bm25_artifacts[i], ch["tech"], ar["tech"],
+                                     ch["dense"], ar["dense"], dense_enabled, dense_model_id, dense_error, modes,
+                                     candidates, debug)
+    return responses
 
 
 # --------------------------------------------------------------------------- ids_only retrieve

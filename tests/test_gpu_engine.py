@@ -607,6 +607,22 @@ def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
     assert fused == step
     assert fused["debug"]["dense"]["enabled"] is False and len(fused["retrieved_ids"]) > 4
 
+    # facade batch: retrieve_ids_batch == [retrieve_ids(q) ...], incl. blank queries and per-query BM25 lanes
+    embeddings.set_embedder(emb)
+    monkeypatch.setattr(settings, "embeddings_base_url", "http://embedder")
+    try:
+        qlist = ["TOK-1 outage on 10.0.0.1", "   ", "TOK-2 and TOK-5", "no tokens at all", "TOK-7 TOK-9 TOK-11"]
+        b_lists = [bm25, [], [], bm25[:2], []]
+        a_lists = [[], [], bm25a, [], bm25a[:1]]
+        for filters in (None, cases[1][1], cases[7][1]):
+            many = retrieve.retrieve_ids_batch(eng, qlist, filters, bm25_chunks=b_lists, bm25_artifacts=a_lists, debug=True)
+            for i, q in enumerate(qlist):
+                one = retrieve.retrieve_ids(eng, q, filters, bm25_chunks=b_lists[i], bm25_artifacts=a_lists[i], debug=True)
+                assert many[i] == one, (i, q, filters)
+    finally:
+        embeddings.set_embedder(None)
+        monkeypatch.setattr(settings, "embeddings_base_url", "")
+
     # batched form: nq queries in one call == nq single calls
     store = eng.stores["chunks"]; dev_index = eng.device_tech_indexes["chunks"]
     qs = orc.synth_rows(SYNTH_QUERY_SEED, 100, 5)
