@@ -348,6 +348,22 @@ def run_batch_bf16(args):
         e_ids, _, _ = searcher.search(q_dev[total - 1][:nr].contiguous(), TOPK, mode="exact")
         got = out[0][:nr].cpu().numpy(); want = e_ids.cpu().numpy()
         recall = float(np.mean([len(set(got[i]) & set(want[i])) / TOPK for i in range(nr)]))
+    # the exact fp32 lane over the same (sharded) corpus, one query per request: device-timed latency
+    exact_q1 = None
+    if store.has_fp32:
+        for i in range(3):
+            searcher.search(q_dev[0][i:i + 1].contiguous(), TOPK, mode="exact")
+        barrier()
+        xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        xa.record()
+        for i in range(20):
+            searcher.search(q_dev[1][i:i + 1].contiguous(), TOPK, mode="exact")
+        xb.record()
+        barrier()
+        xt = torch.tensor([xa.elapsed_time(xb) / 20], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(xt, op=dist.ReduceOp.MAX)
+        exact_q1 = {"ms_per_query": float(xt[0]), "hbm_gbs_per_gpu": float(count) * DIM * 4 / (float(xt[0]) / 1e3) / 1e9}
     # e2e with host buffers (pinned): H2D of the queries + D2H of the merged result every step
     q_pinned = torch.empty(q_dev.shape, dtype=torch.float32, pin_memory=True)
     q_pinned.copy_(q_dev); torch.cuda.synchronize()
@@ -395,7 +411,7 @@ def run_batch_bf16(args):
                            "rows": rows, "rows_per_gpu": count, "dim": DIM, "k": TOPK, "queries_per_step": nq,
                            "resident": "bf16 only" if args.bf16_only else "fp32 + bf16",
                            "l2": "inputs larger than L2", "recall_at_50_vs_exact_fp32_lane": recall,
-                           "exchange": searcher.transport},
+                           "exchange": searcher.transport, "exact_fp32_lane_single_query": exact_q1},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": None if tt is None else {"value": args.steps * nq / float(tt[0]), "unit": UNIT,
                                                 "h2d_bytes_per_step": nq * DIM * 4,
