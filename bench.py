@@ -790,6 +790,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args.rows, args.cpu_sample_rows, args.cpu_sample_queries, 0)
             one = cpu_baseline(args.rows, min(args.cpu_sample_rows, 50_000), 4, 1, target_seconds=4.0)
             line["cpu_baseline"]["single_thread_value"] = one["value"]
+            # the reference's other dense path (mode "ann": HNSW, ef_search = 80), restated, in the same run
+            line["cpu_baseline_hnsw"] = cpu_baseline_hnsw(args.hnsw_rows, 0, target_seconds=5.0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
