@@ -1,24 +1,40 @@
-"""Write side of the dense lane over the resident store -- the reference's app/embedding_pipeline.py
-(`embed_backfill`) with the SQL replaced by store calls:
+"""Write side of the dense lane over the resident store.
 
-  _fetch_pending_rows   :121-146   rows WHERE embedding IS NULL AND text not empty, ORDER BY id LIMIT n
-  _embed_texts_adaptive :83-118    embed in batches, halve the batch when the provider rejects its size
-  _update_embeddings    :149-168   UPDATE ... SET embedding = CAST(:e AS vector(D)) WHERE id = :row_id
-  _backfill_table       :210-238   loop until no row is pending
-  run_embedding_backfill:241-282   all tables -> BackfillSummary
+The reference backfills embeddings with `embed_backfill` (app/embedding_pipeline.py): rows are ingested
+with `embedding IS NULL`, later selected in id order, embedded in batches that shrink when the
+provider rejects their size, and written back one `UPDATE ... SET embedding = CAST(:e AS vector(D))`
+per row.  Here the table is a `DenseStore`: the pending set comes from its validity bitmap and
+payload texts, the write is `DenseStore.update_embeddings` (one kernel per batch, in place).
 
-The texts come from the payload registered with the store (`text` for chunks, `content` for
-artifact_chunks -- the reference's TableSpec.text_column).  The ingestion_runs bookkeeping
-(:171-207) is Postgres-side metadata and stays there."""
+Same entry points as the reference so the call sites read alike:
+
+  infer_batch_size_limit   :57-85     provider error text -> the batch limit it names
+  _embed_texts_adaptive    :88-118    embed, shrinking the batch on provider errors
+  _fetch_pending_rows      :121-146   WHERE embedding IS NULL AND text not blank ORDER BY id LIMIT n
+  _update_embeddings       :149-168   the per-row UPDATE
+  _backfill_table          :210-238   until nothing is pending
+  run_embedding_backfill   :241-282   every table -> BackfillSummary
+
+The ingestion_runs bookkeeping (:171-207) is Postgres-side metadata and stays there.
+"""
 from __future__ import annotations
 
 import re
 from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
+from typing import Any, Dict, Iterator, List, Optional, Sequence, Set, Tuple
 
 from .config import settings
 from .embeddings import EmbeddingClientError, EmbeddingResult, embed_texts, embeddings_enabled
 from .store import DenseStore
+
+# which payload column holds the text that gets embedded (the reference's TableSpec.text_column)
+_TEXT_COLUMN = {"chunks": "text", "artifact_chunks": "content"}
+
+# provider messages that name their limit: "... batch-size must be <= 8 ...", "maximum batch size ... 16"
+_LIMIT_IN_MESSAGE = [re.compile(rx, re.IGNORECASE) for rx in (
+    r"batch[- ]size[^0-9]{0,40}<=\s*(\d+)",
+    r"max(?:imum)?\s+batch[- ]size[^0-9]{0,40}(\d+)",
+)]
 
 
 @dataclass
@@ -36,94 +52,105 @@ class BackfillSummary:
     per_table: Dict[str, int] = field(default_factory=dict)
 
 
-_TEXT_COLUMN = {"chunks": "text", "artifact_chunks": "content"}
-
-
-# provider messages that name their batch limit: "... batch-size must be <= 8 ...", "maximum batch size ... 16"
-_BATCH_SIZE_LIMIT_PATTERNS = (
-    re.compile(r"batch[- ]size[^0-9]{0,40}<=\s*(\d+)", re.IGNORECASE),
-    re.compile(r"max(?:imum)?\s+batch[- ]size[^0-9]{0,40}(\d+)", re.IGNORECASE),
-)
-
-
 def infer_batch_size_limit(error_message: str) -> Optional[int]:
-    """Provider error text -> the batch limit it names, if any (app/embedding_pipeline.py:57-85)."""
-    message = (error_message or "").strip()
-    if not message:
-        return None
-    for pattern in _BATCH_SIZE_LIMIT_PATTERNS:
-        m = pattern.search(message)
-        if not m:
+    text = (error_message or "").strip()
+    for rx in _LIMIT_IN_MESSAGE if text else ():
+        found = rx.search(text)
+        if found is None:
             continue
         try:
-            value = int(m.group(1))
+            limit = int(found.group(1))
         except (TypeError, ValueError):
             continue
-        if value > 0:
-            return value
+        if limit > 0:
+            return limit
     return None
 
 
 def _embed_texts_adaptive(texts: Sequence[str], batch_size: int) -> EmbeddingResult:
-    cleaned = list(texts)
-    vectors: List[List[float]] = []
-    model_used = settings.embeddings_model_id
-    current_batch = max(1, batch_size)
-    index = 0
-    while index < len(cleaned):
-        upper = min(len(cleaned), index + current_batch)
-        chunk = cleaned[index:upper]
+    """Embed `texts` in order.  A provider error on a batch of more than one text shrinks the batch -- to the
+    limit the message names when it names a smaller one, else to half -- and the same position is retried; the
+    smaller size sticks for the rest of the run.  An error on a single text is final."""
+    pending = list(texts)
+    size = max(1, batch_size)
+    done = 0
+    rows: List[List[float]] = []
+    model = settings.embeddings_model_id
+    while done < len(pending):
+        window = pending[done:done + size]
         try:
-            result = embed_texts(chunk)
+            part = embed_texts(window)
         except EmbeddingClientError as exc:
-            if len(chunk) <= 1:
+            if len(window) <= 1:
                 raise
-            inferred = infer_batch_size_limit(str(exc))
-            current_batch = max(1, inferred) if inferred is not None and inferred < len(chunk) else max(1, len(chunk) // 2)
-            continue
-        vectors.extend(result.vectors)
-        model_used = result.model
-        index = upper
-    return EmbeddingResult(vectors=vectors, model=model_used)
+            named = infer_batch_size_limit(str(exc))
+            size = max(1, named if (named is not None and named < len(window)) else len(window) // 2)
+        else:
+            rows += part.vectors
+            model = part.model
+            done += len(window)
+    return EmbeddingResult(vectors=rows, model=model)
+
+
+class _TableBackfill:
+    """The pending-rows / embed / update loop over one resident table."""
+
+    def __init__(self, store: DenseStore, batch_size: int, call_id: Any = None):
+        self.store = store
+        self.batch_size = batch_size
+        self.call_id = call_id
+        self.text_column = _TEXT_COLUMN.get(store.table_name, "text")
+
+    def _call_of(self, row_id: int) -> Any:
+        cols = self.store.host_columns()
+        slot = int(cols["call_slot"][int(cols["ids"].searchsorted(row_id))])
+        known = self.store.call_ids_by_slot
+        return known[slot] if slot < len(known) else slot
+
+    def pending(self, limit: int) -> List[PendingRow]:
+        picked: List[PendingRow] = []
+        for row_id in self.store.pending_ids(None, self.call_id).tolist():
+            content = self.store.payload.get(row_id, {}).get(self.text_column)
+            if content is None or str(content).strip() == "":
+                continue                      # text IS NOT NULL AND length(trim(text)) > 0
+            picked.append(PendingRow(row_id=row_id, call_id=self._call_of(row_id), content=str(content)))
+            if len(picked) == limit:
+                break
+        return picked
+
+    def apply(self, rows: Sequence[PendingRow], vectors: Sequence[Sequence[float]]) -> None:
+        if len(rows) != len(vectors):
+            raise RuntimeError(f"row/vector mismatch for {self.store.table_name}: {len(rows)} rows vs {len(vectors)} vectors")
+        self.store.update_embeddings([row.row_id for row in rows], vectors)
+
+    def batches(self) -> Iterator[Tuple[List[PendingRow], EmbeddingResult]]:
+        while True:
+            rows = self.pending(self.batch_size)
+            if not rows:
+                return
+            embedded = _embed_texts_adaptive([row.content for row in rows], batch_size=self.batch_size)
+            self.apply(rows, embedded.vectors)
+            yield rows, embedded
+
+    def run(self) -> Tuple[int, Set[Any], str]:
+        updated, calls, model = 0, set(), settings.embeddings_model_id
+        for rows, embedded in self.batches():
+            updated += len(rows)
+            calls.update(row.call_id for row in rows)
+            model = embedded.model
+        return updated, calls, model
 
 
 def _fetch_pending_rows(store: DenseStore, limit: int, call_id: Any = None) -> List[PendingRow]:
-    text_column = _TEXT_COLUMN.get(store.table_name, "text")
-    cols = store.host_columns()
-    out: List[PendingRow] = []
-    for row_id in store.pending_ids(None, call_id).tolist():
-        content = store.payload.get(row_id, {}).get(text_column)
-        if content is None or not str(content).strip():
-            continue                                   # AND text IS NOT NULL AND length(trim(text)) > 0
-        pos = int(cols["ids"].searchsorted(row_id))
-        slot = int(cols["call_slot"][pos])
-        call = store.call_ids_by_slot[slot] if slot < len(store.call_ids_by_slot) else slot
-        out.append(PendingRow(row_id=row_id, call_id=call, content=str(content)))
-        if len(out) >= limit:
-            break
-    return out
+    return _TableBackfill(store, limit, call_id).pending(limit)
 
 
 def _update_embeddings(store: DenseStore, rows: Sequence[PendingRow], vectors: Sequence[Sequence[float]]) -> None:
-    if len(rows) != len(vectors):
-        raise RuntimeError(f"row/vector mismatch for {store.table_name}: {len(rows)} rows vs {len(vectors)} vectors")
-    store.update_embeddings([r.row_id for r in rows], vectors)
+    _TableBackfill(store, max(1, len(rows))).apply(rows, vectors)
 
 
 def _backfill_table(store: DenseStore, *, batch_size: int, call_id: Any = None) -> Tuple[int, Set[Any], str]:
-    updated = 0
-    touched: Set[Any] = set()
-    model_used = settings.embeddings_model_id
-    while True:
-        batch = _fetch_pending_rows(store, batch_size, call_id=call_id)
-        if not batch:
-            break
-        result = _embed_texts_adaptive([row.content for row in batch], batch_size=batch_size)
-        _update_embeddings(store, batch, result.vectors)
-        touched.update(row.call_id for row in batch)
-        updated += len(batch)
-        model_used = result.model
-    return updated, touched, model_used
+    return _TableBackfill(store, batch_size, call_id).run()
 
 
 def run_embedding_backfill(stores: Sequence[DenseStore], *, batch_size: int, call_id: Any = None) -> BackfillSummary:
@@ -133,13 +160,12 @@ def run_embedding_backfill(stores: Sequence[DenseStore], *, batch_size: int, cal
         raise RuntimeError("EMBEDDINGS_DIM must be > 0")
     if batch_size <= 0:
         raise RuntimeError("EMBEDDINGS_BATCH_SIZE must be > 0")
-    total = 0
-    calls: Set[Any] = set()
-    model_used = settings.embeddings_model_id
-    per_table: Dict[str, int] = {}
+    summary = BackfillSummary(rows_updated=0, calls_touched=0, model_used=settings.embeddings_model_id)
+    touched: Set[Any] = set()
     for store in stores:
-        updated, touched, model_used = _backfill_table(store, batch_size=batch_size, call_id=call_id)
-        per_table[store.table_name] = updated
-        total += updated
-        calls |= touched
-    return BackfillSummary(rows_updated=total, calls_touched=len(calls), model_used=model_used, per_table=per_table)
+        updated, calls, summary.model_used = _backfill_table(store, batch_size=batch_size, call_id=call_id)
+        summary.per_table[store.table_name] = updated
+        summary.rows_updated += updated
+        touched |= calls
+    summary.calls_touched = len(touched)
+    return summary
