@@ -472,3 +472,17 @@ def test_resolve_call_ids_and_filter_clause_match_reference_golden(golden_dir):
         assert (ours["call_slots"] is not None) == ("call_ids" in keys), case
         assert (ours["tag_mask"] is not None) == ("call_tags" in keys) == case["join_calls"], case
         assert (case["where"] == "TRUE") == all(v is None for v in ours.values())
+
+
+def test_embedding_f32_equals_the_literal_round_trip():
+    """retrieve._embedding_f32 == CAST(_vector_literal(v) AS vector): the float32-representable shortcut and the
+    text path agree, for float32 inputs, fp64 decimals (a JSON body), tiny / huge magnitudes and NaN."""
+    rng = np.random.default_rng(9)
+    f32 = rng.standard_normal(1024).astype(np.float32)
+    f64 = rng.standard_normal(1024) * 10.0 ** rng.integers(-12, 6, size=1024)
+    for values in (f32.astype(np.float64).tolist(), f64.tolist(), [0.1, 1 / 3, 1e-12, -0.0, 1.0, 3.4e38, 1e-45, float("nan")]):
+        via_text = retrieve._query_vector(retrieve._vector_literal(values))
+        got = retrieve._embedding_f32(values)
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), via_text.view(np.uint32)) or \
+            (np.isnan(got).any() and np.array_equal(np.isnan(got), np.isnan(via_text)))
+    assert np.array_equal(retrieve._embedding_f32(f32.astype(np.float64).tolist()), f32)
