@@ -352,12 +352,12 @@ def run_batch_bf16(args):
     exact_q1 = None
     if store.has_fp32:
         for i in range(3):
-            searcher.search(q_dev[0][i:i + 1].contiguous(), TOPK, mode="exact")
+            searcher.search(q_dev[0][i % nq:i % nq + 1].contiguous(), TOPK, mode="exact")
         barrier()
         xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         xa.record()
         for i in range(20):
-            searcher.search(q_dev[1][i:i + 1].contiguous(), TOPK, mode="exact")
+            searcher.search(q_dev[1][i % nq:i % nq + 1].contiguous(), TOPK, mode="exact")
         xb.record()
         barrier()
         xt = torch.tensor([xa.elapsed_time(xb) / 20], dtype=torch.float64, device="cuda")
