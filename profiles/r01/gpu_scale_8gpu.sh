@@ -2,7 +2,7 @@
 # 8-GPU box: scaling points of the contract line (K1, 1M rows, strong scaling) with both exchange transports,
 # single-query latency at 8 GPUs, and BASELINE configs[4] (100M x 1024 bf16 over 8 and 4 GPUs).
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
-T=e10
+T=${1:-e10}
 run() { # N extra-args... ; output name in $OUT
   local n=$1; shift
   timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 200)) bench.py --gpus $n "$@"
