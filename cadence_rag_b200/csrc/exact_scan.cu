@@ -286,18 +286,63 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
 
+            if constexpr (QPC == 1) {
 #pragma unroll
-            for (int r = 0; r < RPW; ++r) {
-                const int64_t row = gather ? (int64_t)g_row[r] : row0 + r;
-                const bool ok = (row < p.n_rows) && ((allow_bits >> r) & 1u);
-#pragma unroll
-                for (int u = 0; u < QPC; ++u) {
-                    const float dot = warp_sum_f32(acc[u][r][0] + acc[u][r][1]);
+                for (int r = 0; r < RPW; ++r) {
+                    const int64_t row = gather ? (int64_t)g_row[r] : row0 + r;
+                    const bool ok = (row < p.n_rows) && ((allow_bits >> r) & 1u);
+                    const float dot = warp_sum_f32(acc[0][r][0] + acc[0][r][1]);
                     if (ok) {
-                        const float score = dot * inv_n[r] * inv_qn[u];
+                        const float score = dot * inv_n[r] * inv_qn[0];
                         const uint64_t key = cdr_pack_key(score, (uint32_t)row);
-                        if (key > top[u].tau) top[u].push(key, lane);
+                        if (key > top[0].tau) top[0].push(key, lane);
                     }
+                }
+            } else {
+                // QPC*RPW (<= 8) dot products are reduced TOGETHER: at offsets 16, 8, 4 every lane keeps half of its
+                // values and hands the other half to its partner, so after three exchanges the four lanes of group
+                // g = lane/4 own value g, and two more butterfly steps finish it -- 9 shuffles instead of 5 per
+                // value.  A lane adds exactly what the plain butterfly adds at every level (own + partner), so the
+                // sums are bit-identical.  The four-lane group of value v = u*RPW + r then scores, packs and tests
+                // its candidate in parallel; the rare survivors are inserted one by one.
+                constexpr int V = QPC * RPW;
+                static_assert(V <= 8, "the transposed reduction handles at most 8 values");
+                float a8[8];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) a8[v] = v < V ? acc[v / RPW][v % RPW][0] + acc[v / RPW][v % RPW][1] : 0.f;
+                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+                float h4[4], h2[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    h4[i] = (b4 ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a8[i] : a8[i + 4], 16);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    h2[i] = (b3 ? h4[i + 2] : h4[i]) + __shfl_xor_sync(0xffffffffu, b3 ? h4[i] : h4[i + 2], 8);
+                float dot = (b2 ? h2[1] : h2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? h2[0] : h2[1], 4);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                const int v = (lane >> 2) & 7;                 // the value this lane group owns
+                const int vu = v / RPW, vr = v % RPW;
+                float s_inv_n = inv_n[0], s_inv_q = inv_qn[0];
+                uint64_t s_tau = top[0].tau;
+                int64_t s_row = gather ? (int64_t)g_row[0] : row0;
+#pragma unroll
+                for (int r = 1; r < RPW; ++r)
+                    if (vr == r) { s_inv_n = inv_n[r]; s_row = gather ? (int64_t)g_row[r] : row0 + r; }
+#pragma unroll
+                for (int u = 1; u < QPC; ++u)
+                    if (vu == u) { s_inv_q = inv_qn[u]; s_tau = top[u].tau; }
+                const bool s_ok = v < V && (s_row < p.n_rows) && ((allow_bits >> vr) & 1u);
+                const uint64_t key = cdr_pack_key(dot * s_inv_n * s_inv_q, (uint32_t)s_row);
+                unsigned pend = __ballot_sync(0xffffffffu, s_ok && key > s_tau) & 0x11111111u;
+                while (pend) {                                 // rare; warp-uniform
+                    const int src = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    const uint64_t k1 = __shfl_sync(0xffffffffu, key, src);
+                    const int su = (src >> 2) / RPW;
+#pragma unroll
+                    for (int u = 0; u < QPC; ++u)
+                        if (su == u && k1 > top[u].tau) top[u].push(k1, lane);   // re-tested: an earlier insert may have raised tau
                 }
             }
         }
