@@ -11,8 +11,12 @@ A "step" is one batch of Q distinct single-query scans (Q = --queries-per-step, 
 the resident corpus: every query reads every row once (no cross-query reuse: the corpus is far
 larger than L2), keeps its top-(k+14) in the scan kernel, is re-scored in fp64 and ordered.  With
 N > 1 the 1M-row corpus is row-sharded (strong scaling: total work fixed), each rank scans its
-shard, and the per-rank top-k lists are exchanged with ONE NCCL all-gather per step and merged
-by the K4 kernel on every rank.
+shard, and the per-rank top-k lists are exchanged and merged on every rank -- by the K4p peer-memory
+kernel over NVLink (default), or ONE NCCL all-gather + the K4 kernel (CADENCE_EXCHANGE=nccl).
+
+Other lines: --workload batch_bf16 (configs[2]; under torchrun configs[4]), --workload hybrid
+(configs[3] + configs[0]).  The default line also carries `exact_batch_shared_reads` (the same steps with
+3 queries sharing every streamed tile; informational) and the CPU baselines (exact scan + HNSW, restated).
 
 value    : whole-job queries/sec with the queries already resident in HBM (device-timed).
 e2e      : the same through the facade with HOST buffers (numpy in, numpy out): H2D of the

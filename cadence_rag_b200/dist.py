@@ -1,10 +1,13 @@
 """Row-sharded multi-GPU search: one process per GPU, each owning a contiguous
 row range of the corpus; the query batch is replicated; each rank's local top-k lists are
-exchanged with ONE all-gather (NCCL over NVLink/NVSwitch; gloo in the CPU tests) and merged by
-the K4 kernel with the global ordering rule, so every rank ends with the identical result.
+exchanged and merged with the global ordering rule, so every rank ends with the identical result.
 
-Payload per rank: nq * (2k+1) * 8 bytes (scores f64 + ids i64 + count) -- 103 KB at nq=128,
-k=50; latency-bound, so it is packed into a single buffer / single collective per batch.
+Two transports for the exchange + merge (same bits):
+  peer  one kernel per rank (K4p, csrc/peer.cu): push the local lists into every peer's CUDA-IPC mapped
+        buffer over NVLink, wait for the peers' lists on local memory, merge.  Default on one node.
+  nccl  ONE all-gather of a packed buffer (gloo in the CPU tests) + the K4 merge kernel.  Payload per
+        rank: nq * (2k+1) * 8 bytes (scores f64 + ids i64 + count) -- 103 KB at nq=128, k=50;
+        latency-bound, so it is a single collective per batch.
 """
 from __future__ import annotations
 
