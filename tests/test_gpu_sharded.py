@@ -92,3 +92,121 @@ def test_two_rank_nccl_sharded_equals_whole(tmp_path):
         recall = np.mean([len(set(r["a_ids"][i]) & set(whole["ids"][i])) / k for i in range(whole["ids"].shape[0])])
         assert recall >= 0.999
     assert np.array_equal(r0["a_ids"], r1["a_ids"])       # every rank holds the identical merged result
+
+
+# ----------------------------------------------------------------------------------------- sharded hybrid /retrieve
+def _hybrid_corpus():
+    """Deterministic 2-table corpus (same on every rank): rows, ids, calls, dates, tags, tech tokens, payload."""
+    from datetime import datetime, timedelta, timezone
+    from uuid import UUID
+    sys.path.insert(0, ROOT)
+    from oracle import cpu_oracle as orc
+    rng = np.random.default_rng(23)
+    t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+    tables = {}
+    for name, rows, seed, key in (("chunks", 6000, 20260209, "chunk_id"), ("artifact_chunks", 600, 20260214, "artifact_chunk_id")):
+        x = orc.synth_rows(seed, 0, rows)
+        call_of_row = np.arange(rows) // (rows // 60)
+        # calls are NOT in time order along the rows, so the tech lane's (started_at DESC, id ASC) interleaves shards
+        hour_of_call = rng.permutation(60)
+        zipf = np.minimum(rng.zipf(1.3, size=(rows, 3)) - 1, 99)
+        ntok = rng.integers(0, 4, size=rows)
+        valid = np.ones(rows, dtype=bool); valid[rng.choice(rows, 15, replace=False)] = False
+        tables[name] = dict(x=x, ids=np.arange(1, rows + 1, dtype=np.int64) * 3, key=key, valid=valid,
+                            call_ids=[UUID(int=int(c) + 1) for c in call_of_row],
+                            started=[t0 + timedelta(hours=int(hour_of_call[c])) for c in call_of_row],
+                            tags=[[f"t{c % 5}", f"u{c % 3}"] for c in call_of_row],
+                            tokens=[[f"TOK-{z}" for z in zipf[r, : ntok[r]]] for r in range(rows)],
+                            payload=[{"text": f"{name} row {r}"} for r in range(rows)])
+    return tables, t0
+
+
+def _build_engine(tables, lo_frac, hi_frac, device):
+    from cadence_rag_b200.lexical import TechTokenIndex
+    from cadence_rag_b200.retrieve import DenseEngine
+    from cadence_rag_b200.store import DenseStore
+    from uuid import UUID
+    eng = DenseEngine()
+    for name, t in tables.items():
+        n = len(t["ids"])
+        lo, hi = int(n * lo_frac), int(n * hi_frac)
+        store = DenseStore(name, max(hi - lo, 1), dim=1024, device=device)
+        store.append(t["x"][lo:hi], ids=t["ids"][lo:hi], call_ids=t["call_ids"][lo:hi], call_started_at=t["started"][lo:hi],
+                     call_tags=t["tags"][lo:hi], valid=t["valid"][lo:hi], payload=t["payload"][lo:hi])
+        store.finalize()
+        index = TechTokenIndex()
+        for r in range(lo, hi):
+            index.add_row(r - lo, t["tokens"][r])
+        eng.register(store, index)
+    for c in range(60):
+        eng.register_call(UUID(int=c + 1), external_id=f"ext-{c // 2}", external_source="crm" if c % 2 else None)
+    return eng
+
+
+def _hybrid_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import json
+    from datetime import timedelta
+    from uuid import UUID
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from cadence_rag_b200 import embeddings, retrieve
+    from cadence_rag_b200.config import settings
+    from cadence_rag_b200.retrieve import RetrieveFilters
+    from cadence_rag_b200.sharded import ShardedEngine, sharded_retrieve_ids
+    settings.embeddings_dim = 1024
+    settings.cadence_gpu_device = rank
+    embeddings.set_embedder(embeddings.SyntheticEmbedder(seed=20260210, dim=1024))
+    tables, t0 = _hybrid_corpus()
+    shard = ShardedEngine(_build_engine(tables, rank / world, (rank + 1) / world, rank))
+    assert all(s.transport == "peer" for s in shard.searchers.values())
+    bm25 = [{"chunk_id": 3 * i} for i in (5, 4100, 77, 5999)]
+    bm25a = [{"artifact_chunk_id": 3 * i} for i in (3, 450)]
+    requests = [("why did TOK-1 fail with TOK-3 on 10.0.0.1", None, bm25, bm25a),
+                ("TOK-0 status", RetrieveFilters(call_ids=[UUID(int=c + 1) for c in range(25, 35)]), [], []),     # spans both shards
+                ("TOK-2 and TOK-5", RetrieveFilters(call_tags=["t2"]), bm25, []),
+                ("no tokens here", RetrieveFilters(date_from=t0 + timedelta(hours=30)), [], bm25a),
+                ("TOK-4 TOK-9", RetrieveFilters(external_id="ext-7"), bm25, bm25a),                                  # lives on one shard
+                ("TOK-4", RetrieveFilters(external_id="missing"), bm25, []),
+                ("   ", None, [], [])]
+    got = [sharded_retrieve_ids(shard, q, f, bm25_chunks=b, bm25_artifacts=a, debug=True) for q, f, b, a in requests]
+    # dense lane disabled on every rank -> lexical-only fusion
+    embeddings.set_embedder(None)
+    settings.embeddings_base_url = ""
+    got.append(sharded_retrieve_ids(shard, "TOK-1 TOK-3", None, bm25_chunks=bm25, debug=True))
+    with open(os.path.join(out_dir, f"sharded{rank}.json"), "w") as f:
+        json.dump(got, f, default=str)
+    if rank == 0:
+        embeddings.set_embedder(embeddings.SyntheticEmbedder(seed=20260210, dim=1024))
+        whole = _build_engine(tables, 0.0, 1.0, 0)
+        want = [retrieve.retrieve_ids(whole, q, f, bm25_chunks=b, bm25_artifacts=a, debug=True) for q, f, b, a in requests]
+        embeddings.set_embedder(None)
+        want.append(retrieve.retrieve_ids(whole, "TOK-1 TOK-3", None, bm25_chunks=bm25, debug=True))
+        with open(os.path.join(out_dir, "whole.json"), "w") as f:
+            json.dump(want, f, default=str)
+        for st in whole.stores.values():
+            st.close()
+    dist.barrier()
+    shard.close()
+    for st in shard.local.stores.values():
+        st.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_sharded_hybrid_retrieve_equals_whole(tmp_path):
+    """cadence_rag_b200.sharded.sharded_retrieve_ids over 2 row shards == retrieve_ids over the whole corpus: lanes,
+    COUNT(*), planner modes, fused ranks (bit-exact RRF) and the ids_only order, identical on both ranks."""
+    import json
+    import torch.multiprocessing as mp
+    mp.spawn(_hybrid_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    want = json.load(open(tmp_path / "whole.json"))
+    for rank in (0, 1):
+        got = json.load(open(tmp_path / f"sharded{rank}.json"))
+        assert len(got) == len(want) == 8
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert g == w, (rank, i)
+    assert len(want[0]["retrieved_ids"]) > 50 and want[-1]["debug"]["dense"]["enabled"] is False
