@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--hnsw-rows", type=int, default=10_000, help="batch_bf16: rows of the CPU HNSW baseline's sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--bf16-only", action="store_true", help="batch_bf16: keep only bf16 rows resident (C5 residency)")
-    ap.add_argument("--workload", default="exact_f32", choices=["exact_f32", "batch_bf16", "hybrid"],
+    ap.add_argument("--workload", default="exact_f32", choices=["exact_f32", "batch_bf16", "hybrid", "ingest"],
                     help="exact_f32 = BASELINE configs[1] (default, the contract line); "
                          "batch_bf16 = configs[2]: 10M x 1024 bf16, 1024 queries on the tcgen05 lane")
     return ap.parse_args()
@@ -608,6 +608,108 @@ def run_hybrid(args):
     return 0
 
 
+def run_ingest(args):
+    """Write side of the store: host rows -> resident rows (fp32 + inverse norm +
+    normalised bf16), the backfill UPDATE in place, growth of a sealed store, snapshot save / load, building the
+    device tech-token index, and the hierarchical (artifact -> shortlist -> scoped chunks) dense request."""
+    import shutil
+    import tempfile
+    import numpy as np
+    import torch
+    from cadence_rag_b200 import retrieve
+    from cadence_rag_b200.config import settings
+    from cadence_rag_b200.lexical import DeviceTechIndex, TechTokenIndex
+    from cadence_rag_b200.retrieve import DenseEngine
+    from cadence_rag_b200.store import DenseStore, SYNTH_CORPUS_SEED, SYNTH_QUERY_SEED, synth_rows_device
+    torch.cuda.set_device(0)
+    settings.embeddings_dim = DIM
+    rows = min(args.rows, 400_000)
+    n_art = rows // 10
+    out = {}
+    x = synth_rows_device(SYNTH_CORPUS_SEED, 0, rows, DIM, device=0).cpu().numpy()        # host rows, as an ingest sees them
+    ids = np.arange(1, rows + 1, dtype=np.int64)
+    slots = [int(r) // 200 for r in range(rows)]
+
+    def timed(fn, reps=1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps, r
+
+    chunk = 65_536
+    store = DenseStore("chunks", rows + chunk, dim=DIM, device=0)
+    valid = np.ones(rows, dtype=bool); valid[::10] = False                                # every 10th row ingested with embedding NULL
+
+    def load():
+        for r0 in range(0, rows, chunk):
+            r1 = min(rows, r0 + chunk)
+            store.append(x[r0:r1], ids=ids[r0:r1], call_ids=slots[r0:r1], valid=valid[r0:r1])
+    dt, _ = timed(load)
+    out["append_host_rows"] = {"rows": rows, "rows_per_s": rows / dt, "gb_per_s": rows * DIM * 4 / dt / 1e9,
+                               "note": "pageable numpy rows -> fp32 + inverse norm + bf16 resident, 65 536 rows per call"}
+    dt, _ = timed(store.finalize)
+    out["finalize_ms"] = dt * 1e3
+    pend = store.pending_ids()
+    m = int(pend.size)
+    dt, _ = timed(lambda: [store.update_embeddings(pend[i:i + 4096], x[pend[i:i + 4096] - 1]) for i in range(0, m, 4096)])
+    out["backfill_update_in_place"] = {"rows": m, "rows_per_s": m / dt, "note": "cdr_store_update_embeddings, 4 096 rows per call"}
+    grow = synth_rows_device(SYNTH_CORPUS_SEED, rows, chunk, DIM, device=0).cpu().numpy()
+    dt, _ = timed(lambda: store.append(grow, ids=np.arange(rows + 1, rows + chunk + 1, dtype=np.int64), call_ids=[rows // 200] * chunk))
+    out["grow_sealed_store"] = {"rows": chunk, "rows_per_s": chunk / dt}
+    tmp = tempfile.mkdtemp(prefix="cdr_snapshot_")
+    try:
+        dt, _ = timed(lambda: store.save(tmp))
+        out["snapshot_save"] = {"rows": store.rows, "seconds": dt, "gb_per_s": store.rows * DIM * 4 / dt / 1e9}
+        dt, restored = timed(lambda: DenseStore.load(tmp, device=0))
+        out["snapshot_load"] = {"rows": restored.rows, "seconds": dt, "gb_per_s": restored.rows * DIM * 4 / dt / 1e9}
+        q = synth_rows_device(SYNTH_QUERY_SEED, 0, 1, DIM, device=0)
+        a, b = store.search_exact(q, TOPK), restored.search_exact(q, TOPK)
+        torch.cuda.synchronize()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1].view(torch.int64), b[1].view(torch.int64)), "restored store answers differently"
+        restored.close()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    # device tech-token index (f-1): 0-3 tokens per row from a 10 000-token Zipf vocabulary
+    rng = np.random.default_rng(1)
+    n_rows = store.rows
+    ntok = rng.integers(0, 4, size=n_rows)
+    tok = np.minimum(rng.zipf(1.1, size=(n_rows, 3)) - 1, 9_999)
+    mask = (np.arange(3)[None, :] < ntok[:, None]).reshape(-1)
+    flat_rows, flat_tok = np.repeat(np.arange(n_rows), 3)[mask], tok.reshape(-1)[mask]
+    order = np.lexsort((flat_rows, flat_tok))
+    flat_rows, flat_tok = flat_rows[order], flat_tok[order]
+    starts = np.searchsorted(flat_tok, np.arange(10_001))
+    index = TechTokenIndex()
+    for t in range(10_000):
+        if starts[t + 1] > starts[t]:
+            index.add_postings(f"TK-{t}", np.unique(flat_rows[starts[t]:starts[t + 1]]))
+    dt, dev_index = timed(lambda: DeviceTechIndex(index, store))
+    out["device_tech_index_build"] = {"rows": n_rows, "postings": int(flat_rows.size), "seconds": dt}
+    # hierarchical dense request (f-4): artifacts -> call shortlist -> chunks scoped to the shortlist
+    arts = DenseStore("artifact_chunks", n_art, dim=DIM, device=0)
+    xa = synth_rows_device(SYNTH_CORPUS_SEED + 5, 0, n_art, DIM, device=0).cpu().numpy()
+    arts.append(xa, ids=np.arange(1, n_art + 1, dtype=np.int64), call_ids=[int(r) // 20 for r in range(n_art)])
+    arts.finalize()
+    eng = DenseEngine()
+    eng.register(store); eng.register(arts)
+    qs = synth_rows_device(SYNTH_QUERY_SEED, 100, 64, DIM, device=0).cpu().numpy()
+    with eng.connect() as conn:
+        retrieve.fetch_chunks_dense_hierarchical(conn, qs[0], None, None)
+        dt, res = timed(lambda: [retrieve.fetch_chunks_dense_hierarchical(conn, qs[i], None, None) for i in range(64)])
+    out["hierarchical_dense_request"] = {"ms_per_request": dt / 64 * 1e3, "chunks": store.rows, "artifact_chunks": n_art,
+                                         "shortlist_calls": len(res[-1]["call_shortlist"]),
+                                         "scoped_candidate_rows": res[-1]["candidate_rows"]["chunks"], "modes": res[-1]["modes"]}
+    line = {"metric": "store write side and f-rows (rows/s, seconds)", "value": out["append_host_rows"]["rows_per_s"], "unit": "rows/s",
+            "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ingest of {rows} x {DIM} fp32 host rows + backfill / growth / snapshot / tech index / hierarchical request"},
+            "ingest": out}
+    print(json.dumps(line), flush=True)
+    dev_index.close(); store.close(); arts.close()
+    return 0
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -616,6 +718,8 @@ def main():
         return run_batch_bf16(args)
     if args.workload == "hybrid":
         return run_hybrid(args)
+    if args.workload == "ingest":
+        return run_ingest(args)
 
     import numpy as np
     import torch

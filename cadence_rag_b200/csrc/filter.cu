@@ -109,25 +109,22 @@ extern "C" int32_t cdr_filter_build(cdr_store *s, const uint32_t *call_slot_bitm
                 "cdr_filter_build: n_call_slots < 0");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    uint32_t *bm_dev = nullptr;
-    if (call_slot_bitmap_host) {
-        const size_t words = (size_t)((n_call_slots + 31) / 32) + 1;
-        CDR_CUDA(cudaMallocAsync(&bm_dev, words * 4, st));
-        CDR_CUDA(cudaMemsetAsync(bm_dev, 0, words * 4, st));
-        if (n_call_slots > 0)
-            CDR_CUDA(cudaMemcpyAsync(bm_dev, call_slot_bitmap_host, (size_t)((n_call_slots + 31) / 32) * 4,
-                                     cudaMemcpyHostToDevice, st));
-    }
-    unsigned long long *cnt = nullptr;
-    CDR_CUDA(cudaMallocAsync(&cnt, sizeof(unsigned long long), st));
-    CDR_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+    // this thread's device staging (a stream-ordered pool allocation per call costs milliseconds once the pool
+    // has trimmed at the previous synchronisation): [counter | call-slot bitmap]
+    const size_t bm_words = call_slot_bitmap_host ? (size_t)((n_call_slots + 31) / 32) + 1 : 0;
+    unsigned char *stage = (unsigned char *)cdr_thread_device(s->device, 16 + bm_words * 4);
+    if (!stage) return CDR_ERR_OOM;
+    unsigned long long *cnt = reinterpret_cast<unsigned long long *>(stage);
+    uint32_t *bm_dev = call_slot_bitmap_host ? reinterpret_cast<uint32_t *>(stage + 16) : nullptr;
+    CDR_CUDA(cudaMemsetAsync(stage, 0, 16 + bm_words * 4, st));
+    if (bm_dev && n_call_slots > 0)
+        CDR_CUDA(cudaMemcpyAsync(bm_dev, call_slot_bitmap_host, (size_t)((n_call_slots + 31) / 32) * 4,
+                                 cudaMemcpyHostToDevice, st));
     int rc = cdr_filter_launch(s, bm_dev, n_call_slots, has_date_from, date_from_us, has_date_to, date_to_us,
                                has_tag_filter, tag_any, out_allow_dev, cnt, st);
     if (rc != CDR_OK) return rc;
     unsigned long long h = 0;
     CDR_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CDR_CUDA(cudaFreeAsync(cnt, st));
-    if (bm_dev) CDR_CUDA(cudaFreeAsync(bm_dev, st));
     CDR_CUDA(cudaStreamSynchronize(st));
     if (out_count_host) *out_count_host = (int64_t)h;
     return CDR_OK;

@@ -159,9 +159,11 @@ extern "C" int32_t cdr_rrf_merge_host(const int64_t *lane_ids_host, const int32_
     const size_t b_oid = (size_t)nq * max_out * 8, b_osc = (size_t)nq * max_out * 8;
     const size_t b_om = (size_t)nq * max_out * 4, b_on = (size_t)nq * 4;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    unsigned char *buf = nullptr;
     const size_t tot = up(b_ids) + up(b_off) + up(b_oid) + up(b_osc) + up(b_om) + up(b_on);
-    CDR_CUDA(cudaMallocAsync(&buf, tot, st));
+    int cur_dev = 0;
+    CDR_CUDA(cudaGetDevice(&cur_dev));
+    unsigned char *buf = (unsigned char *)cdr_thread_device(cur_dev, tot);      // this thread's device staging
+    if (!buf) return CDR_ERR_OOM;
     unsigned char *c = buf;
     int64_t *d_ids = (int64_t *)c; c += up(b_ids);
     int32_t *d_off = (int32_t *)c; c += up(b_off);
@@ -172,12 +174,11 @@ extern "C" int32_t cdr_rrf_merge_host(const int64_t *lane_ids_host, const int32_
     if (total > 0) CDR_CUDA(cudaMemcpyAsync(d_ids, lane_ids_host, (size_t)total * 8, cudaMemcpyHostToDevice, st));
     CDR_CUDA(cudaMemcpyAsync(d_off, lane_offsets_host, b_off, cudaMemcpyHostToDevice, st));
     int rc = cdr_rrf_merge(d_ids, d_off, nq, L, rrf_k, max_out, d_oid, d_osc, d_om, d_on, stream);
-    if (rc != CDR_OK) { cudaFreeAsync(buf, st); return rc; }
+    if (rc != CDR_OK) return rc;
     CDR_CUDA(cudaMemcpyAsync(out_ids_host, d_oid, b_oid, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaMemcpyAsync(out_scores_host, d_osc, b_osc, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaMemcpyAsync(out_lane_mask_host, d_om, b_om, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaMemcpyAsync(out_n_host, d_on, b_on, cudaMemcpyDeviceToHost, st));
-    CDR_CUDA(cudaFreeAsync(buf, st));
     CDR_CUDA(cudaStreamSynchronize(st));
     return CDR_OK;
 }

@@ -237,8 +237,8 @@ extern "C" int32_t cdr_tech_lane_host(cdr_tech_index *ix, const int32_t *token_i
     const size_t b_tok = up((size_t)nq * max_tokens * 4), b_nt = up((size_t)nq * 4);
     const size_t b_bm = call_slot_bitmap_host ? up((size_t)((n_call_slots + 31) / 32 + 1) * 4) : 0;
     const size_t b_oid = up((size_t)nq * limit * 8), b_on = up((size_t)nq * 4);
-    unsigned char *buf = nullptr;
-    CDR_CUDA(cudaMallocAsync(&buf, b_tok + b_nt + b_bm + b_oid + b_on, st));
+    unsigned char *buf = (unsigned char *)cdr_thread_device(s->device, b_tok + b_nt + b_bm + b_oid + b_on);   // this thread's staging
+    if (!buf) return CDR_ERR_OOM;
     unsigned char *c = buf;
     int32_t *d_tok = (int32_t *)c; c += b_tok;
     int32_t *d_nt = (int32_t *)c; c += b_nt;
@@ -255,10 +255,9 @@ extern "C" int32_t cdr_tech_lane_host(cdr_tech_index *ix, const int32_t *token_i
     }
     int rc = cdr_tech_lane_launch(ix, d_tok, d_nt, nq, max_tokens, d_bm, n_call_slots, has_date_from, date_from_us,
                                   has_date_to, date_to_us, has_tag_filter, tag_any, limit, d_oid, d_on, st);
-    if (rc != CDR_OK) { cudaFreeAsync(buf, st); return rc; }
+    if (rc != CDR_OK) return rc;
     CDR_CUDA(cudaMemcpyAsync(out_ids_host, d_oid, (size_t)nq * limit * 8, cudaMemcpyDeviceToHost, st));
     CDR_CUDA(cudaMemcpyAsync(out_n_host, d_on, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    CDR_CUDA(cudaFreeAsync(buf, st));
     CDR_CUDA(cudaStreamSynchronize(st));
     return CDR_OK;
 }
