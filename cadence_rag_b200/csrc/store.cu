@@ -456,21 +456,16 @@ extern "C" int32_t cdr_store_update_embeddings(cdr_store *s, const int64_t *ids_
     std::lock_guard<std::mutex> lk(s->mu);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t d = (size_t)s->dim;
-    int64_t *d_ids = nullptr, *d_rows = nullptr;
-    float *d_src = nullptr;
-    unsigned long long *d_cnt = nullptr;    // [0] missing ids, [1] rows that turned NOT NULL
-    CDR_CUDA(cudaMalloc(&d_ids, (size_t)n * 8));
-    CDR_CUDA(cudaMalloc(&d_rows, (size_t)n * 8));
-    CDR_CUDA(cudaMalloc(&d_cnt, 16));
-    auto release = [&]() { cudaFree(d_ids); cudaFree(d_rows); cudaFree(d_cnt); cudaFree(d_src); };
-    cudaError_t e = cudaMalloc(&d_src, (size_t)n * d * 4);
-    if (e != cudaSuccess) {
-        release();
-        cdr_set_error("cdr_store_update_embeddings: staging %lld rows: %s", (long long)n, cudaGetErrorString(e));
-        return CDR_ERR_OOM;
-    }
+    // this thread's device staging: [missing / newly-valid counters | ids | rows | source vectors]
+    const size_t off_ids = 16, off_rows = off_ids + (size_t)n * 8, off_src = (off_rows + (size_t)n * 8 + 255) & ~(size_t)255;
+    unsigned char *stage = (unsigned char *)cdr_thread_device(s->device, off_src + (size_t)n * d * 4);
+    if (!stage) return CDR_ERR_OOM;
+    unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(stage);    // [0] missing ids, [1] rows that turned NOT NULL
+    int64_t *d_ids = reinterpret_cast<int64_t *>(stage + off_ids);
+    int64_t *d_rows = reinterpret_cast<int64_t *>(stage + off_rows);
+    float *d_src = reinterpret_cast<float *>(stage + off_src);
     unsigned long long h[2] = {0, 0};
-    e = cudaMemsetAsync(d_cnt, 0, 16, st);
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, 16, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         lookup_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->ids, s->n_rows, d_ids, n, d_rows, d_cnt);
@@ -480,7 +475,6 @@ extern "C" int32_t cdr_store_update_embeddings(cdr_store *s, const int64_t *ids_
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess && h[0] != 0) {
-        release();
         cdr_set_error("cdr_store_update_embeddings: %llu of %lld ids are not in the store; nothing was updated", h[0],
                       (long long)n);
         return CDR_ERR_INVALID;
@@ -496,7 +490,6 @@ extern "C" int32_t cdr_store_update_embeddings(cdr_store *s, const int64_t *ids_
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    release();
     if (e != cudaSuccess) {
         cdr_set_error("cdr_store_update_embeddings: %s", cudaGetErrorString(e));
         return CDR_ERR_CUDA;
