@@ -104,12 +104,14 @@ def _sharded_table(eng: ShardedEngine, conn, table: str, q32: Optional[np.ndarra
         if q32.shape[0] != want or q32.shape[0] != store.dim:
             raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[0]}")
         allow, local_count = R._filter_bitmap(conn, table, filters, call_ids)
-        total = torch.tensor([local_count], dtype=torch.int64, device=f"cuda:{store.device}")
+        on_gpu = eng.world == 1 or dist.get_backend(eng.group) == "nccl"      # gloo: the CPU test tier
+        dev = f"cuda:{store.device}" if on_gpu else "cpu"
+        total = torch.tensor([local_count], dtype=torch.int64, device=dev)
         if eng.world > 1:
             dist.all_reduce(total, group=eng.group)
         count = int(total.item())
         if count > 0:
-            qd = torch.from_numpy(q32[None, :]).to(f"cuda:{store.device}")
+            qd = torch.from_numpy(q32[None, :]).to(dev)
             ids, scores, n = searcher.search(qd, dense_limit, allow, mode="exact")
             m = int(n[0].item())
             g_ids = ids[0, :m].cpu().numpy()

@@ -84,3 +84,106 @@ def test_world2_gloo_gather_and_merge(tmp_path):
     want = np.array([orc.exact_scan(qs[i], x, k)[0] for i in range(3)])
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"rank{r}.npy"), want)
+
+
+# ----------------------------------------------------------------------------------------- sharded hybrid facade (host logic)
+def _sharded_worker(rank, world, port, out_dir):
+    """cadence_rag_b200.sharded over 2 gloo ranks with the GPU pieces replaced by the oracle: what is exercised is the
+    cross-rank plumbing -- embedding broadcast from rank 0, all-reduced COUNT(*), tech-lane merge by
+    (call_started_at DESC, id ASC), row dicts from the owning rank, identical responses on every rank."""
+    sys.path.insert(0, ROOT)
+    import contextlib
+    import json
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cadence_rag_b200 import embeddings, retrieve as R, sharded
+    from cadence_rag_b200.config import settings
+    from oracle import cpu_oracle as orc
+    from oracle import ports
+    settings.embeddings_dim = 64
+    n, k_dim = 400, 64
+    x = orc.synth_rows(20260209, 0, n, k_dim)
+    ids_all = np.arange(1, n + 1, dtype=np.int64) * 2
+    rng = np.random.default_rng(4)
+    started_all = rng.permutation(n).astype(np.int64) // 7            # ties in call_started_at, interleaved across shards
+    tokens_all = [["TOK-1"] if r % 3 == 0 else (["TOK-2"] if r % 5 == 0 else []) for r in range(n)]
+    lo, hi = (0, 230) if rank == 0 else (230, n)                      # uneven shards
+
+    class _Store:
+        table_name, key_field, dim, device = "chunks", "chunk_id", k_dim, 0
+        call_ids_by_slot = [f"call-{c}" for c in range(40)]
+        payload = {int(i): {"text": f"row {i}"} for i in ids_all[lo:hi]}
+
+        def host_columns(self):
+            return {"ids": ids_all[lo:hi], "call_slot": (np.arange(lo, hi) % 40).astype(np.int32), "started_at": started_all[lo:hi]}
+
+    class _Local:
+        stores = {"chunks": _Store()}
+        external_ids = {}
+
+        @contextlib.contextmanager
+        def connect(self):
+            conn = type("C", (), {})()
+            conn.engine = self
+            conn.store = lambda t: self.stores[t]
+            yield conn
+
+    class _Searcher:                                                 # the dense lane + exchange, restated with the oracle
+        transport = "fake"
+
+        def search(self, qd, limit, allow, mode="exact"):
+            g_ids, g_sc = orc.exact_scan(qd[0].numpy(), x, limit, ids=ids_all)
+            ids = torch.full((1, limit), -1, dtype=torch.int64); sc = torch.full((1, limit), float("nan"), dtype=torch.float64)
+            ids[0, :len(g_ids)] = torch.from_numpy(g_ids); sc[0, :len(g_sc)] = torch.from_numpy(g_sc)
+            return ids, sc, torch.tensor([len(g_ids)], dtype=torch.int32)
+
+        def close(self):
+            pass
+
+    def fake_fetch_tech(conn, table, tokens, filters, call_ids, limit):
+        rows = [r for r in range(lo, hi) if set(tokens) & set(tokens_all[r])]
+        rows.sort(key=lambda r: (-int(started_all[r]), int(ids_all[r])))
+        return [{"chunk_id": int(ids_all[r]), "call_id": f"call-{r % 40}", "text": f"row {ids_all[r]}"} for r in rows[:limit]]
+
+    R._fetch_tech = fake_fetch_tech
+    R._filter_bitmap = lambda conn, table, filters, call_ids: (None, hi - lo)
+    R._rrf_merge = lambda lanes, key, k=60: ports.rrf_merge(lanes, key, k)
+    eng = sharded.ShardedEngine.__new__(sharded.ShardedEngine)
+    eng.local, eng.group, eng.world, eng.rank, eng.searchers = _Local(), None, world, rank, {"chunks": _Searcher()}
+    calls = []
+
+    def embedder(texts):
+        calls.append(texts)
+        return embeddings.EmbeddingResult(vectors=[orc.synth_rows(20260210, 5, 1, k_dim)[0].astype(float).tolist()], model="m")
+    embeddings.set_embedder(embedder)
+    out = sharded.sharded_retrieve_ids(eng, "what about TOK-1 and TOK-2", None, bm25_chunks=[{"chunk_id": 8}, {"chunk_id": 700}], debug=True)
+    assert (len(calls) == 1) == (rank == 0)                          # rank 0 alone talks to the embedding service
+    with open(os.path.join(out_dir, f"resp{rank}.json"), "w") as f:
+        json.dump(out, f, default=str)
+    if rank == 0:                                                    # expectation from the unsharded restatement
+        q = orc.synth_rows(20260210, 5, 1, k_dim)[0]
+        d_ids, d_sc = orc.exact_scan(q, x, 50, ids=ids_all)
+        rows = [r for r in range(n) if {"TOK-1", "TOK-2"} & set(tokens_all[r])]
+        rows.sort(key=lambda r: (-int(started_all[r]), int(ids_all[r])))
+        t_ids = [int(ids_all[r]) for r in rows[:50]]
+        fused = ports.rrf_merge({"bm25": [{"chunk_id": 8}, {"chunk_id": 700}], "tech_tokens": [{"chunk_id": i} for i in t_ids],
+                                 "dense": [{"chunk_id": int(i)} for i in d_ids]}, "chunk_id")
+        with open(os.path.join(out_dir, "want.json"), "w") as f:
+            json.dump({"tech": t_ids, "dense": [int(i) for i in d_ids], "fused": [[r["chunk_id"], sorted(h), s_] for r, h, s_ in fused],
+                       "count": n}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_sharded_hybrid_plumbing(tmp_path):
+    import json
+    mp.spawn(_sharded_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    want = json.load(open(tmp_path / "want.json"))
+    r0, r1 = json.load(open(tmp_path / "resp0.json")), json.load(open(tmp_path / "resp1.json"))
+    assert r0 == r1
+    dbg = r0["debug"]
+    assert [e["chunk_id"] for e in dbg["lanes"]["chunks"]["tech_tokens"]] == want["tech"]
+    assert [e["chunk_id"] for e in dbg["lanes"]["chunks"]["dense"]] == want["dense"]
+    assert dbg["fused"]["chunks"] == want["fused"]
+    assert dbg["dense"]["candidate_rows"]["chunks"] == want["count"] and dbg["dense"]["modes"]["chunks"] == "ann"
+    assert r0["retrieved_ids"][0].startswith("chunk:")
