@@ -564,6 +564,32 @@ def run_hybrid(args):
             sys.setswitchinterval(old_interval)
             assert not errs, errs
             out[name][label] = n_threads * per_thread / dt
+    # the same clients through the micro-batcher (one worker, one fused call per batch; requests with equal filters
+    # form a group).  "distinct filters": every client scopes to its own 10-call window.
+    for name, f_of in (("filtered_10_calls_2000_rows", lambda t: filt), ("unfiltered", lambda t: None),
+                       ("distinct_filters_per_client", lambda t: RetrieveFilters(call_ids=list(range(10 * t, 10 * t + 10))))):
+        for n_threads in (8, 32):
+            per_thread = max(8, args.steps)
+            batcher = retrieve.RequestBatcher(eng, max_batch=64, max_wait_s=2e-4)
+            errs = []
+
+            def bclient(t, f_of=f_of):
+                try:
+                    for i in range(per_thread):
+                        batcher.retrieve_ids(f"status of TK-{(t * 97 + i) % 500} and TK-{(i * 13 + t) % 900}", f_of(t))
+                except Exception as exc:   # noqa: BLE001
+                    errs.append(repr(exc))
+            threads = [threading.Thread(target=bclient, args=(t,)) for t in range(n_threads)]
+            t0 = time.perf_counter()
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            dt = time.perf_counter() - t0
+            batcher.close()
+            assert not errs, errs
+            out.setdefault(name, {})[f"batcher_{n_threads}_clients_queries_per_s"] = n_threads * per_thread / dt
+            out[name][f"batcher_{n_threads}_clients_mean_batch"] = batcher.requests_served / max(batcher.batches_served, 1)
     if os.environ.get("CADENCE_BENCH_HOST_PROFILE"):
         import cProfile, pstats
         pr = cProfile.Profile(); pr.enable()

@@ -98,6 +98,8 @@ SIGNATURES = {
                                   _vp, _vp, _vp]),
     "cdr_hybrid_retrieve_host": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cdr_hybrid_retrieve_groups_host": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp,
+                                               _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cdr_kernel_launch_count": (_i64, []),
     "cdr_prof_enable": (_i32, [_i32]),
     "cdr_prof_read": (_i32, [_i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),

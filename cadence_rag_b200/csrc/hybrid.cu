@@ -77,18 +77,37 @@ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 }  // namespace
 
-extern "C" int32_t cdr_hybrid_retrieve_host(
-    cdr_store *s, cdr_tech_index *tech_index, const cdr_filter_spec *filter, const float *q_host, int32_t nq,
-    int32_t dense_k, const int32_t *token_ids_host, const int32_t *n_tokens_host, int32_t max_tokens,
-    int32_t tech_limit, const int64_t *bm25_ids_host, const int32_t *bm25_offsets_host, int32_t rrf_k,
-    int32_t max_out, int64_t *out_count_host, int64_t *out_dense_ids_host, double *out_dense_scores_host,
-    int32_t *out_dense_n_host, int64_t *out_tech_ids_host, int32_t *out_tech_n_host, int64_t *out_fused_ids_host,
-    double *out_fused_scores_host, uint32_t *out_fused_mask_host, int32_t *out_fused_n_host, void *stream)
+namespace {
+
+struct GroupPlan {
+    bool has_filter = false, has_bm = false;
+    size_t bm_words = 0;       // call-slot bitmap words
+    size_t in_bm = 0;          // offset of the call-slot bitmap in the request block
+    size_t x_allow = 0;        // offset of the allow bitmap in the scratch block
+};
+
+}  // namespace
+
+// One request block for n_groups groups of consecutive queries, one filter per group.
+extern "C" int32_t cdr_hybrid_retrieve_groups_host(
+    cdr_store *s, cdr_tech_index *tech_index, const cdr_filter_spec *filters, const int32_t *group_offsets_host,
+    int32_t n_groups, const float *q_host, int32_t nq, int32_t dense_k, const int32_t *token_ids_host,
+    const int32_t *n_tokens_host, int32_t max_tokens, int32_t tech_limit, const int64_t *bm25_ids_host,
+    const int32_t *bm25_offsets_host, int32_t rrf_k, int32_t max_out, int64_t *out_count_host,
+    int64_t *out_dense_ids_host, double *out_dense_scores_host, int32_t *out_dense_n_host, int64_t *out_tech_ids_host,
+    int32_t *out_tech_n_host, int64_t *out_fused_ids_host, double *out_fused_scores_host, uint32_t *out_fused_mask_host,
+    int32_t *out_fused_n_host, void *stream)
 {
-    const char *fn = "cdr_hybrid_retrieve_host";
+    const char *fn = "cdr_hybrid_retrieve_groups_host";
     CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "%s: store is NULL", fn);
     CDR_REQUIRE(s->finalized, CDR_ERR_STATE, "%s: store not finalized", fn);
     CDR_REQUIRE(nq >= 0 && nq <= 4096, CDR_ERR_INVALID, "%s: nq=%d outside [0,4096]", fn, nq);
+    CDR_REQUIRE(n_groups >= 1 && n_groups <= 4096 && group_offsets_host != nullptr, CDR_ERR_INVALID,
+                "%s: need 1 <= n_groups <= 4096 and group offsets", fn);
+    CDR_REQUIRE(group_offsets_host[0] == 0 && group_offsets_host[n_groups] == nq, CDR_ERR_INVALID,
+                "%s: group offsets must run from 0 to nq", fn);
+    for (int gi = 0; gi < n_groups; ++gi)
+        CDR_REQUIRE(group_offsets_host[gi + 1] >= group_offsets_host[gi], CDR_ERR_INVALID, "%s: group offsets not monotone", fn);
     const bool dense = q_host != nullptr;
     if (dense) {
         CDR_REQUIRE(s->emb_f32 != nullptr, CDR_ERR_STATE, "%s: the dense lane of the fused call needs fp32 rows", fn);
@@ -124,27 +143,37 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
     CDR_REQUIRE(bm25_max + tech_limit + dense_k <= CDR_RRF_MAX_ITEMS, CDR_ERR_INVALID,
                 "%s: %lld lane items per query exceed %d", fn, (long long)(bm25_max + tech_limit + dense_k),
                 CDR_RRF_MAX_ITEMS);
-    const bool has_filter = filter != nullptr && (filter->call_slot_bitmap_host || filter->has_date_from ||
-                                                  filter->has_date_to || filter->has_tag_filter);
-    const bool has_bm = has_filter && filter->call_slot_bitmap_host != nullptr;
-    CDR_REQUIRE(!has_bm || filter->n_call_slots >= 0, CDR_ERR_INVALID, "%s: n_call_slots < 0", fn);
 
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int dim = s->dim;
     const int L = dense ? 3 : 2;
-    const size_t bm_words = has_bm ? (size_t)((filter->n_call_slots + 31) / 32) : 0;
+    const size_t words = (size_t)((s->n_rows + 31) / 32);
 
-    // ---- packed request (host -> device) and packed response (device -> host)
-    size_t in_q = 0, in_tok, in_nt, in_boff, in_bids, in_bm, in_end;
+    // ---- packed request (host -> device), packed response (device -> host), device-only scratch
+    std::vector<GroupPlan> plan((size_t)n_groups);
+    size_t in_q = 0, in_tok, in_nt, in_boff, in_bids, in_bm0, in_end;
     in_tok = up16(in_q + (dense ? (size_t)nq * dim * 4 : 0));
     in_nt = up16(in_tok + (tech ? (size_t)nq * max_tokens * 4 : 0));
     in_boff = up16(in_nt + (tech ? (size_t)nq * 4 : 0));
     in_bids = up16(in_boff + (bm25_offsets_host ? (size_t)(nq + 1) * 4 : 0));
-    in_bm = up16(in_bids + (size_t)bm25_total * 8);
-    in_end = up16(in_bm + (bm_words + 1) * 4);
+    in_bm0 = up16(in_bids + (size_t)bm25_total * 8);
+    size_t cur = in_bm0;
+    int n_filtered = 0;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const cdr_filter_spec *f = filters ? &filters[gi] : nullptr;
+        GroupPlan &gp = plan[(size_t)gi];
+        gp.has_filter = f != nullptr && (f->call_slot_bitmap_host || f->has_date_from || f->has_date_to || f->has_tag_filter);
+        gp.has_bm = gp.has_filter && f->call_slot_bitmap_host != nullptr;
+        CDR_REQUIRE(!gp.has_bm || f->n_call_slots >= 0, CDR_ERR_INVALID, "%s: n_call_slots < 0 in group %d", fn, gi);
+        gp.bm_words = gp.has_bm ? (size_t)((f->n_call_slots + 31) / 32) : 0;
+        gp.in_bm = cur;
+        cur = up16(cur + (gp.bm_words + 1) * 4);
+        n_filtered += gp.has_filter ? 1 : 0;
+    }
+    in_end = cur;
     size_t o_cnt = in_end, o_did, o_dsc, o_dn, o_tid, o_tn, o_fid, o_fsc, o_fm, o_fn, o_end;
-    o_did = up16(o_cnt + 8);
+    o_did = up16(o_cnt + (size_t)n_groups * 8);
     o_dsc = up16(o_did + (size_t)nq * dense_k * 8);
     o_dn = up16(o_dsc + (size_t)nq * dense_k * 8);
     o_tid = up16(o_dn + (size_t)nq * 4);
@@ -154,10 +183,12 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
     o_fm = up16(o_fsc + (size_t)nq * max_out * 8);
     o_fn = up16(o_fm + (size_t)nq * max_out * 4);
     o_end = up16(o_fn + (size_t)nq * 4);
-    // device-only scratch: allow bitmap, compacted lanes, offsets
-    const size_t words = (size_t)((s->n_rows + 31) / 32);
-    const size_t x_allow = o_end;
-    const size_t x_lids = up16(x_allow + (has_filter ? (words + 1) * 4 : 0));
+    cur = o_end;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        plan[(size_t)gi].x_allow = cur;
+        if (plan[(size_t)gi].has_filter) cur = up16(cur + (words + 1) * 4);
+    }
+    const size_t x_lids = cur;
     const size_t x_loff = up16(x_lids + ((size_t)bm25_total + (size_t)nq * (tech_limit + dense_k) + 1) * 8);
     const size_t x_end = up16(x_loff + ((size_t)nq * L + 1) * 4);
 
@@ -178,48 +209,55 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
         memcpy(h + in_boff, bm25_offsets_host, (size_t)(nq + 1) * 4);
         if (bm25_total) memcpy(h + in_bids, bm25_ids_host, (size_t)bm25_total * 8);
     }
-    memset(h + in_bm, 0, (bm_words + 1) * 4);
-    if (has_bm && bm_words) memcpy(h + in_bm, filter->call_slot_bitmap_host, bm_words * 4);
-    memset(h + o_cnt, 0, 8);                                      // zeroes the device counter through the same copy
-    CDR_CUDA(cudaMemcpyAsync(d, h, o_cnt + 8, cudaMemcpyHostToDevice, st));
+    memset(h + in_bm0, 0, o_did - in_bm0);                        // call-slot bitmaps and the COUNT(*) counters start at zero
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const GroupPlan &gp = plan[(size_t)gi];
+        if (gp.has_bm && gp.bm_words) memcpy(h + gp.in_bm, filters[gi].call_slot_bitmap_host, gp.bm_words * 4);
+    }
+    CDR_CUDA(cudaMemcpyAsync(d, h, o_did, cudaMemcpyHostToDevice, st));
 
-    const uint32_t *d_bm = has_bm ? (const uint32_t *)(d + in_bm) : nullptr;
-    const int64_t n_slots = has_bm ? filter->n_call_slots : 0;
-    const int f_from = has_filter ? filter->has_date_from : 0, f_to = has_filter ? filter->has_date_to : 0;
-    const int f_tags = has_filter ? filter->has_tag_filter : 0;
-    const int64_t t_from = has_filter ? filter->date_from_us : 0, t_to = has_filter ? filter->date_to_us : 0;
-    const uint64_t tag_any = has_filter ? filter->tag_any : 0;
-    int rc;
-
-    // tech_tokens lane first: short, and independent of the dense lane
     int64_t *d_tid = (int64_t *)(d + o_tid);
     int32_t *d_tn = (int32_t *)(d + o_tn);
-    if (tech) {
-        rc = cdr_tech_lane_launch(tech_index, (const int32_t *)(d + in_tok), (const int32_t *)(d + in_nt), nq,
-                                  max_tokens, d_bm, n_slots, f_from, t_from, f_to, t_to, f_tags, tag_any, tech_limit,
-                                  d_tid, d_tn, st);
-        if (rc != CDR_OK) return rc;
-    } else {
+    if (!tech) {
         CDR_CUDA(cudaMemsetAsync(d_tid, 0xFF, (size_t)nq * tech_limit * 8, st));
         CDR_CUDA(cudaMemsetAsync(d_tn, 0, (size_t)nq * 4, st));
     }
-
-    // dense lane: WHERE <filters> AND embedding IS NOT NULL, ORDER BY embedding <=> q LIMIT k
-    const uint32_t *allow = s->any_invalid ? s->valid : nullptr;
-    if (has_filter) {
-        uint32_t *d_allow = (uint32_t *)(d + x_allow);
-        rc = cdr_filter_launch(s, d_bm, n_slots, f_from, t_from, f_to, t_to, f_tags, tag_any, d_allow,
-                               (unsigned long long *)(d + o_cnt), st);
-        if (rc != CDR_OK) return rc;
-        allow = d_allow;
+    int rc;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const int q0 = group_offsets_host[gi], gq = group_offsets_host[gi + 1] - q0;
+        if (gq == 0) continue;
+        const GroupPlan &gp = plan[(size_t)gi];
+        const cdr_filter_spec *f = gp.has_filter ? &filters[gi] : nullptr;
+        const uint32_t *d_bm = gp.has_bm ? (const uint32_t *)(d + gp.in_bm) : nullptr;
+        const int64_t n_slots = gp.has_bm ? f->n_call_slots : 0;
+        const int f_from = f ? f->has_date_from : 0, f_to = f ? f->has_date_to : 0, f_tags = f ? f->has_tag_filter : 0;
+        const int64_t t_from = f ? f->date_from_us : 0, t_to = f ? f->date_to_us : 0;
+        const uint64_t tag_any = f ? f->tag_any : 0;
+        // tech_tokens lane first: short, and independent of the dense lane
+        if (tech) {
+            rc = cdr_tech_lane_launch(tech_index, (const int32_t *)(d + in_tok) + (size_t)q0 * max_tokens,
+                                      (const int32_t *)(d + in_nt) + q0, gq, max_tokens, d_bm, n_slots, f_from, t_from, f_to,
+                                      t_to, f_tags, tag_any, tech_limit, d_tid + (size_t)q0 * tech_limit, d_tn + q0, st);
+            if (rc != CDR_OK) return rc;
+        }
+        // dense lane: WHERE <filters> AND embedding IS NOT NULL, ORDER BY embedding <=> q LIMIT k
+        const uint32_t *allow = s->any_invalid ? s->valid : nullptr;
+        if (gp.has_filter) {
+            uint32_t *d_allow = (uint32_t *)(d + gp.x_allow);
+            rc = cdr_filter_launch(s, d_bm, n_slots, f_from, t_from, f_to, t_to, f_tags, tag_any, d_allow,
+                                   (unsigned long long *)(d + o_cnt) + gi, st);
+            if (rc != CDR_OK) return rc;
+            allow = d_allow;
+        }
+        if (dense) {
+            rc = cdr_exact_scan_launch(s, ws, (const float *)(d + in_q) + (size_t)q0 * dim, gq, allow, dense_k,
+                                       (double *)(d + o_dsc) + (size_t)q0 * dense_k, (int64_t *)(d + o_did) + (size_t)q0 * dense_k,
+                                       (int32_t *)(d + o_dn) + q0, st, /*share_reads=*/true);
+            if (rc != CDR_OK) return rc;
+        }
     }
-    if (dense) {
-        rc = cdr_exact_scan_launch(s, ws, (const float *)(d + in_q), nq, allow, dense_k, (double *)(d + o_dsc),
-                                   (int64_t *)(d + o_did), (int32_t *)(d + o_dn), st, /*share_reads=*/true);
-        if (rc != CDR_OK) return rc;
-    }
 
-    // lanes -> RRF
+    // lanes -> RRF, all queries at once
     AssembleParams ap;
     ap.bm25_off = bm25_offsets_host ? (const int32_t *)(d + in_boff) : nullptr;
     ap.bm25_ids = (const int64_t *)(d + in_bids);
@@ -245,9 +283,11 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
     CDR_CUDA(cudaStreamSynchronize(st));
 
     if (out_count_host) {
-        unsigned long long c;
-        memcpy(&c, h + o_cnt, 8);
-        *out_count_host = has_filter ? (int64_t)c : n_valid_now;
+        for (int gi = 0; gi < n_groups; ++gi) {
+            unsigned long long c;
+            memcpy(&c, h + o_cnt + (size_t)gi * 8, 8);
+            out_count_host[gi] = plan[(size_t)gi].has_filter ? (int64_t)c : n_valid_now;
+        }
     }
     if (dense) {
         memcpy(out_dense_ids_host, h + o_did, (size_t)nq * dense_k * 8);
@@ -261,4 +301,21 @@ extern "C" int32_t cdr_hybrid_retrieve_host(
     memcpy(out_fused_mask_host, h + o_fm, (size_t)nq * max_out * 4);
     memcpy(out_fused_n_host, h + o_fn, (size_t)nq * 4);
     return CDR_OK;
+}
+
+// All queries share one filter: a single group.
+extern "C" int32_t cdr_hybrid_retrieve_host(
+    cdr_store *s, cdr_tech_index *tech_index, const cdr_filter_spec *filter, const float *q_host, int32_t nq,
+    int32_t dense_k, const int32_t *token_ids_host, const int32_t *n_tokens_host, int32_t max_tokens,
+    int32_t tech_limit, const int64_t *bm25_ids_host, const int32_t *bm25_offsets_host, int32_t rrf_k,
+    int32_t max_out, int64_t *out_count_host, int64_t *out_dense_ids_host, double *out_dense_scores_host,
+    int32_t *out_dense_n_host, int64_t *out_tech_ids_host, int32_t *out_tech_n_host, int64_t *out_fused_ids_host,
+    double *out_fused_scores_host, uint32_t *out_fused_mask_host, int32_t *out_fused_n_host, void *stream)
+{
+    const int32_t offsets[2] = {0, nq};
+    return cdr_hybrid_retrieve_groups_host(s, tech_index, filter, offsets, 1, q_host, nq, dense_k, token_ids_host,
+                                           n_tokens_host, max_tokens, tech_limit, bm25_ids_host, bm25_offsets_host, rrf_k,
+                                           max_out, out_count_host, out_dense_ids_host, out_dense_scores_host,
+                                           out_dense_n_host, out_tech_ids_host, out_tech_n_host, out_fused_ids_host,
+                                           out_fused_scores_host, out_fused_mask_host, out_fused_n_host, stream);
 }

@@ -441,14 +441,17 @@ def _fused_path_ok(engine: DenseEngine, table: str, dense: bool) -> bool:
 
 
 def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndarray],
-                        token_lists: Sequence[Sequence[str]], filters: Optional[RetrieveFilters],
-                        call_ids: Optional[Sequence[Any]], bm25_rows: Sequence[Sequence[Mapping[str, Any]]],
+                        token_lists: Sequence[Sequence[str]], filters, call_ids,
+                        bm25_rows: Sequence[Sequence[Mapping[str, Any]]],
                         dense_limit: int, tech_limit: int = DEFAULT_TECH_TOPK,
-                        rrf_k: int = DEFAULT_RRF_K) -> List[Dict[str, Any]]:
-    """All lanes of one table + their fusion for nq requests that share a filter, through ONE
-    `cdr_hybrid_retrieve_host` call.  q32: [nq, dim] float32 or None (dense lane disabled); token_lists and
-    bm25_rows: one entry per request.  Returns, per request, {"tech": rows, "dense": rows, "count": COUNT(*),
-    "ranked": [(row, lane-name set, score)]} with the rows / order the step-by-step functions produce."""
+                        rrf_k: int = DEFAULT_RRF_K, per_request_filters: bool = False) -> List[Dict[str, Any]]:
+    """All lanes of one table + their fusion for nq requests through ONE fused C call.  q32: [nq, dim] float32
+    or None (dense lane disabled); token_lists and bm25_rows: one entry per request.  The requests share
+    `filters` / `call_ids`, or -- with per_request_filters -- each request brings its own (sequences of length
+    nq): requests are then grouped by filter and every group runs its own filter / lane launches inside the
+    same call (`cdr_hybrid_retrieve_groups_host`).  Returns, per request, {"tech": rows, "dense": rows,
+    "count": COUNT(*), "ranked": [(row, lane-name set, score)]} with the rows / order the step-by-step
+    functions produce."""
     store = conn.store(table)
     key = store.key_field
     nq = len(token_lists)
@@ -456,7 +459,26 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
         want = max(1, int(settings.embeddings_dim))
         if q32.shape[1] != want or q32.shape[1] != store.dim:
             raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[1]}")
-    spec = _filter_spec(store, filters, call_ids)
+    order = list(range(nq))                      # request -> position in the C call
+    group_specs = group_off = None
+    if per_request_filters:
+        specs = [_filter_spec(store, filters[i], call_ids[i]) for i in range(nq)]
+        groups: Dict[Tuple, List[int]] = {}
+        for i, sp in enumerate(specs):
+            gk = (None if sp["call_slots"] is None else tuple(sp["call_slots"]), sp["date_from"], sp["date_to"], sp["tag_mask"])
+            groups.setdefault(gk, []).append(i)
+        order, group_specs, group_off = [], [], [0]
+        for members in groups.values():
+            order += members
+            group_specs.append(specs[members[0]])
+            group_off.append(len(order))
+        spec = None
+    else:
+        spec = _filter_spec(store, filters, call_ids)
+    token_lists = [token_lists[i] for i in order]
+    bm25_rows = [bm25_rows[i] for i in order]
+    if q32 is not None and per_request_filters:
+        q32 = np.ascontiguousarray(q32[order])
     dev_index = conn.engine.device_tech_indexes.get(table) if any(token_lists) else None
     tok = nt = None
     if dev_index is not None:
@@ -467,9 +489,16 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
     np.cumsum(counts, out=bm25_off[1:])
     res = store.hybrid_retrieve(q32, dense_limit, tech_index=dev_index, token_ids=tok, n_tokens=nt,
                                 tech_limit=tech_limit, bm25_ids=bm25_ids, bm25_offsets=bm25_off, rrf_k=rrf_k,
-                                filter_spec=spec)
+                                filter_spec=spec, filter_specs=group_specs, group_offsets=group_off)
+    if per_request_filters:                       # COUNT(*) of the group each position belongs to
+        pos_count = [0] * nq
+        for gi in range(len(group_specs)):
+            for pos in range(group_off[gi], group_off[gi + 1]):
+                pos_count[pos] = res["count"][gi]
+    else:
+        pos_count = [res["count"]] * nq
     n_lanes = 3 if q32 is not None else 2
-    out = []
+    out_pos = []
     for qi in range(nq):
         tech_rows = _rows_from_ids(store, res["tech_ids"][qi, :int(res["tech_n"][qi])])
         dense_rows: List[Dict[str, Any]] = []
@@ -485,8 +514,11 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
             mask = int(res["fused_mask"][qi, i])
             hit = {_LANE_NAMES[l] for l in range(n_lanes) if (mask >> l) & 1}
             ranked.append((items[int(res["fused_ids"][qi, i])], hit, float(res["fused_scores"][qi, i])))
-        out.append({"tech": tech_rows, "dense": dense_rows, "count": res["count"] if q32 is not None else 0,
-                    "ranked": ranked})
+        out_pos.append({"tech": tech_rows, "dense": dense_rows, "count": pos_count[qi] if q32 is not None else 0,
+                        "ranked": ranked})
+    out: List[Dict[str, Any]] = [None] * nq      # back to request order
+    for pos, i in enumerate(order):
+        out[i] = out_pos[pos]
     return out
 
 
@@ -499,16 +531,21 @@ def _hybrid_table(conn: DenseConnection, table: str, q32: Optional[np.ndarray], 
                                call_ids, [list(bm25_rows)], dense_limit, tech_limit, rrf_k)[0]
 
 
-def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters: Optional[RetrieveFilters] = None,
+def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters=None,
                        bm25_chunks: Optional[Sequence[Sequence[Mapping[str, Any]]]] = None,
                        bm25_artifacts: Optional[Sequence[Sequence[Mapping[str, Any]]]] = None,
                        debug: bool = False) -> List[Dict[str, Any]]:
-    """`retrieve_ids` for a batch of concurrent requests that share one filter (not in the reference, which
-    serves one query per request): one embedding call, then ONE fused C call per table for the whole batch
-    (shared corpus reads on the dense lane) instead of one per request.  Returns one response per query, each
-    equal to what `retrieve_ids` returns for it.  Falls back to per-request calls when a table cannot take the
-    fused path."""
+    """`retrieve_ids` for a batch of concurrent requests (not in the reference, which serves one query per
+    request): one embedding call, then ONE fused C call per table for the whole batch instead of one per
+    request.  `filters`: one RetrieveFilters / None shared by all requests, or a list with one entry per
+    request (requests with equal filters form a group and share corpus reads on the dense lane).  Returns one
+    response per query, each equal to what `retrieve_ids` returns for it.  Falls back to per-request calls when a
+    table cannot take the fused path."""
     n = len(queries)
+    per_request = isinstance(filters, (list, tuple))
+    if per_request and len(filters) != n:
+        raise ValueError("one filter per query is required")
+    filter_of = (lambda i: filters[i]) if per_request else (lambda i: filters)
     bm25_chunks = [list(r) for r in bm25_chunks] if bm25_chunks is not None else [[] for _ in range(n)]
     bm25_artifacts = [list(r) for r in bm25_artifacts] if bm25_artifacts is not None else [[] for _ in range(n)]
     if len(bm25_chunks) != n or len(bm25_artifacts) != n:
@@ -518,7 +555,7 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters: Opt
     tables = [t for t in ("chunks", "artifact_chunks") if t in engine.stores]
     dense_enabled = embeddings_enabled()
     if not live or not tables or not all(_fused_path_ok(engine, t, dense_enabled) for t in tables):
-        return [retrieve_ids(engine, q, filters, bm25_chunks=bm25_chunks[i], bm25_artifacts=bm25_artifacts[i], debug=debug)
+        return [retrieve_ids(engine, q, filter_of(i), bm25_chunks=bm25_chunks[i], bm25_artifacts=bm25_artifacts[i], debug=debug)
                 for i, q in enumerate(queries)]
     dense_error: Optional[str] = None
     dense_model_id: Optional[str] = None
@@ -535,19 +572,25 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters: Opt
     limits = {"chunks": DEFAULT_DENSE_CHUNK_TOPK, "artifact_chunks": DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK}
     bm25 = {"chunks": [bm25_chunks[i] for i in live], "artifact_chunks": [bm25_artifacts[i] for i in live]}
     with engine.connect() as conn:
-        call_ids = _resolve_call_ids(conn, filters)
+        if per_request:
+            live_filters = [filters[i] for i in live]
+            call_ids = [_resolve_call_ids(conn, f) for f in live_filters]
+        else:
+            live_filters = filters
+            call_ids = _resolve_call_ids(conn, filters)
         per_table: Dict[str, List[Dict[str, Any]]] = {}
         try:
             for t in tables:
-                per_table[t] = _hybrid_table_batch(conn, t, q32 if dense_enabled else None, token_lists, filters,
-                                                   call_ids, bm25[t], limits[t])
+                per_table[t] = _hybrid_table_batch(conn, t, q32 if dense_enabled else None, token_lists, live_filters,
+                                                   call_ids, bm25[t], limits[t], per_request_filters=per_request)
         except DenseEngineError as exc:       # fail open to lexical-only, like EmbeddingClientError
             if not dense_enabled:
                 raise
             dense_enabled = False
             dense_error = str(exc)
             for t in tables:
-                per_table[t] = _hybrid_table_batch(conn, t, None, token_lists, filters, call_ids, bm25[t], limits[t])
+                per_table[t] = _hybrid_table_batch(conn, t, None, token_lists, live_filters, call_ids, bm25[t], limits[t],
+                                                   per_request_filters=per_request)
     empty = {"tech": [], "dense": [], "count": 0, "ranked": []}
     responses: List[Dict[str, Any]] = [{"retrieved_ids": []} for _ in range(n)]
     for j, i in enumerate(live):
@@ -558,7 +601,7 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters: Opt
         if dense_enabled:
             for t in tables:
                 candidates[t] = per_table[t][j]["count"]
-                modes[t] = _choose_dense_mode(candidates[t], filters, call_ids)
+                modes[t] = _choose_dense_mode(candidates[t], filter_of(i), call_ids[j] if per_request else call_ids)
         chunk_ranked, artifact_ranked = ch["ranked"], ar["ranked"]
         if "chunks" not in per_table:
             chunk_ranked = _rrf_merge({"bm25": bm25_chunks[i], "tech_tokens": []}, "chunk_id")
@@ -568,6 +611,100 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters: Opt
                                      ch["dense"], ar["dense"], dense_enabled, dense_model_id, dense_error, modes,
                                      candidates, debug)
     return responses
+
+
+class RequestBatcher:
+    """Micro-batcher in front of concurrent /retrieve requests.  The reference serves every request on its own
+    threadpool thread (app/main.py:184-186); here client threads hand their request to one worker, which drains
+    the queue -- up to `max_batch` requests, waiting at most `max_wait_s` for company -- and serves the whole batch
+    with ONE `retrieve_ids_batch` call: one embedding call, one fused C call per table (requests with equal filters
+    share corpus reads), one synchronisation.  Each client gets exactly the response `retrieve_ids` would give it."""
+
+    def __init__(self, engine: DenseEngine, max_batch: int = 64, max_wait_s: float = 2e-4, workers: int = 1):
+        import queue
+        import threading
+        self.engine = engine
+        self.max_batch = max(1, int(max_batch))
+        self.max_wait_s = float(max_wait_s)
+        self._queue: "queue.Queue" = queue.Queue()
+        self._closed = False
+        self._stats = threading.Lock()
+        self.batches_served = 0
+        self.requests_served = 0
+        # one worker by default: a second one (it would build response dicts while the first waits for the GPU in the
+        # GIL-free C call) halves the batch size and measured no better (profiles/r01/README.md)
+        self._workers = [threading.Thread(target=self._run, name=f"cadence-request-batcher-{i}", daemon=True)
+                         for i in range(max(1, int(workers)))]
+        for w in self._workers:
+            w.start()
+
+    def retrieve_ids(self, query: str, filters: Optional[RetrieveFilters] = None,
+                     bm25_chunks: Sequence[Mapping[str, Any]] = (), bm25_artifacts: Sequence[Mapping[str, Any]] = (),
+                     debug: bool = False) -> Dict[str, Any]:
+        import threading
+        if self._closed:
+            raise DenseEngineError("request batcher is closed", _ffi.CDR_ERR_STATE)
+        ticket = {"args": (query, filters, list(bm25_chunks), list(bm25_artifacts), debug), "done": threading.Event(),
+                  "result": None, "error": None}
+        self._queue.put(ticket)
+        ticket["done"].wait()
+        if ticket["error"] is not None:
+            raise ticket["error"]
+        return ticket["result"]
+
+    def close(self) -> None:
+        self._closed = True
+        for _ in self._workers:
+            self._queue.put(None)
+        for w in self._workers:
+            w.join(timeout=5)
+
+    def _run(self) -> None:
+        import queue
+        import time
+        import torch
+        stores = list(self.engine.stores.values())
+        device = stores[0].device if stores else settings.cadence_gpu_device
+        with torch.cuda.stream(torch.cuda.Stream(device=device)):       # each worker on its own stream
+            self._serve(queue, time)
+
+    def _serve(self, queue, time) -> None:
+        while True:
+            first = self._queue.get()
+            if first is None:
+                return
+            batch = [first]
+            deadline = time.perf_counter() + self.max_wait_s
+            stop = False
+            while len(batch) < self.max_batch:
+                remaining = deadline - time.perf_counter()
+                try:
+                    nxt = self._queue.get(timeout=remaining) if remaining > 0 else self._queue.get_nowait()
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    stop = True
+                    break
+                batch.append(nxt)
+            try:
+                want_debug = any(t["args"][4] for t in batch)
+                responses = retrieve_ids_batch(self.engine, [t["args"][0] for t in batch], [t["args"][1] for t in batch],
+                                               bm25_chunks=[t["args"][2] for t in batch],
+                                               bm25_artifacts=[t["args"][3] for t in batch], debug=want_debug)
+                for t, resp in zip(batch, responses):
+                    if want_debug and not t["args"][4]:
+                        resp = {k: v for k, v in resp.items() if k != "debug"}
+                    t["result"] = resp
+            except BaseException as exc:   # noqa: BLE001 - handed to every waiting client
+                for t in batch:
+                    t["error"] = exc
+            with self._stats:
+                self.batches_served += 1
+                self.requests_served += len(batch)
+            for t in batch:
+                t["done"].set()
+            if stop:
+                return
 
 
 # --------------------------------------------------------------------------- ids_only retrieve

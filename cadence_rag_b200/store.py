@@ -502,13 +502,19 @@ class DenseStore:
     # ------------------------------------------------------------------ fused hybrid /retrieve
     def hybrid_retrieve(self, queries, dense_k: int, *, tech_index=None, token_ids=None, n_tokens=None,
                         tech_limit: int = 50, bm25_ids=None, bm25_offsets=None, rrf_k: int = 60,
-                        filter_spec: Optional[Dict[str, Any]] = None, max_out: Optional[int] = None):
+                        filter_spec: Optional[Dict[str, Any]] = None, max_out: Optional[int] = None,
+                        filter_specs: Optional[Sequence[Optional[Dict[str, Any]]]] = None,
+                        group_offsets: Optional[Sequence[int]] = None):
         """One ``cdr_hybrid_retrieve_host`` call (include/cadence_dense.h): filter -> dense exact lane ->
         tech_tokens lane -> RRF for nq queries sharing one filter; one H2D, one D2H, one sync.
 
         queries: [nq, dim] float32 numpy or None (dense lane disabled).  token_ids [nq, T] int32 /
         n_tokens [nq] int32 with ``tech_index`` a DeviceTechIndex.  bm25_ids / bm25_offsets: the opaque
-        BM25 lane (ranked ids back to back, offsets [nq+1]).  Returns a dict of numpy arrays."""
+        BM25 lane (ranked ids back to back, offsets [nq+1]).  Returns a dict of numpy arrays.
+
+        Requests with different filters: pass ``filter_specs`` (one spec per group, None = unscoped) and
+        ``group_offsets`` ([n_groups + 1], queries of a group are consecutive) instead of ``filter_spec``
+        (``cdr_hybrid_retrieve_groups_host``); ``count`` is then a list with one COUNT(*) per group."""
         torch = _torch()
         dense = queries is not None
         if dense:
@@ -536,12 +542,37 @@ class DenseStore:
         kd = int(dense_k) if dense else 0
         if max_out is None:
             max_out = max(1, bm25_max + int(tech_limit) + kd)
-        spec, keep = self.filter_spec_struct(**(filter_spec or {}))
+        grouped = filter_specs is not None
+        if grouped:
+            n_groups = len(filter_specs)
+            offs = np.ascontiguousarray(group_offsets, dtype=np.int32)
+            if offs.shape[0] != n_groups + 1:
+                raise DenseEngineError("group_offsets must have one more entry than filter_specs")
+            specs = (_ffi.FilterSpec * n_groups)()
+            keep = []
+            for gi, fs in enumerate(filter_specs):
+                one, alive = self.filter_spec_struct(**(fs or {}))
+                keep.append(alive)
+                if one is not None:
+                    specs[gi] = one
+        else:
+            spec, keep = self.filter_spec_struct(**(filter_spec or {}))
         out = {"dense_ids": np.empty((nq, max(kd, 1)), dtype=np.int64), "dense_scores": np.empty((nq, max(kd, 1)), dtype=np.float64),
                "dense_n": np.zeros(nq, dtype=np.int32), "tech_ids": np.empty((nq, tech_limit), dtype=np.int64),
                "tech_n": np.zeros(nq, dtype=np.int32), "fused_ids": np.empty((nq, max_out), dtype=np.int64),
                "fused_scores": np.empty((nq, max_out), dtype=np.float64), "fused_mask": np.empty((nq, max_out), dtype=np.uint32),
                "fused_n": np.zeros(nq, dtype=np.int32)}
+        if grouped:
+            counts = np.zeros(n_groups, dtype=np.int64)
+            _ffi.check(_ffi.lib().cdr_hybrid_retrieve_groups_host(
+                self.handle, None if tech_index is None else tech_index._h, ctypes.addressof(specs), _ffi.ptr(offs), n_groups,
+                _ffi.ptr(q), nq, kd, _ffi.ptr(tok), _ffi.ptr(nt), max_tokens, int(tech_limit), _ffi.ptr(b_ids), _ffi.ptr(b_off),
+                int(rrf_k), int(max_out), _ffi.ptr(counts), _ffi.ptr(out["dense_ids"]), _ffi.ptr(out["dense_scores"]),
+                _ffi.ptr(out["dense_n"]), _ffi.ptr(out["tech_ids"]), _ffi.ptr(out["tech_n"]), _ffi.ptr(out["fused_ids"]),
+                _ffi.ptr(out["fused_scores"]), _ffi.ptr(out["fused_mask"]), _ffi.ptr(out["fused_n"]), self._stream()),
+                "cdr_hybrid_retrieve_groups_host")
+            out["count"] = counts.tolist()
+            return out
         count = ctypes.c_int64(0)
         _ffi.check(_ffi.lib().cdr_hybrid_retrieve_host(
             self.handle, None if tech_index is None else tech_index._h, None if spec is None else ctypes.addressof(spec),

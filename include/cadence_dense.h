@@ -292,6 +292,21 @@ int32_t cdr_hybrid_retrieve_host(
     int32_t *out_dense_n_host, int64_t *out_tech_ids_host, int32_t *out_tech_n_host, int64_t *out_fused_ids_host,
     double *out_fused_scores_host, uint32_t *out_fused_mask_host, int32_t *out_fused_n_host, void *stream);
 
+/* The same call for requests with DIFFERENT filters: the nq queries are ordered so that queries sharing a
+ * filter are consecutive; group g covers queries [group_offsets_host[g], group_offsets_host[g+1]) and uses
+ * filters[g] (an all-empty spec = unscoped; filters == NULL = every group unscoped).  Each group runs its own
+ * K6 / tech-lane / dense launches (shared corpus reads inside a group); lane assembly, RRF, the copies and the
+ * single synchronisation cover the whole block.  out_count_host has n_groups entries.  This is what a
+ * micro-batcher in front of concurrent /retrieve requests calls (cadence_rag_b200.retrieve.RequestBatcher). */
+int32_t cdr_hybrid_retrieve_groups_host(
+    cdr_store *s, cdr_tech_index *tech_index, const cdr_filter_spec *filters, const int32_t *group_offsets_host,
+    int32_t n_groups, const float *q_host, int32_t nq, int32_t dense_k, const int32_t *token_ids_host,
+    const int32_t *n_tokens_host, int32_t max_tokens, int32_t tech_limit, const int64_t *bm25_ids_host,
+    const int32_t *bm25_offsets_host, int32_t rrf_k, int32_t max_out, int64_t *out_count_host,
+    int64_t *out_dense_ids_host, double *out_dense_scores_host, int32_t *out_dense_n_host, int64_t *out_tech_ids_host,
+    int32_t *out_tech_n_host, int64_t *out_fused_ids_host, double *out_fused_scores_host, uint32_t *out_fused_mask_host,
+    int32_t *out_fused_n_host, void *stream);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* Number of this library's kernels launched by the calling process so far (bench.py's
  * gpu_launches claim). */

@@ -623,6 +623,40 @@ def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
         embeddings.set_embedder(None)
         monkeypatch.setattr(settings, "embeddings_base_url", "")
 
+    # requests with DIFFERENT filters in one fused call (grouped by filter), and through the micro-batcher
+    embeddings.set_embedder(emb)
+    try:
+        f_list = [None, cases[1][1], cases[7][1], cases[1][1], RetrieveFilters(external_id="missing"), None, cases[3][1]]
+        q_list = ["TOK-1 outage", "TOK-0 status", "TOK-1", "TOK-2 and TOK-5", "TOK-4", "   ", "TOK-2 and TOK-5"]
+        many = retrieve.retrieve_ids_batch(eng, q_list, f_list, bm25_chunks=[bm25, [], [], bm25[:1], [], [], []], debug=True)
+        for i, (q, f) in enumerate(zip(q_list, f_list)):
+            one = retrieve.retrieve_ids(eng, q, f, bm25_chunks=[bm25, [], [], bm25[:1], [], [], []][i], debug=True)
+            assert many[i] == one, (i, q, f)
+        import threading
+        batcher = retrieve.RequestBatcher(eng, max_batch=16, max_wait_s=2e-3)
+        got, errs = {}, []
+
+        def client(t):
+            try:
+                for j in range(6):
+                    i = (t * 6 + j) % len(q_list)
+                    got[(t, j)] = (i, batcher.retrieve_ids(q_list[i], f_list[i], debug=(j % 2 == 0)))
+            except Exception as exc:   # noqa: BLE001
+                errs.append(repr(exc))
+        threads = [threading.Thread(target=client, args=(t,)) for t in range(8)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        batcher.close()
+        assert not errs, errs
+        assert batcher.requests_served == 48 and batcher.batches_served < 48      # requests really were batched
+        for (t, j), (i, resp) in got.items():
+            want = retrieve.retrieve_ids(eng, q_list[i], f_list[i], debug=(j % 2 == 0))
+            assert resp == want, (t, j, i)
+    finally:
+        embeddings.set_embedder(None)
+
     # batched form: nq queries in one call == nq single calls
     store = eng.stores["chunks"]; dev_index = eng.device_tech_indexes["chunks"]
     qs = orc.synth_rows(SYNTH_QUERY_SEED, 100, 5)
