@@ -580,12 +580,15 @@ def run_hybrid(args):
                 except Exception as exc:   # noqa: BLE001
                     errs.append(repr(exc))
             threads = [threading.Thread(target=bclient, args=(t,)) for t in range(n_threads)]
+            old_interval = sys.getswitchinterval()
+            sys.setswitchinterval(5e-5)          # see above: the default 5 ms GIL hand-over makes thread timings erratic
             t0 = time.perf_counter()
             for th in threads:
                 th.start()
             for th in threads:
                 th.join()
             dt = time.perf_counter() - t0
+            sys.setswitchinterval(old_interval)
             batcher.close()
             assert not errs, errs
             out.setdefault(name, {})[f"batcher_{n_threads}_clients_queries_per_s"] = n_threads * per_thread / dt

@@ -415,18 +415,6 @@ def _embedding_f32(values: Sequence[float]) -> np.ndarray:
     return _query_vector(_vector_literal(values))
 
 
-def _rows_from_ids(store: DenseStore, ids: np.ndarray) -> List[Dict[str, Any]]:
-    cols = store.host_columns()
-    out: List[Dict[str, Any]] = []
-    for i, p in zip(ids.tolist(), np.searchsorted(cols["ids"], ids).tolist()):
-        slot = int(cols["call_slot"][p])
-        call_id = store.call_ids_by_slot[slot] if slot < len(store.call_ids_by_slot) else slot
-        row = {store.key_field: i, "call_id": call_id}
-        row.update(store.payload.get(i, {}))
-        out.append(row)
-    return out
-
-
 def _fused_path_ok(engine: DenseEngine, table: str, dense: bool) -> bool:
     """The fused C call serves a table when its dense lane is the exact fp32 scan and its tech lane
     (if any) is device resident; other configurations take the step-by-step path."""
@@ -451,7 +439,7 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
     nq): requests are then grouped by filter and every group runs its own filter / lane launches inside the
     same call (`cdr_hybrid_retrieve_groups_host`).  Returns, per request, {"tech": rows, "dense": rows,
     "count": COUNT(*), "ranked": [(row, lane-name set, score)]} with the rows / order the step-by-step
-    functions produce."""
+    functions produce (lane rows carry the id -- and the score on the dense lane -- only)."""
     store = conn.store(table)
     key = store.key_field
     nq = len(token_lists)
@@ -500,11 +488,14 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
     n_lanes = 3 if q32 is not None else 2
     out_pos = []
     for qi in range(nq):
-        tech_rows = _rows_from_ids(store, res["tech_ids"][qi, :int(res["tech_n"][qi])])
+        # the ids_only response needs ids, ranks and scores only: the SELECT-list columns (call_id, payload) are
+        # looked up by retrieve_evidence for the few rows that make it into the pack, not for every lane row
+        tech_rows = [{key: i} for i in res["tech_ids"][qi, :int(res["tech_n"][qi])].tolist()]
         dense_rows: List[Dict[str, Any]] = []
         if q32 is not None:
             m = int(res["dense_n"][qi])
-            dense_rows = _rows_from_hits(store, res["dense_ids"][qi, :m], res["dense_scores"][qi, :m])
+            dense_rows = [{key: i, "score": sc} for i, sc in zip(res["dense_ids"][qi, :m].tolist(),
+                                                                 res["dense_scores"][qi, :m].tolist())]
         items: Dict[int, Mapping[str, Any]] = {}
         for lane in (bm25_rows[qi], tech_rows, dense_rows):
             for row in lane:
