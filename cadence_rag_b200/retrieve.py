@@ -638,7 +638,9 @@ class RequestBatcher:
         ticket = {"args": (query, filters, list(bm25_chunks), list(bm25_artifacts), debug), "done": threading.Event(),
                   "result": None, "error": None}
         self._queue.put(ticket)
-        ticket["done"].wait()
+        while not ticket["done"].wait(timeout=1.0):
+            if not any(w.is_alive() for w in self._workers):
+                raise DenseEngineError("request batcher has no live worker", _ffi.CDR_ERR_STATE)
         if ticket["error"] is not None:
             raise ticket["error"]
         return ticket["result"]
@@ -654,10 +656,23 @@ class RequestBatcher:
         import queue
         import time
         import torch
-        stores = list(self.engine.stores.values())
-        device = stores[0].device if stores else settings.cadence_gpu_device
-        with torch.cuda.stream(torch.cuda.Stream(device=device)):       # each worker on its own stream
-            self._serve(queue, time)
+        try:
+            stores = list(self.engine.stores.values())
+            if stores and torch.cuda.is_available():
+                with torch.cuda.stream(torch.cuda.Stream(device=stores[0].device)):   # each worker on its own stream
+                    self._serve(queue, time)
+            else:
+                self._serve(queue, time)
+        except BaseException as exc:   # noqa: BLE001 - a dead worker must not leave clients waiting
+            self._closed = True
+            while True:
+                try:
+                    t = self._queue.get_nowait()
+                except queue.Empty:
+                    break
+                if t is not None:
+                    t["error"] = DenseEngineError(f"request batcher worker died: {exc!r}", _ffi.CDR_ERR_STATE)
+                    t["done"].set()
 
     def _serve(self, queue, time) -> None:
         while True:

@@ -486,3 +486,49 @@ def test_embedding_f32_equals_the_literal_round_trip():
         assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), via_text.view(np.uint32)) or \
             (np.isnan(got).any() and np.array_equal(np.isnan(got), np.isnan(via_text)))
     assert np.array_equal(retrieve._embedding_f32(f32.astype(np.float64).tolist()), f32)
+
+
+def test_request_batcher_queueing(monkeypatch):
+    """RequestBatcher host logic without a GPU: concurrent clients are served in batches by one retrieve_ids_batch
+    call each, every client gets its own response (debug payload only if it asked), an engine failure reaches every
+    client of the batch, and a closed batcher refuses work."""
+    import threading
+    import time
+    from cadence_rag_b200 import retrieve as R
+    seen = []
+
+    def fake_batch(engine, queries, filters, bm25_chunks=None, bm25_artifacts=None, debug=False):
+        seen.append((list(queries), list(filters), debug))
+        time.sleep(0.01)                                   # the "GPU": lets the queue fill behind the worker
+        if any(q == "boom" for q in queries):
+            raise R.DenseEngineError("engine failed")
+        return [{"retrieved_ids": [f"chunk:{q}:{f}"], **({"debug": {"q": q}} if debug else {})} for q, f in zip(queries, filters)]
+
+    monkeypatch.setattr(R, "retrieve_ids_batch", fake_batch)
+    engine = type("E", (), {"stores": {}})()
+    batcher = R.RequestBatcher(engine, max_batch=8, max_wait_s=5e-3)
+    results, errors = {}, {}
+
+    def client(t):
+        for j in range(5):
+            try:
+                results[(t, j)] = batcher.retrieve_ids(f"q{t}-{j}", t, debug=(t % 2 == 0))
+            except R.DenseEngineError as exc:
+                errors[(t, j)] = str(exc)
+    threads = [threading.Thread(target=client, args=(t,)) for t in range(12)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert len(results) == 60 and not errors
+    for (t, j), resp in results.items():
+        assert resp["retrieved_ids"] == [f"chunk:q{t}-{j}:{t}"]
+        assert ("debug" in resp) == (t % 2 == 0)
+    assert batcher.requests_served == 60 and batcher.batches_served < 40 and max(len(b[0]) for b in seen) <= 8
+    # a failing batch: every client in it sees the error, the batcher keeps serving afterwards
+    with pytest.raises(R.DenseEngineError, match="engine failed"):
+        batcher.retrieve_ids("boom", None)
+    assert batcher.retrieve_ids("after", 7)["retrieved_ids"] == ["chunk:after:7"]
+    batcher.close()
+    with pytest.raises(R.DenseEngineError):
+        batcher.retrieve_ids("late", None)
