@@ -119,3 +119,46 @@ def test_batch_lane_overflow_falls_back_to_exact_lane():
         w_ids, w_sc = orc.exact_scan(qs[i], x, 50, variant=orc.VARIANT_F64)
         assert ids[i].tolist() == w_ids.tolist()
     s.close()
+
+
+def test_batch_lane_vs_torch_fp32_matmul_reference_1m():
+    """An oracle that shares no code with the engine: plain PyTorch fp32 matmul (TF32 off) over the regenerated
+    1 M x 1024 corpus in row chunks with a running top-k, for all 1024 queries of a batch.
+    The tensor-core lane must reach recall@50 >= 0.999 against it, and where the ids agree its fp64 scores must
+    equal the fp32 reference within 1e-5 relative; the exact fp32 lane is held to the same reference."""
+    from cadence_rag_b200.store import synth_rows_device
+    n, nq, k = 1_000_000, 1024, 50
+    free, _ = torch.cuda.mem_get_info()
+    if free < 20e9:
+        pytest.skip("needs ~12 GB of free HBM")
+    s = _store(n)
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        q = synth_rows_device(SYNTH_QUERY_SEED, 5000, nq, 1024, device=0)
+        qn = q / q.norm(dim=1, keepdim=True)
+        best_sc = torch.full((nq, k), -2.0, device="cuda")
+        best_id = torch.full((nq, k), -1, dtype=torch.int64, device="cuda")
+        chunk = 100_000
+        for r0 in range(0, n, chunk):
+            x = synth_rows_device(SYNTH_CORPUS_SEED, r0, chunk, 1024, device=0)      # same bits as the store's rows
+            sc = qn @ (x / x.norm(dim=1, keepdim=True)).T                             # fp32 cosine, [nq, chunk]
+            c_sc, c_ix = sc.topk(k, dim=1)
+            all_sc = torch.cat([best_sc, c_sc], dim=1)
+            all_id = torch.cat([best_id, c_ix + (r0 + 1)], dim=1)                     # chunk_id = row + 1
+            best_sc, pick = all_sc.topk(k, dim=1)
+            best_id = all_id.gather(1, pick)
+        ref_id, ref_sc = best_id.cpu().numpy(), best_sc.cpu().numpy().astype(np.float64)
+        for name, (ids, sc, cnt) in (("bf16 tensor-core lane", s.search_batch(q, k)), ("exact fp32 lane", s.search_exact(q[:128].contiguous(), k))):
+            torch.cuda.synchronize()
+            ids, sc, cnt = ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+            m = ids.shape[0]
+            assert np.all(cnt == k), name
+            recall = np.mean([len(set(ids[i]) & set(ref_id[i])) / k for i in range(m)])
+            assert recall >= 0.999, (name, recall)
+            agree = ids == ref_id[:m]
+            assert agree.mean() > 0.97, (name, agree.mean())                           # fp32 vs fp64 order: rare near-tie swaps only
+            assert np.allclose(sc[agree], ref_sc[:m][agree], rtol=1e-5, atol=0), name
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        s.close()
