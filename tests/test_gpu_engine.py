@@ -904,6 +904,30 @@ def test_full_size_10m_properties(monkeypatch):
         assert recall >= 0.999
         same = b_ids[:32] == e_ids
         assert np.array_equal(b_sc[:32][same].view(np.uint64), e_sc[same].view(np.uint64))   # re-scored exactly
+        # BASELINE configs[2] exactly: 1024 queries over the 10 M rows, against plain PyTorch fp32 matmul (TF32 off)
+        from cadence_rag_b200.store import synth_rows_device
+        old_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            q1k = synth_rows_device(SYNTH_QUERY_SEED, 9000, 1024, 1024, device=0)
+            qn = q1k / q1k.norm(dim=1, keepdim=True)
+            best_sc = torch.full((1024, k), -2.0, device="cuda")
+            best_id = torch.full((1024, k), -1, dtype=torch.int64, device="cuda")
+            for r0 in range(0, n, 250_000):
+                xc = synth_rows_device(SYNTH_CORPUS_SEED, r0, 250_000, 1024, device=0)
+                c_sc, c_ix = (qn @ (xc / xc.norm(dim=1, keepdim=True)).T).topk(k, dim=1)
+                best_sc, pick = torch.cat([best_sc, c_sc], dim=1).topk(k, dim=1)
+                best_id = torch.cat([best_id, c_ix + (r0 + 1)], dim=1).gather(1, pick)
+                del xc
+            t_ids, t_sc, t_cnt = s.search_batch(q1k, k)
+            torch.cuda.synchronize()
+            got, ref = t_ids.cpu().numpy(), best_id.cpu().numpy()
+            assert np.mean([len(set(got[i]) & set(ref[i])) / k for i in range(1024)]) >= 0.999
+            agree = got == ref
+            assert agree.mean() > 0.97
+            assert np.allclose(t_sc.cpu().numpy()[agree], best_sc.cpu().numpy().astype(np.float64)[agree], rtol=1e-5, atol=0)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old_tf32
         # selective filter at full size (gather launch) == unfiltered result restricted to the filter, when it fits
         allow, count = s.filter_bitmap(call_slots=list(range(35_000, 35_010)))        # rows 7 000 000 .. 7 001 999
         f_ids, f_sc, f_cnt = s.search_exact(qs[:2], k, allow)
