@@ -228,6 +228,21 @@ struct GemmParams {
     int debug_no_append;       // measurement aid (CADENCE_K2_DRYRUN=1): treat tau as +inf => pure GEMM + max
 };
 
+// A corpus tile (kBlockN = 256 rows = 8 bitmap words) none of whose rows passes the filter is skipped by all
+// three roles (same deterministic test, so their pipeline counters stay in step): no TMA, no MMA, no epilogue.
+// Filters with block structure -- a date range over time-ordered rows, a set of calls -- leave most tiles empty.
+__device__ __forceinline__ bool tile_has_allowed_rows(const uint32_t *allow, int64_t nt, int64_t n_rows)
+{
+    if (allow == nullptr) return true;
+    const int64_t w0 = nt * (kBlockN / 32);
+    const int64_t words = (n_rows + 31) >> 5;
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < kBlockN / 32; ++i)
+        if (w0 + i < words) any |= __ldg(&allow[w0 + i]);
+    return any != 0;
+}
+
 // Flush one epilogue thread's staged appends to the global candidate lists: all atomics first
 // (independent, so their round trips overlap), then the stores.  Deliberately NOT inlined: the
 // epilogue's hot loop must stay small enough for the instruction cache.
@@ -335,6 +350,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 int64_t tj; int mt;
                 item_of(i, tj, mt);
                 const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
+                if (!tile_has_allowed_rows(p.allow, nt, p.n_rows)) continue;
                 for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
                     const int s = it % kStg;
                     const uint32_t ph = (it / kStg) & 1u;
@@ -365,7 +381,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     } else if (warp == 1 && !(k2Sm && crank != 0)) {
         // ---------------------------------------------------------------- MMA issuer (2-SM: leader CTA only)
         uint32_t it = 0, tile_no = 0;
-        for (int64_t i = 0; i < n_my; ++i, ++tile_no) {
+        for (int64_t i = 0; i < n_my; ++i) {
+            {
+                int64_t tj; int mt;
+                item_of(i, tj, mt);
+                if (!tile_has_allowed_rows(p.allow, (tj * p.perm_mul) % p.n_tiles_total, p.n_rows)) continue;
+            }
             const uint32_t buf = tile_no & 1u;
             const uint32_t use = tile_no >> 1;                    // how many times this buffer was used before
             mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
@@ -401,6 +422,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 __syncwarp();
             }
+            ++tile_no;
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue
@@ -408,10 +430,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int et = ew * 32 + lane;                            // epilogue thread 0..127
         int nbuf = 0;
         uint32_t tile_no = 0;
-        for (int64_t i = 0; i < n_my; ++i, ++tile_no) {
+        for (int64_t i = 0; i < n_my; ++i) {
             int64_t tj; int mt;
             item_of(i, tj, mt);
             const int64_t nt = (tj * p.perm_mul) % p.n_tiles_total;
+            if (!tile_has_allowed_rows(p.allow, nt, p.n_rows)) continue;
             const int64_t row0 = nt * kBlockN;
             const int q = mt * kBlockM + et;
             const bool q_ok = q < p.nq;
@@ -483,6 +506,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
                 nbuf = 0;
             }
+            ++tile_no;
         }
         if (nbuf > 0) flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
     }

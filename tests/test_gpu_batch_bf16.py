@@ -162,3 +162,28 @@ def test_batch_lane_vs_torch_fp32_matmul_reference_1m():
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old_tf32
         s.close()
+
+
+def test_batch_lane_skips_empty_tiles_under_block_filters(corpus):
+    """Filters with block structure (a date range over time-ordered rows, a run of calls, a single row) leave whole
+    256-row corpus tiles without an allowed row; the tensor-core lane skips those tiles in all three warp roles.
+    The answer must still be the exact lane's."""
+    from cadence_rag_b200.store import SYNTH_CALL_PERIOD_US, SYNTH_T0_US
+    s, x = corpus
+    n = x.shape[0]
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 7000, 130)
+    singles = np.zeros(n, dtype=bool); singles[[5, 255, 256, 70_000, n - 1]] = True
+    specs = [dict(date_from=SYNTH_T0_US + 300 * SYNTH_CALL_PERIOD_US),                        # the last 40 % of the rows
+             dict(date_from=SYNTH_T0_US + 100 * SYNTH_CALL_PERIOD_US, date_to=SYNTH_T0_US + 130 * SYNTH_CALL_PERIOD_US),
+             dict(call_slots=list(range(40, 60)) + [499])]
+    allows = [s.filter_bitmap(**sp)[0] for sp in specs]
+    allows.append(torch.from_numpy(orc.rows_to_bitmap(singles).view(np.int32)).cuda())       # 5 rows: short result -> exact-lane fallback
+    for allow in allows:
+        for nq in (130, 256):
+            q = np.concatenate([qs, qs[:nq - 130]]) if nq > 130 else qs
+            ids, sc, cnt = s.search_batch(q, 50, allow)
+            e_ids, e_sc, e_cnt = s.search_exact(q, 50, allow)
+            assert np.array_equal(cnt, e_cnt)
+            assert _recall(ids, cnt, [e_ids[i, :int(e_cnt[i])] for i in range(nq)]) >= 0.999
+            same = ids == e_ids
+            assert same.mean() > 0.98 and np.array_equal(sc[same & (ids >= 0)].view(np.uint64), e_sc[same & (ids >= 0)].view(np.uint64))
