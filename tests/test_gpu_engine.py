@@ -1063,3 +1063,49 @@ def test_device_tech_lane_matches_port(hybrid_engine):
         ids, n = dev.query_batch([["TOK-0"], [], ["TOK-5", "TOK-6"]], 50)
         assert n[1] == 0 and ids[0, :n[0]].tolist() == dev.query_ids(["TOK-0"], 50)
         assert ids[2, :n[2]].tolist() == dev.query_ids(["TOK-5", "TOK-6"], 50) and np.all(ids[1] == -1)
+
+
+def test_eval_replay_scores_the_engine_like_run_eval(hybrid_engine, monkeypatch, tmp_path, capsys):
+    """SURVEY 8(f) f-3: a gold set replayed through the fused batch call gives the rows eval/run_eval.py reads;
+    each equals the one-request facade's answer, and the metrics (golden-checked arithmetic) see the planted rows."""
+    from cadence_rag_b200 import eval_replay as E
+    eng, meta = hybrid_engine
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    m = meta["chunks"]
+    rng = np.random.default_rng(23)
+    rows = [int(r) for r in rng.choice(np.flatnonzero(m["valid"]), 70, replace=False)]
+    vec_of_text, gold_rows = {}, []
+    for j, r in enumerate(rows):
+        v = m["x"][r] + 0.02 * rng.standard_normal(1024).astype(np.float32)       # a paraphrase of row r
+        text = f"what was said in passage {j}" + (" about TOK-3" if j % 7 == 0 else "")
+        vec_of_text[text] = (v / np.linalg.norm(v)).astype(np.float32)
+        row = {"query_id": f"g{j}", "query": text, "relevant_ids": [f"chunk:{int(m['ids'][r])}"]}
+        if j % 3 == 0:
+            row["filters"] = {"call_ids": [_uuid(int(m["call_of_row"][r])), _uuid(99)]}
+        if j % 10 == 9:
+            row["filters"] = {"call_tags": m["tags_of_call"][int(m["call_of_row"][r])][:1]}
+        gold_rows.append(row)
+    gold_rows.append({"query_id": "blank", "query": "   ", "relevant_ids": ["chunk:2"]})
+    gold_rows.append({"query_id": "unjudged", "query": gold_rows[0]["query"], "relevant_ids": []})
+    embeddings.set_embedder(lambda batch: embeddings.EmbeddingResult(vectors=[vec_of_text[t].tolist() for t in batch], model="para"))
+    try:
+        out_path = str(tmp_path / "results.jsonl")
+        results = E.replay(eng, gold_rows, batch=32, out_path=out_path)
+        for row, got in zip(gold_rows, results):
+            want = retrieve.retrieve_ids(eng, row["query"], E._filters_of(row))
+            assert got == {"query_id": row["query_id"], "retrieved_ids": want["retrieved_ids"]}
+        metrics = E.evaluate(eng, gold_rows, ks=[1, 5], batch=64)
+    finally:
+        embeddings.set_embedder(None)
+    assert E.load_jsonl(out_path) == results
+    assert results[-2]["retrieved_ids"] == []                                       # blank query
+    judged = len(rows) + 1
+    # the planted row wins the chunk dense lane (1/61); only the artifact table's rank-1 rows (kind order) and, for the
+    # queries with a tech token, rows of that lane can precede it
+    for j, (row, got) in enumerate(zip(gold_rows[:len(rows)], results)):
+        rank = got["retrieved_ids"].index(row["relevant_ids"][0]) + 1
+        assert rank <= (10 if j % 7 == 0 else 2), (j, rank)
+    assert (len(rows) - 10) / judged <= metrics["recall@5"] <= len(rows) / judged
+    assert metrics["mrr"] >= 0.3 * len(rows) / judged
+    gold = {r["query_id"]: r["relevant_ids"] for r in gold_rows}
+    assert metrics == E.compute_metrics(gold, {r["query_id"]: r["retrieved_ids"] for r in results}, [1, 5])

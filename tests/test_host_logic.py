@@ -532,3 +532,35 @@ def test_request_batcher_queueing(monkeypatch):
     batcher.close()
     with pytest.raises(R.DenseEngineError):
         batcher.retrieve_ids("late", None)
+
+
+# ---------------------------------------------------------------- offline evaluation (eval/run_eval.py) on the engine's output
+def test_eval_metrics_match_reference_golden(golden_dir):
+    """recall@k / MRR / nDCG@k of `eval_replay.compute_metrics` equal the reference's `compute_metrics`
+    (eval/run_eval.py:26-65, run live by tests/golden/make_golden_eval.py) bit for bit, key order included."""
+    from cadence_rag_b200.eval_replay import compute_metrics
+    with open(os.path.join(golden_dir, "reference_eval_metrics.json")) as f:
+        gold = json.load(f)
+    assert len(gold["cases"]) >= 20
+    for case in gold["cases"]:
+        got = compute_metrics(case["gold"], case["results"], case["ks"])
+        assert list(got.keys()) == case["metric_order"]
+        assert {k: float(v).hex() for k, v in got.items()} == case["metrics_hex"]
+
+
+def test_eval_cli_and_jsonl_round_trip(tmp_path, capsys):
+    from cadence_rag_b200 import eval_replay as E
+    gold_rows = [{"query_id": "a", "query": "x", "relevant_ids": ["chunk:1", "chunk:2"]},
+                 {"query_id": "b", "query": "y", "relevant_ids": []},
+                 {"query_id": "c", "query": "z", "relevant_ids": ["artifact_chunk:9"]}]
+    result_rows = [{"query_id": "a", "retrieved_ids": ["chunk:7", "chunk:2", "chunk:1"]},
+                   {"query_id": "c", "retrieved": ["artifact_chunk:9"]}]           # legacy key, run_eval.py:82
+    gold_path, res_path = str(tmp_path / "gold.jsonl"), str(tmp_path / "res.jsonl")
+    E.dump_jsonl(gold_rows, gold_path)
+    E.dump_jsonl(result_rows, res_path)
+    assert E.load_jsonl(gold_path) == gold_rows
+    E.main(["--gold", gold_path, "--results", res_path, "--k", "1", "3"])
+    m = json.loads(capsys.readouterr().out)
+    assert m["recall@1"] == 0.5 and m["recall@3"] == 1.0          # (0 + 1)/2, (1 + 1)/2; query b is skipped
+    assert m["mrr"] == 0.75                                        # (1/2 + 1)/2
+    assert E.compute_metrics({}, {}, [5]) == {"recall@5": 0.0, "mrr": 0.0, "ndcg@5": 0.0}
