@@ -61,7 +61,21 @@ struct ScanParams {
 // 3 warps, i.e. <= 170 registers per thread; 4 queries (128 registers of query data) spill, and because the CTA
 // takes ~all of the unified L1/shared memory for its tile ring the spills go to L2 (measured: 1.26x instead of
 // 4x).  3 queries compile to 168 registers with no spills.
+//
+// kDeepQPC = "deep shared reads" for batches of >= 4 exact requests: the roles swap -- a warp keeps its RPW rows of
+// the tile in registers (64 for 2 rows x 1024 dims) and streams the QUERIES from shared memory, 8 of them per
+// corpus pass.  Shared-memory bandwidth is then the limit ((RPW + QPC) x 4 KB of LDS.128 per warp and tile:
+// ~160 clk per row against ~123 clk per row of HBM arrival), the top-k state of the 8 queries lives in shared
+// memory too (thresholds are read back per candidate, pushes are rare), and the tile ring shrinks to 2 stages --
+// enough, because a stage is released as soon as its rows are in registers.  Same lanes, same FMA order, same
+// reduction => same bits as one scan per query.
 constexpr int kSharedQPC = 3;
+constexpr int kDeepQPC = 8;
+struct DeepTopK {     // per (consumer warp, query) in shared memory
+    uint64_t tau;
+    int count;
+    int min_pos;
+};
 template <int J, int RPW, int NPL, int QPC>
 struct ScanSmem {
     static constexpr int DIM = J * 128;
@@ -71,9 +85,14 @@ struct ScanSmem {
     static constexpr size_t kMetaBytes = (size_t)TR * 4;   // inverse norms (multiple of 16)
     static constexpr size_t kListBytes = (size_t)kConsumerWarps * QPC * KC * 8;
     static constexpr size_t kBarBytes = 3 * kMaxStages * 8;   // full + empty barriers + the tile index of each stage
+    // deep shared reads (QPC > kSharedQPC): the queries, their inverse norms and the per-(warp, query) top-k
+    // state live in shared memory instead of registers
+    static constexpr bool kDeep = QPC > kSharedQPC;
+    static constexpr size_t kQueryBytes = kDeep ? (size_t)QPC * DIM * 4 : 0;
+    static constexpr size_t kStateBytes = kDeep ? (size_t)kConsumerWarps * QPC * 16 + (size_t)QPC * 4 : 0;
     static constexpr size_t bytes(int stages)
     {
-        return (size_t)stages * (kTileBytes + kMetaBytes) + kListBytes + kBarBytes + 128;
+        return (size_t)stages * (kTileBytes + kMetaBytes) + kQueryBytes + kListBytes + kStateBytes + kBarBytes + 128;
     }
     static int max_stages(size_t smem_limit)
     {
@@ -93,8 +112,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     const int S = p.n_stages;
     unsigned char *tiles = smem_raw;
     unsigned char *metas = tiles + (size_t)S * L::kTileBytes;
-    uint64_t *lists = reinterpret_cast<uint64_t *>(metas + (size_t)S * L::kMetaBytes);
-    uint64_t *full_bar = lists + kConsumerWarps * QPC * KC;
+    float4 *qs = reinterpret_cast<float4 *>(metas + (size_t)S * L::kMetaBytes);           // deep: [QPC][DIM/4]
+    uint64_t *lists = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(qs) + L::kQueryBytes);
+    DeepTopK *dstate = reinterpret_cast<DeepTopK *>(lists + kConsumerWarps * QPC * KC);   // deep: [warps][QPC]
+    float *qinv_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dstate) + (size_t)kConsumerWarps * QPC * 16 * (L::kDeep ? 1 : 0));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(dstate) + L::kStateBytes);
     uint64_t *empty_bar = full_bar + kMaxStages;
     long long *stage_tile = reinterpret_cast<long long *>(empty_bar + kMaxStages);   // tile held by a stage, -1 = end
 
@@ -206,6 +228,155 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
         }
     } else {
         // ------------------------------------------------------------------ consumers
+        if constexpr (L::kDeep) {
+            // ---- deep shared reads: rows in registers, queries + top-k state in shared memory
+            constexpr int GQ = 8 / RPW;                       // queries per joint reduction (8 values)
+            static_assert(QPC % GQ == 0, "deep shared reads: QPC must be a multiple of 8 / RPW");
+            for (int u = warp; u < QPC; u += kConsumerWarps) {
+                float qn = 0.f;
+                const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(q0 + (u < nqv ? u : 0)) * DIM);
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float4 t = __ldg(&qv[j * 32 + lane]);
+                    qs[u * (DIM / 4) + j * 32 + lane] = t;
+                    qn = fmaf(t.x, t.x, qn);
+                    qn = fmaf(t.y, t.y, qn);
+                    qn = fmaf(t.z, t.z, qn);
+                    qn = fmaf(t.w, t.w, qn);
+                }
+                qn = warp_sum_f32(qn);
+                if (lane == 0) qinv_s[u] = __fdiv_rn(1.0f, __fsqrt_rn(qn));
+            }
+            DeepTopK *my_state = dstate + warp * QPC;
+            uint64_t *my_lists = lists + (size_t)warp * QPC * KC;
+            for (int i = lane; i < QPC * KC; i += 32) my_lists[i] = CDR_EMPTY_KEY;
+            if (lane < QPC) {
+                my_state[lane].tau = 0;
+                my_state[lane].count = 0;
+                my_state[lane].min_pos = 0;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+
+            for (int64_t i = 0;; ++i) {
+                const int s = (int)(i % S);
+                const uint32_t ph = (uint32_t)((i / S) & 1);
+                mbar_wait(&full_bar[s], ph);
+                const int64_t tile = stage_tile[s];
+                if (tile < 0) break;
+                const int64_t row0 = tile * TR + warp * RPW;
+                uint32_t allow_bits = 0xFFFFFFFFu;
+                uint32_t g_row[RPW];
+                float g_inv[RPW];
+                if (gather) {
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) {
+                        const bool in = row0 + r < (int64_t)n_listed;
+                        g_row[r] = in ? __ldg(&p.row_list[row0 + r]) : 0u;
+                        g_inv[r] = __ldg(&p.inv_norm[g_row[r]]);
+                        if (!in) allow_bits &= ~(1u << r);
+                    }
+                } else if (p.allow != nullptr) {
+                    const uint32_t w = (row0 < p.n_rows) ? __ldg(&p.allow[row0 >> 5]) : 0u;
+                    allow_bits = w >> (row0 & 31);
+                }
+                const float4 *tv = reinterpret_cast<const float4 *>(tiles + (size_t)s * L::kTileBytes) +
+                                   (size_t)(warp * RPW) * (DIM / 4);
+                const float *mv = reinterpret_cast<const float *>(metas + (size_t)s * L::kMetaBytes) + warp * RPW;
+                float4 rv[RPW][J];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r)
+#pragma unroll
+                    for (int j = 0; j < J; ++j) rv[r][j] = tv[r * (DIM / 4) + j * 32 + lane];
+                float inv_n[RPW];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) inv_n[r] = gather ? g_inv[r] : mv[r];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);        // the rows are in registers: refill the stage
+
+                const int v = (lane >> 2) & 7;                    // the value this 4-lane group owns after the reduction
+                const int vu = v / RPW, vr = v % RPW;
+                float s_inv_n = inv_n[0];
+                int64_t s_row = gather ? (int64_t)g_row[0] : row0;
+#pragma unroll
+                for (int r = 1; r < RPW; ++r)
+                    if (vr == r) { s_inv_n = inv_n[r]; s_row = gather ? (int64_t)g_row[r] : row0 + r; }
+                const bool s_ok = (s_row < p.n_rows) && ((allow_bits >> vr) & 1u);
+                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+#pragma unroll 1
+                for (int g = 0; g < QPC / GQ; ++g) {
+                    float a8[8];
+#pragma unroll
+                    for (int uu = 0; uu < GQ; ++uu) {
+                        const float4 *qp = qs + (g * GQ + uu) * (DIM / 4) + lane;
+                        float acc[RPW][2];
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) acc[r][0] = acc[r][1] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < J; ++j) {
+                            const float4 qv = qp[j * 32];                 // one LDS.128 feeds RPW rows
+#pragma unroll
+                            for (int r = 0; r < RPW; ++r) {
+                                float a = acc[r][j & 1];
+                                a = fmaf(rv[r][j].x, qv.x, a);
+                                a = fmaf(rv[r][j].y, qv.y, a);
+                                a = fmaf(rv[r][j].z, qv.z, a);
+                                a = fmaf(rv[r][j].w, qv.w, a);
+                                acc[r][j & 1] = a;
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) a8[uu * RPW + r] = acc[r][0] + acc[r][1];
+                    }
+                    // the transposed reduction of the QPC <= 3 path (same additions per lane as the butterfly)
+                    float h4[4], h2[2];
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2)
+                        h4[i2] = (b4 ? a8[i2 + 4] : a8[i2]) + __shfl_xor_sync(0xffffffffu, b4 ? a8[i2] : a8[i2 + 4], 16);
+#pragma unroll
+                    for (int i2 = 0; i2 < 2; ++i2)
+                        h2[i2] = (b3 ? h4[i2 + 2] : h4[i2]) + __shfl_xor_sync(0xffffffffu, b3 ? h4[i2] : h4[i2 + 2], 8);
+                    float dot = (b2 ? h2[1] : h2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? h2[0] : h2[1], 4);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                    const int u_mine = g * GQ + vu;
+                    const uint64_t key = cdr_pack_key(dot * s_inv_n * qinv_s[u_mine], (uint32_t)s_row);
+                    unsigned pend = __ballot_sync(0xffffffffu, s_ok && key > my_state[u_mine].tau) & 0x11111111u;
+                    while (pend) {                                // rare; warp-uniform
+                        const int src = __ffs(pend) - 1;
+                        pend &= pend - 1;
+                        const uint64_t k1 = __shfl_sync(0xffffffffu, key, src);
+                        const int u1 = g * GQ + (src >> 2) / RPW;
+                        DeepTopK *ts = my_state + u1;
+                        uint64_t *tl = my_lists + (size_t)u1 * KC;
+                        if (k1 > ts->tau) {                       // re-tested: an earlier insert may have raised tau
+                            const int cnt = __shfl_sync(0xffffffffu, ts->count, 0);   // lane 0 is the only writer
+                            if (lane == 0) {
+                                tl[cnt < KC ? cnt : ts->min_pos] = k1;
+                                if (cnt < KC) ts->count = cnt + 1;
+                            }
+                            __syncwarp();
+                            if (cnt + 1 >= KC) {                  // list full: new threshold = its minimum
+                                uint64_t m = ~0ull;
+                                int pos = 0;
+#pragma unroll
+                                for (int i2 = 0; i2 < NPL; ++i2) {
+                                    const uint64_t x = tl[i2 * 32 + lane];
+                                    if (x < m) { m = x; pos = i2 * 32 + lane; }
+                                }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    const uint64_t om = __shfl_xor_sync(0xffffffffu, m, o);
+                                    const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+                                    if (om < m) { m = om; pos = op; }
+                                }
+                                if (lane == 0) { ts->tau = m; ts->min_pos = pos; }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        } else {
         float4 q[QPC][J];
         float inv_qn[QPC];
         WarpTopK<NPL> top[QPC];
@@ -345,6 +516,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                         if (su == u && k1 > top[u].tau) top[u].push(k1, lane);   // re-tested: an earlier insert may have raised tau
                 }
             }
+        }
+
         }
 
         // ---- per query: per-warp sort, then 3-level pairwise merge through shared memory
@@ -865,7 +1038,16 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
         stages = st_n;
     }
     const int64_t n_tiles = (s->n_rows + L::TR - 1) / L::TR;
-    int grid = (int)(n_tiles < s->sm_count ? n_tiles : s->sm_count);
+    const int n_groups = (nq + QPC - 1) / QPC;
+    // Shared reads with several query groups: the groups split the SMs instead of queueing behind each other with
+    // a full-width grid each.  The bytes streamed are the same, but a CTA then sees n_groups times more rows per
+    // query, so its running top-k saturates and far fewer rows pass the threshold test (1 M rows, 64 queries:
+    // 27 % -> 5 % of the rows cost an insertion), and the finalize kernel merges n_groups times fewer lists.
+    // CADENCE_K1_SPLIT=0 keeps a full-width grid per group (A/B aid).
+    static const bool k1_split = [] { const char *e = getenv("CADENCE_K1_SPLIT"); return !(e && e[0] == '0'); }();
+    int sm_share = s->sm_count;
+    if (QPC > 1 && n_groups > 1 && k1_split) sm_share = s->sm_count / n_groups > 0 ? s->sm_count / n_groups : 1;
+    int grid = (int)(n_tiles < sm_share ? n_tiles : sm_share);
     if (grid < 1) grid = 1;
 
     // Selective filters.  The reference's planner sends small scoped candidate sets (<= 2 000 rows by default,
@@ -889,7 +1071,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
         if (cap < L::TR) cap = L::TR;
         list_cap = (uint32_t)cap;
         const int64_t gt = (cap + L::TR - 1) / L::TR;
-        g_gather = (int)(gt < s->sm_count ? gt : s->sm_count);
+        g_gather = (int)(gt < sm_share ? gt : sm_share);
         if (cdr_ws_reserve((void **)&ws.row_list, &ws.row_list_bytes, (size_t)cap * 4 + 16) != CDR_OK) return CDR_ERR_OOM;
         unsigned int *cnt = reinterpret_cast<unsigned int *>(ws.row_list) + cap;      // the count lives behind the list
         CDR_CUDA(cudaMemsetAsync(cnt, 0, 4, st));
@@ -927,7 +1109,6 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     sp.lists_per_query = g_total;
     sp.list_offset = 0;
 
-    const int n_groups = (nq + QPC - 1) / QPC;
     cdr_prof_mark_begin(0, st);
     if (g_gather > 0) {
         ScanParams gp = sp;
@@ -967,7 +1148,16 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                     const uint32_t *allow, int k, double *out_score, int64_t *out_id,
                     int32_t *out_n, cudaStream_t st, bool share)
 {
+    // deep shared reads: batches of more than 2 x kSharedQPC requests with the narrow candidate lists (k <= 56);
+    // CADENCE_K1_DEEP=0 keeps the 3-queries-in-registers kernel (A/B aid)
+    static const bool k1_deep = [] { const char *e = getenv("CADENCE_K1_DEEP"); return !(e && e[0] == '0'); }();
+    // (measured at 1 M rows: 4-6 queries 1.17 ms as two register groups on half of the SMs each vs 1.36 ms as one
+    //  deep group; 8 queries 1.51 vs 1.40 ms; 64 queries 9.5 vs 7.5 ms -- profiles/r01/k1_shared_probe_*.json)
+    const bool deep = share && NPL == 2 && nq > 2 * kSharedQPC && k1_deep;
 #define CDR_SCAN_CASE(J_, RPW_)                                                                              \
+    if constexpr (NPL == 2) {                                                                                \
+        if (deep) return launch_scan_t<J_, RPW_, NPL, kDeepQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
+    }                                                                                                        \
     if (share) return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
     return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st)
     switch (s->dim) {

@@ -295,16 +295,24 @@ def fetch_dense_batch(conn: DenseConnection, table_name: str, queries, filters, 
 
 
 def _batch_lane_is_faster(store: DenseStore, nq: int, candidate_rows: int) -> bool:
-    """Lane choice inside mode "ann" for a batch.  The bf16 tensor-core lane multiplies EVERY row (the filter is
-    applied in its epilogue): time ~ max(flops / 1.2 PFLOP/s, bf16 corpus bytes / 6.7 TB/s).  The exact lane with
-    shared reads streams only the candidate rows when the filter keeps <= rows/2 (gather launch, ~5.4 TB/s),
-    once per 3 queries.  Measured rates from profiles/r01/README.md; the exact lane wins for selective filters."""
+    """Lane choice inside mode "ann" for a batch.  The bf16 tensor-core lane multiplies every 256-row tile that
+    keeps at least one row (call-level filters keep runs of rows: ~2.5 x the candidate rows are touched) at
+    ~1.2 PFLOP/s, with ~1.5 ms of small-segment overhead under a filter.  The exact lane with shared reads streams
+    only the candidate rows when the filter keeps <= rows/2 (gather launch), once per 8 queries (shared-memory
+    bound, ~4.3 TB/s of tile reads) or once per 3 queries for batches of <= 6.  Measured rates from
+    profiles/r01/README.md; small candidate sets always stay on the exact lane."""
     rows, dim = store.rows, store.dim
-    nq_pad = -(-nq // 128) * 128
-    t_batch = max(2.0 * nq_pad * rows * dim / 1.2e15, rows * dim * 2 / 6.7e12) + 2e-4
     scanned = candidate_rows if candidate_rows * 2 <= rows else rows
-    rate = 5.4e12 if scanned < rows else 5.8e12
-    t_exact = -(-nq // 3) * (scanned * dim * 4 / rate + 2e-5) + 5e-5
+    if scanned * dim * 4 <= (1 << 26):
+        return False
+    touched = rows if candidate_rows * 2.5 >= rows else int(candidate_rows * 2.5)
+    nq_pad = -(-nq // 128) * 128
+    t_batch = max(2.0 * nq_pad * touched * dim / 1.2e15, touched * dim * 2 / 6.7e12) + (2e-4 if touched == rows else 1.5e-3)
+    if nq > 6:
+        passes, rate = -(-nq // 8), 4.3e12
+    else:
+        passes, rate = -(-nq // 3), (5.4e12 if scanned < rows else 6.5e12)
+    t_exact = passes * (scanned * dim * 4 / rate + 2e-5) + 5e-5
     return t_batch < t_exact
 
 

@@ -491,7 +491,7 @@ class DenseStore:
         """mode="exact": fp32 cosine scan (K1) + fp64 re-score.  Host queries -> host results
         (numpy, through the *_host C entry point: H2D + kernels + D2H + sync); CUDA tensors ->
         CUDA tensors (asynchronous on the current stream).  Returns (ids[nq,k], scores[nq,k], n[nq]).
-        shared=True: a batch of concurrent requests shares every tile read among 3 queries
+        shared=True: a batch of concurrent requests shares every tile read among 3 queries (8 for batches of >= 7)
         (``cdr_search_exact_f32_shared``: nq/3 scans of the corpus, same bits); False = one scan per query."""
         return self._search("cdr_search_exact_f32_shared" if shared else "cdr_search_exact_f32", queries, k, allow)
 

@@ -162,7 +162,8 @@ int32_t cdr_search_exact_f32_host(cdr_store *s, const float *q_host, int32_t nq,
                                   int64_t *out_id_host, int32_t *out_n_host, void *stream);
 
 /* The same lane for a BATCH of concurrent exact requests: every tile a CTA streams from HBM is scored
- * against 3 queries held in registers ("shared reads"), so nq queries cost nq/3 scans of the corpus.
+ * against several queries ("shared reads"): 3 held in registers, or -- for 7 or more queries at k <= 56 -- 8
+ * streamed from shared memory while the rows sit in registers, so nq queries cost nq/3 .. nq/8 scans of the corpus.
  * cdr_search_exact_f32 above keeps one scan per query (the single-query GEMV of the reference's
  * one-query-per-request flow); per-query arithmetic is the same, and so is every bit of the result. */
 int32_t cdr_search_exact_f32_shared(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
