@@ -423,6 +423,22 @@ def _embedding_f32(values: Sequence[float]) -> np.ndarray:
     return _query_vector(_vector_literal(values))
 
 
+def _embeddings_f32(vectors: Sequence[Sequence[float]]) -> np.ndarray:
+    """`_embedding_f32` for a batch: one conversion for all rows; a row that is not float32-representable
+    takes the literal path on its own."""
+    try:
+        a64 = np.asarray(vectors, dtype=np.float64)
+    except ValueError:                                   # ragged rows: let the per-row path report them
+        return np.stack([_embedding_f32(v) for v in vectors])
+    if a64.ndim != 2:
+        return np.stack([_embedding_f32(v) for v in vectors])
+    a32 = a64.astype(np.float32)
+    exact = (a32.astype(np.float64) == a64).all(axis=1)
+    for i in np.flatnonzero(~exact).tolist():
+        a32[i] = _query_vector(_vector_literal(vectors[i]))
+    return a32
+
+
 def _fused_path_ok(engine: DenseEngine, table: str, dense: bool) -> bool:
     """The fused C call serves a table when its dense lane is the exact fp32 scan and its tech lane
     (if any) is device resident; other configurations take the step-by-step path."""
@@ -440,14 +456,17 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
                         token_lists: Sequence[Sequence[str]], filters, call_ids,
                         bm25_rows: Sequence[Sequence[Mapping[str, Any]]],
                         dense_limit: int, tech_limit: int = DEFAULT_TECH_TOPK,
-                        rrf_k: int = DEFAULT_RRF_K, per_request_filters: bool = False) -> List[Dict[str, Any]]:
+                        rrf_k: int = DEFAULT_RRF_K, per_request_filters: bool = False,
+                        ids_only: bool = False) -> List[Dict[str, Any]]:
     """All lanes of one table + their fusion for nq requests through ONE fused C call.  q32: [nq, dim] float32
     or None (dense lane disabled); token_lists and bm25_rows: one entry per request.  The requests share
     `filters` / `call_ids`, or -- with per_request_filters -- each request brings its own (sequences of length
     nq): requests are then grouped by filter and every group runs its own filter / lane launches inside the
     same call (`cdr_hybrid_retrieve_groups_host`).  Returns, per request, {"tech": rows, "dense": rows,
     "count": COUNT(*), "ranked": [(row, lane-name set, score)]} with the rows / order the step-by-step
-    functions produce (lane rows carry the id -- and the score on the dense lane -- only)."""
+    functions produce (lane rows carry the id -- and the score on the dense lane -- only).  With `ids_only` the
+    per-row dicts are skipped: each entry is {"count", "fused": [(id, score)] in fused order} (the response without
+    a debug payload needs nothing else)."""
     store = conn.store(table)
     key = store.key_field
     nq = len(token_lists)
@@ -494,27 +513,37 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
     else:
         pos_count = [res["count"]] * nq
     n_lanes = 3 if q32 is not None else 2
+    # one bulk conversion per output array: indexing numpy scalars row by row costs more than the C call
+    fused_ids, fused_scores, fused_n = res["fused_ids"].tolist(), res["fused_scores"].tolist(), res["fused_n"].tolist()
+    if not ids_only:
+        tech_ids, tech_n, fused_mask = res["tech_ids"].tolist(), res["tech_n"].tolist(), res["fused_mask"].tolist()
+    if q32 is not None and not ids_only:
+        dense_ids, dense_scores, dense_n = res["dense_ids"].tolist(), res["dense_scores"].tolist(), res["dense_n"].tolist()
+    hit_sets = [frozenset(_LANE_NAMES[l] for l in range(n_lanes) if (m >> l) & 1) for m in range(1 << n_lanes)]
     out_pos = []
-    for qi in range(nq):
+    for qi in range(nq if not ids_only else 0):
         # the ids_only response needs ids, ranks and scores only: the SELECT-list columns (call_id, payload) are
         # looked up by retrieve_evidence for the few rows that make it into the pack, not for every lane row
-        tech_rows = [{key: i} for i in res["tech_ids"][qi, :int(res["tech_n"][qi])].tolist()]
+        tech_rows = [{key: i} for i in tech_ids[qi][:tech_n[qi]]]
         dense_rows: List[Dict[str, Any]] = []
         if q32 is not None:
-            m = int(res["dense_n"][qi])
-            dense_rows = [{key: i, "score": sc} for i, sc in zip(res["dense_ids"][qi, :m].tolist(),
-                                                                 res["dense_scores"][qi, :m].tolist())]
+            m = dense_n[qi]
+            dense_rows = [{key: i, "score": sc} for i, sc in zip(dense_ids[qi][:m], dense_scores[qi][:m])]
         items: Dict[int, Mapping[str, Any]] = {}
-        for lane in (bm25_rows[qi], tech_rows, dense_rows):
-            for row in lane:
-                items.setdefault(int(row[key]), row)
-        ranked = []
-        for i in range(int(res["fused_n"][qi])):
-            mask = int(res["fused_mask"][qi, i])
-            hit = {_LANE_NAMES[l] for l in range(n_lanes) if (mask >> l) & 1}
-            ranked.append((items[int(res["fused_ids"][qi, i])], hit, float(res["fused_scores"][qi, i])))
+        for row in bm25_rows[qi]:
+            items.setdefault(int(row[key]), row)
+        for row in tech_rows:
+            items.setdefault(row[key], row)
+        for row in dense_rows:
+            items.setdefault(row[key], row)
+        n_f = fused_n[qi]
+        ranked = [(items[i], set(hit_sets[mk]), sc)
+                  for i, mk, sc in zip(fused_ids[qi][:n_f], fused_mask[qi][:n_f], fused_scores[qi][:n_f])]
         out_pos.append({"tech": tech_rows, "dense": dense_rows, "count": pos_count[qi] if q32 is not None else 0,
                         "ranked": ranked})
+    if ids_only:
+        out_pos = [{"count": pos_count[qi] if q32 is not None else 0,
+                    "fused": list(zip(fused_ids[qi][:fused_n[qi]], fused_scores[qi][:fused_n[qi]]))} for qi in range(nq)]
     out: List[Dict[str, Any]] = [None] * nq      # back to request order
     for pos, i in enumerate(order):
         out[i] = out_pos[pos]
@@ -559,11 +588,12 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters=None
     dense_error: Optional[str] = None
     dense_model_id: Optional[str] = None
     q32 = None
+    lean = not debug            # no debug payload: ids and fused scores straight from the call's output arrays
     if dense_enabled:
         try:
             embedded = embed_texts([cleaned[i] for i in live])
             dense_model_id = embedded.model
-            q32 = np.stack([_embedding_f32(v) for v in embedded.vectors])
+            q32 = _embeddings_f32(embedded.vectors)
         except EmbeddingClientError as exc:
             dense_enabled = False
             dense_error = str(exc)
@@ -581,7 +611,8 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters=None
         try:
             for t in tables:
                 per_table[t] = _hybrid_table_batch(conn, t, q32 if dense_enabled else None, token_lists, live_filters,
-                                                   call_ids, bm25[t], limits[t], per_request_filters=per_request)
+                                                   call_ids, bm25[t], limits[t], per_request_filters=per_request,
+                                                   ids_only=lean)
         except DenseEngineError as exc:       # fail open to lexical-only, like EmbeddingClientError
             if not dense_enabled:
                 raise
@@ -589,9 +620,22 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters=None
             dense_error = str(exc)
             for t in tables:
                 per_table[t] = _hybrid_table_batch(conn, t, None, token_lists, live_filters, call_ids, bm25[t], limits[t],
-                                                   per_request_filters=per_request)
+                                                   per_request_filters=per_request, ids_only=lean)
     empty = {"tech": [], "dense": [], "count": 0, "ranked": []}
     responses: List[Dict[str, Any]] = [{"retrieved_ids": []} for _ in range(n)]
+    if lean:
+        kinds = ("artifact_chunk", "chunk")
+        for j, i in enumerate(live):
+            combined: List[Tuple[float, int, int]] = []
+            for kind, t, key, extra in ((0, "artifact_chunks", "artifact_chunk_id", bm25_artifacts[i]),
+                                        (1, "chunks", "chunk_id", bm25_chunks[i])):
+                if t in per_table:
+                    combined += [(-sc, kind, item) for item, sc in per_table[t][j]["fused"]]
+                else:                                    # table not resident: its BM25 lane alone
+                    combined += [(-sc, kind, row[key]) for row, _l, sc in _rrf_merge({"bm25": extra, "tech_tokens": []}, key)]
+            combined.sort()
+            responses[i] = {"retrieved_ids": [f"{kinds[kind]}:{item}" for _, kind, item in combined]}
+        return responses
     for j, i in enumerate(live):
         ch = per_table["chunks"][j] if "chunks" in per_table else empty
         ar = per_table["artifact_chunks"][j] if "artifact_chunks" in per_table else empty
@@ -825,14 +869,12 @@ def _ids_response(chunk_ranked, artifact_ranked, bm25_chunks, bm25_artifacts, te
                   dense_chunks, dense_artifacts, dense_enabled, dense_model_id, dense_error, modes, candidates,
                   debug: bool) -> Dict[str, Any]:
     """ids_only combine (app/retrieve.py:552-573) + the debug payload."""
-    combined: List[Tuple[str, int, float]] = []
-    for row, _lanes, score in artifact_ranked:
-        combined.append(("artifact_chunk", row["artifact_chunk_id"], score))
-    for row, _lanes, score in chunk_ranked:
-        combined.append(("chunk", row["chunk_id"], score))
-    kind_order = {"artifact_chunk": 0, "chunk": 1}
-    combined.sort(key=lambda item: (-item[2], kind_order[item[0]], item[1]))
-    response: Dict[str, Any] = {"retrieved_ids": [f"{kind}:{item_id}" for kind, item_id, _ in combined]}
+    # sort key (-score, kind order {artifact_chunk: 0, chunk: 1}, id) carried as the tuple itself
+    combined = [(-score, 0, row["artifact_chunk_id"]) for row, _lanes, score in artifact_ranked]
+    combined += [(-score, 1, row["chunk_id"]) for row, _lanes, score in chunk_ranked]
+    combined.sort()
+    kinds = ("artifact_chunk", "chunk")
+    response: Dict[str, Any] = {"retrieved_ids": [f"{kinds[kind]}:{item_id}" for _, kind, item_id in combined]}
     if debug:
         chunk_dbg = {"bm25": _build_debug_lane(list(bm25_chunks), "chunk_id"),
                      "tech_tokens": _build_debug_lane(tech_chunks, "chunk_id")}

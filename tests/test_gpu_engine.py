@@ -626,6 +626,8 @@ def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
             for i, q in enumerate(qlist):
                 one = retrieve.retrieve_ids(eng, q, filters, bm25_chunks=b_lists[i], bm25_artifacts=a_lists[i], debug=True)
                 assert many[i] == one, (i, q, filters)
+            lean = retrieve.retrieve_ids_batch(eng, qlist, filters, bm25_chunks=b_lists, bm25_artifacts=a_lists)
+            assert lean == [{"retrieved_ids": r["retrieved_ids"]} for r in many]     # no debug: the dict-free path
     finally:
         embeddings.set_embedder(None)
         monkeypatch.setattr(settings, "embeddings_base_url", "")
@@ -639,6 +641,8 @@ def test_fused_hybrid_call_equals_stepwise_path(hybrid_engine, monkeypatch):
         for i, (q, f) in enumerate(zip(q_list, f_list)):
             one = retrieve.retrieve_ids(eng, q, f, bm25_chunks=[bm25, [], [], bm25[:1], [], [], []][i], debug=True)
             assert many[i] == one, (i, q, f)
+        lean = retrieve.retrieve_ids_batch(eng, q_list, f_list, bm25_chunks=[bm25, [], [], bm25[:1], [], [], []])
+        assert lean == [{"retrieved_ids": r["retrieved_ids"]} for r in many]
         import threading
         batcher = retrieve.RequestBatcher(eng, max_batch=16, max_wait_s=2e-3)
         got, errs = {}, []

@@ -486,6 +486,12 @@ def test_embedding_f32_equals_the_literal_round_trip():
         assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), via_text.view(np.uint32)) or \
             (np.isnan(got).any() and np.array_equal(np.isnan(got), np.isnan(via_text)))
     assert np.array_equal(retrieve._embedding_f32(f32.astype(np.float64).tolist()), f32)
+    # batch form: row by row the same bits, mixed exact / inexact / NaN rows
+    rows = [f32.astype(np.float64).tolist(), f64.tolist(), [float("nan")] + f64.tolist()[1:], (f32 * 3).astype(np.float64).tolist()]
+    many = retrieve._embeddings_f32(rows)
+    assert many.dtype == np.float32 and many.shape == (4, 1024)
+    for got, values in zip(many, rows):
+        assert np.array_equal(got.view(np.uint32), retrieve._embedding_f32(values).view(np.uint32))
 
 
 def test_request_batcher_queueing(monkeypatch):
