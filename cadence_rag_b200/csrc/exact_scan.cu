@@ -71,6 +71,11 @@ struct ScanParams {
 // reduction => same bits as one scan per query.
 constexpr int kSharedQPC = 3;
 constexpr int kDeepQPC = 8;
+// consumer warps / rows per warp of the deep kernel.  4 warps x 4 rows (194 registers) need 1.67 x fewer LDS wavefronts
+// per (row, query) but one warp per scheduler cannot hide the LDS latency: 8.4 ms vs 7.45 ms for 64 queries over 1 M rows
+// on the same box (profiles/r01/k1_shared_probe_deep4w.json), so the kernel keeps 8 warps x 2 rows.
+constexpr int kDeepWarps = 8;
+constexpr int kDeepRPW = 2;
 struct DeepTopK {     // per (consumer warp, query) in shared memory
     uint64_t tau;
     int count;
@@ -79,17 +84,18 @@ struct DeepTopK {     // per (consumer warp, query) in shared memory
 template <int J, int RPW, int NPL, int QPC>
 struct ScanSmem {
     static constexpr int DIM = J * 128;
-    static constexpr int TR = RPW * kConsumerWarps;
+    static constexpr int CW = QPC > kSharedQPC ? kDeepWarps : kConsumerWarps;   // consumer warps
+    static constexpr int TR = RPW * CW;
     static constexpr int KC = NPL * 32;
     static constexpr size_t kTileBytes = (size_t)TR * DIM * 4;
     static constexpr size_t kMetaBytes = (size_t)TR * 4;   // inverse norms (multiple of 16)
-    static constexpr size_t kListBytes = (size_t)kConsumerWarps * QPC * KC * 8;
+    static constexpr size_t kListBytes = (size_t)CW * QPC * KC * 8;
     static constexpr size_t kBarBytes = 3 * kMaxStages * 8;   // full + empty barriers + the tile index of each stage
     // deep shared reads (QPC > kSharedQPC): the queries, their inverse norms and the per-(warp, query) top-k
     // state live in shared memory instead of registers
     static constexpr bool kDeep = QPC > kSharedQPC;
     static constexpr size_t kQueryBytes = kDeep ? (size_t)QPC * DIM * 4 : 0;
-    static constexpr size_t kStateBytes = kDeep ? (size_t)kConsumerWarps * QPC * 16 + (size_t)QPC * 4 : 0;
+    static constexpr size_t kStateBytes = kDeep ? (size_t)CW * QPC * 16 + (size_t)QPC * 4 : 0;
     static constexpr size_t bytes(int stages)
     {
         return (size_t)stages * (kTileBytes + kMetaBytes) + kQueryBytes + kListBytes + kStateBytes + kBarBytes + 128;
@@ -103,10 +109,10 @@ struct ScanSmem {
 };
 
 template <int J, int RPW, int NPL, int QPC>
-__global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanParams p)
+__global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) exact_scan_kernel(const ScanParams p)
 {
     using L = ScanSmem<J, RPW, NPL, QPC>;
-    constexpr int DIM = L::DIM, TR = L::TR, KC = L::KC;
+    constexpr int DIM = L::DIM, TR = L::TR, KC = L::KC, CW = L::CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int S = p.n_stages;
@@ -114,8 +120,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     unsigned char *metas = tiles + (size_t)S * L::kTileBytes;
     float4 *qs = reinterpret_cast<float4 *>(metas + (size_t)S * L::kMetaBytes);           // deep: [QPC][DIM/4]
     uint64_t *lists = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(qs) + L::kQueryBytes);
-    DeepTopK *dstate = reinterpret_cast<DeepTopK *>(lists + kConsumerWarps * QPC * KC);   // deep: [warps][QPC]
-    float *qinv_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dstate) + (size_t)kConsumerWarps * QPC * 16 * (L::kDeep ? 1 : 0));
+    DeepTopK *dstate = reinterpret_cast<DeepTopK *>(lists + CW * QPC * KC);   // deep: [warps][QPC]
+    float *qinv_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dstate) + (size_t)CW * QPC * 16 * (L::kDeep ? 1 : 0));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(dstate) + L::kStateBytes);
     uint64_t *empty_bar = full_bar + kMaxStages;
     long long *stage_tile = reinterpret_cast<long long *>(empty_bar + kMaxStages);   // tile held by a stage, -1 = end
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
+            mbar_init(&empty_bar[s], CW);
         }
         fence_mbar_init();
     }
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
     // the static split (t = blockIdx.x + i*G).  A stage whose tile index is -1 ends the stream.
     const bool dynamic = p.tile_ctr != nullptr;
 
-    if (warp == kConsumerWarps && gather) {
+    if (warp == CW && gather) {
         // ------------------------------------------------------------------ producer, gather launch
         // The whole warp runs the loop: lane 0 draws tiles and arms the barrier, lanes 0..TR-1 each fetch one
         // list entry and issue that row's bulk copy, so the TR copies of a tile are issued in parallel.
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                 bulk_g2s(tiles + (size_t)s * L::kTileBytes + (size_t)lane * DIM * 4, p.rows + (size_t)my_row * DIM,
                          (uint32_t)(DIM * 4), &full_bar[s]);
         }
-    } else if (warp == kConsumerWarps) {
+    } else if (warp == CW) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
             int64_t next_dyn = -1;
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
             // ---- deep shared reads: rows in registers, queries + top-k state in shared memory
             constexpr int GQ = 8 / RPW;                       // queries per joint reduction (8 values)
             static_assert(QPC % GQ == 0, "deep shared reads: QPC must be a multiple of 8 / RPW");
-            for (int u = warp; u < QPC; u += kConsumerWarps) {
+            for (int u = warp; u < QPC; u += CW) {
                 float qn = 0.f;
                 const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(q0 + (u < nqv ? u : 0)) * DIM);
 #pragma unroll
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                 my_state[lane].count = 0;
                 my_state[lane].min_pos = 0;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
 
             for (int64_t i = 0;; ++i) {
                 const int s = (int)(i % S);
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
                     if (vr == r) { s_inv_n = inv_n[r]; s_row = gather ? (int64_t)g_row[r] : row0 + r; }
                 const bool s_ok = (s_row < p.n_rows) && ((allow_bits >> vr) & 1u);
                 const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-#pragma unroll 1
+#pragma unroll
                 for (int g = 0; g < QPC / GQ; ++g) {
                     float a8[8];
 #pragma unroll
@@ -532,12 +538,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) exact_scan_kernel(const ScanP
 #pragma unroll
             for (int i = 0; i < NPL; ++i) mine[i * 32 + lane] = k[i];
 #pragma unroll
-            for (int step = 1; step < kConsumerWarps; step <<= 1) {
-                asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+            for (int step = 1; step < CW; step <<= 1) {
+                asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
                 if ((warp & (2 * step - 1)) == 0) {
                     warp_merge_topk<NPL>(k, lists + ((warp + step) * QPC + u) * KC, lane);
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
                 if ((warp & (2 * step - 1)) == 0) {
 #pragma unroll
                     for (int i = 0; i < NPL; ++i) mine[i * 32 + lane] = k[i];
@@ -1115,12 +1121,12 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
         gp.row_list = ws.row_list;
         gp.list_count = reinterpret_cast<unsigned int *>(ws.row_list) + list_cap;
         gp.allow = nullptr;
-        exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(g_gather, n_groups), kScanThreads, smem, st>>>(gp);
+        exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(g_gather, n_groups), (L::CW + 1) * 32, smem, st>>>(gp);
         CDR_LAUNCH_CHECK();
         sp.list_count = gp.list_count;
         sp.list_offset = g_gather;
     }
-    exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(grid, n_groups), kScanThreads, smem, st>>>(sp);
+    exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(grid, n_groups), (L::CW + 1) * 32, smem, st>>>(sp);
     CDR_LAUNCH_CHECK();
     cdr_prof_mark_end(0, st);
 
@@ -1156,7 +1162,7 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     const bool deep = share && NPL == 2 && nq > 2 * kSharedQPC && k1_deep;
 #define CDR_SCAN_CASE(J_, RPW_)                                                                              \
     if constexpr (NPL == 2) {                                                                                \
-        if (deep) return launch_scan_t<J_, RPW_, NPL, kDeepQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
+        if (deep) return launch_scan_t<J_, kDeepRPW, NPL, kDeepQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
     }                                                                                                        \
     if (share) return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
     return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st)
