@@ -838,7 +838,7 @@ def main():
         launches_total, k_ms_max = int(launches), k_ms.value
     value = args.steps * Q / (ms / 1e3)
 
-    # informational: the same steps with shared reads (3 queries -- 8 for batches of 7 or more -- score every
+    # informational: the same steps with shared reads (groups of 16 queries -- 3 for short tails -- score every
     # streamed tile; identical results)
     shared = None
     if Q >= 2:
@@ -856,7 +856,7 @@ def main():
             dist.all_reduce(sms, op=dist.ReduceOp.MAX)
         assert torch.equal(got[0], last[0]) and torch.equal(got[1].view(torch.int64), last[1].view(torch.int64)), \
             "shared-read scan differs from one-scan-per-query"
-        shared = {"queries_per_pass": 8 if (Q >= 7 and TOPK <= 56) else 3, "value": args.steps * Q / (float(sms[0]) / 1e3), "unit": UNIT,
+        shared = {"queries_per_pass": 16 if (Q >= 10 and TOPK <= 56) else 3, "value": args.steps * Q / (float(sms[0]) / 1e3), "unit": UNIT,
                   "ms_per_step": float(sms[0]) / args.steps,
                   "note": "cdr_search_exact_f32_shared: not the contract line (configs[1] is one scan per query)"}
 

@@ -28,7 +28,6 @@
 namespace {
 
 constexpr int kConsumerWarps = 8;
-constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
 constexpr int kMaxStages = 6;
 
 struct ScanParams {
@@ -70,12 +69,14 @@ struct ScanParams {
 // enough, because a stage is released as soon as its rows are in registers.  Same lanes, same FMA order, same
 // reduction => same bits as one scan per query.
 constexpr int kSharedQPC = 3;
-constexpr int kDeepQPC = 8;
-// consumer warps / rows per warp of the deep kernel.  4 warps x 4 rows (194 registers) need 1.67 x fewer LDS wavefronts
-// per (row, query) but one warp per scheduler cannot hide the LDS latency: 8.4 ms vs 7.45 ms for 64 queries over 1 M rows
-// on the same box (profiles/r01/k1_shared_probe_deep4w.json), so the kernel keeps 8 warps x 2 rows.
+constexpr int kDeepQPC = 16;
+// Shape of the deep kernel: 8 consumer warps as 4 row groups x kDeepQSplit query halves; a warp owns 4 rows of the
+// 16-row tile and 8 of the CTA's 16 queries.  (Rows resident in registers with the queries streamed past them -- 8 warps
+// x 2 rows, or 4 warps x 4 rows -- cost 20 / 12 LDS wavefronts per (row, query) but left the LSU pipe 71 % busy and the
+// 4-warp form latency-bound: 7.4 / 8.4 ms per 64 queries over 1 M rows, profiles/r01/k1_shared_probe_deep4w.json.)
 constexpr int kDeepWarps = 8;
-constexpr int kDeepRPW = 2;
+constexpr int kDeepRPW = 4;
+constexpr int kDeepQSplit = 2;
 struct DeepTopK {     // per (consumer warp, query) in shared memory
     uint64_t tau;
     int count;
@@ -84,18 +85,19 @@ struct DeepTopK {     // per (consumer warp, query) in shared memory
 template <int J, int RPW, int NPL, int QPC>
 struct ScanSmem {
     static constexpr int DIM = J * 128;
-    static constexpr int CW = QPC > kSharedQPC ? kDeepWarps : kConsumerWarps;   // consumer warps
-    static constexpr int TR = RPW * CW;
+    static constexpr bool kDeep = QPC > kSharedQPC;
+    static constexpr int CW = kDeep ? kDeepWarps : kConsumerWarps;              // consumer warps
+    static constexpr int QW = kDeep ? QPC / kDeepQSplit : QPC;                   // queries a warp keeps top-k lists for
+    static constexpr int TR = kDeep ? RPW * CW / kDeepQSplit : RPW * CW;
     static constexpr int KC = NPL * 32;
     static constexpr size_t kTileBytes = (size_t)TR * DIM * 4;
     static constexpr size_t kMetaBytes = (size_t)TR * 4;   // inverse norms (multiple of 16)
-    static constexpr size_t kListBytes = (size_t)CW * QPC * KC * 8;
+    static constexpr size_t kListBytes = (size_t)CW * QW * KC * 8;
     static constexpr size_t kBarBytes = 3 * kMaxStages * 8;   // full + empty barriers + the tile index of each stage
     // deep shared reads (QPC > kSharedQPC): the queries, their inverse norms and the per-(warp, query) top-k
     // state live in shared memory instead of registers
-    static constexpr bool kDeep = QPC > kSharedQPC;
     static constexpr size_t kQueryBytes = kDeep ? (size_t)QPC * DIM * 4 : 0;
-    static constexpr size_t kStateBytes = kDeep ? (size_t)CW * QPC * 16 + (size_t)QPC * 4 : 0;
+    static constexpr size_t kStateBytes = kDeep ? (size_t)CW * QW * 16 + (size_t)QPC * 4 : 0;
     static constexpr size_t bytes(int stages)
     {
         return (size_t)stages * (kTileBytes + kMetaBytes) + kQueryBytes + kListBytes + kStateBytes + kBarBytes + 128;
@@ -120,8 +122,8 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
     unsigned char *metas = tiles + (size_t)S * L::kTileBytes;
     float4 *qs = reinterpret_cast<float4 *>(metas + (size_t)S * L::kMetaBytes);           // deep: [QPC][DIM/4]
     uint64_t *lists = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(qs) + L::kQueryBytes);
-    DeepTopK *dstate = reinterpret_cast<DeepTopK *>(lists + CW * QPC * KC);   // deep: [warps][QPC]
-    float *qinv_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dstate) + (size_t)CW * QPC * 16 * (L::kDeep ? 1 : 0));
+    DeepTopK *dstate = reinterpret_cast<DeepTopK *>(lists + CW * L::QW * KC);   // deep: [warps][QW]
+    float *qinv_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(dstate) + (size_t)CW * L::QW * 16 * (L::kDeep ? 1 : 0));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(dstate) + L::kStateBytes);
     uint64_t *empty_bar = full_bar + kMaxStages;
     long long *stage_tile = reinterpret_cast<long long *>(empty_bar + kMaxStages);   // tile held by a stage, -1 = end
@@ -235,9 +237,12 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
     } else {
         // ------------------------------------------------------------------ consumers
         if constexpr (L::kDeep) {
-            // ---- deep shared reads: rows in registers, queries + top-k state in shared memory
+            // ---- deep shared reads: a 4-row x 8-query register tile per warp, rows and queries streamed from shared memory
+            constexpr int QW = L::QW;                         // queries of this warp (8)
             constexpr int GQ = 8 / RPW;                       // queries per joint reduction (8 values)
-            static_assert(QPC % GQ == 0, "deep shared reads: QPC must be a multiple of 8 / RPW");
+            static_assert(RPW * GQ == 8 && QW % GQ == 0, "deep shared reads: RPW must divide 8");
+            const int rg = warp / kDeepQSplit;                // row group: rows rg*RPW .. of the tile
+            const int qh = warp % kDeepQSplit;                // query half: queries qh*QW .. of the CTA's group
             for (int u = warp; u < QPC; u += CW) {
                 float qn = 0.f;
                 const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(q0 + (u < nqv ? u : 0)) * DIM);
@@ -253,15 +258,17 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                 qn = warp_sum_f32(qn);
                 if (lane == 0) qinv_s[u] = __fdiv_rn(1.0f, __fsqrt_rn(qn));
             }
-            DeepTopK *my_state = dstate + warp * QPC;
-            uint64_t *my_lists = lists + (size_t)warp * QPC * KC;
-            for (int i = lane; i < QPC * KC; i += 32) my_lists[i] = CDR_EMPTY_KEY;
-            if (lane < QPC) {
+            DeepTopK *my_state = dstate + warp * QW;
+            uint64_t *my_lists = lists + (size_t)warp * QW * KC;
+            for (int i = lane; i < QW * KC; i += 32) my_lists[i] = CDR_EMPTY_KEY;
+            if (lane < QW) {
                 my_state[lane].tau = 0;
                 my_state[lane].count = 0;
                 my_state[lane].min_pos = 0;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
+            const float4 *my_q = qs + (size_t)(qh * QW) * (DIM / 4) + lane;
+            const float *my_qinv = qinv_s + qh * QW;
 
             for (int64_t i = 0;; ++i) {
                 const int s = (int)(i % S);
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                 mbar_wait(&full_bar[s], ph);
                 const int64_t tile = stage_tile[s];
                 if (tile < 0) break;
-                const int64_t row0 = tile * TR + warp * RPW;
+                const int64_t row0 = tile * TR + rg * RPW;    // a multiple of RPW: the rows share one bitmap word
                 uint32_t allow_bits = 0xFFFFFFFFu;
                 uint32_t g_row[RPW];
                 float g_inv[RPW];
@@ -286,20 +293,39 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                     allow_bits = w >> (row0 & 31);
                 }
                 const float4 *tv = reinterpret_cast<const float4 *>(tiles + (size_t)s * L::kTileBytes) +
-                                   (size_t)(warp * RPW) * (DIM / 4);
-                const float *mv = reinterpret_cast<const float *>(metas + (size_t)s * L::kMetaBytes) + warp * RPW;
-                float4 rv[RPW][J];
+                                   (size_t)(rg * RPW) * (DIM / 4) + lane;
+                const float *mv = reinterpret_cast<const float *>(metas + (size_t)s * L::kMetaBytes) + rg * RPW;
+                float acc[QW][RPW][2];
 #pragma unroll
-                for (int r = 0; r < RPW; ++r)
+                for (int u = 0; u < QW; ++u)
 #pragma unroll
-                    for (int j = 0; j < J; ++j) rv[r][j] = tv[r * (DIM / 4) + j * 32 + lane];
+                    for (int r = 0; r < RPW; ++r) acc[u][r][0] = acc[u][r][1] = 0.f;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    float4 rv[RPW];
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) rv[r] = tv[r * (DIM / 4) + j * 32];
+#pragma unroll
+                    for (int u = 0; u < QW; ++u) {
+                        const float4 qv = my_q[u * (DIM / 4) + j * 32];   // RPW + QW LDS.128 feed RPW x QW x 4 FMAs
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) {
+                            float a = acc[u][r][j & 1];
+                            a = fmaf(rv[r].x, qv.x, a);
+                            a = fmaf(rv[r].y, qv.y, a);
+                            a = fmaf(rv[r].z, qv.z, a);
+                            a = fmaf(rv[r].w, qv.w, a);
+                            acc[u][r][j & 1] = a;
+                        }
+                    }
+                }
                 float inv_n[RPW];
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) inv_n[r] = gather ? g_inv[r] : mv[r];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);        // the rows are in registers: refill the stage
+                if (lane == 0) mbar_arrive(&empty_bar[s]);        // all reads of the stage are done
 
-                const int v = (lane >> 2) & 7;                    // the value this 4-lane group owns after the reduction
+                const int v = (lane >> 2) & 7;                    // the value this 4-lane group owns after a reduction
                 const int vu = v / RPW, vr = v % RPW;
                 float s_inv_n = inv_n[0];
                 int64_t s_row = gather ? (int64_t)g_row[0] : row0;
@@ -309,30 +335,10 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                 const bool s_ok = (s_row < p.n_rows) && ((allow_bits >> vr) & 1u);
                 const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
 #pragma unroll
-                for (int g = 0; g < QPC / GQ; ++g) {
+                for (int g = 0; g < QW / GQ; ++g) {
                     float a8[8];
 #pragma unroll
-                    for (int uu = 0; uu < GQ; ++uu) {
-                        const float4 *qp = qs + (g * GQ + uu) * (DIM / 4) + lane;
-                        float acc[RPW][2];
-#pragma unroll
-                        for (int r = 0; r < RPW; ++r) acc[r][0] = acc[r][1] = 0.f;
-#pragma unroll
-                        for (int j = 0; j < J; ++j) {
-                            const float4 qv = qp[j * 32];                 // one LDS.128 feeds RPW rows
-#pragma unroll
-                            for (int r = 0; r < RPW; ++r) {
-                                float a = acc[r][j & 1];
-                                a = fmaf(rv[r][j].x, qv.x, a);
-                                a = fmaf(rv[r][j].y, qv.y, a);
-                                a = fmaf(rv[r][j].z, qv.z, a);
-                                a = fmaf(rv[r][j].w, qv.w, a);
-                                acc[r][j & 1] = a;
-                            }
-                        }
-#pragma unroll
-                        for (int r = 0; r < RPW; ++r) a8[uu * RPW + r] = acc[r][0] + acc[r][1];
-                    }
+                    for (int x = 0; x < 8; ++x) a8[x] = acc[g * GQ + x / RPW][x % RPW][0] + acc[g * GQ + x / RPW][x % RPW][1];
                     // the transposed reduction of the QPC <= 3 path (same additions per lane as the butterfly)
                     float h4[4], h2[2];
 #pragma unroll
@@ -345,7 +351,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                     dot += __shfl_xor_sync(0xffffffffu, dot, 2);
                     dot += __shfl_xor_sync(0xffffffffu, dot, 1);
                     const int u_mine = g * GQ + vu;
-                    const uint64_t key = cdr_pack_key(dot * s_inv_n * qinv_s[u_mine], (uint32_t)s_row);
+                    const uint64_t key = cdr_pack_key(dot * s_inv_n * my_qinv[u_mine], (uint32_t)s_row);
                     unsigned pend = __ballot_sync(0xffffffffu, s_ok && key > my_state[u_mine].tau) & 0x11111111u;
                     while (pend) {                                // rare; warp-uniform
                         const int src = __ffs(pend) - 1;
@@ -380,6 +386,36 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                             __syncwarp();
                         }
                     }
+                }
+            }
+
+            // ---- per query of this warp: sort, then merge across the row groups of the same query half
+#pragma unroll 1
+            for (int u = 0; u < QW; ++u) {
+                uint64_t *mine = my_lists + (size_t)u * KC;
+                uint64_t k[NPL];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) k[i] = mine[i * 32 + lane];
+                warp_bitonic_sort_desc<NPL>(k, lane);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) mine[i * 32 + lane] = k[i];
+#pragma unroll
+                for (int step = 1; step < CW / kDeepQSplit; step <<= 1) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
+                    if ((rg & (2 * step - 1)) == 0)
+                        warp_merge_topk<NPL>(k, lists + ((size_t)(warp + step * kDeepQSplit) * QW + u) * KC, lane);
+                    asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
+                    if ((rg & (2 * step - 1)) == 0) {
+#pragma unroll
+                        for (int i = 0; i < NPL; ++i) mine[i * 32 + lane] = k[i];
+                    }
+                }
+                const int uq = qh * QW + u;
+                if (rg == 0 && uq < nqv) {
+                    uint64_t *out = p.cta_keys + ((size_t)(q0 + uq) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
+#pragma unroll
+                    for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
                 }
             }
         } else {
@@ -528,7 +564,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
 
         // ---- per query: per-warp sort, then 3-level pairwise merge through shared memory
 #pragma unroll 1
-        for (int u = 0; u < QPC; ++u) {
+        for (int u = 0; u < (L::kDeep ? 0 : QPC); ++u) {
             uint64_t *mine = lists + (warp * QPC + u) * KC;
             uint64_t k[NPL];
             __syncwarp();
@@ -1149,22 +1185,20 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     return launch_finalize(fp, KC, nq, st);
 }
 
+enum ScanMode { kScanSingle = 0, kScanShared = 1, kScanDeep = 2 };
+
 template <int NPL>
 int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                     const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                    int32_t *out_n, cudaStream_t st, bool share)
+                    int32_t *out_n, cudaStream_t st, ScanMode mode)
 {
-    // deep shared reads: batches of more than 2 x kSharedQPC requests with the narrow candidate lists (k <= 56);
-    // CADENCE_K1_DEEP=0 keeps the 3-queries-in-registers kernel (A/B aid)
-    static const bool k1_deep = [] { const char *e = getenv("CADENCE_K1_DEEP"); return !(e && e[0] == '0'); }();
-    // (measured at 1 M rows: 4-6 queries 1.17 ms as two register groups on half of the SMs each vs 1.36 ms as one
-    //  deep group; 8 queries 1.51 vs 1.40 ms; 64 queries 9.5 vs 7.5 ms -- profiles/r01/k1_shared_probe_*.json)
-    const bool deep = share && NPL == 2 && nq > 2 * kSharedQPC && k1_deep;
 #define CDR_SCAN_CASE(J_, RPW_)                                                                              \
     if constexpr (NPL == 2) {                                                                                \
-        if (deep) return launch_scan_t<J_, kDeepRPW, NPL, kDeepQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
+        if (mode == kScanDeep)                                                                               \
+            return launch_scan_t<J_, kDeepRPW, NPL, kDeepQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
     }                                                                                                        \
-    if (share) return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
+    if (mode != kScanSingle)                                                                                 \
+        return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
     return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st)
     switch (s->dim) {
     case 256:  CDR_SCAN_CASE(2, 2);
@@ -1184,14 +1218,31 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
 }  // namespace
 
 // Chooses the candidate-list width: KC = 64 serves k <= 56, KC = 256 serves k <= 248
-// (KC - k >= 8 spare slots absorb fp32-vs-fp64 rank swaps at the boundary).
+// (KC - k >= 8 spare slots absorb fp32-vs-fp64 rank swaps at the boundary) -- and, for shared reads, the kernel:
+// whole groups of kDeepQPC = 16 queries take the deep kernel (k <= 56, dim <= 1024), a tail of >= 10 queries is
+// padded into one more deep group, a shorter tail (and batches of <= 9) runs as groups of kSharedQPC = 3 in a second
+// launch.  Measured at 1 M rows (profiles/r01/k1_shared_probe_*.json): a deep group costs 1.6-2.1 ms whatever its
+// fill, three queries in registers 0.63 ms, so 17 queries are 2.05 + 0.57 ms instead of 4.3 ms as two deep groups.
+// CADENCE_K1_DEEP=0 keeps the 3-queries-in-registers kernel for every batch size (A/B aid).
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                           const uint32_t *allow, int k, double *out_score, int64_t *out_id,
                           int32_t *out_n, cudaStream_t st, bool share_reads)
 {
     const bool share = share_reads && nq >= 2;
-    if (k <= 56) return launch_scan_dim<2>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share);
-    return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share);
+    if (k > 56) return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share ? kScanShared : kScanSingle);
+    static const bool k1_deep = [] { const char *e = getenv("CADENCE_K1_DEEP"); return !(e && e[0] == '0'); }();
+    int n_deep = 0;
+    if (share && k1_deep && s->dim <= 1024) {
+        n_deep = nq / kDeepQPC * kDeepQPC;
+        if (nq - n_deep >= 10) n_deep = nq;
+    }
+    if (n_deep > 0) {
+        const int rc = launch_scan_dim<2>(s, ws, q_dev, n_deep, allow, k, out_score, out_id, out_n, st, kScanDeep);
+        if (rc != CDR_OK || n_deep == nq) return rc;
+    }
+    const int rest = nq - n_deep;
+    return launch_scan_dim<2>(s, ws, q_dev + (size_t)n_deep * s->dim, rest, allow, k, out_score + (size_t)n_deep * k,
+                              out_id + (size_t)n_deep * k, out_n + n_deep, st, share && rest >= 2 ? kScanShared : kScanSingle);
 }
 
 // Used by the batched bf16 lane (gemm_topk.cu): select the top-kc of one unsorted candidate

@@ -217,16 +217,16 @@ def test_exact_scan_finalize_variants_agree(corpus_100k, k):
 
 @pytest.mark.parametrize("k", [50, 200])
 def test_exact_scan_shared_reads_same_bits(corpus_100k, k):
-    """cdr_search_exact_f32_shared == one scan per query, bit for bit.  2-3 queries (and k > 56) take the kernel
-    that keeps 3 queries in registers, larger batches at k <= 56 the deep kernel (rows in registers, 8 queries
-    streamed from shared memory): ragged group tails, host and device entry points, filters on both sides of the
-    gather boundary, and the oracle."""
+    """cdr_search_exact_f32_shared == one scan per query, bit for bit.  Whole groups of 16 queries (and tails of
+    >= 10) at k <= 56 take the deep kernel (4-row x 8-query register tiles fed from shared memory), shorter tails,
+    small batches and k > 56 the kernel that keeps 3 queries in registers: every split of a batch between the two,
+    host and device entry points, filters on both sides of the gather boundary, and the oracle."""
     s, x = corpus_100k
     qs = orc.synth_rows(SYNTH_QUERY_SEED, 700, 33)
     wide, _ = s.filter_bitmap(call_slots=list(range(0, 500, 3)))
     narrow, _ = s.filter_bitmap(call_slots=[3, 44, 45])
     for al in (None, wide, narrow):
-        for nq in (2, 4, 5, 7, 8, 9, 33):
+        for nq in (2, 5, 9, 16, 17, 26, 33):
             a = s.search_exact(qs[:nq], k, al)
             b = s.search_exact(qs[:nq], k, al, shared=True)
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
@@ -289,10 +289,10 @@ def test_exact_scan_other_dims(dim, monkeypatch):
     ids, sc, cnt = s.search_exact(qs, 50)
     for i in range(2):
         assert_matches_oracles(ids[i], sc[i], cnt[i], qs[i], x, 50)
-    # shared reads at this width: 3 queries in registers (2-3 queries) / 8 queries from shared memory (more)
-    q11 = orc.synth_rows(SYNTH_QUERY_SEED, 40, 11, dim)
+    # shared reads at this width: 3 queries in registers / the deep kernel (groups of 16, tails of >= 10)
+    q11 = orc.synth_rows(SYNTH_QUERY_SEED, 40, 19, dim)
     a = s.search_exact(q11, 50)
-    for nq in (3, 11):
+    for nq in (3, 11, 19):
         b = s.search_exact(q11[:nq], 50, shared=True)
         assert np.array_equal(a[0][:nq], b[0]) and np.array_equal(a[1][:nq].view(np.uint64), b[1].view(np.uint64))
     s.close()
