@@ -259,7 +259,7 @@ def run_reference(args):
             "config": workload_config(args, 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -435,7 +435,7 @@ def run_batch_bf16(args):
             # the reference's two CPU paths for this config, timed on this box's host cores in the same run
             line["cpu_baseline"] = cpu_baseline(rows, args.cpu_sample_rows, args.cpu_sample_queries, 0)
             line["cpu_baseline_hnsw"] = cpu_baseline_hnsw(args.hnsw_rows, 0)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
     searcher.close()
@@ -631,7 +631,7 @@ def run_hybrid(args):
                                    "K1 + K5, one sync); batched_64 = 64 requests per fused call", "rows": rows, "k": TOPK},
             "hybrid": out, "fused_ranks_bit_exact_queries": 8,
             "c1_exact_scan_2000_rows": {"gpu_device_ms": gpu_ms, "gpu_host_buffers_ms": host_ms, "cpu_ms": cpu}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     embeddings.set_embedder(None)
     store.close(); small.close()
     return 0
@@ -734,13 +734,36 @@ def run_ingest(args):
             "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"ingest of {rows} x {DIM} fp32 host rows + backfill / growth / snapshot / tech index / hierarchical request"},
             "ingest": out}
-    print(json.dumps(line), flush=True)
+    emit(line)
     dev_index.close(); store.close(); arts.close()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries write to fd 1 behind Python's back (NCCL prints its version banner there on the first
+    communicator): point fd 1 at stderr for the run, so that stdout carries the JSON line and nothing else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    """The run's ONE JSON line, on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "batch_bf16":
@@ -930,7 +953,7 @@ def main():
             line["cpu_baseline"]["single_thread_value"] = one["value"]
             # the reference's other dense path (mode "ann": HNSW, ef_search = 80), restated, in the same run
             line["cpu_baseline_hnsw"] = cpu_baseline_hnsw(args.hnsw_rows, 0, target_seconds=5.0)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
     searcher.close()
