@@ -775,6 +775,12 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
     query = query.strip()
     if not query:
         return {"retrieved_ids": []}
+    if not debug:
+        # without a debug payload the response is built straight from the fused call's output arrays
+        resident = [t for t in ("chunks", "artifact_chunks") if t in engine.stores]
+        if resident and all(_fused_path_ok(engine, t, embeddings_enabled()) for t in resident):
+            return retrieve_ids_batch(engine, [query], filters, bm25_chunks=[list(bm25_chunks)],
+                                      bm25_artifacts=[list(bm25_artifacts)])[0]
     tech_tokens = extract_tech_tokens(query)
     dense_enabled = embeddings_enabled()
     dense_error: Optional[str] = None

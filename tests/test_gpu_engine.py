@@ -1103,7 +1103,7 @@ def test_eval_replay_scores_the_engine_like_run_eval(hybrid_engine, monkeypatch,
         out_path = str(tmp_path / "results.jsonl")
         results = E.replay(eng, gold_rows, batch=32, out_path=out_path)
         for row, got in zip(gold_rows, results):
-            want = retrieve.retrieve_ids(eng, row["query"], E._filters_of(row))
+            want = retrieve.retrieve_ids(eng, row["query"], E._filters_of(row), debug=True)     # the row-dict path
             assert got == {"query_id": row["query_id"], "retrieved_ids": want["retrieved_ids"]}
         metrics = E.evaluate(eng, gold_rows, ks=[1, 5], batch=64)
     finally:
