@@ -462,7 +462,7 @@ def run_hybrid(args):
     from oracle import ports
     rows = args.rows
     torch.cuda.set_device(0)
-    store = DenseStore("chunks", rows, dim=DIM, device=0, fp32=True, bf16=False)
+    store = DenseStore("chunks", rows, dim=DIM, device=0, fp32=True, bf16=True)
     store.append_synthetic(rows)
     store.finalize()
     rng = np.random.default_rng(SYNTH_CORPUS_SEED)
@@ -533,6 +533,22 @@ def run_hybrid(args):
                                   filter_spec=spec)
         dt = time.perf_counter() - t0
         out[name]["batched_64_queries_per_s"] = reps * B / dt
+        if f is None:
+            # the same 64 unscoped requests (planner mode "ann") with the group's dense lane on the bf16 tensor cores
+            ann = dict(spec, dense_lane=_ffi.CDR_DENSE_LANE_BATCH_BF16)
+            exact_ids = store.hybrid_retrieve(qv[:B], TOPK, tech_index=dev_index, token_ids=tok[:B], n_tokens=nt[:B], filter_spec=spec)
+            for b in range(2):
+                got = store.hybrid_retrieve(qv[:B], TOPK, tech_index=dev_index, token_ids=tok[:B], n_tokens=nt[:B], filter_spec=ann)
+            same = float(np.mean([len(set(got["dense_ids"][i].tolist()) & set(exact_ids["dense_ids"][i].tolist())) / TOPK for i in range(B)]))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for r in range(reps):
+                o = (r % 4) * B
+                store.hybrid_retrieve(qv[o:o + B], TOPK, tech_index=dev_index, token_ids=tok[o:o + B], n_tokens=nt[o:o + B],
+                                      filter_spec=ann)
+            dt = time.perf_counter() - t0
+            out[name]["batched_64_ann_lane_queries_per_s"] = reps * B / dt
+            out[name]["batched_64_ann_lane_recall_at_50_vs_exact_lane"] = same
     # concurrent clients: the reference serves /retrieve from a threadpool (app/main.py:184-186); 8 client threads,
     # each on its own CUDA stream, one request at a time per thread, through retrieve_ids
     import threading

@@ -107,11 +107,15 @@ SIGNATURES = {
 }
 
 
+CDR_DENSE_LANE_EXACT_F32 = 0
+CDR_DENSE_LANE_BATCH_BF16 = 1
+
+
 class FilterSpec(ctypes.Structure):
     """struct cdr_filter_spec (include/cadence_dense.h)."""
     _fields_ = [("call_slot_bitmap_host", _vp), ("n_call_slots", _i64), ("has_date_from", _i32),
                 ("has_date_to", _i32), ("date_from_us", _i64), ("date_to_us", _i64), ("has_tag_filter", _i32),
-                ("reserved", _i32), ("tag_any", _u64)]
+                ("dense_lane", _i32), ("tag_any", _u64)]
 
 
 def lib() -> ctypes.CDLL:

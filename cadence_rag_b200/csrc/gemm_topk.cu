@@ -687,8 +687,14 @@ extern "C" int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     std::unique_lock<std::mutex> lk(s->mu);
-    ScanWorkspace &ws = s->ws[st];
+    return cdr_batch_bf16_launch(s, s->ws[st], q_dev, nq, k, allow_dev, out_score_dev, out_id_dev, out_n_dev, st);
+}
 
+// The lane itself; the caller holds the store mutex and has validated the arguments (nq <= 16384, k <= 192,
+// bf16 rows resident).  Also the dense lane of the fused hybrid call for mode "ann" (csrc/hybrid.cu).
+int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, int k, const uint32_t *allow_dev,
+                          double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev, cudaStream_t st)
+{
     const int kc = k <= 64 ? 128 : 256;          // candidates kept per query (>= k + 64)
     const int cap = 32 * kc;
     const int nq_pad = (nq + kBlockM - 1) / kBlockM * kBlockM;

@@ -118,6 +118,15 @@ extern "C" int32_t cdr_hybrid_retrieve_groups_host(
     } else {
         dense_k = 0;
     }
+    if (dense && filters != nullptr) {
+        for (int gi = 0; gi < n_groups; ++gi) {
+            if (filters[gi].dense_lane == CDR_DENSE_LANE_EXACT_F32) continue;
+            CDR_REQUIRE(filters[gi].dense_lane == CDR_DENSE_LANE_BATCH_BF16, CDR_ERR_INVALID, "%s: unknown dense_lane %d in group %d",
+                        fn, filters[gi].dense_lane, gi);
+            CDR_REQUIRE(s->emb_bf16 != nullptr && dense_k <= 192 && s->dim % 64 == 0, CDR_ERR_UNSUPPORTED,
+                        "%s: the batched bf16 lane needs bf16 rows, dense_k <= 192 and dim %% 64 == 0 (group %d)", fn, gi);
+        }
+    }
     const bool tech = tech_index != nullptr && token_ids_host != nullptr && n_tokens_host != nullptr;
     CDR_REQUIRE(tech_limit >= 1 && tech_limit <= CDR_MAX_K, CDR_ERR_UNSUPPORTED, "%s: tech_limit=%d outside [1,%d]", fn,
                 tech_limit, CDR_MAX_K);
@@ -250,9 +259,15 @@ extern "C" int32_t cdr_hybrid_retrieve_groups_host(
             allow = d_allow;
         }
         if (dense) {
-            rc = cdr_exact_scan_launch(s, ws, (const float *)(d + in_q) + (size_t)q0 * dim, gq, allow, dense_k,
-                                       (double *)(d + o_dsc) + (size_t)q0 * dense_k, (int64_t *)(d + o_did) + (size_t)q0 * dense_k,
-                                       (int32_t *)(d + o_dn) + q0, st, /*share_reads=*/true);
+            // dense_lane == CDR_DENSE_LANE_BATCH_BF16: the group's planner mode is "ann" (the reference would walk its
+            // HNSW index, app/retrieve.py:291-298) and the caller prefers the tensor-core lane for this batch
+            const bool ann = filters != nullptr && filters[gi].dense_lane == CDR_DENSE_LANE_BATCH_BF16;
+            const float *gq_dev = (const float *)(d + in_q) + (size_t)q0 * dim;
+            double *g_sc = (double *)(d + o_dsc) + (size_t)q0 * dense_k;
+            int64_t *g_id = (int64_t *)(d + o_did) + (size_t)q0 * dense_k;
+            int32_t *g_n = (int32_t *)(d + o_dn) + q0;
+            if (ann) rc = cdr_batch_bf16_launch(s, ws, gq_dev, gq, dense_k, allow, g_sc, g_id, g_n, st);
+            else rc = cdr_exact_scan_launch(s, ws, gq_dev, gq, allow, dense_k, g_sc, g_id, g_n, st, /*share_reads=*/true);
             if (rc != CDR_OK) return rc;
         }
     }

@@ -452,6 +452,20 @@ def _fused_path_ok(engine: DenseEngine, table: str, dense: bool) -> bool:
     return True
 
 
+def _group_dense_lane(store: DenseStore, filters, call_ids, n_requests: int) -> int:
+    """Dense lane of a group of requests inside the fused call.  Unscoped requests always plan "ann"
+    (app/retrieve.py:277-287: the exact mode needs scoping), where the reference walks its HNSW index; a group of at
+    least `cadence_gpu_ann_min_batch` of them goes to the batched bf16 tensor-core lane when that is the faster one.
+    Scoped groups stay on the exact scan: their mode depends on COUNT(*), which is computed inside the same call."""
+    if not store.has_bf16 or n_requests < max(2, int(settings.cadence_gpu_ann_min_batch)):
+        return _ffi.CDR_DENSE_LANE_EXACT_F32
+    if _dense_has_scoping(filters, call_ids):
+        return _ffi.CDR_DENSE_LANE_EXACT_F32
+    if _batch_lane_is_faster(store, n_requests, store.rows):
+        return _ffi.CDR_DENSE_LANE_BATCH_BF16
+    return _ffi.CDR_DENSE_LANE_EXACT_F32
+
+
 def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndarray],
                         token_lists: Sequence[Sequence[str]], filters, call_ids,
                         bm25_rows: Sequence[Sequence[Mapping[str, Any]]],
@@ -485,11 +499,15 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
         order, group_specs, group_off = [], [], [0]
         for members in groups.values():
             order += members
-            group_specs.append(specs[members[0]])
+            lane = _group_dense_lane(store, filters[members[0]], call_ids[members[0]], len(members)) if q32 is not None else 0
+            group_specs.append(dict(specs[members[0]], dense_lane=lane) if lane else specs[members[0]])
             group_off.append(len(order))
         spec = None
     else:
         spec = _filter_spec(store, filters, call_ids)
+        lane = _group_dense_lane(store, filters, call_ids, nq) if q32 is not None else 0
+        if lane:
+            spec = dict(spec, dense_lane=lane)
     token_lists = [token_lists[i] for i in order]
     bm25_rows = [bm25_rows[i] for i in order]
     if q32 is not None and per_request_filters:

@@ -413,12 +413,14 @@ class DenseStore:
                 bm[s >> 5] |= np.uint32(1 << (s & 31))
         return bm, n_slots
 
-    def filter_spec_struct(self, *, call_slots=None, date_from=None, date_to=None, tag_mask=None):
-        """(cdr_filter_spec, keep-alive) for the fused C call; None when the filter is empty."""
-        if call_slots is None and date_from is None and date_to is None and tag_mask is None:
+    def filter_spec_struct(self, *, call_slots=None, date_from=None, date_to=None, tag_mask=None, dense_lane: int = 0):
+        """(cdr_filter_spec, keep-alive) for the fused C call; None when the filter is empty and the dense lane
+        is the default exact scan.  dense_lane: _ffi.CDR_DENSE_LANE_* (the batched bf16 lane for mode "ann")."""
+        if call_slots is None and date_from is None and date_to is None and tag_mask is None and not dense_lane:
             return None, None
         bm, n_slots = self.slot_bitmap(call_slots)
         spec = _ffi.FilterSpec()
+        spec.dense_lane = int(dense_lane)
         spec.call_slot_bitmap_host = _ffi.ptr(bm)
         spec.n_call_slots = n_slots
         spec.has_date_from = 0 if date_from is None else 1

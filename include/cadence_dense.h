@@ -281,9 +281,16 @@ typedef struct cdr_filter_spec {
     int64_t date_from_us;
     int64_t date_to_us;
     int32_t has_tag_filter;
-    int32_t reserved;
+    int32_t dense_lane;                      /* CDR_DENSE_LANE_*: which kernel serves the group's dense lane */
     uint64_t tag_any;
 } cdr_filter_spec;
+
+/* Dense lane of a group.  EXACT_F32: the exact fp32 scan (shared reads inside the group) -- always right, and what
+ * mode "exact" requires.  BATCH_BF16: the tensor-core lane of cdr_search_batch_bf16 (candidates from bf16 products,
+ * re-scored in fp64 on the fp32 rows) for groups whose planner mode is "ann" (unscoped requests: the reference walks its
+ * HNSW index there, app/retrieve.py:291-298); needs CDR_STORE_BF16, dense_k <= 192. */
+#define CDR_DENSE_LANE_EXACT_F32 0
+#define CDR_DENSE_LANE_BATCH_BF16 1
 
 int32_t cdr_hybrid_retrieve_host(
     cdr_store *s, cdr_tech_index *tech_index, const cdr_filter_spec *filter, const float *q_host, int32_t nq,

@@ -1120,3 +1120,58 @@ def test_eval_replay_scores_the_engine_like_run_eval(hybrid_engine, monkeypatch,
     assert metrics["mrr"] >= 0.3 * len(rows) / judged
     gold = {r["query_id"]: r["relevant_ids"] for r in gold_rows}
     assert metrics == E.compute_metrics(gold, {r["query_id"]: r["retrieved_ids"] for r in results}, [1, 5])
+
+
+def test_fused_call_ann_groups_take_the_tensor_core_lane(monkeypatch):
+    """Unscoped requests always plan "ann" (app/retrieve.py:277-287).  A group of >= cadence_gpu_ann_min_batch of
+    them inside the fused call runs its dense lane on the bf16 tensor-core lane (cdr_filter_spec.dense_lane), scoped
+    groups of the same call stay on the exact scan; every response equals the one-request exact-lane response."""
+    from cadence_rag_b200 import _ffi
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    monkeypatch.setattr(settings, "embeddings_base_url", "http://embedder")
+    n = 300_000
+    store = DenseStore("chunks", n, dim=1024, device=0)            # fp32 + bf16
+    store.append_synthetic(n); store.finalize()
+    eng = DenseEngine(); eng.register(store)
+    embeddings.set_embedder(embeddings.SyntheticEmbedder(seed=SYNTH_QUERY_SEED, dim=1024))
+    seen = []
+    real = store.hybrid_retrieve
+
+    def spy(*a, **k):
+        seen.append((k.get("filter_spec"), k.get("filter_specs"), k.get("group_offsets")))
+        return real(*a, **k)
+    monkeypatch.setattr(store, "hybrid_retrieve", spy)
+    try:
+        texts = [f"question number {i}" for i in range(24)]
+        want = [retrieve.retrieve_ids(eng, t, None, debug=True) for t in texts]          # one at a time: exact lane
+        assert all(sp is None or not sp.get("dense_lane") for sp, _g, _o in seen)
+        seen.clear()
+        many = retrieve.retrieve_ids_batch(eng, texts, None, debug=True)
+        assert seen and seen[-1][0]["dense_lane"] == _ffi.CDR_DENSE_LANE_BATCH_BF16
+        for a, b in zip(many, want):
+            assert a["retrieved_ids"] == b["retrieved_ids"] and a["debug"]["dense"] == b["debug"]["dense"]
+            assert a["debug"]["lanes"]["chunks"]["dense"] == b["debug"]["lanes"]["chunks"]["dense"]   # ids, ranks, fp64 scores
+        assert many[0]["debug"]["dense"]["modes"]["chunks"] == "ann"
+        # mixed call: 20 unscoped requests (tensor-core lane) + 6 scoped to two calls (exact lane, gather launch)
+        scoped = RetrieveFilters(call_ids=[3, 44])
+        f_list = [None] * 10 + [scoped] * 6 + [None] * 10
+        t_list = [f"mixed question {i}" for i in range(26)]
+        seen.clear()
+        mixed = retrieve.retrieve_ids_batch(eng, t_list, f_list)
+        lanes = sorted((sp or {}).get("dense_lane", 0) for sp in seen[-1][1])
+        assert lanes == [0, 1]
+        for t, f, got in zip(t_list, f_list, mixed):
+            assert got["retrieved_ids"] == retrieve.retrieve_ids(eng, t, f, debug=True)["retrieved_ids"]
+        # fewer than cadence_gpu_ann_min_batch requests: exact lane
+        seen.clear()
+        retrieve.retrieve_ids_batch(eng, texts[:8], None)
+        assert not (seen[-1][0] or {}).get("dense_lane")
+        # a bf16-less store never takes the lane
+        only32 = DenseStore("chunks", 70_000, dim=1024, device=0, bf16=False)
+        only32.append_synthetic(70_000); only32.finalize()
+        assert retrieve._group_dense_lane(only32, None, None, 64) == _ffi.CDR_DENSE_LANE_EXACT_F32
+        assert retrieve._group_dense_lane(store, scoped, [3, 44], 64) == _ffi.CDR_DENSE_LANE_EXACT_F32
+        only32.close()
+    finally:
+        embeddings.set_embedder(None)
+        store.close()
