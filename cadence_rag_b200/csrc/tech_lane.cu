@@ -10,20 +10,28 @@
 // u64 key / warp top-k machinery as the dense lane applies, with key =
 // ((0xFFFFFFFF - rank) << 32) | (0xFFFFFFFF - row).
 //
-// One CTA (8 warps) per query.  Warp w scans, for every query token, the part of the posting list
-// that falls in its row range [w*N/8, (w+1)*N/8) (two binary searches), so all occurrences of a row
-// (it may match several tokens) meet in one warp and are de-duplicated on insert.  The filter
-// predicate (call_id = ANY, date range, tags overlap -- app/retrieve.py:93-120, WITHOUT the dense
-// lane's `embedding IS NOT NULL`) is evaluated on the posting rows only.
+// Posting lists are kept in RANK order (best row of the lane's ORDER BY first; re-sorted at index build), with the
+// rank stored beside the row.  One CTA (8 warps) per query; warp w takes the 32-posting chunks w, w+8, ... of every
+// query token.  Candidates therefore arrive best-first: a warp's running top-k fills from the head of the list, its
+// threshold then beats everything further down, and the warp leaves the token as soon as the chunk's best possible
+// key cannot enter (unfiltered: after ~2 chunks per warp, whatever the list length; a scan in row order met ever
+// better rows -- newer calls have larger ids -- and paid an insertion per posting: 4.6 ms for 64 queries over
+// frequent tokens).  Under a selective filter the warps keep scanning until enough rows pass.  The filter predicate
+// (call_id = ANY, date range, tags overlap -- app/retrieve.py:93-120, WITHOUT the dense lane's `embedding IS NOT
+// NULL`) is evaluated on the posting rows only.  A row matching several tokens may reach several warps: the eight
+// lists are sorted together and duplicates (identical keys) dropped before the LIMIT.
 #include "common.cuh"
+
+#include <algorithm>
+#include <vector>
 
 struct cdr_tech_index {
     cdr_store *store = nullptr;
     int32_t n_tokens = 0;
     int64_t n_postings = 0;
     int64_t *offsets = nullptr;    // [n_tokens + 1]
-    uint32_t *rows = nullptr;      // [n_postings]
-    uint32_t *rank = nullptr;      // [store rows]
+    uint32_t *rows = nullptr;      // [n_postings]  rows of a token in rank order
+    uint32_t *prank = nullptr;     // [n_postings]  rank of each posting's row (ascending inside a token)
 };
 
 namespace {
@@ -34,7 +42,7 @@ constexpr int kTechMaxTokens = 32;
 struct TechParams {
     const int64_t *offsets;
     const uint32_t *post_rows;
-    const uint32_t *rank;
+    const uint32_t *post_rank;
     const int64_t *ids;
     const int32_t *call_slot;
     const int64_t *started_at;
@@ -54,21 +62,12 @@ struct TechParams {
     int32_t *out_n;                // [nq]
 };
 
-__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *a, int64_t lo, int64_t hi, uint32_t v)
-{
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (a[mid] < v) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
 template <int NPL>
 __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechParams p)
 {
     constexpr int KC = NPL * 32;
-    __shared__ uint64_t s_lists[kTechWarps * KC];
+    constexpr int NK = kTechWarps * KC;                 // keys sorted together at the end
+    __shared__ uint64_t s_lists[NK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x;
     const int ntok = min(p.q_ntok[q], p.max_tokens);
@@ -76,19 +75,21 @@ __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechPa
 
     WarpTopK<NPL> top;
     top.init(s_lists + warp * KC, lane);
-    const uint32_t r_lo = (uint32_t)((p.n_rows * warp) / kTechWarps);
-    const uint32_t r_hi = (uint32_t)((p.n_rows * (warp + 1)) / kTechWarps);
 
     for (int t = 0; t < ntok; ++t) {
         const int32_t tok = toks[t];
         if (tok < 0 || tok >= p.n_index_tokens) continue;            // unknown token: no postings
         const int64_t b0 = p.offsets[tok], b1 = p.offsets[tok + 1];
-        const int64_t lo = lower_bound_u32(p.post_rows, b0, b1, r_lo);
-        const int64_t hi = lower_bound_u32(p.post_rows, lo, b1, r_hi);
-        for (int64_t base = lo; base < hi; base += 32) {
+        for (int64_t base = b0 + (int64_t)warp * 32; base < b1; base += (int64_t)kTechWarps * 32) {
+            // ranks ascend along the list: nothing from here on can enter once the list is full and even the best
+            // possible key of this chunk (its first rank, any row) is not above the threshold
+            if (top.count == KC) {
+                const uint64_t best = ((uint64_t)(0xFFFFFFFFu - p.post_rank[base]) << 32) | 0xFFFFFFFFull;
+                if (best <= top.tau) break;
+            }
             const int64_t i = base + lane;
             uint64_t key = CDR_EMPTY_KEY;
-            if (i < hi) {
+            if (i < b1) {
                 const uint32_t row = p.post_rows[i];
                 bool ok = true;
                 if (p.call_bitmap) {
@@ -101,9 +102,9 @@ __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechPa
                     if (p.has_to && ts > p.date_to) ok = false;
                 }
                 if (ok && p.has_tags) ok = (p.tag_bits[row] & p.tag_any) != 0ull;
-                if (ok) key = ((uint64_t)(0xFFFFFFFFu - p.rank[row]) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+                if (ok) key = ((uint64_t)(0xFFFFFFFFu - p.post_rank[i]) << 32) | (uint64_t)(0xFFFFFFFFu - row);
             }
-            // insert the lanes' candidates one by one (warp-uniform), skipping rows already listed
+            // insert the lanes' candidates one by one (warp-uniform), skipping rows this warp already listed
             unsigned pending = __ballot_sync(0xffffffffu, key > top.tau);
             while (pending) {
                 const int src = __ffs(pending) - 1;
@@ -119,32 +120,35 @@ __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechPa
         }
     }
 
-    // per-warp sort, then pairwise merge tree (as in the dense lane)
-    uint64_t k[NPL];
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) k[i] = top.list[i * 32 + lane];
-    warp_bitonic_sort_desc<NPL>(k, lane);
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
-#pragma unroll
-    for (int step = 1; step < kTechWarps; step <<= 1) {
-        __syncthreads();
-        if ((warp & (2 * step - 1)) == 0) {
-            warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) top.list[i * 32 + lane] = k[i];
+    // all kTechWarps lists sorted together (descending, bitonic network over shared memory), duplicates dropped
+    __syncthreads();
+    for (int size = 2; size <= NK; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < NK / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));           // index with bit `stride` clear
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = s_lists[lo], b = s_lists[hi];
+                if ((a < b) == desc) { s_lists[lo] = b; s_lists[hi] = a; }
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
-    int n = 0;
-    for (int e = threadIdx.x; e < KC; e += blockDim.x) {
-        const uint64_t key = s_lists[e];
-        if (e < p.limit) p.out_ids[(size_t)q * p.limit + e] = key != CDR_EMPTY_KEY ? p.ids[cdr_key_row(key)] : -1;
-    }
-    if (threadIdx.x == 0) {
-        for (int e = 0; e < KC && e < p.limit; ++e) n += s_lists[e] != CDR_EMPTY_KEY;
-        p.out_n[q] = n;
+    if (warp == 0) {
+        int n = 0;
+        for (int base = 0; base < NK && n < p.limit; base += 32) {
+            const uint64_t key = s_lists[base + lane];
+            const uint64_t prev = (base + lane) > 0 ? s_lists[base + lane - 1] : ~0ull;
+            const bool keep = key != CDR_EMPTY_KEY && key != prev;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const int pos = n + __popc(m & ((1u << lane) - 1u));
+            if (keep && pos < p.limit) p.out_ids[(size_t)q * p.limit + pos] = p.ids[cdr_key_row(key)];
+            n += __popc(m);
+            if (__all_sync(0xffffffffu, key == CDR_EMPTY_KEY)) break;   // sorted: only empties follow
+        }
+        if (n > p.limit) n = p.limit;
+        for (int e = n + lane; e < p.limit; e += 32) p.out_ids[(size_t)q * p.limit + e] = -1;
+        if (lane == 0) p.out_n[q] = n;
     }
 }
 
@@ -160,6 +164,25 @@ extern "C" int32_t cdr_tech_index_create(cdr_tech_index **out, cdr_store *s, con
     *out = nullptr;
     const int64_t total = post_offsets_host[n_tokens];
     CDR_REQUIRE(total >= 0 && (total == 0 || post_rows_host), CDR_ERR_INVALID, "cdr_tech_index_create: bad postings");
+    for (int64_t i = 0; i < total; ++i)
+        CDR_REQUIRE((int64_t)post_rows_host[i] < s->n_rows, CDR_ERR_INVALID, "cdr_tech_index_create: posting row out of range");
+    // every token's postings in the lane's order (rank ascending = call_started_at DESC, id ASC), rank beside the row
+    std::vector<uint32_t> rows_sorted((size_t)(total > 0 ? total : 1)), rank_sorted((size_t)(total > 0 ? total : 1));
+    {
+        std::vector<uint64_t> keyed;
+        for (int32_t t = 0; t < n_tokens; ++t) {
+            const int64_t b0 = post_offsets_host[t], b1 = post_offsets_host[t + 1];
+            CDR_REQUIRE(b0 >= 0 && b1 >= b0 && b1 <= total, CDR_ERR_INVALID, "cdr_tech_index_create: offsets not monotone");
+            keyed.resize((size_t)(b1 - b0));
+            for (int64_t i = b0; i < b1; ++i)
+                keyed[(size_t)(i - b0)] = ((uint64_t)rank_host[post_rows_host[i]] << 32) | post_rows_host[i];
+            std::sort(keyed.begin(), keyed.end());
+            for (int64_t i = b0; i < b1; ++i) {
+                rows_sorted[(size_t)i] = (uint32_t)(keyed[(size_t)(i - b0)] & 0xFFFFFFFFull);
+                rank_sorted[(size_t)i] = (uint32_t)(keyed[(size_t)(i - b0)] >> 32);
+            }
+        }
+    }
     DeviceGuard g(s->device);
     cdr_tech_index *ix = new cdr_tech_index();
     ix->store = s;
@@ -167,13 +190,13 @@ extern "C" int32_t cdr_tech_index_create(cdr_tech_index **out, cdr_store *s, con
     ix->n_postings = total;
     cudaError_t e = cudaMalloc(&ix->offsets, (size_t)(n_tokens + 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&ix->rows, (size_t)(total > 0 ? total : 1) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&ix->rank, (size_t)(s->n_rows > 0 ? s->n_rows : 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->prank, (size_t)(total > 0 ? total : 1) * 4);
     if (e == cudaSuccess) e = cudaMemcpy(ix->offsets, post_offsets_host, (size_t)(n_tokens + 1) * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && total > 0) e = cudaMemcpy(ix->rows, post_rows_host, (size_t)total * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && s->n_rows > 0) e = cudaMemcpy(ix->rank, rank_host, (size_t)s->n_rows * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && total > 0) e = cudaMemcpy(ix->rows, rows_sorted.data(), (size_t)total * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && total > 0) e = cudaMemcpy(ix->prank, rank_sorted.data(), (size_t)total * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cdr_set_error("cdr_tech_index_create: %s", cudaGetErrorString(e));
-        cudaFree(ix->offsets); cudaFree(ix->rows); cudaFree(ix->rank);
+        cudaFree(ix->offsets); cudaFree(ix->rows); cudaFree(ix->prank);
         delete ix;
         return e == cudaErrorMemoryAllocation ? CDR_ERR_OOM : CDR_ERR_CUDA;
     }
@@ -188,7 +211,7 @@ extern "C" int32_t cdr_tech_index_destroy(cdr_tech_index *ix)
     cudaDeviceSynchronize();
     cudaFree(ix->offsets);
     cudaFree(ix->rows);
-    cudaFree(ix->rank);
+    cudaFree(ix->prank);
     delete ix;
     return CDR_OK;
 }
@@ -201,7 +224,7 @@ int cdr_tech_lane_launch(cdr_tech_index *ix, const int32_t *d_tok, const int32_t
 {
     cdr_store *s = ix->store;
     TechParams p;
-    p.offsets = ix->offsets; p.post_rows = ix->rows; p.rank = ix->rank;
+    p.offsets = ix->offsets; p.post_rows = ix->rows; p.post_rank = ix->prank;
     p.ids = s->ids; p.call_slot = s->call_slot; p.started_at = s->started_at; p.tag_bits = s->tag_bits;
     p.call_bitmap = d_bm; p.n_call_slots = n_call_slots; p.n_rows = s->n_rows; p.n_index_tokens = ix->n_tokens;
     p.has_from = has_date_from != 0; p.has_to = has_date_to != 0; p.has_tags = has_tag_filter != 0;

@@ -238,9 +238,10 @@ int32_t cdr_rrf_merge_host(const int64_t *lane_ids_host, const int32_t *lane_off
 /* ---- tech_tokens lexical lane, device resident -------------------------
  * Replaces the SQL of _fetch_chunks_tech / _fetch_artifacts_tech (app/retrieve.py:183-242):
  *   WHERE <filters> AND tech_tokens && :tokens ORDER BY call_started_at DESC, id ASC LIMIT :limit
- * The index is CSR postings over dictionary-encoded tokens (token t -> ascending rows
- * post_rows[post_offsets[t] .. post_offsets[t+1])) plus rank[row] = position of the row in the
- * order (call_started_at DESC, id ASC).  Queries carry token ids (-1 = unknown token).  The filter
+ * The index is CSR postings over dictionary-encoded tokens (token t -> rows
+ * post_rows[post_offsets[t] .. post_offsets[t+1]), any order on input) plus rank[row] = position of the row in the
+ * order (call_started_at DESC, id ASC); cdr_tech_index_create keeps every list in rank order on the device, so a
+ * query reads the head of each list instead of all of it.  Queries carry token ids (-1 = unknown token).  The filter
  * arguments are those of cdr_filter_build, without the `embedding IS NOT NULL` term (the tech
  * lane's WHERE has none).  Host buffers; synchronises.  out_ids [nq, limit] (unused slots -1). */
 typedef struct cdr_tech_index cdr_tech_index;
