@@ -368,6 +368,25 @@ def run_batch_bf16(args):
         if world > 1:
             dist.all_reduce(xt, op=dist.ReduceOp.MAX)
         exact_q1 = {"ms_per_query": float(xt[0]), "hbm_gbs_per_gpu": float(count) * DIM * 4 / (float(xt[0]) / 1e3) / 1e9}
+    # mode "ann" for ONE query: the same scan over the bf16 rows (half the bytes), exact re-score
+    scan_q1 = None
+    if store.has_bf16:
+        for i in range(3):
+            searcher.search(q_dev[0][i % nq:i % nq + 1].contiguous(), TOPK, mode="scan_bf16")
+        barrier()
+        xa, xb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        xa.record()
+        for i in range(20):
+            got1 = searcher.search(q_dev[1][i % nq:i % nq + 1].contiguous(), TOPK, mode="scan_bf16")
+        xb.record()
+        barrier()
+        xt = torch.tensor([xa.elapsed_time(xb) / 20], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(xt, op=dist.ReduceOp.MAX)
+        scan_q1 = {"ms_per_query": float(xt[0]), "hbm_gbs_per_gpu": float(count) * DIM * 2 / (float(xt[0]) / 1e3) / 1e9}
+        if store.has_fp32:
+            want1 = searcher.search(q_dev[1][19 % nq:19 % nq + 1].contiguous(), TOPK, mode="exact")
+            scan_q1["recall_at_50_vs_exact_fp32_lane_last_query"] = len(set(got1[0][0].tolist()) & set(want1[0][0].tolist())) / TOPK
     # e2e with host buffers (pinned): H2D of the queries + D2H of the merged result every step
     q_pinned = torch.empty(q_dev.shape, dtype=torch.float32, pin_memory=True)
     q_pinned.copy_(q_dev); torch.cuda.synchronize()
@@ -415,7 +434,8 @@ def run_batch_bf16(args):
                            "rows": rows, "rows_per_gpu": count, "dim": DIM, "k": TOPK, "queries_per_step": nq,
                            "resident": "bf16 only" if args.bf16_only else "fp32 + bf16",
                            "l2": "inputs larger than L2", "recall_at_50_vs_exact_fp32_lane": recall,
-                           "exchange": searcher.transport, "exact_fp32_lane_single_query": exact_q1},
+                           "exchange": searcher.transport, "exact_fp32_lane_single_query": exact_q1,
+                           "ann_bf16_scan_single_query": scan_q1},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": None if tt is None else {"value": args.steps * nq / float(tt[0]), "unit": UNIT,
                                                 "h2d_bytes_per_step": nq * DIM * 4,
@@ -513,6 +533,18 @@ def run_hybrid(args):
             retrieve.retrieve_ids(eng, f"status of TK-{i % 500} and TK-{(i * 13) % 900}", f)
         dt = time.perf_counter() - t0
         out[name] = {"queries_per_s": n / dt, "ms_per_query": dt / n * 1e3, "queries": n}
+        if f is None and settings.cadence_gpu_ann_bf16_scan:
+            # unscoped requests plan "ann" and scan the bf16 rows by default; the same requests on the exact fp32 scan
+            settings.cadence_gpu_ann_bf16_scan = 0
+            try:
+                for i in range(8):
+                    retrieve.retrieve_ids(eng, f"warm TK-{i} TK-{i + 3}", f)
+                t0 = time.perf_counter()
+                for i in range(n):
+                    retrieve.retrieve_ids(eng, f"status of TK-{i % 500} and TK-{(i * 13) % 900}", f)
+                out[name]["queries_per_s_exact_fp32_scan"] = n / (time.perf_counter() - t0)
+            finally:
+                settings.cadence_gpu_ann_bf16_scan = 1
     # batched form: 64 requests per fused C call (cdr_hybrid_retrieve_host), embeddings and token ids prepared
     # outside the timed region (the embedder is a remote model in the reference), host buffers in and out
     dev_index = eng.device_tech_indexes["chunks"]

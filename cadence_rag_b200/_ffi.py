@@ -83,6 +83,8 @@ SIGNATURES = {
     "cdr_search_exact_f32_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_search_exact_f32_shared": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_search_exact_f32_shared_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cdr_search_scan_bf16": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "cdr_search_scan_bf16_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_search_batch_bf16": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_search_batch_bf16_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_topk_merge": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
@@ -109,6 +111,7 @@ SIGNATURES = {
 
 CDR_DENSE_LANE_EXACT_F32 = 0
 CDR_DENSE_LANE_BATCH_BF16 = 1
+CDR_DENSE_LANE_SCAN_BF16 = 2
 
 
 class FilterSpec(ctypes.Structure):

@@ -33,6 +33,9 @@ class Settings:
     # mode "ann" is served by the batched bf16 tensor-core lane when at least this many queries
     # are in flight; smaller batches use the (exact, HBM-bound) fp32 scan when fp32 rows are resident
     cadence_gpu_ann_min_batch: int = 16
+    # 1: single requests (and pairs) whose planner mode is "ann" scan the bf16 copy of the rows (half the bytes,
+    # candidate lists twice as wide, exact re-score: recall ~1.0) instead of the fp32 rows; 0: always the exact scan
+    cadence_gpu_ann_bf16_scan: int = 1
 
     @classmethod
     def from_env(cls) -> "Settings":

@@ -216,6 +216,29 @@ extern "C" int32_t cdr_search_exact_f32_shared(cdr_store *s, const float *q_dev,
                             out_id_dev, out_n_dev, stream);
 }
 
+extern "C" int32_t cdr_search_scan_bf16(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                                        const uint32_t *allow_dev, double *out_score_dev,
+                                        int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
+{
+    const char *fn = "cdr_search_scan_bf16";
+    int rc = check_search_args(fn, s, q_dev, nq, k, out_score_dev, out_id_dev, out_n_dev);
+    if (rc != CDR_OK) return rc;
+    CDR_REQUIRE(s->emb_bf16 != nullptr, CDR_ERR_STATE, "%s: store has no bf16 rows (created without CDR_STORE_BF16)", fn);
+    if (nq == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(s->mu);
+    ScanWorkspace &ws = s->ws[st];
+    const uint32_t *allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
+    for (int q0 = 0; q0 < nq; q0 += 32768) {
+        const int m = (nq - q0) < 32768 ? (nq - q0) : 32768;
+        rc = cdr_bf16_scan_launch(s, ws, q_dev + (size_t)q0 * s->dim, m, allow, k, out_score_dev + (size_t)q0 * k,
+                                  out_id_dev + (size_t)q0 * k, out_n_dev + q0, st);
+        if (rc != CDR_OK) return rc;
+    }
+    return CDR_OK;
+}
+
 // Shared host-buffer wrapper: H2D queries, run `fn`, D2H results, synchronise.
 typedef int32_t (*search_fn)(cdr_store *, const float *, int32_t, int32_t, const uint32_t *, double *,
                              int64_t *, int32_t *, void *);
@@ -282,6 +305,14 @@ extern "C" int32_t cdr_search_exact_f32_shared_host(cdr_store *s, const float *q
                                                     int64_t *out_id_host, int32_t *out_n_host, void *stream)
 {
     return search_host("cdr_search_exact_f32_shared_host", cdr_search_exact_f32_shared, s, q_host, nq, k, allow_dev,
+                       out_score_host, out_id_host, out_n_host, stream);
+}
+
+extern "C" int32_t cdr_search_scan_bf16_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                             const uint32_t *allow_dev, double *out_score_host,
+                                             int64_t *out_id_host, int32_t *out_n_host, void *stream)
+{
+    return search_host("cdr_search_scan_bf16_host", cdr_search_scan_bf16, s, q_host, nq, k, allow_dev,
                        out_score_host, out_id_host, out_n_host, stream);
 }
 

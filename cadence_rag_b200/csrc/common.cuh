@@ -104,6 +104,9 @@ struct DeviceGuard {
 
 // K1 + finalize on `st` (exact_scan.cu).  share_reads: score every streamed tile against 3 queries per CTA
 // (batches of concurrent exact requests); false = one scan of the corpus per query.  Same bits either way.
+// Single-query "ann" lane (exact_scan.cu): candidate pass over the bf16 rows, exact re-score.  Store mutex held by the caller.
+int cdr_bf16_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
+                         double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st);
 // K2 (gemm_topk.cu) with the store mutex held by the caller: nq <= 16384, k <= 192, bf16 rows resident.
 int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, int k, const uint32_t *allow_dev,
                           double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev, cudaStream_t st);

@@ -82,15 +82,18 @@ struct DeepTopK {     // per (consumer warp, query) in shared memory
     int count;
     int min_pos;
 };
-template <int J, int RPW, int NPL, int QPC>
+// BF = the rows streamed are the store's bf16 copy (row L2-normalised, RN-even) instead of the fp32 rows: the
+// candidate pass of the single-query "ann" lane (cdr_search_scan_bf16), half the bytes per row.
+template <int J, int RPW, int NPL, int QPC, bool BF = false>
 struct ScanSmem {
     static constexpr int DIM = J * 128;
+    static constexpr size_t kRowBytes = (size_t)DIM * (BF ? 2 : 4);
     static constexpr bool kDeep = QPC > kSharedQPC;
     static constexpr int CW = kDeep ? kDeepWarps : kConsumerWarps;              // consumer warps
     static constexpr int QW = kDeep ? QPC / kDeepQSplit : QPC;                   // queries a warp keeps top-k lists for
     static constexpr int TR = kDeep ? RPW * CW / kDeepQSplit : RPW * CW;
     static constexpr int KC = NPL * 32;
-    static constexpr size_t kTileBytes = (size_t)TR * DIM * 4;
+    static constexpr size_t kTileBytes = (size_t)TR * kRowBytes;
     static constexpr size_t kMetaBytes = (size_t)TR * 4;   // inverse norms (multiple of 16)
     static constexpr size_t kListBytes = (size_t)CW * QW * KC * 8;
     static constexpr size_t kBarBytes = 3 * kMaxStages * 8;   // full + empty barriers + the tile index of each stage
@@ -110,10 +113,10 @@ struct ScanSmem {
     }
 };
 
-template <int J, int RPW, int NPL, int QPC>
-__global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) exact_scan_kernel(const ScanParams p)
+template <int J, int RPW, int NPL, int QPC, bool BF = false>
+__global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32, 1) exact_scan_kernel(const ScanParams p)
 {
-    using L = ScanSmem<J, RPW, NPL, QPC>;
+    using L = ScanSmem<J, RPW, NPL, QPC, BF>;
     constexpr int DIM = L::DIM, TR = L::TR, KC = L::KC, CW = L::CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
@@ -198,12 +201,13 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
             }
             if (lane == 0) {
                 stage_tile[s] = tile;
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nr * DIM * 4));
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(nr * L::kRowBytes));
             }
             __syncwarp();
             if (lane < nr)
-                bulk_g2s(tiles + (size_t)s * L::kTileBytes + (size_t)lane * DIM * 4, p.rows + (size_t)my_row * DIM,
-                         (uint32_t)(DIM * 4), &full_bar[s]);
+                bulk_g2s(tiles + (size_t)s * L::kTileBytes + (size_t)lane * L::kRowBytes,
+                         reinterpret_cast<const unsigned char *>(p.rows) + (size_t)my_row * L::kRowBytes,
+                         (uint32_t)L::kRowBytes, &full_bar[s]);
         }
     } else if (warp == CW) {
         // ------------------------------------------------------------------ producer
@@ -226,9 +230,10 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                 const int64_t row0 = tile * TR;
                 int64_t nr = p.n_rows - row0;
                 if (nr > TR) nr = TR;
-                const uint32_t row_bytes = (uint32_t)(nr * DIM * 4);
+                const uint32_t row_bytes = (uint32_t)(nr * L::kRowBytes);
                 mbar_arrive_expect_tx(&full_bar[s], row_bytes + (uint32_t)L::kMetaBytes);
-                bulk_g2s(tiles + (size_t)s * L::kTileBytes, p.rows + row0 * DIM, row_bytes,
+                bulk_g2s(tiles + (size_t)s * L::kTileBytes,
+                         reinterpret_cast<const unsigned char *>(p.rows) + (size_t)row0 * L::kRowBytes, row_bytes,
                          &full_bar[s]);
                 bulk_g2s(metas + (size_t)s * L::kMetaBytes, p.inv_norm + row0,
                          (uint32_t)L::kMetaBytes, &full_bar[s]);
@@ -416,6 +421,84 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC>::CW + 1) * 32, 1) 
                     uint64_t *out = p.cta_keys + ((size_t)(q0 + uq) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
 #pragma unroll
                     for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
+                }
+            }
+        } else if constexpr (BF) {
+            // ---- candidate pass over the bf16 rows (single-query "ann" lane): a lane takes 8 consecutive elements
+            // per 16-byte step, widens them with a shift / mask and accumulates in fp32 against the fp32 query.
+            // The rows are stored normalised, so the score is dot / |q|; survivors are re-scored exactly (fp64 on
+            // the fp32 rows) by the finalize kernel.
+            static_assert(QPC == 1 && J % 2 == 0, "bf16 scan: one query per CTA, dim a multiple of 256");
+            constexpr int JB = J / 2;
+            float4 qa[JB], qb[JB];
+            float qn = 0.f;
+            const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)q0 * DIM);
+#pragma unroll
+            for (int j = 0; j < JB; ++j) {
+                qa[j] = __ldg(&qv[(j * 32 + lane) * 2]);
+                qb[j] = __ldg(&qv[(j * 32 + lane) * 2 + 1]);
+                qn = fmaf(qa[j].x, qa[j].x, qn); qn = fmaf(qa[j].y, qa[j].y, qn);
+                qn = fmaf(qa[j].z, qa[j].z, qn); qn = fmaf(qa[j].w, qa[j].w, qn);
+                qn = fmaf(qb[j].x, qb[j].x, qn); qn = fmaf(qb[j].y, qb[j].y, qn);
+                qn = fmaf(qb[j].z, qb[j].z, qn); qn = fmaf(qb[j].w, qb[j].w, qn);
+            }
+            qn = warp_sum_f32(qn);
+            const float inv_q = __fdiv_rn(1.0f, __fsqrt_rn(qn));
+            WarpTopK<NPL> top;
+            top.init(lists + warp * KC, lane);
+            for (int64_t i = 0;; ++i) {
+                const int s = (int)(i % S);
+                const uint32_t ph = (uint32_t)((i / S) & 1);
+                mbar_wait(&full_bar[s], ph);
+                const int64_t tile = stage_tile[s];
+                if (tile < 0) break;
+                const int64_t row0 = tile * TR + warp * RPW;      // a multiple of RPW (<= 4): one bitmap word
+                uint32_t allow_bits = 0xFFFFFFFFu;
+                uint32_t g_row[RPW];
+                if (gather) {
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) {
+                        const bool in = row0 + r < (int64_t)n_listed;
+                        g_row[r] = in ? __ldg(&p.row_list[row0 + r]) : 0u;
+                        if (!in) allow_bits &= ~(1u << r);
+                    }
+                } else if (p.allow != nullptr) {
+                    const uint32_t w = (row0 < p.n_rows) ? __ldg(&p.allow[row0 >> 5]) : 0u;
+                    allow_bits = w >> (row0 & 31);
+                }
+                const uint4 *tv = reinterpret_cast<const uint4 *>(tiles + (size_t)s * L::kTileBytes) +
+                                  (size_t)(warp * RPW) * (DIM / 8) + lane;
+                float acc[RPW][2];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) acc[r][0] = acc[r][1] = 0.f;
+#pragma unroll
+                for (int j = 0; j < JB; ++j) {
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) {
+                        const uint4 v = tv[r * (DIM / 8) + j * 32];
+                        float a = acc[r][j & 1];
+                        a = fmaf(__uint_as_float(v.x << 16), qa[j].x, a);
+                        a = fmaf(__uint_as_float(v.x & 0xFFFF0000u), qa[j].y, a);
+                        a = fmaf(__uint_as_float(v.y << 16), qa[j].z, a);
+                        a = fmaf(__uint_as_float(v.y & 0xFFFF0000u), qa[j].w, a);
+                        a = fmaf(__uint_as_float(v.z << 16), qb[j].x, a);
+                        a = fmaf(__uint_as_float(v.z & 0xFFFF0000u), qb[j].y, a);
+                        a = fmaf(__uint_as_float(v.w << 16), qb[j].z, a);
+                        a = fmaf(__uint_as_float(v.w & 0xFFFF0000u), qb[j].w, a);
+                        acc[r][j & 1] = a;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) {
+                    const int64_t row = gather ? (int64_t)g_row[r] : row0 + r;
+                    const bool ok = (row < p.n_rows) && ((allow_bits >> r) & 1u);
+                    const float dot = warp_sum_f32(acc[r][0] + acc[r][1]);
+                    if (ok) {
+                        const uint64_t key = cdr_pack_key(dot * inv_q, (uint32_t)row);
+                        if (key > top.tau) top.push(key, lane);
+                    }
                 }
             }
         } else {
@@ -1041,8 +1124,9 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
     // 25.5 us vs 31.6 us per launch, profiles/r01/README.md)
     // small batches of sorted per-CTA lists (the exact lane serving single requests): 8-CTA cluster per query
     static const bool no_cluster = [] { const char *e = getenv("CADENCE_FIN_CLUSTER"); return e && e[0] == '0'; }();
-    if (fp.counts == nullptr && nq <= 16 && !no_cluster && (kc == 64 || kc == 256)) {
+    if (fp.counts == nullptr && nq <= 16 && !no_cluster && (kc == 64 || kc == 128 || kc == 256)) {
         if (kc == 64) scan_finalize_cluster_kernel<2><<<nq * kFinCluster, 256, 0, st>>>(fp);
+        else if (kc == 128) scan_finalize_cluster_kernel<4><<<nq * kFinCluster, 256, 0, st>>>(fp);
         else scan_finalize_cluster_kernel<8><<<nq * kFinCluster, 256, 0, st>>>(fp);
         CDR_LAUNCH_CHECK();
         return CDR_OK;
@@ -1058,12 +1142,12 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
     return CDR_OK;
 }
 
-template <int J, int RPW, int NPL, int QPC>
+template <int J, int RPW, int NPL, int QPC, bool BF = false>
 int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                   const uint32_t *allow, int k, double *out_score, int64_t *out_id, int32_t *out_n,
                   cudaStream_t st)
 {
-    using L = ScanSmem<J, RPW, NPL, QPC>;
+    using L = ScanSmem<J, RPW, NPL, QPC, BF>;
     constexpr int KC = L::KC;
     // per-device launch configuration (the smem opt-in attribute is per device)
     static int stages_by_dev[64] = {0};
@@ -1075,7 +1159,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
         CDR_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
         int st_n = L::max_stages((size_t)dev_smem);
         smem = L::bytes(st_n);
-        CDR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<J, RPW, NPL, QPC>,
+        CDR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<J, RPW, NPL, QPC, BF>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         stages = st_n;
     }
@@ -1135,7 +1219,7 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     }
 
     ScanParams sp;
-    sp.rows = s->emb_f32;
+    sp.rows = BF ? reinterpret_cast<const float *>(s->emb_bf16) : s->emb_f32;
     sp.inv_norm = s->inv_norm;
     sp.allow = allow;
     sp.queries = q_dev;
@@ -1157,12 +1241,12 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
         gp.row_list = ws.row_list;
         gp.list_count = reinterpret_cast<unsigned int *>(ws.row_list) + list_cap;
         gp.allow = nullptr;
-        exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(g_gather, n_groups), (L::CW + 1) * 32, smem, st>>>(gp);
+        exact_scan_kernel<J, RPW, NPL, QPC, BF><<<dim3(g_gather, n_groups), (L::CW + 1) * 32, smem, st>>>(gp);
         CDR_LAUNCH_CHECK();
         sp.list_count = gp.list_count;
         sp.list_offset = g_gather;
     }
-    exact_scan_kernel<J, RPW, NPL, QPC><<<dim3(grid, n_groups), (L::CW + 1) * 32, smem, st>>>(sp);
+    exact_scan_kernel<J, RPW, NPL, QPC, BF><<<dim3(grid, n_groups), (L::CW + 1) * 32, smem, st>>>(sp);
     CDR_LAUNCH_CHECK();
     cdr_prof_mark_end(0, st);
 
@@ -1171,8 +1255,8 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     fp.n_lists = g_total;
     fp.counts = nullptr;
     fp.cap = 0;
-    fp.rows = s->emb_f32;
-    fp.bf16_rows = nullptr;
+    fp.rows = s->emb_f32;                            // BF: exact re-score on the fp32 rows when they are resident
+    fp.bf16_rows = BF ? s->emb_bf16 : nullptr;
     fp.queries = q_dev;
     fp.ids = s->ids;
     fp.dim = s->dim;
@@ -1243,6 +1327,26 @@ int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
     const int rest = nq - n_deep;
     return launch_scan_dim<2>(s, ws, q_dev + (size_t)n_deep * s->dim, rest, allow, k, out_score + (size_t)n_deep * k,
                               out_id + (size_t)n_deep * k, out_n + n_deep, st, share && rest >= 2 ? kScanShared : kScanSingle);
+}
+
+// Single-query "ann" lane: the same scan over the bf16 copy of the rows (half the bytes), candidate lists twice as wide
+// as the exact lane's (KC = 128 for k <= 120, else 256), exact fp64 re-score of the survivors.  One scan per query.
+int cdr_bf16_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
+                         double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st)
+{
+#define CDR_BF_CASE(J_)                                                                                          \
+    if (k <= 120) return launch_scan_t<J_, 4, 4, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
+    return launch_scan_t<J_, 4, 8, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st)
+    switch (s->dim) {
+    case 256:  CDR_BF_CASE(2);
+    case 512:  CDR_BF_CASE(4);
+    case 768:  CDR_BF_CASE(6);
+    case 1024: CDR_BF_CASE(8);
+    default:
+        cdr_set_error("bf16 scan: dim %d not built (supported: 256,512,768,1024)", s->dim);
+        return CDR_ERR_UNSUPPORTED;
+    }
+#undef CDR_BF_CASE
 }
 
 // Used by the batched bf16 lane (gemm_topk.cu): select the top-kc of one unsorted candidate

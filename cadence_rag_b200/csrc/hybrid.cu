@@ -121,10 +121,10 @@ extern "C" int32_t cdr_hybrid_retrieve_groups_host(
     if (dense && filters != nullptr) {
         for (int gi = 0; gi < n_groups; ++gi) {
             if (filters[gi].dense_lane == CDR_DENSE_LANE_EXACT_F32) continue;
-            CDR_REQUIRE(filters[gi].dense_lane == CDR_DENSE_LANE_BATCH_BF16, CDR_ERR_INVALID, "%s: unknown dense_lane %d in group %d",
-                        fn, filters[gi].dense_lane, gi);
-            CDR_REQUIRE(s->emb_bf16 != nullptr && dense_k <= 192 && s->dim % 64 == 0, CDR_ERR_UNSUPPORTED,
-                        "%s: the batched bf16 lane needs bf16 rows, dense_k <= 192 and dim %% 64 == 0 (group %d)", fn, gi);
+            CDR_REQUIRE(filters[gi].dense_lane == CDR_DENSE_LANE_BATCH_BF16 || filters[gi].dense_lane == CDR_DENSE_LANE_SCAN_BF16,
+                        CDR_ERR_INVALID, "%s: unknown dense_lane %d in group %d", fn, filters[gi].dense_lane, gi);
+            CDR_REQUIRE(s->emb_bf16 != nullptr && dense_k <= 192 && s->dim % 256 == 0 && s->dim <= 1024, CDR_ERR_UNSUPPORTED,
+                        "%s: the bf16 lanes need bf16 rows, dense_k <= 192 and dim in {256,512,768,1024} (group %d)", fn, gi);
         }
     }
     const bool tech = tech_index != nullptr && token_ids_host != nullptr && n_tokens_host != nullptr;
@@ -266,7 +266,9 @@ extern "C" int32_t cdr_hybrid_retrieve_groups_host(
             double *g_sc = (double *)(d + o_dsc) + (size_t)q0 * dense_k;
             int64_t *g_id = (int64_t *)(d + o_did) + (size_t)q0 * dense_k;
             int32_t *g_n = (int32_t *)(d + o_dn) + q0;
+            const bool ann_scan = filters != nullptr && filters[gi].dense_lane == CDR_DENSE_LANE_SCAN_BF16;
             if (ann) rc = cdr_batch_bf16_launch(s, ws, gq_dev, gq, dense_k, allow, g_sc, g_id, g_n, st);
+            else if (ann_scan) rc = cdr_bf16_scan_launch(s, ws, gq_dev, gq, allow, dense_k, g_sc, g_id, g_n, st);
             else rc = cdr_exact_scan_launch(s, ws, gq_dev, gq, allow, dense_k, g_sc, g_id, g_n, st, /*share_reads=*/true);
             if (rc != CDR_OK) return rc;
         }

@@ -160,9 +160,12 @@ class ShardedSearcher:
 
     def search(self, queries_dev, k: int, allow=None, mode: str = "exact", shared: bool = False):
         """queries_dev: [nq, dim] CUDA tensor replicated on every rank.  Returns the global
-        (ids, scores, n) on every rank.  shared: see DenseStore.search_exact."""
+        (ids, scores, n) on every rank.  mode: "exact" (fp32 scan; shared: see DenseStore.search_exact), "scan_bf16"
+        (single-query ann lane) or "batch" (bf16 tensor-core lane)."""
         if mode == "exact":
             ids, scores, n = self.store.search_exact(queries_dev, k, allow, shared=shared)
+        elif mode == "scan_bf16":           # mode "ann" for single queries: one scan of the bf16 rows per query
+            ids, scores, n = self.store.search_scan_bf16(queries_dev, k, allow)
         else:
             ids, scores, n = self.store.search_batch(queries_dev, k, allow)
         if self.world == 1:

@@ -262,8 +262,12 @@ def _fetch_dense(conn: DenseConnection, table_name: str, query_embedding, filter
     # a single query is answered exactly by the HBM-bound scan whenever fp32 rows are resident.
     use_batch = (mode == "ann" and store.has_bf16 and
                  (not store.has_fp32 or settings.cadence_gpu_ann_min_batch <= 1))
+    use_scan = (mode == "ann" and store.has_bf16 and not use_batch and int(settings.cadence_gpu_ann_bf16_scan)
+                and not _dense_has_scoping(filters, call_ids) and store.dim in (256, 512, 768, 1024))
     if use_batch:
         ids, scores, n = store.search_batch(q, limit, allow)
+    elif use_scan:
+        ids, scores, n = store.search_scan_bf16(q, limit, allow)
     else:
         ids, scores, n = store.search_exact(q, limit, allow)
     m = int(n[0])
@@ -457,9 +461,12 @@ def _group_dense_lane(store: DenseStore, filters, call_ids, n_requests: int) -> 
     (app/retrieve.py:277-287: the exact mode needs scoping), where the reference walks its HNSW index; a group of at
     least `cadence_gpu_ann_min_batch` of them goes to the batched bf16 tensor-core lane when that is the faster one.
     Scoped groups stay on the exact scan: their mode depends on COUNT(*), which is computed inside the same call."""
-    if not store.has_bf16 or n_requests < max(2, int(settings.cadence_gpu_ann_min_batch)):
+    if not store.has_bf16 or _dense_has_scoping(filters, call_ids):
         return _ffi.CDR_DENSE_LANE_EXACT_F32
-    if _dense_has_scoping(filters, call_ids):
+    if n_requests < max(2, int(settings.cadence_gpu_ann_min_batch)):
+        # one or two requests: a scan of the bf16 rows per query beats one (shared) scan of the fp32 rows
+        if int(settings.cadence_gpu_ann_bf16_scan) and n_requests <= 2 and store.dim in (256, 512, 768, 1024):
+            return _ffi.CDR_DENSE_LANE_SCAN_BF16
         return _ffi.CDR_DENSE_LANE_EXACT_F32
     if _batch_lane_is_faster(store, n_requests, store.rows):
         return _ffi.CDR_DENSE_LANE_BATCH_BF16

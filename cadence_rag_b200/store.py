@@ -493,9 +493,14 @@ class DenseStore:
         """mode="exact": fp32 cosine scan (K1) + fp64 re-score.  Host queries -> host results
         (numpy, through the *_host C entry point: H2D + kernels + D2H + sync); CUDA tensors ->
         CUDA tensors (asynchronous on the current stream).  Returns (ids[nq,k], scores[nq,k], n[nq]).
-        shared=True: a batch of concurrent requests shares every tile read among 3 queries (8 for batches of >= 7)
+        shared=True: a batch of concurrent requests shares every tile read among 3 queries (16 for larger batches)
         (``cdr_search_exact_f32_shared``: nq/3 scans of the corpus, same bits); False = one scan per query."""
         return self._search("cdr_search_exact_f32_shared" if shared else "cdr_search_exact_f32", queries, k, allow)
+
+    def search_scan_bf16(self, queries, k: int, allow=None):
+        """mode="ann" for a single query or a few (``cdr_search_scan_bf16``): the HBM-bound scan over the bf16 copy
+        of the rows (half the bytes of the exact scan), candidate lists twice as wide, exact re-score."""
+        return self._search("cdr_search_scan_bf16", queries, k, allow)
 
     def search_batch(self, queries, k: int, allow=None):
         """mode="ann" served by the batched bf16 tensor-core lane (K2) + exact re-score."""

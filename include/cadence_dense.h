@@ -161,6 +161,18 @@ int32_t cdr_search_exact_f32_host(cdr_store *s, const float *q_host, int32_t nq,
                                   const uint32_t *allow_dev, double *out_score_host,
                                   int64_t *out_id_host, int32_t *out_n_host, void *stream);
 
+/* Mode "ann" for a single query (or a few): the same HBM-bound scan over the store's bf16 copy of the rows -- half the
+ * bytes of the fp32 scan -- with candidate lists twice as wide (128 for k <= 120), and the survivors re-scored exactly
+ * (fp64 on the fp32 rows when they are resident, else on the bf16 rows).  Where the reference's planner says "ann" it
+ * walks an HNSW index with ef_search = 80 (app/retrieve.py:291-298); this lane answers with recall ~1.0 against the
+ * exact scan (tests/test_gpu_engine.py::test_bf16_scan_lane).  Needs CDR_STORE_BF16, dim in {256,512,768,1024}. */
+int32_t cdr_search_scan_bf16(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                             const uint32_t *allow_dev, double *out_score_dev,
+                             int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
+int32_t cdr_search_scan_bf16_host(cdr_store *s, const float *q_host, int32_t nq, int32_t k,
+                                  const uint32_t *allow_dev, double *out_score_host,
+                                  int64_t *out_id_host, int32_t *out_n_host, void *stream);
+
 /* The same lane for a BATCH of concurrent exact requests: every tile a CTA streams from HBM is scored
  * against several queries ("shared reads"): 3 held in registers, or -- for 7 or more queries at k <= 56 -- 8
  * streamed from shared memory while the rows sit in registers, so nq queries cost nq/3 .. nq/8 scans of the corpus.
@@ -292,6 +304,8 @@ typedef struct cdr_filter_spec {
  * HNSW index there, app/retrieve.py:291-298); needs CDR_STORE_BF16, dense_k <= 192. */
 #define CDR_DENSE_LANE_EXACT_F32 0
 #define CDR_DENSE_LANE_BATCH_BF16 1
+#define CDR_DENSE_LANE_SCAN_BF16 2   /* cdr_search_scan_bf16: one HBM-bound scan of the bf16 rows per query (mode "ann",
+                                        single requests / small groups), exact re-score; dim in {256,512,768,1024} */
 
 int32_t cdr_hybrid_retrieve_host(
     cdr_store *s, cdr_tech_index *tech_index, const cdr_filter_spec *filter, const float *q_host, int32_t nq,

@@ -1129,6 +1129,7 @@ def test_fused_call_ann_groups_take_the_tensor_core_lane(monkeypatch):
     from cadence_rag_b200 import _ffi
     monkeypatch.setattr(settings, "embeddings_dim", 1024)
     monkeypatch.setattr(settings, "embeddings_base_url", "http://embedder")
+    monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 0)      # single requests on the exact scan: the yardstick
     n = 300_000
     store = DenseStore("chunks", n, dim=1024, device=0)            # fp32 + bf16
     store.append_synthetic(n); store.finalize()
@@ -1166,6 +1167,14 @@ def test_fused_call_ann_groups_take_the_tensor_core_lane(monkeypatch):
         seen.clear()
         retrieve.retrieve_ids_batch(eng, texts[:8], None)
         assert not (seen[-1][0] or {}).get("dense_lane")
+        # single unscoped requests with the bf16 scan switched on: same responses
+        monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
+        seen.clear()
+        for t, b in zip(texts[:6], want[:6]):
+            a = retrieve.retrieve_ids(eng, t, None, debug=True)
+            assert seen[-1][0]["dense_lane"] == _ffi.CDR_DENSE_LANE_SCAN_BF16
+            assert a["retrieved_ids"] == b["retrieved_ids"] and a["debug"]["lanes"]["chunks"]["dense"] == b["debug"]["lanes"]["chunks"]["dense"]
+        monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 0)
         # a bf16-less store never takes the lane
         only32 = DenseStore("chunks", 70_000, dim=1024, device=0, bf16=False)
         only32.append_synthetic(70_000); only32.finalize()
@@ -1175,3 +1184,59 @@ def test_fused_call_ann_groups_take_the_tensor_core_lane(monkeypatch):
     finally:
         embeddings.set_embedder(None)
         store.close()
+
+
+def test_bf16_scan_lane(corpus_100k, monkeypatch):
+    """cdr_search_scan_bf16 (mode "ann" for single requests): candidates from one scan of the bf16 rows, exact
+    re-score.  Against the exact lane: recall@k >= 0.999 (north_star's bar for the bf16 path), scores of shared ids
+    bit-identical (both re-score in fp64 on the fp32 rows), filters on both sides of the gather boundary, k up to
+    200, other widths, a bf16-only store, and the facade switch."""
+    s, x = corpus_100k
+    if not s.has_bf16:
+        pytest.skip("fixture store keeps no bf16 rows")
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 900, 24)
+    wide, _ = s.filter_bitmap(call_slots=list(range(0, 500, 3)))
+    narrow, _ = s.filter_bitmap(call_slots=[3, 44, 45])
+    for k in (50, 10, 200):
+        for al in (None, wide, narrow):
+            e_ids, e_sc, e_n = s.search_exact(qs, k, al)
+            b_ids, b_sc, b_n = s.search_scan_bf16(qs, k, al)
+            assert np.array_equal(e_n, b_n)
+            hits = total = 0
+            for i in range(qs.shape[0]):
+                m = int(e_n[i])
+                want, got = e_ids[i, :m].tolist(), b_ids[i, :m].tolist()
+                hits += len(set(want) & set(got)); total += m
+                pos = {v: j for j, v in enumerate(want)}
+                for j, v in enumerate(got):
+                    if v in pos:
+                        assert b_sc[i, j] == e_sc[i, pos[v]]
+            assert hits >= 0.999 * total, (k, hits, total)
+    # device-resident queries, same answer as the host entry point
+    d = s.search_scan_bf16(torch.from_numpy(qs).cuda(), 50, None)
+    torch.cuda.synchronize()
+    h = s.search_scan_bf16(qs, 50, None)
+    assert np.array_equal(d[0].cpu().numpy(), h[0]) and np.array_equal(d[1].cpu().numpy().view(np.uint64), h[1].view(np.uint64))
+    # other widths; a store without fp32 rows re-scores on the bf16 rows
+    for dim in (256, 768):
+        st = make_synth_store(5000, dim=dim, bf16=True)
+        q = orc.synth_rows(SYNTH_QUERY_SEED, 0, 3, dim)
+        a, b = st.search_exact(q, 50), st.search_scan_bf16(q, 50)
+        assert sum(len(set(a[0][i].tolist()) & set(b[0][i].tolist())) for i in range(3)) >= 148
+        st.close()
+    only16 = DenseStore("chunks", 20_000, dim=1024, device=0, fp32=False, bf16=True)
+    only16.append_synthetic(20_000); only16.finalize()
+    o = only16.search_scan_bf16(qs[:4], 50)
+    ref = s.search_exact(qs[:4], 50, s.filter_bitmap(call_slots=list(range(100)))[0])      # rows 0..19999 of the same corpus
+    assert sum(len(set(o[0][i].tolist()) & set(ref[0][i].tolist())) for i in range(4)) >= 198
+    only16.close()
+    with pytest.raises(DenseEngineError):
+        make_synth_store(1000, dim=1536, bf16=False).search_scan_bf16(orc.synth_rows(SYNTH_QUERY_SEED, 0, 1, 1536), 10)
+    # facade: unscoped single requests plan "ann"; with the switch on they take the bf16 scan, scoped ones never do
+    from cadence_rag_b200 import _ffi
+    monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
+    assert retrieve._group_dense_lane(s, None, None, 1) == _ffi.CDR_DENSE_LANE_SCAN_BF16
+    assert retrieve._group_dense_lane(s, None, None, 5) == _ffi.CDR_DENSE_LANE_EXACT_F32
+    assert retrieve._group_dense_lane(s, RetrieveFilters(call_ids=[1]), [1], 1) == _ffi.CDR_DENSE_LANE_EXACT_F32
+    monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 0)
+    assert retrieve._group_dense_lane(s, None, None, 1) == _ffi.CDR_DENSE_LANE_EXACT_F32
