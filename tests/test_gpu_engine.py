@@ -1165,8 +1165,12 @@ def test_fused_call_ann_groups_take_the_tensor_core_lane(monkeypatch):
             assert got["retrieved_ids"] == retrieve.retrieve_ids(eng, t, f, debug=True)["retrieved_ids"]
         # fewer than cadence_gpu_ann_min_batch requests: exact lane
         seen.clear()
+        retrieve.retrieve_ids_batch(eng, texts[:3], None)
+        assert not (seen[-1][0] or {}).get("dense_lane")
+        monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 16)
         retrieve.retrieve_ids_batch(eng, texts[:8], None)
         assert not (seen[-1][0] or {}).get("dense_lane")
+        monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 4)
         # single unscoped requests with the bf16 scan switched on: same responses
         monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
         seen.clear()
