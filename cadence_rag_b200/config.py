@@ -34,7 +34,7 @@ class Settings:
     # the lane is the faster one for the table); smaller batches use an HBM-bound scan.  4: from four unscoped requests
     # on, one pass of the tensor-core lane (0.56 ms over 1 M rows) beats two shared passes of the fp32 scan (1.17 ms)
     cadence_gpu_ann_min_batch: int = 4
-    # 1: single requests (and pairs) whose planner mode is "ann" scan the bf16 copy of the rows (half the bytes,
+    # 1: single requests whose planner mode is "ann" scan the bf16 copy of the rows (half the bytes,
     # candidate lists twice as wide, exact re-score: recall ~1.0) instead of the fp32 rows; 0: always the exact scan
     cadence_gpu_ann_bf16_scan: int = 1
 

@@ -464,8 +464,9 @@ def _group_dense_lane(store: DenseStore, filters, call_ids, n_requests: int) -> 
     if not store.has_bf16 or _dense_has_scoping(filters, call_ids):
         return _ffi.CDR_DENSE_LANE_EXACT_F32
     if n_requests < max(2, int(settings.cadence_gpu_ann_min_batch)):
-        # one or two requests: a scan of the bf16 rows per query beats one (shared) scan of the fp32 rows
-        if int(settings.cadence_gpu_ann_bf16_scan) and n_requests <= 2 and store.dim in (256, 512, 768, 1024):
+        # one request: a scan of the bf16 rows (0.35 ms per 1 M rows) beats a scan of the fp32 rows (0.57 ms); two or
+        # three share ONE fp32 scan (0.63 ms), which beats two or three bf16 scans
+        if int(settings.cadence_gpu_ann_bf16_scan) and n_requests == 1 and store.dim in (256, 512, 768, 1024):
             return _ffi.CDR_DENSE_LANE_SCAN_BF16
         return _ffi.CDR_DENSE_LANE_EXACT_F32
     if _batch_lane_is_faster(store, n_requests, store.rows):
