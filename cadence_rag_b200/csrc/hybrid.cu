@@ -123,8 +123,10 @@ extern "C" int32_t cdr_hybrid_retrieve_groups_host(
             if (filters[gi].dense_lane == CDR_DENSE_LANE_EXACT_F32) continue;
             CDR_REQUIRE(filters[gi].dense_lane == CDR_DENSE_LANE_BATCH_BF16 || filters[gi].dense_lane == CDR_DENSE_LANE_SCAN_BF16,
                         CDR_ERR_INVALID, "%s: unknown dense_lane %d in group %d", fn, filters[gi].dense_lane, gi);
-            CDR_REQUIRE(s->emb_bf16 != nullptr && dense_k <= 192 && s->dim % 256 == 0 && s->dim <= 1024, CDR_ERR_UNSUPPORTED,
-                        "%s: the bf16 lanes need bf16 rows, dense_k <= 192 and dim in {256,512,768,1024} (group %d)", fn, gi);
+            CDR_REQUIRE(s->emb_bf16 != nullptr && dense_k <= 192 && s->dim % 64 == 0, CDR_ERR_UNSUPPORTED,
+                        "%s: the bf16 lanes need bf16 rows, dense_k <= 192 and dim %% 64 == 0 (group %d)", fn, gi);
+            CDR_REQUIRE(filters[gi].dense_lane != CDR_DENSE_LANE_SCAN_BF16 || (s->dim % 256 == 0 && s->dim <= 1024),
+                        CDR_ERR_UNSUPPORTED, "%s: the bf16 scan lane needs dim in {256,512,768,1024} (group %d)", fn, gi);
         }
     }
     const bool tech = tech_index != nullptr && token_ids_host != nullptr && n_tokens_host != nullptr;

@@ -342,6 +342,44 @@ def test_batch_lane_choice_inside_mode_ann():
     assert _batch_lane_is_faster(_S, 128, 10_000_000)             # HBM-bound small batch, unfiltered
 
 
+def test_dense_lane_of_a_request_group(monkeypatch):
+    """Which kernel serves a group's dense lane inside the fused call (retrieve._group_dense_lane): scoped groups
+    always the exact scan (their mode depends on COUNT(*)); unscoped ones plan "ann" -- one request scans the bf16
+    rows, two or three share one fp32 scan, >= cadence_gpu_ann_min_batch take the tensor-core lane when it is the
+    faster one; stores without bf16 rows, other widths and the switches fall back to the exact scan."""
+    from cadence_rag_b200 import _ffi
+    from cadence_rag_b200.retrieve import RetrieveFilters, _group_dense_lane
+    EXACT, BATCH, SCAN = _ffi.CDR_DENSE_LANE_EXACT_F32, _ffi.CDR_DENSE_LANE_BATCH_BF16, _ffi.CDR_DENSE_LANE_SCAN_BF16
+
+    class _Big:
+        rows, dim, has_bf16, has_fp32 = 1_000_000, 1024, True, True
+
+    class _Small(_Big):
+        rows = 10_000                                              # 41 MB of rows: the cost model keeps the exact scan
+
+    class _NoBf16(_Big):
+        has_bf16 = False
+
+    class _Wide(_Big):
+        dim = 1536
+
+    monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 4)
+    monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
+    assert [_group_dense_lane(_Big, None, None, n) for n in (1, 2, 3, 4, 64)] == [SCAN, EXACT, EXACT, BATCH, BATCH]
+    assert _group_dense_lane(_Big, RetrieveFilters(), None, 1) == SCAN             # an empty filter object scopes nothing
+    scoped = RetrieveFilters(call_ids=["c1"])
+    assert [_group_dense_lane(_Big, scoped, ["c1"], n) for n in (1, 64)] == [EXACT, EXACT]
+    assert _group_dense_lane(_Big, RetrieveFilters(call_tags=["vip"]), None, 64) == EXACT
+    assert _group_dense_lane(_Big, RetrieveFilters(external_id="x"), [], 64) == EXACT   # resolved to no call: scoped to nothing
+    assert [_group_dense_lane(_Small, None, None, n) for n in (1, 64)] == [SCAN, EXACT]
+    assert [_group_dense_lane(_NoBf16, None, None, n) for n in (1, 64)] == [EXACT, EXACT]
+    assert [_group_dense_lane(_Wide, None, None, n) for n in (1, 2)] == [EXACT, EXACT]
+    monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 0)
+    assert _group_dense_lane(_Big, None, None, 1) == EXACT
+    monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 128)
+    assert _group_dense_lane(_Big, None, None, 64) == EXACT
+
+
 # ---------------------------------------------------------------- /retrieve response contract vs the reference's own code
 def test_retrieve_evidence_matches_reference_golden(monkeypatch, golden_dir):
     """tests/golden/reference_evidence.json holds the REFERENCE's retrieve_evidence (app/retrieve.py:392-688, run
