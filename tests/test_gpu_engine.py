@@ -325,6 +325,23 @@ def test_exact_scan_edge_semantics():
     # zero query -> every score NaN -> id order
     ids, sc, cnt = s.search_exact(np.zeros(1024, dtype=np.float32), 4)
     assert ids[0].tolist() == [row_ids[r] for r in (0, 1, 2, 3)] and np.all(np.isnan(sc[0]))
+    # the same semantics through shared reads (register groups and the deep kernel) and through the bf16-row scan:
+    # a batch mixing the query, scaled copies, a zero query and random ones
+    batch = np.stack([q, q * 3.0, np.zeros(1024, dtype=np.float32)] + [rng.standard_normal(1024).astype(np.float32) for _ in range(17)])
+    for k in (5, 50):
+        one = s.search_exact(batch, k)
+        for nq in (3, 20):
+            sh = s.search_exact(batch[:nq], k, shared=True)
+            assert np.array_equal(one[0][:nq], sh[0]) and np.array_equal(one[2][:nq], sh[2])
+            assert np.array_equal(one[1][:nq].view(np.uint64), sh[1].view(np.uint64))
+        bf = s.search_scan_bf16(batch, k)
+        assert np.array_equal(bf[2], one[2])
+        for i in range(batch.shape[0]):
+            if i == 2:                       # zero query: every score NaN, ids in id order on both lanes
+                assert bf[0][i].tolist() == one[0][i].tolist() and np.all(np.isnan(bf[1][i]))
+                continue
+            finite = ~np.isnan(one[1][i])
+            assert set(bf[0][i][finite].tolist()) == set(one[0][i][finite].tolist()), (k, i)
     s.close()
     # LIMIT larger than the table, NaN rows still returned last
     t = DenseStore("chunks", 8, dim=1024, device=0)
@@ -349,6 +366,13 @@ def test_exact_scan_adversarial_order():
     s.finalize()
     ids, sc, cnt = s.search_exact(q, 50)
     assert_matches_oracles(ids[0], sc[0], cnt[0], q, x, 50)
+    # the same corpus through the batch kernels (20 copies of the worst-case query) and the bf16-row scan
+    qs = np.stack([q] * 20)
+    sh = s.search_exact(qs, 50, shared=True)
+    for i in range(20):
+        assert np.array_equal(sh[0][i], ids[0]) and np.array_equal(sh[1][i].view(np.uint64), sc[0].view(np.uint64))
+    bf = s.search_scan_bf16(q, 50)
+    assert len(set(bf[0][0].tolist()) & set(ids[0].tolist())) >= 49
     s.close()
 
 
