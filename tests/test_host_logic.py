@@ -608,3 +608,125 @@ def test_eval_cli_and_jsonl_round_trip(tmp_path, capsys):
     assert m["recall@1"] == 0.5 and m["recall@3"] == 1.0          # (0 + 1)/2, (1 + 1)/2; query b is skipped
     assert m["mrr"] == 0.75                                        # (1/2 + 1)/2
     assert E.compute_metrics({}, {}, [5]) == {"recall@5": 0.0, "mrr": 0.0, "ndcg@5": 0.0}
+
+
+# ---------------------------------------------------------------- the fused request path above the C call (no GPU)
+class _FakeFusedStore:
+    """Stands where DenseStore stands for the fused path: `hybrid_retrieve` answers from a deterministic toy model
+    (dense score of row r for a query = -(|sum(q) * 1000 - r| mod 997), filters keep every `stride`-th row) and fuses
+    the lanes with the restated RRF, in the array layout of the real call.  It records the specs it was given."""
+    key_field, dim, has_fp32, has_bf16, rows, synthetic, device = "chunk_id", 256, True, True, 5_000_000, None, 0
+    table_name = "chunks"
+
+    def __init__(self):
+        self.calls = []
+        self.fail_dense = False
+
+    def slot_of_call(self, call_id, create=False):
+        return int(call_id)
+
+    def bits_of_tags(self, tags, create=False):
+        return 1
+
+    def _dense(self, q, spec, k):
+        stride = 1 if not spec or spec.get("call_slots") is None else 1 + len(spec["call_slots"])
+        base = int(abs(float(np.sum(q))) * 1000) % 4000
+        rows = [r for r in range(base, base + 400) if r % stride == 0]
+        rows.sort(key=lambda r: ((r * 7919) % 997, r))
+        return [(r + 1, 1.0 - ((r * 7919) % 997) / 1000.0) for r in rows[:k]]
+
+    def hybrid_retrieve(self, queries, dense_k, *, tech_index=None, token_ids=None, n_tokens=None, tech_limit=50,
+                        bm25_ids=None, bm25_offsets=None, rrf_k=60, filter_spec=None, max_out=None, filter_specs=None,
+                        group_offsets=None):
+        self.calls.append({"filter_spec": filter_spec, "filter_specs": filter_specs, "group_offsets": group_offsets,
+                           "nq": 0 if queries is None else len(queries)})
+        if self.fail_dense and queries is not None:
+            raise _ffi.DenseEngineError("device lost")
+        nq = len(bm25_offsets) - 1
+        specs = [filter_spec] * nq
+        counts = 1234
+        if filter_specs is not None:
+            specs = [filter_specs[g] for g in range(len(filter_specs)) for _ in range(group_offsets[g], group_offsets[g + 1])]
+            counts = [1000 + g for g in range(len(filter_specs))]
+        kd = dense_k if queries is not None else 0
+        width = max(1, int(np.diff(bm25_offsets).max()) + tech_limit + kd)
+        out = {"dense_ids": np.full((nq, max(kd, 1)), -1, dtype=np.int64), "dense_scores": np.zeros((nq, max(kd, 1))),
+               "dense_n": np.zeros(nq, dtype=np.int32), "tech_ids": np.full((nq, tech_limit), -1, dtype=np.int64),
+               "tech_n": np.zeros(nq, dtype=np.int32), "fused_ids": np.full((nq, width), -1, dtype=np.int64),
+               "fused_scores": np.zeros((nq, width)), "fused_mask": np.zeros((nq, width), dtype=np.uint32),
+               "fused_n": np.zeros(nq, dtype=np.int32), "count": counts}
+        for i in range(nq):
+            lanes = {"bm25": [{"chunk_id": int(v)} for v in bm25_ids[bm25_offsets[i]:bm25_offsets[i + 1]]], "tech_tokens": []}
+            if queries is not None:
+                hits = self._dense(queries[i], specs[i], dense_k)
+                out["dense_n"][i] = len(hits)
+                for j, (cid, sc) in enumerate(hits):
+                    out["dense_ids"][i, j], out["dense_scores"][i, j] = cid, sc
+                lanes["dense"] = [{"chunk_id": cid} for cid, _ in hits]
+            fused = ports.rrf_merge(lanes, "chunk_id", rrf_k)
+            out["fused_n"][i] = len(fused)
+            for j, (row, hit, sc) in enumerate(fused):
+                out["fused_ids"][i, j], out["fused_scores"][i, j] = row["chunk_id"], sc
+                out["fused_mask"][i, j] = sum(1 << l for l, name in enumerate(("bm25", "tech_tokens", "dense")) if name in hit)
+        return out
+
+
+def test_fused_request_path_above_the_c_call(monkeypatch):
+    """Everything `retrieve_ids` / `retrieve_ids_batch` do around the fused C call, against a toy store: the dict-free
+    response (no debug) equals the row-dict response, per-request filters are grouped and the responses return in
+    request order, unscoped groups get their dense lane, the dense lane fails open on both kinds of error."""
+    monkeypatch.setattr(settings, "embeddings_dim", 256)
+    monkeypatch.setattr(settings, "embeddings_base_url", "http://embedder")
+    monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 4)
+    monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
+    store = _FakeFusedStore()
+    eng = retrieve.DenseEngine()
+    eng.stores["chunks"] = store
+    vec = lambda t: [float((sum(map(ord, t)) * (j + 3)) % 17) / 16.0 for j in range(256)]     # noqa: E731
+    embeddings.set_embedder(lambda batch: embeddings.EmbeddingResult(vectors=[vec(t) for t in batch], model="toy"))
+    bm25 = [{"chunk_id": 11, "text": "a"}, {"chunk_id": 3012, "text": "b"}]
+    try:
+        scoped = RetrieveFilters(call_ids=[1, 2])
+        texts = [f"question {i}" for i in range(9)]
+        filt = [None, scoped, None, None, scoped, None, RetrieveFilters(call_ids=[7]), None, None]
+        full = [retrieve.retrieve_ids(eng, t, f, bm25_chunks=bm25 if i % 2 else (), debug=True) for i, (t, f) in enumerate(zip(texts, filt))]
+        assert all(c["nq"] == 1 for c in store.calls)
+        lanes = [(c["filter_spec"] or {}).get("dense_lane", 0) for c in store.calls]
+        assert lanes == [(_ffi.CDR_DENSE_LANE_SCAN_BF16 if f is None else 0) for f in filt]       # single unscoped: bf16 scan
+        lean = [retrieve.retrieve_ids(eng, t, f, bm25_chunks=bm25 if i % 2 else ()) for i, (t, f) in enumerate(zip(texts, filt))]
+        assert lean == [{"retrieved_ids": r["retrieved_ids"]} for r in full]
+        assert full[1]["debug"]["dense"]["modes"]["chunks"] == "exact" and full[0]["debug"]["dense"]["modes"]["chunks"] == "ann"
+        assert full[1]["debug"]["dense"]["candidate_rows"]["chunks"] == 1234
+        assert full[1]["debug"]["lanes"]["chunks"]["bm25"][0] == {"chunk_id": 11, "rank": 1, "score": None}
+        # one fused call for all nine: three groups (unscoped x6 -> tensor-core lane, the two scoped filters -> exact)
+        store.calls.clear()
+        many = retrieve.retrieve_ids_batch(eng, texts, filt, bm25_chunks=[bm25 if i % 2 else [] for i in range(9)], debug=True)
+        assert len(store.calls) == 1 and store.calls[0]["nq"] == 9
+        call = store.calls[0]
+        assert call["group_offsets"] == [0, 6, 8, 9]
+        assert [(s or {}).get("dense_lane", 0) for s in call["filter_specs"]] == [_ffi.CDR_DENSE_LANE_BATCH_BF16, 0, 0]
+        assert [(s or {}).get("call_slots") for s in call["filter_specs"]] == [None, [1, 2], [7]]
+        for i in range(9):
+            assert many[i]["retrieved_ids"] == full[i]["retrieved_ids"], i
+            assert many[i]["debug"]["lanes"] == full[i]["debug"]["lanes"] and many[i]["debug"]["fused"] == full[i]["debug"]["fused"]
+        assert [m["debug"]["dense"]["candidate_rows"]["chunks"] for m in many] == [1000, 1001, 1000, 1000, 1001, 1000, 1002, 1000, 1000]
+        assert retrieve.retrieve_ids_batch(eng, texts, filt, bm25_chunks=[bm25 if i % 2 else [] for i in range(9)]) == lean
+        # blank queries keep their slot
+        mixed = retrieve.retrieve_ids_batch(eng, ["  ", texts[0], ""], None)
+        assert mixed[0] == {"retrieved_ids": []} and mixed[2] == {"retrieved_ids": []} and mixed[1] == lean[0]
+        # the embedding service fails: lexical-only, dense_error carried in the debug payload
+        def boom(batch):
+            raise embeddings.EmbeddingClientError("embedding HTTP request failed: down")
+        embeddings.set_embedder(boom)
+        off = retrieve.retrieve_ids(eng, texts[1], None, bm25_chunks=bm25, debug=True)
+        assert off["retrieved_ids"] == ["chunk:11", "chunk:3012"] and off["debug"]["dense"]["enabled"] is False
+        assert "down" in off["debug"]["dense"]["error"]
+        assert retrieve.retrieve_ids(eng, texts[1], None, bm25_chunks=bm25) == {"retrieved_ids": ["chunk:11", "chunk:3012"]}
+        # the engine fails on the dense lane: same fail-open, for the one-request and the batch form
+        embeddings.set_embedder(lambda batch: embeddings.EmbeddingResult(vectors=[vec(t) for t in batch], model="toy"))
+        store.fail_dense = True
+        off = retrieve.retrieve_ids(eng, texts[1], None, bm25_chunks=bm25, debug=True)
+        assert off["retrieved_ids"] == ["chunk:11", "chunk:3012"] and off["debug"]["dense"]["error"] == "device lost"
+        assert retrieve.retrieve_ids_batch(eng, texts[:2], None, bm25_chunks=[bm25, []]) == [{"retrieved_ids": ["chunk:11", "chunk:3012"]}, {"retrieved_ids": []}]
+    finally:
+        embeddings.set_embedder(None)
