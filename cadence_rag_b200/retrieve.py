@@ -543,9 +543,9 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
     fused_ids, fused_scores, fused_n = res["fused_ids"].tolist(), res["fused_scores"].tolist(), res["fused_n"].tolist()
     if not ids_only:
         tech_ids, tech_n, fused_mask = res["tech_ids"].tolist(), res["tech_n"].tolist(), res["fused_mask"].tolist()
+        hit_sets = [frozenset(_LANE_NAMES[l] for l in range(n_lanes) if (m >> l) & 1) for m in range(1 << n_lanes)]
     if q32 is not None and not ids_only:
         dense_ids, dense_scores, dense_n = res["dense_ids"].tolist(), res["dense_scores"].tolist(), res["dense_n"].tolist()
-    hit_sets = [frozenset(_LANE_NAMES[l] for l in range(n_lanes) if (m >> l) & 1) for m in range(1 << n_lanes)]
     out_pos = []
     for qi in range(nq if not ids_only else 0):
         # the ids_only response needs ids, ranks and scores only: the SELECT-list columns (call_id, payload) are
