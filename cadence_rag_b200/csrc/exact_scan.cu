@@ -18,6 +18,9 @@
 //   epilogue      : each warp sorts its list (register bitonic network), the 8 lists are
 //                   merged pairwise through shared memory, and the CTA writes its KC best keys.
 // The corpus is read exactly once per query; nothing but KC keys per CTA goes back to HBM.
+// Variants of the same kernel (template parameters QPC / BF, see ScanSmem): shared reads for batches (3 queries in
+// registers; 16 queries per CTA as register tiles), the gather launch for selective filters, and the candidate pass
+// of the single-query "ann" lane over the bf16 rows.
 //
 // Algorithmic bytes per query: n_rows * dim * 4.
 #include "common.cuh"
@@ -61,13 +64,13 @@ struct ScanParams {
 // takes ~all of the unified L1/shared memory for its tile ring the spills go to L2 (measured: 1.26x instead of
 // 4x).  3 queries compile to 168 registers with no spills.
 //
-// kDeepQPC = "deep shared reads" for batches of >= 4 exact requests: the roles swap -- a warp keeps its RPW rows of
-// the tile in registers (64 for 2 rows x 1024 dims) and streams the QUERIES from shared memory, 8 of them per
-// corpus pass.  Shared-memory bandwidth is then the limit ((RPW + QPC) x 4 KB of LDS.128 per warp and tile:
-// ~160 clk per row against ~123 clk per row of HBM arrival), the top-k state of the 8 queries lives in shared
-// memory too (thresholds are read back per candidate, pushes are rare), and the tile ring shrinks to 2 stages --
-// enough, because a stage is released as soon as its rows are in registers.  Same lanes, same FMA order, same
-// reduction => same bits as one scan per query.
+// kDeepQPC = "deep shared reads" for whole groups of 16 exact requests (and tails of >= 10): a register-tiled
+// kernel.  The 16 queries of the CTA are staged once in shared memory (64 KB); the 8 consumer warps form 4 row groups
+// x 2 query halves, and a warp keeps the 4 rows x 8 queries x 2 partial sums of its part of the tile in registers
+// while it streams both operands from shared memory: 4 + 8 LDS.128 feed 4 x 8 x 4 FMAs per 128-byte column step (12
+// shared-memory wavefronts per (row, query)).  The top-k state of a warp's 8 queries lives in shared memory too
+// (thresholds are read back per candidate, pushes are rare), the tile ring shrinks to 2 stages, 168 registers, no
+// spills.  Same lanes, same FMA order, same reduction => same bits as one scan per query.
 constexpr int kSharedQPC = 3;
 constexpr int kDeepQPC = 16;
 // Shape of the deep kernel: 8 consumer warps as 4 row groups x kDeepQSplit query halves; a warp owns 4 rows of the
