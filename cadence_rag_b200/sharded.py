@@ -9,8 +9,10 @@ index over those rows and a `ShardedSearcher`.  Per request and table:
   dense lane  local K1 / K2 scan, then the exchange + merge of `ShardedSearcher` (K4p peer-memory kernel
               over NVLink, or NCCL all-gather + K4): every rank ends with the global top-k
   tech lane   local top-`limit` in the lane's order (call_started_at DESC, id ASC); the (started_at, id)
-              pairs of all ranks are gathered and merged by the same key
-  rows        every rank contributes the row dicts (call_id, payload) of the ids it owns
+              pairs of all ranks travel with the local counts in ONE small object all-gather per table and
+              are merged by the same key
+  rows        the ids_only response needs ids and scores only; payload columns stay on the owning rank
+              (`_owned_rows`)
   fusion      the bit-exact RRF kernel (K5) and the ids_only combine, on every rank (inputs are identical)
 
 The result equals `retrieve_ids` over the unsharded corpus (`tests/test_gpu_sharded.py`).
@@ -81,49 +83,44 @@ def _owned_rows(store, ids: Sequence[int]) -> Dict[int, Dict[str, Any]]:
 
 def _sharded_table(eng: ShardedEngine, conn, table: str, q32: Optional[np.ndarray], tech_tokens: Sequence[str],
                    filters, call_ids, dense_limit: int, tech_limit: int) -> Tuple[List[Dict[str, Any]], List[Dict[str, Any]], int]:
-    """(tech rows, dense rows, COUNT(*)) of one table, identical on every rank."""
+    """(tech rows, dense rows, COUNT(*)) of one table, identical on every rank.  Rows carry what the ids_only
+    response needs -- the id, and the score on the dense lane; payload columns stay on the owning rank
+    (`_owned_rows` fetches them when a caller wants them).  Host traffic per table: ONE small object all-gather
+    (the tech lane's (call_started_at, id) candidates + the local COUNT(*)); the dense lane's exchange runs on the
+    devices (`ShardedSearcher`)."""
     import torch
     import torch.distributed as dist
     store = conn.store(table)
     searcher = eng.searchers[table]
     key = store.key_field
-    # ---- tech lane: local winners with their sort key, merged across ranks
+    dense = q32 is not None
+    if dense:
+        want = max(1, int(R.settings.embeddings_dim))
+        if q32.shape[0] != want or q32.shape[0] != store.dim:
+            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[0]}")
+    # ---- local halves: tech-lane winners with their sort key, filter bitmap + local COUNT(*)
     local_tech = R._fetch_tech(conn, table, tech_tokens, filters, call_ids, tech_limit)
     cols = store.host_columns()
     keyed = []
     for row in local_tech:
         p = int(np.searchsorted(cols["ids"], row[key]))
-        keyed.append((-int(cols["started_at"][p]), int(row[key]), row))
-    merged = sorted((item for part in _gather_objects(keyed, eng) for item in part), key=lambda t: (t[0], t[1]))
-    tech_rows = [item[2] for item in merged[:tech_limit]]
-    # ---- dense lane
+        keyed.append((-int(cols["started_at"][p]), int(row[key])))
+    allow, local_count = R._filter_bitmap(conn, table, filters, call_ids) if dense else (None, 0)
+    # ---- one exchange of host objects: merge the tech lane by its ORDER BY key, sum the counts
+    parts = _gather_objects((keyed, int(local_count)), eng)
+    merged = sorted(pair for part, _c in parts for pair in part)
+    tech_rows = [{key: item[1]} for item in merged[:tech_limit]]
+    count = sum(int(c) for _p, c in parts)
+    # ---- dense lane: local scan, device-side exchange + merge
     dense_rows: List[Dict[str, Any]] = []
-    count = 0
-    if q32 is not None:
-        want = max(1, int(R.settings.embeddings_dim))
-        if q32.shape[0] != want or q32.shape[0] != store.dim:
-            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[0]}")
-        allow, local_count = R._filter_bitmap(conn, table, filters, call_ids)
+    if dense and count > 0:
         on_gpu = eng.world == 1 or dist.get_backend(eng.group) == "nccl"      # gloo: the CPU test tier
         dev = f"cuda:{store.device}" if on_gpu else "cpu"
-        total = torch.tensor([local_count], dtype=torch.int64, device=dev)
-        if eng.world > 1:
-            dist.all_reduce(total, group=eng.group)
-        count = int(total.item())
-        if count > 0:
-            qd = torch.from_numpy(q32[None, :]).to(dev)
-            ids, scores, n = searcher.search(qd, dense_limit, allow, mode="exact")
-            m = int(n[0].item())
-            g_ids = ids[0, :m].cpu().numpy()
-            g_sc = scores[0, :m].cpu().numpy()
-            owned: Dict[int, Dict[str, Any]] = {}
-            for part in _gather_objects(_owned_rows(store, g_ids.tolist()), eng):
-                owned.update(part)
-            for i, sc in zip(g_ids.tolist(), g_sc.tolist()):
-                row = dict(owned[i])
-                row["score"] = sc
-                dense_rows.append(row)
-    return tech_rows, dense_rows, count
+        qd = torch.from_numpy(q32[None, :]).to(dev)
+        ids, scores, n = searcher.search(qd, dense_limit, allow, mode="exact")
+        m = int(n[0].item())
+        dense_rows = [{key: i, "score": sc} for i, sc in zip(ids[0, :m].tolist(), scores[0, :m].tolist())]
+    return tech_rows, dense_rows, count if dense else 0
 
 
 def sharded_retrieve_ids(eng: ShardedEngine, query: str, filters: Optional[R.RetrieveFilters] = None,
