@@ -27,6 +27,7 @@
 
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <mutex>
 
 namespace {
 
@@ -1153,18 +1154,25 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     using L = ScanSmem<J, RPW, NPL, QPC, BF>;
     constexpr int KC = L::KC;
     // per-device launch configuration (the smem opt-in attribute is per device)
+    // (stores on the same device have different mutexes: the first-use initialisation takes its own lock)
+    static std::mutex init_mu;
     static int stages_by_dev[64] = {0};
     static size_t smem_by_dev[64] = {0};
-    int &stages = stages_by_dev[s->device & 63];
-    size_t &smem = smem_by_dev[s->device & 63];
-    if (stages == 0) {
-        int dev_smem = 0;
-        CDR_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
-        int st_n = L::max_stages((size_t)dev_smem);
-        smem = L::bytes(st_n);
-        CDR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<J, RPW, NPL, QPC, BF>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stages = st_n;
+    int stages;
+    size_t smem;
+    {
+        std::lock_guard<std::mutex> init_lock(init_mu);
+        if (stages_by_dev[s->device & 63] == 0) {
+            int dev_smem = 0;
+            CDR_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+            const int st_n = L::max_stages((size_t)dev_smem);
+            CDR_CUDA(cudaFuncSetAttribute(exact_scan_kernel<J, RPW, NPL, QPC, BF>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes(st_n)));
+            smem_by_dev[s->device & 63] = L::bytes(st_n);
+            stages_by_dev[s->device & 63] = st_n;
+        }
+        stages = stages_by_dev[s->device & 63];
+        smem = smem_by_dev[s->device & 63];
     }
     const int64_t n_tiles = (s->n_rows + L::TR - 1) / L::TR;
     const int n_groups = (nq + QPC - 1) / QPC;

@@ -723,13 +723,16 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
     rc = make_map(&map_x, s->emb_bf16, s->n_rows, dim, kBlockN / cluster);
     if (rc != CDR_OK) return rc;
 
+    static std::mutex attr_mu;
     static bool attr_done[64] = {false};
+    std::unique_lock<std::mutex> attr_lock(attr_mu);
     if (!attr_done[s->device & 63]) {
         CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr_done[s->device & 63] = true;
     }
+    attr_lock.unlock();
 
     GemmParams p;
     p.tau = tau;

@@ -19,6 +19,8 @@
 // same order on every rank and on one stream per rank.
 #include "common.cuh"
 
+#include <mutex>
+
 #include <cstring>
 
 struct cdr_peer_group {
@@ -231,10 +233,14 @@ extern "C" int32_t cdr_peer_exchange_merge(cdr_peer_group *pg, const double *sco
                 pg->max_k);
     DeviceGuard g(pg->device);
     const size_t smem = (size_t)pg->world * k * 16;
-    static bool attr_set[64] = {false};
-    if (!attr_set[pg->device & 63] && smem > 48 * 1024) {
-        CDR_CUDA(cudaFuncSetAttribute(peer_publish_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-        attr_set[pg->device & 63] = true;
+    {
+        static std::mutex attr_mu;
+        static bool attr_set[64] = {false};
+        std::lock_guard<std::mutex> attr_lock(attr_mu);
+        if (!attr_set[pg->device & 63] && smem > 48 * 1024) {
+            CDR_CUDA(cudaFuncSetAttribute(peer_publish_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+            attr_set[pg->device & 63] = true;
+        }
     }
     for (int q0 = 0; q0 < nq; q0 += pg->max_nq) {
         const int m = nq - q0 < pg->max_nq ? nq - q0 : pg->max_nq;

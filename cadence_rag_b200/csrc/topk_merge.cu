@@ -6,6 +6,8 @@
 // One CTA per query; R*k <= 4096 entries ranked by counting in shared memory.
 #include "common.cuh"
 
+#include <mutex>
+
 namespace {
 
 constexpr int kMergeMax = 4096;
@@ -76,11 +78,18 @@ extern "C" int32_t cdr_topk_merge(const double *scores_dev, const int64_t *ids_d
                 "cdr_topk_merge: need R >= 1, k >= 1, R*k <= %d (got R=%d k=%d)", kMergeMax, R, k);
     if (nq == 0) return CDR_OK;
     const size_t smem = (size_t)R * k * 16;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        CDR_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kMergeMax * 16));
-        attr_set = true;
+    {
+        // the opt-in is per device: one flag per device of the calling thread, set under a lock
+        static std::mutex attr_mu;
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        CDR_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> attr_lock(attr_mu);
+        if (!attr_set[dev & 63] && smem > 48 * 1024) {
+            CDR_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kMergeMax * 16));
+            attr_set[dev & 63] = true;
+        }
     }
     MergeParams p{scores_dev, ids_dev, n_dev, R, nq, k, out_score_dev, out_id_dev, out_n_dev};
     topk_merge_kernel<<<nq, 256, smem, (cudaStream_t)stream>>>(p);
