@@ -730,3 +730,48 @@ def test_fused_request_path_above_the_c_call(monkeypatch):
         assert retrieve.retrieve_ids_batch(eng, texts[:2], None, bm25_chunks=[bm25, []]) == [{"retrieved_ids": ["chunk:11", "chunk:3012"]}, {"retrieved_ids": []}]
     finally:
         embeddings.set_embedder(None)
+
+
+def test_request_batcher_over_the_fused_path(monkeypatch):
+    """RequestBatcher with the real retrieve_ids_batch underneath (toy store, no GPU): 8 client threads with mixed
+    filters get exactly the one-request responses, requests were served in shared fused calls, and every call's
+    groups are consistent (offsets cover the batch, one spec per group)."""
+    import threading
+    monkeypatch.setattr(settings, "embeddings_dim", 256)
+    monkeypatch.setattr(settings, "embeddings_base_url", "http://embedder")
+    store = _FakeFusedStore()
+    eng = retrieve.DenseEngine()
+    eng.stores["chunks"] = store
+    vec = lambda t: [float((sum(map(ord, t)) * (j + 3)) % 17) / 16.0 for j in range(256)]     # noqa: E731
+    embeddings.set_embedder(lambda batch: embeddings.EmbeddingResult(vectors=[vec(t) for t in batch], model="toy"))
+    filters = [None, RetrieveFilters(call_ids=[1, 2]), RetrieveFilters(call_ids=[7]), None]
+    texts = [f"client question {i}" for i in range(12)]
+    try:
+        want = {(i, j): retrieve.retrieve_ids(eng, texts[i], filters[j], debug=True)["retrieved_ids"]
+                for i in range(12) for j in range(4)}
+        store.calls.clear()
+        batcher = retrieve.RequestBatcher(eng, max_batch=16, max_wait_s=5e-3)
+        got, errs = {}, []
+
+        def client(t):
+            try:
+                for r in range(6):
+                    i, j = (t * 5 + r) % 12, (t + r) % 4
+                    got[(t, r)] = ((i, j), batcher.retrieve_ids(texts[i], filters[j])["retrieved_ids"])
+            except Exception as exc:   # noqa: BLE001
+                errs.append(repr(exc))
+        threads = [threading.Thread(target=client, args=(t,)) for t in range(8)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        batcher.close()
+        assert not errs, errs
+        assert len(got) == 48 and all(ids == want[key] for key, ids in got.values())
+        assert batcher.requests_served == 48 and batcher.batches_served < 48
+        assert sum(c["nq"] for c in store.calls) == 48
+        for c in store.calls:
+            assert c["filter_specs"] is not None and c["group_offsets"][0] == 0 and c["group_offsets"][-1] == c["nq"]
+            assert len(c["filter_specs"]) == len(c["group_offsets"]) - 1 <= 3
+    finally:
+        embeddings.set_embedder(None)
