@@ -44,15 +44,21 @@ _DOMAIN_SPECS = (
 )
 _PATTERNS = tuple(re.compile(p, f) for p, f in _PATTERN_SPECS)
 _DOMAIN = tuple((re.compile(p, re.IGNORECASE), canon) for canon, p in _DOMAIN_SPECS)
+# one-shot prechecks: a text that matches none of the alternatives matches none of the patterns, so plain-language
+# queries (the common case) cost two searches instead of thirty-two
+_ANY_PATTERN = re.compile("|".join(f"(?i:{p})" if f & re.IGNORECASE else f"(?:{p})" for p, f in _PATTERN_SPECS))
+_ANY_DOMAIN = re.compile("|".join(f"(?:{p})" for _canon, p in _DOMAIN_SPECS), re.IGNORECASE)
 
 
 def extract_tech_tokens(text: str) -> List[str]:
     """Tokens of the exact-match lane: regex hits, then domain canonicals; stripped, empty dropped,
     first occurrence kept under case-insensitive comparison, original casing preserved."""
     found: List[str] = []
-    for rx in _PATTERNS:
-        found += rx.findall(text)
-    found += [canon for rx, canon in _DOMAIN if rx.search(text)]
+    if _ANY_PATTERN.search(text):
+        for rx in _PATTERNS:
+            found += rx.findall(text)
+    if _ANY_DOMAIN.search(text):
+        found += [canon for rx, canon in _DOMAIN if rx.search(text)]
     out: Dict[str, str] = {}
     for tok in found:
         tok = tok.strip()
