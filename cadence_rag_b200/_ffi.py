@@ -75,6 +75,7 @@ SIGNATURES = {
     "cdr_store_info": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i32), ctypes.POINTER(_u32),
                               ctypes.POINTER(_i64), ctypes.POINTER(_i32)]),
     "cdr_store_read_rows": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cdr_store_copy_rows_device": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "cdr_store_read_valid": (_i32, [_vp, _i64, _i64, _vp]),
     "cdr_synth_rows": (_i32, [_vp, _u64, _i64, _i64, _i32, _vp]),
     "cdr_filter_build": (_i32, [_vp, _vp, _i64, _i32, _i64, _i32, _i64, _i32, _u64, _vp,

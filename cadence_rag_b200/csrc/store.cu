@@ -628,6 +628,30 @@ extern "C" int32_t cdr_store_read_rows(cdr_store *s, int64_t first_row, int64_t 
     return CDR_OK;
 }
 
+extern "C" int32_t cdr_store_copy_rows_device(cdr_store *s, int64_t first_row, int64_t n, float *out_f32_dev,
+                                              uint16_t *out_bf16_dev, void *stream)
+{
+    CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "cdr_store_copy_rows_device: store is NULL");
+    CDR_REQUIRE(first_row >= 0 && n >= 0 && first_row + n <= s->n_rows, CDR_ERR_INVALID,
+                "cdr_store_copy_rows_device: range [%lld,+%lld) outside [0,%lld)", (long long)first_row,
+                (long long)n, (long long)s->n_rows);
+    if (n == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t d = (size_t)s->dim;
+    if (out_f32_dev) {
+        CDR_REQUIRE(s->emb_f32 != nullptr, CDR_ERR_STATE, "cdr_store_copy_rows_device: no fp32 rows resident");
+        CDR_CUDA(cudaMemcpyAsync(out_f32_dev, s->emb_f32 + (size_t)first_row * d, (size_t)n * d * 4,
+                                 cudaMemcpyDeviceToDevice, st));
+    }
+    if (out_bf16_dev) {
+        CDR_REQUIRE(s->emb_bf16 != nullptr, CDR_ERR_STATE, "cdr_store_copy_rows_device: no bf16 rows resident");
+        CDR_CUDA(cudaMemcpyAsync(out_bf16_dev, s->emb_bf16 + (size_t)first_row * d, (size_t)n * d * 2,
+                                 cudaMemcpyDeviceToDevice, st));
+    }
+    return CDR_OK;
+}
+
 extern "C" int32_t cdr_store_read_valid(cdr_store *s, int64_t first_row, int64_t n, uint8_t *out_valid_u8_host)
 {
     CDR_REQUIRE(s != nullptr && out_valid_u8_host != nullptr, CDR_ERR_INVALID, "cdr_store_read_valid: NULL argument");

@@ -392,6 +392,19 @@ class DenseStore:
         _ffi.check(_ffi.lib().cdr_store_read_rows(self.handle, first_row, n, *ptrs), "cdr_store_read_rows")
         return out
 
+    def read_rows_device(self, first_row: int, n: int, what: str = "f32"):
+        """Rows [first_row, first_row+n) as stored, copied into a new CUDA tensor on the current stream
+        (``cdr_store_copy_rows_device``): "f32" -> float32 [n, dim], "bf16" -> bfloat16 [n, dim]."""
+        torch = _torch()
+        if what not in ("f32", "bf16"):
+            raise ValueError(f"read_rows_device: {what!r}: expected 'f32' or 'bf16'")
+        out = torch.empty((n, self.dim), dtype=torch.float32 if what == "f32" else torch.bfloat16,
+                          device=f"cuda:{self.device}")
+        _ffi.check(_ffi.lib().cdr_store_copy_rows_device(
+            self.handle, first_row, n, _ffi.ptr(out) if what == "f32" else None,
+            _ffi.ptr(out) if what == "bf16" else None, self._stream()), "cdr_store_copy_rows_device")
+        return out
+
     def host_columns(self) -> Dict[str, np.ndarray]:
         """ids / call_slot / started_at / tag_bits of all rows on the host (cached; lexical lane)."""
         if self._host_cols is None:

@@ -117,6 +117,12 @@ int32_t cdr_store_read_rows(cdr_store *s, int64_t first_row, int64_t n, float *o
                             int32_t *out_call_slot_host, int64_t *out_started_at_host,
                             uint64_t *out_tag_bits_host, float *out_inv_norm_host);
 
+/* The same for device destinations (checkers that recompute scores on the GPU without a host round trip, e.g. the
+ * independent matmul oracle of bench.py): rows [first_row, first_row+n) as stored -- fp32 and / or the normalised
+ * bf16 copy -- into caller-owned DEVICE buffers, asynchronously on `stream`.  Either out pointer may be NULL. */
+int32_t cdr_store_copy_rows_device(cdr_store *s, int64_t first_row, int64_t n, float *out_f32_dev,
+                                   uint16_t *out_bf16_dev, void *stream);
+
 /* Validity flags (embedding IS NOT NULL) of rows [first_row, first_row+n) as bytes (snapshots). */
 int32_t cdr_store_read_valid(cdr_store *s, int64_t first_row, int64_t n, uint8_t *out_valid_u8_host);
 
