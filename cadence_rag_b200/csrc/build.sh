@@ -20,6 +20,6 @@ for f in abi store filter exact_scan rrf topk_merge gemm_topk tech_lane hybrid p
     fi
 done
 for p in $pids; do wait $p; done
-$NVCC -shared -o "$OUT" "$OBJ"/abi.o "$OBJ"/store.o "$OBJ"/filter.o "$OBJ"/exact_scan.o "$OBJ"/rrf.o \
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ"/abi.o "$OBJ"/store.o "$OBJ"/filter.o "$OBJ"/exact_scan.o "$OBJ"/rrf.o \
     "$OBJ"/topk_merge.o "$OBJ"/gemm_topk.o "$OBJ"/tech_lane.o "$OBJ"/hybrid.o "$OBJ"/peer.o -ccbin /usr/bin/g++
 echo "built $OUT"

@@ -105,8 +105,15 @@ struct DeviceGuard {
 // K1 + finalize on `st` (exact_scan.cu).  share_reads: score every streamed tile against 3 queries per CTA
 // (batches of concurrent exact requests); false = one scan of the corpus per query.  Same bits either way.
 // Single-query "ann" lane (exact_scan.cu): candidate pass over the bf16 rows, exact re-score.  Store mutex held by the caller.
+// q_index / q_count: the conditional re-run form (see cdr_exact_scan_redo_launch), both null for a plain launch.
 int cdr_bf16_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
-                         double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st);
+                         double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st,
+                         const int *q_index = nullptr, const int *q_count = nullptr);
+// Re-run queries q_index[0 .. min(*q_count, n_slots)) (count on the device) on the exact fp32 lane, results written to
+// the queries' own output rows; with a zero count the launches exit at once.
+int cdr_exact_scan_redo_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int n_slots, const uint32_t *allow,
+                               int k, double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st,
+                               const int *q_index, const int *q_count);
 // K2 (gemm_topk.cu) with the store mutex held by the caller: nq <= 16384, k <= 192, bf16 rows resident.
 int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, int k, const uint32_t *allow_dev,
                           double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev, cudaStream_t st);

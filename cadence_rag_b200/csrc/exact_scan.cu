@@ -54,6 +54,11 @@ struct ScanParams {
     uint32_t list_cap;
     int lists_per_query;      // per-query stride of cta_keys in lists (gather CTAs + full CTAs)
     int list_offset;          // first list of this launch inside a query's block
+    // conditional re-run of a few queries of a batch (K2's overflow path, QPC == 1 only): the launch serves
+    // min(*q_count, nq) SLOTS, slot g scans for query q_index[g] and writes the lists of slot g; with a zero count
+    // every CTA exits at once.  Both null = the plain launch (slot == query, nq of them).
+    const int *q_index;
+    const int *q_count;
 };
 
 // Dynamic shared memory carve-up (computed identically on host and device).
@@ -136,8 +141,17 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
     long long *stage_tile = reinterpret_cast<long long *>(empty_bar + kMaxStages);   // tile held by a stage, -1 = end
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.y * QPC;                                  // first query of this CTA's group
-    const int nqv = p.nq - q0 < QPC ? p.nq - q0 : QPC;                // valid queries in the group
+    // A CTA is persistent over query groups: group g = blockIdx.y, blockIdx.y + gridDim.y, ...  The stage ring
+    // (counter `it` below, advanced identically by the producer and the consumers, end-of-stream stages included)
+    // runs on across groups, so the producer prefetches the next group's first tiles while the consumers sort and
+    // merge the lists of the current one.
+    int nq_eff = p.nq;
+    if (p.q_count != nullptr) {
+        const int c = *p.q_count;                     // written earlier on the stream
+        nq_eff = c < p.nq ? c : p.nq;
+    }
+    const int n_groups = (nq_eff + QPC - 1) / QPC;
+    if ((int)blockIdx.y >= n_groups) return;
     const int64_t G = gridDim.x;
     const bool gather = p.row_list != nullptr;
     int64_t n_tiles = p.n_tiles;
@@ -147,10 +161,14 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
         const bool list_serves = n_listed <= p.list_cap;
         if (gather != list_serves) {                  // the other launch of the pair does the work: empty lists
             if (warp == 0) {
-                for (int u = 0; u < nqv; ++u) {
-                    uint64_t *out = p.cta_keys + ((size_t)(q0 + u) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
+                for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
+                    const int gq0 = g * QPC;
+                    const int gn = nq_eff - gq0 < QPC ? nq_eff - gq0 : QPC;
+                    for (int u = 0; u < gn; ++u) {
+                        uint64_t *out = p.cta_keys + ((size_t)(gq0 + u) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = CDR_EMPTY_KEY;
+                        for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = CDR_EMPTY_KEY;
+                    }
                 }
             }
             return;
@@ -179,15 +197,17 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
         // The whole warp runs the loop: lane 0 draws tiles and arms the barrier, lanes 0..TR-1 each fetch one
         // list entry and issue that row's bulk copy, so the TR copies of a tile are issued in parallel.
         static_assert(TR <= 32, "one lane per row of a tile");
+        uint32_t it = 0;
+        for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
         int64_t next_dyn = -1;
-        for (int64_t i = 0;; ++i) {
-            const int s = (int)(i % S);
-            const uint32_t ph = (uint32_t)((i / S) & 1);
+        for (int64_t i = 0;; ++i, ++it) {
+            const int s = (int)(it % (uint32_t)S);
+            const uint32_t ph = (it / (uint32_t)S) & 1u;
             int64_t tile = blockIdx.x + i * G;
             if (dynamic && i >= S) tile = next_dyn;
             if (dynamic && i + 1 >= S) {
                 unsigned int t = 0;
-                if (lane == 0) t = atomicAdd(&p.tile_ctr[blockIdx.y], 1u);
+                if (lane == 0) t = atomicAdd(&p.tile_ctr[g], 1u);
                 next_dyn = (int64_t)S * G + __shfl_sync(0xffffffffu, t, 0);
             }
             // the list entry of this lane's row can be fetched while the stage is still busy
@@ -201,6 +221,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                     stage_tile[s] = -1;
                     mbar_arrive(&full_bar[s]);
                 }
+                ++it;
                 break;
             }
             if (lane == 0) {
@@ -213,21 +234,25 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                          reinterpret_cast<const unsigned char *>(p.rows) + (size_t)my_row * L::kRowBytes,
                          (uint32_t)L::kRowBytes, &full_bar[s]);
         }
+        }
     } else if (warp == CW) {
         // ------------------------------------------------------------------ producer
         if (lane == 0) {
+            uint32_t it = 0;
+            for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
             int64_t next_dyn = -1;
-            for (int64_t i = 0;; ++i) {
-                const int s = (int)(i % S);
-                const uint32_t ph = (uint32_t)((i / S) & 1);
+            for (int64_t i = 0;; ++i, ++it) {
+                const int s = (int)(it % (uint32_t)S);
+                const uint32_t ph = (it / (uint32_t)S) & 1u;
                 int64_t tile = blockIdx.x + i * G;
                 if (dynamic && i >= S) tile = next_dyn;
                 // draw the next tile now: the atomic's round trip overlaps the wait for a free stage
-                if (dynamic && i + 1 >= S) next_dyn = (int64_t)S * G + atomicAdd(&p.tile_ctr[blockIdx.y], 1u);
+                if (dynamic && i + 1 >= S) next_dyn = (int64_t)S * G + atomicAdd(&p.tile_ctr[g], 1u);
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 if (tile >= n_tiles) {
                     stage_tile[s] = -1;
                     mbar_arrive(&full_bar[s]);
+                    ++it;
                     break;
                 }
                 stage_tile[s] = tile;
@@ -242,9 +267,15 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 bulk_g2s(metas + (size_t)s * L::kMetaBytes, p.inv_norm + row0,
                          (uint32_t)L::kMetaBytes, &full_bar[s]);
             }
+            }
         }
     } else {
         // ------------------------------------------------------------------ consumers
+        uint32_t it = 0;
+        for (int g = blockIdx.y; g < n_groups; g += gridDim.y) {
+        const int q0 = g * QPC;                                           // first SLOT of this group (lists are per slot)
+        const int nqv = nq_eff - q0 < QPC ? nq_eff - q0 : QPC;            // valid queries in the group
+        const int qsrc0 = (QPC == 1 && p.q_index != nullptr) ? __ldg(&p.q_index[q0]) : q0;   // first QUERY of the group
         if constexpr (L::kDeep) {
             // ---- deep shared reads: a 4-row x 8-query register tile per warp, rows and queries streamed from shared memory
             constexpr int QW = L::QW;                         // queries of this warp (8)
@@ -254,7 +285,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
             const int qh = warp % kDeepQSplit;                // query half: queries qh*QW .. of the CTA's group
             for (int u = warp; u < QPC; u += CW) {
                 float qn = 0.f;
-                const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(q0 + (u < nqv ? u : 0)) * DIM);
+                const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(qsrc0 + (u < nqv ? u : 0)) * DIM);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const float4 t = __ldg(&qv[j * 32 + lane]);
@@ -279,12 +310,17 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
             const float4 *my_q = qs + (size_t)(qh * QW) * (DIM / 4) + lane;
             const float *my_qinv = qinv_s + qh * QW;
 
-            for (int64_t i = 0;; ++i) {
-                const int s = (int)(i % S);
-                const uint32_t ph = (uint32_t)((i / S) & 1);
+            for (;; ++it) {
+                const int s = (int)(it % (uint32_t)S);
+                const uint32_t ph = (it / (uint32_t)S) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 const int64_t tile = stage_tile[s];
-                if (tile < 0) break;
+                if (tile < 0) {                                   // end of this group's stream: hand the stage back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                    ++it;
+                    break;
+                }
                 const int64_t row0 = tile * TR + rg * RPW;    // a multiple of RPW: the rows share one bitmap word
                 uint32_t allow_bits = 0xFFFFFFFFu;
                 uint32_t g_row[RPW];
@@ -436,7 +472,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
             constexpr int JB = J / 2;
             float4 qa[JB], qb[JB];
             float qn = 0.f;
-            const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)q0 * DIM);
+            const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)qsrc0 * DIM);
 #pragma unroll
             for (int j = 0; j < JB; ++j) {
                 qa[j] = __ldg(&qv[(j * 32 + lane) * 2]);
@@ -450,12 +486,17 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
             const float inv_q = __fdiv_rn(1.0f, __fsqrt_rn(qn));
             WarpTopK<NPL> top;
             top.init(lists + warp * KC, lane);
-            for (int64_t i = 0;; ++i) {
-                const int s = (int)(i % S);
-                const uint32_t ph = (uint32_t)((i / S) & 1);
+            for (;; ++it) {
+                const int s = (int)(it % (uint32_t)S);
+                const uint32_t ph = (it / (uint32_t)S) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 const int64_t tile = stage_tile[s];
-                if (tile < 0) break;
+                if (tile < 0) {                                   // end of this group's stream: hand the stage back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                    ++it;
+                    break;
+                }
                 const int64_t row0 = tile * TR + warp * RPW;      // a multiple of RPW (<= 4): one bitmap word
                 uint32_t allow_bits = 0xFFFFFFFFu;
                 uint32_t g_row[RPW];
@@ -513,7 +554,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
         for (int u = 0; u < QPC; ++u) {
             float qn = 0.f;
             // a missing query of the last group re-reads the group's first query; its results are never written
-            const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(q0 + (u < nqv ? u : 0)) * DIM);
+            const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(qsrc0 + (u < nqv ? u : 0)) * DIM);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 q[u][j] = __ldg(&qv[j * 32 + lane]);
@@ -527,12 +568,17 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
             top[u].init(lists + (warp * QPC + u) * KC, lane);
         }
 
-        for (int64_t i = 0;; ++i) {
-            const int s = (int)(i % S);
-            const uint32_t ph = (uint32_t)((i / S) & 1);
+        for (;; ++it) {
+            const int s = (int)(it % (uint32_t)S);
+            const uint32_t ph = (it / (uint32_t)S) & 1u;
             mbar_wait(&full_bar[s], ph);
             const int64_t tile = stage_tile[s];
-            if (tile < 0) break;
+            if (tile < 0) {                                       // end of this group's stream: hand the stage back
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                ++it;
+                break;
+            }
             const int64_t row0 = tile * TR + warp * RPW;   // gather: first LIST ENTRY of this warp
             // filter bits for this warp's rows (consumed after the dot products, so the load overlaps them)
             uint32_t allow_bits = 0xFFFFFFFFu;
@@ -678,6 +724,9 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
             }
         }
+        // the next group re-initialises the lists (and, deep reads, the staged queries): every merge that reads
+        // another warp's list ended before the last barrier above
+        }
     }
 }
 
@@ -739,6 +788,11 @@ struct FinalizeParams {
     int32_t *out_n;           // [nq]
     unsigned int *reset_ctr;  // nullable: K1's work-stealing counter of this query's group, zeroed for the next launch
     int reset_div;            // queries per K1 group (counter index = query / reset_div)
+    // conditional re-run (see ScanParams): lists of SLOT g belong to query q_index[g]; min(*q_count, n_slots) slots are
+    // live and the CTAs of the launch walk them; both null = slot == query, one CTA per query
+    const int *q_index;
+    const int *q_count;
+    int n_slots;
 };
 
 // fp64 cosine of query (a-values in smem as float) x one resident row; all lanes return the result.
@@ -773,8 +827,15 @@ __global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const Finaliz
     __shared__ int s_nvalid;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = blockIdx.x;
-    const uint64_t *base = p.lists + (size_t)qi * p.n_lists * KC;
+    int n_live = p.n_slots;
+    if (p.q_count != nullptr) {
+        const int c = *p.q_count;
+        n_live = c < n_live ? c : n_live;
+    }
+    for (int slot = blockIdx.x; slot < n_live; slot += gridDim.x) {
+    const int qi = p.q_index != nullptr ? __ldg(&p.q_index[slot]) : slot;     // query: inputs and outputs
+    const uint64_t *base = p.lists + (size_t)slot * p.n_lists * KC;
+    __syncthreads();                                                          // the previous slot's shared state is dead
     if (threadIdx.x == 0) s_nvalid = 0;
 
     uint64_t k[NPL];
@@ -804,8 +865,8 @@ __global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const Finaliz
         }
     } else {
         // one unsorted list per query (K2 candidates): sort KC-sized chunks, fold them in
-        const uint64_t *list = p.lists + (size_t)qi * p.cap;
-        uint32_t n = p.counts[qi];
+        const uint64_t *list = p.lists + (size_t)slot * p.cap;
+        uint32_t n = p.counts[slot];
         if (n > (uint32_t)p.cap) n = p.cap;
         const int chunks = (int)((n + KC - 1) / KC);
         for (int ch = warp; ch < chunks; ch += WARPS) {
@@ -933,7 +994,8 @@ __global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const Finaliz
     }
     if (threadIdx.x == 0) {
         p.out_n[qi] = n_out;
-        if (p.reset_ctr) p.reset_ctr[qi / p.reset_div] = 0u;
+        if (p.reset_ctr) p.reset_ctr[slot / p.reset_div] = 0u;
+    }
     }
 }
 
@@ -1128,7 +1190,7 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
     // 25.5 us vs 31.6 us per launch, profiles/r01/README.md)
     // small batches of sorted per-CTA lists (the exact lane serving single requests): 8-CTA cluster per query
     static const bool no_cluster = [] { const char *e = getenv("CADENCE_FIN_CLUSTER"); return e && e[0] == '0'; }();
-    if (fp.counts == nullptr && nq <= 16 && !no_cluster && (kc == 64 || kc == 128 || kc == 256)) {
+    if (fp.counts == nullptr && fp.q_index == nullptr && nq <= 16 && !no_cluster && (kc == 64 || kc == 128 || kc == 256)) {
         if (kc == 64) scan_finalize_cluster_kernel<2><<<nq * kFinCluster, 256, 0, st>>>(fp);
         else if (kc == 128) scan_finalize_cluster_kernel<4><<<nq * kFinCluster, 256, 0, st>>>(fp);
         else scan_finalize_cluster_kernel<8><<<nq * kFinCluster, 256, 0, st>>>(fp);
@@ -1146,10 +1208,11 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
     return CDR_OK;
 }
 
+// q_index / q_count (QPC == 1 only): the conditional re-run of ScanParams -- nq is then the number of slots.
 template <int J, int RPW, int NPL, int QPC, bool BF = false>
 int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                   const uint32_t *allow, int k, double *out_score, int64_t *out_id, int32_t *out_n,
-                  cudaStream_t st)
+                  cudaStream_t st, const int *q_index = nullptr, const int *q_count = nullptr)
 {
     using L = ScanSmem<J, RPW, NPL, QPC, BF>;
     constexpr int KC = L::KC;
@@ -1245,6 +1308,14 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     sp.list_cap = list_cap;
     sp.lists_per_query = g_total;
     sp.list_offset = 0;
+    sp.q_index = QPC == 1 ? q_index : nullptr;
+    sp.q_count = QPC == 1 ? q_count : nullptr;
+    // One scan per query (QPC == 1): the CTAs are persistent over the queries of the launch (gridDim.y = 1), so a CTA's
+    // producer warp prefetches query y+1's first tiles while its consumers sort and merge the lists of query y, instead
+    // of a fresh CTA per (SM, query) paying pipeline fill and epilogue alone.  CADENCE_K1_PERSIST=0 restores one CTA
+    // per (SM, query) (A/B aid).  Shared-read launches keep one grid row per query group (the groups split the SMs).
+    static const bool k1_persist = [] { const char *e = getenv("CADENCE_K1_PERSIST"); return !(e && e[0] == '0'); }();
+    const int grid_y = (QPC == 1 && (k1_persist || q_index != nullptr)) ? 1 : n_groups;
 
     cdr_prof_mark_begin(0, st);
     if (g_gather > 0) {
@@ -1252,12 +1323,12 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
         gp.row_list = ws.row_list;
         gp.list_count = reinterpret_cast<unsigned int *>(ws.row_list) + list_cap;
         gp.allow = nullptr;
-        exact_scan_kernel<J, RPW, NPL, QPC, BF><<<dim3(g_gather, n_groups), (L::CW + 1) * 32, smem, st>>>(gp);
+        exact_scan_kernel<J, RPW, NPL, QPC, BF><<<dim3(g_gather, grid_y), (L::CW + 1) * 32, smem, st>>>(gp);
         CDR_LAUNCH_CHECK();
         sp.list_count = gp.list_count;
         sp.list_offset = g_gather;
     }
-    exact_scan_kernel<J, RPW, NPL, QPC, BF><<<dim3(grid, n_groups), (L::CW + 1) * 32, smem, st>>>(sp);
+    exact_scan_kernel<J, RPW, NPL, QPC, BF><<<dim3(grid, grid_y), (L::CW + 1) * 32, smem, st>>>(sp);
     CDR_LAUNCH_CHECK();
     cdr_prof_mark_end(0, st);
 
@@ -1277,7 +1348,10 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     fp.out_n = out_n;
     fp.reset_ctr = sp.tile_ctr;
     fp.reset_div = QPC;
-    return launch_finalize(fp, KC, nq, st);
+    fp.q_index = sp.q_index;
+    fp.q_count = sp.q_count;
+    fp.n_slots = nq;
+    return launch_finalize(fp, KC, sp.q_index != nullptr && nq > 64 ? 64 : nq, st);
 }
 
 enum ScanMode { kScanSingle = 0, kScanShared = 1, kScanDeep = 2 };
@@ -1285,7 +1359,8 @@ enum ScanMode { kScanSingle = 0, kScanShared = 1, kScanDeep = 2 };
 template <int NPL>
 int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                     const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                    int32_t *out_n, cudaStream_t st, ScanMode mode)
+                    int32_t *out_n, cudaStream_t st, ScanMode mode, const int *q_index = nullptr,
+                    const int *q_count = nullptr)
 {
 #define CDR_SCAN_CASE(J_, RPW_)                                                                              \
     if constexpr (NPL == 2) {                                                                                \
@@ -1294,15 +1369,15 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     }                                                                                                        \
     if (mode != kScanSingle)                                                                                 \
         return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
-    return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st)
+    return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count)
     switch (s->dim) {
     case 256:  CDR_SCAN_CASE(2, 2);
     case 512:  CDR_SCAN_CASE(4, 2);
     case 768:  CDR_SCAN_CASE(6, 2);
     case 1024: CDR_SCAN_CASE(8, 2);
     // kSharedQPC queries x J float4 would not fit the register budget: one scan per query
-    case 1536: return launch_scan_t<12, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
-    case 2048: return launch_scan_t<16, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st);
+    case 1536: return launch_scan_t<12, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count);
+    case 2048: return launch_scan_t<16, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count);
     default:
         cdr_set_error("exact scan: dim %d not built (supported: 256,512,768,1024,1536,2048)", s->dim);
         return CDR_ERR_UNSUPPORTED;
@@ -1340,14 +1415,26 @@ int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
                               out_id + (size_t)n_deep * k, out_n + n_deep, st, share && rest >= 2 ? kScanShared : kScanSingle);
 }
 
+// Conditional re-run of the queries q_index[0 .. min(*q_count, n_slots)) of a batch on the exact lane, one scan per
+// query, results written to the queries' own output rows (K2's overflow path: the count lives on the device, and a
+// zero count costs two empty launches).  Store mutex held by the caller.
+int cdr_exact_scan_redo_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int n_slots, const uint32_t *allow,
+                               int k, double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st,
+                               const int *q_index, const int *q_count)
+{
+    if (k > 56) return launch_scan_dim<8>(s, ws, q_dev, n_slots, allow, k, out_score, out_id, out_n, st, kScanSingle, q_index, q_count);
+    return launch_scan_dim<2>(s, ws, q_dev, n_slots, allow, k, out_score, out_id, out_n, st, kScanSingle, q_index, q_count);
+}
+
 // Single-query "ann" lane: the same scan over the bf16 copy of the rows (half the bytes), candidate lists twice as wide
 // as the exact lane's (KC = 128 for k <= 120, else 256), exact fp64 re-score of the survivors.  One scan per query.
 int cdr_bf16_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
-                         double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st)
+                         double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st, const int *q_index,
+                         const int *q_count)
 {
 #define CDR_BF_CASE(J_)                                                                                          \
-    if (k <= 120) return launch_scan_t<J_, 4, 4, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
-    return launch_scan_t<J_, 4, 8, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st)
+    if (k <= 120) return launch_scan_t<J_, 4, 4, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count); \
+    return launch_scan_t<J_, 4, 8, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count)
     switch (s->dim) {
     case 256:  CDR_BF_CASE(2);
     case 512:  CDR_BF_CASE(4);
@@ -1382,5 +1469,8 @@ int cdr_finalize_unsorted_launch(cdr_store *s, const uint64_t *lists, const uint
     fp.out_n = out_n;
     fp.reset_ctr = nullptr;
     fp.reset_div = 1;
+    fp.q_index = nullptr;
+    fp.q_count = nullptr;
+    fp.n_slots = nq;
     return launch_finalize(fp, kc, nq, st);
 }

@@ -211,8 +211,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 3-input maximum (SASS FMNMX3 on sm_100a): halves the max chain of the epilogue's fast path.  NaN operands are
+// ignored like fmaxf's (the result is NaN only when all three are).
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 struct GemmParams {
-    const float *tau;          // [nq_pad] admission threshold per query (-inf => take everything)
+    const float *tau;          // [nq_pad] admission threshold per query as a score (-inf => take everything): fast test
+    const uint64_t *tau_key;   // [nq_pad] the same threshold as a packed key (0 => take everything): exact test
     uint64_t *lists;           // [nq, cap] candidate keys
     uint32_t *counts;          // [nq]
     const uint32_t *allow;     // nullable row bitmap
@@ -438,7 +448,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int64_t row0 = nt * kBlockN;
             const int q = mt * kBlockM + et;
             const bool q_ok = q < p.nq;
-            const float tau = (q_ok && p.debug_no_append != 1) ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
+            const bool live = q_ok && p.debug_no_append != 1;
+            const float tau = live ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
+            const uint64_t tau_key = live ? __ldg(&p.tau_key[q]) : ~0ull;
             int64_t lim = p.n_rows - row0;                        // valid columns in this tile
             if (lim > kBlockN) lim = kBlockN;
             const uint32_t buf = tile_no & 1u;
@@ -452,42 +464,43 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
                 if (c * 32 >= lim) continue;                      // warp-uniform (tail tile)
-                // max of the chunk as a 4-wide tree (short dependency chain: this warp is alone on its SMSP)
-                float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
+                // fast path: the maximum of the chunk as four 8-column sub-maxima (3-input max: 18 instead of 31
+                // operations per chunk) against the query's threshold.  !(m < tau) also holds for a NaN maximum
+                // (a chunk of NaN scores: rows with a zero or non-finite norm), which the slow path sorts out.
+                float ms[4];
 #pragma unroll
-                for (int j = 8; j < 32; j += 4) {
-                    m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const float *w = v + 8 * s4;
+                    ms[s4] = fmaxf(fmax3(fmax3(w[0], w[1], w[2]), fmax3(w[3], w[4], w[5]), w[6]), w[7]);
                 }
-                const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                const int rem = (int)(lim - c * 32);
-                if (m >= tau) {
-                    // slow path (rare): exact per-element test, filter bit, staged append
-                    uint32_t mask = 0;
+                const float m = fmaxf(fmax3(ms[0], ms[1], ms[2]), ms[3]);
+                if (!(m < tau)) {
+                    // slow path (rare): only the sub-chunks whose maximum passed are looked at element by element;
+                    // admission is decided on the packed key (score desc, row asc), like the exact lane: NaN scores
+                    // stay eligible below every real score, ties with the threshold are cut by row order
+                    uint32_t allow_w = 0xFFFFFFFFu;
+                    // 32 consecutive rows starting at a multiple of 32: exactly one bitmap word
+                    if (p.allow != nullptr) allow_w = __ldg(&p.allow[(row0 + c * 32) >> 5]);
+                    const int rem = (int)(lim - c * 32);
+                    if (rem < 32) allow_w &= (1u << rem) - 1u;
+                    if (p.debug_no_append == 2) allow_w = 0;       // timing aid: tests run, nothing staged
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (v[j] >= tau) mask |= 1u << j;
-                    if (rem < 32) mask &= (1u << rem) - 1u;
-                    if (mask != 0 && p.allow != nullptr) {
-                        // 32 consecutive rows starting at a multiple of 32: exactly one bitmap word
-                        mask &= __ldg(&p.allow[(row0 + c * 32) >> 5]);
-                    }
-                    if (p.debug_no_append == 2) mask = 0;          // timing aid: mask built, nothing staged
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t mh = (mask >> (16 * h)) & 0xFFFFu;
-                        if (mh != 0) {
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        if (!(ms[s4] < tau)) {
                             if (p.debug_no_append == 3) nbuf = 0;  // timing aid: stage, never flush
-                            if (nbuf + __popc(mh) > kBufN) {       // make room for up to 16 hits
+                            if (nbuf > kBufN - 8) {                // make room for up to 8 hits
                                 flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
                                 nbuf = 0;
                             }
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                if ((mh >> j) & 1u) {
-                                    buf_key[nbuf * 128 + et] =
-                                        cdr_pack_key(v[16 * h + j], (uint32_t)(row0 + c * 32 + 16 * h + j));
-                                    buf_q[nbuf * 128 + et] = (uint16_t)q;
-                                    ++nbuf;
+                            for (int j = 8 * s4; j < 8 * s4 + 8; ++j) {
+                                if (!(v[j] < tau) && ((allow_w >> j) & 1u)) {
+                                    const uint64_t key = cdr_pack_key(v[j], (uint32_t)(row0 + c * 32 + j));
+                                    if (key > tau_key) {
+                                        buf_key[nbuf * 128 + et] = key;
+                                        buf_q[nbuf * 128 + et] = (uint16_t)q;
+                                        ++nbuf;
+                                    }
                                 }
                             }
                         }
@@ -522,7 +535,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 }
 
 // ---- query preparation: q_bf16[q,:] = RN(q / ||q||), zero rows for padding; tau = -inf
-__global__ void prep_queries_kernel(const float *q, __nv_bfloat16 *out, float *tau, uint32_t *counts,
+__global__ void prep_queries_kernel(const float *q, __nv_bfloat16 *out, float *tau, uint64_t *tau_key, uint32_t *counts,
                                     uint32_t *overflow, int nq, int nq_pad, int dim)
 {
     const int lane = threadIdx.x & 31;
@@ -531,7 +544,10 @@ __global__ void prep_queries_kernel(const float *q, __nv_bfloat16 *out, float *t
     __nv_bfloat16 *o = out + (size_t)row * dim;
     if (row >= nq) {
         for (int i = lane; i < dim; i += 32) o[i] = __float2bfloat16_rn(0.f);
-        if (lane == 0) tau[row] = __int_as_float(0x7f800000);
+        if (lane == 0) {
+            tau[row] = __int_as_float(0x7f800000);
+            tau_key[row] = ~0ull;
+        }
         return;
     }
     const float *r = q + (size_t)row * dim;
@@ -542,6 +558,7 @@ __global__ void prep_queries_kernel(const float *q, __nv_bfloat16 *out, float *t
     for (int i = lane; i < dim; i += 32) o[i] = __float2bfloat16_rn(r[i] * inv);
     if (lane == 0) {
         tau[row] = __int_as_float(0xff800000);   // -inf
+        tau_key[row] = 0ull;                     // every key, NaN scores included, is admitted until the list is full
         counts[row] = 0;
         overflow[row] = 0;
     }
@@ -556,7 +573,7 @@ __device__ __forceinline__ float key_score(uint64_t key)
 // ---- between segments: compact list[q] to its top-KC (sorted desc), raise tau[q]
 template <int NPL>
 __global__ void __launch_bounds__(256) select_compact_kernel(uint64_t *lists, uint32_t *counts, float *tau,
-                                                             uint32_t *overflow, int cap)
+                                                             uint64_t *tau_key, uint32_t *overflow, int cap)
 {
     constexpr int KC = NPL * 32;
     __shared__ uint64_t s_lists[8 * KC];
@@ -606,8 +623,31 @@ __global__ void __launch_bounds__(256) select_compact_kernel(uint64_t *lists, ui
         const uint64_t last = __shfl_sync(0xffffffffu, k[NPL - 1], 31);   // element KC-1
         if (lane == 0) {
             counts[q] = n < (uint32_t)KC ? n : (uint32_t)KC;
-            if (last != CDR_EMPTY_KEY) tau[q] = key_score(last);
+            if (last != CDR_EMPTY_KEY) {
+                // the list is full: its KC-th key is the new threshold.  While that key is a NaN score (fewer than KC
+                // real scores seen so far) the float test must let every real score through.
+                tau_key[q] = last;
+                tau[q] = (uint32_t)(last >> 32) > 1u ? key_score(last) : __int_as_float(0xff800000);
+            }
         }
+    }
+}
+
+// ---- after the last segment: the queries whose candidate list overflowed in any segment (lost candidates), as a
+// compact list for the conditional exact-lane re-run; cnt[r] = live slots of round r (kRedoSlots slots per round)
+constexpr int kRedoSlots = 1024;
+__global__ void __launch_bounds__(1024) redo_list_kernel(const uint32_t *overflow, const uint32_t *counts, int cap, int nq,
+                                                         int *idx, int *cnt, int slots, int rounds)
+{
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < nq; q += blockDim.x)
+        if (overflow[q] != 0u || counts[q] > (uint32_t)cap) idx[atomicAdd(&s_n, 1)] = q;
+    __syncthreads();
+    for (int r = threadIdx.x; r < rounds; r += blockDim.x) {
+        const int left = s_n - r * slots;
+        cnt[r] = left < 0 ? 0 : (left > slots ? slots : left);
     }
 }
 
@@ -696,21 +736,32 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
                           double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev, cudaStream_t st)
 {
     const int kc = k <= 64 ? 128 : 256;          // candidates kept per query (>= k + 64)
-    const int cap = 32 * kc;
+    int cap = 32 * kc;
+    // test hook: a smaller list capacity makes the first segment overflow, so the tests can drive the device-side
+    // re-run of overflowed queries (read per call; costs nothing next to a batch)
+    if (const char *e = getenv("CADENCE_K2_TEST_CAP")) {
+        const int v = atoi(e);
+        if (v >= kc && v < cap) cap = v;
+    }
     const int nq_pad = (nq + kBlockM - 1) / kBlockM * kBlockM;
     const int dim = s->dim;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_q = up((size_t)nq_pad * dim * 2), b_tau = up((size_t)nq_pad * 4), b_cnt = up((size_t)nq_pad * 4);
-    const size_t b_ovf = up((size_t)nq_pad * 4), b_lists = up((size_t)nq * cap * 8);
-    if (cdr_ws_reserve(&ws.gemm_ws, &ws.gemm_ws_bytes, b_q + b_tau + b_cnt + b_ovf + b_lists) != CDR_OK) return CDR_ERR_OOM;
+    const size_t b_ovf = up((size_t)nq_pad * 4), b_lists = up((size_t)nq * cap * 8), b_tk = up((size_t)nq_pad * 8);
+    const size_t b_redo = up(((size_t)nq + 64) * 4);
+    if (cdr_ws_reserve(&ws.gemm_ws, &ws.gemm_ws_bytes, b_q + b_tau + b_tk + b_cnt + b_ovf + b_redo + b_lists) != CDR_OK) return CDR_ERR_OOM;
     unsigned char *c = (unsigned char *)ws.gemm_ws;
     __nv_bfloat16 *q_bf16 = (__nv_bfloat16 *)c; c += b_q;
     float *tau = (float *)c; c += b_tau;
+    uint64_t *tau_key = (uint64_t *)c; c += b_tk;
     uint32_t *counts = (uint32_t *)c; c += b_cnt;
     uint32_t *overflow = (uint32_t *)c; c += b_ovf;
+    int *redo_cnt = (int *)c;                    // [<= 64] live slots per re-run round
+    int *redo_idx = redo_cnt + 64;               // [nq] overflowed queries
+    c += b_redo;
     uint64_t *lists = (uint64_t *)c;
 
-    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q_dev, q_bf16, tau, counts, overflow, nq, nq_pad, dim);
+    prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(q_dev, q_bf16, tau, tau_key, counts, overflow, nq, nq_pad, dim);
     CDR_LAUNCH_CHECK();
 
     CUtensorMap map_q, map_x;
@@ -736,6 +787,7 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
 
     GemmParams p;
     p.tau = tau;
+    p.tau_key = tau_key;
     p.lists = lists;
     p.counts = counts;
     p.allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
@@ -801,8 +853,8 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
         CDR_LAUNCH_CHECK();
         cdr_prof_mark_end(1, st);
         if (end < p.n_tiles_total) {
-            if (kc == 128) select_compact_kernel<4><<<nq, 256, 0, st>>>(lists, counts, tau, overflow, cap);
-            else select_compact_kernel<8><<<nq, 256, 0, st>>>(lists, counts, tau, overflow, cap);
+            if (kc == 128) select_compact_kernel<4><<<nq, 256, 0, st>>>(lists, counts, tau, tau_key, overflow, cap);
+            else select_compact_kernel<8><<<nq, 256, 0, st>>>(lists, counts, tau, tau_key, overflow, cap);
             CDR_LAUNCH_CHECK();
         }
         begin = end;
@@ -812,23 +864,22 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
                                       out_id_dev, out_n_dev, st);
     if (rc != CDR_OK) return rc;
 
-    // ---- overflow / short-result check (one small D2H + sync), exact-lane fallback per query
-    std::vector<uint32_t> h_ovf(nq), h_cnt(nq);
-    std::vector<int32_t> h_n(nq);
-    CDR_CUDA(cudaMemcpyAsync(h_ovf.data(), overflow, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    CDR_CUDA(cudaMemcpyAsync(h_cnt.data(), counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    CDR_CUDA(cudaMemcpyAsync(h_n.data(), out_n_dev, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    CDR_CUDA(cudaStreamSynchronize(st));
-    const uint32_t *allow = p.allow;
-    for (int q = 0; q < nq; ++q) {
-        const bool over = h_ovf[q] != 0 || h_cnt[q] > (uint32_t)cap;
-        const bool shrt = h_n[q] < k && h_n[q] < s->n_valid;   // NaN rows / restrictive filters
-        if (!over && !shrt) continue;
-        CDR_REQUIRE(s->emb_f32 != nullptr, CDR_ERR_UNSUPPORTED,
-                    "cdr_search_batch_bf16: query %d needs the exact lane (candidate overflow or short result) "
-                    "but the store keeps no fp32 rows", q);
-        rc = cdr_exact_scan_launch(s, ws, q_dev + (size_t)q * dim, 1, allow, k,
-                                   out_score_dev + (size_t)q * k, out_id_dev + (size_t)q * k, out_n_dev + q, st, false);
+    // ---- candidate-list overflow (adversarial data): detected and repaired ON THE DEVICE, no host round trip.  A
+    // one-block kernel lists the overflowed queries; the exact lane then re-runs exactly those (count read from device
+    // memory by the kernels themselves: with none listed -- always, on real data -- its two launches exit at once).
+    // Short results need no second look: NaN-scored rows are admitted like in the exact lane, so fewer than k results
+    // means fewer than k allowed rows.
+    const int rounds = (nq + kRedoSlots - 1) / kRedoSlots;
+    redo_list_kernel<<<1, 1024, 0, st>>>(overflow, counts, cap, nq, redo_idx, redo_cnt, kRedoSlots, rounds);
+    CDR_LAUNCH_CHECK();
+    for (int r = 0; r < rounds; ++r) {
+        const int n_slots = nq - r * kRedoSlots < kRedoSlots ? nq - r * kRedoSlots : kRedoSlots;
+        if (s->emb_f32 != nullptr)
+            rc = cdr_exact_scan_redo_launch(s, ws, q_dev, n_slots, p.allow, k, out_score_dev, out_id_dev, out_n_dev, st,
+                                            redo_idx + r * kRedoSlots, redo_cnt + r);
+        else      // bf16-only store: the scan lane over the bf16 rows is exact over the rows as stored
+            rc = cdr_bf16_scan_launch(s, ws, q_dev, n_slots, p.allow, k, out_score_dev, out_id_dev, out_n_dev, st,
+                                      redo_idx + r * kRedoSlots, redo_cnt + r);
         if (rc != CDR_OK) return rc;
     }
     return CDR_OK;

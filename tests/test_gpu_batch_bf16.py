@@ -102,9 +102,9 @@ def test_batch_lane_bf16_only_store():
     s.close()
 
 
-def test_batch_lane_overflow_falls_back_to_exact_lane():
-    """Adversarial corpus: thousands of identical rows overflow the candidate lists; the wrapper
-    re-runs those queries on the exact lane, so results stay exact (ties by id)."""
+def test_batch_lane_thousands_of_identical_rows():
+    """Adversarial corpus: 20 000 identical rows tie at the top.  Admission is decided on the packed key (score desc,
+    row asc), so ties are cut by row order like in the exact lane and the result stays exact (ties by id)."""
     rng = np.random.default_rng(3)
     n = 30_000
     x = rng.standard_normal((n, 1024)).astype(np.float32)
@@ -119,6 +119,58 @@ def test_batch_lane_overflow_falls_back_to_exact_lane():
         w_ids, w_sc = orc.exact_scan(qs[i], x, 50, variant=orc.VARIANT_F64)
         assert ids[i].tolist() == w_ids.tolist()
     s.close()
+
+
+@pytest.mark.parametrize("fp32", [True, False])
+def test_batch_lane_overflow_is_repaired_on_the_device(monkeypatch, fp32):
+    """Candidate-list overflow (forced with a reduced list capacity: the first segment appends every row) is
+    detected and repaired on the device: the overflowed queries are re-run on the exact lane (fp32 stores) or the
+    bf16 scan lane (bf16-only stores) by kernels that read the query list from device memory -- the call never
+    synchronises.  Results must carry that lane's bits; queries that did not overflow keep the tensor-core result."""
+    n = 20_000
+    s = _store(n, fp32=fp32)
+    qs = torch.from_numpy(orc.synth_rows(SYNTH_QUERY_SEED, 300, 1100)).cuda()        # 1100 queries: two re-run rounds
+    exact = (s.search_exact if fp32 else s.search_scan_bf16)(qs, 50)
+    plain = s.search_batch(qs, 50)
+    monkeypatch.setenv("CADENCE_K2_TEST_CAP", "2000")                                # < 4096 rows of the first segment
+    redo = s.search_batch(qs, 50)
+    torch.cuda.synchronize()
+    for a, b in zip(redo, exact):
+        assert torch.equal(a.view(torch.int64) if a.dtype == torch.float64 else a, b.view(torch.int64) if b.dtype == torch.float64 else b)
+    monkeypatch.delenv("CADENCE_K2_TEST_CAP")
+    again = s.search_batch(qs, 50)
+    torch.cuda.synchronize()
+    assert torch.equal(again[0], plain[0])
+    rec = _recall(plain[0].cpu().numpy(), plain[2].cpu().numpy(), [r for r in exact[0].cpu().numpy()])
+    assert rec >= 0.999
+    s.close()
+
+
+def test_batch_lane_nan_rows_and_tight_filters_need_no_second_pass():
+    """Rows whose score is NaN (zero embeddings) are admitted by the tensor-core lane exactly as by the exact lane
+    (below every real score, id order), so short and NaN-tailed results agree with the exact lane without any
+    fallback -- on bf16-only stores too, where no exact fp32 lane exists."""
+    rng = np.random.default_rng(11)
+    n = 6_000
+    x = rng.standard_normal((n, 1024)).astype(np.float32)
+    x[100:140] = 0.0                                            # 40 zero rows: NaN cosine
+    qs = rng.standard_normal((5, 1024)).astype(np.float32)
+    for fp32 in (True, False):
+        s = DenseStore("chunks", n, dim=1024, device=0, fp32=fp32, bf16=True)
+        s.append(x, ids=np.arange(1, n + 1), call_ids=[r // 20 for r in range(n)])
+        s.finalize()
+        other = s.search_exact if fp32 else s.search_scan_bf16
+        for slots in ([5, 6], [4, 5, 6], [0, 1], list(range(300))):   # 40 rows incl. 20 NaN / 60 rows / 40 real rows / all
+            allow, count = s.filter_bitmap(call_slots=slots)
+            ids, sc, cnt = s.search_batch(qs, 50, allow)
+            e_ids, e_sc, e_cnt = other(qs, 50, allow)
+            assert np.array_equal(cnt, e_cnt) and np.all(cnt == min(count, 50))
+            if count <= 128:                                     # every allowed row is a candidate: identical lists
+                assert np.array_equal(ids, e_ids)
+                assert np.array_equal(np.isnan(sc), np.isnan(e_sc))
+            else:
+                assert _recall(ids, cnt, [e_ids[i, :int(e_cnt[i])] for i in range(5)]) >= 0.999
+        s.close()
 
 
 def test_batch_lane_vs_torch_fp32_matmul_reference_1m():

@@ -250,11 +250,45 @@ def test_library_exports_every_declared_symbol():
     assert _ffi.abi_version() == 1
 
 
+def _sass_by_kernel():
+    """SASS of the shipped library split by kernel name (cuobjdump -sass)."""
+    out = subprocess.run(["cuobjdump", "-sass", _ffi.library_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    kernels, name = {}, None
+    for line in out.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            kernels[name] = []
+        elif name is not None:
+            kernels[name].append(line)
+    return {k: "\n".join(v) for k, v in kernels.items()}
+
+
 def test_library_is_sm100a_with_bulk_copy_and_no_legacy_mma():
+    """The shipped binary is sm_100a only, the tensor-core lane is tcgen05 (UTCHMMA issued from TMA-fed shared memory,
+    accumulators read back from TMEM with LDTM) with no legacy warp-level MMA anywhere, and the exact scan streams its
+    tiles with bulk async copies.  profiles/r02/sass_summary.txt records the same counts."""
     out = subprocess.run(["cuobjdump", "-lelf", _ffi.library_path()], capture_output=True, text=True)
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
-    assert "sm_100a" in out.stdout
+    elfs = [ln for ln in out.stdout.splitlines() if "ELF file" in ln]
+    assert elfs and all("sm_100a" in ln for ln in elfs), elfs
+    sass = _sass_by_kernel()
+    gemm = [v for k, v in sass.items() if "gemm_topk_kernel" in k]
+    scan = [v for k, v in sass.items() if "exact_scan_kernel" in k]
+    assert len(gemm) >= 3 and len(scan) >= 8
+    for body in gemm:
+        assert "UTCHMMA" in body, "tcgen05.mma missing from a gemm_topk_kernel instantiation"
+        assert "LDTM" in body, "tcgen05.ld missing"
+        assert "UTMALDG" in body, "TMA tensor loads missing"
+        assert "FMNMX3" in body, "3-input max missing from the epilogue"
+    for body in scan:
+        assert "UBLKCP" in body, "bulk async copy missing from an exact_scan_kernel instantiation"
+    legacy = re.compile(r"\b(HMMA|IMMA|DMMA|HGMMA|QGMMA)\b")
+    for name, body in sass.items():
+        assert not legacy.search(body), f"legacy MMA instruction in {name}"
 
 
 def test_no_device_fails_loudly():
