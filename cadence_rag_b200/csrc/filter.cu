@@ -17,6 +17,7 @@ struct FilterParams {
     const uint32_t *call_bitmap;   // device copy, nullable
     int64_t n_call_slots;
     int64_t n_rows;
+    int64_t n_words;               // words of the output bitmap = ceil(capacity / 32)
     int has_from, has_to, has_tags;
     int64_t date_from, date_to;
     uint64_t tag_any;
@@ -26,7 +27,9 @@ struct FilterParams {
 
 __global__ void __launch_bounds__(256) filter_bitmap_kernel(const FilterParams p)
 {
-    const int64_t words = (p.n_rows + 31) >> 5;
+    // The bitmap covers the store's CAPACITY (p.n_words words): rows appended after this launch read as "not
+    // allowed" instead of lying beyond the bitmap of a scan that sees the larger row count.
+    const int64_t words = p.n_words;
     unsigned long long local = 0;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -79,6 +82,7 @@ int cdr_filter_launch(cdr_store *s, const uint32_t *bm_dev, int64_t n_call_slots
     p.call_bitmap = bm_dev;
     p.n_call_slots = n_call_slots;
     p.n_rows = s->n_rows;
+    p.n_words = (s->capacity + 31) / 32;
     p.has_from = has_from != 0;
     p.has_to = has_to != 0;
     p.has_tags = has_tags != 0;
@@ -87,7 +91,7 @@ int cdr_filter_launch(cdr_store *s, const uint32_t *bm_dev, int64_t n_call_slots
     p.tag_any = tag_any;
     p.out_allow = out_allow_dev;
     p.out_count = cnt_dev;
-    const int64_t words = (s->n_rows + 31) / 32;
+    const int64_t words = p.n_words;
     int64_t blocks = (words + 7) / 8;
     const int64_t cap = (int64_t)s->sm_count * 8;
     if (blocks > cap) blocks = cap;
@@ -120,8 +124,12 @@ extern "C" int32_t cdr_filter_build(cdr_store *s, const uint32_t *call_slot_bitm
     if (bm_dev && n_call_slots > 0)
         CDR_CUDA(cudaMemcpyAsync(bm_dev, call_slot_bitmap_host, (size_t)((n_call_slots + 31) / 32) * 4,
                                  cudaMemcpyHostToDevice, st));
-    int rc = cdr_filter_launch(s, bm_dev, n_call_slots, has_date_from, date_from_us, has_date_to, date_to_us,
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);          // one row count for the whole bitmap (appends take the same lock)
+        rc = cdr_filter_launch(s, bm_dev, n_call_slots, has_date_from, date_from_us, has_date_to, date_to_us,
                                has_tag_filter, tag_any, out_allow_dev, cnt, st);
+    }
     if (rc != CDR_OK) return rc;
     unsigned long long h = 0;
     CDR_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -159,7 +159,9 @@ extern "C" int32_t cdr_hybrid_retrieve_groups_host(
     cudaStream_t st = (cudaStream_t)stream;
     const int dim = s->dim;
     const int L = dense ? 3 : 2;
-    const size_t words = (size_t)((s->n_rows + 31) / 32);
+    // allow bitmaps cover the store's capacity (filter.cu): their size does not depend on the row count, which a
+    // concurrent append may raise before this call takes the store lock
+    const size_t words = (size_t)((s->capacity + 31) / 32);
 
     // ---- packed request (host -> device), packed response (device -> host), device-only scratch
     std::vector<GroupPlan> plan((size_t)n_groups);

@@ -358,11 +358,12 @@ extern "C" int32_t cdr_store_append(cdr_store *s, const float *rows_f32, const i
     CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "cdr_store_append: store is NULL");
     CDR_REQUIRE(n >= 0 && rows_f32 && ids, CDR_ERR_INVALID, "cdr_store_append: rows/ids required");
     if (n == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    std::lock_guard<std::mutex> lk(s->mu);
+    // (checked under the lock: two concurrent appends must not both pass against the same row count)
     CDR_REQUIRE(s->n_rows + n <= s->capacity, CDR_ERR_OOM,
                 "cdr_store_append: %lld + %lld rows exceed capacity %lld", (long long)s->n_rows,
                 (long long)n, (long long)s->capacity);
-    DeviceGuard g(s->device);
-    std::lock_guard<std::mutex> lk(s->mu);
     cudaStream_t st = (cudaStream_t)stream;
     // A sealed store keeps serving while it grows (new chunks of an ingested call): the id order is then
     // verified BEFORE anything is written, so a rejected batch leaves the store untouched.
@@ -532,11 +533,11 @@ extern "C" int32_t cdr_store_append_synthetic(cdr_store *s, uint64_t seed, int64
     CDR_REQUIRE(n >= 0 && first_row >= 0 && rows_per_call > 0, CDR_ERR_INVALID,
                 "cdr_store_append_synthetic: bad n/first_row/rows_per_call");
     if (n == 0) return CDR_OK;
+    DeviceGuard g(s->device);
+    std::lock_guard<std::mutex> lk(s->mu);
     CDR_REQUIRE(s->n_rows + n <= s->capacity, CDR_ERR_OOM,
                 "cdr_store_append_synthetic: %lld + %lld rows exceed capacity %lld",
                 (long long)s->n_rows, (long long)n, (long long)s->capacity);
-    DeviceGuard g(s->device);
-    std::lock_guard<std::mutex> lk(s->mu);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t r0 = s->n_rows;
     const size_t d = (size_t)s->dim;

@@ -73,16 +73,19 @@ class TechTokenIndex:
     def __init__(self):
         self._lists: Dict[str, List[int]] = {}
         self._arrays: Dict[str, np.ndarray] = {}
+        self.version = 0            # bumped by every change: device copies know when they are out of date
 
     def add_row(self, row: int, tokens: Iterable[str]) -> None:
         for tok in set(tokens):
             self._lists.setdefault(tok, []).append(row)
         self._arrays.clear()
+        self.version += 1
 
     def add_postings(self, token: str, rows: np.ndarray) -> None:
         """Bulk load (synthetic corpora): rows must be ascending."""
         self._arrays[token] = np.ascontiguousarray(rows, dtype=np.int64)
         self._lists.pop(token, None)
+        self.version += 1
 
     def postings(self, token: str) -> np.ndarray:
         arr = self._arrays.get(token)
@@ -129,6 +132,11 @@ class DeviceTechIndex:
         from . import _ffi
         self._ffi = _ffi
         self.store = store
+        self.host_index = host_index
+        # what this copy was built from: a sealed store may grow and the host index with it (DenseStore.append /
+        # TechTokenIndex.add_row); postings AND the global (call_started_at DESC, id ASC) ranks are then out of date
+        self.built_rows = int(store.rows)
+        self.built_version = int(host_index.version)
         tokens = sorted(set(host_index._lists) | set(host_index._arrays))
         self.token_ids: Dict[str, int] = {t: i for i, t in enumerate(tokens)}
         lists = [host_index.postings(t) for t in tokens]
@@ -144,6 +152,14 @@ class DeviceTechIndex:
         _ffi.check(_ffi.lib().cdr_tech_index_create(ctypes.byref(self._h), store.handle, _ffi.ptr(offsets),
                                                     len(tokens), _ffi.ptr(rows), _ffi.ptr(rank)),
                    "cdr_tech_index_create")
+
+    def stale(self) -> bool:
+        """True once the store or the host index changed after this copy was built."""
+        return int(self.store.rows) != self.built_rows or int(self.host_index.version) != self.built_version
+
+    def fits(self, tokens: Sequence[str]) -> bool:
+        """A query's tokens fit the kernel's per-query token table (known tokens only count)."""
+        return sum(1 for t in set(tokens) if t in self.token_ids) <= self.MAX_TOKENS
 
     def close(self) -> None:
         if self._h:
@@ -162,9 +178,17 @@ class DeviceTechIndex:
         nq = len(token_lists)
         tok = np.full((nq, self.MAX_TOKENS), -1, dtype=np.int32)
         ntok = np.zeros(nq, dtype=np.int32)
+        if self.stale():
+            raise self._ffi.DenseEngineError("device tech-token index is out of date (the store or the host index changed "
+                                             "after it was built): take it from DenseEngine.device_tech_index(), which "
+                                             "rebuilds it", self._ffi.CDR_ERR_STATE)
         for i, toks in enumerate(token_lists):
-            ids = [self.token_ids.get(t, -1) for t in toks]
-            ids = [t for t in ids if t >= 0][: self.MAX_TOKENS]
+            ids = [self.token_ids.get(t, -1) for t in dict.fromkeys(toks)]      # duplicates add nothing to `&&`
+            ids = [t for t in ids if t >= 0]
+            if len(ids) > self.MAX_TOKENS:
+                raise self._ffi.DenseEngineError(f"query {i} carries {len(ids)} known tech tokens; the device lane takes "
+                                                 f"{self.MAX_TOKENS} (callers route such requests to the host index)",
+                                                 self._ffi.CDR_ERR_UNSUPPORTED)
             tok[i, :len(ids)] = ids
             ntok[i] = len(ids)
         return tok, ntok

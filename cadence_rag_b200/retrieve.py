@@ -86,6 +86,12 @@ class DenseEngine:
         self.tech_indexes: Dict[str, TechTokenIndex] = {}
         self.device_tech_indexes: Dict[str, DeviceTechIndex] = {}
         self.external_ids: Dict[Tuple[str, Optional[str]], Set[Any]] = {}
+        # optional provider of the opaque BM25 lanes for retrieve_evidence(payload):
+        # (query, filters) -> (chunk rows, artifact rows), ranked, each row carrying its id field
+        self.bm25_lanes = None
+        import threading
+        self._tech_lock = threading.Lock()
+        self._retired_tech_indexes: List[DeviceTechIndex] = []
 
     def register(self, store: DenseStore, tech_index: Optional[TechTokenIndex] = None,
                  device_tech_lane: bool = True) -> None:
@@ -96,6 +102,27 @@ class DenseEngine:
             self.tech_indexes[store.table_name] = tech_index
             if device_tech_lane:
                 self.device_tech_indexes[store.table_name] = DeviceTechIndex(tech_index, store)
+
+    def device_tech_index(self, table_name: str) -> Optional[DeviceTechIndex]:
+        """The table's device tech-token index, rebuilt first when the store grew or the host index changed since it
+        was built (a sealed store keeps serving while it grows; the lane must see the new rows like the reference's
+        SQL does).  None when the table has no device lane."""
+        dev = self.device_tech_indexes.get(table_name)
+        if dev is not None and dev.stale():
+            with self._tech_lock:
+                dev = self.device_tech_indexes.get(table_name)
+                if dev is not None and dev.stale():
+                    fresh = DeviceTechIndex(dev.host_index, dev.store)
+                    self.device_tech_indexes[table_name] = fresh
+                    self._retired_tech_indexes.append(dev)      # requests in flight may still hold it: freed at close()
+                    dev = fresh
+        return dev
+
+    def close(self) -> None:
+        for dev in list(self.device_tech_indexes.values()) + self._retired_tech_indexes:
+            dev.close()
+        self.device_tech_indexes.clear()
+        self._retired_tech_indexes.clear()
 
     def register_call(self, call_id, external_id: Optional[str] = None, external_source: Optional[str] = None) -> None:
         if external_id is not None:
@@ -200,8 +227,14 @@ def _filter_spec(store: DenseStore, filters: Optional[RetrieveFilters],
                 s = int(c)          # synthetic stores: call id == slot number
             if s is not None:
                 slots.append(s)
-    return dict(call_slots=slots, date_from=date_from, date_to=date_to,
-                tag_mask=None if tags is None else store.bits_of_tags(tags))
+    tag_mask = None
+    if tags is not None:
+        # tags beyond the 64 device bits live host-side as call-slot sets (store.tag_filter): such a filter becomes
+        # a call-slot set, intersected with the scoped calls when there are any
+        tag_mask, tag_slots = store.tag_filter(tags)
+        if tag_slots is not None:
+            slots = tag_slots if slots is None else sorted(set(slots) & set(tag_slots))
+    return dict(call_slots=slots, date_from=date_from, date_to=date_to, tag_mask=tag_mask)
 
 
 def _filter_bitmap(conn: DenseConnection, table_name: str, filters: Optional[RetrieveFilters],
@@ -332,7 +365,9 @@ def _fetch_tech(conn: DenseConnection, table_name: str, tokens: Sequence[str], f
     # the tech lane's WHERE has no `embedding IS NOT NULL` term (app/retrieve.py:195-208), so the
     # predicate is evaluated on the host columns of the posting rows, not through the K6 bitmap
     spec = _filter_spec(store, filters, call_ids)
-    dev_index = conn.engine.device_tech_indexes.get(table_name)
+    dev_index = conn.engine.device_tech_index(table_name)
+    if dev_index is not None and not dev_index.fits(tokens):
+        dev_index = None                           # more tokens than the kernel's table: the host index serves
     cols = store.host_columns()
     if dev_index is not None:                      # GPU lane (f-1); ids come back already ordered
         hit_ids = np.asarray(dev_index.query_ids(tokens, limit, **spec), dtype=np.int64)
@@ -443,11 +478,15 @@ def _embeddings_f32(vectors: Sequence[Sequence[float]]) -> np.ndarray:
     return a32
 
 
-def _fused_path_ok(engine: DenseEngine, table: str, dense: bool) -> bool:
+def _fused_path_ok(engine: DenseEngine, table: str, dense: bool, token_lists: Sequence[Sequence[str]] = ()) -> bool:
     """The fused C call serves a table when its dense lane is the exact fp32 scan and its tech lane
-    (if any) is device resident; other configurations take the step-by-step path."""
+    (if any) is device resident and can take every request's tokens; other configurations take the
+    step-by-step path."""
     store = engine.stores[table]
     if table in engine.tech_indexes and table not in engine.device_tech_indexes:
+        return False
+    dev = engine.device_tech_indexes.get(table)
+    if dev is not None and any(len(t) > dev.MAX_TOKENS and not dev.fits(t) for t in token_lists):
         return False
     if dense and not store.has_fp32:
         return False
@@ -520,7 +559,7 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
     bm25_rows = [bm25_rows[i] for i in order]
     if q32 is not None and per_request_filters:
         q32 = np.ascontiguousarray(q32[order])
-    dev_index = conn.engine.device_tech_indexes.get(table) if any(token_lists) else None
+    dev_index = conn.engine.device_tech_index(table) if any(token_lists) else None
     tok = nt = None
     if dev_index is not None:
         tok, nt = dev_index.encode_tokens([list(t) for t in token_lists])
@@ -608,7 +647,8 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters=None
     live = [i for i, q in enumerate(cleaned) if q]
     tables = [t for t in ("chunks", "artifact_chunks") if t in engine.stores]
     dense_enabled = embeddings_enabled()
-    if not live or not tables or not all(_fused_path_ok(engine, t, dense_enabled) for t in tables):
+    live_tokens = [extract_tech_tokens(cleaned[i]) for i in live]
+    if not live or not tables or not all(_fused_path_ok(engine, t, dense_enabled, live_tokens) for t in tables):
         return [retrieve_ids(engine, q, filter_of(i), bm25_chunks=bm25_chunks[i], bm25_artifacts=bm25_artifacts[i], debug=debug)
                 for i, q in enumerate(queries)]
     dense_error: Optional[str] = None
@@ -623,7 +663,7 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters=None
         except EmbeddingClientError as exc:
             dense_enabled = False
             dense_error = str(exc)
-    token_lists = [extract_tech_tokens(cleaned[i]) for i in live]
+    token_lists = live_tokens
     limits = {"chunks": DEFAULT_DENSE_CHUNK_TOPK, "artifact_chunks": DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK}
     bm25 = {"chunks": [bm25_chunks[i] for i in live], "artifact_chunks": [bm25_artifacts[i] for i in live]}
     with engine.connect() as conn:
@@ -804,7 +844,7 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
     if not debug:
         # without a debug payload the response is built straight from the fused call's output arrays
         resident = [t for t in ("chunks", "artifact_chunks") if t in engine.stores]
-        if resident and all(_fused_path_ok(engine, t, embeddings_enabled()) for t in resident):
+        if resident and all(_fused_path_ok(engine, t, embeddings_enabled(), [extract_tech_tokens(query)]) for t in resident):
             return retrieve_ids_batch(engine, [query], filters, bm25_chunks=[list(bm25_chunks)],
                                       bm25_artifacts=[list(bm25_artifacts)])[0]
     tech_tokens = extract_tech_tokens(query)
@@ -828,7 +868,7 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
     modes: Dict[str, Optional[str]] = {"chunks": None, "artifact_chunks": None}
     candidates = {"chunks": 0, "artifact_chunks": 0}
     tables = [t for t in ("chunks", "artifact_chunks") if t in engine.stores]
-    fused = bool(tables) and all(_fused_path_ok(engine, t, dense_enabled) for t in tables)
+    fused = bool(tables) and all(_fused_path_ok(engine, t, dense_enabled, [tech_tokens]) for t in tables)
     if fused:
         # one C call per table: filter + lanes + RRF on the device, one sync (csrc/hybrid.cu)
         limits = {"chunks": DEFAULT_DENSE_CHUNK_TOPK, "artifact_chunks": DEFAULT_DENSE_ARTIFACT_CHUNK_TOPK}
@@ -950,7 +990,29 @@ def _clip(text: str, max_chars: int) -> str:
     return text if len(text) <= max_chars else text[: max_chars - 1].rstrip() + "…"
 
 
-def retrieve_evidence(engine: DenseEngine, query: str, filters: Optional[RetrieveFilters] = None,
+_default_engine: Optional[DenseEngine] = None
+
+
+def set_default_engine(engine: Optional[DenseEngine]) -> None:
+    """The engine ``retrieve_evidence(payload)`` serves from -- the counterpart of the reference's module-level
+    SQLAlchemy ``engine`` (app/db.py:11, used at app/retrieve.py:445)."""
+    global _default_engine
+    _default_engine = engine
+
+
+def default_engine() -> DenseEngine:
+    if _default_engine is None:
+        raise DenseEngineError("retrieve_evidence(payload): no engine installed (call set_default_engine(engine) once at "
+                               "start-up, as the reference creates its SQLAlchemy engine at import time)", _ffi.CDR_ERR_STATE)
+    return _default_engine
+
+
+def _budget_dict(budget) -> Dict[str, int]:
+    """``budget.model_dump()`` of the reference (app/retrieve.py:413) for its pydantic Budget and for ours."""
+    return {"max_evidence_items": int(budget.max_evidence_items), "max_total_chars": int(budget.max_total_chars)}
+
+
+def retrieve_evidence(engine, query: Optional[str] = None, filters: Optional[RetrieveFilters] = None,
                       budget: Optional[Budget] = None, intent: str = "auto",
                       return_style: str = "evidence_pack_json", debug: bool = False,
                       bm25_chunks: Sequence[Mapping[str, Any]] = (),
@@ -959,14 +1021,29 @@ def retrieve_evidence(engine: DenseEngine, query: str, filters: Optional[Retriev
     lanes -> RRF -> either ``ids_only`` or the budgeted evidence pack (<= 2 artifacts, <= 2 quotes
     per call, snippet <= 800 chars, total chars <= budget) with the same ``notes.retrieval`` block.
     Payload columns (`content`, `artifact_id`, `kind`, `text`, `speaker`, `start_ts_ms`,
-    `end_ts_ms`) come from the rows registered with the stores."""
+    `end_ts_ms`) come from the rows registered with the stores.
+
+    Two call shapes:
+      ``retrieve_evidence(payload)`` -- the reference's own signature (app/retrieve.py:392): ``payload`` is its
+        ``RetrieveRequest`` (app/schemas.py:86-93; any object with query / intent / filters / budget / return_style /
+        debug), served from the engine installed with :func:`set_default_engine`; the opaque BM25 lanes come from
+        the engine's ``bm25_lanes`` hook when one is registered (pg_search is out of scope, SURVEY 2);
+      ``retrieve_evidence(engine, query, filters, budget, ...)`` -- the explicit form (tests, replay)."""
+    if not isinstance(engine, DenseEngine) and hasattr(engine, "query") and hasattr(engine, "return_style"):
+        payload, eng = engine, default_engine()
+        lanes = ((), ())
+        if getattr(eng, "bm25_lanes", None) is not None:
+            lanes = eng.bm25_lanes(payload.query.strip(), payload.filters)
+        return retrieve_evidence(eng, payload.query, payload.filters, payload.budget, payload.intent,
+                                 payload.return_style, payload.debug, lanes[0], lanes[1])
     from uuid import uuid4
     query_id = str(uuid4())
     budget = budget or Budget()
-    if not query.strip():
+    query = query.strip()                                   # app/retrieve.py:394
+    if not query:
         if return_style == "ids_only":
             return {"query_id": query_id, "retrieved_ids": []}
-        return {"query_id": query_id, "intent": intent, "budget": dict(vars(budget)), "artifacts": [],
+        return {"query_id": query_id, "intent": intent, "budget": _budget_dict(budget), "artifacts": [],
                 "quotes": [], "notes": {"error": "empty query"}}
     inner = retrieve_ids(engine, query, filters, bm25_chunks=bm25_chunks, bm25_artifacts=bm25_artifacts, debug=True)
     dbg = inner["debug"]
@@ -1028,7 +1105,7 @@ def retrieve_evidence(engine: DenseEngine, query: str, filters: Optional[Retriev
     planner = ("lexical_only" if not dense["enabled"] else
                ("ann" if "ann" in (modes.get("chunks"), modes.get("artifact_chunks")) else "exact"))
     response = {
-        "query_id": query_id, "intent": intent, "budget": dict(vars(budget)),
+        "query_id": query_id, "intent": intent, "budget": _budget_dict(budget),
         "artifacts": artifacts_out, "quotes": quotes_out,
         "notes": {"retrieval": {
             "planner": planner,

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 from datetime import datetime, timezone
-from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Set, Tuple
 
 import numpy as np
 
@@ -33,6 +33,22 @@ def to_micros(value) -> int:
         delta = value - _EPOCH
         return (delta.days * 86400 + delta.seconds) * 1_000_000 + delta.microseconds
     return int(value)
+
+
+def _encode_call_id(c):
+    """JSON form of a call id with its type kept (snapshots): UUID, int or str."""
+    import uuid
+    if isinstance(c, uuid.UUID):
+        return ["uuid", str(c)]
+    if isinstance(c, (int, np.integer)):
+        return ["int", int(c)]
+    return ["str", str(c)]
+
+
+def _decode_call_id(c):
+    import uuid
+    kind, value = c
+    return uuid.UUID(value) if kind == "uuid" else (int(value) if kind == "int" else value)
 
 
 def _torch():
@@ -75,6 +91,10 @@ class DenseStore:
         self.call_slots: Dict[Any, int] = {}
         self.call_ids_by_slot: List[Any] = []
         self.tag_bits: Dict[str, int] = {}
+        # tags beyond the 64 bits of the device column ("overflow -> host-side call set"):
+        # tag -> the call slots that carry it; a filter naming such a tag is served as a call-slot set
+        self.overflow_tag_slots: Dict[str, Set[int]] = {}
+        self.slot_tag_mask: Dict[int, int] = {}       # call slot -> its hot-tag mask (the calls.tags of that call)
         # optional payload columns returned with each hit (speaker, text, ... as in the SQL SELECT)
         self.payload: Dict[int, Dict[str, Any]] = {}
         self.synthetic = None   # (seed, first_row) when filled by the on-device generator
@@ -112,18 +132,40 @@ class DenseStore:
             self.call_ids_by_slot.append(call_id)
         return slot
 
-    def bits_of_tags(self, tags: Optional[Iterable[str]], create: bool = False) -> int:
+    def bits_of_tags(self, tags: Optional[Iterable[str]], create: bool = False, slot: Optional[int] = None) -> int:
+        """Hot-tag mask of a tag list.  ``create`` (ingest): unknown tags take the next free bit; once the 64 bits of
+        the device column are taken, further tags are kept host-side as tag -> call-slot sets (``slot`` = the call
+        the row belongs to: tags are a property of the call, ``calls.tags`` in the reference's schema)."""
         mask = 0
         for tag in tags or ():
             bit = self.tag_bits.get(tag)
-            if bit is None and create:
-                if len(self.tag_bits) >= 64:
-                    raise DenseEngineError("tag dictionary is limited to 64 distinct tags", _ffi.CDR_ERR_UNSUPPORTED)
+            if bit is None and create and tag not in self.overflow_tag_slots and len(self.tag_bits) < 64:
                 bit = len(self.tag_bits)
                 self.tag_bits[tag] = bit
             if bit is not None:
                 mask |= 1 << bit
+            elif create:
+                if slot is None:
+                    raise DenseEngineError(f"tag {tag!r} is beyond the 64 device tag bits and needs the row's call "
+                                           "(pass call_ids with call_tags)", _ffi.CDR_ERR_INVALID)
+                self.overflow_tag_slots.setdefault(tag, set()).add(int(slot))
+        if create and slot is not None and mask:
+            self.slot_tag_mask[int(slot)] = self.slot_tag_mask.get(int(slot), 0) | mask
         return mask
+
+    def tag_filter(self, tags: Iterable[str]):
+        """``c.tags && :call_tags`` (app/retrieve.py:112-115) as store codes: (tag_mask, None) when every known
+        tag of the filter has a device bit; (None, sorted call slots) when the filter names an overflow tag -- the
+        calls carrying ANY of the tags, hot ones included, as one call-slot set."""
+        tags = list(tags)
+        mask = self.bits_of_tags(tags)
+        extra = [self.overflow_tag_slots[t] for t in tags if t in self.overflow_tag_slots]
+        if not extra:
+            return mask, None
+        slots = set().union(*extra)
+        if mask:
+            slots.update(sl for sl, m in self.slot_tag_mask.items() if m & mask)
+        return None, sorted(slots)
 
     # ------------------------------------------------------------------ ingest
     def append(self, embeddings, ids: Sequence[int], call_ids: Optional[Sequence[Any]] = None,
@@ -154,7 +196,8 @@ class DenseStore:
             started = np.fromiter((to_micros(t) for t in call_started_at), dtype=np.int64, count=n)
         tags = np.zeros(n, dtype=np.uint64)
         if call_tags is not None:
-            tags = np.fromiter((self.bits_of_tags(t, create=True) for t in call_tags), dtype=np.uint64, count=n)
+            tags = np.fromiter((self.bits_of_tags(t, create=True, slot=int(slots[i]) if call_ids is not None else None)
+                                for i, t in enumerate(call_tags)), dtype=np.uint64, count=n)
         valid_np = None
         if valid is not None:
             valid_np = np.ascontiguousarray(np.asarray(valid, dtype=np.uint8))
@@ -263,7 +306,7 @@ class DenseStore:
         """Snapshot the resident store to a directory: raw fp32 rows (or bf16 bits for bf16-only
         stores) plus the filter columns, validity, dictionaries and payload.  The reference keeps this
         state durable in Postgres; here it is what a restart reloads instead of re-reading the DB."""
-        import json, os, pickle
+        import json, os
         os.makedirs(path, exist_ok=True)
         rows = self.rows
         what = "f32" if self.has_fp32 else "bf16"
@@ -279,11 +322,16 @@ class DenseStore:
         cols = self.read_rows(0, rows, ("ids", "call_slot", "started_at", "tag_bits"))
         np.savez(os.path.join(path, "columns.npz"), valid=valid, **cols)
         meta = dict(table_name=self.table_name, key_field=self.key_field, dim=self.dim, rows=rows, fp32=self.has_fp32,
-                    bf16=self.has_bf16, tag_bits=self.tag_bits, synthetic=self.synthetic)
+                    bf16=self.has_bf16, tag_bits=self.tag_bits, synthetic=self.synthetic,
+                    overflow_tag_slots={t: sorted(v) for t, v in self.overflow_tag_slots.items()},
+                    slot_tag_mask={str(k): v for k, v in self.slot_tag_mask.items()})
         with open(os.path.join(path, "meta.json"), "w") as f:
             json.dump(meta, f)
-        with open(os.path.join(path, "host_state.pkl"), "wb") as f:
-            pickle.dump(dict(call_ids_by_slot=self.call_ids_by_slot, payload=self.payload), f)
+        # host dictionaries as JSON (a snapshot directory is data, never code: nothing in it is unpickled).  Call ids
+        # keep their type through a tag: UUIDs, ints and strings are what the reference's schema can hold.
+        with open(os.path.join(path, "host_state.json"), "w") as f:
+            json.dump(dict(call_ids_by_slot=[_encode_call_id(c) for c in self.call_ids_by_slot],
+                           payload={str(k): v for k, v in self.payload.items()}), f, default=str)
 
     @classmethod
     def load(cls, path: str, device: Optional[int] = None, capacity_rows: Optional[int] = None,
@@ -292,7 +340,7 @@ class DenseStore:
         bf16 values exactly (they are widened to fp32, whose re-normalisation and RN-even rounding
         reproduce the same bits for already-rounded unit rows only approximately, so fp32 snapshots
         are the lossless form)."""
-        import json, os, pickle
+        import json, os
         torch = _torch()
         with open(os.path.join(path, "meta.json")) as f:
             meta = json.load(f)
@@ -302,12 +350,14 @@ class DenseStore:
         cols = np.load(os.path.join(path, "columns.npz"))
         what = "f32" if meta["fp32"] else "bf16"
         mm = np.load(os.path.join(path, f"emb_{what}.npy"), mmap_mode="r")
-        with open(os.path.join(path, "host_state.pkl"), "rb") as f:
-            host = pickle.load(f)
-        store.call_ids_by_slot = host["call_ids_by_slot"]
+        with open(os.path.join(path, "host_state.json")) as f:
+            host = json.load(f)
+        store.call_ids_by_slot = [_decode_call_id(c) for c in host["call_ids_by_slot"]]
         store.call_slots = {c: i for i, c in enumerate(store.call_ids_by_slot)}
-        store.payload = host["payload"]
+        store.payload = {int(k): v for k, v in host["payload"].items()}
         store.tag_bits = {k: int(v) for k, v in meta["tag_bits"].items()}
+        store.overflow_tag_slots = {t: set(v) for t, v in meta.get("overflow_tag_slots", {}).items()}
+        store.slot_tag_mask = {int(k): int(v) for k, v in meta.get("slot_tag_mask", {}).items()}
         store.synthetic = meta["synthetic"]
         with torch.cuda.device(store.device):
             for r0 in range(0, rows, chunk_rows):
@@ -450,10 +500,11 @@ class DenseStore:
 
         call_slots: None = unscoped; [] = ``call_ids == []`` (matches nothing).
         tag_mask: None = no tag filter; 0 = a tag filter whose tags are all unknown (matches nothing).
-        Returns (allow: torch.int32 CUDA tensor [ceil(rows/32)], count: int)."""
+        Returns (allow: torch.int32 CUDA tensor [ceil(capacity/32)], count: int)."""
         torch = _torch()
-        rows = self.rows
-        words = (rows + 31) // 32
+        # the bitmap covers the store's CAPACITY: rows appended after it was built read as "not allowed", and a scan
+        # that already sees the larger row count never reads past it
+        words = (self.capacity + 31) // 32
         bm, n_slots = self.slot_bitmap(call_slots)
         count = ctypes.c_int64(0)
         with torch.cuda.device(self.device):

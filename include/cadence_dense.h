@@ -140,7 +140,11 @@ int32_t cdr_synth_rows(float *out_dev, uint64_t seed, int64_t first_row, int64_t
  *         AND (!has_tag_filter OR (tag_bits & tag_any) != 0)          -- c.tags && :call_tags
  * call_slot_bitmap_host: nullable host bitmap over call slots (n_call_slots bits, uint32 words);
  * a non-NULL all-zero bitmap is `call_ids == []` (matches nothing).
- * out_allow_dev: uint32[ceil(rows/32)] device bitmap, bit r => row r passes.
+ * out_allow_dev: uint32[ceil(CAPACITY/32)] device bitmap (capacity_rows of cdr_store_create), bit r => row r passes;
+ *   bits of rows beyond the row count at the time of the call are written as 0.  Sizing by capacity is what makes a
+ *   bitmap safe to use while the sealed store grows (cdr_store_append): a later scan that already sees the larger row
+ *   count reads "not allowed" for the new rows instead of reading past the bitmap.  Every allow_dev argument below
+ *   must cover ceil(capacity/32) words.
  * out_count_host: number of passing rows (the call synchronises the stream to return it). */
 int32_t cdr_filter_build(cdr_store *s, const uint32_t *call_slot_bitmap_host,
                          int64_t n_call_slots, int32_t has_date_from, int64_t date_from_us,
@@ -195,7 +199,11 @@ int32_t cdr_search_exact_f32_shared_host(cdr_store *s, const float *q_host, int3
  * Serves mode "ann" of app/retrieve.py:290-298 (_configure_dense_session: HNSW ef_search) by
  * brute force on the tensor cores: the score matrix never reaches HBM; survivors are re-scored
  * exactly (fp64 accumulate on the fp32 rows when resident, else on the bf16 rows) and ordered
- * like the exact lane.  q_dev: [nq, dim] fp32 (converted to bf16 internally). */
+ * like the exact lane.  q_dev: [nq, dim] fp32 (converted to bf16 internally).
+ * Asynchronous on `stream` like every device-pointer entry point: a candidate-list overflow (adversarial data) is
+ * detected on the device and the affected queries are re-run on the exact lane (the bf16 scan lane for bf16-only
+ * stores) by launches that read the query list from device memory -- no host round trip.  Rows whose score is NaN
+ * (zero or non-finite embeddings) are admitted as in the exact lane: below every real score, in id order. */
 int32_t cdr_search_batch_bf16(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
                               const uint32_t *allow_dev, double *out_score_dev,
                               int64_t *out_id_dev, int32_t *out_n_dev, void *stream);

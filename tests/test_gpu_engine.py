@@ -27,6 +27,7 @@ from cadence_rag_b200.store import (DenseStore, SYNTH_CALL_PERIOD_US, SYNTH_CORP
                                     SYNTH_QUERY_SEED, SYNTH_ROWS_PER_CALL, SYNTH_T0_US, synth_rows_device)
 from oracle import cpu_oracle as orc  # noqa: E402
 from oracle import ports  # noqa: E402
+from cadence_rag_b200.store import to_micros as store_to_us  # noqa: E402
 
 REL_F64 = 1e-12     # GPU fp64 re-score vs oracle fp64 (summation order only)
 REL_PGV = 1e-5      # north_star: scores within 1e-5 relative of pgvector exact
@@ -148,6 +149,54 @@ def test_filter_bitmap_matches_port():
         got = allow.cpu().numpy().view(np.uint32)
         assert np.array_equal(got[: (n + 31) // 32], orc.rows_to_bitmap(keep)), spec
     s.close()
+
+
+def test_tag_filter_beyond_64_distinct_tags(tmp_path):
+    """`c.tags && :call_tags` over arbitrary TEXT[] (app/retrieve.py:112-115): 100 distinct tags -- 64 get a bit of the
+    device column, the rest live host-side as call-slot sets -- filtered through the facade's
+    _filter_spec + K6 and held to the SQL overlap restated row by row and to ports.filter_rows; the dense lane under
+    such a filter equals the oracle's, and the dictionaries survive a snapshot."""
+    from cadence_rag_b200 import retrieve
+    from cadence_rag_b200.retrieve import DenseEngine, RetrieveFilters
+    rng = np.random.default_rng(17)
+    n, rows_per_call = 3000, 10
+    x = rng.standard_normal((n, 1024)).astype(np.float32)
+    all_tags = [f"topic-{i}" for i in range(100)]
+    call_tags = [list(rng.choice(all_tags, size=rng.integers(0, 4), replace=False)) for _ in range(n // rows_per_call)]
+    s = DenseStore("chunks", n, dim=1024, device=0)
+    s.append(x, ids=np.arange(1, n + 1), call_ids=[f"call-{r // rows_per_call}" for r in range(n)],
+             call_tags=[call_tags[r // rows_per_call] for r in range(n)])
+    s.finalize()
+    assert len(s.tag_bits) == 64 and len(s.overflow_tag_slots) >= 30
+    hot, cold = list(s.tag_bits)[:3], list(s.overflow_tag_slots)[:3]
+    eng = DenseEngine(); eng.register(s)
+    cols = s.read_rows(0, n, ("call_slot", "started_at", "tag_bits"))
+    q = rng.standard_normal(1024).astype(np.float32)
+    cases = [hot[:1], cold[:1], [hot[0], cold[0]], cold, hot + cold, ["never-seen"], ["never-seen", cold[1]]]
+    for tags in cases:
+        for call_ids in (None, [f"call-{i}" for i in range(0, 300, 2)]):
+            filt = RetrieveFilters(call_tags=tags, call_ids=call_ids)
+            want_keep = np.array([bool(set(call_tags[r // rows_per_call]) & set(tags))
+                                  and (call_ids is None or (r // rows_per_call) % 2 == 0) for r in range(n)])
+            with eng.connect() as conn:
+                resolved = retrieve._resolve_call_ids(conn, filt)
+                allow, count = retrieve._filter_bitmap(conn, "chunks", filt, resolved)
+                assert count == int(want_keep.sum()), (tags, call_ids is None)
+                if allow is not None:
+                    assert np.array_equal(allow.cpu().numpy().view(np.uint32)[: (n + 31) // 32], orc.rows_to_bitmap(want_keep))
+                spec = retrieve._filter_spec(s, filt, resolved)
+                port_keep = ports.filter_rows(cols["call_slot"], cols["started_at"], cols["tag_bits"], None,
+                                              call_slots=spec["call_slots"], tag_mask=spec["tag_mask"])
+                assert np.array_equal(port_keep, want_keep)
+                rows = retrieve._fetch_chunks_dense(conn, q, filt, resolved, "exact", 50)
+            w_ids, _ = orc.exact_scan(q, x, 50, allow=orc.rows_to_bitmap(want_keep))
+            assert [r["chunk_id"] for r in rows] == w_ids.tolist()
+    s.save(str(tmp_path / "snap"))
+    r = DenseStore.load(str(tmp_path / "snap"), device=0)
+    assert r.tag_bits == s.tag_bits and r.overflow_tag_slots == s.overflow_tag_slots and r.slot_tag_mask == s.slot_tag_mask
+    assert r.call_ids_by_slot == s.call_ids_by_slot
+    assert r.tag_filter([hot[0], cold[0]]) == s.tag_filter([hot[0], cold[0]])
+    r.close(); s.close()
 
 
 # =================================================================== K1 exact scan parity
@@ -833,6 +882,114 @@ def test_live_store_backfill_and_growth(monkeypatch):
     allow, cnt = live.filter_bitmap(call_slots=[live.slot_of_call("call-3"), live.slot_of_call("call-31")])
     assert cnt == 200 - int(valid_all[300:400].size - valid_all[300:400].sum())
     live.close(); whole.close()
+
+
+def test_growth_reaches_the_tech_and_hybrid_lanes(monkeypatch):
+    """A sealed store that grows must serve the new rows on EVERY lane, as the reference's SQL sees new rows at once:
+    the device tech-token index is rebuilt when the store or the host index changed (DenseEngine.device_tech_index),
+    a stale copy refuses to serve, and requests with more than 32 known tokens go to the host index."""
+    monkeypatch.setattr(settings, "embeddings_dim", 1024)
+    n, n2 = 2000, 600
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, n + n2)
+    ids = np.arange(1, n + n2 + 1, dtype=np.int64)
+    t0 = datetime(2026, 1, 1, tzinfo=timezone.utc)
+    started = [t0 + timedelta(hours=r // 50) for r in range(n + n2)]          # newer calls = larger ids
+    toks = [[f"TOK-{r % 7}", f"ERR-{r % 45}"] for r in range(n + n2)]
+    store = DenseStore("chunks", n + n2, dim=1024, device=0)
+    index = TechTokenIndex()
+    store.append(x[:n], ids=ids[:n], call_ids=[f"c{r // 50}" for r in range(n)], call_started_at=started[:n])
+    store.finalize()
+    for r in range(n):
+        index.add_row(r, toks[r])
+    eng = DenseEngine(); eng.register(store, index)
+    emb = embeddings.SyntheticEmbedder(seed=SYNTH_QUERY_SEED, dim=1024)
+    embeddings.set_embedder(emb)
+    try:
+        old_dev = eng.device_tech_indexes["chunks"]
+        q = "why did TOK-3 fail with ERR-12"
+        before = retrieve.retrieve_ids(eng, q, None, debug=True)
+        # growth: the newest calls now own the top of the tech lane (ORDER BY call_started_at DESC, id ASC)
+        store.append(x[n:], ids=ids[n:], call_ids=[f"c{r // 50}" for r in range(n, n + n2)], call_started_at=started[n:])
+        for r in range(n, n + n2):
+            index.add_row(r, toks[r])
+        assert old_dev.stale()
+        with pytest.raises(DenseEngineError):
+            old_dev.encode_tokens([["TOK-3"]])
+        for debug in (True, False):
+            after = retrieve.retrieve_ids(eng, q, None, debug=debug)
+            assert eng.device_tech_indexes["chunks"] is not old_dev and not eng.device_tech_indexes["chunks"].stale()
+            keep = np.ones(n + n2, dtype=bool)
+            want_tech = ports.tech_lane(toks, ids, np.array([store_to_us(t) for t in started]), keep,
+                                        retrieve.extract_tech_tokens(q), 50)
+            qv = np.array(emb([q]).vectors[0], dtype=np.float32)
+            want_dense, _ = orc.exact_scan(qv, x, 50)
+            want = ports.rrf_merge({"bm25": [], "tech_tokens": [{"chunk_id": i} for i in want_tech],
+                                    "dense": [{"chunk_id": int(i)} for i in want_dense]}, "chunk_id")
+            want_ids = [f"chunk:{r['chunk_id']}" for r, _, _ in want]
+            assert after["retrieved_ids"] == want_ids
+            assert after["retrieved_ids"] != before["retrieved_ids"]
+        assert max(want_tech) > n                                  # new rows really are in the lane
+        # more known tokens than the kernel's table: the host index serves, same answer as the restated SQL
+        many = " ".join(f"ERR-{i}" for i in range(40))
+        got = retrieve.retrieve_ids(eng, many, None, debug=True)
+        want_tech = ports.tech_lane(toks, ids, np.array([store_to_us(t) for t in started]), keep,
+                                    retrieve.extract_tech_tokens(many), 50)
+        assert len(retrieve.extract_tech_tokens(many)) == 41                  # the 40 codes + the bare "ERR"
+        assert [r["chunk_id"] for r in got["debug"]["lanes"]["tech_tokens"]["chunks"]] == want_tech
+        assert retrieve.retrieve_ids(eng, many, None)["retrieved_ids"] == got["retrieved_ids"]
+    finally:
+        embeddings.set_embedder(None)
+        eng.close(); store.close()
+
+
+def test_concurrent_append_filter_and_search():
+    """A sealed store grows from one thread while another builds filter bitmaps and searches with them.  Bitmaps cover
+    the store's capacity and every entry point snapshots the row count under the store lock, so a scan that already
+    sees more rows than the bitmap was built for reads "not allowed" for them -- never past the bitmap."""
+    import threading
+    n0, step, cap = 20_000, 2_000, 60_000
+    x = orc.synth_rows(SYNTH_CORPUS_SEED, 0, cap)
+    store = DenseStore("chunks", cap, dim=1024, device=0)
+    store.append(x[:n0], ids=np.arange(1, n0 + 1), call_ids=[r // 100 for r in range(n0)])
+    store.finalize()
+    errors, done = [], threading.Event()
+
+    def writer():
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for r0 in range(n0, cap, step):
+                    store.append(x[r0:r0 + step], ids=np.arange(r0 + 1, r0 + step + 1), call_ids=[r // 100 for r in range(r0, r0 + step)])
+        except Exception as exc:   # noqa: BLE001
+            errors.append(repr(exc))
+        finally:
+            done.set()
+
+    qs = orc.synth_rows(SYNTH_QUERY_SEED, 9, 3)
+    th = threading.Thread(target=writer)
+    th.start()
+    rounds = 0
+    try:
+        with torch.cuda.stream(torch.cuda.Stream()):
+            while not done.is_set() or rounds < 3:
+                slots = list(range(0, 150, 3))
+                allow, count = store.filter_bitmap(call_slots=slots)
+                assert allow.numel() == (cap + 31) // 32
+                ids, sc, cnt = store.search_exact(qs, 50, allow)
+                assert np.all(cnt == 50) and count == 5000
+                assert all((int(i) - 1) // 100 in slots for i in ids.reshape(-1))     # only rows the bitmap allows
+                b_ids, _, b_cnt = store.search_batch(qs, 50, allow)
+                assert np.all(b_cnt == 50) and all((int(i) - 1) // 100 in slots for i in b_ids.reshape(-1))
+                rounds += 1
+    finally:
+        th.join()
+    assert not errors, errors
+    assert store.rows == cap
+    # and the grown store answers like the oracle over all rows
+    ids, sc, cnt = store.search_exact(qs, 50)
+    for i in range(3):
+        w_ids, _ = orc.exact_scan(qs[i], x, 50)
+        assert ids[i].tolist() == w_ids.tolist()
+    store.close()
 
 
 # =================================================================== full size (BASELINE C2): 1M x 1024

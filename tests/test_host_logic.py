@@ -9,6 +9,7 @@ import json
 import os
 import re
 import subprocess
+import sys
 from datetime import datetime, timezone
 from uuid import uuid4
 
@@ -415,6 +416,44 @@ def test_dense_lane_of_a_request_group(monkeypatch):
 
 
 # ---------------------------------------------------------------- /retrieve response contract vs the reference's own code
+def _ref_request_models():
+    """pydantic request models with the reference's fields and defaults (app/schemas.py:71-93); when the reference
+    tree is present (this container) the REAL classes are used instead."""
+    try:
+        sys.path.insert(0, "/root/reference")
+        from app.schemas import Budget as B, RetrieveRequest as RR       # noqa: WPS433
+        return B, RR
+    except Exception:
+        from typing import Literal, Optional
+        from pydantic import BaseModel, Field
+
+        class B(BaseModel):
+            max_evidence_items: int = 8
+            max_total_chars: int = 6000
+
+        class RR(BaseModel):
+            query: str
+            intent: Literal["auto", "decision", "action_items", "who_said", "troubleshooting", "status"] = "auto"
+            filters: Optional[dict] = None
+            budget: B = Field(default_factory=B)
+            return_style: Literal["evidence_pack_json", "ids_only"] = "evidence_pack_json"
+            debug: bool = False
+        return B, RR
+    finally:
+        if sys.path and sys.path[0] == "/root/reference":
+            sys.path.pop(0)
+
+
+_RefBudget, _RefRetrieveRequest = _ref_request_models()
+
+
+def test_retrieve_evidence_payload_form_needs_an_engine():
+    from cadence_rag_b200 import retrieve as R
+    R.set_default_engine(None)
+    with pytest.raises(pkg.DenseEngineError):
+        R.retrieve_evidence(_RefRetrieveRequest(query="anything"))
+
+
 def test_retrieve_evidence_matches_reference_golden(monkeypatch, golden_dir):
     """tests/golden/reference_evidence.json holds the REFERENCE's retrieve_evidence (app/retrieve.py:392-688, run
     live by tests/golden/make_golden_evidence.py) on canned lane rows.  The same lanes replayed through
@@ -483,6 +522,18 @@ def test_retrieve_evidence_matches_reference_golden(monkeypatch, golden_dir):
                                   bm25_chunks=rows_of(case, "bm25_chunks", "chunks", "chunk_id"),
                                   bm25_artifacts=rows_of(case, "bm25_artifacts", "artifact_chunks", "artifact_chunk_id"))
         got = json.loads(json.dumps(got, default=str))
+        # the reference's own call shape, retrieve_evidence(payload: RetrieveRequest) (app/retrieve.py:392), with
+        # pydantic request objects shaped like app/schemas.py:71-93, must give the same response
+        R.set_default_engine(eng := _Engine())
+        eng.bm25_lanes = lambda q, f, c=case: (rows_of(c, "bm25_chunks", "chunks", "chunk_id"),
+                                               rows_of(c, "bm25_artifacts", "artifact_chunks", "artifact_chunk_id"))
+        payload = _RefRetrieveRequest(query=case["query"], intent=case["intent"], return_style=case["return_style"],
+                                      debug=case["debug"], budget=_RefBudget(max_evidence_items=case["budget"][0],
+                                                                             max_total_chars=case["budget"][1]))
+        got2 = json.loads(json.dumps(R.retrieve_evidence(payload), default=str))
+        R.set_default_engine(None)
+        got2.pop("query_id"); g1 = dict(got); g1.pop("query_id")
+        assert got2 == g1, case["query"]
         assert set(want) - {"debug"} <= set(got), (case["query"], set(want) - set(got))
         for key in want:
             if key == "query_id":
@@ -530,6 +581,9 @@ def test_resolve_call_ids_and_filter_clause_match_reference_golden(golden_dir):
 
         def bits_of_tags(self, tags, create=False):
             return sum(1 << {"a": 0, "b": 1}.get(t, 63) for t in tags if t in ("a", "b"))
+
+        def tag_filter(self, tags):
+            return self.bits_of_tags(tags), None
 
     for case in gold["filter_clause"]:
         spec = case["filters"]
