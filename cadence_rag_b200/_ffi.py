@@ -93,6 +93,7 @@ SIGNATURES = {
     "cdr_peer_group_connect": (_i32, [_vp, _vp]),
     "cdr_peer_group_destroy": (_i32, [_vp]),
     "cdr_peer_exchange_merge": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cdr_search_sharded": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_rrf_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_rrf_merge_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "cdr_tech_index_create": (_i32, [ctypes.POINTER(_vp), _vp, _vp, _i32, _vp, _vp]),
@@ -113,6 +114,7 @@ SIGNATURES = {
 CDR_DENSE_LANE_EXACT_F32 = 0
 CDR_DENSE_LANE_BATCH_BF16 = 1
 CDR_DENSE_LANE_SCAN_BF16 = 2
+CDR_DENSE_LANE_EXACT_F32_SHARED = 3     # cdr_search_sharded only
 
 
 class FilterSpec(ctypes.Structure):

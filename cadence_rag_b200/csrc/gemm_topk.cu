@@ -448,7 +448,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int64_t row0 = nt * kBlockN;
             const int q = mt * kBlockM + et;
             const bool q_ok = q < p.nq;
-            const bool live = q_ok && p.debug_no_append != 1;
+            const bool live = q_ok && (p.debug_no_append == 0 || p.debug_no_append == 2 || p.debug_no_append == 3);
             const float tau = live ? __ldg(&p.tau[q]) : __int_as_float(0x7f800000);   // +inf: never passes
             const uint64_t tau_key = live ? __ldg(&p.tau_key[q]) : ~0ull;
             int64_t lim = p.n_rows - row0;                        // valid columns in this tile
@@ -461,8 +461,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll 1
             for (int c = 0; c < kBlockN / 32; ++c) {
                 __syncwarp();
+                if (p.debug_no_append == 5) continue;             // timing aid: no epilogue work at all (mainloop alone)
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
+                if (p.debug_no_append == 4) {                     // timing aid: TMEM reads only, no maxima
+                    if (v[0] == 12345.678f && v[31] == 8765.4321f) buf_q[et] = 1;   // keeps the load alive
+                    continue;
+                }
                 if (c * 32 >= lim) continue;                      // warp-uniform (tail tile)
                 // fast path: the maximum of the chunk as four 8-column sub-maxima (3-input max: 18 instead of 31
                 // operations per chunk) against the query's threshold.  !(m < tau) also holds for a NaN maximum

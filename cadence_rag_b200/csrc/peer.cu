@@ -33,6 +33,10 @@ struct cdr_peer_group {
     unsigned char *peer[CDR_PEER_MAX_RANKS] = {nullptr};   // mapped base of every rank's buffer (own included)
     bool connected = false;
     uint32_t epoch = 0;
+    // local lists of cdr_search_sharded (this rank's [max_nq, max_k] results between the lane and the exchange)
+    double *loc_score = nullptr;
+    int64_t *loc_id = nullptr;
+    int32_t *loc_n = nullptr;
 };
 
 namespace {
@@ -170,12 +174,15 @@ extern "C" int32_t cdr_peer_group_create(cdr_peer_group **out, int32_t device, i
     pg->bytes = pg->flags_off + (size_t)world * max_nq * 4;
     cudaError_t e = cudaMalloc(&pg->local, pg->bytes);
     if (e == cudaSuccess) e = cudaMemset(pg->local, 0, pg->bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&pg->loc_score, (size_t)max_nq * max_k * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&pg->loc_id, (size_t)max_nq * max_k * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&pg->loc_n, (size_t)max_nq * 4);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, pg->local);
     if (e != cudaSuccess) {
         cdr_set_error("cdr_peer_group_create: %s", cudaGetErrorString(e));
-        cudaFree(pg->local);
+        cudaFree(pg->local); cudaFree(pg->loc_score); cudaFree(pg->loc_id); cudaFree(pg->loc_n);
         delete pg;
         return e == cudaErrorMemoryAllocation ? CDR_ERR_OOM : CDR_ERR_CUDA;
     }
@@ -217,7 +224,7 @@ extern "C" int32_t cdr_peer_group_destroy(cdr_peer_group *pg)
     cudaDeviceSynchronize();
     for (int r = 0; r < pg->world; ++r)
         if (r != pg->rank && pg->peer[r]) cudaIpcCloseMemHandle(pg->peer[r]);
-    cudaFree(pg->local);
+    cudaFree(pg->local); cudaFree(pg->loc_score); cudaFree(pg->loc_id); cudaFree(pg->loc_n);
     delete pg;
     return CDR_OK;
 }
@@ -254,6 +261,40 @@ extern "C" int32_t cdr_peer_exchange_merge(cdr_peer_group *pg, const double *sco
         p.out_score = out_score_dev + (size_t)q0 * k; p.out_id = out_id_dev + (size_t)q0 * k; p.out_n = out_n_dev + q0;
         peer_publish_merge_kernel<<<m, 256, smem, (cudaStream_t)stream>>>(p);
         CDR_LAUNCH_CHECK();
+    }
+    return CDR_OK;
+}
+
+extern "C" int32_t cdr_search_sharded(cdr_store *s, cdr_peer_group *pg, int32_t lane, const float *q_dev, int32_t nq,
+                                      int32_t k, const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev,
+                                      int32_t *out_n_dev, void *stream)
+{
+    typedef int32_t (*lane_fn)(cdr_store *, const float *, int32_t, int32_t, const uint32_t *, double *, int64_t *,
+                               int32_t *, void *);
+    lane_fn fn = nullptr;
+    switch (lane) {
+    case CDR_DENSE_LANE_EXACT_F32: fn = cdr_search_exact_f32; break;
+    case CDR_DENSE_LANE_EXACT_F32_SHARED: fn = cdr_search_exact_f32_shared; break;
+    case CDR_DENSE_LANE_SCAN_BF16: fn = cdr_search_scan_bf16; break;
+    case CDR_DENSE_LANE_BATCH_BF16: fn = cdr_search_batch_bf16; break;
+    default: break;
+    }
+    CDR_REQUIRE(fn != nullptr, CDR_ERR_INVALID, "cdr_search_sharded: unknown lane %d", lane);
+    CDR_REQUIRE(s != nullptr, CDR_ERR_INVALID, "cdr_search_sharded: store is NULL");
+    if (pg == nullptr || pg->world == 1)
+        return fn(s, q_dev, nq, k, allow_dev, out_score_dev, out_id_dev, out_n_dev, stream);
+    CDR_REQUIRE(pg->connected, CDR_ERR_STATE, "cdr_search_sharded: group not connected");
+    CDR_REQUIRE(pg->device == s->device, CDR_ERR_INVALID, "cdr_search_sharded: store on device %d, group on %d", s->device,
+                pg->device);
+    CDR_REQUIRE(k >= 1 && k <= pg->max_k, CDR_ERR_INVALID, "cdr_search_sharded: k=%d outside [1,%d]", k, pg->max_k);
+    CDR_REQUIRE(nq >= 0 && out_score_dev && out_id_dev && out_n_dev, CDR_ERR_INVALID, "cdr_search_sharded: bad arguments");
+    for (int q0 = 0; q0 < nq; q0 += pg->max_nq) {
+        const int m = nq - q0 < pg->max_nq ? nq - q0 : pg->max_nq;
+        int rc = fn(s, q_dev + (size_t)q0 * s->dim, m, k, allow_dev, pg->loc_score, pg->loc_id, pg->loc_n, stream);
+        if (rc != CDR_OK) return rc;
+        rc = cdr_peer_exchange_merge(pg, pg->loc_score, pg->loc_id, pg->loc_n, m, k, out_score_dev + (size_t)q0 * k,
+                                     out_id_dev + (size_t)q0 * k, out_n_dev + q0, stream);
+        if (rc != CDR_OK) return rc;
     }
     return CDR_OK;
 }

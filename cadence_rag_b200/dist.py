@@ -162,6 +162,8 @@ class ShardedSearcher:
         """queries_dev: [nq, dim] CUDA tensor replicated on every rank.  Returns the global
         (ids, scores, n) on every rank.  mode: "exact" (fp32 scan; shared: see DenseStore.search_exact), "scan_bf16"
         (single-query ann lane) or "batch" (bf16 tensor-core lane)."""
+        if self.peer is not None and k <= self.peer.max_k and getattr(queries_dev, "is_cuda", False):
+            return self._search_one_call(queries_dev, k, allow, mode, shared)
         if mode == "exact":
             ids, scores, n = self.store.search_exact(queries_dev, k, allow, shared=shared)
         elif mode == "scan_bf16":           # mode "ann" for single queries: one scan of the bf16 rows per query
@@ -174,3 +176,23 @@ class ShardedSearcher:
             return self.peer.exchange_merge(ids, scores, n, k)
         g_sc, g_id, g_n = gather_shard_results(ids, scores, n, self.group)
         return merge_shard_results(g_sc, g_id, g_n, k)
+
+    def _search_one_call(self, queries_dev, k: int, allow, mode: str, shared: bool):
+        """Peer transport: the local lane + the K4p exchange + merge through ONE C call (``cdr_search_sharded``), so
+        the step's launches are enqueued back to back instead of across two trips through Python."""
+        import torch
+        lane = {"exact": _ffi.CDR_DENSE_LANE_EXACT_F32_SHARED if shared else _ffi.CDR_DENSE_LANE_EXACT_F32,
+                "scan_bf16": _ffi.CDR_DENSE_LANE_SCAN_BF16}.get(mode, _ffi.CDR_DENSE_LANE_BATCH_BF16)
+        q = queries_dev.to(dtype=torch.float32).contiguous()
+        if q.dim() == 1:
+            q = q.unsqueeze(0)
+        if int(q.shape[1]) != self.store.dim:
+            raise _ffi.DenseEngineError(f"query dim {int(q.shape[1])} != store dim {self.store.dim}")
+        nq, dev = int(q.shape[0]), q.device
+        out_sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
+        out_id = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        out_n = torch.empty((nq,), dtype=torch.int32, device=dev)
+        _ffi.check(_ffi.lib().cdr_search_sharded(self.store.handle, self.peer._h, lane, _ffi.ptr(q), nq, k, _ffi.ptr(allow),
+                                                 _ffi.ptr(out_sc), _ffi.ptr(out_id), _ffi.ptr(out_n),
+                                                 _ffi.stream_ptr(torch.cuda.current_stream(dev))), "cdr_search_sharded")
+        return out_id, out_sc, out_n

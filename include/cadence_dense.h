@@ -242,6 +242,18 @@ int32_t cdr_peer_exchange_merge(cdr_peer_group *g, const double *scores_dev, con
                                 const int32_t *n_dev, int32_t nq, int32_t k, double *out_score_dev,
                                 int64_t *out_id_dev, int32_t *out_n_dev, void *stream);
 
+/* One rank's whole step over a row-sharded table in ONE call: the local lane over this rank's shard followed by the
+ * K4p exchange + merge, enqueued back to back on `stream` (the local lists live in the group's own buffers).  On a
+ * small shard a single-query request is a few tens of microseconds of kernels; issuing its launches from one C call
+ * keeps the GPU from idling between them while the host returns to Python and calls again.
+ * lane: CDR_DENSE_LANE_EXACT_F32 (one scan per query), CDR_DENSE_LANE_EXACT_F32_SHARED (shared reads for a batch),
+ * CDR_DENSE_LANE_SCAN_BF16 or CDR_DENSE_LANE_BATCH_BF16.  g == NULL (one rank): the lane alone.  Same arguments,
+ * results and ordering as the lane's own entry point followed by cdr_peer_exchange_merge; k <= the group's max_k. */
+#define CDR_DENSE_LANE_EXACT_F32_SHARED 3
+int32_t cdr_search_sharded(cdr_store *s, cdr_peer_group *g, int32_t lane, const float *q_dev, int32_t nq, int32_t k,
+                           const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev,
+                           int32_t *out_n_dev, void *stream);
+
 /* ---- K5: reciprocal-rank fusion -------------------------------------------------------------
  * Replaces app/retrieve.py:245-260 (_rrf_merge), bit-exact: for lanes in order (bm25,
  * tech_tokens, dense; app/retrieve.py:537-547) and ranks from 1,

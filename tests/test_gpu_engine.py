@@ -925,7 +925,7 @@ def test_growth_reaches_the_tech_and_hybrid_lanes(monkeypatch):
             want_dense, _ = orc.exact_scan(qv, x, 50)
             want = ports.rrf_merge({"bm25": [], "tech_tokens": [{"chunk_id": i} for i in want_tech],
                                     "dense": [{"chunk_id": int(i)} for i in want_dense]}, "chunk_id")
-            want_ids = [f"chunk:{r['chunk_id']}" for r, _, _ in want]
+            want_ids = ports.ids_only_order([], want)              # ids_only combine: (-score, kind, id)
             assert after["retrieved_ids"] == want_ids
             assert after["retrieved_ids"] != before["retrieved_ids"]
         assert max(want_tech) > n                                  # new rows really are in the lane
@@ -1127,6 +1127,57 @@ def test_full_size_10m_properties(monkeypatch):
         for qi in range(2):
             w_ids, w_sc = orc.exact_scan(qs[qi], xw[:2000], k, ids=np.arange(w0 + 1, w0 + 2001), variant=orc.VARIANT_F64)
             assert f_ids[qi].tolist() == w_ids.tolist() and np.allclose(f_sc[qi], w_sc, rtol=REL_F64)
+    finally:
+        s.close()
+
+
+def test_full_size_10m_c_oracle_pass(golden_dir):
+    """The exact lane at the north-star size (10 M x 1024, single-query scans) against a FULL pass of the C oracle over
+    the same 41 GB corpus: tests/golden/dense_10m.json holds the oracle's top-51 of headline queries 0..3 for both
+    variants (fp64 accumulate = ground-truth order, and the pgvector-restated fp32 loop), generated by
+    tests/golden/make_golden_dense_10m.py (streamed in 250 000-row chunks, ~2 minutes on 8 cores).  The engine must
+    return the fp64 list -- ids identical, scores within 1e-12 -- and agree with the fp32 variant on every position
+    outside near-ties (< 2e-6 relative); for these seeds the two variants agree on every id, and the
+    only near-tie is one adjacent pair of query 0 (gap 1.92e-6 at ranks 40/41).  With CADENCE_TEST_FULL_C_PASS=1 the
+    pass is repeated live for query 0 instead of read from the fixture.  pgvector-generated goldens remain the open
+    item: this pins the engine to the restatement at full size."""
+    n, k, chunk = 10_000_000, 50, 250_000
+    free, _total = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of free HBM")
+    with open(os.path.join(golden_dir, "dense_10m.json")) as f:
+        gold = json.load(f)
+    assert gold["rows"] == n and gold["corpus_seed"] == SYNTH_CORPUS_SEED and gold["query_seed"] == SYNTH_QUERY_SEED
+    s = make_synth_store(n, bf16=False)
+    try:
+        qs = orc.synth_rows(SYNTH_QUERY_SEED, 0, len(gold["queries"]))
+        ids, sc, cnt = s.search_exact(qs, k)
+        one = s.search_exact(qs[0], k)                      # the single-query launch (BASELINE configs[1] shape)
+        assert np.array_equal(one[0][0], ids[0]) and np.array_equal(one[1][0].view(np.uint64), sc[0].view(np.uint64))
+        ambiguous = 0
+        for rec in gold["queries"]:
+            qi = rec["query_row"]
+            w_ids = np.array(rec["f64"]["ids"]); w_sc = np.array([float.fromhex(h) for h in rec["f64"]["scores_hex"]])
+            if qi == 0 and os.environ.get("CADENCE_TEST_FULL_C_PASS") == "1":
+                acc = []
+                for r0 in range(0, n, chunk):
+                    x = orc.synth_rows(SYNTH_CORPUS_SEED, r0, chunk)
+                    acc.append(orc.exact_scan(qs[0], x, k + 14, ids=np.arange(r0 + 1, r0 + chunk + 1, dtype=np.int64)))
+                a_ids = np.concatenate([a for a, _ in acc]); a_sc = np.concatenate([b for _, b in acc])
+                order = np.lexsort((a_ids, -a_sc))[:k + 1]
+                assert a_ids[order].tolist() == w_ids.tolist()
+            assert int(cnt[qi]) == k and ids[qi].tolist() == w_ids[:k].tolist()
+            assert np.allclose(sc[qi], w_sc[:k], rtol=REL_F64, atol=0)
+            gaps = np.abs(np.diff(w_sc)) / np.abs(w_sc[:-1])            # 50 gaps over the top 51: includes the k / k+1 boundary
+            amb = np.zeros(k + 1, dtype=bool)
+            amb[:-1] |= gaps < AMBIG
+            amb[1:] |= gaps < AMBIG
+            ambiguous += int(amb[:k].sum())
+            p_ids = np.array(rec["pgv32"]["ids"]); p_sc = np.array([float.fromhex(h) for h in rec["pgv32"]["scores_hex"]])
+            assert [i for i, a in zip(p_ids[:k].tolist(), amb) if not a] == [i for i, a in zip(ids[qi].tolist(), amb) if not a]
+            assert p_ids[:k].tolist() == ids[qi].tolist()           # (and for these seeds: on the near-tie as well)
+            assert np.allclose(sc[qi], p_sc[:k], rtol=REL_PGV, atol=0)
+        assert ambiguous == 2                                       # the one adjacent pair of query 0
     finally:
         s.close()
 
