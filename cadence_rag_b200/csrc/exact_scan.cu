@@ -29,7 +29,32 @@
 #include <cstdlib>
 #include <mutex>
 
+#ifndef CDR_BF16_FHFMA
+#define CDR_BF16_FHFMA 1      // 0: the widening (shift / mask + FFMA) form of the bf16 scan, for A/B builds
+#endif
+
 namespace {
+
+// two bf16 values (RN-even) in one register, first value in the low half
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+// acc += row.lo * query.lo + row.hi * query.hi, fp32 accumulate, low half first (two FHFMA.BF16)
+__device__ __forceinline__ float fhfma_bf16x2(uint32_t row, uint32_t query, float acc)
+{
+    asm("{\n"
+        ".reg .b16 rl, rh, ql, qh;\n"
+        "mov.b32 {rl, rh}, %1;\n"
+        "mov.b32 {ql, qh}, %2;\n"
+        "fma.rn.f32.bf16 %0, rl, ql, %0;\n"
+        "fma.rn.f32.bf16 %0, rh, qh, %0;\n"
+        "}\n"
+        : "+f"(acc)
+        : "r"(row), "r"(query));
+    return acc;
+}
 
 constexpr int kConsumerWarps = 8;
 constexpr int kMaxStages = 6;
@@ -484,6 +509,18 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
             }
             qn = warp_sum_f32(qn);
             const float inv_q = __fdiv_rn(1.0f, __fsqrt_rn(qn));
+#if CDR_BF16_FHFMA
+            // The query as bf16 pairs (RN-even, like the tensor-core lane's): a row element and its query element then
+            // meet in ONE mixed-precision FMA (fma.rn.f32.bf16, SASS FHFMA.BF16 with .H0/.H1 operand selectors, fp32
+            // accumulate) -- 8 instructions per 16-byte shared-memory load instead of 8 shift/mask + 8 FFMA, which left
+            // this scan issue-bound at 5.9-6.7 TB/s.  Candidate scores only: the survivors are re-scored in fp64.
+            uint32_t qh[JB][4];
+#pragma unroll
+            for (int j = 0; j < JB; ++j) {
+                qh[j][0] = pack_bf16x2(qa[j].x, qa[j].y); qh[j][1] = pack_bf16x2(qa[j].z, qa[j].w);
+                qh[j][2] = pack_bf16x2(qb[j].x, qb[j].y); qh[j][3] = pack_bf16x2(qb[j].z, qb[j].w);
+            }
+#endif
             WarpTopK<NPL> top;
             top.init(lists + warp * KC, lane);
             for (;; ++it) {
@@ -522,6 +559,14 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                     for (int r = 0; r < RPW; ++r) {
                         const uint4 v = tv[r * (DIM / 8) + j * 32];
                         float a = acc[r][j & 1];
+#if CDR_BF16_FHFMA
+                        a = fhfma_bf16x2(v.x, qh[j][0], a);
+                        a = fhfma_bf16x2(v.y, qh[j][1], a);
+                        a = fhfma_bf16x2(v.z, qh[j][2], a);
+                        a = fhfma_bf16x2(v.w, qh[j][3], a);
+                        acc[r][j & 1] = a;
+                        continue;
+#endif
                         a = fmaf(__uint_as_float(v.x << 16), qa[j].x, a);
                         a = fmaf(__uint_as_float(v.x & 0xFFFF0000u), qa[j].y, a);
                         a = fmaf(__uint_as_float(v.y << 16), qa[j].z, a);
@@ -535,6 +580,38 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
+                if constexpr (RPW == 4) {
+                    // the 4 dot products of the warp are reduced TOGETHER (as in the shared-read path): at offsets 16 and
+                    // 8 a lane keeps half of its values and hands the rest to its partner, so the eight lanes of group
+                    // g = lane / 8 end up owning value g -- 6 shuffles instead of 20; the group then packs and tests its
+                    // candidate in parallel and the rare survivors are inserted one by one
+                    float a4[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) a4[r] = acc[r][0] + acc[r][1];
+                    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+                    float h2[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        h2[i] = (b4 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a4[i] : a4[i + 2], 16);
+                    float dot = (b3 ? h2[1] : h2[0]) + __shfl_xor_sync(0xffffffffu, b3 ? h2[0] : h2[1], 8);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                    const int vr = lane >> 3;                  // value (row) this 8-lane group owns: bit4 -> +2, bit3 -> +1
+                    int64_t s_row = gather ? (int64_t)g_row[0] : row0;
+#pragma unroll
+                    for (int r = 1; r < 4; ++r)
+                        if (vr == r) s_row = gather ? (int64_t)g_row[r] : row0 + r;
+                    const bool s_ok = (s_row < p.n_rows) && ((allow_bits >> vr) & 1u);
+                    const uint64_t key = cdr_pack_key(dot * inv_q, (uint32_t)s_row);
+                    unsigned pend = __ballot_sync(0xffffffffu, s_ok && key > top.tau) & 0x01010101u;
+                    while (pend) {                             // rare; warp-uniform
+                        const int src = __ffs(pend) - 1;
+                        pend &= pend - 1;
+                        const uint64_t k1 = __shfl_sync(0xffffffffu, key, src);
+                        if (k1 > top.tau) top.push(k1, lane);  // re-tested: an earlier insert may have raised tau
+                    }
+                } else {
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const int64_t row = gather ? (int64_t)g_row[r] : row0 + r;
@@ -544,6 +621,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                         const uint64_t key = cdr_pack_key(dot * inv_q, (uint32_t)row);
                         if (key > top.tau) top.push(key, lane);
                     }
+                }
                 }
             }
         } else {

@@ -383,7 +383,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         // this CTA's half of the corpus box (128 rows), delivered to both CTAs
                         const int half = kBlockN / kCluster;
                         tma_load_2d_mc(a + kABytes + (size_t)crank * (kBBytes / kCluster), &map_x, kb * kBlockK,
-                                       (int)(nt * kBlockN) + (int)crank * half, &full_bar[s], (uint16_t)0x3);
+                                       (int)(nt * kBlockN) + (int)crank * half, &full_bar[s], (uint16_t)((1u << kCluster) - 1u));
                     }
                 }
             }
@@ -424,7 +424,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     // smem stage free when these MMAs retire (in every CTA that TMA-writes it)
                     if (k2Sm) umma_commit_2sm_mc(&empty_bar[s], (uint16_t)0x3);
                     else if (kCluster == 1) umma_commit(&empty_bar[s]);
-                    else umma_commit_mc(&empty_bar[s], (uint16_t)0x3);
+                    else umma_commit_mc(&empty_bar[s], (uint16_t)((1u << kCluster) - 1u));
                     if (kb == p.k_blocks - 1) {
                         if (k2Sm) umma_commit_2sm_mc(&tmem_full[buf], (uint16_t)0x3);
                         else umma_commit(&tmem_full[buf]);
@@ -699,7 +699,7 @@ int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = 
 int g_k2_cluster = [] {
     const char *e = getenv("CADENCE_K2_CLUSTER");
     const int v = e ? atoi(e) : 2;
-    return (v >= 1 && v <= 3) ? v : 2;
+    return (v >= 1 && v <= 4) ? v : 2;      // 4 = the corpus tile multicast across a 4-CTA cluster (4 query tiles)
 }();
 
 }  // namespace
@@ -774,7 +774,8 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
     if (rc != CDR_OK) return rc;
     // B-tile multicast across a 2-CTA cluster needs an even number of query tiles
     const int m_tiles = nq_pad / kBlockM;
-    const int cluster = (m_tiles % 2 == 0 && g_k2_cluster >= 2) ? 2 : 1;
+    int cluster = (m_tiles % 2 == 0 && g_k2_cluster >= 2) ? 2 : 1;
+    if (g_k2_cluster == 4 && m_tiles % 4 == 0) cluster = 4;
     const bool two_sm = cluster == 2 && g_k2_cluster == 3;
     rc = make_map(&map_x, s->emb_bf16, s->n_rows, dim, kBlockN / cluster);
     if (rc != CDR_OK) return rc;
@@ -786,6 +787,7 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
         CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
         attr_done[s->device & 63] = true;
     }
     attr_lock.unlock();
@@ -825,13 +827,37 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
         const int v = e ? atoi(e) : 4;
         return (int64_t)((v >= 1 && v <= 12) ? v : 4);
     }();
+    // A persistent grid must be co-resident: with 4-CTA clusters a GPC's SM count need not be a multiple of 4, so the
+    // number of clusters that fit can be smaller than sm_count / 4 (a cluster that waits for a free slot would run
+    // its share of the segment alone afterwards).
+    int64_t resident_clusters = s->sm_count / cluster;
+    if (cluster == 4) {
+        static std::mutex occ_mu;
+        static int occ_by_dev[64] = {0};
+        std::lock_guard<std::mutex> occ_lock(occ_mu);
+        if (occ_by_dev[s->device & 63] == 0) {
+            cudaLaunchConfig_t oc = {};
+            oc.gridDim = dim3((unsigned)(s->sm_count / 4 * 4));
+            oc.blockDim = dim3(kGemmThreads);
+            oc.dynamicSmemBytes = kGemmSmem;
+            cudaLaunchAttribute oa[1];
+            oa[0].id = cudaLaunchAttributeClusterDimension;
+            oa[0].val.clusterDim.x = 4; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+            oc.attrs = oa; oc.numAttrs = 1;
+            int n_act = 0;
+            CDR_CUDA(cudaOccupancyMaxActiveClusters(&n_act, gemm_topk_kernel<4, false>, &oc));
+            occ_by_dev[s->device & 63] = n_act > 0 ? n_act : 1;
+            if (getenv("CADENCE_K2_VERBOSE")) fprintf(stderr, "K2: %d co-resident 4-CTA clusters on device %d\n", n_act, s->device);
+        }
+        if (occ_by_dev[s->device & 63] < resident_clusters) resident_clusters = occ_by_dev[s->device & 63];
+    }
     int64_t begin = 0;
     while (begin < p.n_tiles_total) {
         int64_t end = begin == 0 ? 16 : begin + kSegGrowth * begin;
         if (end > p.n_tiles_total) end = p.n_tiles_total;
         p.tile_begin = begin;
         p.tile_end = end;
-        int64_t max_clusters = s->sm_count / cluster;
+        int64_t max_clusters = resident_clusters;
         // tile-major walk only where every cluster gets >= 32 corpus tiles (imbalance <= 1/32)
         p.tile_major = (k2_order == 1 && (end - begin) >= 32 * max_clusters && p.m_tiles / cluster > 1) ? 1 : 0;
         const int64_t items = p.tile_major ? (end - begin) : (end - begin) * (p.m_tiles / cluster);
@@ -847,12 +873,13 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
             cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.x = cluster;
             at[0].val.clusterDim.y = 1;
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
             if (two_sm) CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2, true>, map_q, map_x, p));
+            else if (cluster == 4) CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<4, false>, map_q, map_x, p));
             else CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2, false>, map_q, map_x, p));
         }
         CDR_LAUNCH_CHECK();

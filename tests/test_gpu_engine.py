@@ -935,7 +935,7 @@ def test_growth_reaches_the_tech_and_hybrid_lanes(monkeypatch):
         want_tech = ports.tech_lane(toks, ids, np.array([store_to_us(t) for t in started]), keep,
                                     retrieve.extract_tech_tokens(many), 50)
         assert len(retrieve.extract_tech_tokens(many)) == 41                  # the 40 codes + the bare "ERR"
-        assert [r["chunk_id"] for r in got["debug"]["lanes"]["tech_tokens"]["chunks"]] == want_tech
+        assert [r["chunk_id"] for r in got["debug"]["lanes"]["chunks"]["tech_tokens"]] == want_tech
         assert retrieve.retrieve_ids(eng, many, None)["retrieved_ids"] == got["retrieved_ids"]
     finally:
         embeddings.set_embedder(None)
@@ -1300,9 +1300,16 @@ def test_device_tech_lane_matches_port(hybrid_engine):
                                          date_from_us=to_micros(spec["date_from"]) if "date_from" in spec else None,
                                          date_to_us=to_micros(spec["date_to"]) if "date_to" in spec else None,
                                          tag_mask=spec.get("tag_mask"))
-                want = ports.tech_lane(m["row_tokens"], m["ids"], cols["started_at"], keep, tokens[:32], limit)
+                want = ports.tech_lane(m["row_tokens"], m["ids"], cols["started_at"], keep, tokens, limit)
+                assert cols["ids"][host.query(tokens, cols, limit, **spec)].tolist() == want
+                if not dev.fits(tokens):
+                    # more known tokens than the kernel's per-query table: the device lane refuses (it never drops
+                    # tokens silently) and the facade serves such a request from the host index
+                    with pytest.raises(DenseEngineError) as err:
+                        dev.query_ids(tokens, limit, **spec)
+                    assert err.value.code == _ffi.CDR_ERR_UNSUPPORTED
+                    continue
                 assert dev.query_ids(tokens, limit, **spec) == want, (table, tokens, spec, limit)
-                assert cols["ids"][host.query(tokens[:32], cols, limit, **spec)].tolist() == want
         ids, n = dev.query_batch([["TOK-0"], [], ["TOK-5", "TOK-6"]], 50)
         assert n[1] == 0 and ids[0, :n[0]].tolist() == dev.query_ids(["TOK-0"], 50)
         assert ids[2, :n[2]].tolist() == dev.query_ids(["TOK-5", "TOK-6"], 50) and np.all(ids[1] == -1)
