@@ -64,7 +64,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch-queries", type=int, default=1024, help="batch_bf16: queries per batch (configs[2]: 1024)")
-    ap.add_argument("--hnsw-rows", type=int, default=10_000, help="rows of the CPU HNSW baseline's sample (0 = skip)")
+    ap.add_argument("--hnsw-rows", type=int, default=0, help="rows of the CPU HNSW baseline's sample (default 0: not run -- "
+                                                             "on the iid synthetic corpus a graph index is not a comparable baseline, BASELINE.md 4)")
     ap.add_argument("--batch-rows", type=int, default=0, help="batch_bf16: corpus rows (default 10M on 1 GPU, 100M on N > 1)")
     ap.add_argument("--no-sub-records", action="store_true", help="default line only: skip the configs[2..4] sub-records")
     ap.add_argument("--no-parity", action="store_true", help="A/B timing aids only (e.g. CADENCE_K2_DRYRUN, wrong results by design): "
@@ -660,6 +661,11 @@ def record_exact_f32(args, ctx, keep_store=False):
             if args.hnsw_rows > 0:
                 # the reference's other dense path (mode "ann": HNSW, ef_search = 80), restated, in the same run
                 line["cpu_baseline_hnsw"] = cpu_baseline_hnsw(args.hnsw_rows, 0, target_seconds=5.0)
+            else:
+                line["cpu_baseline_hnsw"] = {
+                    "not_comparable": "HNSW (m=16, ef_construction=64, ef_search=80, restated) on the iid 1024-d synthetic corpus reaches "
+                                      "recall@50 0.31 at 10 000 rows, 0.096 at 50 000 and 0.026 at 200 000 (profiles/r01/hnsw_cpu_sweep.json), "
+                                      "and a 1M-row build takes hours on host cores: see BASELINE.md 4; --hnsw-rows N times it on an N-row sample"}
     barrier()
     searcher.close()
     if keep_store and world == 1:
@@ -732,12 +738,10 @@ def record_batch_bf16(args, ctx):
     # over the bf16-valued rows
     per = (rows + world - 1) // world
     bf16_only = args.bf16_only or per * DIM * 6 > 110e9
-    t_build = time.perf_counter()
     store = DenseStore("chunks", max(count, 1), dim=DIM, device=local_rank, fp32=not bf16_only, bf16=True)
     store.append_synthetic(count, first_row=first)
     store.finalize()
     torch.cuda.synchronize()
-    t_build = time.perf_counter() - t_build
     searcher = ShardedSearcher(store)
     total = args.warmup + args.steps
     q_dev = synth_rows_device(SYNTH_QUERY_SEED, 0, total * nq, DIM, device=local_rank).view(total, nq, DIM)
@@ -861,7 +865,7 @@ def record_batch_bf16(args, ctx):
                            "resident": "bf16 only" if bf16_only else "fp32 + bf16",
                            "l2": "inputs larger than L2", "recall_at_50_vs_exact_fp32_lane": recall_exact_lane,
                            "exchange": searcher.transport, "exact_fp32_lane_single_query": exact_q1,
-                           "ann_bf16_scan_single_query": scan_q1, "store_build_seconds": t_build},
+                           "ann_bf16_scan_single_query": scan_q1},
                 "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak if achieved else None, "traffic": traffic,
