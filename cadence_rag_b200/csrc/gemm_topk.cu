@@ -375,8 +375,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                         (int)(nt * kBlockN) + (int)crank * (kBlockN / 2), leader_bar);
                         continue;
                     }
-                    mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                    tma_load_2d(a, &map_q, kb * kBlockK, mt * kBlockM, &full_bar[s]);
+                    if (p.debug_no_append == 7) {                 // timing aid: no operand traffic at all (MMA issue alone)
+                        mbar_arrive(&full_bar[s]);
+                        continue;
+                    }
+                    if (p.debug_no_append == 6) {                 // timing aid: corpus tiles only, the query tile is not re-read
+                        mbar_arrive_expect_tx(&full_bar[s], kBBytes);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                        tma_load_2d(a, &map_q, kb * kBlockK, mt * kBlockM, &full_bar[s]);
+                    }
                     if (kCluster == 1) {
                         tma_load_2d(a + kABytes, &map_x, kb * kBlockK, (int)(nt * kBlockN), &full_bar[s]);
                     } else {
@@ -461,7 +469,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll 1
             for (int c = 0; c < kBlockN / 32; ++c) {
                 __syncwarp();
-                if (p.debug_no_append == 5) continue;             // timing aid: no epilogue work at all (mainloop alone)
+                if (p.debug_no_append >= 5) continue;             // timing aid: no epilogue work at all (mainloop alone)
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
                 if (p.debug_no_append == 4) {                     // timing aid: TMEM reads only, no maxima

@@ -132,6 +132,22 @@ class DenseEngine:
         return DenseConnection(self)
 
 
+# --------------------------------------------------------------------------- dense-lane failures
+_RECOVERABLE_DENSE_CODES = (_ffi.CDR_ERR_UNSUPPORTED, _ffi.CDR_ERR_OOM, _ffi.CDR_ERR_NO_DEVICE)
+
+
+def _dense_failure_is_recoverable(exc: DenseEngineError) -> bool:
+    """The reference fails open to lexical-only on `EmbeddingClientError` alone (app/retrieve.py:426-432).  The engine's
+    counterpart: a request the dense lane cannot serve (unsupported shape, out of device memory, no device) degrades
+    the same way; a CUDA error, a bad argument or a store in the wrong state is an engine fault -- it is logged and
+    re-raised, never hidden behind a lexical-only answer."""
+    ok = getattr(exc, "code", _ffi.CDR_ERR_INVALID) in _RECOVERABLE_DENSE_CODES
+    if not ok:
+        import logging
+        logging.getLogger("cadence_rag_b200").error("dense lane failed (code %s): %s", getattr(exc, "code", None), exc)
+    return ok
+
+
 # --------------------------------------------------------------------------- small pure helpers
 def _build_debug_lane(rows: Sequence[Mapping[str, Any]], id_field: str) -> List[Dict[str, Any]]:
     return [{id_field: row[id_field], "rank": rank, "score": row.get("score")}
@@ -287,7 +303,7 @@ def _fetch_dense(conn: DenseConnection, table_name: str, query_embedding, filter
     q = _query_vector(query_embedding)
     want = max(1, int(settings.embeddings_dim))
     if q.shape[0] != want or q.shape[0] != store.dim:
-        raise DenseEngineError(f"expected {want} dimensions, not {q.shape[0]}")
+        raise DenseEngineError(f"expected {want} dimensions, not {q.shape[0]}", _ffi.CDR_ERR_UNSUPPORTED)
     allow, count = _filter_bitmap(conn, table_name, filters, call_ids)
     if count <= 0:
         return []
@@ -534,7 +550,7 @@ def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndar
     if q32 is not None:
         want = max(1, int(settings.embeddings_dim))
         if q32.shape[1] != want or q32.shape[1] != store.dim:
-            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[1]}")
+            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[1]}", _ffi.CDR_ERR_UNSUPPORTED)
     order = list(range(nq))                      # request -> position in the C call
     group_specs = group_off = None
     if per_request_filters:
@@ -680,7 +696,7 @@ def retrieve_ids_batch(engine: DenseEngine, queries: Sequence[str], filters=None
                                                    call_ids, bm25[t], limits[t], per_request_filters=per_request,
                                                    ids_only=lean)
         except DenseEngineError as exc:       # fail open to lexical-only, like EmbeddingClientError
-            if not dense_enabled:
+            if not dense_enabled or not _dense_failure_is_recoverable(exc):
                 raise
             dense_enabled = False
             dense_error = str(exc)
@@ -819,9 +835,16 @@ class RequestBatcher:
                     if want_debug and not t["args"][4]:
                         resp = {k: v for k, v in resp.items() if k != "debug"}
                     t["result"] = resp
-            except BaseException as exc:   # noqa: BLE001 - handed to every waiting client
+            except BaseException:   # noqa: BLE001
+                # fault isolation: one client's malformed request (filters, BM25 rows) or one engine fault must not fail
+                # up to max_batch unrelated clients -- the members are retried one at a time and each gets its own
+                # response or its own error
                 for t in batch:
-                    t["error"] = exc
+                    try:
+                        q, f, bc, ba, dbg = t["args"]
+                        t["result"] = retrieve_ids(self.engine, q, f, bm25_chunks=bc, bm25_artifacts=ba, debug=dbg)
+                    except BaseException as exc:   # noqa: BLE001 - handed to the client that sent it
+                        t["error"] = exc
             with self._stats:
                 self.batches_served += 1
                 self.requests_served += len(batch)
@@ -881,7 +904,7 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
                     per_table[t] = _hybrid_table(conn, t, query_embedding if dense_enabled else None, tech_tokens,
                                                  filters, call_ids, bm25[t], limits[t])
             except DenseEngineError as exc:       # fail open to lexical-only, like EmbeddingClientError
-                if not dense_enabled:
+                if not dense_enabled or not _dense_failure_is_recoverable(exc):
                     raise
                 dense_enabled = False
                 dense_error = str(exc)
@@ -920,6 +943,8 @@ def retrieve_ids(engine: DenseEngine, query: str, filters: Optional[RetrieveFilt
                     modes[table] = _choose_dense_mode(candidates[table], filters, call_ids)
                     sink.extend(fetch(conn, query_embedding, filters, call_ids, modes[table], topk))
             except DenseEngineError as exc:   # fail open to lexical-only, like EmbeddingClientError
+                if not _dense_failure_is_recoverable(exc):
+                    raise
                 dense_enabled = False
                 dense_error = str(exc)
                 dense_chunks.clear()

@@ -24,6 +24,7 @@ from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple
 import numpy as np
 
 from . import retrieve as R
+from . import _ffi
 from ._ffi import DenseEngineError
 from .dist import ShardedSearcher
 from .embeddings import EmbeddingClientError, embed_texts, embeddings_enabled
@@ -97,7 +98,7 @@ def _sharded_table(eng: ShardedEngine, conn, table: str, q32: Optional[np.ndarra
     if dense:
         want = max(1, int(R.settings.embeddings_dim))
         if q32.shape[0] != want or q32.shape[0] != store.dim:
-            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[0]}")
+            raise DenseEngineError(f"expected {want} dimensions, not {q32.shape[0]}", _ffi.CDR_ERR_UNSUPPORTED)
     # ---- local halves: tech-lane winners with their sort key, filter bitmap + local COUNT(*)
     local_tech = R._fetch_tech(conn, table, tech_tokens, filters, call_ids, tech_limit)
     cols = store.host_columns()
@@ -171,7 +172,7 @@ def sharded_retrieve_ids(eng: ShardedEngine, query: str, filters: Optional[R.Ret
                         modes[table] = R._choose_dense_mode(count, filters, call_ids)
                 break
             except DenseEngineError as exc:       # deterministic on every rank: fail open to lexical-only
-                if not dense_enabled or attempt == 1:
+                if not dense_enabled or attempt == 1 or not R._dense_failure_is_recoverable(exc):
                     raise
                 dense_enabled, dense_error = False, str(exc)
                 modes = {"chunks": None, "artifact_chunks": None}

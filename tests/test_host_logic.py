@@ -622,8 +622,8 @@ def test_embedding_f32_equals_the_literal_round_trip():
 
 def test_request_batcher_queueing(monkeypatch):
     """RequestBatcher host logic without a GPU: concurrent clients are served in batches by one retrieve_ids_batch
-    call each, every client gets its own response (debug payload only if it asked), an engine failure reaches every
-    client of the batch, and a closed batcher refuses work."""
+    call each, every client gets its own response (debug payload only if it asked), a failing request gets its own
+    error (the batch is retried member by member), and a closed batcher refuses work."""
     import threading
     import time
     from cadence_rag_b200 import retrieve as R
@@ -636,7 +636,11 @@ def test_request_batcher_queueing(monkeypatch):
             raise R.DenseEngineError("engine failed")
         return [{"retrieved_ids": [f"chunk:{q}:{f}"], **({"debug": {"q": q}} if debug else {})} for q, f in zip(queries, filters)]
 
+    def fake_one(engine, query, filters=None, bm25_chunks=(), bm25_artifacts=(), debug=False):
+        return fake_batch(engine, [query], [filters], debug=debug)[0]     # the per-member retry after a failed batch
+
     monkeypatch.setattr(R, "retrieve_ids_batch", fake_batch)
+    monkeypatch.setattr(R, "retrieve_ids", fake_one)
     engine = type("E", (), {"stores": {}})()
     batcher = R.RequestBatcher(engine, max_batch=8, max_wait_s=5e-3)
     results, errors = {}, {}
@@ -657,7 +661,7 @@ def test_request_batcher_queueing(monkeypatch):
         assert resp["retrieved_ids"] == [f"chunk:q{t}-{j}:{t}"]
         assert ("debug" in resp) == (t % 2 == 0)
     assert batcher.requests_served == 60 and batcher.batches_served < 40 and max(len(b[0]) for b in seen) <= 8
-    # a failing batch: every client in it sees the error, the batcher keeps serving afterwards
+    # a failing batch is retried member by member: the request that fails sees its error, the batcher keeps serving
     with pytest.raises(R.DenseEngineError, match="engine failed"):
         batcher.retrieve_ids("boom", None)
     assert batcher.retrieve_ids("after", 7)["retrieved_ids"] == ["chunk:after:7"]
@@ -709,6 +713,7 @@ class _FakeFusedStore:
     def __init__(self):
         self.calls = []
         self.fail_dense = False
+        self.fail_code = _ffi.CDR_ERR_NO_DEVICE
 
     def slot_of_call(self, call_id, create=False):
         return int(call_id)
@@ -729,7 +734,7 @@ class _FakeFusedStore:
         self.calls.append({"filter_spec": filter_spec, "filter_specs": filter_specs, "group_offsets": group_offsets,
                            "nq": 0 if queries is None else len(queries)})
         if self.fail_dense and queries is not None:
-            raise _ffi.DenseEngineError("device lost")
+            raise _ffi.DenseEngineError("device lost", self.fail_code)
         nq = len(bm25_offsets) - 1
         specs = [filter_spec] * nq
         counts = 1234
@@ -816,6 +821,14 @@ def test_fused_request_path_above_the_c_call(monkeypatch):
         off = retrieve.retrieve_ids(eng, texts[1], None, bm25_chunks=bm25, debug=True)
         assert off["retrieved_ids"] == ["chunk:11", "chunk:3012"] and off["debug"]["dense"]["error"] == "device lost"
         assert retrieve.retrieve_ids_batch(eng, texts[:2], None, bm25_chunks=[bm25, []]) == [{"retrieved_ids": ["chunk:11", "chunk:3012"]}, {"retrieved_ids": []}]
+        # ... but only for failures the lane can degrade from: a CUDA error / bad argument / bad state is an engine
+        # fault and surfaces (the reference fails open on EmbeddingClientError alone)
+        for code in (_ffi.CDR_ERR_CUDA, _ffi.CDR_ERR_INVALID, _ffi.CDR_ERR_STATE):
+            store.fail_code = code
+            with pytest.raises(_ffi.DenseEngineError):
+                retrieve.retrieve_ids(eng, texts[1], None, bm25_chunks=bm25, debug=True)
+            with pytest.raises(_ffi.DenseEngineError):
+                retrieve.retrieve_ids_batch(eng, texts[:2], None, bm25_chunks=[bm25, []])
     finally:
         embeddings.set_embedder(None)
 
@@ -861,5 +874,39 @@ def test_request_batcher_over_the_fused_path(monkeypatch):
         for c in store.calls:
             assert c["filter_specs"] is not None and c["group_offsets"][0] == 0 and c["group_offsets"][-1] == c["nq"]
             assert len(c["filter_specs"]) == len(c["group_offsets"]) - 1 <= 3
+    finally:
+        embeddings.set_embedder(None)
+
+
+def test_request_batcher_isolates_a_failing_request(monkeypatch):
+    """One client's malformed request must not fail the other clients of its batch: when the fused batch call raises,
+    the batcher retries the members one at a time and each ticket gets its own response or its own error."""
+    import threading
+    monkeypatch.setattr(settings, "embeddings_dim", 256)
+    monkeypatch.setattr(settings, "embeddings_base_url", "http://embedder")
+    store = _FakeFusedStore()
+    eng = retrieve.DenseEngine()
+    eng.stores["chunks"] = store
+    vec = lambda t: [float((sum(map(ord, t)) * (j + 3)) % 17) / 16.0 for j in range(256)]     # noqa: E731
+    embeddings.set_embedder(lambda batch: embeddings.EmbeddingResult(vectors=[vec(t) for t in batch], model="toy"))
+    bad_rows = [{"not_the_id_field": 1}]                                      # a BM25 row without chunk_id: KeyError
+    try:
+        want = retrieve.retrieve_ids(eng, "good question", None)
+        batcher = retrieve.RequestBatcher(eng, max_batch=8, max_wait_s=0.05)
+        results, errors = {}, {}
+
+        def client(i):
+            try:
+                results[i] = batcher.retrieve_ids("good question", None, bm25_chunks=bad_rows if i == 3 else ())
+            except Exception as exc:   # noqa: BLE001
+                errors[i] = exc
+        threads = [threading.Thread(target=client, args=(i,)) for i in range(6)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(30)
+        batcher.close()
+        assert sorted(errors) == [3] and isinstance(errors[3], KeyError)
+        assert sorted(results) == [0, 1, 2, 4, 5] and all(r == want for r in results.values())
     finally:
         embeddings.set_embedder(None)
