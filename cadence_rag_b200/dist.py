@@ -189,9 +189,12 @@ class ShardedSearcher:
         if int(q.shape[1]) != self.store.dim:
             raise _ffi.DenseEngineError(f"query dim {int(q.shape[1])} != store dim {self.store.dim}")
         nq, dev = int(q.shape[0]), q.device
-        out_sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
-        out_id = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        out_n = torch.empty((nq,), dtype=torch.int32, device=dev)
+        # one allocation for the three outputs (a single-query step is a few tens of microseconds of kernels: every
+        # allocator round trip on the host shows up as GPU idle time in its latency)
+        buf = torch.empty((2 * nq * k + (nq + 1) // 2,), dtype=torch.int64, device=dev)
+        out_sc = buf[:nq * k].view(torch.float64).view(nq, k)
+        out_id = buf[nq * k:2 * nq * k].view(nq, k)
+        out_n = buf[2 * nq * k:].view(torch.int32)[:nq]
         _ffi.check(_ffi.lib().cdr_search_sharded(self.store.handle, self.peer._h, lane, _ffi.ptr(q), nq, k, _ffi.ptr(allow),
                                                  _ffi.ptr(out_sc), _ffi.ptr(out_id), _ffi.ptr(out_n),
                                                  _ffi.stream_ptr(torch.cuda.current_stream(dev))), "cdr_search_sharded")
