@@ -129,6 +129,22 @@ void cdr_prof_mark_end(int kind, cudaStream_t st);
 
 #define CDR_EMPTY_KEY 0ull
 
+// Own bounds / protocol checks (compute-sanitizer is not available on every pool): a build with -DCDR_DEBUG_BOUNDS traps
+// (launch error, reported through the C ABI) where an index leaves its array or a pipeline invariant breaks.  Compiled
+// out of the shipped library.  tools/sanitize_driver.cc runs every kernel family against such a build.
+#ifdef CDR_DEBUG_BOUNDS
+#define CDR_DEV_ASSERT(cond)                                                                    \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            printf("CDR_DEV_ASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                           \
+            __trap();                                                                           \
+        }                                                                                       \
+    } while (0)
+#else
+#define CDR_DEV_ASSERT(cond) do { } while (0)
+#endif
+
 // Monotone map float -> uint32 (larger float => larger code).  NaN => 1 (below every real
 // cosine, above the empty key's 0), so NaN rows sort last but stay eligible (SQL semantics).
 __device__ __forceinline__ uint32_t cdr_order_f32(float f)
@@ -343,6 +359,7 @@ struct WarpTopK {
     __device__ __forceinline__ void push(uint64_t key, int lane)
     {
         constexpr int KC = NPL * 32;
+        CDR_DEV_ASSERT(count >= 0 && count <= KC && min_pos >= 0 && min_pos < KC && key != CDR_EMPTY_KEY);
         if (count < KC) {
             if (lane == 0) list[count] = key;
             ++count;

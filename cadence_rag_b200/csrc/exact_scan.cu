@@ -346,6 +346,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                     ++it;
                     break;
                 }
+                CDR_DEV_ASSERT(s >= 0 && s < S && S <= kMaxStages && tile < n_tiles);
                 const int64_t row0 = tile * TR + rg * RPW;    // a multiple of RPW: the rows share one bitmap word
                 uint32_t allow_bits = 0xFFFFFFFFu;
                 uint32_t g_row[RPW];
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                         uint64_t *tl = my_lists + (size_t)u1 * KC;
                         if (k1 > ts->tau) {                       // re-tested: an earlier insert may have raised tau
                             const int cnt = __shfl_sync(0xffffffffu, ts->count, 0);   // lane 0 is the only writer
+                            CDR_DEV_ASSERT(cnt >= 0 && cnt <= KC && ts->min_pos >= 0 && ts->min_pos < KC);
                             if (lane == 0) {
                                 tl[cnt < KC ? cnt : ts->min_pos] = k1;
                                 if (cnt < KC) ts->count = cnt + 1;
@@ -483,6 +485,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 }
                 const int uq = qh * QW + u;
                 if (rg == 0 && uq < nqv) {
+                    CDR_DEV_ASSERT(q0 + uq < nq_eff && p.list_offset + (int)blockIdx.x < p.lists_per_query);
                     uint64_t *out = p.cta_keys + ((size_t)(q0 + uq) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
 #pragma unroll
                     for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
@@ -534,6 +537,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                     ++it;
                     break;
                 }
+                CDR_DEV_ASSERT(s >= 0 && s < S && S <= kMaxStages && tile < n_tiles);
                 const int64_t row0 = tile * TR + warp * RPW;      // a multiple of RPW (<= 4): one bitmap word
                 uint32_t allow_bits = 0xFFFFFFFFu;
                 uint32_t g_row[RPW];
@@ -657,6 +661,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 ++it;
                 break;
             }
+            CDR_DEV_ASSERT(s >= 0 && s < S && S <= kMaxStages && tile < n_tiles);
             const int64_t row0 = tile * TR + warp * RPW;   // gather: first LIST ENTRY of this warp
             // filter bits for this warp's rows (consumed after the dot products, so the load overlaps them)
             uint32_t allow_bits = 0xFFFFFFFFu;
@@ -797,6 +802,7 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 }
             }
             if (warp == 0 && u < nqv) {
+                CDR_DEV_ASSERT(q0 + u < nq_eff && p.list_offset + (int)blockIdx.x < p.lists_per_query);
                 uint64_t *out = p.cta_keys + ((size_t)(q0 + u) * p.lists_per_query + p.list_offset + blockIdx.x) * KC;
 #pragma unroll
                 for (int i = 0; i < NPL; ++i) out[i * 32 + lane] = k[i];
@@ -912,6 +918,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const Finaliz
     }
     for (int slot = blockIdx.x; slot < n_live; slot += gridDim.x) {
     const int qi = p.q_index != nullptr ? __ldg(&p.q_index[slot]) : slot;     // query: inputs and outputs
+    CDR_DEV_ASSERT(qi >= 0 && slot < p.n_slots);
     const uint64_t *base = p.lists + (size_t)slot * p.n_lists * KC;
     __syncthreads();                                                          // the previous slot's shared state is dead
     if (threadIdx.x == 0) s_nvalid = 0;

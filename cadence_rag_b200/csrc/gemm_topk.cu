@@ -260,6 +260,7 @@ __device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int
                                           const uint16_t *buf_q, int et, int nbuf)
 {
     uint32_t base[kBufN];
+    CDR_DEV_ASSERT(nbuf >= 0 && nbuf <= kBufN && et >= 0 && et < 128);
 #pragma unroll
     for (int i = 0; i < kBufN; ++i)
         if (i < nbuf) base[i] = atomicAdd(&counts[buf_q[i * 128 + et]], 1u);
@@ -463,6 +464,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (lim > kBlockN) lim = kBlockN;
             const uint32_t buf = tile_no & 1u;
             const uint32_t use = tile_no >> 1;
+            CDR_DEV_ASSERT(nt >= 0 && nt < p.n_tiles_total && mt >= 0 && mt < p.m_tiles && row0 < p.n_rows);
             mbar_wait(&tmem_full[buf], use & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * kBlockN;
@@ -510,6 +512,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                 if (!(v[j] < tau) && ((allow_w >> j) & 1u)) {
                                     const uint64_t key = cdr_pack_key(v[j], (uint32_t)(row0 + c * 32 + j));
                                     if (key > tau_key) {
+                                        CDR_DEV_ASSERT(nbuf >= 0 && nbuf < kBufN && q < p.nq && row0 + c * 32 + j < p.n_rows);
                                         buf_key[nbuf * 128 + et] = key;
                                         buf_q[nbuf * 128 + et] = (uint16_t)q;
                                         ++nbuf;

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) peer_publish_merge_kernel(const PeerParam
     const int q = blockIdx.x;
     const uint32_t par = p.epoch & 1u;
     const size_t slot_me = (((size_t)par * p.world + p.rank) * p.max_nq + q) * p.entry_bytes;
+    CDR_DEV_ASSERT(q < p.max_nq && p.k <= p.max_k && slot_me + p.entry_bytes <= p.flags_off && p.n[q] >= 0 && p.n[q] <= p.k);
 
     // ---- push: my list for query q into every rank's buffer
     const int my_n = p.n[q];
