@@ -901,7 +901,7 @@ __device__ __forceinline__ float4 load_row_vec(const float *rows, const __nv_bfl
 }
 
 template <int NPL, int WARPS, int kRB>
-__global__ void __launch_bounds__(WARPS * 32) scan_finalize_kernel(const FinalizeParams p)
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 4 : 1) scan_finalize_kernel(const FinalizeParams p)
 {
     constexpr int KC = NPL * 32;
     __shared__ uint64_t s_lists[WARPS * KC];
@@ -1279,6 +1279,16 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
         if (kc == 64) scan_finalize_cluster_kernel<2><<<nq * kFinCluster, 256, 0, st>>>(fp);
         else if (kc == 128) scan_finalize_cluster_kernel<4><<<nq * kFinCluster, 256, 0, st>>>(fp);
         else scan_finalize_cluster_kernel<8><<<nq * kFinCluster, 256, 0, st>>>(fp);
+        CDR_LAUNCH_CHECK();
+        return CDR_OK;
+    }
+    // Large batches of unsorted lists (the tensor-core lane: 1024 queries per batch): a 1024-thread CTA owns a whole SM
+    // (64 registers x 1024 threads) and spends most of its 25 us waiting on its own merge tree and row reads, so 1024 of
+    // them are 7 waves; 256-thread CTAs run 4 per SM and overlap each other's latencies.  CADENCE_FIN_WARPS=32 keeps the
+    // wide form (A/B aid).  Same arithmetic and order => same bits.
+    static const int fin_warps = [] { const char *e = getenv("CADENCE_FIN_WARPS"); return e ? atoi(e) : 8; }();
+    if (kc == 128 && fp.counts != nullptr && nq >= 256 && fin_warps == 8) {
+        scan_finalize_kernel<4, 8, 2><<<nq, 256, 0, st>>>(fp);
         CDR_LAUNCH_CHECK();
         return CDR_OK;
     }

@@ -96,8 +96,12 @@ class PeerExchange:
         handles = [None] * self.world
         dist.all_gather_object(handles, handle.raw, group=group)
         status = _ffi.lib().cdr_peer_group_connect(self._h, b"".join(handles))
-        # every rank must take the same transport: agree on the outcome
-        ok = torch.tensor([1 if status == _ffi.CDR_OK else 0], dtype=torch.int32, device=f"cuda:{device}")
+        # every rank must take the same transport: agree on the outcome (a CPU tensor under gloo: two ranks may share
+        # ONE device there -- CUDA IPC maps a buffer of the same device as well -- which is how the 1-GPU test tier
+        # exercises the multi-rank exchange)
+        on_cpu = dist.get_backend(group) != "nccl"
+        ok = torch.tensor([1 if status == _ffi.CDR_OK else 0], dtype=torch.int32,
+                          device="cpu" if on_cpu else f"cuda:{device}")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
             msg = _ffi.last_error() if status != _ffi.CDR_OK else "a peer rank could not map the buffers"
@@ -143,15 +147,17 @@ class ShardedSearcher:
             raise ValueError(f"transport {transport!r}: expected auto, peer or nccl")
         self.peer: Optional[PeerExchange] = None
         self.transport = "none" if self.world == 1 else "nccl"
-        if self.world > 1 and transport in ("auto", "peer") and dist.get_backend(group) == "nccl":
+        if transport == "peer" and self.world > 1 and dist.get_backend(group) != "nccl":
+            import torch
+            if not torch.cuda.is_available():
+                raise _ffi.DenseEngineError("peer transport needs CUDA ranks", _ffi.CDR_ERR_UNSUPPORTED)
+        if self.world > 1 and transport in ("auto", "peer") and (dist.get_backend(group) == "nccl" or transport == "peer"):
             try:
                 self.peer = PeerExchange(store.device, group, max_nq=max_nq, max_k=max_k)
                 self.transport = "peer"
             except _ffi.DenseEngineError:
                 if transport == "peer":
                     raise
-        elif transport == "peer" and self.world > 1:
-            raise _ffi.DenseEngineError("peer transport needs CUDA ranks (nccl backend)", _ffi.CDR_ERR_UNSUPPORTED)
 
     def close(self) -> None:
         if self.peer is not None:

@@ -94,6 +94,78 @@ def test_two_rank_nccl_sharded_equals_whole(tmp_path):
     assert np.array_equal(r0["a_ids"], r1["a_ids"])       # every rank holds the identical merged result
 
 
+def _one_gpu_worker(rank, world, port, n_total, k, out_dir):
+    """Two ranks on ONE device (gloo process group; the peer buffers are mapped with CUDA IPC within the device): the
+    K4p exchange kernel of each rank really waits for the other process's push.  Kernels of the two processes are
+    time-sliced by the driver, so a spinning exchange kernel is preempted for its peer -- slow, but the protocol and the
+    merge are the ones the multi-GPU runs use."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cadence_rag_b200.dist import ShardedSearcher, shard_range
+    from cadence_rag_b200.store import DenseStore, SYNTH_QUERY_SEED, synth_rows_device
+    first, cnt = shard_range(n_total, rank, world)
+    store = DenseStore("chunks", cnt, dim=1024, device=0)
+    store.append_synthetic(cnt, first_row=first)
+    store.finalize()
+    peer = ShardedSearcher(store, transport="peer", max_nq=64, max_k=64)
+    assert peer.transport == "peer" and peer.world == world
+    qs = synth_rows_device(SYNTH_QUERY_SEED, 0, 70, 1024, device=0)
+    out = {}
+    for name, nq_i, kk, mode in (("exact", 70, k, "exact"), ("one", 1, k, "exact"), ("k10", 64, 10, "exact"),
+                                 ("shared", 40, k, "exact_shared"), ("ann", 70, k, "ann"), ("scan", 3, k, "scan_bf16")):
+        ids, sc, n = peer.search(qs[:nq_i], kk, mode="exact" if mode == "exact_shared" else mode, shared=mode == "exact_shared")
+        torch.cuda.synchronize()
+        out[name] = (ids.cpu().numpy(), sc.cpu().numpy(), n.cpu().numpy())
+    allow, _cnt = store.filter_bitmap(call_slots=[0, 1])                  # rows 0..399: rank 0's shard only
+    ids, sc, n = peer.search(qs[:5], k, allow=allow, mode="exact")
+    torch.cuda.synchronize()
+    out["filtered"] = (ids.cpu().numpy(), sc.cpu().numpy(), n.cpu().numpy())
+    dist.barrier()
+    peer.close()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{f"{k_}_{part}": v[i] for k_, v in out.items()
+                                                         for i, part in enumerate(("ids", "sc", "n"))})
+    store.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path):
+    """The multi-rank exchange on a ONE-GPU box: 2 processes share cuda:0, each owns half of the rows, and every
+    merged result must carry the bits of the unsharded scan (exact lanes) or reach recall 0.999 against it (bf16 lanes)
+    and be identical on both ranks."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    n_total, k, world = 60_001, 50, 2
+    mp.spawn(_one_gpu_worker, args=(world, _free_port(), n_total, k, str(tmp_path)), nprocs=world, join=True)
+    from cadence_rag_b200.store import DenseStore, SYNTH_QUERY_SEED, synth_rows_device
+    whole = DenseStore("chunks", n_total, dim=1024, device=0)
+    whole.append_synthetic(n_total)
+    whole.finalize()
+    qs = synth_rows_device(SYNTH_QUERY_SEED, 0, 70, 1024, device=0)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for key in r0.files:
+        assert np.array_equal(r0[key], r1[key]), key                       # every rank holds the identical result
+    for name, nq_i, kk in (("exact", 70, k), ("one", 1, k), ("k10", 64, 10), ("shared", 40, k)):
+        w_ids, w_sc, w_n = whole.search_exact(qs[:nq_i], kk)
+        torch.cuda.synchronize()
+        assert np.array_equal(r0[f"{name}_ids"], w_ids.cpu().numpy()), name
+        assert np.array_equal(r0[f"{name}_sc"].view(np.uint64), w_sc.cpu().numpy().view(np.uint64)), name
+        assert np.array_equal(r0[f"{name}_n"], w_n.cpu().numpy())
+    w_ids = whole.search_exact(qs, k)[0].cpu().numpy()
+    for name, nq_i in (("ann", 70), ("scan", 3)):
+        got = r0[f"{name}_ids"]
+        assert np.mean([len(set(got[i]) & set(w_ids[i])) / k for i in range(nq_i)]) >= 0.999, name
+    allow, cnt_allowed = whole.filter_bitmap(call_slots=[0, 1])
+    f_ids, f_sc, f_n = whole.search_exact(qs[:5], k, allow)
+    torch.cuda.synchronize()
+    assert cnt_allowed == 400 and np.array_equal(r0["filtered_ids"], f_ids.cpu().numpy())
+    assert np.array_equal(r0["filtered_sc"].view(np.uint64), f_sc.cpu().numpy().view(np.uint64))
+    whole.close()
+
+
 # ----------------------------------------------------------------------------------------- sharded hybrid /retrieve
 def _hybrid_corpus():
     """Deterministic 2-table corpus (same on every rank): rows, ids, calls, dates, tags, tech tokens, payload."""
