@@ -93,6 +93,11 @@ int cdr_ws_reserve(void **ptr, size_t *have, size_t need);
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
+        // Every entry point builds one of these before it launches anything.  A non-sticky error left behind by an
+        // earlier failed runtime call of ANOTHER library in the process (a peer-access probe on a one-GPU box answers
+        // "invalid device ordinal") would otherwise be picked up by this call's first cudaGetLastError() and blamed on a
+        // kernel launch that was fine; sticky errors (real faults) survive this and still fail the call.
+        (void)cudaGetLastError();
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
         else prev = -1;

@@ -11,7 +11,7 @@ for cl in 1 2 3 4; do
   CADENCE_K2_CLUSTER=$cl LD_LIBRARY_PATH=$PWD/build/ab/bounds timeout 600 ./build/sanitize_driver > $out/bounds_driver_k2c$cl.log 2>&1
   echo "rc=$? $(tail -1 $out/bounds_driver_k2c$cl.log)"
 done
-ldd ./build/sanitize_driver | grep cadence
+LD_LIBRARY_PATH=$PWD/build/ab/bounds ldd ./build/sanitize_driver | grep cadence
 echo "== gpu test tier, bounds build"
 CADENCE_DENSE_LIB=$PWD/build/ab/bounds/libcadence_dense.so timeout 1200 python -m pytest tests -m gpu -x -q > $out/bounds_pytest_gpu.log 2>&1
 echo "rc=$? $(tail -1 $out/bounds_pytest_gpu.log)"
