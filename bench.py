@@ -637,8 +637,11 @@ def record_exact_f32(args, ctx, keep_store=False):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
         launches_k1 = int(k_n.value)
-        bytes_per_launch = float(count) * DIM * 4 * Q          # one launch scans the shard for Q queries
-        achieved = bytes_per_launch / (k_ms_max / max(launches_k1, 1) / 1e3) / 1e9 if k_ms_max > 0 else None
+        # a step scans the shard once per query; its K1 time is one launch (N = 1) or one launch per 16-query chunk
+        # (the pipelined sharded step): algorithmic bytes of all timed steps / total K1 time of those steps
+        per_step = max(1, launches_k1 // max(args.steps, 1))
+        bytes_per_launch = float(count) * DIM * 4 * Q / per_step
+        achieved = float(count) * DIM * 4 * Q * args.steps / (k_ms_max / 1e3) / 1e9 if k_ms_max > 0 else None
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tpath) and world == 1:
@@ -659,7 +662,8 @@ def record_exact_f32(args, ctx, keep_store=False):
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "exact_scan_kernel<8,2,2>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "avg_launch_ms": k_ms_max / max(launches_k1, 1), "launches_timed": launches_k1},
+                         "avg_launch_ms": k_ms_max / max(launches_k1, 1), "launches_timed": launches_k1,
+                         "launches_per_step": per_step, "k1_ms_per_step": k_ms_max / max(args.steps, 1)},
             "parity": parity,
         }
         line["exact_batch_shared_reads"] = shared

@@ -86,6 +86,7 @@ struct cdr_store {
 
     std::mutex mu;
     std::map<cudaStream_t, ScanWorkspace> ws;
+    std::map<cudaStream_t, ScanWorkspace> ws_pipe[2];   // the two alternating workspaces of a pipelined sharded step
 };
 
 int cdr_ws_reserve(void **ptr, size_t *have, size_t need);
@@ -122,8 +123,16 @@ int cdr_exact_scan_redo_launch(cdr_store *s, ScanWorkspace &ws, const float *q_d
 // K2 (gemm_topk.cu) with the store mutex held by the caller: nq <= 16384, k <= 192, bf16 rows resident.
 int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, int k, const uint32_t *allow_dev,
                           double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev, cudaStream_t st);
+// fin: when set, the finalize kernel of the launch goes to another stream -- `scan_done` is recorded on `st` after the scan
+// kernels and `fin->stream` waits for it -- so the caller can overlap it (and what it enqueues behind it) with the NEXT
+// scan on `st` (peer.cu: the sharded step pipelines chunks of a batch this way).
+struct ScanFinalizeOn {
+    cudaStream_t stream;
+    cudaEvent_t scan_done;
+};
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
-                          double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st, bool share_reads);
+                          double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st, bool share_reads,
+                          const ScanFinalizeOn *fin = nullptr);
 
 // profiling hooks (abi.cu)
 void cdr_prof_mark_begin(int kind, cudaStream_t st);

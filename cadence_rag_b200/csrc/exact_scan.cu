@@ -1307,7 +1307,8 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
 template <int J, int RPW, int NPL, int QPC, bool BF = false>
 int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                   const uint32_t *allow, int k, double *out_score, int64_t *out_id, int32_t *out_n,
-                  cudaStream_t st, const int *q_index = nullptr, const int *q_count = nullptr)
+                  cudaStream_t st, const int *q_index = nullptr, const int *q_count = nullptr,
+                  const ScanFinalizeOn *fin = nullptr)
 {
     using L = ScanSmem<J, RPW, NPL, QPC, BF>;
     constexpr int KC = L::KC;
@@ -1446,7 +1447,13 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     fp.q_index = sp.q_index;
     fp.q_count = sp.q_count;
     fp.n_slots = nq;
-    return launch_finalize(fp, KC, sp.q_index != nullptr && nq > 64 ? 64 : nq, st);
+    cudaStream_t fst = st;
+    if (fin != nullptr && fin->stream != st) {          // the finalize (and what follows it) runs beside the next scan
+        CDR_CUDA(cudaEventRecord(fin->scan_done, st));
+        CDR_CUDA(cudaStreamWaitEvent(fin->stream, fin->scan_done, 0));
+        fst = fin->stream;
+    }
+    return launch_finalize(fp, KC, sp.q_index != nullptr && nq > 64 ? 64 : nq, fst);
 }
 
 enum ScanMode { kScanSingle = 0, kScanShared = 1, kScanDeep = 2 };
@@ -1455,7 +1462,7 @@ template <int NPL>
 int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                     const uint32_t *allow, int k, double *out_score, int64_t *out_id,
                     int32_t *out_n, cudaStream_t st, ScanMode mode, const int *q_index = nullptr,
-                    const int *q_count = nullptr)
+                    const int *q_count = nullptr, const ScanFinalizeOn *fin = nullptr)
 {
 #define CDR_SCAN_CASE(J_, RPW_)                                                                              \
     if constexpr (NPL == 2) {                                                                                \
@@ -1464,15 +1471,15 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     }                                                                                                        \
     if (mode != kScanSingle)                                                                                 \
         return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
-    return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count)
+    return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin)
     switch (s->dim) {
     case 256:  CDR_SCAN_CASE(2, 2);
     case 512:  CDR_SCAN_CASE(4, 2);
     case 768:  CDR_SCAN_CASE(6, 2);
     case 1024: CDR_SCAN_CASE(8, 2);
     // kSharedQPC queries x J float4 would not fit the register budget: one scan per query
-    case 1536: return launch_scan_t<12, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count);
-    case 2048: return launch_scan_t<16, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count);
+    case 1536: return launch_scan_t<12, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin);
+    case 2048: return launch_scan_t<16, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin);
     default:
         cdr_set_error("exact scan: dim %d not built (supported: 256,512,768,1024,1536,2048)", s->dim);
         return CDR_ERR_UNSUPPORTED;
@@ -1491,9 +1498,12 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
 // CADENCE_K1_DEEP=0 keeps the 3-queries-in-registers kernel for every batch size (A/B aid).
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                           const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                          int32_t *out_n, cudaStream_t st, bool share_reads)
+                          int32_t *out_n, cudaStream_t st, bool share_reads, const ScanFinalizeOn *fin)
 {
     const bool share = share_reads && nq >= 2;
+    if (fin != nullptr && !share)       // (one scan per query only: the pipelined sharded step)
+        return k > 56 ? launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, kScanSingle, nullptr, nullptr, fin)
+                      : launch_scan_dim<2>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, kScanSingle, nullptr, nullptr, fin);
     if (k > 56) return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share ? kScanShared : kScanSingle);
     static const bool k1_deep = [] { const char *e = getenv("CADENCE_K1_DEEP"); return !(e && e[0] == '0'); }();
     int n_deep = 0;

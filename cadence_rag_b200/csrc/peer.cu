@@ -21,6 +21,7 @@
 
 #include <mutex>
 
+#include <cstdlib>
 #include <cstring>
 
 struct cdr_peer_group {
@@ -37,6 +38,11 @@ struct cdr_peer_group {
     double *loc_score = nullptr;
     int64_t *loc_id = nullptr;
     int32_t *loc_n = nullptr;
+    // pipelined step (cdr_search_sharded, one scan per query, batches of more than kPipeChunk queries): the finalize and
+    // exchange kernels of chunk c run on `side` while the scan of chunk c+1 runs on the caller's stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t scan_done[2] = {nullptr, nullptr};
+    cudaEvent_t fin_done[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -178,6 +184,15 @@ extern "C" int32_t cdr_peer_group_create(cdr_peer_group **out, int32_t device, i
     if (e == cudaSuccess) e = cudaMalloc(&pg->loc_score, (size_t)max_nq * max_k * 8);
     if (e == cudaSuccess) e = cudaMalloc(&pg->loc_id, (size_t)max_nq * max_k * 8);
     if (e == cudaSuccess) e = cudaMalloc(&pg->loc_n, (size_t)max_nq * 4);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;                                   // the side stream's small kernels go first when SMs free up
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&pg->side, cudaStreamNonBlocking, hi);
+    }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&pg->scan_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pg->fin_done[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, pg->local);
@@ -226,7 +241,48 @@ extern "C" int32_t cdr_peer_group_destroy(cdr_peer_group *pg)
     for (int r = 0; r < pg->world; ++r)
         if (r != pg->rank && pg->peer[r]) cudaIpcCloseMemHandle(pg->peer[r]);
     cudaFree(pg->local); cudaFree(pg->loc_score); cudaFree(pg->loc_id); cudaFree(pg->loc_n);
+    for (int i = 0; i < 2; ++i) {
+        if (pg->scan_done[i]) cudaEventDestroy(pg->scan_done[i]);
+        if (pg->fin_done[i]) cudaEventDestroy(pg->fin_done[i]);
+    }
+    if (pg->side) cudaStreamDestroy(pg->side);
     delete pg;
+    return CDR_OK;
+}
+
+// The pipelined form of a sharded step (one scan per query, more than kPipeChunk queries): the batch goes through in chunks
+// of kPipeChunk queries -- the size the 8-CTA-cluster finalize serves; its 256-thread CTAs (80 registers, 10 KB) and the
+// exchange kernel's fit on an SM BESIDE a scan CTA (288 threads, 126 registers, 197 KB) -- with the finalize + exchange of chunk
+// c on the group's side stream while the scan of chunk c+1 runs on the caller's stream.  Only the last chunk's tail (and the
+// wait for the slowest rank inside its exchange) is left on the critical path; the call still completes in stream order on
+// the caller's stream.  Two scan workspaces alternate; a workspace is re-used only after its chunk's finalize has finished.
+constexpr int kPipeChunk = 16;
+
+static int sharded_exact_pipelined(cdr_store *s, cdr_peer_group *pg, const float *q_dev, int nq, int k,
+                                   const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev,
+                                   int32_t *out_n_dev, cudaStream_t st)
+{
+    DeviceGuard g(s->device);
+    std::lock_guard<std::mutex> lk(s->mu);
+    const uint32_t *allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
+    int last = -1;
+    for (int q0 = 0, c = 0; q0 < nq; q0 += kPipeChunk, ++c) {
+        const int m = nq - q0 < kPipeChunk ? nq - q0 : kPipeChunk;
+        const int par = c & 1;
+        const int l0 = q0 % pg->max_nq;                          // slice of the group's local-list buffers
+        if (c >= 2) CDR_CUDA(cudaStreamWaitEvent(st, pg->fin_done[par], 0));     // this workspace's previous chunk is done
+        ScanFinalizeOn fin{pg->side, pg->scan_done[par]};
+        int rc = cdr_exact_scan_launch(s, s->ws_pipe[par][st], q_dev + (size_t)q0 * s->dim, m, allow, k,
+                                       pg->loc_score + (size_t)l0 * k, pg->loc_id + (size_t)l0 * k, pg->loc_n + l0, st,
+                                       /*share_reads=*/false, &fin);
+        if (rc != CDR_OK) return rc;
+        rc = cdr_peer_exchange_merge(pg, pg->loc_score + (size_t)l0 * k, pg->loc_id + (size_t)l0 * k, pg->loc_n + l0, m, k,
+                                     out_score_dev + (size_t)q0 * k, out_id_dev + (size_t)q0 * k, out_n_dev + q0, pg->side);
+        if (rc != CDR_OK) return rc;
+        CDR_CUDA(cudaEventRecord(pg->fin_done[par], pg->side));
+        last = par;
+    }
+    if (last >= 0) CDR_CUDA(cudaStreamWaitEvent(st, pg->fin_done[last], 0));     // the side stream is in order: the last event covers all
     return CDR_OK;
 }
 
@@ -289,6 +345,14 @@ extern "C" int32_t cdr_search_sharded(cdr_store *s, cdr_peer_group *pg, int32_t 
                 pg->device);
     CDR_REQUIRE(k >= 1 && k <= pg->max_k, CDR_ERR_INVALID, "cdr_search_sharded: k=%d outside [1,%d]", k, pg->max_k);
     CDR_REQUIRE(nq >= 0 && out_score_dev && out_id_dev && out_n_dev, CDR_ERR_INVALID, "cdr_search_sharded: bad arguments");
+    // Off by default: measured at 8 GPUs it LOSES (13 420 vs 14 160 queries/s, profiles/r02/README.md) -- four exchanges per
+    // step are four points where every rank waits for the slowest one, and the scan of chunk c+2 waits for them through
+    // its workspace; at 2 GPUs it is a wash.  CADENCE_SHARD_PIPELINE=1 turns it on (A/B aid, covered by the tests).
+    static const bool pipelined = [] { const char *e = getenv("CADENCE_SHARD_PIPELINE"); return e && e[0] == '1'; }();
+    if (pipelined && lane == CDR_DENSE_LANE_EXACT_F32 && nq > kPipeChunk && k <= 56 && pg->max_nq >= kPipeChunk &&
+        pg->max_nq % kPipeChunk == 0 && s->finalized && s->emb_f32 != nullptr && q_dev != nullptr)
+        return sharded_exact_pipelined(s, pg, q_dev, nq, k, allow_dev, out_score_dev, out_id_dev, out_n_dev,
+                                       (cudaStream_t)stream);
     for (int q0 = 0; q0 < nq; q0 += pg->max_nq) {
         const int m = nq - q0 < pg->max_nq ? nq - q0 : pg->max_nq;
         int rc = fn(s, q_dev + (size_t)q0 * s->dim, m, k, allow_dev, pg->loc_score, pg->loc_id, pg->loc_n, stream);

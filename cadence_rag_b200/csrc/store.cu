@@ -346,6 +346,8 @@ extern "C" int32_t cdr_store_destroy(cdr_store *s)
     cudaFree(s->valid);
     cudaFree(s->d_scratch);
     for (auto &kv : s->ws) free_ws(kv.second);
+    for (auto &m : s->ws_pipe)
+        for (auto &kv : m) free_ws(kv.second);
     delete s;
     return CDR_OK;
 }
