@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-rows", type=int, default=0,
+                    help="--impl reference: rows the CPU arm scans (default 0 = the WHOLE corpus of the config, no scaling; "
+                         "a smaller value scans a sample and scales the rate by rows, and the line says so)")
     ap.add_argument("--batch-queries", type=int, default=1024, help="batch_bf16: queries per batch (configs[2]: 1024)")
     ap.add_argument("--hnsw-rows", type=int, default=0, help="rows of the CPU HNSW baseline's sample (default 0: not run -- "
                                                              "on the iid synthetic corpus a graph index is not a comparable baseline, BASELINE.md 4)")
@@ -164,9 +167,12 @@ class ClockSampler:
 
 def workload_config(args, world):
     label = "BASELINE configs[1]" if args.rows == N_ROWS else "north_star headline (configs[1] kernel)"
+    # the SAME dict in both arms (the driver compares them): everything that describes this run rather than the workload
+    # -- sharding, transport, latencies -- lives under the line's "run" key
     return {"workload": f"{label}: {args.rows} x {DIM} fp32 corpus, single-query exact cosine scan + "
                         f"top-k={TOPK}; step = {args.queries_per_step} distinct queries, one scan of the corpus per query",
-            "rows": args.rows, "dim": DIM, "k": TOPK, "queries_per_step": args.queries_per_step}
+            "rows": args.rows, "dim": DIM, "k": TOPK, "queries_per_step": args.queries_per_step,
+            "l2": "inputs larger than L2 (corpus bytes >> 126 MB), distinct queries every step"}
 
 
 # ----------------------------------------------------------------------------- CPU baseline
@@ -248,7 +254,7 @@ def run_reference(args):
         return 0
     from oracle import cpu_oracle as orc
     import numpy as np
-    rows = min(args.cpu_sample_rows, args.rows)
+    rows = args.rows if args.reference_rows <= 0 else min(args.reference_rows, args.rows)
     cores = os.cpu_count() or 1            # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     q_per_step = max(1, args.queries_per_step)      # same step as the B200 arm: Q distinct single-query scans
     x = orc.synth_rows(20260209, 0, rows)
@@ -264,8 +270,10 @@ def run_reference(args):
             orc.exact_scan(qs[qi % 4096], x, TOPK, variant=orc.VARIANT_PGV32, nthreads=cores); qi += 1
     dt = time.perf_counter() - t0
     value = args.steps * q_per_step / dt * rows / args.rows
-    sample = (f"{q_per_step} queries/step x {rows} of {args.rows} rows, rate scaled by rows; pgvector 0.8.1 "
-              f"exact-scan loop restated in C (oracle/pgvector_restated.c), {cores} OpenMP threads")
+    scaled = "" if rows == args.rows else ", rate scaled by rows"
+    sample = (f"{q_per_step} queries/step x {rows} of {args.rows} rows{scaled}; pgvector 0.8.1 "
+              f"exact-scan loop restated in C (oracle/pgvector_restated.c), {cores} OpenMP threads; no Postgres (no TOAST / "
+              f"tuple / executor overhead): optimistic for the reference")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -653,10 +661,9 @@ def record_exact_f32(args, ctx, keep_store=False):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, world), sharding=f"rows/{world}" if world > 1 else "none",
-                           exchange=searcher.transport,
-                           l2="inputs larger than L2 (shard bytes >> 126 MB), distinct queries every step",
-                           single_query_latency_ms_p50=lat[len(lat) // 2], single_query_latency_ms_min=lat[0]),
+            "config": workload_config(args, world),
+            "run": {"sharding": f"rows/{world}" if world > 1 else "none", "exchange": searcher.transport,
+                    "single_query_latency_ms_p50": lat[len(lat) // 2], "single_query_latency_ms_min": lat[0]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,

@@ -13,7 +13,7 @@ import json,glob
 for f in sorted(glob.glob('gpurun_out/r02_pipe*_${N}gpu_r*.json')):
     try:
         d=json.load(open(f)); r=d['roofline']
-        print(f.split('/')[-1], 'q/s', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'k1 ms/step', round(r.get('k1_ms_per_step', r['avg_launch_ms']),4), 'frac', round(r['frac'],4), 'lat', round(d['config']['single_query_latency_ms_p50'],4), 'parity', [v.get('identical_positions', v.get('identical')) for v in d['parity'].values()])
+        print(f.split('/')[-1], 'q/s', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'k1 ms/step', round(r.get('k1_ms_per_step', r['avg_launch_ms']),4), 'frac', round(r['frac'],4), 'lat', round(d.get('run', d['config'])['single_query_latency_ms_p50'],4), 'parity', [v.get('identical_positions', v.get('identical')) for v in d['parity'].values()])
     except Exception as e:
         print(f, 'ERR', e)
 PY

@@ -9,7 +9,7 @@ python - <<'PY'
 import json
 try:
     d=json.load(open('gpurun_out/r02_bench_2gpu_v1.json'))
-    print('K1 N=2', d['value'], d['ms_per_step'], d['config']['single_query_latency_ms_p50'], d['roofline']['frac'], json.dumps(d['parity'])[:1500])
+    print('K1 N=2', d['value'], d['ms_per_step'], d.get('run', d['config'])['single_query_latency_ms_p50'], d['roofline']['frac'], json.dumps(d['parity'])[:1500])
     b=d['sub_records']['batch_bf16']
     print('K2 N=2', b['value'], b['ms_per_step'], b['roofline']['achieved'], b['roofline']['frac'], b['config']['resident'], json.dumps(b['parity'])[:2500])
     print(b['config'])

@@ -8,7 +8,7 @@ python - <<PY
 import json
 try:
     d=json.load(open('gpurun_out/r02_bench_${N}gpu_v1.json'))
-    print('K1', d['n_gpus'], d['value'], d['ms_per_step'], 'lat', d['config']['single_query_latency_ms_p50'], 'frac', d['roofline']['frac'], 'avg_launch_ms', d['roofline']['avg_launch_ms'], d['clocks'])
+    print('K1', d['n_gpus'], d['value'], d['ms_per_step'], 'lat', d.get('run', d['config'])['single_query_latency_ms_p50'], 'frac', d['roofline']['frac'], 'avg_launch_ms', d['roofline']['avg_launch_ms'], d['clocks'])
     print(' parity', {k:(v.get('identical_positions', v.get('identical'))) for k,v in d['parity'].items()})
     print(' shared', d['exact_batch_shared_reads'])
     b=d['sub_records']['batch_bf16']

@@ -18,6 +18,6 @@ PY
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/r02_bench_default_v2.json'))
-print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['config']['single_query_latency_ms_p50'], d['e2e'])
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d.get('run', d['config'])['single_query_latency_ms_p50'], d['e2e'])
 for k,v in d['sub_records'].items(): print(k, v.get('value'), v.get('ms_per_step'), (v.get('roofline') or {}).get('frac'), v.get('invalid'))
 PY
