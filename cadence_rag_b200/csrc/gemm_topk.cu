@@ -50,11 +50,12 @@ constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 256;
 constexpr int kTmemCols = 512;
-// epilogue append staging: each of the 128 epilogue threads owns kBufN (key, query) slots in
-// shared memory, laid out [slot][thread]; they are flushed to the global candidate lists in
-// batches (kBufN independent atomics in flight) instead of one blocking atomic per hit
+// epilogue append staging: each of the 128 epilogue threads owns kBufN key slots in shared memory, laid out
+// [slot][thread].  A thread's staged keys all belong to ONE query (its row of the current tile): they are flushed to that
+// query's global candidate list when the tile is done -- after the accumulator buffer went back to the MMA warp -- with
+// ONE atomicAdd for the whole batch (the list slots are reserved together) instead of one atomic per key.
 constexpr int kBufN = 16;
-constexpr size_t kBufBytes = (size_t)kBufN * 128 * (8 + 2);
+constexpr size_t kBufBytes = (size_t)kBufN * 128 * 8;
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBufBytes;
 
 // ---- PTX wrappers (tcgen05 / TMA); forms follow the PTX ISA for sm_100a
@@ -253,21 +254,17 @@ __device__ __forceinline__ bool tile_has_allowed_rows(const uint32_t *allow, int
     return any != 0;
 }
 
-// Flush one epilogue thread's staged appends to the global candidate lists: all atomics first
-// (independent, so their round trips overlap), then the stores.  Deliberately NOT inlined: the
-// epilogue's hot loop must stay small enough for the instruction cache.
-__device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int cap, const uint64_t *buf_key,
-                                          const uint16_t *buf_q, int et, int nbuf)
+// Flush one epilogue thread's staged keys to its query's global candidate list: one atomic reserves the slots, then the
+// stores.  Deliberately NOT inlined: the epilogue's hot loop must stay small enough for the instruction cache.
+__device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int cap, const uint64_t *buf_key, int et,
+                                          int nbuf, int q)
 {
-    uint32_t base[kBufN];
-    CDR_DEV_ASSERT(nbuf >= 0 && nbuf <= kBufN && et >= 0 && et < 128);
+    CDR_DEV_ASSERT(nbuf > 0 && nbuf <= kBufN && et >= 0 && et < 128 && q >= 0);
+    const uint32_t base = atomicAdd(&counts[q], (uint32_t)nbuf);     // counts may pass cap: that IS the overflow signal
+    uint64_t *dst = lists + (size_t)q * cap;
 #pragma unroll
     for (int i = 0; i < kBufN; ++i)
-        if (i < nbuf) base[i] = atomicAdd(&counts[buf_q[i * 128 + et]], 1u);
-#pragma unroll
-    for (int i = 0; i < kBufN; ++i)
-        if (i < nbuf && base[i] < (uint32_t)cap)
-            lists[(size_t)buf_q[i * 128 + et] * cap + base[i]] = buf_key[i * 128 + et];
+        if (i < nbuf && base + (uint32_t)i < (uint32_t)cap) dst[base + i] = buf_key[i * 128 + et];
 }
 
 // kCluster == 2: the two CTAs of a cluster work on the same corpus tile with different query
@@ -300,7 +297,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t *tmem_empty = bars + 2 * kStg + 2;   // [2]
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStg + 4);
     uint64_t *buf_key = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [kBufN][128]
-    uint16_t *buf_q = reinterpret_cast<uint16_t *>(buf_key + kBufN * 128);                            // [kBufN][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -475,7 +471,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
                 if (p.debug_no_append == 4) {                     // timing aid: TMEM reads only, no maxima
-                    if (v[0] == 12345.678f && v[31] == 8765.4321f) buf_q[et] = 1;   // keeps the load alive
+                    if (v[0] == 12345.678f && v[31] == 8765.4321f) buf_key[et] = 1;   // keeps the load alive
                     continue;
                 }
                 if (c * 32 >= lim) continue;                      // warp-uniform (tail tile)
@@ -504,17 +500,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         if (!(ms[s4] < tau)) {
                             if (p.debug_no_append == 3) nbuf = 0;  // timing aid: stage, never flush
                             if (nbuf > kBufN - 8) {                // make room for up to 8 hits
-                                flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
+                                flush_staged(p.counts, p.lists, p.cap, buf_key, et, nbuf, q);
                                 nbuf = 0;
                             }
+                            const uint32_t row_lo = 0xFFFFFFFFu - (uint32_t)(row0 + c * 32 + 8 * s4);   // key low word of column 8*s4
 #pragma unroll
                             for (int j = 8 * s4; j < 8 * s4 + 8; ++j) {
                                 if (!(v[j] < tau) && ((allow_w >> j) & 1u)) {
-                                    const uint64_t key = cdr_pack_key(v[j], (uint32_t)(row0 + c * 32 + j));
-                                    if (key > tau_key) {
+                                    // above the threshold: in.  Equal to it (or NaN): the packed key decides (row order / NaN code)
+                                    const uint64_t key = ((uint64_t)cdr_order_f32(v[j]) << 32) | (uint64_t)(row_lo - (uint32_t)(j - 8 * s4));
+                                    if (v[j] > tau || key > tau_key) {
                                         CDR_DEV_ASSERT(nbuf >= 0 && nbuf < kBufN && q < p.nq && row0 + c * 32 + j < p.n_rows);
                                         buf_key[nbuf * 128 + et] = key;
-                                        buf_q[nbuf * 128 + et] = (uint16_t)q;
                                         ++nbuf;
                                     }
                                 }
@@ -529,15 +526,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 if (k2Sm && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[buf]), 0u));   // leader's barrier
                 else mbar_arrive(&tmem_empty[buf]);
             }
-            // Flush half-full staging buffers NOW, after the accumulator buffer went back to the MMA
-            // warp: the atomics' round trip then overlaps the next tile's MMAs instead of holding TMEM.
-            if (nbuf >= kBufN / 2 && p.debug_no_append != 3) {
-                flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
-                nbuf = 0;
-            }
+            // The tile's keys go out NOW, after the accumulator buffer went back to the MMA warp (the atomic's round trip
+            // overlaps the next tile's MMAs instead of holding TMEM): the next tile is another query's.
+            if (nbuf > 0 && p.debug_no_append != 3) flush_staged(p.counts, p.lists, p.cap, buf_key, et, nbuf, q);
+            nbuf = 0;
             ++tile_no;
         }
-        if (nbuf > 0) flush_staged(p.counts, p.lists, p.cap, buf_key, buf_q, et, nbuf);
     }
 
     tc_fence_before();
