@@ -12,15 +12,15 @@
 // accumulator buffers (2 x 256 columns = all 512) so the epilogue of tile t overlaps the MMAs of
 // tile t+1.
 //
-// Warp roles (256 threads, one CTA per SM, persistent over work items):
+// Warp roles (256 or 384 threads, one CTA per SM, persistent over work items):
 //   warp 0   TMA producer   : cp.async.bulk.tensor.2d (128B swizzle) A and B boxes per K block
 //   warp 1   MMA issuer     : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //                             (128x256x16), tcgen05.commit releases smem stages / publishes TMEM
 //   warp 2   TMEM allocator
 //   warps 4-7 epilogue      : tcgen05.ld 32x32b (thread = one query row), running max of each
-//                             32-column chunk against the query's threshold tau; the rare chunks
-//                             that beat it append (score,row) keys to the query's candidate list
-//                             in global memory (one atomicAdd per chunk).
+//   (+ 8-11 in the small,     32-column chunk against the query's threshold tau; the rare chunks
+//    append-heavy segments)   that beat it stage (score,row) keys in shared memory and append them to
+//                             the query's candidate list in global memory (one atomicAdd per tile).
 //
 // Exactness argument: every row whose bf16 score >= tau[q] is appended (complete above the
 // threshold), and tau[q] is always the KC-th best score of a subset of the rows seen so far, so
@@ -48,15 +48,22 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kBBytes = kBlockN * kBlockK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kGemmThreads = 256;
 constexpr int kTmemCols = 512;
+// kEpi epilogue warp groups of 4 warps (one warp per TMEM lane quarter); group g reads the g-th share of a tile's 256
+// accumulator columns.  One group leaves ONE warp per scheduler for the epilogue, so the slow path (a dependent chain of
+// ~300 instructions per 32-column chunk with a hit) runs at the latency of a single warp: ~1 us per chunk, exposed in the
+// early, append-heavy segments.  Two groups halve the columns per warp and give every scheduler two warps to interleave.
+__host__ __device__ constexpr int gemm_threads(int kEpi) { return 128 + 128 * kEpi; }
 // epilogue append staging: each of the 128 epilogue threads owns kBufN key slots in shared memory, laid out
 // [slot][thread].  A thread's staged keys all belong to ONE query (its row of the current tile): they are flushed to that
 // query's global candidate list when the tile is done -- after the accumulator buffer went back to the MMA warp -- with
 // ONE atomicAdd for the whole batch (the list slots are reserved together) instead of one atomic per key.
-constexpr int kBufN = 16;
-constexpr size_t kBufBytes = (size_t)kBufN * 128 * 8;
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBufBytes;
+__host__ __device__ constexpr int buf_slots(int kEpi) { return kEpi == 4 ? 8 : 16; }     // key slots per epilogue thread (<= 32 KB in all)
+__host__ __device__ constexpr size_t gemm_smem(int kEpi)
+{
+    return (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + (size_t)buf_slots(kEpi) * 128 * kEpi * 8;
+}
+static_assert(gemm_smem(2) <= 232448 && gemm_smem(4) <= 232448, "dynamic shared memory limit of sm_100a");
 
 // ---- PTX wrappers (tcgen05 / TMA); forms follow the PTX ISA for sm_100a
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
@@ -256,15 +263,16 @@ __device__ __forceinline__ bool tile_has_allowed_rows(const uint32_t *allow, int
 
 // Flush one epilogue thread's staged keys to its query's global candidate list: one atomic reserves the slots, then the
 // stores.  Deliberately NOT inlined: the epilogue's hot loop must stay small enough for the instruction cache.
-__device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int cap, const uint64_t *buf_key, int et,
+template <int kBufN, int kStride>
+__device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int cap, const uint64_t *buf_key, int es,
                                           int nbuf, int q)
 {
-    CDR_DEV_ASSERT(nbuf > 0 && nbuf <= kBufN && et >= 0 && et < 128 && q >= 0);
+    CDR_DEV_ASSERT(nbuf > 0 && nbuf <= kBufN && es >= 0 && es < kStride && q >= 0);
     const uint32_t base = atomicAdd(&counts[q], (uint32_t)nbuf);     // counts may pass cap: that IS the overflow signal
     uint64_t *dst = lists + (size_t)q * cap;
 #pragma unroll
     for (int i = 0; i < kBufN; ++i)
-        if (i < nbuf && base + (uint32_t)i < (uint32_t)cap) dst[base + i] = buf_key[i * 128 + et];
+        if (i < nbuf && base + (uint32_t)i < (uint32_t)cap) dst[base + i] = buf_key[i * kStride + es];
 }
 
 // kCluster == 2: the two CTAs of a cluster work on the same corpus tile with different query
@@ -276,8 +284,8 @@ __device__ __noinline__ void flush_staged(uint32_t *counts, uint64_t *lists, int
 // memory read per MMA), TMA completions of both CTAs are credited to the leader's "full" barrier,
 // the leader's MMA warp issues for the pair and commits to both CTAs' barriers, and both CTAs'
 // epilogue warps hand their TMEM buffers back to the leader.
-template <int kCluster, bool k2Sm>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int kCluster, bool k2Sm, int kEpi>
+__global__ void __launch_bounds__(gemm_threads(kEpi), 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const GemmParams p)
 {
@@ -285,6 +293,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     // 128B swizzle needs 1024-byte aligned tiles
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     static_assert(!k2Sm || kCluster == 2, "2-SM MMA needs a CTA pair");
+    static_assert(kEpi == 1 || kEpi == 2 || kEpi == 4, "epilogue warp groups");
+    constexpr int kBufN = buf_slots(kEpi);
+    constexpr int kEpiThreads = 128 * kEpi;                               // staging stride: [slot][epilogue thread]
+    constexpr int kChunksPer = (kBlockN / 32) / kEpi;                     // 32-column chunks per epilogue warp and tile
     constexpr int kStg = k2Sm ? 6 : kStages;                              // ring depth
     constexpr int kBLocal = k2Sm ? kBBytes / 2 : kBBytes;                  // B bytes staged per CTA per stage
     constexpr int kStgBytes = kABytes + kBLocal;
@@ -296,7 +308,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t *tmem_full = bars + 2 * kStg;        // [2]
     uint64_t *tmem_empty = bars + 2 * kStg + 2;   // [2]
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStg + 4);
-    uint64_t *buf_key = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [kBufN][128]
+    uint64_t *buf_key = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(bars) + 256);   // [kBufN][kEpiThreads]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -311,7 +323,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], k2Sm ? 8 : 4);             // one arrival per epilogue warp (of both CTAs)
+            mbar_init(&tmem_empty[b], (k2Sm ? 8 : 4) * kEpi);    // one arrival per epilogue warp (of both CTAs)
         }
         fence_mbar_init();
     }
@@ -442,7 +454,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue
         const int ew = warp & 3;                                  // TMEM lane quarter of this warp
-        const int et = ew * 32 + lane;                            // epilogue thread 0..127
+        const int et = ew * 32 + lane;                            // query row of the tile, 0..127
+        const int eg = (warp - 4) >> 2;                           // column group of this warp, 0..kEpi-1
+        const int es = eg * 128 + et;                             // staging column of this thread
         int nbuf = 0;
         uint32_t tile_no = 0;
         for (int64_t i = 0; i < n_my; ++i) {
@@ -465,13 +479,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * kBlockN;
 #pragma unroll 1
-            for (int c = 0; c < kBlockN / 32; ++c) {
+            for (int c = eg * kChunksPer; c < (eg + 1) * kChunksPer; ++c) {
                 __syncwarp();
                 if (p.debug_no_append >= 5) continue;             // timing aid: no epilogue work at all (mainloop alone)
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
                 if (p.debug_no_append == 4) {                     // timing aid: TMEM reads only, no maxima
-                    if (v[0] == 12345.678f && v[31] == 8765.4321f) buf_key[et] = 1;   // keeps the load alive
+                    if (v[0] == 12345.678f && v[31] == 8765.4321f) buf_key[es] = 1;   // keeps the load alive
                     continue;
                 }
                 if (c * 32 >= lim) continue;                      // warp-uniform (tail tile)
@@ -500,7 +514,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         if (!(ms[s4] < tau)) {
                             if (p.debug_no_append == 3) nbuf = 0;  // timing aid: stage, never flush
                             if (nbuf > kBufN - 8) {                // make room for up to 8 hits
-                                flush_staged(p.counts, p.lists, p.cap, buf_key, et, nbuf, q);
+                                flush_staged<kBufN, kEpiThreads>(p.counts, p.lists, p.cap, buf_key, es, nbuf, q);
                                 nbuf = 0;
                             }
                             const uint32_t row_lo = 0xFFFFFFFFu - (uint32_t)(row0 + c * 32 + 8 * s4);   // key low word of column 8*s4
@@ -511,7 +525,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                     const uint64_t key = ((uint64_t)cdr_order_f32(v[j]) << 32) | (uint64_t)(row_lo - (uint32_t)(j - 8 * s4));
                                     if (v[j] > tau || key > tau_key) {
                                         CDR_DEV_ASSERT(nbuf >= 0 && nbuf < kBufN && q < p.nq && row0 + c * 32 + j < p.n_rows);
-                                        buf_key[nbuf * 128 + et] = key;
+                                        buf_key[nbuf * kEpiThreads + es] = key;
                                         ++nbuf;
                                     }
                                 }
@@ -528,7 +542,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             }
             // The tile's keys go out NOW, after the accumulator buffer went back to the MMA warp (the atomic's round trip
             // overlaps the next tile's MMAs instead of holding TMEM): the next tile is another query's.
-            if (nbuf > 0 && p.debug_no_append != 3) flush_staged(p.counts, p.lists, p.cap, buf_key, et, nbuf, q);
+            if (nbuf > 0 && p.debug_no_append != 3) flush_staged<kBufN, kEpiThreads>(p.counts, p.lists, p.cap, buf_key, es, nbuf, q);
             nbuf = 0;
             ++tile_no;
         }
@@ -700,11 +714,13 @@ int make_map(CUtensorMap *map, const void *base, int64_t rows, int dim, int box_
 int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
 // CADENCE_K2_CLUSTER selects the GEMM variant (A/B measurements): 1 = independent CTAs,
-// 2 = multicast the corpus tile across a 2-CTA cluster (default), 3 = cta_group::2 MMAs (2-SM).
+// 2 = multicast the corpus tile across a 2-CTA cluster, 3 = cta_group::2 MMAs (2-SM; default since round 2: three
+// interleaved runs each on one box, 10M x 1024 queries: 16.73-16.87 ms of GEMM per batch vs 16.94-17.11 for the multicast
+// form, profiles/r02/k2_epilogue_groups/), 4 = the corpus tile multicast across a 4-CTA cluster (4 query tiles).
 int g_k2_cluster = [] {
     const char *e = getenv("CADENCE_K2_CLUSTER");
-    const int v = e ? atoi(e) : 2;
-    return (v >= 1 && v <= 4) ? v : 2;      // 4 = the corpus tile multicast across a 4-CTA cluster (4 query tiles)
+    const int v = e ? atoi(e) : 3;
+    return (v >= 1 && v <= 4) ? v : 3;
 }();
 
 }  // namespace
@@ -785,14 +801,30 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
     rc = make_map(&map_x, s->emb_bf16, s->n_rows, dim, kBlockN / cluster);
     if (rc != CDR_OK) return rc;
 
+    // epilogue warp groups (see gemm_threads()): two in the small, append-heavy segments, one in the large ones, where the
+    // appends are rare and the extra warps only add barrier polling beside the MMA issuer (measured: segments 2-3 of a
+    // 10M x 1024 batch 0.15 / 0.30 -> 0.08 / 0.19 ms with two groups, the 7.5 M-row segment +1 %).  CADENCE_K2_EPI = 1 | 2 | 4
+    // forces one form for every segment (A/B aid).
+    static const int epi_forced = [] {
+        const char *e = getenv("CADENCE_K2_EPI");
+        const int v = e ? atoi(e) : 0;
+        return (v == 1 || v == 2 || v == 4) ? v : 0;
+    }();
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const GemmParams);
+    const int form = two_sm ? 2 : (cluster == 4 ? 3 : (cluster == 2 ? 1 : 0));     // c1, c2 multicast, c2 2-SM MMA, c4 multicast
+    static const gemm_fn fns[4][3] = {
+        {gemm_topk_kernel<1, false, 1>, gemm_topk_kernel<1, false, 2>, gemm_topk_kernel<1, false, 4>},
+        {gemm_topk_kernel<2, false, 1>, gemm_topk_kernel<2, false, 2>, gemm_topk_kernel<2, false, 4>},
+        {gemm_topk_kernel<2, true, 1>, gemm_topk_kernel<2, true, 2>, gemm_topk_kernel<2, true, 4>},
+        {gemm_topk_kernel<4, false, 1>, gemm_topk_kernel<4, false, 2>, gemm_topk_kernel<4, false, 4>}};
     static std::mutex attr_mu;
     static bool attr_done[64] = {false};
     std::unique_lock<std::mutex> attr_lock(attr_mu);
     if (!attr_done[s->device & 63]) {
-        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-        CDR_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        for (int f = 0; f < 4; ++f)
+            for (int e = 0; e < 3; ++e)
+                CDR_CUDA(cudaFuncSetAttribute((const void *)fns[f][e], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)gemm_smem(1 << e)));
         attr_done[s->device & 63] = true;
     }
     attr_lock.unlock();
@@ -832,6 +864,12 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
         const int v = e ? atoi(e) : 4;
         return (int64_t)((v >= 1 && v <= 12) ? v : 4);
     }();
+    // first segment (every row is appended: tau = -inf): 256 * kSeg0 rows must fit the list capacity 32 * KC >= 4096
+    static const int64_t kSeg0 = [] {                // CADENCE_K2_SEG0: A/B aid (4, 8, 16), default 16
+        const char *e = getenv("CADENCE_K2_SEG0");
+        const int v = e ? atoi(e) : 16;
+        return (int64_t)((v == 4 || v == 8 || v == 16) ? v : 16);
+    }();
     // A persistent grid must be co-resident: with 4-CTA clusters a GPC's SM count need not be a multiple of 4, so the
     // number of clusters that fit can be smaller than sm_count / 4 (a cluster that waits for a free slot would run
     // its share of the segment alone afterwards).
@@ -843,14 +881,14 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
         if (occ_by_dev[s->device & 63] == 0) {
             cudaLaunchConfig_t oc = {};
             oc.gridDim = dim3((unsigned)(s->sm_count / 4 * 4));
-            oc.blockDim = dim3(kGemmThreads);
-            oc.dynamicSmemBytes = kGemmSmem;
+            oc.blockDim = dim3(gemm_threads(2));
+            oc.dynamicSmemBytes = gemm_smem(2);
             cudaLaunchAttribute oa[1];
             oa[0].id = cudaLaunchAttributeClusterDimension;
             oa[0].val.clusterDim.x = 4; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
             oc.attrs = oa; oc.numAttrs = 1;
             int n_act = 0;
-            CDR_CUDA(cudaOccupancyMaxActiveClusters(&n_act, gemm_topk_kernel<4, false>, &oc));
+            CDR_CUDA(cudaOccupancyMaxActiveClusters(&n_act, (const void *)fns[3][1], &oc));
             occ_by_dev[s->device & 63] = n_act > 0 ? n_act : 1;
             if (getenv("CADENCE_K2_VERBOSE")) fprintf(stderr, "K2: %d co-resident 4-CTA clusters on device %d\n", n_act, s->device);
         }
@@ -858,7 +896,7 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
     }
     int64_t begin = 0;
     while (begin < p.n_tiles_total) {
-        int64_t end = begin == 0 ? 16 : begin + kSegGrowth * begin;
+        int64_t end = begin == 0 ? kSeg0 : begin + kSegGrowth * begin;
         if (end > p.n_tiles_total) end = p.n_tiles_total;
         p.tile_begin = begin;
         p.tile_end = end;
@@ -868,13 +906,13 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
         const int64_t items = p.tile_major ? (end - begin) : (end - begin) * (p.m_tiles / cluster);
         const int grid = (int)(items < max_clusters ? items : max_clusters) * cluster;
         cdr_prof_mark_begin(1, st);
-        if (cluster == 1) {
-            gemm_topk_kernel<1, false><<<grid, kGemmThreads, kGemmSmem, st>>>(map_q, map_x, p);
-        } else {
+        {
+            const int epi = epi_forced ? epi_forced : (p.tile_major ? 1 : 2);
+            const gemm_fn fn = fns[form][epi == 4 ? 2 : epi - 1];
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
-            cfg.blockDim = dim3(kGemmThreads);
-            cfg.dynamicSmemBytes = kGemmSmem;
+            cfg.blockDim = dim3(gemm_threads(epi));
+            cfg.dynamicSmemBytes = gemm_smem(epi);
             cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
@@ -882,10 +920,8 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
             at[0].val.clusterDim.y = 1;
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
-            cfg.numAttrs = 1;
-            if (two_sm) CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2, true>, map_q, map_x, p));
-            else if (cluster == 4) CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<4, false>, map_q, map_x, p));
-            else CDR_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2, false>, map_q, map_x, p));
+            cfg.numAttrs = cluster > 1 ? 1 : 0;
+            CDR_CUDA(cudaLaunchKernelEx(&cfg, fn, map_q, map_x, p));
         }
         CDR_LAUNCH_CHECK();
         cdr_prof_mark_end(1, st);
