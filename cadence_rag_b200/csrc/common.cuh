@@ -238,6 +238,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// The same for waits that are long by design and off the critical path (an epilogue warp waiting for the next
+// accumulator): the warp sleeps between polls instead of spinning on the issue port.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, unsigned ns)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (ns) __nanosleep(ns);
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
 // 1-D bulk async copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                          uint64_t *bar)

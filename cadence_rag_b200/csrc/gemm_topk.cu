@@ -243,6 +243,7 @@ struct GemmParams {
     int64_t tile_begin, tile_end;   // permuted tile index range of this segment
     int k_blocks;              // D / 64
     int tile_major;            // 1: a cluster walks all query tiles of one corpus tile back to back (see item_of)
+    unsigned epi_sleep_ns;     // epilogue warps sleep this long between polls of the accumulator barrier (0 = spin)
     int debug_no_append;       // measurement aid (CADENCE_K2_DRYRUN=1): treat tau as +inf => pure GEMM + max
 };
 
@@ -475,7 +476,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint32_t buf = tile_no & 1u;
             const uint32_t use = tile_no >> 1;
             CDR_DEV_ASSERT(nt >= 0 && nt < p.n_tiles_total && mt >= 0 && mt < p.m_tiles && row0 < p.n_rows);
-            mbar_wait(&tmem_full[buf], use & 1u);
+            mbar_wait_backoff(&tmem_full[buf], use & 1u, p.epi_sleep_ns);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * kBlockN;
 #pragma unroll 1
@@ -843,6 +844,8 @@ int cdr_batch_bf16_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
     p.k_blocks = dim / kBlockK;
     static const int dryrun = [] { const char *e = getenv("CADENCE_K2_DRYRUN"); return e ? atoi(e) : 0; }();
     p.debug_no_append = dryrun;
+    static const unsigned epi_sleep = [] { const char *e = getenv("CADENCE_K2_EPI_SLEEP"); return e ? (unsigned)atoi(e) : 0u; }();
+    p.epi_sleep_ns = epi_sleep;
     // CADENCE_K2_ORDER: 0 = item-major everywhere, 1 (default) = tile-major on large segments.  Measured at
     // 10M rows x 1024 queries: 16.43 vs 16.58-16.64 ms per batch, DRAM traffic 1.00x algorithmic either way
     // (profiles/r01/k2_dram_per_launch_order{0,1}.csv).
