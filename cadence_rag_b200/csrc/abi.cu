@@ -103,6 +103,8 @@ void cdr_prof_mark_begin(int kind, cudaStream_t st)
     g_prof.pending[kind] = e;
 }
 
+bool cdr_prof_active() { return g_prof.on; }
+
 void cdr_prof_mark_end(int kind, cudaStream_t st)
 {
     if (!g_prof.on) return;
@@ -177,7 +179,7 @@ static int check_search_args(const char *fn, cdr_store *s, const void *q, int nq
 
 static int32_t search_exact_dev(const char *fn, bool share_reads, cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
                                 const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev,
-                                int32_t *out_n_dev, void *stream)
+                                int32_t *out_n_dev, void *stream, const PeerLink *peer = nullptr)
 {
     int rc = check_search_args(fn, s, q_dev, nq, k, out_score_dev, out_id_dev, out_n_dev);
     if (rc != CDR_OK) return rc;
@@ -189,15 +191,24 @@ static int32_t search_exact_dev(const char *fn, bool share_reads, cdr_store *s, 
     ScanWorkspace &ws = s->ws[st];
     // rows with embedding IS NULL are excluded even when the caller passes no filter
     const uint32_t *allow = allow_dev ? allow_dev : (s->any_invalid ? s->valid : nullptr);
-    // grid.y is limited to 65535 query groups per launch
+    // grid.y is limited to 65535 query groups per launch (a fused exchange serves at most its group's max_nq queries)
+    CDR_REQUIRE(peer == nullptr || nq <= peer->max_nq, CDR_ERR_INVALID, "%s: %d queries in one exchange epoch", fn, nq);
     for (int q0 = 0; q0 < nq; q0 += 32768) {
         const int m = (nq - q0) < 32768 ? (nq - q0) : 32768;
         rc = cdr_exact_scan_launch(s, ws, q_dev + (size_t)q0 * s->dim, m, allow, k,
                                    out_score_dev + (size_t)q0 * k, out_id_dev + (size_t)q0 * k,
-                                   out_n_dev + q0, st, share_reads);
+                                   out_n_dev + q0, st, share_reads, nullptr, peer);
         if (rc != CDR_OK) return rc;
     }
     return CDR_OK;
+}
+
+int32_t cdr_search_exact_peer(bool share_reads, cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                              const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev,
+                              void *stream, const PeerLink *peer)
+{
+    return search_exact_dev("cdr_search_sharded (exact lane)", share_reads, s, q_dev, nq, k, allow_dev, out_score_dev,
+                            out_id_dev, out_n_dev, stream, peer);
 }
 
 extern "C" int32_t cdr_search_exact_f32(cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
@@ -220,7 +231,15 @@ extern "C" int32_t cdr_search_scan_bf16(cdr_store *s, const float *q_dev, int32_
                                         const uint32_t *allow_dev, double *out_score_dev,
                                         int64_t *out_id_dev, int32_t *out_n_dev, void *stream)
 {
+    return cdr_search_scan_bf16_peer(s, q_dev, nq, k, allow_dev, out_score_dev, out_id_dev, out_n_dev, stream, nullptr);
+}
+
+int32_t cdr_search_scan_bf16_peer(cdr_store *s, const float *q_dev, int32_t nq, int32_t k, const uint32_t *allow_dev,
+                                  double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev, void *stream,
+                                  const PeerLink *peer)
+{
     const char *fn = "cdr_search_scan_bf16";
+    CDR_REQUIRE(peer == nullptr || nq <= peer->max_nq, CDR_ERR_INVALID, "%s: %d queries in one exchange epoch", fn, nq);
     int rc = check_search_args(fn, s, q_dev, nq, k, out_score_dev, out_id_dev, out_n_dev);
     if (rc != CDR_OK) return rc;
     CDR_REQUIRE(s->emb_bf16 != nullptr, CDR_ERR_STATE, "%s: store has no bf16 rows (created without CDR_STORE_BF16)", fn);
@@ -233,7 +252,7 @@ extern "C" int32_t cdr_search_scan_bf16(cdr_store *s, const float *q_dev, int32_
     for (int q0 = 0; q0 < nq; q0 += 32768) {
         const int m = (nq - q0) < 32768 ? (nq - q0) : 32768;
         rc = cdr_bf16_scan_launch(s, ws, q_dev + (size_t)q0 * s->dim, m, allow, k, out_score_dev + (size_t)q0 * k,
-                                  out_id_dev + (size_t)q0 * k, out_n_dev + q0, st);
+                                  out_id_dev + (size_t)q0 * k, out_n_dev + q0, st, nullptr, nullptr, peer);
         if (rc != CDR_OK) return rc;
     }
     return CDR_OK;

@@ -108,13 +108,30 @@ struct DeviceGuard {
     }
 };
 
+// One rank's view of a peer-memory exchange group (peer.cu) for ONE epoch, passed by value to the kernels that take part in
+// the exchange: the K4p kernel, and -- fused -- the finalize kernels of the scan lanes, whose ordering CTA pushes the
+// query's final list straight into the peers' buffers, waits for theirs and merges (no local list round trip, one launch
+// less per step).  world == 0: no exchange.
+constexpr int kPeerFusedRanks = 8;      // the fused form keeps its merge scratch in static shared memory:
+constexpr int kPeerFusedK = 64;         // world <= 8 ranks x k <= 64 entries x 16 bytes = 8 KB
+struct PeerLink {
+    unsigned char *base[CDR_PEER_MAX_RANKS];   // every rank's receive buffer as mapped here (own included)
+    int rank = 0, world = 0;
+    int max_nq = 0, max_k = 0;
+    size_t entry_bytes = 0, flags_off = 0;
+    uint32_t epoch = 0;
+    int q0 = 0;                                // buffer slot of the launch's first query
+};
+
 // K1 + finalize on `st` (exact_scan.cu).  share_reads: score every streamed tile against 3 queries per CTA
 // (batches of concurrent exact requests); false = one scan of the corpus per query.  Same bits either way.
 // Single-query "ann" lane (exact_scan.cu): candidate pass over the bf16 rows, exact re-score.  Store mutex held by the caller.
 // q_index / q_count: the conditional re-run form (see cdr_exact_scan_redo_launch), both null for a plain launch.
+// peer (plain launches only): the finalize kernel ends with the exchange of `peer`'s epoch -- out_* then receive the
+// MERGED lists of all ranks (see PeerLink).
 int cdr_bf16_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
                          double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st,
-                         const int *q_index = nullptr, const int *q_count = nullptr);
+                         const int *q_index = nullptr, const int *q_count = nullptr, const PeerLink *peer = nullptr);
 // Re-run queries q_index[0 .. min(*q_count, n_slots)) (count on the device) on the exact fp32 lane, results written to
 // the queries' own output rows; with a zero count the launches exit at once.
 int cdr_exact_scan_redo_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int n_slots, const uint32_t *allow,
@@ -132,11 +149,20 @@ struct ScanFinalizeOn {
 };
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
                           double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st, bool share_reads,
-                          const ScanFinalizeOn *fin = nullptr);
+                          const ScanFinalizeOn *fin = nullptr, const PeerLink *peer = nullptr);
+bool cdr_scan_peer_fusable(bool bf16_rows, int k, int world);
+// The scan lanes behind cdr_search_exact_f32[_shared] / cdr_search_scan_bf16 with an optional fused exchange (abi.cu).
+int32_t cdr_search_exact_peer(bool share_reads, cdr_store *s, const float *q_dev, int32_t nq, int32_t k,
+                              const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev,
+                              void *stream, const PeerLink *peer);
+int32_t cdr_search_scan_bf16_peer(cdr_store *s, const float *q_dev, int32_t nq, int32_t k, const uint32_t *allow_dev,
+                                  double *out_score_dev, int64_t *out_id_dev, int32_t *out_n_dev, void *stream,
+                                  const PeerLink *peer);
 
 // profiling hooks (abi.cu)
 void cdr_prof_mark_begin(int kind, cudaStream_t st);
 void cdr_prof_mark_end(int kind, cudaStream_t st);
+bool cdr_prof_active();
 
 // ------------------------------------------------------------------------------------ device
 #ifdef __CUDACC__
@@ -185,6 +211,42 @@ __device__ __forceinline__ bool cdr_result_before(double sa, int64_t ia, double 
     if (na != nb) return nb;
     if (!na && sa != sb) return sa > sb;
     return ia < ib;
+}
+
+// The same order on integers: the B200's fp64 compare path is slow (a 64 x 64 rank count over double scores cost 14.5 us
+// in the latency finalize, profiles/r02/latency), so the ranking loops compare order keys.  Monotone map double -> uint64
+// (larger score => larger key), NaN => 0 (below every number: NaN last), +-0 => one key (they compare equal).
+// cdr_key_before(ka, ia, kb, ib) == cdr_result_before(sa, ia, sb, ib) for ka = cdr_order_f64(sa), kb = cdr_order_f64(sb).
+__device__ __forceinline__ uint64_t cdr_order_f64_bits(uint64_t b)
+{
+    const uint64_t mag = b & 0x7FFFFFFFFFFFFFFFull;
+    if (mag > 0x7FF0000000000000ull) return 0ull;
+    if (mag == 0ull) return 0x8000000000000000ull;
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ uint64_t cdr_order_f64(double s)
+{
+    return cdr_order_f64_bits((uint64_t)__double_as_longlong(s));
+}
+__device__ __forceinline__ bool cdr_key_before(uint64_t ka, int64_t ia, uint64_t kb, int64_t ib)
+{
+    return ka > kb || (ka == kb && ia < ib);
+}
+
+// Number of entries of an ORDERED list (keys / ids, n valid entries, n <= k_cap) that sort before (key, id): branch-free
+// binary search with a trip count fixed by k_cap.
+__device__ __forceinline__ int cdr_sorted_count_before(const uint64_t *keys, const int64_t *ids, int n, int k_cap, uint64_t key,
+                                                       int64_t id)
+{
+    int cnt = 0;
+    for (int half = 1 << (31 - __clz(k_cap > 1 ? k_cap : 1)); half > 0; half >>= 1) {
+        const int pos = cnt + half;
+        const bool in = pos <= n;
+        const int idx = in ? pos - 1 : 0;
+        const bool before = cdr_key_before(keys[idx], ids[idx], key, id);
+        cnt = (in && before) ? pos : cnt;
+    }
+    return cnt;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -257,6 +319,22 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// ---- pushes between the CTAs of a cluster: a remote shared-memory store that completes `8 bytes` on an mbarrier in the
+// RECEIVER's shared memory (st.async), so the receiver waits on its own barrier and no cluster-wide barrier (whose release
+// fence costs microseconds) sits on the path.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_b64(uint32_t dst_cluster_addr, uint64_t v, uint32_t bar_cluster_addr)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(dst_cluster_addr), "l"(v), "r"(bar_cluster_addr)
+                 : "memory");
 }
 
 __device__ __forceinline__ float warp_sum_f32(float v)
@@ -398,5 +476,104 @@ struct WarpTopK {
     }
 };
 
+
+// ---- peer-memory exchange of one query's list, by one CTA (the protocol is described at the top of peer.cu).
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const void *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by every thread of the CTA.  l_sc / l_id: this rank's ordered list for the query (my_n entries; shared or global
+// memory, written before the call -- the function starts with a CTA barrier).  slot: the query's slot in the group's buffers.
+// m_key / m_id (world * k entries), s_n (world ints) and s_cnt: shared-memory scratch.  o_*: the query's output row.
+//   push  : the list goes into slot[parity][me][slot] of EVERY rank's buffer (posted NVLink writes), then flag[me][slot] =
+//           epoch is published in every buffer with a system-scope release store;
+//   wait  : `world` threads spin (acquire loads on LOCAL memory) until flag[r][slot] >= epoch for every r;
+//   merge : the `world` lists are ranked by counting with the global ordering rule and the first k written out.
+__device__ __forceinline__ void peer_exchange_cta(const PeerLink &pl, int slot, int k, const double *l_sc,
+                                                  const int64_t *l_id, int my_n, uint64_t *m_key, int64_t *m_id, int *s_n,
+                                                  int *s_cnt, double *o_sc, int64_t *o_id, int32_t *o_n)
+{
+    const uint32_t par = pl.epoch & 1u;
+    const size_t slot_me = (((size_t)par * pl.world + pl.rank) * pl.max_nq + slot) * pl.entry_bytes;
+    CDR_DEV_ASSERT(slot >= 0 && slot < pl.max_nq && k <= pl.max_k && slot_me + pl.entry_bytes <= pl.flags_off && my_n >= 0 &&
+                   my_n <= k);
+    if (threadIdx.x == 0) *s_cnt = 0;
+    __syncthreads();
+    for (int r = 0; r < pl.world; ++r) {
+        unsigned char *dst = pl.base[r] + slot_me;
+        unsigned long long *d_sc = reinterpret_cast<unsigned long long *>(dst);
+        unsigned long long *d_id = d_sc + pl.max_k;
+        for (int i = threadIdx.x; i < my_n; i += blockDim.x) {
+            d_sc[i] = (unsigned long long)__double_as_longlong(l_sc[i]);
+            d_id[i] = (unsigned long long)l_id[i];
+        }
+        if (threadIdx.x == 0) *reinterpret_cast<int32_t *>(d_id + pl.max_k) = my_n;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pl.world) {
+        const int r = threadIdx.x;
+        // the CTA's stores above are ordered before this release (bar.sync + cumulativity)
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<uint32_t *>(pl.base[r] + pl.flags_off) + (size_t)pl.rank * pl.max_nq + slot, pl.epoch);
+        // rank r's list for this query has landed in MY buffer
+        const uint32_t *flag =
+            reinterpret_cast<const uint32_t *>(pl.base[pl.rank] + pl.flags_off) + (size_t)r * pl.max_nq + slot;
+        long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(flag) - pl.epoch) < 0) {
+            if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer never launched -> fail, do not hang
+        }
+        const unsigned char *src = pl.base[pl.rank] + (((size_t)par * pl.world + r) * pl.max_nq + slot) * pl.entry_bytes;
+        s_n[r] = *reinterpret_cast<const volatile int32_t *>(src + (size_t)pl.max_k * 16);
+    }
+    __syncthreads();
+
+    // merge: every list arrives ordered, so entry i of list r has global rank i + (entries of the other lists before it),
+    // each found by a branch-free binary search (cdr_sorted_count_before); a winner's score bits are read again from the buffer
+    const int tot = pl.world * k;
+    int local = 0;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int r = e / k, i = e - r * k;
+        const bool ok = i < s_n[r];
+        const unsigned char *src = pl.base[pl.rank] + (((size_t)par * pl.world + r) * pl.max_nq + slot) * pl.entry_bytes;
+        m_key[e] = ok ? cdr_order_f64_bits(ld_relaxed_sys_u64(src + (size_t)i * 8)) : 0ull;
+        m_id[e] = ok ? (int64_t)ld_relaxed_sys_u64(src + (size_t)(pl.max_k + i) * 8) : INT64_MAX;
+        local += ok;
+    }
+    if (local) atomicAdd(s_cnt, local);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int r = e / k, i = e - r * k;
+        if (i >= s_n[r]) continue;
+        const uint64_t key = m_key[e];
+        const int64_t id = m_id[e];
+        int rank = i;
+        for (int o = 0; o < pl.world; ++o)
+            if (o != r) rank += cdr_sorted_count_before(m_key + o * k, m_id + o * k, s_n[o], k, key, id);
+        if (rank < k) {
+            const unsigned char *src = pl.base[pl.rank] + (((size_t)par * pl.world + r) * pl.max_nq + slot) * pl.entry_bytes;
+            o_sc[rank] = __longlong_as_double((long long)ld_relaxed_sys_u64(src + (size_t)i * 8));
+            o_id[rank] = id;
+        }
+    }
+    const int n_out = *s_cnt < k ? *s_cnt : k;
+    for (int i = n_out + threadIdx.x; i < k; i += blockDim.x) {
+        o_sc[i] = __longlong_as_double(0x7FF8000000000000ll);
+        o_id[i] = -1;
+    }
+    if (threadIdx.x == 0) *o_n = n_out;
+}
 
 #endif  // __CUDACC__

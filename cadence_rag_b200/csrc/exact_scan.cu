@@ -154,6 +154,11 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
     constexpr int DIM = L::DIM, TR = L::TR, KC = L::KC, CW = L::CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
+    // Programmatic dependent launch: the finalize kernel behind this launch may be scheduled now (its CTAs fit beside a
+    // scan CTA in the latency form) and sleeps in griddepcontrol.wait until this grid has completed and its lists are
+    // visible -- its launch latency and query-norm prologue leave the critical path.  No effect on a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;");
+
     const int S = p.n_stages;
     unsigned char *tiles = smem_raw;
     unsigned char *metas = tiles + (size_t)S * L::kTileBytes;
@@ -877,6 +882,20 @@ struct FinalizeParams {
     const int *q_index;
     const int *q_count;
     int n_slots;
+    // PEER instantiations (plain launches of a row-sharded step): the CTA that orders a query's list goes on to exchange it
+    // with the other ranks (peer_exchange_cta) and out_* receive the MERGED lists -- the K4p kernel folded into this one
+    PeerLink peer;
+};
+
+// Shared memory of the fused exchange: this rank's ordered list and the merge scratch (world <= 8 ranks x k <= 64).
+template <bool PEER>
+struct PeerFusedSmem {
+    double l_sc[PEER ? kPeerFusedK : 1];
+    int64_t l_id[PEER ? kPeerFusedK : 1];
+    uint64_t m_key[PEER ? kPeerFusedRanks * kPeerFusedK : 1];
+    int64_t m_id[PEER ? kPeerFusedRanks * kPeerFusedK : 1];
+    int n[kPeerFusedRanks];
+    int cnt;
 };
 
 // fp64 cosine of query (a-values in smem as float) x one resident row; all lanes return the result.
@@ -900,17 +919,20 @@ __device__ __forceinline__ float4 load_row_vec(const float *rows, const __nv_bfl
                        __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
 }
 
-template <int NPL, int WARPS, int kRB>
+template <int NPL, int WARPS, int kRB, bool PEER = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 4 : 1) scan_finalize_kernel(const FinalizeParams p)
 {
     constexpr int KC = NPL * 32;
     __shared__ uint64_t s_lists[WARPS * KC];
     __shared__ double s_score[KC];
+    __shared__ uint64_t s_key[KC];            // order key of s_score (0 for an empty slot): the ranking compares integers
     __shared__ int64_t s_id[KC];
     __shared__ int s_valid[KC];
     __shared__ int s_nvalid;
+    __shared__ PeerFusedSmem<PEER> s_peer;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched beside the scan (see exact_scan_kernel): its lists are complete now
     int n_live = p.n_slots;
     if (p.q_count != nullptr) {
         const int c = *p.q_count;
@@ -1044,12 +1066,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 4 : 1) scan_finalize_
                     if (sim > 1.0) sim = 1.0;
                     else if (sim < -1.0) sim = -1.0;
                     const double dist = __dsub_rn(1.0, sim);       // pgvector cosine_distance (float8)
-                    s_score[c] = __dsub_rn(1.0, dist);             // SQL: 1 - (embedding <=> q)
+                    const double score = __dsub_rn(1.0, dist);     // SQL: 1 - (embedding <=> q)
+                    s_score[c] = score;
+                    s_key[c] = cdr_order_f64(score);
                     s_id[c] = p.ids[lane == 0 ? row0 : row1];
                     s_valid[c] = 1;
                     my_valid += 1;
                 } else {
-                    s_valid[c] = 0; s_score[c] = 0.0; s_id[c] = -1;
+                    s_valid[c] = 0; s_score[c] = 0.0; s_key[c] = 0ull; s_id[c] = INT64_MAX;
                 }
             }
         }
@@ -1057,22 +1081,44 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 4 : 1) scan_finalize_
     if (my_valid) atomicAdd(&s_nvalid, my_valid);
     __syncthreads();
 
-    // ---- final order by rank counting
+    // ---- final order by rank counting: KC candidates x PARTS threads each (a thread counts every PARTS-th rival)
     const int n_valid = s_nvalid;
-    for (int c = threadIdx.x; c < KC; c += blockDim.x) {
-        if (!s_valid[c]) continue;
-        const double sc = s_score[c];
+    constexpr int PARTS = (WARPS * 32) / KC >= 32 ? 32 : ((WARPS * 32) / KC >= 1 ? (WARPS * 32) / KC : 1);
+    static_assert((PARTS & (PARTS - 1)) == 0 && KC * PARTS <= WARPS * 32, "rank-count split");
+    for (int t = threadIdx.x; t < KC * PARTS; t += blockDim.x) {
+        const int c = t / PARTS, part = t % PARTS;
+        const bool live = s_valid[c] != 0;
+        const uint64_t key = s_key[c];
         const int64_t id = s_id[c];
+        // branch-free: an empty slot carries (key 0, id INT64_MAX) and is never "before" anything, nor is c before itself
         int rank = 0;
-        for (int o = 0; o < KC; ++o) {
-            if (o != c && s_valid[o] && cdr_result_before(s_score[o], s_id[o], sc, id)) ++rank;
+#pragma unroll 16
+        for (int j = 0; j < KC / PARTS; ++j) {
+            const int o = part + j * PARTS;
+            const uint64_t ko = s_key[o];
+            const int64_t io = s_id[o];
+            rank += (int)((ko > key) | ((ko == key) & (io < id)));
         }
+#pragma unroll
+        for (int d = PARTS >> 1; d > 0; d >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
+        if (!live || part != 0) continue;
+        const double sc = s_score[c];
         if (rank < p.k) {
-            p.out_score[(size_t)qi * p.k + rank] = sc;
-            p.out_id[(size_t)qi * p.k + rank] = id;
+            if constexpr (PEER) {
+                s_peer.l_sc[rank] = sc;
+                s_peer.l_id[rank] = id;
+            } else {
+                p.out_score[(size_t)qi * p.k + rank] = sc;
+                p.out_id[(size_t)qi * p.k + rank] = id;
+            }
         }
     }
     const int n_out = n_valid < p.k ? n_valid : p.k;
+    if constexpr (PEER) {
+        if (threadIdx.x == 0 && p.reset_ctr) p.reset_ctr[slot / p.reset_div] = 0u;
+        peer_exchange_cta(p.peer, p.peer.q0 + qi, p.k, s_peer.l_sc, s_peer.l_id, n_out, s_peer.m_key, s_peer.m_id, s_peer.n,
+                          &s_peer.cnt, p.out_score + (size_t)qi * p.k, p.out_id + (size_t)qi * p.k, p.out_n + qi);
+    } else {
     for (int c = n_out + threadIdx.x; c < p.k; c += blockDim.x) {
         p.out_score[(size_t)qi * p.k + c] = __longlong_as_double(0x7FF8000000000000ll);
         p.out_id[(size_t)qi * p.k + c] = -1;
@@ -1080,6 +1126,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 4 : 1) scan_finalize_
     if (threadIdx.x == 0) {
         p.out_n[qi] = n_out;
         if (p.reset_ctr) p.reset_ctr[slot / p.reset_div] = 0u;
+    }
     }
     }
 }
@@ -1095,7 +1142,15 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 4 : 1) scan_finalize_
 // Same arithmetic and ordering as scan_finalize_kernel => identical bits.
 constexpr int kFinCluster = 8;
 
-template <int NPL>
+// -DCDR_FIN_TIMING: thread 0 of the cluster's first CTA prints the kernel's phase boundaries (globaltimer, ns) -- a probe
+// build (csrc/build_ab.sh), compiled out of the shipped library.
+#ifdef CDR_FIN_TIMING
+#define CDR_FIN_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); fin_t[i] = t_; } } while (0)
+#else
+#define CDR_FIN_STAMP(i) do { } while (0)
+#endif
+
+template <int NPL, bool PEER = false>
 __global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256)
     scan_finalize_cluster_kernel(const FinalizeParams p)
 {
@@ -1103,17 +1158,64 @@ __global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256)
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int KC = NPL * 32, WARPS = 8;
     __shared__ uint64_t s_lists[WARPS * KC];   // phase 1: this CTA's partial lists; [0, KC) = its top-KC
-    __shared__ uint64_t s_tree[WARPS * KC];    // phase 2 (CTA 0): the 8 CTAs' lists; [0, KC) = the survivors
+    __shared__ uint64_t s_tree[WARPS * KC];    // phase 2 (CTA 0): the 8 CTAs' lists, pushed by their owners
+    __shared__ uint64_t s_surv[KC];            // phase 3: the survivors this CTA re-scores (slots c of its warps), pushed by CTA 0
     __shared__ double s_score[KC];             // phase 3 results, written into CTA 0 by all CTAs
+    __shared__ uint64_t s_key[KC];             // order key of s_score (0 for an empty slot): the ranking compares integers
     __shared__ int64_t s_id[KC];
-    __shared__ int s_valid[KC];
     __shared__ int s_nvalid;
+    __shared__ __align__(8) uint64_t s_bar[3];  // arrival of: the 8 lists (CTA 0), my survivors, the KC results (CTA 0)
+    __shared__ PeerFusedSmem<PEER> s_peer;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned crank = cluster.block_rank();
+#ifdef CDR_FIN_TIMING
+    unsigned long long fin_t[16] = {0};
+#endif
+    CDR_FIN_STAMP(0);
     const int qi = blockIdx.x / kFinCluster;
     const uint64_t *base = p.lists + (size_t)qi * p.n_lists * KC;
     if (threadIdx.x == 0) s_nvalid = 0;
+
+    // The query row (registers, 16-byte vectors v = lane + 32 u) and its fp64 norm need nothing from the scan: both are
+    // ready before the dependency wait.
+    const float *qrow = p.queries + (size_t)qi * p.dim;
+    const int nvec = p.dim >> 2;
+    constexpr int kMaxU = 16;                      // dim <= 2048
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a[kMaxU];
+#pragma unroll
+    for (int u = 0; u < kMaxU; ++u) {
+        const int v = lane + 32 * u;
+        a[u] = v < nvec ? __ldg(reinterpret_cast<const float4 *>(qrow) + v) : zero4;
+    }
+    double aa = 0.0;
+#pragma unroll
+    for (int u = 0; u < kMaxU; ++u) {
+        if (32 * u < nvec) {                       // (vectors past the row end are zero: they would add nothing)
+            aa = __fma_rn((double)a[u].x, (double)a[u].x, aa);
+            aa = __fma_rn((double)a[u].y, (double)a[u].y, aa);
+            aa = __fma_rn((double)a[u].z, (double)a[u].z, aa);
+            aa = __fma_rn((double)a[u].w, (double)a[u].w, aa);
+        }
+    }
+    aa = warp_sum_f64(aa);
+    // Every exchange between the CTAs of the cluster is a PUSH: st.async stores into the receiver's shared memory that
+    // complete bytes on an mbarrier there, armed here (a cluster barrier costs 2.5-4 us on this path, profiles/r02/latency;
+    // the one below, which publishes the barriers, runs before the dependency wait).  Each barrier serves one phase.
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
+        fence_mbar_init();
+        if (crank == 0) mbar_arrive_expect_tx(&s_bar[0], (uint32_t)(kFinCluster * KC * 8));
+        mbar_arrive_expect_tx(&s_bar[1], (uint32_t)(KC / kFinCluster * 8));
+        if (crank == 0) mbar_arrive_expect_tx(&s_bar[2], (uint32_t)(KC * 24));
+    }
+    cluster.sync();
+    const uint32_t bar0_tree = mapa_u32(smem_u32(&s_bar[0]), 0), bar0_res = mapa_u32(smem_u32(&s_bar[2]), 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched beside the scan (see exact_scan_kernel): its lists are complete now
+    CDR_FIN_STAMP(1);
 
     // ---- 1. this CTA's lists: l = crank + 8 * (warp + 8 * j), software-pipelined like the 1-CTA kernel
     uint64_t k[NPL];
@@ -1149,136 +1251,207 @@ __global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256)
         __syncthreads();
         if ((warp & (2 * step - 1)) == 0) {
             warp_merge_topk<NPL>(k, s_lists + (warp + step) * KC, lane);
+            if (step * 2 < WARPS) {
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+                for (int i = 0; i < NPL; ++i) s_lists[warp * KC + i * 32 + lane] = k[i];
+            }
         }
     }
-    cluster.sync();
+    if (warp == 0) {                              // this CTA's top-KC goes to CTA 0 as list `crank` of its tree
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+            st_async_b64(mapa_u32(smem_u32(&s_tree[crank * KC + i * 32 + lane]), 0), k[i], bar0_tree);
+    }
+    CDR_FIN_STAMP(2);
 
-    // ---- 2. CTA 0: warp w fetches CTA w's top-KC over DSMEM, then the same pairwise tree
+    // ---- 2. CTA 0: the same pairwise tree over the 8 CTAs' lists; warp 0 ends with the KC survivors, sorted, and hands
+    //         survivor c to its owner CTA (c mod 64) / 8, which re-scores it in warp c mod 8
     if (crank == 0) {
-        const uint64_t *remote = cluster.map_shared_rank(s_lists, warp);
+        mbar_wait(&s_bar[0], 0);
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) k[i] = remote[i * 32 + lane];
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) s_tree[warp * KC + i * 32 + lane] = k[i];
+        for (int i = 0; i < NPL; ++i) k[i] = s_tree[warp * KC + i * 32 + lane];
 #pragma unroll
         for (int step = 1; step < WARPS; step <<= 1) {
-            __syncthreads();
+            if (step > 1) __syncthreads();
             if ((warp & (2 * step - 1)) == 0) {
                 warp_merge_topk<NPL>(k, s_tree + (warp + step) * KC, lane);
+                if (step * 2 < WARPS) {
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) s_tree[warp * KC + i * 32 + lane] = k[i];
+                    for (int i = 0; i < NPL; ++i) s_tree[warp * KC + i * 32 + lane] = k[i];
+                }
+            }
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                const int c = i * 32 + lane;
+                const uint32_t owner = (uint32_t)((c % (kFinCluster * WARPS)) / WARPS);
+                st_async_b64(mapa_u32(smem_u32(&s_surv[c]), owner), k[i], mapa_u32(smem_u32(&s_bar[1]), owner));
             }
         }
     }
-    cluster.sync();
+    mbar_wait(&s_bar[1], 0);
+    CDR_FIN_STAMP(3);
 
-    // ---- 3. fp64 re-score, one survivor per warp at a time: c = crank*8 + warp + 64*j
-    const uint64_t *survivors = cluster.map_shared_rank(s_tree, 0);
-    double *r_score = cluster.map_shared_rank(s_score, 0);
-    int64_t *r_id = cluster.map_shared_rank(s_id, 0);
-    int *r_valid = cluster.map_shared_rank(s_valid, 0);
-    const float *qrow = p.queries + (size_t)qi * p.dim;
-    const int nvec = p.dim >> 2;
-    constexpr int kRB = 4;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    double aa = 0.0;
-    for (int v0 = lane; v0 < nvec; v0 += 32 * 2 * kRB) {
-        float4 a[2 * kRB];
-#pragma unroll
-        for (int u = 0; u < 2 * kRB; ++u) {
-            const int v = v0 + 32 * u;
-            a[u] = v < nvec ? __ldg(reinterpret_cast<const float4 *>(qrow) + v) : zero4;
-        }
-#pragma unroll
-        for (int u = 0; u < 2 * kRB; ++u) {
-            aa = __fma_rn((double)a[u].x, (double)a[u].x, aa);
-            aa = __fma_rn((double)a[u].y, (double)a[u].y, aa);
-            aa = __fma_rn((double)a[u].z, (double)a[u].z, aa);
-            aa = __fma_rn((double)a[u].w, (double)a[u].w, aa);
-        }
-    }
-    aa = warp_sum_f64(aa);
+    // ---- 3. fp64 re-score, one survivor per warp at a time: c = crank*8 + warp + 64*j; the row is read in ONE batch of
+    //         independent 16-byte loads per lane (the query vectors are in registers), accumulated in the order
+    //         v = lane, lane + 32, ... of scan_finalize_kernel => the same bits
+    CDR_FIN_STAMP(15);
     for (int c = (int)crank * WARPS + warp; c < KC; c += kFinCluster * WARPS) {
-        const uint64_t key = survivors[c];
+        const uint64_t key = s_surv[c];
         const bool ok = key != CDR_EMPTY_KEY;
         const size_t row = ok ? cdr_key_row(key) : 0;
-        double ab = 0.0, bb = 0.0;
-        if (ok) {
-            for (int v0 = lane; v0 < nvec; v0 += 32 * kRB) {
-                float4 a[kRB], b[kRB];
+        CDR_FIN_STAMP(7);
+        int64_t row_id = INT64_MAX;
+        if (ok && lane == 0) row_id = __ldg(&p.ids[row]);
+        float4 b[kMaxU];
 #pragma unroll
-                for (int u = 0; u < kRB; ++u) {
-                    const int v = v0 + 32 * u;
-                    const bool in = v < nvec;
-                    b[u] = in ? load_row_vec(p.rows, p.bf16_rows, row, p.dim, v) : zero4;
-                    a[u] = in ? __ldg(reinterpret_cast<const float4 *>(qrow) + v) : zero4;
-                }
-#pragma unroll
-                for (int u = 0; u < kRB; ++u) rescore_accumulate(a[u], b[u], ab, bb);
-            }
+        for (int u = 0; u < kMaxU; ++u) {
+            const int v = lane + 32 * u;
+            b[u] = (ok && v < nvec) ? load_row_vec(p.rows, p.bf16_rows, row, p.dim, v) : zero4;
+            // (the widest candidate lists leave no registers to hold the query across the merges: read again, L1/L2 hits)
+            if constexpr (NPL > 4) a[u] = (ok && v < nvec) ? __ldg(reinterpret_cast<const float4 *>(qrow) + v) : zero4;
         }
+        double ab = 0.0, bb = 0.0;
+#pragma unroll
+        for (int u = 0; u < kMaxU; ++u) {
+            if (ok && 32 * u < nvec) rescore_accumulate(a[u], b[u], ab, bb);
+        }
+        CDR_FIN_STAMP(8);
         ab = warp_sum_f64(ab);
         bb = warp_sum_f64(bb);
-        if (lane == 0) {
+        CDR_FIN_STAMP(9);
+        if (lane == 0) {                          // result c -> CTA 0: score, its order key, id (INT64_MAX = empty slot)
+            double score = 0.0;
             if (ok) {
                 double sim = __ddiv_rn(ab, __dsqrt_rn(__dmul_rn(aa, bb)));
                 if (sim > 1.0) sim = 1.0;
                 else if (sim < -1.0) sim = -1.0;
                 const double dist = __dsub_rn(1.0, sim);
-                r_score[c] = __dsub_rn(1.0, dist);
-                r_id[c] = p.ids[row];
-                r_valid[c] = 1;
-            } else {
-                r_score[c] = 0.0; r_id[c] = -1; r_valid[c] = 0;
+                score = __dsub_rn(1.0, dist);
             }
+            CDR_FIN_STAMP(10);
+            st_async_b64(mapa_u32(smem_u32(&s_score[c]), 0), (uint64_t)__double_as_longlong(score), bar0_res);
+            st_async_b64(mapa_u32(smem_u32(&s_key[c]), 0), ok ? cdr_order_f64(score) : 0ull, bar0_res);
+            st_async_b64(mapa_u32(smem_u32(&s_id[c]), 0), (uint64_t)row_id, bar0_res);
         }
     }
-    cluster.sync();
-    if (crank != 0) return;
+    CDR_FIN_STAMP(11);
+    if (crank != 0) return;                       // (its pushes are posted; nobody reads this CTA's memory any more)
+    mbar_wait(&s_bar[2], 0);
+    CDR_FIN_STAMP(4);
 
     // ---- 4. CTA 0: final order by rank counting
     int mine = 0;
-    for (int c = threadIdx.x; c < KC; c += blockDim.x) mine += s_valid[c];
+    for (int c = threadIdx.x; c < KC; c += blockDim.x) mine += s_id[c] != INT64_MAX;
     if (mine) atomicAdd(&s_nvalid, mine);
+    CDR_FIN_STAMP(12);
     __syncthreads();
+    CDR_FIN_STAMP(13);
     const int n_valid = s_nvalid;
-    for (int c = threadIdx.x; c < KC; c += blockDim.x) {
-        if (!s_valid[c]) continue;
-        const double sc = s_score[c];
+    constexpr int PARTS = 256 / KC >= 1 ? 256 / KC : 1;       // threads per candidate: each counts every PARTS-th rival
+    for (int t = threadIdx.x; t < KC * PARTS; t += blockDim.x) {
+        const int c = t / PARTS, part = t % PARTS;
+        const bool live = s_id[c] != INT64_MAX;
+        const uint64_t key = s_key[c];
         const int64_t id = s_id[c];
+        // branch-free: an empty slot carries (key 0, id INT64_MAX) and is never "before" anything, nor is c before itself
         int rank = 0;
-        for (int o = 0; o < KC; ++o) {
-            if (o != c && s_valid[o] && cdr_result_before(s_score[o], s_id[o], sc, id)) ++rank;
+#pragma unroll 16
+        for (int j = 0; j < KC / PARTS; ++j) {
+            const int o = part + j * PARTS;
+            const uint64_t ko = s_key[o];
+            const int64_t io = s_id[o];
+            rank += (int)((ko > key) | ((ko == key) & (io < id)));
         }
+        CDR_FIN_STAMP(14);
+#pragma unroll
+        for (int d = PARTS >> 1; d > 0; d >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
+        if (!live || part != 0) continue;
+        const double sc = s_score[c];
         if (rank < p.k) {
-            p.out_score[(size_t)qi * p.k + rank] = sc;
-            p.out_id[(size_t)qi * p.k + rank] = id;
+            if constexpr (PEER) {
+                s_peer.l_sc[rank] = sc;
+                s_peer.l_id[rank] = id;
+            } else {
+                p.out_score[(size_t)qi * p.k + rank] = sc;
+                p.out_id[(size_t)qi * p.k + rank] = id;
+            }
         }
     }
     const int n_out = n_valid < p.k ? n_valid : p.k;
-    for (int c = n_out + threadIdx.x; c < p.k; c += blockDim.x) {
-        p.out_score[(size_t)qi * p.k + c] = __longlong_as_double(0x7FF8000000000000ll);
-        p.out_id[(size_t)qi * p.k + c] = -1;
+    CDR_FIN_STAMP(5);
+    if constexpr (PEER) {
+        if (threadIdx.x == 0 && p.reset_ctr) p.reset_ctr[qi / p.reset_div] = 0u;
+        peer_exchange_cta(p.peer, p.peer.q0 + qi, p.k, s_peer.l_sc, s_peer.l_id, n_out, s_peer.m_key, s_peer.m_id, s_peer.n,
+                          &s_peer.cnt, p.out_score + (size_t)qi * p.k, p.out_id + (size_t)qi * p.k, p.out_n + qi);
+    } else {
+        for (int c = n_out + threadIdx.x; c < p.k; c += blockDim.x) {
+            p.out_score[(size_t)qi * p.k + c] = __longlong_as_double(0x7FF8000000000000ll);
+            p.out_id[(size_t)qi * p.k + c] = -1;
+        }
+        if (threadIdx.x == 0) {
+            p.out_n[qi] = n_out;
+            if (p.reset_ctr) p.reset_ctr[qi / p.reset_div] = 0u;
+        }
     }
-    if (threadIdx.x == 0) {
-        p.out_n[qi] = n_out;
-        if (p.reset_ctr) p.reset_ctr[qi / p.reset_div] = 0u;
-    }
+    CDR_FIN_STAMP(6);
+#ifdef CDR_FIN_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("FIN start->wait %llu | lists+tree %llu | cta0 tree %llu | rescore %llu (map %llu, key %llu, rows+fma %llu, sums %llu, div %llu, store+id %llu, "
+               "sync %llu) | rank %llu (count %llu, bar %llu, loop %llu, shfl+store %llu) | out/exchange %llu | since-release %llu ns\n",
+               fin_t[1] - fin_t[0], fin_t[2] - fin_t[1], fin_t[3] - fin_t[2], fin_t[4] - fin_t[3], fin_t[15] - fin_t[3], fin_t[7] - fin_t[15],
+               fin_t[8] - fin_t[7], fin_t[9] - fin_t[8], fin_t[10] - fin_t[9], fin_t[11] - fin_t[10], fin_t[4] - fin_t[11],
+               fin_t[5] - fin_t[4], fin_t[12] - fin_t[4], fin_t[13] - fin_t[12], fin_t[14] - fin_t[13], fin_t[5] - fin_t[14],
+               fin_t[6] - fin_t[5], fin_t[6] - fin_t[1]);
+#endif
+}
+
+// pdl: the launch may be scheduled while the kernel before it on `st` (the scan) is still running -- the finalize kernels
+// wait for that grid themselves (griddepcontrol.wait) before they read its lists.
+template <typename Kern>
+static void launch_fin(Kern kern, unsigned grid, unsigned block, cudaStream_t st, bool pdl, const FinalizeParams &fp)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, fp);        // the caller reads the launch status (CDR_LAUNCH_CHECK)
 }
 
 // one launch helper for every candidate width
-static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_t st)
+static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_t st, bool pdl = false)
 {
     // load batch kRB: 2 fits the 64-register budget of the 1024-thread variants (4 spills; measured
     // 25.5 us vs 31.6 us per launch, profiles/r01/README.md)
     // small batches of sorted per-CTA lists (the exact lane serving single requests): 8-CTA cluster per query
     static const bool no_cluster = [] { const char *e = getenv("CADENCE_FIN_CLUSTER"); return e && e[0] == '0'; }();
+    if (fp.peer.world > 0) {
+        // fused exchange (cdr_scan_peer_fusable checked the shape): sorted per-CTA lists, KC 64 or 128
+        if (fp.counts != nullptr || fp.q_index != nullptr || (kc != 64 && kc != 128)) {
+            cdr_set_error("finalize: fused exchange not built for this launch shape (kc %d)", kc);
+            return CDR_ERR_UNSUPPORTED;
+        }
+        if (nq <= 16 && !no_cluster) {
+            if (kc == 64) launch_fin(scan_finalize_cluster_kernel<2, true>, nq * kFinCluster, 256, st, pdl, fp);
+            else launch_fin(scan_finalize_cluster_kernel<4, true>, nq * kFinCluster, 256, st, pdl, fp);
+        } else {
+            if (kc == 64) launch_fin(scan_finalize_kernel<2, 32, 2, true>, nq, 1024, st, pdl, fp);
+            else launch_fin(scan_finalize_kernel<4, 32, 2, true>, nq, 1024, st, pdl, fp);
+        }
+        CDR_LAUNCH_CHECK();
+        return CDR_OK;
+    }
     if (fp.counts == nullptr && fp.q_index == nullptr && nq <= 16 && !no_cluster && (kc == 64 || kc == 128 || kc == 256)) {
-        if (kc == 64) scan_finalize_cluster_kernel<2><<<nq * kFinCluster, 256, 0, st>>>(fp);
-        else if (kc == 128) scan_finalize_cluster_kernel<4><<<nq * kFinCluster, 256, 0, st>>>(fp);
-        else scan_finalize_cluster_kernel<8><<<nq * kFinCluster, 256, 0, st>>>(fp);
+        if (kc == 64) launch_fin(scan_finalize_cluster_kernel<2>, nq * kFinCluster, 256, st, pdl, fp);
+        else if (kc == 128) launch_fin(scan_finalize_cluster_kernel<4>, nq * kFinCluster, 256, st, pdl, fp);
+        else launch_fin(scan_finalize_cluster_kernel<8>, nq * kFinCluster, 256, st, pdl, fp);
         CDR_LAUNCH_CHECK();
         return CDR_OK;
     }
@@ -1292,9 +1465,9 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
         CDR_LAUNCH_CHECK();
         return CDR_OK;
     }
-    if (kc == 64) scan_finalize_kernel<2, 32, 2><<<nq, 1024, 0, st>>>(fp);
-    else if (kc == 128) scan_finalize_kernel<4, 32, 2><<<nq, 1024, 0, st>>>(fp);
-    else if (kc == 256) scan_finalize_kernel<8, 16, 4><<<nq, 512, 0, st>>>(fp);
+    if (kc == 64) launch_fin(scan_finalize_kernel<2, 32, 2>, nq, 1024, st, pdl, fp);
+    else if (kc == 128) launch_fin(scan_finalize_kernel<4, 32, 2>, nq, 1024, st, pdl, fp);
+    else if (kc == 256) launch_fin(scan_finalize_kernel<8, 16, 4>, nq, 512, st, pdl, fp);
     else {
         cdr_set_error("finalize: candidate width %d not built", kc);
         return CDR_ERR_UNSUPPORTED;
@@ -1308,7 +1481,7 @@ template <int J, int RPW, int NPL, int QPC, bool BF = false>
 int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                   const uint32_t *allow, int k, double *out_score, int64_t *out_id, int32_t *out_n,
                   cudaStream_t st, const int *q_index = nullptr, const int *q_count = nullptr,
-                  const ScanFinalizeOn *fin = nullptr)
+                  const ScanFinalizeOn *fin = nullptr, const PeerLink *peer = nullptr)
 {
     using L = ScanSmem<J, RPW, NPL, QPC, BF>;
     constexpr int KC = L::KC;
@@ -1447,13 +1620,23 @@ int launch_scan_t(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
     fp.q_index = sp.q_index;
     fp.q_count = sp.q_count;
     fp.n_slots = nq;
+    if (peer != nullptr) fp.peer = *peer;
     cudaStream_t fst = st;
     if (fin != nullptr && fin->stream != st) {          // the finalize (and what follows it) runs beside the next scan
         CDR_CUDA(cudaEventRecord(fin->scan_done, st));
         CDR_CUDA(cudaStreamWaitEvent(fin->stream, fin->scan_done, 0));
         fst = fin->stream;
     }
-    return launch_finalize(fp, KC, sp.q_index != nullptr && nq > 64 ? 64 : nq, fst);
+    // Programmatic dependent launch of the finalize behind the scan on the same stream (CADENCE_PDL=0: plain stream order;
+    // also off while the profiling marks record an event between the two kernels).
+    static const bool pdl_on = [] { const char *e = getenv("CADENCE_PDL"); return !(e && e[0] == '0'); }();
+    const bool pdl = pdl_on && fst == st && !cdr_prof_active();
+#ifdef CDR_FIN_TIMING
+    // probe: the same finalize twice -- the second run finds its code and rows in the caches
+    static const bool fin_twice = [] { const char *e = getenv("CADENCE_FIN_TWICE"); return e && e[0] == '1'; }();
+    if (fin_twice && peer == nullptr) launch_finalize(fp, KC, sp.q_index != nullptr && nq > 64 ? 64 : nq, fst, pdl);
+#endif
+    return launch_finalize(fp, KC, sp.q_index != nullptr && nq > 64 ? 64 : nq, fst, pdl);
 }
 
 enum ScanMode { kScanSingle = 0, kScanShared = 1, kScanDeep = 2 };
@@ -1462,24 +1645,26 @@ template <int NPL>
 int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                     const uint32_t *allow, int k, double *out_score, int64_t *out_id,
                     int32_t *out_n, cudaStream_t st, ScanMode mode, const int *q_index = nullptr,
-                    const int *q_count = nullptr, const ScanFinalizeOn *fin = nullptr)
+                    const int *q_count = nullptr, const ScanFinalizeOn *fin = nullptr, const PeerLink *peer = nullptr)
 {
 #define CDR_SCAN_CASE(J_, RPW_)                                                                              \
     if constexpr (NPL == 2) {                                                                                \
         if (mode == kScanDeep)                                                                               \
-            return launch_scan_t<J_, kDeepRPW, NPL, kDeepQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
+            return launch_scan_t<J_, kDeepRPW, NPL, kDeepQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, \
+                                                              nullptr, nullptr, nullptr, peer);              \
     }                                                                                                        \
     if (mode != kScanSingle)                                                                                 \
-        return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st); \
-    return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin)
+        return launch_scan_t<J_, RPW_, NPL, kSharedQPC>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, nullptr, \
+                                                        nullptr, nullptr, peer);                             \
+    return launch_scan_t<J_, RPW_, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin, peer)
     switch (s->dim) {
     case 256:  CDR_SCAN_CASE(2, 2);
     case 512:  CDR_SCAN_CASE(4, 2);
     case 768:  CDR_SCAN_CASE(6, 2);
     case 1024: CDR_SCAN_CASE(8, 2);
     // kSharedQPC queries x J float4 would not fit the register budget: one scan per query
-    case 1536: return launch_scan_t<12, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin);
-    case 2048: return launch_scan_t<16, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin);
+    case 1536: return launch_scan_t<12, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin, peer);
+    case 2048: return launch_scan_t<16, 1, NPL, 1>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, fin, peer);
     default:
         cdr_set_error("exact scan: dim %d not built (supported: 256,512,768,1024,1536,2048)", s->dim);
         return CDR_ERR_UNSUPPORTED;
@@ -1498,13 +1683,15 @@ int launch_scan_dim(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
 // CADENCE_K1_DEEP=0 keeps the 3-queries-in-registers kernel for every batch size (A/B aid).
 int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq,
                           const uint32_t *allow, int k, double *out_score, int64_t *out_id,
-                          int32_t *out_n, cudaStream_t st, bool share_reads, const ScanFinalizeOn *fin)
+                          int32_t *out_n, cudaStream_t st, bool share_reads, const ScanFinalizeOn *fin, const PeerLink *peer)
 {
     const bool share = share_reads && nq >= 2;
     if (fin != nullptr && !share)       // (one scan per query only: the pipelined sharded step)
         return k > 56 ? launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, kScanSingle, nullptr, nullptr, fin)
                       : launch_scan_dim<2>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, kScanSingle, nullptr, nullptr, fin);
-    if (k > 56) return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share ? kScanShared : kScanSingle);
+    if (k > 56)
+        return launch_scan_dim<8>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, share ? kScanShared : kScanSingle,
+                                  nullptr, nullptr, nullptr, peer);
     static const bool k1_deep = [] { const char *e = getenv("CADENCE_K1_DEEP"); return !(e && e[0] == '0'); }();
     int n_deep = 0;
     if (share && k1_deep && s->dim <= 1024) {
@@ -1512,12 +1699,26 @@ int cdr_exact_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, i
         if (nq - n_deep >= 10) n_deep = nq;
     }
     if (n_deep > 0) {
-        const int rc = launch_scan_dim<2>(s, ws, q_dev, n_deep, allow, k, out_score, out_id, out_n, st, kScanDeep);
+        const int rc = launch_scan_dim<2>(s, ws, q_dev, n_deep, allow, k, out_score, out_id, out_n, st, kScanDeep, nullptr,
+                                          nullptr, nullptr, peer);
         if (rc != CDR_OK || n_deep == nq) return rc;
     }
     const int rest = nq - n_deep;
+    PeerLink tail;                       // the second launch's queries sit behind the deep groups' in the exchange buffers
+    if (peer != nullptr) {
+        tail = *peer;
+        tail.q0 += n_deep;
+    }
     return launch_scan_dim<2>(s, ws, q_dev + (size_t)n_deep * s->dim, rest, allow, k, out_score + (size_t)n_deep * k,
-                              out_id + (size_t)n_deep * k, out_n + n_deep, st, share && rest >= 2 ? kScanShared : kScanSingle);
+                              out_id + (size_t)n_deep * k, out_n + n_deep, st, share && rest >= 2 ? kScanShared : kScanSingle,
+                              nullptr, nullptr, nullptr, peer != nullptr ? &tail : nullptr);
+}
+
+// The scan lanes' finalize kernels can end with the exchange (PeerLink) for these shapes: candidate width 64 or 128
+// (exact lane: k <= 56; bf16-row lane: k <= 120), merge scratch in static shared memory.
+bool cdr_scan_peer_fusable(bool bf16_rows, int k, int world)
+{
+    return world >= 2 && world <= kPeerFusedRanks && k <= kPeerFusedK && k <= (bf16_rows ? 120 : 56);
 }
 
 // Conditional re-run of the queries q_index[0 .. min(*q_count, n_slots)) of a batch on the exact lane, one scan per
@@ -1535,11 +1736,11 @@ int cdr_exact_scan_redo_launch(cdr_store *s, ScanWorkspace &ws, const float *q_d
 // as the exact lane's (KC = 128 for k <= 120, else 256), exact fp64 re-score of the survivors.  One scan per query.
 int cdr_bf16_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
                          double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st, const int *q_index,
-                         const int *q_count)
+                         const int *q_count, const PeerLink *peer)
 {
 #define CDR_BF_CASE(J_)                                                                                          \
-    if (k <= 120) return launch_scan_t<J_, 4, 4, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count); \
-    return launch_scan_t<J_, 4, 8, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count)
+    if (k <= 120) return launch_scan_t<J_, 4, 4, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, nullptr, peer); \
+    return launch_scan_t<J_, 4, 8, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, nullptr, peer)
     switch (s->dim) {
     case 256:  CDR_BF_CASE(2);
     case 512:  CDR_BF_CASE(4);

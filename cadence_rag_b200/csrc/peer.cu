@@ -48,11 +48,7 @@ struct cdr_peer_group {
 namespace {
 
 struct PeerParams {
-    unsigned char *base[CDR_PEER_MAX_RANKS];
-    int rank, world;
-    int max_nq, max_k;
-    size_t entry_bytes, flags_off;
-    uint32_t epoch;
+    PeerLink link;
     const double *scores;   // this rank's lists [nq, k]
     const int64_t *ids;
     const int32_t *n;
@@ -62,98 +58,16 @@ struct PeerParams {
     int32_t *out_n;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const void *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __global__ void __launch_bounds__(256) peer_publish_merge_kernel(const PeerParams p)
 {
     extern __shared__ unsigned char raw[];
-    double *s_sc = reinterpret_cast<double *>(raw);
-    int64_t *s_id = reinterpret_cast<int64_t *>(s_sc + (size_t)p.world * p.k);
+    uint64_t *s_sc = reinterpret_cast<uint64_t *>(raw);                    // order keys of the scores
+    int64_t *s_id = reinterpret_cast<int64_t *>(s_sc + (size_t)p.link.world * p.k);
     __shared__ int s_cnt;
     __shared__ int s_n[CDR_PEER_MAX_RANKS];
     const int q = blockIdx.x;
-    const uint32_t par = p.epoch & 1u;
-    const size_t slot_me = (((size_t)par * p.world + p.rank) * p.max_nq + q) * p.entry_bytes;
-    CDR_DEV_ASSERT(q < p.max_nq && p.k <= p.max_k && slot_me + p.entry_bytes <= p.flags_off && p.n[q] >= 0 && p.n[q] <= p.k);
-
-    // ---- push: my list for query q into every rank's buffer
-    const int my_n = p.n[q];
-    for (int r = 0; r < p.world; ++r) {
-        unsigned char *dst = p.base[r] + slot_me;
-        unsigned long long *d_sc = reinterpret_cast<unsigned long long *>(dst);
-        unsigned long long *d_id = d_sc + p.max_k;
-        for (int i = threadIdx.x; i < my_n; i += blockDim.x) {
-            d_sc[i] = (unsigned long long)__double_as_longlong(p.scores[(size_t)q * p.k + i]);
-            d_id[i] = (unsigned long long)p.ids[(size_t)q * p.k + i];
-        }
-        if (threadIdx.x == 0) *reinterpret_cast<int32_t *>(d_id + p.max_k) = my_n;
-    }
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    if (threadIdx.x < p.world) {
-        const int r = threadIdx.x;
-        // the CTA's stores above are ordered before this release (bar.sync + cumulativity)
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<uint32_t *>(p.base[r] + p.flags_off) + (size_t)p.rank * p.max_nq + q, p.epoch);
-        // ---- wait: rank r's list for query q has landed in MY buffer
-        const uint32_t *flag = reinterpret_cast<const uint32_t *>(p.base[p.rank] + p.flags_off) + (size_t)r * p.max_nq + q;
-        long long t0 = clock64();
-        while ((int32_t)(ld_acquire_sys(flag) - p.epoch) < 0) {
-            if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer never launched -> fail, do not hang
-        }
-        const unsigned char *src = p.base[p.rank] + (((size_t)par * p.world + r) * p.max_nq + q) * p.entry_bytes;
-        s_n[r] = *reinterpret_cast<const volatile int32_t *>(src + (size_t)p.max_k * 16);
-    }
-    __syncthreads();
-
-    // ---- merge (rank counting, as topk_merge_kernel)
-    const int tot = p.world * p.k;
-    int local = 0;
-    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
-        const int r = e / p.k, i = e - r * p.k;
-        const bool ok = i < s_n[r];
-        const unsigned char *src = p.base[p.rank] + (((size_t)par * p.world + r) * p.max_nq + q) * p.entry_bytes;
-        s_sc[e] = ok ? __longlong_as_double((long long)ld_relaxed_sys_u64(src + (size_t)i * 8)) : 0.0;
-        s_id[e] = ok ? (int64_t)ld_relaxed_sys_u64(src + (size_t)(p.max_k + i) * 8) : -1;
-        local += ok;
-    }
-    if (local) atomicAdd(&s_cnt, local);
-    __syncthreads();
-    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
-        const int64_t id = s_id[e];
-        if (id < 0) continue;
-        const double sc = s_sc[e];
-        int rank = 0;
-        for (int o = 0; o < tot; ++o) {
-            const int64_t oid = s_id[o];
-            if (oid >= 0 && o != e && cdr_result_before(s_sc[o], oid, sc, id)) ++rank;
-        }
-        if (rank < p.k) {
-            p.out_score[(size_t)q * p.k + rank] = sc;
-            p.out_id[(size_t)q * p.k + rank] = id;
-        }
-    }
-    const int n_out = s_cnt < p.k ? s_cnt : p.k;
-    for (int i = n_out + threadIdx.x; i < p.k; i += blockDim.x) {
-        p.out_score[(size_t)q * p.k + i] = __longlong_as_double(0x7FF8000000000000ll);
-        p.out_id[(size_t)q * p.k + i] = -1;
-    }
-    if (threadIdx.x == 0) p.out_n[q] = n_out;
+    peer_exchange_cta(p.link, p.link.q0 + q, p.k, p.scores + (size_t)q * p.k, p.ids + (size_t)q * p.k, p.n[q], s_sc, s_id,
+                      s_n, &s_cnt, p.out_score + (size_t)q * p.k, p.out_id + (size_t)q * p.k, p.out_n + q);
 }
 
 }  // namespace
@@ -250,6 +164,18 @@ extern "C" int32_t cdr_peer_group_destroy(cdr_peer_group *pg)
     return CDR_OK;
 }
 
+// The group's view for its NEXT epoch (one epoch = one exchange of up to max_nq queries).
+static PeerLink next_epoch_link(cdr_peer_group *pg)
+{
+    PeerLink l;
+    for (int r = 0; r < CDR_PEER_MAX_RANKS; ++r) l.base[r] = pg->peer[r];
+    l.rank = pg->rank; l.world = pg->world; l.max_nq = pg->max_nq; l.max_k = pg->max_k;
+    l.entry_bytes = pg->entry_bytes; l.flags_off = pg->flags_off;
+    l.epoch = ++pg->epoch;
+    l.q0 = 0;
+    return l;
+}
+
 // The pipelined form of a sharded step (one scan per query, more than kPipeChunk queries): the batch goes through in chunks
 // of kPipeChunk queries -- the size the 8-CTA-cluster finalize serves; its 256-thread CTAs (80 registers, 10 KB) and the
 // exchange kernel's fit on an SM BESIDE a scan CTA (288 threads, 126 registers, 197 KB) -- with the finalize + exchange of chunk
@@ -309,10 +235,7 @@ extern "C" int32_t cdr_peer_exchange_merge(cdr_peer_group *pg, const double *sco
     for (int q0 = 0; q0 < nq; q0 += pg->max_nq) {
         const int m = nq - q0 < pg->max_nq ? nq - q0 : pg->max_nq;
         PeerParams p;
-        for (int r = 0; r < CDR_PEER_MAX_RANKS; ++r) p.base[r] = pg->peer[r];
-        p.rank = pg->rank; p.world = pg->world; p.max_nq = pg->max_nq; p.max_k = pg->max_k;
-        p.entry_bytes = pg->entry_bytes; p.flags_off = pg->flags_off;
-        p.epoch = ++pg->epoch;
+        p.link = next_epoch_link(pg);
         p.scores = scores_dev + (size_t)q0 * k; p.ids = ids_dev + (size_t)q0 * k; p.n = n_dev + q0;
         p.nq = m; p.k = k;
         p.out_score = out_score_dev + (size_t)q0 * k; p.out_id = out_id_dev + (size_t)q0 * k; p.out_n = out_n_dev + q0;
@@ -353,6 +276,27 @@ extern "C" int32_t cdr_search_sharded(cdr_store *s, cdr_peer_group *pg, int32_t 
         pg->max_nq % kPipeChunk == 0 && s->finalized && s->emb_f32 != nullptr && q_dev != nullptr)
         return sharded_exact_pipelined(s, pg, q_dev, nq, k, allow_dev, out_score_dev, out_id_dev, out_n_dev,
                                        (cudaStream_t)stream);
+    // Scan lanes: the exchange is folded into the lane's finalize kernel (the CTA that orders a query's list pushes it to the
+    // peers, waits for theirs and merges: one launch and one local round trip less per step).  CADENCE_PEER_FUSED=0 keeps
+    // the separate K4p launch (A/B aid; same bits, covered by the tests).
+    static const bool fused_on = [] { const char *e = getenv("CADENCE_PEER_FUSED"); return !(e && e[0] == '0'); }();
+    const bool bf_lane = lane == CDR_DENSE_LANE_SCAN_BF16;
+    if (fused_on && lane != CDR_DENSE_LANE_BATCH_BF16 && cdr_scan_peer_fusable(bf_lane, k, pg->world)) {
+        for (int q0 = 0; q0 < nq; q0 += pg->max_nq) {
+            const int m = nq - q0 < pg->max_nq ? nq - q0 : pg->max_nq;
+            const PeerLink link = next_epoch_link(pg);
+            const int rc = bf_lane ? cdr_search_scan_bf16_peer(s, q_dev + (size_t)q0 * s->dim, m, k, allow_dev,
+                                                               out_score_dev + (size_t)q0 * k, out_id_dev + (size_t)q0 * k,
+                                                               out_n_dev + q0, stream, &link)
+                                   : cdr_search_exact_peer(lane == CDR_DENSE_LANE_EXACT_F32_SHARED, s,
+                                                           q_dev + (size_t)q0 * s->dim, m, k, allow_dev,
+                                                           out_score_dev + (size_t)q0 * k, out_id_dev + (size_t)q0 * k,
+                                                           out_n_dev + q0, stream, &link);
+            // (an epoch consumed by a failed call is harmless only if every rank fails alike: argument errors are)
+            if (rc != CDR_OK) return rc;
+        }
+        return CDR_OK;
+    }
     for (int q0 = 0; q0 < nq; q0 += pg->max_nq) {
         const int m = nq - q0 < pg->max_nq ? nq - q0 : pg->max_nq;
         int rc = fn(s, q_dev + (size_t)q0 * s->dim, m, k, allow_dev, pg->loc_score, pg->loc_id, pg->loc_n, stream);

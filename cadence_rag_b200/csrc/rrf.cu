@@ -78,11 +78,12 @@ __global__ void __launch_bounds__(kRrfThreads) rrf_merge_kernel(const RrfParams 
         if (!s_first[i]) continue;
         ++uniq_local;
         const double sc = s_score[i];
+        // compared through order keys (cdr_order_f64: same order as the doubles, integer compares -- the fast path here)
+        const uint64_t sc_key = cdr_order_f64(sc);
         int pos = 0;
         for (int j = 0; j < total; ++j) {
-            if (!s_first[j]) continue;
-            const double o = s_score[j];
-            if (o > sc || (o == sc && j < i)) ++pos;
+            const uint64_t o = cdr_order_f64(s_score[j]);
+            pos += (s_first[j] && (o > sc_key || (o == sc_key && j < i))) ? 1 : 0;
         }
         if (pos < p.max_out) {
             uint32_t mask = 0;

@@ -25,35 +25,41 @@ struct MergeParams {
 __global__ void __launch_bounds__(256) topk_merge_kernel(const MergeParams p)
 {
     extern __shared__ unsigned char raw[];
-    double *s_sc = reinterpret_cast<double *>(raw);
-    int64_t *s_id = reinterpret_cast<int64_t *>(s_sc + (size_t)p.R * p.k);
+    uint64_t *s_key = reinterpret_cast<uint64_t *>(raw);                   // order keys of the scores (integer compares)
+    int64_t *s_id = reinterpret_cast<int64_t *>(s_key + (size_t)p.R * p.k);
     __shared__ int s_cnt;
     const int q = blockIdx.x;
     const int tot = p.R * p.k;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    int local = 0;
-    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
-        const int r = e / p.k, i = e - r * p.k;
-        const bool ok = i < p.n[(size_t)r * p.nq + q];
-        const size_t g = ((size_t)r * p.nq + q) * p.k + i;
-        s_sc[e] = ok ? p.scores[g] : 0.0;
-        s_id[e] = ok ? p.ids[g] : -1;     // id -1 marks an empty slot (real ids are >= 0)
-        local += ok;
+    int *s_n = reinterpret_cast<int *>(s_id + (size_t)p.R * p.k);          // valid entries of list r
+    for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
+        int n = p.n[(size_t)r * p.nq + q];
+        n = n < 0 ? 0 : (n > p.k ? p.k : n);
+        s_n[r] = n;
+        if (n) atomicAdd(&s_cnt, n);
     }
-    if (local) atomicAdd(&s_cnt, local);
     __syncthreads();
     for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int r = e / p.k, i = e - r * p.k;
+        const bool ok = i < s_n[r];
+        const size_t g = ((size_t)r * p.nq + q) * p.k + i;
+        s_key[e] = ok ? cdr_order_f64(p.scores[g]) : 0ull;
+        s_id[e] = ok ? p.ids[g] : INT64_MAX;
+    }
+    __syncthreads();
+    // every list is ordered: global rank of entry i of list r = i + (entries of the other lists before it), each found by
+    // a branch-free binary search
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int r = e / p.k, i = e - r * p.k;
+        if (i >= s_n[r]) continue;
+        const uint64_t key = s_key[e];
         const int64_t id = s_id[e];
-        if (id < 0) continue;
-        const double sc = s_sc[e];
-        int rank = 0;
-        for (int o = 0; o < tot; ++o) {
-            const int64_t oid = s_id[o];
-            if (oid >= 0 && o != e && cdr_result_before(s_sc[o], oid, sc, id)) ++rank;
-        }
+        int rank = i;
+        for (int o = 0; o < p.R; ++o)
+            if (o != r) rank += cdr_sorted_count_before(s_key + o * p.k, s_id + o * p.k, s_n[o], p.k, key, id);
         if (rank < p.k) {
-            p.out_score[(size_t)q * p.k + rank] = sc;
+            p.out_score[(size_t)q * p.k + rank] = p.scores[((size_t)r * p.nq + q) * p.k + i];
             p.out_id[(size_t)q * p.k + rank] = id;
         }
     }
@@ -77,7 +83,7 @@ extern "C" int32_t cdr_topk_merge(const double *scores_dev, const int64_t *ids_d
     CDR_REQUIRE(R >= 1 && nq >= 0 && k >= 1 && (int64_t)R * k <= kMergeMax, CDR_ERR_INVALID,
                 "cdr_topk_merge: need R >= 1, k >= 1, R*k <= %d (got R=%d k=%d)", kMergeMax, R, k);
     if (nq == 0) return CDR_OK;
-    const size_t smem = (size_t)R * k * 16;
+    const size_t smem = (size_t)R * k * 16 + (size_t)R * 4;
     {
         // the opt-in is per device: one flag per device of the calling thread, set under a lock
         static std::mutex attr_mu;
@@ -87,7 +93,7 @@ extern "C" int32_t cdr_topk_merge(const double *scores_dev, const int64_t *ids_d
         std::lock_guard<std::mutex> attr_lock(attr_mu);
         if (!attr_set[dev & 63] && smem > 48 * 1024) {
             CDR_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kMergeMax * 16));
+                                          kMergeMax * 20));
             attr_set[dev & 63] = true;
         }
     }

@@ -214,7 +214,9 @@ int32_t cdr_search_batch_bf16_host(cdr_store *s, const float *q_host, int32_t nq
 /* ---- K4: k-way merge of per-shard top-k lists ---------------------------------------------
  * Row-sharded corpora (one store per GPU): after the NCCL all-gather of every rank's
  * [nq,k] (score,id,n) lists this merges R lists per query into the global top-k with the
- * same ordering rule.  scores f64[R,nq,k], ids i64[R,nq,k], n i32[R,nq]. */
+ * same ordering rule.  scores f64[R,nq,k], ids i64[R,nq,k], n i32[R,nq].  Every input list must be in
+ * result order (score desc, NaN last, id asc) -- as every search entry point returns it: the merge ranks
+ * an entry by its own position plus a binary search in each of the other lists. */
 int32_t cdr_topk_merge(const double *scores_dev, const int64_t *ids_dev, const int32_t *n_dev,
                        int32_t R, int32_t nq, int32_t k, double *out_score_dev,
                        int64_t *out_id_dev, int32_t *out_n_dev, void *stream);

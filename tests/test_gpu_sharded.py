@@ -94,14 +94,15 @@ def test_two_rank_nccl_sharded_equals_whole(tmp_path):
     assert np.array_equal(r0["a_ids"], r1["a_ids"])       # every rank holds the identical merged result
 
 
-def _one_gpu_worker(rank, world, port, n_total, k, out_dir, pipeline):
+def _one_gpu_worker(rank, world, port, n_total, k, out_dir, pipeline, fused):
     """Two ranks on ONE device (gloo process group; the peer buffers are mapped with CUDA IPC within the device): the
     K4p exchange kernel of each rank really waits for the other process's push.  Kernels of the two processes are
     time-sliced by the driver, so a spinning exchange kernel is preempted for its peer -- slow, but the protocol and the
     merge are the ones the multi-GPU runs use."""
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CADENCE_SHARD_PIPELINE=str(pipeline))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CADENCE_SHARD_PIPELINE=str(pipeline),
+                      CADENCE_PEER_FUSED=str(fused))
     torch.cuda.set_device(0)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from cadence_rag_b200.dist import ShardedSearcher, shard_range
@@ -132,16 +133,18 @@ def _one_gpu_worker(rank, world, port, n_total, k, out_dir, pipeline):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("pipeline", [0, 1])
-def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path, pipeline):
+@pytest.mark.parametrize("pipeline,fused", [(0, 1), (0, 0), (1, 1)])
+def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path, pipeline, fused):
     """The multi-rank exchange on a ONE-GPU box: 2 processes share cuda:0, each owns half of the rows, and every
     merged result must carry the bits of the unsharded scan (exact lanes) or reach recall 0.999 against it (bf16 lanes)
     and be identical on both ranks.  pipeline=1: the chunked form of the step (finalize + exchange of chunk c on a side
-    stream beside the scan of chunk c+1, CADENCE_SHARD_PIPELINE=1; off by default)."""
+    stream beside the scan of chunk c+1, CADENCE_SHARD_PIPELINE=1; off by default).  fused=1 (default): the scan lanes'
+    finalize kernels end with the exchange (push, wait, merge in the CTA that ordered the list); fused=0: the separate K4p
+    launch behind the lane (CADENCE_PEER_FUSED=0)."""
     import torch.multiprocessing as mp
     sys.path.insert(0, ROOT)
     n_total, k, world = 60_001, 50, 2
-    mp.spawn(_one_gpu_worker, args=(world, _free_port(), n_total, k, str(tmp_path), pipeline), nprocs=world, join=True)
+    mp.spawn(_one_gpu_worker, args=(world, _free_port(), n_total, k, str(tmp_path), pipeline, fused), nprocs=world, join=True)
     from cadence_rag_b200.store import DenseStore, SYNTH_QUERY_SEED, synth_rows_device
     whole = DenseStore("chunks", n_total, dim=1024, device=0)
     whole.append_synthetic(n_total)
