@@ -35,6 +35,9 @@ __global__ void __launch_bounds__(kRrfThreads) rrf_merge_kernel(const RrfParams 
     __shared__ uint16_t s_rank[CDR_RRF_MAX_ITEMS];    // 1-based rank inside its lane
     __shared__ uint8_t s_lane[CDR_RRF_MAX_ITEMS];
     __shared__ uint8_t s_first[CDR_RRF_MAX_ITEMS];    // 1 when item i is the first occurrence of its id
+    __shared__ double s_term[CDR_RRF_MAX_ITEMS];      // 1 / (k + rank) of item i
+    __shared__ uint64_t s_key[CDR_RRF_MAX_ITEMS];     // order key of s_score for the owners
+    __shared__ uint32_t s_mask[CDR_RRF_MAX_ITEMS];
     __shared__ int s_total, s_unique;
 
     const int q = blockIdx.x;
@@ -52,24 +55,31 @@ __global__ void __launch_bounds__(kRrfThreads) rrf_merge_kernel(const RrfParams 
         s_id[i] = p.lane_ids[g];
         s_lane[i] = (uint8_t)l;
         s_rank[i] = (uint16_t)(g - off[l] + 1);
+        s_term[i] = __ddiv_rn(1.0, (double)(p.rrf_k + (g - off[l] + 1)));
     }
     __syncthreads();
 
+    // One branch-free pass per item over the whole sequence (data-dependent branches in these short loops cost more than
+    // the arithmetic they skip): is an earlier item the same id?  If not, item i owns the id and adds the terms of its
+    // occurrences IN SEQUENCE ORDER -- every other step adds +0.0, which leaves the sum's bits alone -- and collects the
+    // lanes that carry it.
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int64_t id = s_id[i];
-        bool first = true;
-        for (int j = 0; j < i; ++j) {
-            if (s_id[j] == id) { first = false; break; }
+        int earlier = 0;
+        double sc = 0.0;
+        uint32_t mask = 0;
+#pragma unroll 8
+        for (int j = 0; j < total; ++j) {
+            const bool eq = s_id[j] == id;
+            earlier |= (int)(eq & (j < i));
+            const bool mine = eq & (j >= i);
+            sc = __dadd_rn(sc, mine ? s_term[j] : 0.0);
+            mask |= mine ? (1u << s_lane[j]) : 0u;
         }
-        s_first[i] = first ? 1 : 0;
-        if (first) {
-            double sc = 0.0;
-            for (int j = i; j < total; ++j) {
-                if (s_id[j] == id)
-                    sc = __dadd_rn(sc, __ddiv_rn(1.0, (double)(p.rrf_k + (int)s_rank[j])));
-            }
-            s_score[i] = sc;
-        }
+        s_first[i] = earlier ? 0 : 1;
+        s_score[i] = sc;
+        s_key[i] = earlier ? 0ull : cdr_order_f64(sc);          // compared as integers below (same order as the doubles)
+        s_mask[i] = mask;
     }
     __syncthreads();
 
@@ -77,23 +87,18 @@ __global__ void __launch_bounds__(kRrfThreads) rrf_merge_kernel(const RrfParams 
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         if (!s_first[i]) continue;
         ++uniq_local;
-        const double sc = s_score[i];
-        // compared through order keys (cdr_order_f64: same order as the doubles, integer compares -- the fast path here)
-        const uint64_t sc_key = cdr_order_f64(sc);
+        const uint64_t key = s_key[i];
         int pos = 0;
+#pragma unroll 8
         for (int j = 0; j < total; ++j) {
-            const uint64_t o = cdr_order_f64(s_score[j]);
-            pos += (s_first[j] && (o > sc_key || (o == sc_key && j < i))) ? 1 : 0;
+            const uint64_t o = s_key[j];
+            pos += (int)(s_first[j] != 0) & (int)((o > key) | ((o == key) & (j < i)));
         }
         if (pos < p.max_out) {
-            uint32_t mask = 0;
-            const int64_t id = s_id[i];
-            for (int j = i; j < total; ++j)
-                if (s_id[j] == id) mask |= 1u << s_lane[j];
             const size_t o = (size_t)q * p.max_out + pos;
-            p.out_ids[o] = id;
-            p.out_scores[o] = sc;
-            p.out_mask[o] = mask;
+            p.out_ids[o] = s_id[i];
+            p.out_scores[o] = s_score[i];
+            p.out_mask[o] = s_mask[i];
         }
     }
     if (uniq_local) atomicAdd(&s_unique, uniq_local);

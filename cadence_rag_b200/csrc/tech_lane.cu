@@ -12,14 +12,15 @@
 //
 // Posting lists are kept in RANK order (best row of the lane's ORDER BY first; re-sorted at index build), with the
 // rank stored beside the row.  One CTA (8 warps) per query; warp w takes the 32-posting chunks w, w+8, ... of every
-// query token.  Candidates therefore arrive best-first: a warp's running top-k fills from the head of the list, its
-// threshold then beats everything further down, and the warp leaves the token as soon as the chunk's best possible
-// key cannot enter (unfiltered: after ~2 chunks per warp, whatever the list length; a scan in row order met ever
-// better rows -- newer calls have larger ids -- and paid an insertion per posting: 4.6 ms for 64 queries over
-// frequent tokens).  Under a selective filter the warps keep scanning until enough rows pass.  The filter predicate
+// query token.  Candidates therefore arrive best-first and in order: the postings that pass the filter are compacted
+// into an already-sorted staged list (no insertion per posting) and the warp leaves the token once KC are staged or
+// the chunk's best possible key cannot enter its running list (unfiltered: after 2 chunks per warp, whatever the list
+// length).  Under a selective filter the warps keep scanning until enough rows pass.  The filter predicate
 // (call_id = ANY, date range, tags overlap -- app/retrieve.py:93-120, WITHOUT the dense lane's `embedding IS NOT
-// NULL`) is evaluated on the posting rows only.  A row matching several tokens may reach several warps: the eight
-// lists are sorted together and duplicates (identical keys) dropped before the LIMIT.
+// NULL`) is evaluated on the posting rows only.  A row matching several tokens appears in several lists: every merge
+// (staged -> running list, and the pairwise tree over the 8 warps) drops identical keys before it cuts to KC.
+// (Round 1/2 history: a scan in row order paid an insertion per posting, 4.6 ms for 64 queries over frequent tokens;
+// rank order with one-by-one insertion + a 512-key shared-memory sort cost 98 us per single-query launch.)
 #include "common.cuh"
 
 #include <algorithm>
@@ -62,35 +63,79 @@ struct TechParams {
     int32_t *out_n;                // [nq]
 };
 
+// a: this warp's running list (registers, sorted descending, distinct, CDR_EMPTY_KEY = 0 at the tail); b: another such
+// list of KC keys in shared memory.  Result in a: the first KC DISTINCT keys of the union, sorted.  Identical keys (a row
+// that matched several tokens) are dropped BEFORE the cut to KC, so duplicates never push a row out.  scratch: KC keys.
+template <int NPL>
+__device__ __forceinline__ void warp_merge_distinct(uint64_t (&a)[NPL], const uint64_t *b, uint64_t *scratch, int lane)
+{
+    constexpr int KC = NPL * 32;
+    uint64_t m[2 * NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        m[i] = a[i];
+        m[NPL + i] = b[KC - 1 - (i * 32 + lane)];          // ascending half: the 2 KC keys form a bitonic sequence
+    }
+    warp_bitonic_merge_desc<2 * NPL>(m, lane);
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * NPL; ++i) {
+        const uint64_t up = __shfl_up_sync(0xffffffffu, m[i], 1);
+        const uint64_t wrap = i > 0 ? __shfl_sync(0xffffffffu, m[i > 0 ? i - 1 : 0], 31) : ~0ull;
+        const uint64_t prev = lane > 0 ? up : wrap;
+        const bool keep = m[i] != CDR_EMPTY_KEY && m[i] != prev;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int pos = off + __popc(mask & ((1u << lane) - 1u));
+        if (keep && pos < KC) scratch[pos] = m[i];
+        off += __popc(mask);
+    }
+    for (int e = (off < KC ? off : KC) + lane; e < KC; e += 32) scratch[e] = CDR_EMPTY_KEY;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) a[i] = scratch[i * 32 + lane];
+    __syncwarp();
+}
+
+// One CTA (8 warps) per query.  Warp w takes the 32-posting chunks w, w+8, ... of every query token, in list (= rank)
+// order: the postings that pass the filter are COMPACTED (ballot + prefix count, no insertion per posting) into a
+// staged list that is therefore already sorted, until KC of them are staged or nothing further down can still enter
+// the warp's running list; the staged list is merged into the running one with duplicates dropped.  The 8 running lists
+// are then merged pairwise the same way and warp 0 writes the first `limit` rows.  Any row of the final answer is among
+// the first `limit` <= KC passing postings of its (warp, token) chunk set, so nothing is lost by the cuts.
 template <int NPL>
 __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechParams p)
 {
     constexpr int KC = NPL * 32;
-    constexpr int NK = kTechWarps * KC;                 // keys sorted together at the end
-    __shared__ uint64_t s_lists[NK];
+    __shared__ uint64_t s_stage[kTechWarps * KC];        // a token's passing postings / the list handed to the merge tree
+    __shared__ uint64_t s_scratch[kTechWarps * KC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x;
     const int ntok = min(p.q_ntok[q], p.max_tokens);
     const int32_t *toks = p.q_tokens + (size_t)q * p.max_tokens;
+    uint64_t *stage = s_stage + warp * KC, *scratch = s_scratch + warp * KC;
 
-    WarpTopK<NPL> top;
-    top.init(s_lists + warp * KC, lane);
+    uint64_t top[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) top[i] = CDR_EMPTY_KEY;
 
     for (int t = 0; t < ntok; ++t) {
         const int32_t tok = toks[t];
         if (tok < 0 || tok >= p.n_index_tokens) continue;            // unknown token: no postings
         const int64_t b0 = p.offsets[tok], b1 = p.offsets[tok + 1];
-        for (int64_t base = b0 + (int64_t)warp * 32; base < b1; base += (int64_t)kTechWarps * 32) {
-            // ranks ascend along the list: nothing from here on can enter once the list is full and even the best
-            // possible key of this chunk (its first rank, any row) is not above the threshold
-            if (top.count == KC) {
+        int cnt = 0;
+        for (int64_t base = b0 + (int64_t)warp * 32; base < b1 && cnt < KC; base += (int64_t)kTechWarps * 32) {
+            // ranks ascend along the list: once the running list is full and even the best possible key of this chunk
+            // (its first rank, any row) is not above its last key, nothing from here on can enter
+            const uint64_t tau = __shfl_sync(0xffffffffu, top[NPL - 1], 31);
+            if (tau != CDR_EMPTY_KEY) {
                 const uint64_t best = ((uint64_t)(0xFFFFFFFFu - p.post_rank[base]) << 32) | 0xFFFFFFFFull;
-                if (best <= top.tau) break;
+                if (best <= tau) break;
             }
             const int64_t i = base + lane;
             uint64_t key = CDR_EMPTY_KEY;
             if (i < b1) {
                 const uint32_t row = p.post_rows[i];
+                const uint32_t rank = p.post_rank[i];
                 bool ok = true;
                 if (p.call_bitmap) {
                     const int32_t slot = p.call_slot[row];
@@ -102,49 +147,37 @@ __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechPa
                     if (p.has_to && ts > p.date_to) ok = false;
                 }
                 if (ok && p.has_tags) ok = (p.tag_bits[row] & p.tag_any) != 0ull;
-                if (ok) key = ((uint64_t)(0xFFFFFFFFu - p.post_rank[i]) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+                if (ok) key = ((uint64_t)(0xFFFFFFFFu - rank) << 32) | (uint64_t)(0xFFFFFFFFu - row);
             }
-            // insert the lanes' candidates one by one (warp-uniform), skipping rows this warp already listed
-            unsigned pending = __ballot_sync(0xffffffffu, key > top.tau);
-            while (pending) {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const uint64_t k = __shfl_sync(0xffffffffu, key, src);
-                if (k <= top.tau) continue;
-                bool dup = false;
-#pragma unroll
-                for (int e = 0; e < NPL; ++e) dup |= top.list[e * 32 + lane] == k;
-                if (__any_sync(0xffffffffu, dup)) continue;
-                top.push(k, lane);
-            }
+            const unsigned mask = __ballot_sync(0xffffffffu, key != CDR_EMPTY_KEY);
+            const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+            if (key != CDR_EMPTY_KEY && pos < KC) stage[pos] = key;
+            cnt += __popc(mask);
         }
+        if (cnt == 0) continue;                                       // (warp-uniform)
+        for (int e = (cnt < KC ? cnt : KC) + lane; e < KC; e += 32) stage[e] = CDR_EMPTY_KEY;
+        __syncwarp();
+        warp_merge_distinct<NPL>(top, stage, scratch, lane);
     }
 
-    // all kTechWarps lists sorted together (descending, bitonic network over shared memory), duplicates dropped
-    __syncthreads();
-    for (int size = 2; size <= NK; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < NK / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride - 1));           // index with bit `stride` clear
-                const int hi = lo + stride;
-                const bool desc = (lo & size) == 0;
-                const uint64_t a = s_lists[lo], b = s_lists[hi];
-                if ((a < b) == desc) { s_lists[lo] = b; s_lists[hi] = a; }
-            }
-            __syncthreads();
+    // the 8 running lists, pairwise
+#pragma unroll
+    for (int step = 1; step < kTechWarps; step <<= 1) {
+        if ((warp & (2 * step - 1)) == step) {
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) stage[i * 32 + lane] = top[i];
         }
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0) warp_merge_distinct<NPL>(top, s_stage + (warp + step) * KC, scratch, lane);
     }
     if (warp == 0) {
         int n = 0;
-        for (int base = 0; base < NK && n < p.limit; base += 32) {
-            const uint64_t key = s_lists[base + lane];
-            const uint64_t prev = (base + lane) > 0 ? s_lists[base + lane - 1] : ~0ull;
-            const bool keep = key != CDR_EMPTY_KEY && key != prev;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            const int pos = n + __popc(m & ((1u << lane) - 1u));
-            if (keep && pos < p.limit) p.out_ids[(size_t)q * p.limit + pos] = p.ids[cdr_key_row(key)];
-            n += __popc(m);
-            if (__all_sync(0xffffffffu, key == CDR_EMPTY_KEY)) break;   // sorted: only empties follow
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int e = i * 32 + lane;
+            const bool keep = top[i] != CDR_EMPTY_KEY;
+            if (keep && e < p.limit) p.out_ids[(size_t)q * p.limit + e] = p.ids[cdr_key_row(top[i])];
+            n += __popc(__ballot_sync(0xffffffffu, keep));
         }
         if (n > p.limit) n = p.limit;
         for (int e = n + lane; e < p.limit; e += 32) p.out_ids[(size_t)q * p.limit + e] = -1;
