@@ -563,8 +563,15 @@ __device__ __forceinline__ void peer_exchange_cta(const PeerLink &pl, int slot, 
         for (int o = 0; o < pl.world; ++o)
             if (o != r) rank += cdr_sorted_count_before(m_key + o * k, m_id + o * k, s_n[o], k, key, id);
         if (rank < k) {
-            const unsigned char *src = pl.base[pl.rank] + (((size_t)par * pl.world + r) * pl.max_nq + slot) * pl.entry_bytes;
-            o_sc[rank] = __longlong_as_double((long long)ld_relaxed_sys_u64(src + (size_t)i * 8));
+            // the score's bits back from its order key; the two keys that do not determine them (NaN payloads, the sign of
+            // a zero) are read again from the buffer
+            uint64_t bits = (key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+            if (key == 0ull || key == 0x8000000000000000ull) {
+                const unsigned char *src =
+                    pl.base[pl.rank] + (((size_t)par * pl.world + r) * pl.max_nq + slot) * pl.entry_bytes;
+                bits = ld_relaxed_sys_u64(src + (size_t)i * 8);
+            }
+            o_sc[rank] = __longlong_as_double((long long)bits);
             o_id[rank] = id;
         }
     }

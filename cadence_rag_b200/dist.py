@@ -189,7 +189,9 @@ class ShardedSearcher:
         import torch
         lane = {"exact": _ffi.CDR_DENSE_LANE_EXACT_F32_SHARED if shared else _ffi.CDR_DENSE_LANE_EXACT_F32,
                 "scan_bf16": _ffi.CDR_DENSE_LANE_SCAN_BF16}.get(mode, _ffi.CDR_DENSE_LANE_BATCH_BF16)
-        q = queries_dev.to(dtype=torch.float32).contiguous()
+        q = queries_dev
+        if q.dtype is not torch.float32 or not q.is_contiguous():
+            q = q.to(dtype=torch.float32).contiguous()
         if q.dim() == 1:
             q = q.unsqueeze(0)
         if int(q.shape[1]) != self.store.dim:
