@@ -23,7 +23,10 @@
 // rank order with one-by-one insertion + a 512-key shared-memory sort cost 98 us per single-query launch.)
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 struct cdr_tech_index {
@@ -96,25 +99,22 @@ __device__ __forceinline__ void warp_merge_distinct(uint64_t (&a)[NPL], const ui
     __syncwarp();
 }
 
-// One CTA (8 warps) per query.  Warp w takes the 32-posting chunks w, w+8, ... of every query token, in list (= rank)
-// order: the postings that pass the filter are COMPACTED (ballot + prefix count, no insertion per posting) into a
-// staged list that is therefore already sorted, until KC of them are staged or nothing further down can still enter
-// the warp's running list; the staged list is merged into the running one with duplicates dropped.  The 8 running lists
-// are then merged pairwise the same way and warp 0 writes the first `limit` rows.  Any row of the final answer is among
-// the first `limit` <= KC passing postings of its (warp, token) chunk set, so nothing is lost by the cuts.
+// The lane for one query inside one CTA (8 warps).  The query's posting chunks are numbered along every token's list; this
+// CTA takes chunks first_chunk + warp, then every chunk_stride-th, in list (= rank) order: the postings that pass the filter
+// are COMPACTED (ballot + prefix count, no insertion per posting) into a staged list that is therefore already sorted,
+// until KC of them are staged or nothing further down can still enter the warp's running list; the staged list is merged
+// into the running one with duplicates dropped.  The 8 running lists are then merged pairwise the same way: warp 0
+// returns with the CTA's list in `top`.  Any row of the final answer is among the first `limit` <= KC passing postings of
+// its (warp, token) chunk set, so nothing is lost by the cuts.
 template <int NPL>
-__global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechParams p)
+__device__ __forceinline__ void tech_cta_list(const TechParams &p, int q, int first_chunk, int chunk_stride,
+                                              uint64_t (&top)[NPL], uint64_t *s_stage, uint64_t *s_scratch)
 {
     constexpr int KC = NPL * 32;
-    __shared__ uint64_t s_stage[kTechWarps * KC];        // a token's passing postings / the list handed to the merge tree
-    __shared__ uint64_t s_scratch[kTechWarps * KC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = blockIdx.x;
     const int ntok = min(p.q_ntok[q], p.max_tokens);
     const int32_t *toks = p.q_tokens + (size_t)q * p.max_tokens;
     uint64_t *stage = s_stage + warp * KC, *scratch = s_scratch + warp * KC;
-
-    uint64_t top[NPL];
 #pragma unroll
     for (int i = 0; i < NPL; ++i) top[i] = CDR_EMPTY_KEY;
 
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechPa
         if (tok < 0 || tok >= p.n_index_tokens) continue;            // unknown token: no postings
         const int64_t b0 = p.offsets[tok], b1 = p.offsets[tok + 1];
         int cnt = 0;
-        for (int64_t base = b0 + (int64_t)warp * 32; base < b1 && cnt < KC; base += (int64_t)kTechWarps * 32) {
+        for (int64_t base = b0 + (int64_t)(first_chunk + warp) * 32; base < b1 && cnt < KC; base += (int64_t)chunk_stride * 32) {
             // ranks ascend along the list: once the running list is full and even the best possible key of this chunk
             // (its first rank, any row) is not above its last key, nothing from here on can enter
             const uint64_t tau = __shfl_sync(0xffffffffu, top[NPL - 1], 31);
@@ -170,19 +170,75 @@ __global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechPa
         __syncthreads();
         if ((warp & (2 * step - 1)) == 0) warp_merge_distinct<NPL>(top, s_stage + (warp + step) * KC, scratch, lane);
     }
-    if (warp == 0) {
-        int n = 0;
+}
+
+// warp 0: the first `limit` rows of the query's list
+template <int NPL>
+__device__ __forceinline__ void tech_write_out(const TechParams &p, int q, const uint64_t (&top)[NPL], int lane)
+{
+    int n = 0;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-            const int e = i * 32 + lane;
-            const bool keep = top[i] != CDR_EMPTY_KEY;
-            if (keep && e < p.limit) p.out_ids[(size_t)q * p.limit + e] = p.ids[cdr_key_row(top[i])];
-            n += __popc(__ballot_sync(0xffffffffu, keep));
-        }
-        if (n > p.limit) n = p.limit;
-        for (int e = n + lane; e < p.limit; e += 32) p.out_ids[(size_t)q * p.limit + e] = -1;
-        if (lane == 0) p.out_n[q] = n;
+    for (int i = 0; i < NPL; ++i) {
+        const int e = i * 32 + lane;
+        const bool keep = top[i] != CDR_EMPTY_KEY;
+        if (keep && e < p.limit) p.out_ids[(size_t)q * p.limit + e] = p.ids[cdr_key_row(top[i])];
+        n += __popc(__ballot_sync(0xffffffffu, keep));
     }
+    if (n > p.limit) n = p.limit;
+    for (int e = n + lane; e < p.limit; e += 32) p.out_ids[(size_t)q * p.limit + e] = -1;
+    if (lane == 0) p.out_n[q] = n;
+}
+
+// Unfiltered queries: one CTA per query (2 chunks per warp and token are read, whatever the list length).
+template <int NPL>
+__global__ void __launch_bounds__(kTechWarps * 32) tech_lane_kernel(const TechParams p)
+{
+    constexpr int KC = NPL * 32;
+    __shared__ uint64_t s_stage[kTechWarps * KC];        // a token's passing postings / the list handed to the merge tree
+    __shared__ uint64_t s_scratch[kTechWarps * KC];
+    uint64_t top[NPL];
+    tech_cta_list<NPL>(p, blockIdx.x, 0, kTechWarps, top, s_stage, s_scratch);
+    if (threadIdx.x < 32) tech_write_out<NPL>(p, blockIdx.x, top, threadIdx.x);
+}
+
+// Filtered queries: under a selective filter a frequent token's whole list is walked before `limit` rows pass (0.87 ms in
+// one CTA for a 0.2 % filter, profiles/r02/README.md 8), so a cluster of 8 CTAs shares the chunks of a query; their 8
+// lists go to CTA 0 through distributed shared memory and are merged by the same pairwise tree.
+constexpr int kTechCluster = 8;
+template <int NPL>
+__global__ void __cluster_dims__(kTechCluster, 1, 1) __launch_bounds__(kTechWarps * 32) tech_lane_cluster_kernel(const TechParams p)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int KC = NPL * 32;
+    __shared__ uint64_t s_stage[kTechWarps * KC];
+    __shared__ uint64_t s_scratch[kTechWarps * KC];
+    __shared__ uint64_t s_gather[kTechCluster * KC];      // CTA 0: the 8 CTAs' lists
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned crank = cluster.block_rank();
+    const int q = blockIdx.x / kTechCluster;
+    uint64_t top[NPL];
+    tech_cta_list<NPL>(p, q, (int)crank * kTechWarps, kTechCluster * kTechWarps, top, s_stage, s_scratch);
+    if (warp == 0) {
+        uint64_t *g0 = cluster.map_shared_rank(s_gather, 0);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) g0[crank * KC + i * 32 + lane] = top[i];
+    }
+    cluster.sync();
+    if (crank != 0) return;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) top[i] = s_gather[warp * KC + i * 32 + lane];
+#pragma unroll
+    for (int step = 1; step < kTechWarps; step <<= 1) {
+        if ((warp & (2 * step - 1)) == step) {
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) s_stage[warp * KC + i * 32 + lane] = top[i];
+        }
+        __syncthreads();
+        if ((warp & (2 * step - 1)) == 0)
+            warp_merge_distinct<NPL>(top, s_stage + (warp + step) * KC, s_scratch + warp * KC, lane);
+    }
+    if (warp == 0) tech_write_out<NPL>(p, q, top, lane);
 }
 
 }  // namespace
@@ -264,7 +320,11 @@ int cdr_tech_lane_launch(cdr_tech_index *ix, const int32_t *d_tok, const int32_t
     p.date_from = date_from_us; p.date_to = date_to_us; p.tag_any = tag_any;
     p.q_tokens = d_tok; p.q_ntok = d_nt; p.max_tokens = max_tokens; p.limit = limit;
     p.out_ids = d_oid; p.out_n = d_on;
-    if (limit <= 64) tech_lane_kernel<2><<<nq, kTechWarps * 32, 0, st>>>(p);
+    // CADENCE_TECH_CLUSTER=0 keeps one CTA per query for filtered requests too (A/B aid)
+    static const bool use_cluster = [] { const char *e = getenv("CADENCE_TECH_CLUSTER"); return !(e && e[0] == '0'); }();
+    const bool filtered = d_bm != nullptr || p.has_from || p.has_to || p.has_tags;
+    if (filtered && use_cluster && limit <= 64) tech_lane_cluster_kernel<2><<<nq * kTechCluster, kTechWarps * 32, 0, st>>>(p);
+    else if (limit <= 64) tech_lane_kernel<2><<<nq, kTechWarps * 32, 0, st>>>(p);
     else tech_lane_kernel<8><<<nq, kTechWarps * 32, 0, st>>>(p);
     CDR_LAUNCH_CHECK();
     return CDR_OK;

@@ -462,6 +462,37 @@ def test_topk_merge_and_sharded_equals_unsharded(corpus_100k):
     assert m_ids.cpu().tolist() == [[3, 9, 8]]
 
 
+def test_topk_merge_random_ordered_lists_ties_nan_zero_signs():
+    """K4 ranks an entry by its position plus a binary search in each other list (integer order keys): random ORDERED
+    lists with score ties across lists (broken by id), NaN tails, +-0 (equal in the order, sign kept in the output),
+    infinities, short and empty lists, against the port."""
+    from cadence_rag_b200.dist import merge_shard_results
+    rng = np.random.default_rng(77)
+    pool = np.array([1.0, 0.5, 0.5, 0.25, 0.0, -0.0, -0.25, np.inf, -np.inf, np.nan, 0.125, 0.75])
+    for case in range(40):
+        R, nq, k = int(rng.integers(1, 9)), int(rng.integers(1, 5)), int(rng.choice([1, 3, 10, 50, 64]))
+        sc = np.zeros((R, nq, k)); ids = np.zeros((R, nq, k), dtype=np.int64); cnt = np.zeros((R, nq), dtype=np.int32)
+        for r in range(R):
+            for q in range(nq):
+                m = int(rng.integers(0, k + 1))
+                vals = rng.choice(pool, size=m) if case % 2 == 0 else np.round(rng.standard_normal(m), 1)
+                # distinct ids across ALL lists of a query (rows live on one shard each)
+                own = (rng.permutation(4 * k)[:m] * R + r).astype(np.int64)
+                order = sorted(range(m), key=lambda i: (vals[i] != vals[i], -vals[i] if vals[i] == vals[i] else 0.0, own[i]))
+                sc[r, q, :m] = vals[order]; ids[r, q, :m] = own[order]; cnt[r, q] = m
+                sc[r, q, m:] = 123.0; ids[r, q, m:] = 7           # garbage behind n: must be ignored
+        m_ids, m_sc, m_n = merge_shard_results(torch.from_numpy(sc).cuda(), torch.from_numpy(ids).cuda(),
+                                               torch.from_numpy(cnt).cuda(), k)
+        torch.cuda.synchronize()
+        g_ids, g_sc, g_n = m_ids.cpu().numpy(), m_sc.cpu().numpy(), m_n.cpu().numpy()
+        want = ports.merge_topk(sc, ids, cnt, k)
+        for q, (w_ids, w_sc) in enumerate(want):
+            assert int(g_n[q]) == len(w_ids), (case, q)
+            assert g_ids[q, :len(w_ids)].tolist() == w_ids, (case, q)
+            assert np.array_equal(g_sc[q, :len(w_ids)].view(np.uint64), np.array(w_sc, dtype=np.float64).view(np.uint64)), (case, q)
+            assert (g_ids[q, len(w_ids):] == -1).all()
+
+
 # =================================================================== K5 RRF
 def test_rrf_kernel_bit_exact_vs_reference_golden(golden_dir):
     with open(os.path.join(golden_dir, "reference_pure.json")) as f:
