@@ -238,6 +238,7 @@ __device__ __forceinline__ bool cdr_key_before(uint64_t ka, int64_t ia, uint64_t
 __device__ __forceinline__ int cdr_sorted_count_before(const uint64_t *keys, const int64_t *ids, int n, int k_cap, uint64_t key,
                                                        int64_t id)
 {
+    CDR_DEV_ASSERT(n >= 0 && n <= k_cap);
     int cnt = 0;
     for (int half = 1 << (31 - __clz(k_cap > 1 ? k_cap : 1)); half > 0; half >>= 1) {
         const int pos = cnt + half;

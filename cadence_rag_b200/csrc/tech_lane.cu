@@ -91,6 +91,7 @@ __device__ __forceinline__ void warp_merge_distinct(uint64_t (&a)[NPL], const ui
         const int pos = off + __popc(mask & ((1u << lane) - 1u));
         if (keep && pos < KC) scratch[pos] = m[i];
         off += __popc(mask);
+        CDR_DEV_ASSERT(i == 0 || m[i] == CDR_EMPTY_KEY || prev >= m[i]);      // the merged sequence is sorted
     }
     for (int e = (off < KC ? off : KC) + lane; e < KC; e += 32) scratch[e] = CDR_EMPTY_KEY;
     __syncwarp();

@@ -220,6 +220,12 @@ int main(int argc, char **argv)
         CK(cdr_tech_lane_host(ix, tok.data(), nt.data(), 2, 4, nullptr, 0, 0, 0, 0, 0, 0, 0, 50, o_ids.data(), o_n.data(), nullptr));
         REQUIRE(o_n[0] == 50 && o_n[1] == 50, "tech lane counts");
         REQUIRE(o_ids[0] > 5800 && o_ids[0] <= 6000, "tech lane head %lld is not in the newest indexed call", (long long)o_ids[0]);
+        // filtered request (cluster form of the lane): call slots 0..2 = rows 0..599, newest allowed call = rows 400..599
+        std::vector<uint32_t> bmap = {0x7u};
+        CK(cdr_tech_lane_host(ix, tok.data(), nt.data(), 2, 4, bmap.data(), 3, 0, 0, 0, 0, 0, 0, 50, o_ids.data(), o_n.data(), nullptr));
+        REQUIRE(o_n[0] == 50 && o_n[1] == 50, "filtered tech lane counts %d %d", o_n[0], o_n[1]);
+        for (int i = 0; i < 100; ++i)
+            REQUIRE(o_ids[i] > 400 && o_ids[i] <= 600, "filtered tech lane id %lld outside the newest allowed call", (long long)o_ids[i]);
         printf("tech ok\n");
     }
     if (on("hybrid")) {
