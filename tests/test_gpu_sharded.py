@@ -115,8 +115,10 @@ def _one_gpu_worker(rank, world, port, n_total, k, out_dir, pipeline, fused):
     assert peer.transport == "peer" and peer.world == world
     qs = synth_rows_device(SYNTH_QUERY_SEED, 0, 70, 1024, device=0)
     out = {}
+    # k60: candidate width 256 on the exact lane (not fusable: separate exchange launch); scan64: the widest fused form
     for name, nq_i, kk, mode in (("exact", 70, k, "exact"), ("one", 1, k, "exact"), ("k10", 64, 10, "exact"),
-                                 ("shared", 40, k, "exact_shared"), ("ann", 70, k, "ann"), ("scan", 3, k, "scan_bf16")):
+                                 ("shared", 40, k, "exact_shared"), ("ann", 70, k, "ann"), ("scan", 3, k, "scan_bf16"),
+                                 ("k60", 5, 60, "exact"), ("scan64", 2, 64, "scan_bf16")):
         ids, sc, n = peer.search(qs[:nq_i], kk, mode="exact" if mode == "exact_shared" else mode, shared=mode == "exact_shared")
         torch.cuda.synchronize()
         out[name] = (ids.cpu().numpy(), sc.cpu().numpy(), n.cpu().numpy())
@@ -153,16 +155,16 @@ def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path, pipeline, fus
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     for key in r0.files:
         assert np.array_equal(r0[key], r1[key]), key                       # every rank holds the identical result
-    for name, nq_i, kk in (("exact", 70, k), ("one", 1, k), ("k10", 64, 10), ("shared", 40, k)):
+    for name, nq_i, kk in (("exact", 70, k), ("one", 1, k), ("k10", 64, 10), ("shared", 40, k), ("k60", 5, 60)):
         w_ids, w_sc, w_n = whole.search_exact(qs[:nq_i], kk)
         torch.cuda.synchronize()
         assert np.array_equal(r0[f"{name}_ids"], w_ids.cpu().numpy()), name
         assert np.array_equal(r0[f"{name}_sc"].view(np.uint64), w_sc.cpu().numpy().view(np.uint64)), name
         assert np.array_equal(r0[f"{name}_n"], w_n.cpu().numpy())
-    w_ids = whole.search_exact(qs, k)[0].cpu().numpy()
-    for name, nq_i in (("ann", 70), ("scan", 3)):
+    for name, nq_i, kk in (("ann", 70, k), ("scan", 3, k), ("scan64", 2, 64)):
+        w_ids = whole.search_exact(qs[:nq_i], kk)[0].cpu().numpy()
         got = r0[f"{name}_ids"]
-        assert np.mean([len(set(got[i]) & set(w_ids[i])) / k for i in range(nq_i)]) >= 0.999, name
+        assert np.mean([len(set(got[i]) & set(w_ids[i])) / kk for i in range(nq_i)]) >= 0.999, name
     allow, cnt_allowed = whole.filter_bitmap(call_slots=[0, 1])
     f_ids, f_sc, f_n = whole.search_exact(qs[:5], k, allow)
     torch.cuda.synchronize()
