@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cadence_rag_b200", "libcadence_dense.so")
-MNEMONICS = ["UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "FMNMX3", "FHFMA", "SYNCS", "HMMA", "IMMA", "DMMA", "HGMMA", "QGMMA"]
+MNEMONICS = ["UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "FMNMX3", "FHFMA", "SYNCS", "STAS", "HMMA", "IMMA", "DMMA", "HGMMA", "QGMMA"]
 
 
 def demangle(names):

@@ -287,6 +287,11 @@ def test_library_is_sm100a_with_bulk_copy_and_no_legacy_mma():
         assert "FMNMX3" in body, "3-input max missing from the epilogue"
     for body in scan:
         assert "UBLKCP" in body, "bulk async copy missing from an exact_scan_kernel instantiation"
+    # the latency finalize hands data between the CTAs of its cluster with st.async (STAS) + mbarrier waits, not cluster barriers
+    fin = [v for k, v in sass.items() if "scan_finalize_cluster_kernel" in k]
+    assert len(fin) >= 5
+    for body in fin:
+        assert "STAS" in body and "SYNCS" in body, "st.async / mbarrier hand-over missing from the latency finalize"
     legacy = re.compile(r"\b(HMMA|IMMA|DMMA|HGMMA|QGMMA)\b")
     for name, body in sass.items():
         assert not legacy.search(body), f"legacy MMA instruction in {name}"
