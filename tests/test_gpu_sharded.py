@@ -94,6 +94,20 @@ def test_two_rank_nccl_sharded_equals_whole(tmp_path):
     assert np.array_equal(r0["a_ids"], r1["a_ids"])       # every rank holds the identical merged result
 
 
+def _crafted_lists(rank, world, nq=6, k=24):
+    """Rank `rank`'s ordered (scores [nq,k], ids [nq,k], n [nq]) lists for the exchange test; ids are distinct across ranks."""
+    rng = np.random.default_rng(1000 + rank)
+    pool = np.array([1.0, 0.5, 0.5, 0.25, 0.0, -0.0, -0.25, np.inf, -np.inf, np.nan, np.nan, 0.125])
+    sc = np.full((nq, k), 77.0); ids = np.full((nq, k), 5, dtype=np.int64); n = np.zeros(nq, dtype=np.int32)
+    for q in range(nq):
+        m = 0 if (q == 1 and rank == 0) else int(rng.integers(0, k + 1))
+        vals = rng.choice(pool, size=m)
+        own = (rng.permutation(4 * k)[:m] * world + rank).astype(np.int64)
+        order = sorted(range(m), key=lambda i: (vals[i] != vals[i], -vals[i] if vals[i] == vals[i] else 0.0, own[i]))
+        sc[q, :m] = vals[order]; ids[q, :m] = own[order]; n[q] = m
+    return sc, ids, n
+
+
 def _one_gpu_worker(rank, world, port, n_total, k, out_dir, pipeline, fused):
     """Two ranks on ONE device (gloo process group; the peer buffers are mapped with CUDA IPC within the device): the
     K4p exchange kernel of each rank really waits for the other process's push.  Kernels of the two processes are
@@ -126,6 +140,13 @@ def _one_gpu_worker(rank, world, port, n_total, k, out_dir, pipeline, fused):
     ids, sc, n = peer.search(qs[:5], k, allow=allow, mode="exact")
     torch.cuda.synchronize()
     out["filtered"] = (ids.cpu().numpy(), sc.cpu().numpy(), n.cpu().numpy())
+    # the exchange on crafted ORDERED lists: ties across ranks (broken by id), NaN tails, signed zeros, infinities, short
+    # and empty lists -- the merge works on integer order keys and must hand back every score's own bits
+    c_sc, c_ids, c_n = _crafted_lists(rank, world)
+    m_ids, m_sc, m_n = peer.peer.exchange_merge(torch.from_numpy(c_ids).cuda(), torch.from_numpy(c_sc).cuda(),
+                                                torch.from_numpy(c_n).cuda(), c_sc.shape[1])
+    torch.cuda.synchronize()
+    out["crafted"] = (m_ids.cpu().numpy(), m_sc.cpu().numpy(), m_n.cpu().numpy())
     dist.barrier()
     peer.close()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **{f"{k_}_{part}": v[i] for k_, v in out.items()
@@ -135,8 +156,8 @@ def _one_gpu_worker(rank, world, port, n_total, k, out_dir, pipeline, fused):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("pipeline,fused", [(0, 1), (0, 0), (1, 1)])
-def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path, pipeline, fused):
+@pytest.mark.parametrize("pipeline,fused,world", [(0, 1, 2), (0, 0, 2), (1, 1, 2), (0, 1, 3)])
+def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path, pipeline, fused, world):
     """The multi-rank exchange on a ONE-GPU box: 2 processes share cuda:0, each owns half of the rows, and every
     merged result must carry the bits of the unsharded scan (exact lanes) or reach recall 0.999 against it (bf16 lanes)
     and be identical on both ranks.  pipeline=1: the chunked form of the step (finalize + exchange of chunk c on a side
@@ -145,16 +166,18 @@ def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path, pipeline, fus
     launch behind the lane (CADENCE_PEER_FUSED=0)."""
     import torch.multiprocessing as mp
     sys.path.insert(0, ROOT)
-    n_total, k, world = 60_001, 50, 2
+    n_total, k = 60_001, 50
     mp.spawn(_one_gpu_worker, args=(world, _free_port(), n_total, k, str(tmp_path), pipeline, fused), nprocs=world, join=True)
     from cadence_rag_b200.store import DenseStore, SYNTH_QUERY_SEED, synth_rows_device
     whole = DenseStore("chunks", n_total, dim=1024, device=0)
     whole.append_synthetic(n_total)
     whole.finalize()
     qs = synth_rows_device(SYNTH_QUERY_SEED, 0, 70, 1024, device=0)
-    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
-    for key in r0.files:
-        assert np.array_equal(r0[key], r1[key]), key                       # every rank holds the identical result
+    r0 = np.load(tmp_path / "rank0.npz")
+    for r in range(1, world):
+        rr = np.load(tmp_path / f"rank{r}.npz")
+        for key in r0.files:
+            assert np.array_equal(r0[key], rr[key], equal_nan=rr[key].dtype.kind == "f"), key    # every rank holds the identical result
     for name, nq_i, kk in (("exact", 70, k), ("one", 1, k), ("k10", 64, 10), ("shared", 40, k), ("k60", 5, 60)):
         w_ids, w_sc, w_n = whole.search_exact(qs[:nq_i], kk)
         torch.cuda.synchronize()
@@ -171,6 +194,16 @@ def test_two_ranks_on_one_gpu_peer_exchange_equals_whole(tmp_path, pipeline, fus
     assert cnt_allowed == 400 and np.array_equal(r0["filtered_ids"], f_ids.cpu().numpy())
     assert np.array_equal(r0["filtered_sc"].view(np.uint64), f_sc.cpu().numpy().view(np.uint64))
     whole.close()
+    from oracle import ports
+    parts = [_crafted_lists(r, world) for r in range(world)]
+    kk = parts[0][0].shape[1]
+    want = ports.merge_topk(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), np.stack([p[2] for p in parts]), kk)
+    for q, (w_ids, w_sc) in enumerate(want):
+        m = len(w_ids)
+        assert int(r0["crafted_n"][q]) == m, q
+        assert r0["crafted_ids"][q, :m].tolist() == w_ids, q
+        assert np.array_equal(r0["crafted_sc"][q, :m].view(np.uint64), np.array(w_sc, dtype=np.float64).view(np.uint64)), q
+        assert (r0["crafted_ids"][q, m:] == -1).all()
 
 
 # ----------------------------------------------------------------------------------------- sharded hybrid /retrieve
