@@ -1150,8 +1150,10 @@ constexpr int kFinCluster = 8;
 #define CDR_FIN_STAMP(i) do { } while (0)
 #endif
 
-template <int NPL, bool PEER = false>
-__global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256)
+// U: 16-byte vectors of a row per lane (dim <= 128 U); the U = 8 instantiation (dim <= 1024) fits beside a scan CTA (36 K of
+// the SM's 64 K registers), so the programmatically launched finalize is resident and through its prologue while the scan runs.
+template <int NPL, bool PEER = false, int U = 16>
+__global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256) __maxnreg__(U == 8 ? 112 : 255)
     scan_finalize_cluster_kernel(const FinalizeParams p)
 {
     namespace cg = cooperative_groups;
@@ -1181,7 +1183,7 @@ __global__ void __cluster_dims__(kFinCluster, 1, 1) __launch_bounds__(256)
     // ready before the dependency wait.
     const float *qrow = p.queries + (size_t)qi * p.dim;
     const int nvec = p.dim >> 2;
-    constexpr int kMaxU = 16;                      // dim <= 2048
+    constexpr int kMaxU = U;                       // dim <= 128 U
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 a[kMaxU];
 #pragma unroll
@@ -1439,7 +1441,9 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
             return CDR_ERR_UNSUPPORTED;
         }
         if (nq <= 16 && !no_cluster) {
-            if (kc == 64) launch_fin(scan_finalize_cluster_kernel<2, true>, nq * kFinCluster, 256, st, pdl, fp);
+            if (kc == 64 && fp.dim <= 1024) launch_fin(scan_finalize_cluster_kernel<2, true, 8>, nq * kFinCluster, 256, st, pdl, fp);
+            else if (kc == 64) launch_fin(scan_finalize_cluster_kernel<2, true>, nq * kFinCluster, 256, st, pdl, fp);
+            else if (fp.dim <= 1024) launch_fin(scan_finalize_cluster_kernel<4, true, 8>, nq * kFinCluster, 256, st, pdl, fp);
             else launch_fin(scan_finalize_cluster_kernel<4, true>, nq * kFinCluster, 256, st, pdl, fp);
         } else {
             if (kc == 64) launch_fin(scan_finalize_kernel<2, 32, 2, true>, nq, 1024, st, pdl, fp);
@@ -1449,7 +1453,9 @@ static int launch_finalize(const FinalizeParams &fp, int kc, int nq, cudaStream_
         return CDR_OK;
     }
     if (fp.counts == nullptr && fp.q_index == nullptr && nq <= 16 && !no_cluster && (kc == 64 || kc == 128 || kc == 256)) {
-        if (kc == 64) launch_fin(scan_finalize_cluster_kernel<2>, nq * kFinCluster, 256, st, pdl, fp);
+        if (kc == 64 && fp.dim <= 1024) launch_fin(scan_finalize_cluster_kernel<2, false, 8>, nq * kFinCluster, 256, st, pdl, fp);
+        else if (kc == 64) launch_fin(scan_finalize_cluster_kernel<2>, nq * kFinCluster, 256, st, pdl, fp);
+        else if (kc == 128 && fp.dim <= 1024) launch_fin(scan_finalize_cluster_kernel<4, false, 8>, nq * kFinCluster, 256, st, pdl, fp);
         else if (kc == 128) launch_fin(scan_finalize_cluster_kernel<4>, nq * kFinCluster, 256, st, pdl, fp);
         else launch_fin(scan_finalize_cluster_kernel<8>, nq * kFinCluster, 256, st, pdl, fp);
         CDR_LAUNCH_CHECK();
