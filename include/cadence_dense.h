@@ -250,7 +250,10 @@ int32_t cdr_peer_exchange_merge(cdr_peer_group *g, const double *scores_dev, con
  * keeps the GPU from idling between them while the host returns to Python and calls again.
  * lane: CDR_DENSE_LANE_EXACT_F32 (one scan per query), CDR_DENSE_LANE_EXACT_F32_SHARED (shared reads for a batch),
  * CDR_DENSE_LANE_SCAN_BF16 or CDR_DENSE_LANE_BATCH_BF16.  g == NULL (one rank): the lane alone.  Same arguments,
- * results and ordering as the lane's own entry point followed by cdr_peer_exchange_merge; k <= the group's max_k. */
+ * results and ordering as the lane's own entry point followed by cdr_peer_exchange_merge; k <= the group's max_k.
+ * For the three scan lanes (<= 8 ranks, k <= 56 on fp32 rows / k <= 64 on bf16 rows) the exchange runs INSIDE the lane's
+ * finalize kernel -- the CTA that ordered a query's list pushes it to the peers, waits for theirs and merges -- so there
+ * is no separate exchange launch and no local list round trip; other shapes enqueue the K4p kernel behind the lane. */
 #define CDR_DENSE_LANE_EXACT_F32_SHARED 3
 int32_t cdr_search_sharded(cdr_store *s, cdr_peer_group *g, int32_t lane, const float *q_dev, int32_t nq, int32_t k,
                            const uint32_t *allow_dev, double *out_score_dev, int64_t *out_id_dev,
