@@ -653,11 +653,12 @@ def record_exact_f32(args, ctx, keep_store=False):
         achieved = float(count) * DIM * 4 * Q * args.steps / (k_ms_max / 1e3) / 1e9 if k_ms_max > 0 else None
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tpath) and world == 1:
+        if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("dram_bytes_per_row"):
                 traffic = tj["dram_bytes_per_row"] * count * Q
-                traffic_src = "committed ncu --set full capture of this kernel (profiles/k1_traffic.json: DRAM bytes per row), scaled to this launch"
+                traffic_src = ("committed ncu --set full capture of this kernel (profiles/k1_traffic.json: DRAM bytes per row), scaled to this launch"
+                               + ("" if world == 1 else "; per GPU: the same kernel over this rank's shard (the capture is a 1-GPU one)"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
