@@ -31,9 +31,10 @@ class Settings:
     # this engine
     cadence_gpu_device: int = 0
     # mode "ann" is served by the batched bf16 tensor-core lane when at least this many queries are in flight (and
-    # the lane is the faster one for the table); smaller batches use an HBM-bound scan.  4: from four unscoped requests
-    # on, one pass of the tensor-core lane (0.56 ms over 1 M rows) beats two shared passes of the fp32 scan (1.17 ms)
-    cadence_gpu_ann_min_batch: int = 4
+    # the lane is the faster one for the table); smaller batches use an HBM-bound scan.  3: over 1 M rows one request scans
+    # the bf16 rows in 0.30 ms, two share one such pass (0.39 ms), and from three on one step of the tensor-core lane
+    # (0.44 ms for any batch up to 64) beats a pair plus a single pass (0.65 ms) -- profiles/r02/bf16_share_probe.jsonl
+    cadence_gpu_ann_min_batch: int = 3
     # 1: single requests whose planner mode is "ann" scan the bf16 copy of the rows (half the bytes,
     # candidate lists twice as wide, exact re-score: recall ~1.0) instead of the fp32 rows; 0: always the exact scan
     cadence_gpu_ann_bf16_scan: int = 1

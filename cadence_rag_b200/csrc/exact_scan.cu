@@ -122,7 +122,7 @@ template <int J, int RPW, int NPL, int QPC, bool BF = false>
 struct ScanSmem {
     static constexpr int DIM = J * 128;
     static constexpr size_t kRowBytes = (size_t)DIM * (BF ? 2 : 4);
-    static constexpr bool kDeep = QPC > kSharedQPC;
+    static constexpr bool kDeep = !BF && QPC > kSharedQPC;              // (bf16-row passes shared by 2 or 4 queries keep them in registers)
     static constexpr int CW = kDeep ? kDeepWarps : kConsumerWarps;              // consumer warps
     static constexpr int QW = kDeep ? QPC / kDeepQSplit : QPC;                   // queries a warp keeps top-k lists for
     static constexpr int TR = kDeep ? RPW * CW / kDeepQSplit : RPW * CW;
@@ -497,40 +497,45 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 }
             }
         } else if constexpr (BF) {
-            // ---- candidate pass over the bf16 rows (single-query "ann" lane): a lane takes 8 consecutive elements
-            // per 16-byte step, widens them with a shift / mask and accumulates in fp32 against the fp32 query.
-            // The rows are stored normalised, so the score is dot / |q|; survivors are re-scored exactly (fp64 on
-            // the fp32 rows) by the finalize kernel.
-            static_assert(QPC == 1 && J % 2 == 0, "bf16 scan: one query per CTA, dim a multiple of 256");
+            // ---- candidate pass over the bf16 rows (the "ann" scan lane): a lane takes 8 consecutive elements
+            // per 16-byte step and accumulates in fp32 against the query.  The rows are stored normalised, so the
+            // score is dot / |q|; survivors are re-scored exactly (fp64 on the fp32 rows) by the finalize kernel.
+            // QPC == 1: one query per pass, 4 rows per warp.  QPC x RPW == 8 (built: 2 x 4): the queries of a batch
+            // share passes over the rows -- every 16-byte shared-memory load feeds QPC queries.
+            static_assert(J % 2 == 0, "bf16 scan: dim a multiple of 256");
+            static_assert(QPC == 1 || QPC * RPW == 8, "bf16 scan: shared passes reduce 8 dot products together");
+            static_assert(QPC == 1 || CDR_BF16_FHFMA, "bf16 scan: shared passes use the mixed-precision FMA form");
             constexpr int JB = J / 2;
-            float4 qa[JB], qb[JB];
-            float qn = 0.f;
-            const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)qsrc0 * DIM);
+            float inv_q[QPC];
+            uint32_t qh[QPC][JB][4];
+            float4 qa[QPC == 1 ? JB : 1], qb[QPC == 1 ? JB : 1];       // fp32 query of the widening form (A/B build)
+            (void)qa; (void)qb;
+            WarpTopK<NPL> top[QPC];
 #pragma unroll
-            for (int j = 0; j < JB; ++j) {
-                qa[j] = __ldg(&qv[(j * 32 + lane) * 2]);
-                qb[j] = __ldg(&qv[(j * 32 + lane) * 2 + 1]);
-                qn = fmaf(qa[j].x, qa[j].x, qn); qn = fmaf(qa[j].y, qa[j].y, qn);
-                qn = fmaf(qa[j].z, qa[j].z, qn); qn = fmaf(qa[j].w, qa[j].w, qn);
-                qn = fmaf(qb[j].x, qb[j].x, qn); qn = fmaf(qb[j].y, qb[j].y, qn);
-                qn = fmaf(qb[j].z, qb[j].z, qn); qn = fmaf(qb[j].w, qb[j].w, qn);
-            }
-            qn = warp_sum_f32(qn);
-            const float inv_q = __fdiv_rn(1.0f, __fsqrt_rn(qn));
-#if CDR_BF16_FHFMA
-            // The query as bf16 pairs (RN-even, like the tensor-core lane's): a row element and its query element then
-            // meet in ONE mixed-precision FMA (fma.rn.f32.bf16, SASS FHFMA.BF16 with .H0/.H1 operand selectors, fp32
-            // accumulate) -- 8 instructions per 16-byte shared-memory load instead of 8 shift/mask + 8 FFMA, which left
-            // this scan issue-bound at 5.9-6.7 TB/s.  Candidate scores only: the survivors are re-scored in fp64.
-            uint32_t qh[JB][4];
+            for (int u = 0; u < QPC; ++u) {
+                float qn = 0.f;
+                // a missing query of the last group re-reads the group's first query; its results are never written
+                const float4 *qv = reinterpret_cast<const float4 *>(p.queries + (size_t)(qsrc0 + (u < nqv ? u : 0)) * DIM);
 #pragma unroll
-            for (int j = 0; j < JB; ++j) {
-                qh[j][0] = pack_bf16x2(qa[j].x, qa[j].y); qh[j][1] = pack_bf16x2(qa[j].z, qa[j].w);
-                qh[j][2] = pack_bf16x2(qb[j].x, qb[j].y); qh[j][3] = pack_bf16x2(qb[j].z, qb[j].w);
+                for (int j = 0; j < JB; ++j) {
+                    const float4 xa = __ldg(&qv[(j * 32 + lane) * 2]);
+                    const float4 xb = __ldg(&qv[(j * 32 + lane) * 2 + 1]);
+                    qn = fmaf(xa.x, xa.x, qn); qn = fmaf(xa.y, xa.y, qn);
+                    qn = fmaf(xa.z, xa.z, qn); qn = fmaf(xa.w, xa.w, qn);
+                    qn = fmaf(xb.x, xb.x, qn); qn = fmaf(xb.y, xb.y, qn);
+                    qn = fmaf(xb.z, xb.z, qn); qn = fmaf(xb.w, xb.w, qn);
+                    // The query as bf16 pairs (RN-even, like the tensor-core lane's): a row element and its query element
+                    // then meet in ONE mixed-precision FMA (fma.rn.f32.bf16, SASS FHFMA.BF16 with .H0/.H1 operand
+                    // selectors, fp32 accumulate) -- 8 instructions per 16-byte shared-memory load instead of 8 shift/mask +
+                    // 8 FFMA, which left this scan issue-bound at 5.9-6.7 TB/s.  Candidate scores only.
+                    qh[u][j][0] = pack_bf16x2(xa.x, xa.y); qh[u][j][1] = pack_bf16x2(xa.z, xa.w);
+                    qh[u][j][2] = pack_bf16x2(xb.x, xb.y); qh[u][j][3] = pack_bf16x2(xb.z, xb.w);
+                    if constexpr (QPC == 1) { qa[j] = xa; qb[j] = xb; }
+                }
+                qn = warp_sum_f32(qn);
+                inv_q[u] = __fdiv_rn(1.0f, __fsqrt_rn(qn));
+                top[u].init(lists + (warp * QPC + u) * KC, lane);
             }
-#endif
-            WarpTopK<NPL> top;
-            top.init(lists + warp * KC, lane);
             for (;; ++it) {
                 const int s = (int)(it % (uint32_t)S);
                 const uint32_t ph = (it / (uint32_t)S) & 1u;
@@ -559,23 +564,28 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                 }
                 const uint4 *tv = reinterpret_cast<const uint4 *>(tiles + (size_t)s * L::kTileBytes) +
                                   (size_t)(warp * RPW) * (DIM / 8) + lane;
-                float acc[RPW][2];
+                float acc[QPC][RPW][2];
 #pragma unroll
-                for (int r = 0; r < RPW; ++r) acc[r][0] = acc[r][1] = 0.f;
+                for (int u = 0; u < QPC; ++u)
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) acc[u][r][0] = acc[u][r][1] = 0.f;
 #pragma unroll
                 for (int j = 0; j < JB; ++j) {
 #pragma unroll
                     for (int r = 0; r < RPW; ++r) {
                         const uint4 v = tv[r * (DIM / 8) + j * 32];
-                        float a = acc[r][j & 1];
 #if CDR_BF16_FHFMA
-                        a = fhfma_bf16x2(v.x, qh[j][0], a);
-                        a = fhfma_bf16x2(v.y, qh[j][1], a);
-                        a = fhfma_bf16x2(v.z, qh[j][2], a);
-                        a = fhfma_bf16x2(v.w, qh[j][3], a);
-                        acc[r][j & 1] = a;
-                        continue;
-#endif
+#pragma unroll
+                        for (int u = 0; u < QPC; ++u) {
+                            float a = acc[u][r][j & 1];
+                            a = fhfma_bf16x2(v.x, qh[u][j][0], a);
+                            a = fhfma_bf16x2(v.y, qh[u][j][1], a);
+                            a = fhfma_bf16x2(v.z, qh[u][j][2], a);
+                            a = fhfma_bf16x2(v.w, qh[u][j][3], a);
+                            acc[u][r][j & 1] = a;
+                        }
+#else
+                        float a = acc[0][r][j & 1];
                         a = fmaf(__uint_as_float(v.x << 16), qa[j].x, a);
                         a = fmaf(__uint_as_float(v.x & 0xFFFF0000u), qa[j].y, a);
                         a = fmaf(__uint_as_float(v.y << 16), qa[j].z, a);
@@ -584,19 +594,61 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                         a = fmaf(__uint_as_float(v.z & 0xFFFF0000u), qb[j].y, a);
                         a = fmaf(__uint_as_float(v.w << 16), qb[j].z, a);
                         a = fmaf(__uint_as_float(v.w & 0xFFFF0000u), qb[j].w, a);
-                        acc[r][j & 1] = a;
+                        acc[0][r][j & 1] = a;
+#endif
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
-                if constexpr (RPW == 4) {
+                if constexpr (QPC > 1) {
+                    // QPC x RPW = 8 dot products reduced TOGETHER, exactly as in the fp32 shared-read path below: after
+                    // the exchanges at offsets 16, 8, 4 the four lanes of group g = lane / 4 own value g = u * RPW + r
+                    // (same additions per value as the plain butterfly => the bits of a one-query pass)
+                    float a8[8];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) a8[v] = acc[v / RPW][v % RPW][0] + acc[v / RPW][v % RPW][1];
+                    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+                    float h4[4], h2[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        h4[i] = (b4 ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a8[i] : a8[i + 4], 16);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        h2[i] = (b3 ? h4[i + 2] : h4[i]) + __shfl_xor_sync(0xffffffffu, b3 ? h4[i] : h4[i + 2], 8);
+                    float dot = (b2 ? h2[1] : h2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? h2[0] : h2[1], 4);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                    const int v = (lane >> 2) & 7;
+                    const int vu = v / RPW, vr = v % RPW;
+                    float s_inv_q = inv_q[0];
+                    uint64_t s_tau = top[0].tau;
+                    int64_t s_row = gather ? (int64_t)g_row[0] : row0;
+#pragma unroll
+                    for (int r = 1; r < RPW; ++r)
+                        if (vr == r) s_row = gather ? (int64_t)g_row[r] : row0 + r;
+#pragma unroll
+                    for (int u = 1; u < QPC; ++u)
+                        if (vu == u) { s_inv_q = inv_q[u]; s_tau = top[u].tau; }
+                    const bool s_ok = (s_row < p.n_rows) && ((allow_bits >> vr) & 1u);
+                    const uint64_t key = cdr_pack_key(dot * s_inv_q, (uint32_t)s_row);
+                    unsigned pend = __ballot_sync(0xffffffffu, s_ok && key > s_tau) & 0x11111111u;
+                    while (pend) {                             // rare; warp-uniform
+                        const int src = __ffs(pend) - 1;
+                        pend &= pend - 1;
+                        const uint64_t k1 = __shfl_sync(0xffffffffu, key, src);
+                        const int su = (src >> 2) / RPW;
+#pragma unroll
+                        for (int u = 0; u < QPC; ++u)
+                            if (su == u && k1 > top[u].tau) top[u].push(k1, lane);   // re-tested: an earlier insert may have raised tau
+                    }
+                } else if constexpr (RPW == 4) {
                     // the 4 dot products of the warp are reduced TOGETHER (as in the shared-read path): at offsets 16 and
                     // 8 a lane keeps half of its values and hands the rest to its partner, so the eight lanes of group
                     // g = lane / 8 end up owning value g -- 6 shuffles instead of 20; the group then packs and tests its
                     // candidate in parallel and the rare survivors are inserted one by one
                     float a4[4];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) a4[r] = acc[r][0] + acc[r][1];
+                    for (int r = 0; r < 4; ++r) a4[r] = acc[0][r][0] + acc[0][r][1];
                     const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
                     float h2[2];
 #pragma unroll
@@ -612,23 +664,23 @@ __global__ void __launch_bounds__((ScanSmem<J, RPW, NPL, QPC, BF>::CW + 1) * 32,
                     for (int r = 1; r < 4; ++r)
                         if (vr == r) s_row = gather ? (int64_t)g_row[r] : row0 + r;
                     const bool s_ok = (s_row < p.n_rows) && ((allow_bits >> vr) & 1u);
-                    const uint64_t key = cdr_pack_key(dot * inv_q, (uint32_t)s_row);
-                    unsigned pend = __ballot_sync(0xffffffffu, s_ok && key > top.tau) & 0x01010101u;
+                    const uint64_t key = cdr_pack_key(dot * inv_q[0], (uint32_t)s_row);
+                    unsigned pend = __ballot_sync(0xffffffffu, s_ok && key > top[0].tau) & 0x01010101u;
                     while (pend) {                             // rare; warp-uniform
                         const int src = __ffs(pend) - 1;
                         pend &= pend - 1;
                         const uint64_t k1 = __shfl_sync(0xffffffffu, key, src);
-                        if (k1 > top.tau) top.push(k1, lane);  // re-tested: an earlier insert may have raised tau
+                        if (k1 > top[0].tau) top[0].push(k1, lane);  // re-tested: an earlier insert may have raised tau
                     }
                 } else {
 #pragma unroll
                 for (int r = 0; r < RPW; ++r) {
                     const int64_t row = gather ? (int64_t)g_row[r] : row0 + r;
                     const bool ok = (row < p.n_rows) && ((allow_bits >> r) & 1u);
-                    const float dot = warp_sum_f32(acc[r][0] + acc[r][1]);
+                    const float dot = warp_sum_f32(acc[0][r][0] + acc[0][r][1]);
                     if (ok) {
-                        const uint64_t key = cdr_pack_key(dot * inv_q, (uint32_t)row);
-                        if (key > top.tau) top.push(key, lane);
+                        const uint64_t key = cdr_pack_key(dot * inv_q[0], (uint32_t)row);
+                        if (key > top[0].tau) top[0].push(key, lane);
                     }
                 }
                 }
@@ -1738,13 +1790,21 @@ int cdr_exact_scan_redo_launch(cdr_store *s, ScanWorkspace &ws, const float *q_d
     return launch_scan_dim<2>(s, ws, q_dev, n_slots, allow, k, out_score, out_id, out_n, st, kScanSingle, q_index, q_count);
 }
 
-// Single-query "ann" lane: the same scan over the bf16 copy of the rows (half the bytes), candidate lists twice as wide
-// as the exact lane's (KC = 128 for k <= 120, else 256), exact fp64 re-score of the survivors.  One scan per query.
+// The "ann" scan lane: the same scan over the bf16 copy of the rows (half the bytes), candidate lists twice as wide
+// as the exact lane's (KC = 128 for k <= 120, else 256), exact fp64 re-score of the survivors.  One query: one pass.  A
+// batch: its queries SHARE passes in pairs (every 16-byte shared-memory load feeds two queries, the 2 x 4 dot products
+// of a warp are reduced together): 0.39 ms per pair over 1 M rows against 0.30 ms for one query; four queries per pass
+// with 2 rows per warp turned issue-bound (0.79 ms) and is not built (profiles/r02/bf16_share_probe.jsonl).
+// CADENCE_BF16_SHARE=0: no sharing (A/B aid).  Same per-(row, query) arithmetic and reduction => the same bits.
 int cdr_bf16_scan_launch(cdr_store *s, ScanWorkspace &ws, const float *q_dev, int nq, const uint32_t *allow, int k,
                          double *out_score, int64_t *out_id, int32_t *out_n, cudaStream_t st, const int *q_index,
                          const int *q_count, const PeerLink *peer)
 {
+    static const int share_env = [] { const char *e = getenv("CADENCE_BF16_SHARE"); return e ? atoi(e) : -1; }();
+    int share = 1;
+    if (q_index == nullptr && nq >= 2 && k <= 120 && CDR_BF16_FHFMA) share = share_env == 0 ? 1 : 2;
 #define CDR_BF_CASE(J_)                                                                                          \
+    if (share == 2) return launch_scan_t<J_, 4, 4, 2, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, nullptr, nullptr, nullptr, peer); \
     if (k <= 120) return launch_scan_t<J_, 4, 4, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, nullptr, peer); \
     return launch_scan_t<J_, 4, 8, 1, true>(s, ws, q_dev, nq, allow, k, out_score, out_id, out_n, st, q_index, q_count, nullptr, peer)
     switch (s->dim) {

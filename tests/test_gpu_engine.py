@@ -1435,7 +1435,7 @@ def test_fused_call_ann_groups_take_the_tensor_core_lane(monkeypatch):
             assert got["retrieved_ids"] == retrieve.retrieve_ids(eng, t, f, debug=True)["retrieved_ids"]
         # fewer than cadence_gpu_ann_min_batch requests: exact lane
         seen.clear()
-        retrieve.retrieve_ids_batch(eng, texts[:3], None)
+        retrieve.retrieve_ids_batch(eng, texts[:2], None)
         assert not (seen[-1][0] or {}).get("dense_lane")
         monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 16)
         retrieve.retrieve_ids_batch(eng, texts[:8], None)
@@ -1510,7 +1510,33 @@ def test_bf16_scan_lane(corpus_100k, monkeypatch):
     from cadence_rag_b200 import _ffi
     monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
     assert retrieve._group_dense_lane(s, None, None, 1) == _ffi.CDR_DENSE_LANE_SCAN_BF16
+    assert retrieve._group_dense_lane(s, None, None, 2) == _ffi.CDR_DENSE_LANE_SCAN_BF16      # shared passes over the bf16 rows
+    assert retrieve._group_dense_lane(s, None, None, 3) == _ffi.CDR_DENSE_LANE_SCAN_BF16
     assert retrieve._group_dense_lane(s, None, None, 5) == _ffi.CDR_DENSE_LANE_EXACT_F32
     assert retrieve._group_dense_lane(s, RetrieveFilters(call_ids=[1]), [1], 1) == _ffi.CDR_DENSE_LANE_EXACT_F32
     monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 0)
     assert retrieve._group_dense_lane(s, None, None, 1) == _ffi.CDR_DENSE_LANE_EXACT_F32
+
+
+def test_bf16_scan_shared_passes_same_bits(corpus_100k):
+    """Batches on the bf16-row scan lane share passes over the rows (two queries per pass with 4 rows per warp, four with
+    2 rows per warp): every per-(row, query) sum is formed by the same additions as in a one-query pass, so ids, score
+    bits and counts must equal the one-query calls -- unfiltered, under a wide filter (bitmap path), under a narrow
+    one (gather launch), for ragged batch sizes, and k above the shared forms' limit (no sharing)."""
+    s, x = corpus_100k
+    if not s.has_bf16:
+        pytest.skip("fixture store keeps no bf16 rows")
+    qs = torch.from_numpy(orc.synth_rows(SYNTH_QUERY_SEED, 1200, 9)).cuda()
+    wide, _ = s.filter_bitmap(call_slots=list(range(0, 500, 3)))
+    narrow, _ = s.filter_bitmap(call_slots=[3, 44, 45])
+    for k in (50, 100, 150):
+        for al in (None, wide, narrow):
+            ones = [s.search_scan_bf16(qs[i:i + 1], k, al) for i in range(9)]
+            torch.cuda.synchronize()
+            for n in (2, 3, 4, 5, 9):
+                ids, sc, cnt = s.search_scan_bf16(qs[:n], k, al)
+                torch.cuda.synchronize()
+                for i in range(n):
+                    assert torch.equal(ids[i], ones[i][0][0]), (k, n, i)
+                    assert torch.equal(sc[i].view(torch.int64), ones[i][1][0].view(torch.int64)), (k, n, i)
+                    assert int(cnt[i]) == int(ones[i][2][0])

@@ -385,7 +385,7 @@ def test_batch_lane_choice_inside_mode_ann():
 def test_dense_lane_of_a_request_group(monkeypatch):
     """Which kernel serves a group's dense lane inside the fused call (retrieve._group_dense_lane): scoped groups
     always the exact scan (their mode depends on COUNT(*)); unscoped ones plan "ann" -- one request scans the bf16
-    rows, two or three share one fp32 scan, >= cadence_gpu_ann_min_batch take the tensor-core lane when it is the
+    rows, fewer than cadence_gpu_ann_min_batch share passes over the bf16 rows, >= that many take the tensor-core lane when it is the
     faster one; stores without bf16 rows, other widths and the switches fall back to the exact scan."""
     from cadence_rag_b200 import _ffi
     from cadence_rag_b200.retrieve import RetrieveFilters, _group_dense_lane
@@ -405,7 +405,7 @@ def test_dense_lane_of_a_request_group(monkeypatch):
 
     monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 4)
     monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
-    assert [_group_dense_lane(_Big, None, None, n) for n in (1, 2, 3, 4, 64)] == [SCAN, EXACT, EXACT, BATCH, BATCH]
+    assert [_group_dense_lane(_Big, None, None, n) for n in (1, 2, 3, 4, 64)] == [SCAN, SCAN, SCAN, BATCH, BATCH]
     assert _group_dense_lane(_Big, RetrieveFilters(), None, 1) == SCAN             # an empty filter object scopes nothing
     scoped = RetrieveFilters(call_ids=["c1"])
     assert [_group_dense_lane(_Big, scoped, ["c1"], n) for n in (1, 64)] == [EXACT, EXACT]
