@@ -344,9 +344,9 @@ def fetch_dense_batch(conn: DenseConnection, table_name: str, queries, filters, 
     if mode == "ann" and store.has_bf16 and (nq >= settings.cadence_gpu_ann_min_batch or not store.has_fp32):
         if not store.has_fp32 or _batch_lane_is_faster(store, nq, count):
             return store.search_batch(queries, limit, allow)
-    if (mode == "ann" and store.has_bf16 and nq < settings.cadence_gpu_ann_min_batch and int(settings.cadence_gpu_ann_bf16_scan)
+    if (mode == "ann" and store.has_bf16 and nq <= 8 and int(settings.cadence_gpu_ann_bf16_scan)
             and not _dense_has_scoping(filters, call_ids) and store.dim in (256, 512, 768, 1024)):
-        return store.search_scan_bf16(queries, limit, allow)          # 2-3 unscoped queries share one pass over the bf16 rows
+        return store.search_scan_bf16(queries, limit, allow)          # a few unscoped queries share passes over the bf16 rows
     return store.search_exact(queries, limit, allow, shared=True)
 
 
@@ -521,16 +521,17 @@ def _group_dense_lane(store: DenseStore, filters, call_ids, n_requests: int) -> 
     Scoped groups stay on the exact scan: their mode depends on COUNT(*), which is computed inside the same call."""
     if not store.has_bf16 or _dense_has_scoping(filters, call_ids):
         return _ffi.CDR_DENSE_LANE_EXACT_F32
+    # Without the tensor-core lane: one request scans the bf16 rows (0.30 ms per 1 M rows; the fp32 rows 0.58 ms), a few
+    # share passes over the bf16 rows in pairs (two 0.39 ms, eight 1.05 ms; the shared fp32 scan 0.62 / 1.36 ms); from
+    # about sixteen on the register-tiled fp32 scan (16 queries per pass) is the faster one (profiles/r02/README.md 10)
+    scan = (_ffi.CDR_DENSE_LANE_SCAN_BF16
+            if int(settings.cadence_gpu_ann_bf16_scan) and store.dim in (256, 512, 768, 1024) and n_requests <= 8
+            else _ffi.CDR_DENSE_LANE_EXACT_F32)
     if n_requests < max(2, int(settings.cadence_gpu_ann_min_batch)):
-        # one request: a scan of the bf16 rows (0.32 ms per 1 M rows) beats a scan of the fp32 rows (0.58 ms); two or
-        # three SHARE one pass over the bf16 rows (every streamed tile is scored against 2 / 4 queries), which beats
-        # the shared fp32 scan (0.63 ms) they took before
-        if int(settings.cadence_gpu_ann_bf16_scan) and store.dim in (256, 512, 768, 1024):
-            return _ffi.CDR_DENSE_LANE_SCAN_BF16
-        return _ffi.CDR_DENSE_LANE_EXACT_F32
+        return scan
     if _batch_lane_is_faster(store, n_requests, store.rows):
         return _ffi.CDR_DENSE_LANE_BATCH_BF16
-    return _ffi.CDR_DENSE_LANE_EXACT_F32
+    return scan
 
 
 def _hybrid_table_batch(conn: DenseConnection, table: str, q32: Optional[np.ndarray],

@@ -1511,8 +1511,12 @@ def test_bf16_scan_lane(corpus_100k, monkeypatch):
     monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 1)
     assert retrieve._group_dense_lane(s, None, None, 1) == _ffi.CDR_DENSE_LANE_SCAN_BF16
     assert retrieve._group_dense_lane(s, None, None, 2) == _ffi.CDR_DENSE_LANE_SCAN_BF16      # shared passes over the bf16 rows
-    assert retrieve._group_dense_lane(s, None, None, 3) == _ffi.CDR_DENSE_LANE_SCAN_BF16
-    assert retrieve._group_dense_lane(s, None, None, 5) == _ffi.CDR_DENSE_LANE_EXACT_F32
+    # from cadence_gpu_ann_min_batch requests on the cost model may prefer the tensor-core lane; the scan lane never serves > 8
+    assert retrieve._group_dense_lane(s, None, None, 3) in (_ffi.CDR_DENSE_LANE_SCAN_BF16, _ffi.CDR_DENSE_LANE_BATCH_BF16)
+    assert retrieve._group_dense_lane(s, None, None, 16) in (_ffi.CDR_DENSE_LANE_EXACT_F32, _ffi.CDR_DENSE_LANE_BATCH_BF16)
+    monkeypatch.setattr(settings, "cadence_gpu_ann_min_batch", 128)
+    assert retrieve._group_dense_lane(s, None, None, 8) == _ffi.CDR_DENSE_LANE_SCAN_BF16
+    assert retrieve._group_dense_lane(s, None, None, 16) == _ffi.CDR_DENSE_LANE_EXACT_F32
     assert retrieve._group_dense_lane(s, RetrieveFilters(call_ids=[1]), [1], 1) == _ffi.CDR_DENSE_LANE_EXACT_F32
     monkeypatch.setattr(settings, "cadence_gpu_ann_bf16_scan", 0)
     assert retrieve._group_dense_lane(s, None, None, 1) == _ffi.CDR_DENSE_LANE_EXACT_F32
