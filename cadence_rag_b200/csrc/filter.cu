@@ -34,26 +34,43 @@ __global__ void __launch_bounds__(256) filter_bitmap_kernel(const FilterParams p
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = warp0; w < words; w += nwarps) {
-        const int64_t row = (w << 5) + lane;
-        bool ok = false;
-        if (row < p.n_rows) {
-            ok = (p.valid[w] >> lane) & 1u;
-            if (ok && p.call_bitmap) {
-                const int32_t slot = p.call_slot[row];
-                ok = slot >= 0 && slot < p.n_call_slots && ((p.call_bitmap[slot >> 5] >> (slot & 31)) & 1u);
-            }
-            if (ok && (p.has_from | p.has_to)) {
-                const int64_t t = p.started_at[row];
-                if (p.has_from && t < p.date_from) ok = false;
-                if (p.has_to && t > p.date_to) ok = false;
-            }
-            if (ok && p.has_tags) ok = (p.tag_bits[row] & p.tag_any) != 0ull;
+    // Four bitmap words (128 rows) per warp and trip, every column read issued before the first is used: the kernel is a
+    // short chain of dependent loads per row (validity word -> call slot -> call bitmap), so its time is load latency x
+    // trips, not bytes (12 us for 1 M rows with one word per trip against 3 us of column traffic).
+    constexpr int U = 4;
+    for (int64_t w0 = warp0 * U; w0 < words; w0 += nwarps * U) {
+        uint32_t vbits[U];
+        int32_t slot[U];
+        int64_t ts[U];
+        uint64_t tags[U];
+        bool in[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t w = w0 + j, row = (w << 5) + lane;
+            in[j] = w < words && row < p.n_rows;
+            vbits[j] = in[j] ? p.valid[w] : 0u;
+            slot[j] = (in[j] && p.call_bitmap) ? p.call_slot[row] : 0;
+            ts[j] = (in[j] && (p.has_from | p.has_to)) ? p.started_at[row] : 0;
+            tags[j] = (in[j] && p.has_tags) ? p.tag_bits[row] : 0ull;
         }
-        const unsigned bits = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) {
-            p.out_allow[w] = bits;
-            local += __popc(bits);
+        uint32_t cword[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const bool s_ok = p.call_bitmap && slot[j] >= 0 && slot[j] < p.n_call_slots;
+            cword[j] = s_ok ? p.call_bitmap[slot[j] >> 5] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            bool ok = in[j] && ((vbits[j] >> lane) & 1u);
+            if (p.call_bitmap) ok = ok && ((cword[j] >> (slot[j] & 31)) & 1u);
+            if (p.has_from) ok = ok && ts[j] >= p.date_from;
+            if (p.has_to) ok = ok && ts[j] <= p.date_to;
+            if (p.has_tags) ok = ok && (tags[j] & p.tag_any) != 0ull;
+            const unsigned bits = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0 && w0 + j < words) {
+                p.out_allow[w0 + j] = bits;
+                local += __popc(bits);
+            }
         }
     }
     // one atomic per block
