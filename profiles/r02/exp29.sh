@@ -5,19 +5,14 @@ cd $GRAFT_REPO_ROOT
 NCU=/usr/local/cuda/bin/ncu
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-(time python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_reference_v6.json 2> gpurun_out/r02_bench_reference_v6.err); echo "reference rc=$?"
-(time python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_default_v6.json 2> gpurun_out/r02_bench_default_v6.err); echo "bench rc=$?"
+(time python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_reference_v7.json 2> gpurun_out/r02_bench_reference_v7.err); echo "reference rc=$?"
+(time python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_default_v7.json 2> gpurun_out/r02_bench_default_v7.err); echo "bench rc=$?"
 python - <<'PY'
 import json
-r=json.load(open('gpurun_out/r02_bench_reference_v6.json')); d=json.load(open('gpurun_out/r02_bench_default_v6.json'))
+r=json.load(open('gpurun_out/r02_bench_reference_v7.json')); d=json.load(open('gpurun_out/r02_bench_default_v7.json'))
 print('reference', r['value'], r['ms_per_step'], r['cpu_baseline']['cores'], r['cpu_baseline']['sample'][:80])
 print('same config:', r['config'] == d['config'])
 print('b200', d['value'], d['e2e']['value'], 'ratio', d['value']/r['value'], 'e2e ratio', d['e2e']['value']/r['value'], d['roofline']['frac'], d['run'], d['clocks'])
 for k,v in d['sub_records'].items(): print(k, v.get('value'), v.get('ms_per_step'), (v.get('roofline') or {}).get('frac'), v.get('invalid'), list((v.get('parity') or {}).keys()))
 print(d['cpu_baseline'], d['cpu_baseline_hnsw'])
 PY
-python profiles/r02/k1_probe.py > gpurun_out/k1_probe_plain.log 2>&1 || { echo "plain K1 probe failed"; cat gpurun_out/k1_probe_plain.log; exit 1; }
-timeout 900 $NCU --set full --clock-control none --import-source on -k regex:"exact_scan_kernel|scan_finalize" --launch-skip 12 --launch-count 6 -f -o gpurun_out/k1_r02_final python profiles/r02/k1_probe.py > gpurun_out/ncu_k1_final.log 2>&1
-echo "ncu k1 rc=$?"
-$NCU -i gpurun_out/k1_r02_final.ncu-rep --page raw --csv > gpurun_out/k1_r02_final_raw.csv 2>/dev/null
-ls -la gpurun_out/k1_r02_final*
