@@ -183,6 +183,16 @@ def stream_ptr(stream=None) -> int:
     return int(stream.cuda_stream)
 
 
+def current_stream_ptr(device_index: int) -> int:
+    """cudaStream_t of torch's current stream on a device, without building a torch.cuda.Stream object (this sits on the
+    path of every search call, ahead of the first kernel launch)."""
+    import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return int(raw(device_index))
+    return int(torch.cuda.current_stream(device_index).cuda_stream)
+
+
 def ptr(t) -> Optional[int]:
     """data pointer of a torch tensor / numpy array, or None."""
     if t is None:

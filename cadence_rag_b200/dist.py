@@ -200,10 +200,11 @@ class ShardedSearcher:
         # one allocation for the three outputs (a single-query step is a few tens of microseconds of kernels: every
         # allocator round trip on the host shows up as GPU idle time in its latency)
         buf = torch.empty((2 * nq * k + (nq + 1) // 2,), dtype=torch.int64, device=dev)
+        base = buf.data_ptr()              # [scores f64 | ids i64 | counts i32]; the views are built after the launches
+        _ffi.check(_ffi.lib().cdr_search_sharded(self.store.handle, self.peer._h, lane, _ffi.ptr(q), nq, k, _ffi.ptr(allow),
+                                                 base, base + nq * k * 8, base + 2 * nq * k * 8,
+                                                 _ffi.current_stream_ptr(dev.index)), "cdr_search_sharded")
         out_sc = buf[:nq * k].view(torch.float64).view(nq, k)
         out_id = buf[nq * k:2 * nq * k].view(nq, k)
         out_n = buf[2 * nq * k:].view(torch.int32)[:nq]
-        _ffi.check(_ffi.lib().cdr_search_sharded(self.store.handle, self.peer._h, lane, _ffi.ptr(q), nq, k, _ffi.ptr(allow),
-                                                 _ffi.ptr(out_sc), _ffi.ptr(out_id), _ffi.ptr(out_n),
-                                                 _ffi.stream_ptr(torch.cuda.current_stream(dev))), "cdr_search_sharded")
         return out_id, out_sc, out_n

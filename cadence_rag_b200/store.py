@@ -120,8 +120,7 @@ class DenseStore:
             pass
 
     def _stream(self) -> int:
-        torch = _torch()
-        return _ffi.stream_ptr(torch.cuda.current_stream(self.device))
+        return _ffi.current_stream_ptr(self.device)
 
     # ------------------------------------------------------------------ dictionaries
     def slot_of_call(self, call_id, create: bool = False) -> Optional[int]:
@@ -538,12 +537,17 @@ class DenseStore:
             dev = q.device
             if dev.index != self.device:
                 raise DenseEngineError(f"queries live on {dev}, the store on cuda:{self.device}")
-            sc = torch.empty((nq, k), dtype=torch.float64, device=dev)
-            ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-            cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+            # One allocation for the three outputs, addressed by pointer arithmetic: the launches are enqueued before any
+            # view is built (a single-query request is a few hundred microseconds of kernels, and every host operation
+            # ahead of the first launch is GPU idle time in its latency); the views are made while the GPU works.
+            buf = torch.empty((2 * nq * k + (nq + 1) // 2,), dtype=torch.int64, device=dev)
+            base = buf.data_ptr()
             fn = getattr(_ffi.lib(), fn_name)
-            _ffi.check(fn(self.handle, _ffi.ptr(q), nq, k, _ffi.ptr(allow), _ffi.ptr(sc), _ffi.ptr(ids),
-                          _ffi.ptr(cnt), self._stream()), fn_name)
+            _ffi.check(fn(self.handle, _ffi.ptr(q), nq, k, _ffi.ptr(allow), base, base + nq * k * 8, base + 2 * nq * k * 8,
+                          self._stream()), fn_name)
+            sc = buf[:nq * k].view(torch.float64).view(nq, k)
+            ids = buf[nq * k:2 * nq * k].view(nq, k)
+            cnt = buf[2 * nq * k:].view(torch.int32)[:nq]
             return ids, sc, cnt
         sc = np.empty((nq, k), dtype=np.float64)
         ids = np.empty((nq, k), dtype=np.int64)

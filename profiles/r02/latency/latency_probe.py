@@ -6,7 +6,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, os.environ.get("PROBE_PKG_ROOT", ROOT))      # (A/B of the Python side: another copy of the package)
 import torch
 import torch.distributed as dist
 
